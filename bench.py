@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py -- genes/sec of GLM-mode testDynamic() (BASELINE.json metric) on synthetic NB counts.
+
+A "step" is one pass of the whole per-gene path (sort/gather, forward null fits + score sweeps, backward WIC
+pass, final + null glm.nb, LRT) over one batch of synthetic counts.
+
+  value  = genes/s with the counts already resident in HBM (sclane_test_dynamic_device), device-timed
+  e2e    = genes/s through the reference-facing call with HOST buffers (sclane_test_dynamic): pinned-host -> device
+           copy of the counts and device -> host copy of the records inside the timed region
+  roofline = score-sweep kernel (K2): algorithmic bytes (12 B per cell per swept gene-iteration + 8 B per cell per
+           launch) / CUDA-event time of the sweep launches, vs the measured HBM copy bandwidth
+  cpu_baseline = the numpy oracle timed on a bounded gene sample on this box's host cores
+
+Workload: BASELINE.json configs[1] (2,000 genes x 10,000 cells, one lineage, no offsets) per GPU (weak scaling:
+every rank fits its own 2,000-gene shard; genes are independent, no collective on the data path).
+`--config c5` runs the atlas-scale cell count (200,000 cells) with `--genes` genes per GPU.
+
+`--impl reference` times the reference algorithm's CPU restatement (the oracle: R is not installable here) on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "c2": {"genes": 2000, "cells": 10000, "name": "synthetic NB 2,000 genes x 10,000 cells, 1 lineage, GLM (BASELINE configs[1])"},
+    "c5": {"genes": 256, "cells": 200000, "name": "synthetic NB, 200,000 cells (BASELINE configs[4] cell count), gene subset per GPU"},
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh).get("hbm_gbs", 6546.2), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(counts, pt, n_sample: int):
+    """The oracle (kind "port") on the first n_sample genes, single process, on this box's host cores."""
+    from oracle.test_dynamic import test_dynamic as oracle_td
+    t0 = time.time()
+    oracle_td(counts[:n_sample], pt, None, None, keep_preds=False)
+    dt = time.time() - t0
+    return {"value": n_sample / dt, "unit": "genes/s", "cores": 1, "kind": "port",
+            "sample": f"{n_sample} genes x {counts.shape[1]} cells of the same synthetic workload, numpy oracle, 1 process, {dt:.1f} s"}
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; one process per core, the
+    reference's own parallel model -- one gene per worker, testDynamic.R:136-142,170-179)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ProcessPoolExecutor
+    from sclane_b200 import synth
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 2 * cores if cfg["cells"] <= 20000 else cores)
+    counts, pt, _ = synth.make_counts(per_step, cfg["cells"], seed=312)
+    chunks = [(counts[i::cores], pt) for i in range(cores)]
+    times = []
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        for it in range(args.warmup + args.steps):
+            t0 = time.time()
+            list(ex.map(_oracle_chunk, chunks))
+            if it >= args.warmup:
+                times.append(time.time() - t0)
+    ms = 1000.0 * float(np.mean(times))
+    val = per_step / (ms / 1000.0)
+    line = {"impl": "reference", "metric": "genes/sec for testDynamic GLM mode", "value": val, "unit": "genes/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "cells": cfg["cells"], "genes_per_step": per_step},
+            "cpu_baseline": {"value": val, "unit": "genes/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} genes x {cfg['cells']} cells per step, numpy oracle, {cores} processes"},
+            "e2e": {"value": val, "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def _oracle_chunk(a):
+    from oracle.test_dynamic import test_dynamic as oracle_td
+    counts, pt = a
+    oracle_td(counts, pt, None, None, keep_preds=False)
+    return counts.shape[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--genes", type=int, default=0, help="genes per GPU (default: the config's)")
+    ap.add_argument("--cpu-sample", type=int, default=24, help="genes of the CPU-baseline sample (0 = skip)")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.genes:
+        cfg["genes"] = args.genes
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sclane_b200 as sb
+    from sclane_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    G, N = cfg["genes"], cfg["cells"]
+    # every rank draws its own gene shard (weak scaling); pseudotime is shared
+    counts, pt, _ = synth.make_counts(G, N, seed=312 + 1000 * rank)
+    _, pt, _ = synth.make_counts(1, N, seed=312)
+    h_counts = torch.from_numpy(counts).pin_memory()
+    d_counts = h_counts.to(dev, non_blocking=False)
+    opts = sb.api._opts(gpu_ids=[local])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return sb.run_records(G, pt, None, opts, device_ptr=d_counts.data_ptr(), device=local)
+
+    def step_host():
+        return sb.run_records(h_counts.numpy(), pt, None, opts)
+
+    # ---- device-resident measurement (value) ---------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    sb.reset_launch_count()
+    prof_acc = None
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                                   # evict the previous step's working set from L2
+        torch.cuda.synchronize()
+        step_device()
+        p = sb.get_profile()
+        dev_ms += sum(v for k, v in p["ms"].items())
+        if prof_acc is None:
+            prof_acc = p
+        else:
+            for k in p["ms"]:
+                prof_acc["ms"][k] += p["ms"][k]
+                prof_acc["launches"][k] += p["launches"][k]
+            prof_acc["sweep_bytes"] += p["sweep_bytes"]
+            prof_acc["sweep_gene_iters"] += p["sweep_gene_iters"]
+    barrier()
+    wall_ms = 1000.0 * (time.perf_counter() - t0)
+    launches = sb.launch_count()
+    # device time per step = CUDA-event time of every stage on the library's stream (max over ranks below)
+    ms_step = dev_ms / args.steps
+    # ---- end-to-end measurement (e2e): host buffers, copies inside the timed region ----------------
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    barrier()
+    t1 = time.perf_counter()
+    h2d = d2h = 0.0
+    for _ in range(args.steps):
+        step_host()
+        p = sb.get_profile()
+        h2d += p["h2d_bytes"]
+        d2h += p["d2h_bytes"]
+    barrier()
+    e2e_ms = 1000.0 * (time.perf_counter() - t1) / args.steps
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_ms, wall_ms / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms, wall_step = (float(v) for v in t.tolist())
+    else:
+        wall_step = wall_ms / args.steps
+    total_genes = G * world
+    value = total_genes / (ms_step / 1000.0)
+    e2e_val = total_genes / (e2e_ms / 1000.0)
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        sweep_ms = prof_acc["ms"]["sweep"]
+        sweep_launches = prof_acc["launches"]["sweep"]
+        achieved = (prof_acc["sweep_bytes"] / 1e9) / (sweep_ms / 1000.0) if sweep_ms > 0 else 0.0
+        line = {
+            "metric": "genes/sec for testDynamic GLM mode", "value": value, "unit": "genes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "genes_per_gpu": G, "cells": N, "lineages": 1, "M": 5, "sharding": f"genes x{world}",
+                       "l2": "flushed between timed steps (256 MiB write); per-step working set 240 MB > L2"},
+            "e2e": {"value": e2e_val, "unit": "genes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d / args.steps,
+                    "d2h_bytes_per_step": d2h / args.steps},
+            "gpu_launches": int(launches),
+            "wall_ms_per_step": wall_step,
+            "stage_ms_per_step": {k: v / args.steps for k, v in prof_acc["ms"].items()},
+            "roofline": {"kernel": "k_stage<STAGE_SWEEP> (score sweep, K2)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind, "traffic": None,
+                         "bytes_per_launch": prof_acc["sweep_bytes"] / max(1, sweep_launches),
+                         "ms_per_launch": sweep_ms / max(1, sweep_launches)},
+            "clocks": sampler.result(),
+        }
+        if args.cpu_sample > 0:
+            line["cpu_baseline"] = cpu_baseline(counts, pt, min(args.cpu_sample, G))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

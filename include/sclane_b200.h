@@ -1,0 +1,259 @@
+/*
+ * sclane_b200.h -- C ABI of libsclane_b200.so: the B200-native engine for scLANE's
+ * per-gene trajectory-DE fitting path (testDynamic() -> marge2() -> NB fits -> LRT).
+ *
+ * Plain C: pointers + sizes, caller-owned buffers, no C++/torch types.  Every entry point
+ * names the reference interface it replaces (file:line relative to the scLANE checkout,
+ * v0.99.2).  The reference's own native boundary is `.Call("_scLANE_eigenMap*", ...)`
+ * (R/RcppExports.R:4-14, src/RcppExports.cpp:14-63); the R-side stubs a maintainer would add
+ * for the entry points below are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - return 0 = call completed; per-gene failures are DATA (status bits / NaN statistics),
+ *     mirroring try(..., silent = TRUE) + .errorhandling = "pass" (testDynamic.R:176,188-199,387-420).
+ *   - return != 0 = global failure (bad arguments, CUDA error, out of memory, no CUDA device);
+ *     a message is written to errbuf (NUL terminated).  The library never exits, never throws
+ *     across the boundary and has NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with SCLANE_ERR_CUDA.
+ *   - NA_real_ inputs are NaN (tested with isnan); NaN is emitted for NA outputs.
+ *   - all matrices of the eigenMap* drop-ins are column-major doubles, as R/Eigen::Map hand them over.
+ */
+#ifndef SCLANE_B200_H
+#define SCLANE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCLANE_ABI_VERSION 1
+#define SCLANE_PMAX 7          /* max columns of a model (intercept + hinges): M <= 7 (marge2.R:756) */
+#define SCLANE_TMAX 32         /* max candidate knots per lineage (n.knot.max, marge2.R:66; default 25) */
+#define SCLANE_MAX_GPUS 16
+
+/* error codes */
+#define SCLANE_OK 0
+#define SCLANE_ERR_ARG 1
+#define SCLANE_ERR_CUDA 2
+#define SCLANE_ERR_NOMEM 3
+#define SCLANE_ERR_UNSUPPORTED 4
+
+/* sclane_record.status bits (the four Model_Status strings of testDynamic.R:266-278) */
+#define SCLANE_MARGE_OK 1
+#define SCLANE_NULL_OK 2
+
+/* sclane_record.*_notes bits */
+#define SCLANE_NOTE_TH_ITER_LIMIT 1     /* theta.ml "iteration limit reached"           (th.warn) */
+#define SCLANE_NOTE_ALT_LIMIT 2         /* glm.nb "alternation limit reached"            (th.warn) */
+#define SCLANE_NOTE_TH_TRUNC 4          /* theta.ml "estimate truncated at zero"         (th.warn) */
+#define SCLANE_NOTE_NOT_CONVERGED 8     /* last glm.fit2 did not converge                          */
+#define SCLANE_NOTE_FWD_EMPTY 16        /* forward pass added < 2 columns -> marge2 subscript error (marge2.R:777) */
+#define SCLANE_NOTE_ALL_ZERO 32         /* all counts zero in this lineage                         */
+#define SCLANE_NOTE_NUMERIC 64          /* non-finite intermediate (R: "missing value where TRUE/FALSE needed") */
+
+/* hinge direction of a model term */
+#define SCLANE_TERM_INTERCEPT 0
+#define SCLANE_TERM_TP1 1               /* (x - t)+  "Right", name h_<Lineage>_<knot>  (tp1.R:17, marge2.R:593) */
+#define SCLANE_TERM_TP2 2               /* (t - x)+  "Left",  name h_<knot>_<Lineage>  (tp2.R:17, marge2.R:594) */
+
+/* Arguments of testDynamic() (testDynamic.R:60-75) and marge2() (marge2.R:56-72) that reach the path. */
+typedef struct sclane_opts {
+  int32_t abi_version;        /* must be SCLANE_ABI_VERSION */
+  int32_t mode;               /* 0 = GLM (is.gee = FALSE, is.glmm = FALSE).  1 = GEE: not built yet -> SCLANE_ERR_UNSUPPORTED */
+  int32_t M;                  /* n.potential.basis.fns / marge2 M, default 5, 3 <= M <= SCLANE_PMAX */
+  int32_t approx_knot;        /* approx.knot, default 1 (0 -> SCLANE_ERR_UNSUPPORTED for now) */
+  int32_t n_knot_max;         /* n.knot.max, default 25, <= SCLANE_TMAX */
+  int32_t minspan;            /* marge2 minspan; -1 = NULL (automatic, min_span.R:24-26) */
+  double  tols_score;         /* marge2 tols_score, default 1e-5 */
+  int32_t n_gpus;             /* devices to shard genes over (0 = all visible) */
+  int32_t gpu_ids[SCLANE_MAX_GPUS]; /* used when n_gpus > 0 */
+  int32_t genes_per_batch;    /* 0 = automatic (bounded by free device memory) */
+  int32_t verbose;
+  int32_t reserved[8];
+} sclane_opts;
+
+/* One record per (gene, lineage): everything testDynamic() returns for that pair except the
+ * two per-cell data.frames, which are reproduced on demand by sclane_link_preds().
+ * Field sources: testDynamic.R:320-342, pullMARGESummary.R:66-98, pullNullSummary.R:66-80,
+ * modelLRT.R:43-53, marge2.R:860-866. */
+typedef struct sclane_record {
+  int32_t status;                       /* SCLANE_MARGE_OK | SCLANE_NULL_OK */
+  int32_t marge_notes;                  /* SCLANE_NOTE_* of the alternative model */
+  int32_t null_notes;                   /* SCLANE_NOTE_* of the null model */
+  int32_t n_terms;                      /* columns of the final model incl. intercept; 0 if marge2 failed */
+  int32_t term_kind[SCLANE_PMAX];       /* SCLANE_TERM_* ; term 0 is the intercept */
+  int32_t term_knot_idx[SCLANE_PMAX];   /* index into the lineage's candidate knots; -1 for the intercept */
+  double  term_knot[SCLANE_PMAX];       /* the knot itself (what tp1/tp2 were built with, marge2.R:589-590) */
+  double  term_label[SCLANE_PMAX];      /* signif(knot, 4): the number printed in the coefficient name and parsed back
+                                           by extractBreakpoints() (marge2.R:593-594, extractBreakpoints.R:27-28) */
+  double  coef[SCLANE_PMAX];            /* MARGE_Summary$estimate  */
+  double  se[SCLANE_PMAX];              /* MARGE_Summary$std.error (dispersion 1) */
+  double  z[SCLANE_PMAX];               /* MARGE_Summary$statistic */
+  double  p[SCLANE_PMAX];               /* MARGE_Summary$p.value = 2*pnorm(-|z|) */
+  double  cov[SCLANE_PMAX * SCLANE_PMAX]; /* (X'WX)^-1 of the last IRLS solve, row-major n_terms x n_terms
+                                             (vcov() for summarizeModel.R:37-39 and se.fit of predict()) */
+  double  theta, se_theta;              /* final_mod$theta, $SE.theta */
+  double  loglik, deviance;             /* LogLik_MARGE, Dev_MARGE */
+  int32_t alternations, irls_iters;     /* glm.nb alternation count; total glm.fit2 iterations */
+  double  null_coef, null_se, null_z, null_p;   /* Null_Summary row */
+  double  null_theta, null_se_theta;
+  double  null_loglik, null_deviance;   /* LogLik_Null, Dev_Null */
+  int32_t null_alternations, null_irls_iters;
+  double  test_stat;                    /* Test_Stat  = LRT_Stat = 2 (l1 - l0) */
+  double  df;                           /* Degrees_Freedom (0 -> 1 rule, modelLRT.R:48-50) */
+  double  p_val;                        /* P_Val = pchisq(LRT, DF, lower = FALSE) */
+  /* trace of the discrete path, for parity tests and debugging */
+  int32_t fwd_n_terms;                  /* columns after the forward pass */
+  int32_t fwd_kind[SCLANE_PMAX];
+  int32_t fwd_knot_idx[SCLANE_PMAX];
+  double  fwd_score[4];                 /* score2 of each forward iteration (marge2.R:675) */
+  double  fwd_sigma[4];                 /* sigma of each forward null fit; 0 = Poisson regime */
+  double  wic[SCLANE_PMAX];             /* WIC_vec_2[-1] (marge2.R:778-797) */
+  int32_t n_wic;
+  int32_t fit_passes;                   /* passes over the cells spent on this record */
+  double  gene_time;                    /* Gene_Time surrogate: seconds of device time / genes in the batch */
+} sclane_record;
+
+/* Per-lineage description returned to the caller (knots, cell membership). */
+typedef struct sclane_lineage_info {
+  int64_t n_cells;                      /* cells with a non-NA pseudotime in this lineage (testDynamic.R:183) */
+  int32_t n_knots;
+  int32_t minspan;
+  double  knots[SCLANE_TMAX];           /* X_red of marge2.R:152-166, ascending */
+  double  pt_min, pt_max;               /* of the unrounded pseudotime (summarizeModel.R:71-72) */
+} sclane_lineage_info;
+
+/* ---------------------------------------------------------------------------------------
+ * Library / device queries (no compute)
+ * ------------------------------------------------------------------------------------- */
+int32_t sclane_abi_version(void);
+/* number of usable CUDA devices (0 if none); never fails */
+int32_t sclane_device_count(void);
+/* fills *opts with the defaults of testDynamic.R:60-75 / marge2.R:56-72 */
+void sclane_default_opts(sclane_opts* opts);
+size_t sclane_record_size(void);
+/* kernels launched by this process since load / since the last reset (the bench's gpu_launches claim) */
+int64_t sclane_launch_count(void);
+void sclane_reset_launch_count(void);
+
+/* Device-side timing of the last sclane_test_dynamic*() call on this process (CUDA events on the
+ * library's own stream, summed over batches / lineages / GPUs): what bench.py's roofline uses. */
+#define SCLANE_NSTAGES 6
+#define SCLANE_STAGE_GATHER 0      /* sort permutation + per-gene constants              */
+#define SCLANE_STAGE_FWD_FIT 1     /* K1 forward null fits (stat_out_score_glm_null)     */
+#define SCLANE_STAGE_SWEEP 2       /* K2 score sweep (score_fun_glm x T x {one, both})   */
+#define SCLANE_STAGE_BACKWARD 3    /* K4 backward WIC pass                               */
+#define SCLANE_STAGE_FINAL 4       /* K5 final + null glm.nb                             */
+#define SCLANE_STAGE_COPY 5        /* H2D of counts + D2H of records                     */
+typedef struct sclane_profile {
+  double  ms[SCLANE_NSTAGES];          /* device milliseconds per stage                                   */
+  int64_t launches[SCLANE_NSTAGES];    /* kernel launches (memcpys for SCLANE_STAGE_COPY) per stage        */
+  double  sweep_bytes;                 /* algorithmic bytes the sweep launches moved: sum of 12*N_l per
+                                          (gene, forward iteration actually swept) + 8*N_l per launch       */
+  int64_t sweep_gene_iters;            /* (gene, iteration) pairs swept                                    */
+  double  h2d_bytes, d2h_bytes;
+  double  wall_ms;                     /* host wall clock of the call                                      */
+} sclane_profile;
+void sclane_get_profile(sclane_profile* out);
+
+/* ---------------------------------------------------------------------------------------
+ * The hot path.  Replaces the cluster set-up, FBM creation and the foreach() of
+ * testDynamic.R:135-385 (GLM mode): for every gene and lineage the marge2() forward pass
+ * (marge2.R:109-759), backward WIC pass (:763-812), final glm.nb fit (:841-847), the
+ * intercept-only null glm.nb (testDynamic.R:254-260) and modelLRT (modelLRT.R:43-53).
+ *
+ * counts        n_cells x n_genes column-major int32 == gene-major: gene g's cells are
+ *               counts[g*n_cells .. (g+1)*n_cells) -- the bytes of the bigstatsr FBM the
+ *               reference builds at testDynamic.R:145-147.  HOST pointer.
+ * pt            n_cells x n_lineages column-major doubles, NaN = cell not in lineage (:183). HOST.
+ * size_factor   n_cells doubles (createCellOffset(), enters as offset(log(1/sf)),
+ *               marge2.R:826-829, testDynamic.R:228-231) or NULL.  HOST.
+ * out           n_genes x n_lineages records, gene-major (record of gene g, lineage l at
+ *               out[g*n_lineages + l]); caller allocated.
+ * lineages      n_lineages entries or NULL.
+ * ------------------------------------------------------------------------------------- */
+int32_t sclane_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t n_genes,
+                            const double* pt, int32_t n_lineages,
+                            const double* size_factor,
+                            const sclane_opts* opts,
+                            sclane_record* out, sclane_lineage_info* lineages,
+                            char* errbuf, size_t errlen);
+
+/* Same computation with `counts` already resident in device memory on `device`
+ * (the "inputs in HBM" measurement of bench.py; also what a caller uses to keep a count
+ * matrix on the GPU across calls).  pt / size_factor / out stay host pointers (small). */
+int32_t sclane_test_dynamic_device(const int32_t* d_counts, int32_t device,
+                                   int64_t n_cells, int64_t n_genes,
+                                   const double* pt, int32_t n_lineages,
+                                   const double* size_factor,
+                                   const sclane_opts* opts,
+                                   sclane_record* out, sclane_lineage_info* lineages,
+                                   char* errbuf, size_t errlen);
+
+/* Candidate knots of one lineage (marge2.R:150-173 with min_span.R / max_span.R): host-side,
+ * no GPU needed.  x: n doubles without NaN.  Returns the number of knots (<= SCLANE_TMAX)
+ * or a negative error code. */
+int32_t sclane_candidate_knots(const double* x, int64_t n, const sclane_opts* opts,
+                               double* knots_out, int32_t* minspan_out);
+
+/* ---------------------------------------------------------------------------------------
+ * Single-step entry points used by the unit tests (and by an R-side marge2() wrapper).
+ * All pointers are HOST pointers; each call uploads, runs the same kernels as the batch
+ * path on `device`, and downloads.
+ * ------------------------------------------------------------------------------------- */
+
+/* stat_out_score_glm_null() (stat_out_score_glm_null.R:18-48) for a batch of genes that share
+ * one basis given as (kind, knot) terms: NB fit of Y ~ B - 1, returns per gene beta (n_terms),
+ * sigma (0 = Poisson regime) and, if mu_out != NULL, the fitted means (n_genes x n_cells,
+ * gene-major, in the CALLER's cell order). */
+int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_genes,
+                              const double* x, const double* knots, int32_t n_knots,
+                              const int32_t* term_kind, const int32_t* term_knot_idx, int32_t n_terms,
+                              int32_t device,
+                              double* beta_out, double* sigma_out, double* mu_out,
+                              char* errbuf, size_t errlen);
+
+/* The score sweep: score_fun_glm() (score_fun_glm.R:21-54) for every candidate knot and both
+ * candidate shapes ("one" = tp1 only, "both" = tp1+tp2), given counts, fitted means mu and
+ * sigma of the working null model with basis `terms`.  scores_out: n_genes x 2 x n_knots
+ * ([g][0][k] = one, [g][1][k] = both), NaN = NA (rank rule).  This is the HBM-bound kernel
+ * (12 bytes per cell per gene: int32 count + fp64 mu). */
+int32_t sclane_score_glm(const int32_t* counts, const double* mu, int64_t n_cells, int64_t n_genes,
+                         const double* x, const double* knots, int32_t n_knots,
+                         const int32_t* term_kind, const int32_t* term_knot_idx, int32_t n_terms,
+                         const double* sigma, int32_t device,
+                         double* scores_out,
+                         char* errbuf, size_t errlen);
+
+/* Per-cell link-scale fit and standard error of a fitted record -- the MARGE_Preds /
+ * Null_Preds data.frames (pullMARGESummary.R:66-69, pullNullSummary.R:69-72:
+ * predict(type = "link", se.fit = TRUE)).  x: the lineage's pseudotime (n doubles, unrounded;
+ * rounded internally as marge2.R:154), size_factor may be NULL.  Outputs: n doubles each,
+ * any may be NULL. */
+int32_t sclane_link_preds(const sclane_record* rec, const double* x, int64_t n,
+                          const double* size_factor, int32_t device,
+                          double* marge_link_fit, double* marge_link_se,
+                          double* null_link_fit, double* null_link_se,
+                          char* errbuf, size_t errlen);
+
+/* ---------------------------------------------------------------------------------------
+ * Drop-ins for the reference's three RcppEigen helpers (column-major doubles, HOST pointers).
+ * ------------------------------------------------------------------------------------- */
+/* eigenMapMatMult(A, B, n_cores) -- src/eigenMapMatMult.cpp:6-15.  C (m x n) = A (m x k) * B (k x n). */
+int32_t sclane_matmul(const double* A, const double* B, double* C, int64_t m, int64_t k, int64_t n,
+                      int32_t device, char* errbuf, size_t errlen);
+/* eigenMapMatrixInvert(A, n_cores) -- src/eigenMapInvert.cpp:6-11: A.llt().solve(I), n x n,
+ * lower triangle read, NO positive-definiteness check (garbage in, garbage out, as Eigen). n <= 64. */
+int32_t sclane_llt_inverse(const double* A, double* Ainv, int64_t n,
+                           int32_t device, char* errbuf, size_t errlen);
+/* eigenMapPseudoInverse(A, tolerance, n_cores) -- src/eigenMapPseudoInverse.cpp:6-21:
+ * Jacobi SVD, singular values > tolerance (absolute) inverted.  A is m x n, out is n x m. m,n <= 48. */
+int32_t sclane_pinv(const double* A, double* Apinv, int64_t m, int64_t n, double tolerance,
+                    int32_t device, char* errbuf, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCLANE_B200_H */

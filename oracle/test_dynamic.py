@@ -134,15 +134,23 @@ def test_dynamic(counts: np.ndarray, pt: np.ndarray, genes=None, size_factor_off
             y = counts[i, cells].astype(np.float64)
             sf = None if size_factor_offset is None else np.asarray(size_factor_offset, dtype=np.float64)[cells]
             t0 = time.time()
-            res = marge2(pt[cells, j], y, sf, M=n_potential_basis_fns, approx_knot=approx_knot,
-                         var_name=f"Lineage_{lin}", knots_cache=kc)
-            gene_time = time.time() - t0
             off = None if sf is None else np.log(1.0 / sf)
-            try:
-                null_fit = glm_nb(np.ones((y.size, 1)), y, off)
-                null_err = None
-            except (FloatingPointError, np.linalg.LinAlgError, ZeroDivisionError) as e:
-                null_fit, null_err = None, str(e)
+            if y.sum() == 0.0:
+                # Documented rule: a lineage with no counts for the gene is an error record for both
+                # models (the reference stops in stat_out() -- "GCV.null argument to stat_out() cannot be 0",
+                # stat_out.R:31 -- and its glm.nb degenerates to mu -> 0).
+                from .marge import MargeResult, MargeTrace
+                res = MargeResult(False, "all counts are zero", [], kc[1], kc[0], None, [], MargeTrace())
+                null_fit, null_err = None, "all counts are zero"
+            else:
+                res = marge2(pt[cells, j], y, sf, M=n_potential_basis_fns, approx_knot=approx_knot,
+                             var_name=f"Lineage_{lin}", knots_cache=kc)
+                try:
+                    null_fit = glm_nb(np.ones((y.size, 1)), y, off)
+                    null_err = None
+                except (FloatingPointError, np.linalg.LinAlgError, ZeroDivisionError) as e:
+                    null_fit, null_err = None, str(e)
+            gene_time = time.time() - t0
             status = ("MARGE model " + ("OK" if res.ok else "error") + ", null model " + ("OK" if null_fit is not None else "error"))
             rec = {"Gene": genes[i], "Lineage": lin, "Test_Stat": np.nan, "Test_Stat_Type": "LRT", "Test_Stat_Note": None,
                    "Degrees_Freedom": np.nan, "P_Val": np.nan,

@@ -1,0 +1,574 @@
+"""Host-side mirror of the reference's R interface for the per-gene fitting path.
+
+Same names, argument meaning and error behaviour as scLANE's R functions (R is not available in
+this image, so the host side above the C ABI is Python; the R shim a maintainer would use is in
+r/ and INTEGRATION.md):
+
+    testDynamic()       R/testDynamic.R:60-448      -> sclane_test_dynamic()
+    marge2()            R/marge2.R:56-889           -> sclane_test_dynamic() on one gene
+    modelLRT()          R/modelLRT.R:12-63
+    getResultsDE()      R/getResultsDE.R:23-45
+    testSlope()         R/testSlope.R:21-39
+    createCellOffset()  R/createCellOffset.R:19-38
+    eigenMapMatMult / eigenMapMatrixInvert / eigenMapPseudoInverse   R/RcppExports.R:4-14
+
+All numerics run in libsclane_b200.so on the GPU; this module only marshals buffers and rebuilds
+the 21-field result list of testDynamic.R:320-342 from the fixed-size records.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from typing import Any
+
+import numpy as np
+
+from . import _abi
+from ._lib import SclaneError, check, lib
+
+LETTERS = "ABCDEFGHIJKLMNOPQRSTUVWXYZ"
+_ERRLEN = 1024
+
+
+# ------------------------------------------------------------------------------------------------
+# small R semantics needed on the host side
+# ------------------------------------------------------------------------------------------------
+def _fmt_num(x: float) -> str:
+    """as.character(<double>): 15 significant digits (paste() at marge2.R:593-594)."""
+    return f"{x:.15g}"
+
+
+def _p_adjust_bh(p: np.ndarray) -> np.ndarray:
+    """stats::p.adjust(method = "fdr"); NA stays NA and is not counted."""
+    p = np.asarray(p, dtype=np.float64)
+    out = np.full(p.shape, np.nan)
+    ok = ~np.isnan(p)
+    pv = p[ok]
+    n = pv.size
+    if n:
+        o = np.argsort(-pv, kind="stable")
+        ro = np.argsort(o, kind="stable")
+        i = np.arange(n, 0, -1, dtype=np.float64)
+        out[ok] = np.minimum(1.0, np.minimum.accumulate(n / i * pv[o]))[ro]
+    return out
+
+
+def _na(x):
+    return None if (isinstance(x, float) and math.isnan(x)) else x
+
+
+# ------------------------------------------------------------------------------------------------
+# results container
+# ------------------------------------------------------------------------------------------------
+class ScLANE(dict):
+    """Result of testDynamic(): {gene: {"Lineage_A": {...21 fields...}, ...}} (class "scLANE", testDynamic.R:446)."""
+
+    lineage_info: list
+    profile: dict
+    records: Any
+
+
+class LazyPreds:
+    """MARGE_Preds / Null_Preds (testDynamic.R:339-340) computed on first use by sclane_link_preds():
+    the per-cell link fit and its standard error are 2 x 2 doubles per cell per gene (128 GB at
+    20k genes x 200k cells), so they are materialised on demand instead of eagerly."""
+
+    def __init__(self, record, x, size_factor, which, device=0):
+        self._rec, self._x, self._sf, self._which, self._dev = record, x, size_factor, which, device
+        self._val = None
+
+    def compute(self) -> dict:
+        if self._val is None:
+            f1, s1, f0, s0 = link_preds(self._rec, self._x, self._sf, self._dev)
+            self._val = ({"marge_link_fit": f1, "marge_link_se": s1} if self._which == "marge"
+                         else {"null_link_fit": f0, "null_link_se": s0})
+        return self._val
+
+    def __getitem__(self, k):
+        return self.compute()[k]
+
+    def keys(self):
+        return self.compute().keys()
+
+
+# ------------------------------------------------------------------------------------------------
+# low-level calls
+# ------------------------------------------------------------------------------------------------
+def device_count() -> int:
+    return int(lib().sclane_device_count())
+
+
+def launch_count() -> int:
+    return int(lib().sclane_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().sclane_reset_launch_count()
+
+
+class _Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 6), ("launches", C.c_int64 * 6), ("sweep_bytes", C.c_double),
+                ("sweep_gene_iters", C.c_int64), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
+                ("wall_ms", C.c_double)]
+
+
+STAGE_NAMES = ["gather", "fwd_fit", "sweep", "backward", "final", "copy"]
+
+
+def get_profile() -> dict:
+    p = _Profile()
+    lib().sclane_get_profile(C.byref(p))
+    return {"ms": {n: p.ms[i] for i, n in enumerate(STAGE_NAMES)},
+            "launches": {n: int(p.launches[i]) for i, n in enumerate(STAGE_NAMES)},
+            "sweep_bytes": p.sweep_bytes, "sweep_gene_iters": int(p.sweep_gene_iters),
+            "h2d_bytes": p.h2d_bytes, "d2h_bytes": p.d2h_bytes, "wall_ms": p.wall_ms}
+
+
+def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None, tols_score=1e-5,
+          n_gpus=0, gpu_ids=None, genes_per_batch=0, verbose=False) -> _abi.SclaneOpts:
+    o = _abi.default_opts()
+    o.M = int(n_potential_basis_fns)
+    o.approx_knot = 1 if approx_knot else 0
+    o.n_knot_max = int(n_knot_max)
+    o.minspan = -1 if minspan is None else int(minspan)
+    o.tols_score = float(tols_score)
+    if gpu_ids is not None:
+        o.n_gpus = len(gpu_ids)
+        for i, d in enumerate(gpu_ids):
+            o.gpu_ids[i] = int(d)
+    elif n_gpus:
+        o.n_gpus = int(n_gpus)
+        for i in range(int(n_gpus)):
+            o.gpu_ids[i] = i
+    o.genes_per_batch = int(genes_per_batch)
+    o.verbose = 1 if verbose else 0
+    return o
+
+
+def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = None, device_ptr: int | None = None,
+                device: int = 0):
+    """Thin call of sclane_test_dynamic[_device]: counts int32 [genes, cells] C-contiguous (gene-major), pt float64
+    [cells, lineages].  Returns (records ctypes array [genes * lineages], lineage infos)."""
+    L = lib()
+    pt = np.asarray(pt, dtype=np.float64)
+    if pt.ndim == 1:
+        pt = pt[:, None]
+    n_cells, n_lin = pt.shape
+    pt_cm = np.ascontiguousarray(pt.T)          # column-major cells x lineages
+    if opts is None:
+        opts = _opts()
+    sf = None if size_factor is None else np.ascontiguousarray(size_factor, dtype=np.float64)
+    if sf is not None and sf.shape != (n_cells,):
+        raise ValueError("size.factor.offset must have one entry per cell")
+    err = C.create_string_buffer(_ERRLEN)
+    if device_ptr is None:
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        if counts.ndim != 2 or counts.shape[1] != n_cells:
+            raise ValueError("expr.mat must be genes x cells with one column per row of pt")
+        n_genes = counts.shape[0]
+        recs = (_abi.SclaneRecord * (n_genes * n_lin))()
+        infos = (_abi.SclaneLineageInfo * n_lin)()
+        rc = L.sclane_test_dynamic(counts.ctypes.data, n_cells, n_genes, pt_cm.ctypes.data, n_lin,
+                                   None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
+    else:
+        n_genes = int(counts)  # when a device pointer is given, `counts` is the number of genes
+        recs = (_abi.SclaneRecord * (n_genes * n_lin))()
+        infos = (_abi.SclaneLineageInfo * n_lin)()
+        rc = L.sclane_test_dynamic_device(C.c_void_p(device_ptr), device, n_cells, n_genes, pt_cm.ctypes.data, n_lin,
+                                          None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
+    check(rc, err)
+    return recs, infos
+
+
+def link_preds(record, x, size_factor=None, device: int = 0):
+    """predict(type = "link", se.fit = TRUE) for both models of one record (pullMARGESummary.R:66-69)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.size
+    sf = None if size_factor is None else np.ascontiguousarray(size_factor, dtype=np.float64)
+    outs = [np.empty(n) for _ in range(4)]
+    err = C.create_string_buffer(_ERRLEN)
+    rc = lib().sclane_link_preds(C.byref(record), x.ctypes.data, n, None if sf is None else sf.ctypes.data, device,
+                                 *[o.ctypes.data for o in outs], err, _ERRLEN)
+    check(rc, err)
+    return tuple(outs)
+
+
+def candidate_knots(x, approx_knot=True, n_knot_max=25, minspan=None):
+    """marge2.R:150-173 (host-side; no GPU needed)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    o = _opts(approx_knot=approx_knot, n_knot_max=n_knot_max, minspan=minspan)
+    out = np.empty(_abi.SCLANE_TMAX)
+    ms = C.c_int32(0)
+    n = lib().sclane_candidate_knots(x.ctypes.data, x.size, C.byref(o), out.ctypes.data, C.byref(ms))
+    if n < 0:
+        raise SclaneError(-n, "sclane_candidate_knots failed")
+    return out[:n].copy(), int(ms.value)
+
+
+def stat_out_score_glm_null(counts, x, knots, term_kind, term_knot_idx, device: int = 0, want_mu: bool = True):
+    """stat_out_score_glm_null.R:18-48 for a batch of genes sharing one basis.  Returns (beta [G, p], sigma [G], mu [G, N])."""
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    G, N = counts.shape
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    knots = np.ascontiguousarray(knots, dtype=np.float64)
+    tk = np.ascontiguousarray(term_kind, dtype=np.int32)
+    ti = np.ascontiguousarray(term_knot_idx, dtype=np.int32)
+    p = tk.size
+    beta = np.empty((G, p))
+    sigma = np.empty(G)
+    mu = np.empty((G, N)) if want_mu else None
+    err = C.create_string_buffer(_ERRLEN)
+    rc = lib().sclane_null_stats_glm(counts.ctypes.data, N, G, x.ctypes.data, knots.ctypes.data, knots.size, tk.ctypes.data,
+                                     ti.ctypes.data, p, device, beta.ctypes.data, sigma.ctypes.data,
+                                     None if mu is None else mu.ctypes.data, err, _ERRLEN)
+    check(rc, err)
+    return beta, sigma, mu
+
+
+def score_fun_glm_sweep(counts, mu, sigma, x, knots, term_kind, term_knot_idx, device: int = 0):
+    """score_fun_glm.R:21-54 for every candidate knot and both candidate shapes.  Returns scores [G, 2, T]
+    ([:, 0] = tp1 only, [:, 1] = hinge pair); NaN = NA."""
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    G, N = counts.shape
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    knots = np.ascontiguousarray(knots, dtype=np.float64)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    tk = np.ascontiguousarray(term_kind, dtype=np.int32)
+    ti = np.ascontiguousarray(term_knot_idx, dtype=np.int32)
+    out = np.empty((G, 2, knots.size))
+    err = C.create_string_buffer(_ERRLEN)
+    rc = lib().sclane_score_glm(counts.ctypes.data, mu.ctypes.data, N, G, x.ctypes.data, knots.ctypes.data, knots.size,
+                                tk.ctypes.data, ti.ctypes.data, tk.size, sigma.ctypes.data, device, out.ctypes.data, err, _ERRLEN)
+    check(rc, err)
+    return out
+
+
+# ---- drop-ins for the RcppEigen helpers (R/RcppExports.R:4-14) -------------------------------------
+def eigenMapMatMult(A, B, n_cores: int = 1, device: int = 0):
+    A = np.asarray(A, dtype=np.float64)
+    B = np.asarray(B, dtype=np.float64)
+    if A.ndim != 2 or B.ndim != 2 or A.shape[1] != B.shape[0]:
+        raise ValueError("non-conformable arguments")
+    m, k = A.shape
+    n = B.shape[1]
+    Af, Bf = np.asfortranarray(A), np.asfortranarray(B)
+    Cm = np.empty((m, n), order="F")
+    err = C.create_string_buffer(_ERRLEN)
+    check(lib().sclane_matmul(Af.ctypes.data, Bf.ctypes.data, Cm.ctypes.data, m, k, n, device, err, _ERRLEN), err)
+    return Cm
+
+
+def eigenMapMatrixInvert(A, n_cores: int = 1, device: int = 0):
+    A = np.asfortranarray(np.asarray(A, dtype=np.float64))
+    n = A.shape[0]
+    out = np.empty((n, n), order="F")
+    err = C.create_string_buffer(_ERRLEN)
+    check(lib().sclane_llt_inverse(A.ctypes.data, out.ctypes.data, n, device, err, _ERRLEN), err)
+    return out
+
+
+def eigenMapPseudoInverse(A, tolerance: float = 1e-6, n_cores: int = 1, device: int = 0):
+    A = np.asfortranarray(np.asarray(A, dtype=np.float64))
+    m, n = A.shape
+    out = np.empty((n, m), order="F")
+    err = C.create_string_buffer(_ERRLEN)
+    check(lib().sclane_pinv(A.ctypes.data, out.ctypes.data, m, n, float(tolerance), device, err, _ERRLEN), err)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# record -> the reference's list fields
+# ------------------------------------------------------------------------------------------------
+def _term_names(rec, lineage_letter: str) -> list[str]:
+    """marge2.R:593-594 + :817-821: Intercept, h_<Lineage>_<knot> (tp1) / h_<knot>_<Lineage> (tp2)."""
+    var = f"Lineage_{lineage_letter}"
+    names = ["Intercept"]
+    for j in range(1, rec.n_terms):
+        lab = _fmt_num(rec.term_label[j])
+        names.append(f"h_{var}_{lab}" if rec.term_kind[j] == _abi.TERM_TP1 else f"h_{lab}_{var}")
+    return names
+
+
+def _status_string(rec) -> str:
+    """testDynamic.R:266-278."""
+    m_ok = bool(rec.status & _abi.SCLANE_MARGE_OK)
+    n_ok = bool(rec.status & _abi.SCLANE_NULL_OK)
+    return f"MARGE model {'OK' if m_ok else 'error'}, null model {'OK' if n_ok else 'error'}"
+
+
+def _notes(bits: int, ok: bool) -> str | None:
+    if ok:
+        return None
+    msgs = []
+    if bits & _abi.NOTE_FWD_EMPTY:
+        msgs.append("Error in wic_mat_2[...] : subscript out of bounds (forward pass added fewer than two basis functions)")
+    if bits & _abi.NOTE_ALL_ZERO:
+        msgs.append("all counts are zero")
+    if bits & _abi.NOTE_NUMERIC:
+        msgs.append("missing value where TRUE/FALSE needed")
+    return "; ".join(msgs) if msgs else "model fit failed"
+
+
+def _slope_data(rec, names, pt_lineage, gene, letter):
+    """createSlopeTestData.R:15-74 + testDynamic.R:295-298."""
+    m_ok = bool(rec.status & _abi.SCLANE_MARGE_OK)
+    if not m_ok or rec.n_terms == 1:
+        note = "MARGE model error" if not m_ok else "No non-intercept coefficients"
+        return {"Gene": [gene], "Lineage": [letter], "Breakpoint": [None], "Rounded_Breakpoint": [None], "Direction": [None],
+                "Beta": [None], "Test_Stat": [None], "P_Val": [None], "Notes": [note]}
+    k = rec.n_terms - 1
+    rounded = [float(rec.term_label[j]) for j in range(1, rec.n_terms)]
+    dirs = ["Right" if rec.term_kind[j] == _abi.TERM_TP1 else "Left" for j in range(1, rec.n_terms)]
+    brk = [float(pt_lineage[int(np.argmin(np.abs(pt_lineage - x)))]) for x in rounded]
+    return {"Gene": [gene] * k, "Lineage": [letter] * k, "Breakpoint": brk, "Rounded_Breakpoint": rounded, "Direction": dirs,
+            "Beta": [float(rec.coef[j]) for j in range(1, rec.n_terms)], "Test_Stat": [float(rec.z[j]) for j in range(1, rec.n_terms)],
+            "P_Val": [float(rec.p[j]) for j in range(1, rec.n_terms)], "Notes": [None] * k}
+
+
+def _summarize_model(rec, pt_min, pt_max):
+    """summarizeModel.R:28-140 (GLM branch), including its duplicate-breakpoint indexing."""
+    if not (rec.status & _abi.SCLANE_MARGE_OK):
+        return {"Breakpoint": [None], "Slope.Segment": [None], "Trend.Segment": [None]}
+    if rec.n_terms == 1:
+        return {"Breakpoint": [None], "Slope.Segment": [0.0], "Trend.Segment": [0.0]}
+    rows = [(float(rec.term_label[j]), "Right" if rec.term_kind[j] == _abi.TERM_TP1 else "Left", float(rec.coef[j]))
+            for j in range(1, rec.n_terms)]
+    rows.sort(key=lambda r: (r[0], r[1]))
+    ranges = [(b, pt_max) if d == "Right" else (pt_min, b) for b, d, _ in rows]
+    bps = [r[0] for r in rows]
+    uniq = []
+    for b in bps:
+        if b not in uniq:
+            uniq.append(b)
+    nseg = len(uniq) + 1
+
+    def bp(i):
+        return bps[i - 1] if 1 <= i <= len(bps) else float("nan")
+
+    segs = [(pt_min, bp(1)) if i == 1 else ((bp(i - 1), pt_max) if i == nseg else (bp(i - 1), bp(i))) for i in range(1, nseg + 1)]
+    slopes = []
+    for lo, hi in segs:
+        s = 0.0
+        for j, (a, b) in enumerate(ranges):
+            if lo < b and hi > a:
+                s += rows[j][2] if rows[j][1] == "Right" else -rows[j][2]
+        slopes.append(s)
+    trends = [1.0 if s > 0 else (-1.0 if s < 0 else 0.0) for s in slopes]
+    return {"Breakpoint": uniq, "Slope.Segment": slopes, "Trend.Segment": trends}
+
+
+def _record_to_list(rec, gene, lin_idx, info, pt_lineage, x_lineage, sf_lineage, preds, device):
+    letter = LETTERS[lin_idx]
+    m_ok = bool(rec.status & _abi.SCLANE_MARGE_OK)
+    n_ok = bool(rec.status & _abi.SCLANE_NULL_OK)
+    names = _term_names(rec, letter) if m_ok else []
+    out = {
+        "Gene": gene, "Lineage": letter,
+        "Test_Stat": _na(rec.test_stat), "Test_Stat_Type": "LRT",
+        "Test_Stat_Note": None if (m_ok and n_ok) else "No test performed due to model failure.",
+        "Degrees_Freedom": _na(rec.df), "P_Val": _na(rec.p_val),
+        "LogLik_MARGE": _na(rec.loglik), "LogLik_Null": _na(rec.null_loglik),
+        "Dev_MARGE": _na(rec.deviance), "Dev_Null": _na(rec.null_deviance),
+        "Model_Status": _status_string(rec),
+        "MARGE_Fit_Notes": _notes(rec.marge_notes, m_ok), "Null_Fit_Notes": _notes(rec.null_notes, n_ok),
+        "Gene_Time": rec.gene_time,
+    }
+    out["MARGE_Summary"] = ({"term": names, "estimate": [rec.coef[j] for j in range(rec.n_terms)],
+                             "std.error": [rec.se[j] for j in range(rec.n_terms)],
+                             "statistic": [rec.z[j] for j in range(rec.n_terms)],
+                             "p.value": [rec.p[j] for j in range(rec.n_terms)]} if m_ok else None)
+    out["Null_Summary"] = ({"term": ["Intercept"], "estimate": [rec.null_coef], "std.error": [rec.null_se],
+                            "statistic": [rec.null_z], "p.value": [rec.null_p]} if n_ok else None)
+    if preds == "none":
+        out["MARGE_Preds"] = None
+        out["Null_Preds"] = None
+    else:
+        out["MARGE_Preds"] = LazyPreds(rec, x_lineage, sf_lineage, "marge", device) if m_ok else None
+        out["Null_Preds"] = LazyPreds(rec, x_lineage, sf_lineage, "null", device) if n_ok else None
+        if preds == "eager":
+            for k in ("MARGE_Preds", "Null_Preds"):
+                if out[k] is not None:
+                    out[k] = out[k].compute()
+    out["MARGE_Slope_Data"] = _slope_data(rec, names, pt_lineage, gene, letter)
+    gd = _summarize_model(rec, info.pt_min, info.pt_max)
+    flat = {"Gene": [gene], "Lineage": [letter]}
+    for key in ("Breakpoint", "Slope.Segment", "Trend.Segment"):
+        vals = gd[key]
+        if len(vals) == 1:
+            flat[key] = [vals[0]]
+        else:
+            for q, v in enumerate(vals, 1):
+                flat[f"{key}{q}"] = [v]
+    out["Gene_Dynamics"] = flat
+    # extras (not in the reference's list): fitted dispersion and the record itself
+    out["Theta"] = (_na(rec.theta), _na(rec.null_theta))
+    out["record"] = rec
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's public functions
+# ------------------------------------------------------------------------------------------------
+def createCellOffset(expr_mat, scale_factor: float = 1e4) -> np.ndarray:
+    """createCellOffset.R:19-38: scale.factor / colSums(counts); expr.mat is genes x cells."""
+    if expr_mat is None:
+        raise ValueError("Please provide expr.mat to createCellOffset().")
+    m = np.asarray(expr_mat)
+    if m.ndim != 2:
+        raise ValueError("Input expr.mat must be coerceable to a matrix of integer counts.")
+    return float(scale_factor) / m.sum(axis=0).astype(np.float64)
+
+
+def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_gee: bool = False,
+                cor_structure: str = "ar1", gee_bias_correction_method=None, gee_test: str = "wald",
+                is_glmm: bool = False, glmm_adaptive: bool = True, id_vec=None, n_potential_basis_fns: int = 5,
+                n_cores: int = 4, approx_knot: bool = True, verbose: bool = False, random_seed: int = 312,
+                n_gpus: int = 0, gpu_ids=None, genes_per_batch: int = 0, preds: str = "lazy") -> ScLANE:
+    """testDynamic.R:60-448, GLM mode.  expr_mat: genes x cells integer counts (rows named by `genes`); pt: cells x
+    lineages pseudotime (NaN = cell not in the lineage).  `n_cores` is kept for signature compatibility; the work is
+    sharded over `n_gpus` B200s instead (0 = all visible).  Returns a ScLANE dict of per-gene, per-lineage lists."""
+    if expr_mat is None or pt is None:
+        raise ValueError("You forgot some inputs to testDynamic().")
+    if is_gee or is_glmm:
+        if id_vec is None:
+            raise ValueError("You must provide a vector of IDs if you're using GEE / GLMM modes.")
+        raise SclaneError(_abi_unsupported(), "GEE / GLMM modes are not built into sclane_b200 yet; only GLM mode runs on the GPU")
+    counts = np.ascontiguousarray(expr_mat, dtype=np.int32)
+    if counts.ndim != 2:
+        raise ValueError("Input expr.mat must be coerceable to a matrix of integer counts.")
+    pt_arr = np.asarray(pt, dtype=np.float64)
+    if pt_arr.ndim == 1:
+        pt_arr = pt_arr[:, None]
+    n_genes = counts.shape[0]
+    if genes is None:
+        genes = [f"Gene_{i + 1}" for i in range(n_genes)]
+    genes = [str(g) for g in genes]
+    if len(genes) != n_genes:
+        raise ValueError("genes must name every row of expr.mat")
+    t0 = time.time()
+    o = _opts(n_potential_basis_fns, approx_knot, 25, None, 1e-5, n_gpus, gpu_ids, genes_per_batch, verbose)
+    recs, infos = run_records(counts, pt_arr, size_factor_offset, o)
+    n_lin = pt_arr.shape[1]
+    res = ScLANE()
+    dev0 = int(gpu_ids[0]) if gpu_ids else 0
+    lin_cache = []
+    for l in range(n_lin):
+        cells = np.flatnonzero(~np.isnan(pt_arr[:, l]))
+        ptl = pt_arr[cells, l]
+        sfl = None if size_factor_offset is None else np.asarray(size_factor_offset, dtype=np.float64)[cells]
+        lin_cache.append((ptl, sfl))
+    for g in range(n_genes):
+        per_l = {}
+        for l in range(n_lin):
+            ptl, sfl = lin_cache[l]
+            per_l[f"Lineage_{LETTERS[l]}"] = _record_to_list(recs[g * n_lin + l], genes[g], l, infos[l], ptl, ptl, sfl, preds, dev0)
+        res[genes[g]] = per_l
+    res.lineage_info = [{"n_cells": int(i.n_cells), "knots": [i.knots[k] for k in range(i.n_knots)], "minspan": int(i.minspan),
+                         "pt_min": i.pt_min, "pt_max": i.pt_max} for i in infos]
+    res.profile = get_profile()
+    res.records = recs
+    if verbose:
+        dt = time.time() - t0
+        print(f"scLANE testing in GLM mode completed for {n_genes} genes across {n_lin} "
+              f"{'lineage' if n_lin == 1 else 'lineages'} in {dt:.3f} secs")
+    return res
+
+
+def _abi_unsupported() -> int:
+    return 4
+
+
+def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False, approx_knot: bool = True,
+           n_knot_max: int = 25, tols_score: float = 1e-5, minspan=None, device: int = 0) -> dict:
+    """marge2.R:56-889 for one gene (GLM mode): X_pred = pseudotime of the lineage's cells, Y = counts, Y_offset =
+    size factors.  Returns final_mod-like fields (coefficients, SEs, theta, logLik, deviance), coef_names,
+    marge_coef_names, model_type."""
+    if X_pred is None or Y is None:
+        raise ValueError("Some required inputs to marge2() are missing.")
+    if is_gee:
+        raise SclaneError(4, "GEE mode is not built into sclane_b200 yet")
+    y = np.ascontiguousarray(np.asarray(Y).reshape(1, -1), dtype=np.int32)
+    x = np.asarray(X_pred, dtype=np.float64).reshape(-1)
+    o = _opts(M, approx_knot, n_knot_max, minspan, tols_score, gpu_ids=[device])
+    recs, infos = run_records(y, x[:, None], Y_offset, o)
+    rec = recs[0]
+    if not (rec.status & _abi.SCLANE_MARGE_OK):
+        raise SclaneError(0, _notes(rec.marge_notes, False))
+    names = _term_names(rec, "A")
+    p = rec.n_terms
+    return {"final_mod": {"coefficients": dict(zip(names, [rec.coef[j] for j in range(p)])),
+                          "std.error": [rec.se[j] for j in range(p)], "theta": rec.theta, "SE.theta": rec.se_theta,
+                          "twologlik": 2.0 * rec.loglik, "logLik": rec.loglik, "df": p + 1, "deviance": rec.deviance,
+                          "converged": not bool(rec.marge_notes & _abi.NOTE_NOT_CONVERGED),
+                          "th.warn": _th_warn(rec.marge_notes),
+                          "vcov": np.array([rec.cov[j] for j in range(p * p)]).reshape(p, p)},
+            "basis_mtx": None, "WIC_mtx": None, "GCV": None, "model_type": "GLM",
+            "coef_names": names, "marge_coef_names": names, "record": rec,
+            "knots": [infos[0].knots[k] for k in range(infos[0].n_knots)]}
+
+
+def _th_warn(bits: int):
+    if bits & _abi.NOTE_ALT_LIMIT:
+        return "alternation limit reached"
+    if bits & _abi.NOTE_TH_ITER_LIMIT:
+        return "iteration limit reached"
+    if bits & _abi.NOTE_TH_TRUNC:
+        return "estimate truncated at zero"
+    return None
+
+
+def modelLRT(mod_1=None, mod_0=None, is_glmm: bool = False) -> dict:
+    """modelLRT.R:12-63.  mod_1: result of marge2() (or None/exception for a failed fit); mod_0: dict with logLik and df."""
+    if mod_1 is None or mod_0 is None or isinstance(mod_1, Exception) or isinstance(mod_0, Exception):
+        return {"Alt_Mod_LL": None, "Null_Mod_LL": None, "LRT_Stat": None, "DF": None, "P_Val": None, "Model_Type": None,
+                "Notes": "No test performed due to model failure."}
+    from scipy.stats import chi2  # host-side convenience only
+    m1 = mod_1["final_mod"]
+    ll1, ll0 = m1["logLik"], mod_0["logLik"]
+    lrt = 2.0 * (ll1 - ll0)
+    df = m1["df"] - mod_0["df"]
+    if df == 0:
+        df = 1
+    return {"Alt_Mod_LL": ll1, "Null_Mod_LL": ll0, "LRT_Stat": lrt, "DF": df, "P_Val": float(chi2.sf(lrt, df)),
+            "Model_Type": "GLM", "Notes": None}
+
+
+def getResultsDE(test_dyn_res=None, p_adj_method: str = "fdr", fdr_cutoff: float = 0.01):
+    """getResultsDE.R:23-45: first 15 fields -> table sorted by decreasing Test_Stat, BH adjustment, dynamic if
+    P_Val_Adj < cutoff (NA -> 0), per-gene max over lineages.  Returns a pandas DataFrame."""
+    if test_dyn_res is None:
+        raise ValueError("Please provide a result list from testDynamic().")
+    if p_adj_method not in ("fdr", "BH"):
+        raise ValueError("Please choose a valid p-value adjustment method.")
+    import pandas as pd
+    keys = ["Gene", "Lineage", "Test_Stat", "Test_Stat_Type", "Test_Stat_Note", "Degrees_Freedom", "P_Val", "LogLik_MARGE",
+            "LogLik_Null", "Dev_MARGE", "Dev_Null", "Model_Status", "MARGE_Fit_Notes", "Null_Fit_Notes", "Gene_Time"]
+    rows = [{k: r[k] for k in keys} for lins in test_dyn_res.values() for r in lins.values()]
+    df = pd.DataFrame(rows, columns=keys)
+    df = df.sort_values("Test_Stat", ascending=False, kind="stable", na_position="last").reset_index(drop=True)
+    padj = _p_adjust_bh(df["P_Val"].to_numpy(dtype=np.float64, na_value=np.nan))
+    df["P_Val_Adj"] = padj
+    df["Gene_Dynamic_Lineage"] = np.where(np.isnan(padj), 0, (padj < fdr_cutoff).astype(int))
+    df["Gene_Dynamic_Overall"] = df.groupby("Gene")["Gene_Dynamic_Lineage"].transform("max")
+    front = ["Gene", "Lineage", "Test_Stat", "P_Val"]
+    return df[front + [c for c in df.columns if c not in front]]
+
+
+def testSlope(test_dyn_res=None, p_adj_method: str = "fdr", fdr_cutoff: float = 0.01):
+    """testSlope.R:21-39."""
+    if test_dyn_res is None:
+        raise ValueError("You forgot to provide results from testDynamic() to testSlope().")
+    import pandas as pd
+    frames = [pd.DataFrame(r["MARGE_Slope_Data"]) for lins in test_dyn_res.values() for r in lins.values()]
+    df = pd.concat(frames, ignore_index=True)
+    df["_abs"] = df["Test_Stat"].astype(float).abs()
+    df = df.sort_values("_abs", ascending=False, kind="stable", na_position="last").drop(columns="_abs")
+    df["P_Val_Adj"] = _p_adjust_bh(df["P_Val"].to_numpy(dtype=np.float64, na_value=np.nan))
+    df = df.sort_values(["Gene", "Breakpoint"], kind="stable", na_position="last").reset_index(drop=True)
+    padj = df["P_Val_Adj"].to_numpy(dtype=np.float64)
+    df["Gene_Dynamic_Lineage_Slope"] = np.where(np.isnan(padj), 0, (padj < fdr_cutoff).astype(int))
+    df["Gene_Dynamic_Lineage"] = df.groupby(["Gene", "Lineage"])["Gene_Dynamic_Lineage_Slope"].transform("max")
+    df["Gene_Dynamic_Overall"] = df.groupby("Gene")["Gene_Dynamic_Lineage"].transform("max")
+    return df

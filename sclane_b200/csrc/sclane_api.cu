@@ -1,0 +1,757 @@
+// sclane_api.cu -- C ABI of libsclane_b200.so (include/sclane_b200.h): host orchestration of the
+// per-lineage / per-batch kernel sequence, gene sharding over GPUs, and the small drop-in helpers.
+// There is no CPU compute path in this file: every entry point that computes launches CUDA kernels
+// and fails with SCLANE_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <thread>
+
+#include "sclane_device.cuh"
+#include "sclane_host.hpp"
+
+using namespace sclane;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+std::mutex g_prof_mu;
+sclane_profile g_prof;
+
+void set_err(char* errbuf, size_t errlen, const char* fmt, ...) {
+  if (!errbuf || errlen == 0) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(errbuf, errlen, fmt, ap);
+  va_end(ap);
+}
+
+struct CudaFail {
+  std::string msg;
+};
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512];                                                                                \
+      snprintf(b_, sizeof(b_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      throw CudaFail{b_};                                                                          \
+    }                                                                                              \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    if (count == 0) return;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+struct EventTimer {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> stage;     // stage of interval [i, i+1)
+  cudaStream_t s;
+  explicit EventTimer(cudaStream_t st) : s(st) {}
+  void mark(int stage_of_next) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(e, s));
+    ev.push_back(e);
+    stage.push_back(stage_of_next);
+  }
+  // call after the stream is synchronised
+  void collect(sclane_profile& p) {
+    for (size_t i = 0; i + 1 < ev.size(); ++i) {
+      float ms = 0.f;
+      if (stage[i] >= 0 && cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) p.ms[stage[i]] += ms;
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear(); stage.clear();
+  }
+  ~EventTimer() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
+struct DevicePlan {
+  DevBuf<int> perm;
+  DevBuf<double> u, off;
+  DevBuf<Lineage> lin;
+  void upload(const LineagePlan& P, cudaStream_t s) {
+    perm.alloc(P.perm.size());
+    u.alloc(P.u.size());
+    lin.alloc(1);
+    CK(cudaMemcpyAsync(perm.p, P.perm.data(), P.perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(u.p, P.u.data(), P.u.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(lin.p, &P.L, sizeof(Lineage), cudaMemcpyHostToDevice, s));
+    if (!P.off.empty()) {
+      off.alloc(P.off.size());
+      CK(cudaMemcpyAsync(off.p, P.off.data(), P.off.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+  }
+};
+
+template <int STAGE>
+void launch_stage(const StageArgs& A, cudaStream_t s) {
+  k_stage<STAGE><<<A.n_genes, kThreads, 0, s>>>(A);
+  CK(cudaGetLastError());
+  g_launches.fetch_add(1);
+}
+
+int forward_iterations(int M) { return (M - 1 + 1) / 2; }   // m = 1, 3, 5, ... until m >= M (marge2.R:752-757)
+
+// Run genes [g0, g1) of one lineage on one device.  Exactly one of h_counts / d_counts is non-null;
+// both are gene-major with leading dimension n_cells.  Records go to out[(g - out_g0) * n_lineages + lin_idx].
+void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int64_t n_cells, int64_t g0, int64_t g1,
+               const LineagePlan& P, const sclane_opts& o, bool use_offset, sclane_record* out, int64_t out_g0, int n_lineages,
+               int lin_idx, sclane_profile& prof) {
+  if (g1 <= g0) return;
+  CK(cudaSetDevice(device));
+  cudaStream_t s;
+  CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+  DevicePlan D;
+  D.upload(P, s);
+  const Lineage& L = P.L;
+  const int64_t G = g1 - g0;
+  // batch size from free memory: raw (host path) + sorted counts + mu + records
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t per_gene = (h_counts ? (size_t)n_cells * 4 : 0) + (size_t)L.Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats);
+  size_t budget = (size_t)((double)free_b * 0.6);
+  const size_t cap = (size_t)24 << 30;
+  if (budget > cap) budget = cap;
+  int64_t B = (int64_t)(budget / per_gene);
+  if (o.genes_per_batch > 0 && o.genes_per_batch < B) B = o.genes_per_batch;
+  if (B > G) B = G;
+  if (B < 1) throw CudaFail{"not enough free device memory for a single gene"};
+  DevBuf<int> d_raw, d_ys;
+  DevBuf<double> d_mu;
+  DevBuf<GeneStats> d_stats;
+  DevBuf<GeneOutDev> d_out;
+  if (h_counts) d_raw.alloc((size_t)B * (size_t)n_cells);
+  d_ys.alloc((size_t)B * (size_t)L.Npad);
+  d_mu.alloc((size_t)B * (size_t)L.Npad);
+  d_stats.alloc((size_t)B);
+  d_out.alloc((size_t)B);
+  std::vector<GeneOutDev> h_out((size_t)B);
+  const int n_iter = forward_iterations(o.M);
+  EventTimer tm(s);
+  for (int64_t b0 = g0; b0 < g1; b0 += B) {
+    const int64_t b1 = std::min<int64_t>(b0 + B, g1);
+    const int nb = (int)(b1 - b0);
+    tm.mark(SCLANE_STAGE_COPY);
+    const int* raw = nullptr;
+    if (h_counts) {
+      CK(cudaMemcpyAsync(d_raw.p, h_counts + (size_t)b0 * (size_t)n_cells, (size_t)nb * (size_t)n_cells * 4, cudaMemcpyHostToDevice, s));
+      prof.h2d_bytes += (double)nb * (double)n_cells * 4.0;
+      prof.launches[SCLANE_STAGE_COPY]++;
+      raw = d_raw.p;
+    } else {
+      raw = d_counts + (size_t)b0 * (size_t)n_cells;
+    }
+    tm.mark(SCLANE_STAGE_GATHER);
+    k_gather_stats<<<nb, kThreads, 0, s>>>(raw, (long long)n_cells, D.perm.p, L.N, L.Npad, d_ys.p, d_stats.p, d_out.p, nb);
+    CK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    prof.launches[SCLANE_STAGE_GATHER]++;
+    StageArgs A;
+    A.lineage = D.lin.p; A.ys = d_ys.p; A.u = D.u.p; A.off = D.off.p; A.mu = d_mu.p; A.stats = d_stats.p; A.out = d_out.p;
+    A.scores = nullptr; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
+    for (int it = 0; it < n_iter; ++it) {
+      tm.mark(SCLANE_STAGE_FWD_FIT);
+      launch_stage<STAGE_FWD_FIT>(A, s);
+      prof.launches[SCLANE_STAGE_FWD_FIT]++;
+      tm.mark(SCLANE_STAGE_SWEEP);
+      launch_stage<STAGE_SWEEP>(A, s);
+      prof.launches[SCLANE_STAGE_SWEEP]++;
+    }
+    tm.mark(SCLANE_STAGE_BACKWARD);
+    launch_stage<STAGE_BACKWARD>(A, s);
+    prof.launches[SCLANE_STAGE_BACKWARD]++;
+    tm.mark(SCLANE_STAGE_FINAL);
+    launch_stage<STAGE_FINAL>(A, s);
+    prof.launches[SCLANE_STAGE_FINAL]++;
+    tm.mark(SCLANE_STAGE_COPY);
+    CK(cudaMemcpyAsync(h_out.data(), d_out.p, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
+    prof.d2h_bytes += (double)nb * sizeof(GeneOutDev);
+    prof.launches[SCLANE_STAGE_COPY]++;
+    tm.mark(-1);
+    CK(cudaStreamSynchronize(s));
+    tm.collect(prof);
+    for (int i = 0; i < nb; ++i) {
+      GeneOut go;
+      go.st = h_out[(size_t)i].st; go.alt = h_out[(size_t)i].alt; go.null = h_out[(size_t)i].null;
+      sclane_record& r = out[((b0 - out_g0) + i) * n_lineages + lin_idx];
+      finalize_record(go, L, r);
+      // sweeps actually run for this gene: one per forward iteration it entered
+      const int sw = go.st.fwd_iters;
+      prof.sweep_gene_iters += sw;
+      prof.sweep_bytes += 12.0 * (double)L.N * (double)sw;
+    }
+    prof.sweep_bytes += 8.0 * (double)L.N * (double)n_iter;
+  }
+}
+
+int check_opts(const sclane_opts* o, char* errbuf, size_t errlen) {
+  if (!o) { set_err(errbuf, errlen, "opts is NULL"); return SCLANE_ERR_ARG; }
+  if (o->abi_version != SCLANE_ABI_VERSION) { set_err(errbuf, errlen, "ABI version mismatch: caller %d, library %d", o->abi_version, SCLANE_ABI_VERSION); return SCLANE_ERR_ARG; }
+  if (o->mode != 0) { set_err(errbuf, errlen, "mode %d (GEE) is not built yet; only GLM mode (0)", o->mode); return SCLANE_ERR_UNSUPPORTED; }
+  if (o->M < 3 || o->M > SCLANE_PMAX) { set_err(errbuf, errlen, "M must be in [3, %d]", SCLANE_PMAX); return SCLANE_ERR_ARG; }
+  if (!o->approx_knot) { set_err(errbuf, errlen, "approx_knot = 0 is not supported yet"); return SCLANE_ERR_UNSUPPORTED; }
+  if (o->n_knot_max < 1 || o->n_knot_max > SCLANE_TMAX) { set_err(errbuf, errlen, "n_knot_max must be in [1, %d]", SCLANE_TMAX); return SCLANE_ERR_ARG; }
+  return SCLANE_OK;
+}
+
+int usable_devices() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void merge_profile(const sclane_profile& p) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < SCLANE_NSTAGES; ++i) { g_prof.ms[i] += p.ms[i]; g_prof.launches[i] += p.launches[i]; }
+  g_prof.sweep_bytes += p.sweep_bytes;
+  g_prof.sweep_gene_iters += p.sweep_gene_iters;
+  g_prof.h2d_bytes += p.h2d_bytes;
+  g_prof.d2h_bytes += p.d2h_bytes;
+}
+
+int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int device_for_d, int64_t n_cells, int64_t n_genes,
+                      const double* pt, int32_t n_lineages, const double* size_factor, const sclane_opts* opts,
+                      sclane_record* out, sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  int rc = check_opts(opts, errbuf, errlen);
+  if (rc) return rc;
+  if ((!h_counts && !d_counts) || !pt || !out || n_cells <= 0 || n_genes <= 0 || n_lineages <= 0) {
+    set_err(errbuf, errlen, "bad arguments (null pointer or non-positive size)");
+    return SCLANE_ERR_ARG;
+  }
+  if (n_cells > (int64_t)2000000000) { set_err(errbuf, errlen, "n_cells too large"); return SCLANE_ERR_ARG; }
+  const int ndev = usable_devices();
+  if (ndev <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
+  std::vector<int> devs;
+  if (d_counts) devs.push_back(device_for_d);
+  else if (opts->n_gpus > 0) { for (int i = 0; i < opts->n_gpus && i < SCLANE_MAX_GPUS; ++i) devs.push_back(opts->gpu_ids[i]); }
+  else { for (int i = 0; i < ndev; ++i) devs.push_back(i); }
+  for (int d : devs) if (d < 0 || d >= ndev) { set_err(errbuf, errlen, "device id %d out of range (0..%d)", d, ndev - 1); return SCLANE_ERR_ARG; }
+  const auto t_start = std::chrono::steady_clock::now();
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::memset(&g_prof, 0, sizeof(g_prof));
+  }
+  for (int l = 0; l < n_lineages; ++l) {
+    LineagePlan P;
+    if (!build_lineage_plan(pt + (int64_t)l * n_cells, n_cells, size_factor, *opts, P)) {
+      set_err(errbuf, errlen, "lineage %d: %s", l, P.error.c_str());
+      return SCLANE_ERR_ARG;
+    }
+    if (lineages) {
+      sclane_lineage_info& li = lineages[l];
+      std::memset(&li, 0, sizeof(li));
+      li.n_cells = P.L.N; li.n_knots = P.L.T; li.minspan = P.minspan;
+      for (int k = 0; k < P.L.T; ++k) li.knots[k] = P.L.knots[k];
+      li.pt_min = P.pt_min; li.pt_max = P.pt_max;
+    }
+    const int nd = (int)devs.size();
+    std::vector<std::string> errs((size_t)nd);
+    std::vector<sclane_profile> profs((size_t)nd);
+    for (auto& p : profs) std::memset(&p, 0, sizeof(p));
+    auto work = [&](int di) {
+      // contiguous gene blocks per device (gene-major matrix => contiguous memory per shard)
+      const int64_t g0 = n_genes * di / nd, g1 = n_genes * (di + 1) / nd;
+      try {
+        run_shard(devs[(size_t)di], h_counts, d_counts, n_cells, g0, g1, P, *opts, size_factor != nullptr, out, 0, n_lineages, l, profs[(size_t)di]);
+      } catch (const CudaFail& f) {
+        errs[(size_t)di] = f.msg;
+      } catch (const std::exception& e) {
+        errs[(size_t)di] = e.what();
+      }
+    };
+    if (nd == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (int di = 0; di < nd; ++di) th.emplace_back(work, di);
+      for (auto& t : th) t.join();
+    }
+    for (int di = 0; di < nd; ++di) {
+      if (!errs[(size_t)di].empty()) {
+        set_err(errbuf, errlen, "device %d: %s", devs[(size_t)di], errs[(size_t)di].c_str());
+        return SCLANE_ERR_CUDA;
+      }
+      merge_profile(profs[(size_t)di]);
+    }
+  }
+  const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.wall_ms = wall;
+  }
+  const double per_gene = wall / 1000.0 / (double)(n_genes * n_lineages);
+  for (int64_t i = 0; i < n_genes * n_lineages; ++i) out[i].gene_time = per_gene;
+  return SCLANE_OK;
+}
+
+// ---- small helper kernels -------------------------------------------------------------------------
+__global__ void k_matmul(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int m, int k, int n) {
+  // column-major: A m x k, B k x n, C m x n; 16x16 shared tiles
+  __shared__ double As[16][17], Bs[16][17];
+  const int row = blockIdx.x * 16 + threadIdx.x, col = blockIdx.y * 16 + threadIdx.y;
+  double acc = 0.0;
+  for (int t = 0; t < k; t += 16) {
+    As[threadIdx.y][threadIdx.x] = (row < m && t + threadIdx.y < k) ? A[(size_t)(t + threadIdx.y) * m + row] : 0.0;
+    Bs[threadIdx.y][threadIdx.x] = (t + threadIdx.x < k && col < n) ? B[(size_t)col * k + t + threadIdx.x] : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc += As[q][threadIdx.x] * Bs[threadIdx.y][q];
+    __syncthreads();
+  }
+  if (row < m && col < n) C[(size_t)col * m + row] = acc;
+}
+
+// Eigen-style unblocked LLT + solve against identity, one CTA, n <= 64, column-major in/out.
+__global__ void k_llt_inverse(const double* __restrict__ A, double* __restrict__ Ainv, int n) {
+  __shared__ double Lm[64][65];
+  __shared__ int stop_at;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n * n; i += blockDim.x) { const int r = i % n, c = i / n; Lm[r][c] = A[(size_t)c * n + r]; }
+  if (tid == 0) stop_at = -1;
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    if (tid == 0) {
+      double x = Lm[k][k];
+      for (int j = 0; j < k; ++j) x -= Lm[k][j] * Lm[k][j];
+      if (x <= 0.0) stop_at = k;                 // Eigen: return k, matrix left as is from here on
+      else Lm[k][k] = sqrt(x);
+    }
+    __syncthreads();
+    if (stop_at >= 0) break;
+    const double piv = Lm[k][k];
+    for (int i = k + 1 + tid; i < n; i += blockDim.x) {
+      double s = Lm[i][k];
+      for (int j = 0; j < k; ++j) s -= Lm[i][j] * Lm[k][j];
+      Lm[i][k] = s / piv;
+    }
+    __syncthreads();
+  }
+  // solve L y = e_c, L^T x = y for every column c (lower triangle only is read)
+  for (int c = tid; c < n; c += blockDim.x) {
+    double yv[64];
+    for (int i = 0; i < n; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int j = 0; j < i; ++j) s -= Lm[i][j] * yv[j];
+      yv[i] = s / Lm[i][i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double s = yv[i];
+      for (int j = i + 1; j < n; ++j) s -= Lm[j][i] * yv[j];
+      yv[i] = s / Lm[i][i];
+    }
+    for (int i = 0; i < n; ++i) Ainv[(size_t)c * n + i] = yv[i];
+  }
+}
+
+// One-sided Jacobi SVD pseudo-inverse, one CTA; works on W = A (m x n, m >= n) in shared memory.
+// out = V diag(1/s_i if s_i > tol) U^T  (n x m), column-major.
+__global__ void k_pinv_tall(const double* __restrict__ A, double* __restrict__ out, int m, int n, double tol) {
+  __shared__ double Wm[48][49];   // columns of A being orthogonalised: Wm[row][col]
+  __shared__ double Vm[48][49];
+  __shared__ double red[3];
+  __shared__ int rotated;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < m * n; i += blockDim.x) { const int r = i % m, c = i / m; Wm[r][c] = A[(size_t)c * m + r]; }
+  for (int i = tid; i < n * n; i += blockDim.x) { const int r = i % n, c = i / n; Vm[r][c] = (r == c) ? 1.0 : 0.0; }
+  __syncthreads();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    for (int p = 0; p < n - 1; ++p) {
+      for (int q = p + 1; q < n; ++q) {
+        if (tid == 0) {
+          double a = 0.0, b = 0.0, g = 0.0;
+          for (int r = 0; r < m; ++r) { a += Wm[r][p] * Wm[r][p]; b += Wm[r][q] * Wm[r][q]; g += Wm[r][p] * Wm[r][q]; }
+          red[0] = a; red[1] = b; red[2] = g;
+        }
+        __syncthreads();
+        const double a = red[0], b = red[1], g = red[2];
+        const bool rot = fabs(g) > 1e-15 * sqrt(a * b) && g != 0.0;
+        if (rot) {
+          const double zeta = (b - a) / (2.0 * g);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+          for (int r = tid; r < m; r += blockDim.x) {
+            const double wp = Wm[r][p], wq = Wm[r][q];
+            Wm[r][p] = cs * wp - sn * wq;
+            Wm[r][q] = sn * wp + cs * wq;
+          }
+          for (int r = tid; r < n; r += blockDim.x) {
+            const double vp = Vm[r][p], vq = Vm[r][q];
+            Vm[r][p] = cs * vp - sn * vq;
+            Vm[r][q] = sn * vp + cs * vq;
+          }
+          if (tid == 0) rotated = 1;
+        }
+        __syncthreads();
+      }
+    }
+    if (!rotated) break;
+    __syncthreads();
+  }
+  // singular values = column norms of W; pinv[i][r] = sum_c V[i][c] * W[r][c] / s_c^2  (U = W / s)
+  __shared__ double sv[48];
+  for (int c = tid; c < n; c += blockDim.x) {
+    double a = 0.0;
+    for (int r = 0; r < m; ++r) a += Wm[r][c] * Wm[r][c];
+    sv[c] = sqrt(a);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * m; idx += blockDim.x) {
+    const int i = idx % n, r = idx / n;
+    double s = 0.0;
+    for (int c = 0; c < n; ++c) if (sv[c] > tol) s += Vm[i][c] * Wm[r][c] / (sv[c] * sv[c]);
+    out[(size_t)r * n + i] = s;
+  }
+}
+
+struct PredModel {
+  int n_alt;
+  int kind[PMAX];
+  double knot[PMAX];
+  double coef[PMAX];
+  double cov[PMAX * PMAX];   // row-major n_alt x n_alt
+  int has_null;
+  double null_coef, null_var;
+};
+
+// predict(type = "link", se.fit = TRUE) per cell (pullMARGESummary.R:66-69, pullNullSummary.R:69-72)
+__global__ void k_link_preds(PredModel M, const double* __restrict__ x, const double* __restrict__ sf, long long n,
+                             double* fit1, double* se1, double* fit0, double* se0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double X = r_round(x[i], 1e4);                 // marge2.R:154
+  const double off = sf ? log(1.0 / sf[i]) : 0.0;
+  if (M.n_alt > 0) {
+    double col[PMAX];
+    double eta = 0.0;
+    for (int j = 0; j < M.n_alt; ++j) {
+      double v;
+      if (M.kind[j] == SCLANE_TERM_INTERCEPT) v = 1.0;
+      else if (M.kind[j] == SCLANE_TERM_TP1) v = X > M.knot[j] ? X - M.knot[j] : 0.0;
+      else v = X < M.knot[j] ? M.knot[j] - X : 0.0;
+      col[j] = v;
+      eta += v * M.coef[j];
+    }
+    double q = 0.0;
+    for (int j = 0; j < M.n_alt; ++j)
+      for (int l = 0; l < M.n_alt; ++l) q += col[j] * M.cov[j * M.n_alt + l] * col[l];
+    if (fit1) fit1[i] = eta + off;
+    if (se1) se1[i] = sqrt(q);
+  } else {
+    if (fit1) fit1[i] = nan("");
+    if (se1) se1[i] = nan("");
+  }
+  if (M.has_null) {
+    if (fit0) fit0[i] = M.null_coef + off;
+    if (se0) se0[i] = sqrt(M.null_var);
+  } else {
+    if (fit0) fit0[i] = nan("");
+    if (se0) se0[i] = nan("");
+  }
+}
+
+// explicit-knot lineage plan for the single-step entry points
+bool plan_from_knots(const double* x, int64_t n, const double* knots, int n_knots, LineagePlan& P, char* errbuf, size_t errlen) {
+  if (n_knots < 1 || n_knots > SCLANE_TMAX) { set_err(errbuf, errlen, "n_knots must be in [1, %d]", SCLANE_TMAX); return false; }
+  for (int k = 1; k < n_knots; ++k) if (!(knots[k] >= knots[k - 1])) { set_err(errbuf, errlen, "knots must be ascending"); return false; }
+  Lineage& L = P.L;
+  std::memset(&L, 0, sizeof(L));
+  L.N = (int)n;
+  L.Npad = (int)((n + 127) / 128 * 128);
+  L.T = n_knots;
+  for (int k = 0; k < n_knots; ++k) L.knots[k] = knots[k];
+  L.ref[0] = L.knots[0];
+  for (int b = 1; b <= L.T; ++b) L.ref[b] = L.knots[b - 1];
+  std::vector<double> X((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (std::isnan(x[i])) { set_err(errbuf, errlen, "x must not contain NaN"); return false; }
+    X[(size_t)i] = r_round(x[i], 1e4);
+  }
+  std::vector<int32_t> order((size_t)n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return X[(size_t)a] < X[(size_t)b]; });
+  P.perm.assign(order.begin(), order.end());
+  P.u.assign((size_t)L.Npad, 0.0);
+  P.off.clear();
+  std::vector<int> cnt((size_t)L.T + 1, 0);
+  const double* kb = L.knots;
+  for (int64_t i = 0; i < n; ++i) {
+    const double xv = X[(size_t)order[(size_t)i]];
+    const int b = (int)(std::upper_bound(kb, kb + L.T, xv) - kb);
+    cnt[(size_t)b]++;
+    const double u = xv - L.ref[b];
+    P.u[(size_t)i] = u;
+    L.U0[b] += 1.0; L.U1[b] += u; L.U2[b] += u * u;
+  }
+  int acc = 0;
+  for (int b = 0; b <= L.T; ++b) { L.bstart[b] = acc; acc += cnt[(size_t)b]; }
+  for (int b = L.T + 1; b <= NBMAX; ++b) L.bstart[b] = acc;
+  return true;
+}
+
+bool model_from_terms(const int32_t* kind, const int32_t* knot_idx, int n_terms, int n_knots, Model& m, char* errbuf, size_t errlen) {
+  if (n_terms < 1 || n_terms > PMAX || kind[0] != SCLANE_TERM_INTERCEPT) { set_err(errbuf, errlen, "terms: 1..%d terms, intercept first", PMAX); return false; }
+  m.n = n_terms;
+  for (int j = 0; j < n_terms; ++j) {
+    m.kind[j] = kind[j];
+    m.knot[j] = j == 0 ? 0 : knot_idx[j];
+    if (j > 0 && (kind[j] < 1 || kind[j] > 2 || knot_idx[j] < 0 || knot_idx[j] >= n_knots)) { set_err(errbuf, errlen, "bad term %d", j); return false; }
+  }
+  return true;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// exported C ABI
+// =====================================================================================================
+extern "C" {
+
+int32_t sclane_abi_version(void) { return SCLANE_ABI_VERSION; }
+int32_t sclane_device_count(void) { return usable_devices(); }
+size_t sclane_record_size(void) { return sizeof(sclane_record); }
+int64_t sclane_launch_count(void) { return g_launches.load(); }
+void sclane_reset_launch_count(void) { g_launches.store(0); }
+
+void sclane_default_opts(sclane_opts* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->abi_version = SCLANE_ABI_VERSION;
+  o->mode = 0;
+  o->M = 5;
+  o->approx_knot = 1;
+  o->n_knot_max = 25;
+  o->minspan = -1;
+  o->tols_score = 1e-5;
+}
+
+void sclane_get_profile(sclane_profile* out) {
+  if (!out) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  *out = g_prof;
+}
+
+int32_t sclane_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
+                            const double* size_factor, const sclane_opts* opts, sclane_record* out,
+                            sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  return test_dynamic_impl(counts, nullptr, -1, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen);
+}
+
+int32_t sclane_test_dynamic_device(const int32_t* d_counts, int32_t device, int64_t n_cells, int64_t n_genes, const double* pt,
+                                   int32_t n_lineages, const double* size_factor, const sclane_opts* opts, sclane_record* out,
+                                   sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  return test_dynamic_impl(nullptr, d_counts, device, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen);
+}
+
+int32_t sclane_candidate_knots(const double* x, int64_t n, const sclane_opts* opts, double* knots_out, int32_t* minspan_out) {
+  if (!x || !opts || !knots_out || n < 1) return -SCLANE_ERR_ARG;
+  std::vector<double> xv(x, x + n), X;
+  for (double v : xv) if (std::isnan(v)) return -SCLANE_ERR_ARG;
+  int ms = 0;
+  std::vector<double> k = candidate_knots(xv, opts->approx_knot != 0, opts->n_knot_max, opts->minspan, &X, &ms);
+  if (minspan_out) *minspan_out = ms;
+  if ((int)k.size() > SCLANE_TMAX) return -SCLANE_ERR_UNSUPPORTED;
+  std::sort(k.begin(), k.end());
+  for (size_t i = 0; i < k.size(); ++i) knots_out[i] = k[i];
+  return (int32_t)k.size();
+}
+
+int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* x, const double* knots,
+                              int32_t n_knots, const int32_t* term_kind, const int32_t* term_knot_idx, int32_t n_terms,
+                              int32_t device, double* beta_out, double* sigma_out, double* mu_out, char* errbuf, size_t errlen) {
+  if (!counts || !x || !knots || !term_kind || !term_knot_idx || !beta_out || !sigma_out || n_cells < 1 || n_genes < 1) {
+    set_err(errbuf, errlen, "bad arguments"); return SCLANE_ERR_ARG;
+  }
+  if (usable_devices() <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
+  LineagePlan P;
+  Model m;
+  if (!plan_from_knots(x, n_cells, knots, n_knots, P, errbuf, errlen)) return SCLANE_ERR_ARG;
+  if (!model_from_terms(term_kind, term_knot_idx, n_terms, n_knots, m, errbuf, errlen)) return SCLANE_ERR_ARG;
+  try {
+    CK(cudaSetDevice(device));
+    cudaStream_t s = 0;
+    DevicePlan D;
+    D.upload(P, s);
+    const Lineage& L = P.L;
+    const int nb = (int)n_genes;
+    DevBuf<int> d_raw, d_ys; DevBuf<double> d_mu; DevBuf<GeneStats> d_stats; DevBuf<GeneOutDev> d_out;
+    d_raw.alloc((size_t)nb * n_cells); d_ys.alloc((size_t)nb * L.Npad); d_mu.alloc((size_t)nb * L.Npad); d_stats.alloc(nb); d_out.alloc(nb);
+    CK(cudaMemcpyAsync(d_raw.p, counts, (size_t)nb * n_cells * 4, cudaMemcpyHostToDevice, s));
+    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw.p, (long long)n_cells, D.perm.p, L.N, L.Npad, d_ys.p, d_stats.p, d_out.p, nb);
+    CK(cudaGetLastError()); g_launches.fetch_add(1);
+    std::vector<GeneOutDev> h((size_t)nb);
+    CK(cudaMemcpyAsync(h.data(), d_out.p, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (auto& g : h) g.st.fwd = m;                       // preset basis; fwd_iters = 0 => cold start
+    CK(cudaMemcpyAsync(d_out.p, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
+    StageArgs A;
+    A.lineage = D.lin.p; A.ys = d_ys.p; A.u = D.u.p; A.off = nullptr; A.mu = d_mu.p; A.stats = d_stats.p; A.out = d_out.p;
+    A.scores = nullptr; A.n_genes = nb; A.M = 5; A.tols_score = 1e-5; A.use_offset = 0;
+    launch_stage<STAGE_NULLSTATS>(A, s);
+    CK(cudaMemcpyAsync(h.data(), d_out.p, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
+    std::vector<double> hmu;
+    if (mu_out) { hmu.resize((size_t)nb * L.Npad); CK(cudaMemcpyAsync(hmu.data(), d_mu.p, hmu.size() * 8, cudaMemcpyDeviceToHost, s)); }
+    CK(cudaStreamSynchronize(s));
+    for (int g = 0; g < nb; ++g) {
+      const bool bad = (h[(size_t)g].st.error != 0);
+      for (int j = 0; j < n_terms; ++j) beta_out[(size_t)g * n_terms + j] = bad ? std::nan("") : h[(size_t)g].st.beta[j];
+      sigma_out[g] = bad ? std::nan("") : h[(size_t)g].st.sigma;
+      if (mu_out) for (int i = 0; i < L.N; ++i) mu_out[(size_t)g * n_cells + P.perm[(size_t)i]] = bad ? std::nan("") : hmu[(size_t)g * L.Npad + i];
+    }
+  } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }
+  return SCLANE_OK;
+}
+
+int32_t sclane_score_glm(const int32_t* counts, const double* mu, int64_t n_cells, int64_t n_genes, const double* x,
+                         const double* knots, int32_t n_knots, const int32_t* term_kind, const int32_t* term_knot_idx,
+                         int32_t n_terms, const double* sigma, int32_t device, double* scores_out, char* errbuf, size_t errlen) {
+  if (!counts || !mu || !x || !knots || !term_kind || !term_knot_idx || !sigma || !scores_out || n_cells < 1 || n_genes < 1) {
+    set_err(errbuf, errlen, "bad arguments"); return SCLANE_ERR_ARG;
+  }
+  if (usable_devices() <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
+  LineagePlan P;
+  Model m;
+  if (!plan_from_knots(x, n_cells, knots, n_knots, P, errbuf, errlen)) return SCLANE_ERR_ARG;
+  if (!model_from_terms(term_kind, term_knot_idx, n_terms, n_knots, m, errbuf, errlen)) return SCLANE_ERR_ARG;
+  try {
+    CK(cudaSetDevice(device));
+    cudaStream_t s = 0;
+    DevicePlan D;
+    D.upload(P, s);
+    const Lineage& L = P.L;
+    const int nb = (int)n_genes;
+    DevBuf<int> d_raw, d_ys; DevBuf<double> d_mu_raw, d_mu, d_scores; DevBuf<GeneStats> d_stats; DevBuf<GeneOutDev> d_out;
+    d_raw.alloc((size_t)nb * n_cells); d_ys.alloc((size_t)nb * L.Npad); d_mu_raw.alloc((size_t)nb * n_cells); d_mu.alloc((size_t)nb * L.Npad);
+    d_stats.alloc(nb); d_out.alloc(nb); d_scores.alloc((size_t)nb * 2 * L.T);
+    CK(cudaMemcpyAsync(d_raw.p, counts, (size_t)nb * n_cells * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_mu_raw.p, mu, (size_t)nb * n_cells * 8, cudaMemcpyHostToDevice, s));
+    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw.p, (long long)n_cells, D.perm.p, L.N, L.Npad, d_ys.p, d_stats.p, d_out.p, nb);
+    CK(cudaGetLastError()); g_launches.fetch_add(1);
+    k_gather_f64<<<nb, 256, 0, s>>>(d_mu_raw.p, (long long)n_cells, D.perm.p, L.N, L.Npad, d_mu.p, nb);
+    CK(cudaGetLastError()); g_launches.fetch_add(1);
+    std::vector<GeneOutDev> h((size_t)nb);
+    CK(cudaMemcpyAsync(h.data(), d_out.p, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int g = 0; g < nb; ++g) { h[(size_t)g].st.fwd = m; h[(size_t)g].st.sigma = sigma[g]; h[(size_t)g].st.error = 0; }
+    CK(cudaMemcpyAsync(d_out.p, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
+    StageArgs A;
+    A.lineage = D.lin.p; A.ys = d_ys.p; A.u = D.u.p; A.off = nullptr; A.mu = d_mu.p; A.stats = d_stats.p; A.out = d_out.p;
+    A.scores = d_scores.p; A.n_genes = nb; A.M = 99; A.tols_score = 1e-5; A.use_offset = 0;
+    launch_stage<STAGE_SCOREONLY>(A, s);
+    std::vector<double> hs((size_t)nb * 2 * L.T);
+    CK(cudaMemcpyAsync(hs.data(), d_scores.p, hs.size() * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::memcpy(scores_out, hs.data(), hs.size() * 8);
+  } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }
+  return SCLANE_OK;
+}
+
+int32_t sclane_link_preds(const sclane_record* rec, const double* x, int64_t n, const double* size_factor, int32_t device,
+                          double* marge_link_fit, double* marge_link_se, double* null_link_fit, double* null_link_se,
+                          char* errbuf, size_t errlen) {
+  if (!rec || !x || n < 1) { set_err(errbuf, errlen, "bad arguments"); return SCLANE_ERR_ARG; }
+  if (usable_devices() <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
+  PredModel M;
+  std::memset(&M, 0, sizeof(M));
+  if (rec->status & SCLANE_MARGE_OK) {
+    M.n_alt = rec->n_terms;
+    for (int j = 0; j < rec->n_terms; ++j) { M.kind[j] = rec->term_kind[j]; M.knot[j] = rec->term_knot[j]; M.coef[j] = rec->coef[j]; }
+    for (int j = 0; j < rec->n_terms * rec->n_terms; ++j) M.cov[j] = rec->cov[j];
+  }
+  if (rec->status & SCLANE_NULL_OK) { M.has_null = 1; M.null_coef = rec->null_coef; M.null_var = rec->null_se * rec->null_se; }
+  try {
+    CK(cudaSetDevice(device));
+    DevBuf<double> dx, dsf, o[4];
+    dx.alloc((size_t)n);
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+    if (size_factor) { dsf.alloc((size_t)n); CK(cudaMemcpy(dsf.p, size_factor, (size_t)n * 8, cudaMemcpyHostToDevice)); }
+    double* host[4] = {marge_link_fit, marge_link_se, null_link_fit, null_link_se};
+    for (int k = 0; k < 4; ++k) if (host[k]) o[k].alloc((size_t)n);
+    k_link_preds<<<(unsigned)((n + 255) / 256), 256>>>(M, dx.p, dsf.p, (long long)n, o[0].p, o[1].p, o[2].p, o[3].p);
+    CK(cudaGetLastError()); g_launches.fetch_add(1);
+    for (int k = 0; k < 4; ++k) if (host[k]) CK(cudaMemcpy(host[k], o[k].p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }
+  return SCLANE_OK;
+}
+
+int32_t sclane_matmul(const double* A, const double* B, double* C, int64_t m, int64_t k, int64_t n, int32_t device, char* errbuf, size_t errlen) {
+  if (!A || !B || !C || m < 1 || k < 1 || n < 1) { set_err(errbuf, errlen, "bad arguments"); return SCLANE_ERR_ARG; }
+  if (usable_devices() <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
+  try {
+    CK(cudaSetDevice(device));
+    DevBuf<double> dA, dB, dC;
+    dA.alloc((size_t)(m * k)); dB.alloc((size_t)(k * n)); dC.alloc((size_t)(m * n));
+    CK(cudaMemcpy(dA.p, A, (size_t)(m * k) * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB.p, B, (size_t)(k * n) * 8, cudaMemcpyHostToDevice));
+    dim3 grid((unsigned)((m + 15) / 16), (unsigned)((n + 15) / 16)), block(16, 16);
+    k_matmul<<<grid, block>>>(dA.p, dB.p, dC.p, (int)m, (int)k, (int)n);
+    CK(cudaGetLastError()); g_launches.fetch_add(1);
+    CK(cudaMemcpy(C, dC.p, (size_t)(m * n) * 8, cudaMemcpyDeviceToHost));
+  } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }
+  return SCLANE_OK;
+}
+
+int32_t sclane_llt_inverse(const double* A, double* Ainv, int64_t n, int32_t device, char* errbuf, size_t errlen) {
+  if (!A || !Ainv || n < 1 || n > 64) { set_err(errbuf, errlen, "bad arguments (1 <= n <= 64)"); return SCLANE_ERR_ARG; }
+  if (usable_devices() <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
+  try {
+    CK(cudaSetDevice(device));
+    DevBuf<double> dA, dI;
+    dA.alloc((size_t)(n * n)); dI.alloc((size_t)(n * n));
+    CK(cudaMemcpy(dA.p, A, (size_t)(n * n) * 8, cudaMemcpyHostToDevice));
+    k_llt_inverse<<<1, 64>>>(dA.p, dI.p, (int)n);
+    CK(cudaGetLastError()); g_launches.fetch_add(1);
+    CK(cudaMemcpy(Ainv, dI.p, (size_t)(n * n) * 8, cudaMemcpyDeviceToHost));
+  } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }
+  return SCLANE_OK;
+}
+
+int32_t sclane_pinv(const double* A, double* Apinv, int64_t m, int64_t n, double tolerance, int32_t device, char* errbuf, size_t errlen) {
+  if (!A || !Apinv || m < 1 || n < 1 || m > 48 || n > 48) { set_err(errbuf, errlen, "bad arguments (1 <= m, n <= 48)"); return SCLANE_ERR_ARG; }
+  if (usable_devices() <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
+  try {
+    CK(cudaSetDevice(device));
+    // the kernel wants a tall matrix; for a wide one use pinv(A) = pinv(A^T)^T
+    const bool wide = m < n;
+    const int64_t mm = wide ? n : m, nn = wide ? m : n;
+    std::vector<double> At;
+    const double* src = A;
+    if (wide) {
+      At.resize((size_t)(m * n));
+      for (int64_t r = 0; r < m; ++r) for (int64_t c = 0; c < n; ++c) At[(size_t)(r * n + c)] = A[(size_t)(c * m + r)];   // A^T (n x m) column-major
+      src = At.data();
+    }
+    DevBuf<double> dA, dP;
+    dA.alloc((size_t)(mm * nn)); dP.alloc((size_t)(mm * nn));
+    CK(cudaMemcpy(dA.p, src, (size_t)(mm * nn) * 8, cudaMemcpyHostToDevice));
+    k_pinv_tall<<<1, 64>>>(dA.p, dP.p, (int)mm, (int)nn, tolerance);
+    CK(cudaGetLastError()); g_launches.fetch_add(1);
+    std::vector<double> P((size_t)(mm * nn));
+    CK(cudaMemcpy(P.data(), dP.p, P.size() * 8, cudaMemcpyDeviceToHost));   // nn x mm column-major
+    if (!wide) std::memcpy(Apinv, P.data(), P.size() * 8);                  // n x m
+    else for (int64_t r = 0; r < n; ++r) for (int64_t c = 0; c < m; ++c) Apinv[(size_t)(c * n + r)] = P[(size_t)(r * nn + c)];   // transpose back: (m x n)^T
+  } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }
+  return SCLANE_OK;
+}
+
+}  // extern "C"

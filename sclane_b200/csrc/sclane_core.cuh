@@ -1,0 +1,1135 @@
+// sclane_core.cuh -- the per-gene algorithm of the path, written once for host and device.
+//
+// Everything a gene needs after its cells have been streamed is a function of PER-BUCKET
+// MOMENTS: the <= T candidate knots cut the (sorted) cells into T+1 buckets, and inside bucket b
+// every dictionary column (intercept, tp1(x,t_k), tp2(x,t_k); tp1.R:17, tp2.R:17) is affine in the
+// bucket-local coordinate u = x - ref_b:   column = alpha + gamma * u.  So X'WX, X'Wz, X'r of ANY
+// basis drawn from the dictionary are small sums over buckets of (sum w, sum w u, sum w u^2, ...).
+// A "pass" streams the gene's cells once and produces those moments; the fits below are
+// sequences of passes with O(T p^2) algebra in between.
+//
+// The code is templated on an executor E that owns the pass:
+//   E::pass<MODE>()  cooperative on device (one CTA per gene, sclane_device.cuh), a plain loop in
+//                    the host test harness (tests/host_emu) -- never in the product library.
+//   E::leader()/sync()  leader-only sections for the small algebra; all threads follow the same
+//                    control flow by reading the shared workspace after a sync.
+#pragma once
+#include "../../include/sclane_b200.h"
+#include "sclane_math.cuh"
+
+namespace sclane {
+
+constexpr int PMAX = SCLANE_PMAX;     // 7 columns
+constexpr int TMAX = SCLANE_TMAX;     // 32 knots
+constexpr int NBMAX = TMAX + 1;       // buckets
+constexpr int NACC = 7;               // per-bucket accumulators of a pass
+constexpr int NSC = 4;                // scalar accumulators of a pass
+constexpr int NSYS = PMAX + 1;        // joint (beta, log sigma) system
+constexpr double kSigmaPoisson = 1e-4;   // gamlss.dist dNBI -> Poisson switch (DESIGN.md rule 2)
+constexpr double kSigmaMax = 1e8;
+constexpr double kEpsGlm = 1e-8;         // glm.control(epsilon)
+constexpr int kMaxitGlm = 25;            // glm.control(maxit)
+constexpr int kMaxNewton = 60;
+
+enum PassMode : int {
+  PASS_FIT = 0,        // NBI joint-Newton pass: observed-information moments, score, sigma derivatives, loglik
+  PASS_IRLS = 1,       // glm.fit pass at eta = X beta + offset: Fisher moments, deviance, t0-sum, loglik
+  PASS_IRLS_START = 2, // glm.fit pass at family$initialize: mustart = y + (y == 0)/6
+  PASS_THETA = 3,      // theta.ml pass: score and information of theta at fixed mu
+  PASS_SWEEP = 4,      // score sweep pass: reads (y, mu) -> weighted/unweighted bucket moments
+  PASS_EMIT = 5        // writes mu = exp(eta) for the sweep
+};
+
+// Lineage geometry (gene independent; marge2.R:152-166 computed once per lineage, K0).
+struct Lineage {
+  int N;                 // cells in the lineage
+  int Npad;              // row stride of the sorted count matrix (multiple of 128)
+  int T;                 // candidate knots
+  double knots[TMAX];    // ascending
+  double ref[NBMAX];     // bucket reference point: ref[0] = knots[0], ref[b] = knots[b-1]
+  int bstart[NBMAX + 1]; // cell index range of bucket b in sorted order: [bstart[b], bstart[b+1])
+  double U0[NBMAX], U1[NBMAX], U2[NBMAX];   // unweighted moments: count, sum u, sum u^2
+};
+
+// alpha/gamma of dictionary column (kind, knot k) in bucket b.
+SC_HD void term_ab(const Lineage& L, int kind, int k, int b, double& al, double& ga) {
+  if (kind == SCLANE_TERM_INTERCEPT) { al = 1.0; ga = 0.0; }
+  else if (kind == SCLANE_TERM_TP1) {
+    if (b >= k + 1) { al = L.ref[b] - L.knots[k]; ga = 1.0; } else { al = 0.0; ga = 0.0; }
+  } else {
+    if (b <= k) { al = L.knots[k] - L.ref[b]; ga = -1.0; } else { al = 0.0; ga = 0.0; }
+  }
+}
+
+// A model: ordered list of terms (intercept first).
+struct Model {
+  int n;
+  int kind[PMAX];
+  int knot[PMAX];
+};
+
+// Per-gene constants gathered while the counts are sorted (k_gather_stats).
+struct GeneStats {
+  double sum_y, sum_y2, sum_ylogy, sum_lgamma_y1;
+  int ymax;
+  int pad;
+};
+
+// Shared workspace of one gene (shared memory on device).  The leader thread mutates it between
+// syncs; every thread reads it after a sync to take the same branches.
+struct Work {
+  // ---- pass inputs
+  double a[NBMAX], c[NBMAX];   // eta = a[b] + c[b] * u (+ offset)
+  double sigma;                // NB sigma = 1/theta; 0 => Poisson
+  double theta;                // 1/sigma (unused when sigma == 0)
+  int use_offset;
+  // ---- pass outputs
+  double acc[NBMAX][NACC];
+  double sc[NSC];
+  // ---- fit state
+  double beta[PMAX];
+  double s;                    // log sigma
+  int flag;                    // loop control broadcast
+  int flag2;
+  int passes;
+  // leader algebra scratch
+  double H[NSYS * NSYS];
+  double grad[NSYS];
+  double step[NSYS];
+  double cov[NSYS * NSYS];
+  // nb_mle (Newton) state
+  double nt_prev[NSYS];        // last accepted point (beta.., s)
+  double nt_ell_prev;
+  double nt_scale;
+  int nt_have_prev, nt_poisson, nt_converged;
+  // glm.fit2 state
+  double gf_devold, gf_dev, gf_coefold[PMAX], gf_G[PMAX * PMAX];
+  int gf_have_coefold, gf_ii, gf_conv;
+  // theta.ml state
+  double tm_theta, tm_del, tm_info;
+  int tm_notes;
+  // glm.nb alternation state
+  double nb_th, nb_Lm, nb_Lm0, nb_del, nb_dev, nb_se_th, nb_t0sum;
+  double nb_beta_stale[PMAX];
+  int nb_iter, nb_notes;
+  // backward pass state
+  Model bw_cur, bw_models[PMAX];
+  double bw_wic[PMAX], bw_cum;
+  // sweep scores (NaN = NA)
+  double sw_one[TMAX], sw_both[TMAX];
+  // misc broadcast
+  double bc[4];
+};
+
+// eta parameters per bucket from beta.
+SC_HD void set_eta(const Lineage& L, const Model& m, const double* beta, Work& W) {
+  for (int b = 0; b <= L.T; ++b) {
+    double a = 0.0, c = 0.0;
+    for (int j = 0; j < m.n; ++j) {
+      double al, ga;
+      term_ab(L, m.kind[j], m.knot[j], b, al, ga);
+      a += beta[j] * al;
+      c += beta[j] * ga;
+    }
+    W.a[b] = a;
+    W.c[b] = c;
+  }
+}
+
+// <d_j, d_l>_w from accumulators I0..I0+2 and <d_j, v> from I0, I0+1.
+SC_HD double gram2(const Lineage& L, const double (*acc)[NACC], int I0, int kj, int tj, int kl, int tl) {
+  double s = 0.0;
+  for (int b = 0; b <= L.T; ++b) {
+    double aj, gj, al, gl;
+    term_ab(L, kj, tj, b, aj, gj);
+    term_ab(L, kl, tl, b, al, gl);
+    s += aj * al * acc[b][I0] + (aj * gl + al * gj) * acc[b][I0 + 1] + gj * gl * acc[b][I0 + 2];
+  }
+  return s;
+}
+SC_HD double lin2(const Lineage& L, const double (*acc)[NACC], int I0, int kj, int tj) {
+  double s = 0.0;
+  for (int b = 0; b <= L.T; ++b) {
+    double aj, gj;
+    term_ab(L, kj, tj, b, aj, gj);
+    s += aj * acc[b][I0] + gj * acc[b][I0 + 1];
+  }
+  return s;
+}
+// unweighted versions from the lineage tables
+SC_HD double gram_u(const Lineage& L, int kj, int tj, int kl, int tl) {
+  double s = 0.0;
+  for (int b = 0; b <= L.T; ++b) {
+    double aj, gj, al, gl;
+    term_ab(L, kj, tj, b, aj, gj);
+    term_ab(L, kl, tl, b, al, gl);
+    s += aj * al * L.U0[b] + (aj * gl + al * gj) * L.U1[b] + gj * gl * L.U2[b];
+  }
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-cell contributions.  y: count, u: bucket-local coordinate, off: offset (0 if none),
+// a/c: eta parameters of the cell's bucket.  acc[NACC], sc[NSC] are the running sums.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double sigma, double theta,
+                        double mu_in, double* acc, double* sc, double& mu_out) {
+  const double y = (double)yi;
+  if (MODE == PASS_EMIT) {
+    mu_out = exp(a + c * u);
+    return;
+  }
+  if (MODE == PASS_SWEEP) {
+    // stat_out_score_glm_null.R:27-30 / score_fun_glm.R:40,44: w = mu^2/V, r = mu*VS = (y-mu)/(1+mu sigma)
+    const double inv = 1.0 / (1.0 + sigma * mu_in);
+    const double w = mu_in * inv, r = (y - mu_in) * inv;
+    acc[0] += w; acc[1] += w * u; acc[2] += w * u * u;
+    acc[3] += r; acc[4] += r * u;
+    acc[5] += y; acc[6] += y * u;
+    return;
+  }
+  if (MODE == PASS_FIT) {
+    const double eta = a + c * u;
+    const double mu = exp(eta);
+    if (sigma == 0.0) {   // Poisson
+      const double r = y - mu;
+      acc[0] += mu; acc[1] += mu * u; acc[2] += mu * u * u;
+      acc[3] += r; acc[4] += r * u;
+      sc[2] += y * eta - mu;
+      return;
+    }
+    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double r = (y - mu) * inv;                       // d l / d eta
+    const double o = mu * (1.0 + sigma * y) * inv * inv;   // - d2 l / d eta2
+    const double cc = sigma * mu * r * inv;                // - d2 l / d eta d(log sigma)
+    const double lg = log1p(sigma * mu);
+    const double g = psi_diff(yi, theta) - lg - sigma * r;                                   // d l / d theta
+    const double h = -tri_diff(yi, theta) + sigma - 2.0 * sigma * inv + sigma * (1.0 + sigma * y) * inv * inv;  // d2 l / d theta2
+    acc[0] += o; acc[1] += o * u; acc[2] += o * u * u;
+    acc[3] += r; acc[4] += r * u;
+    acc[5] += cc; acc[6] += cc * u;
+    sc[0] += g; sc[1] += h;
+    sc[2] += nb_lambda(yi, sigma, theta) + y * eta - (y + theta) * lg;
+    return;
+  }
+  if (MODE == PASS_IRLS || MODE == PASS_IRLS_START) {
+    double eta, mu;
+    if (MODE == PASS_IRLS_START) { mu = y + (yi == 0 ? 1.0 / 6.0 : 0.0); eta = log(mu); }   // negative.binomial()$initialize
+    else { eta = a + c * u + off; mu = exp(eta); }
+    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double w = mu * inv;                             // mu.eta^2 / variance(mu)
+    const double r = (y - mu) * inv;
+    const double wz = w * (eta - off) + r;                 // w * z, z = (eta - offset) + (y - mu)/mu.eta
+    acc[0] += w; acc[1] += w * u; acc[2] += w * u * u;
+    acc[3] += wz; acc[4] += wz * u;
+    const double lg = log1p(sigma * mu);
+    // dev.resids: 2 (y log(max(1,y)/mu) - (y+th) log((y+th)/(mu+th))); the y log y part is a gene constant
+    sc[0] += -y * eta - (y + theta) * (log1p(sigma * y) - lg);
+    const double e = (y - mu) / mu;
+    sc[1] += e * e;                                        // theta.ml start: n / sum((y/mu - 1)^2)
+    sc[2] += nb_lambda(yi, sigma, theta) + y * eta - (y + theta) * lg;   // glm.nb loglik() minus sum lgamma(y+1)
+    return;
+  }
+  if (MODE == PASS_THETA) {
+    const double eta = a + c * u + off;
+    const double mu = exp(eta);
+    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double r = (y - mu) * inv;
+    const double lg = log1p(sigma * mu);
+    sc[0] += psi_diff(yi, theta) - lg - sigma * r;                                            // theta.ml score
+    sc[1] += tri_diff(yi, theta) - sigma + 2.0 * sigma * inv - sigma * (1.0 + sigma * y) * inv * inv;  // theta.ml info
+    return;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NB maximum-likelihood fit of y ~ B - 1 (no offset): stands in for gamlss NBI
+// (stat_out_score_glm_null.R:22-25, backward_sel_WIC.R:44-47).  Joint Newton on (beta, log sigma)
+// with the observed information and a log-likelihood backtracking guard; sigma is clamped at
+// kSigmaPoisson, and if the optimum sits on that bound with the likelihood still increasing towards
+// sigma -> 0 the fit is Poisson (sigma := 0, DESIGN.md rule 2).
+// On return W.acc / W.sc hold the last pass (taken at the pre-final-step point), W.beta / W.sigma /
+// W.s the estimate.
+// ---------------------------------------------------------------------------------------------
+struct FitResult {
+  int converged;
+  int poisson;
+};
+
+// Build -H (joint observed information) and the gradient from a PASS_FIT result.
+SC_HD void build_newton_system(const Lineage& L, const Model& m, Work& W, bool sigma_free) {
+  const int p = m.n;
+  for (int j = 0; j < p; ++j) {
+    for (int l = 0; l <= j; ++l) {
+      double v = gram2(L, W.acc, 0, m.kind[j], m.knot[j], m.kind[l], m.knot[l]);
+      W.H[j * NSYS + l] = v;
+      W.H[l * NSYS + j] = v;
+    }
+    W.grad[j] = lin2(L, W.acc, 3, m.kind[j], m.knot[j]);
+  }
+  if (sigma_free) {
+    const double th = W.theta;
+    const double G = W.sc[0], Hh = W.sc[1];
+    const double d1 = -th * G;                  // d l / d s,  s = log sigma
+    const double d2 = th * G + th * th * Hh;    // d2 l / d s2
+    for (int j = 0; j < p; ++j) {
+      double v = lin2(L, W.acc, 5, m.kind[j], m.knot[j]);   // - d2 l / d beta_j d s
+      W.H[j * NSYS + p] = v;
+      W.H[p * NSYS + j] = v;
+    }
+    W.H[p * NSYS + p] = -d2;
+    W.grad[p] = d1;
+  }
+}
+
+// One leader-side Newton decision after a PASS_FIT.  Sets W.flag = 1 when the iteration is over.
+SC_HD void nb_mle_step(const Lineage& L, const Model& m, Work& W, double smin, double smax) {
+  const int p = m.n;
+  const bool pois = W.nt_poisson != 0;
+  const double ell = W.sc[2];
+  bool accept;
+  if (W.nt_have_prev) accept = (ell >= W.nt_ell_prev - 1e-10 * (fabs(W.nt_ell_prev) + 1.0));   // false for NaN
+  else accept = (ell == ell) && !isinf(ell);
+  if (!accept) {
+    if (!W.nt_have_prev || W.nt_scale < 1e-6) {
+      W.flag = 1;                                   // cannot improve: stay at the last accepted point
+      if (W.nt_have_prev) {
+        for (int j = 0; j < p; ++j) W.beta[j] = W.nt_prev[j];
+        if (!pois) W.s = W.nt_prev[p];
+      }
+    } else {                                        // halve the last step and retry
+      W.nt_scale *= 0.5;
+      for (int j = 0; j < p; ++j) W.beta[j] = W.nt_prev[j] + W.nt_scale * W.step[j];
+      if (!pois) {
+        double s = W.nt_prev[p] + W.nt_scale * W.step[p];
+        W.s = s < smin ? smin : (s > smax ? smax : s);
+      }
+    }
+    return;
+  }
+  W.nt_have_prev = 1;
+  W.nt_ell_prev = ell;
+  const bool sigma_free = !pois;
+  build_newton_system(L, m, W, sigma_free);
+  // active-set treatment of the bounds on s
+  const bool at_lo = sigma_free && (W.s <= smin) && (W.grad[p] < 0.0);
+  const bool at_hi = sigma_free && (W.s >= smax) && (W.grad[p] > 0.0);
+  const bool s_moves = sigma_free && !at_lo && !at_hi;
+  double Lm[NSYS * NSYS];
+  bool ok = false;
+  if (s_moves) {
+    for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+    ok = chol_factor<NSYS>(p + 1, Lm);
+    if (ok) chol_solve<NSYS>(p + 1, Lm, W.grad, W.step);
+  }
+  if (!ok) {
+    // beta block alone (always used when s is fixed); safeguarded 1-D Newton on s otherwise
+    for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+    const bool okb = chol_factor<NSYS>(p, Lm);
+    if (okb) chol_solve<NSYS>(p, Lm, W.grad, W.step);
+    else { for (int j = 0; j < p; ++j) W.step[j] = 0.0; W.flag = 1; }   // singular information: stop here
+    W.step[p] = 0.0;
+    if (s_moves) {
+      const double d2 = W.H[p * NSYS + p];
+      W.step[p] = d2 > 0.0 ? W.grad[p] / d2 : (W.grad[p] > 0.0 ? 1.0 : -1.0);
+    }
+  }
+  // step limits: |delta s| <= 2, |delta beta_j| <= 5
+  double scale = 1.0;
+  if (s_moves && fabs(W.step[p]) > 2.0) scale = 2.0 / fabs(W.step[p]);
+  for (int j = 0; j < p; ++j) if (fabs(W.step[j]) * scale > 5.0) scale = 5.0 / fabs(W.step[j]);
+  if (scale < 1.0) for (int j = 0; j <= p; ++j) W.step[j] *= scale;
+  double gain = 0.0, dmax = 0.0;
+  for (int j = 0; j < p; ++j) {
+    gain += W.grad[j] * W.step[j];
+    const double d = fabs(W.step[j]) / (1.0 + fabs(W.beta[j]));
+    if (d > dmax) dmax = d;
+  }
+  if (s_moves) { gain += W.grad[p] * W.step[p]; if (fabs(W.step[p]) > dmax) dmax = fabs(W.step[p]); }
+  for (int j = 0; j < p; ++j) W.nt_prev[j] = W.beta[j];
+  W.nt_prev[p] = W.s;
+  W.nt_scale = 1.0;
+  const bool conv = (dmax <= 1e-8) || (0.5 * gain <= 1e-13 * (1.0 + fabs(ell)));
+  for (int j = 0; j < p; ++j) W.beta[j] += W.step[j];
+  if (s_moves) {
+    const double s = W.s + W.step[p];
+    W.s = s < smin ? smin : (s > smax ? smax : s);
+  }
+  if (conv && W.flag == 0) {
+    if (at_lo) {            // optimum on the sigma = kSigmaPoisson bound, d l/d s < 0: Poisson regime
+      W.nt_poisson = 1;
+      W.nt_have_prev = 0;
+    } else {
+      W.flag = 1;
+      W.nt_converged = 1;
+    }
+  }
+}
+
+template <class E>
+SC_HDN FitResult nb_mle(E& ex, const Lineage& L, const Model& m, const GeneStats& gs, Work& W, bool warm) {
+  const int p = m.n;
+  const double smin = log(kSigmaPoisson), smax = log(kSigmaMax);
+  ex.sync();
+  if (ex.leader()) {
+    if (!warm) {
+      const double ybar = gs.sum_y / (double)L.N;
+      for (int j = 0; j < p; ++j) W.beta[j] = 0.0;
+      W.beta[0] = log(ybar);
+      const double var = (gs.sum_y2 - gs.sum_y * ybar) / (double)(L.N > 1 ? L.N - 1 : 1);
+      double sg = (var - ybar) / (ybar * ybar);
+      if (!(sg > 0.1)) sg = 0.1;               // gamlss NBI initial sigma: max(.., 0.1)
+      W.s = log(sg);
+    }
+    if (!(W.s >= smin)) W.s = smin;
+    if (W.s > smax) W.s = smax;
+    W.flag = 0;
+    W.nt_poisson = 0;
+    W.nt_have_prev = 0;
+    W.nt_converged = 0;
+    W.nt_scale = 1.0;
+    W.use_offset = 0;
+  }
+  ex.sync();
+  for (int it = 0; it < kMaxNewton; ++it) {
+    if (ex.leader()) {
+      set_eta(L, m, W.beta, W);
+      if (W.nt_poisson) { W.sigma = 0.0; W.theta = 0.0; }
+      else { W.sigma = exp(W.s); W.theta = 1.0 / W.sigma; }
+      W.passes++;
+    }
+    ex.sync();
+    ex.template pass<PASS_FIT>();
+    if (ex.leader()) {
+#ifdef SCLANE_EMU_DEBUG
+      printf("  it %d ell=%.10g s=%g pois=%d beta=%g %g %g %g | scale=%g\n", it, W.sc[2], W.s, W.nt_poisson, W.beta[0], W.beta[1], W.beta[2], W.beta[3], W.nt_scale);
+#endif
+      nb_mle_step(L, m, W, smin, smax);
+    }
+    ex.sync();
+    if (W.flag) break;
+  }
+  FitResult res;
+  res.converged = W.nt_converged;
+  res.poisson = W.nt_poisson;
+  ex.sync();
+  if (ex.leader()) {
+    if (W.nt_poisson) { W.sigma = 0.0; W.theta = 0.0; }
+    else { W.sigma = exp(W.s); W.theta = 1.0 / W.sigma; }
+  }
+  ex.sync();
+  return res;
+}
+
+// Wald statistics of the non-intercept columns from the last PASS_FIT of nb_mle
+// (backward_sel_WIC.R:47-52).  Leader only.  out[0..p-2].
+SC_HD void wald_from_fit(const Lineage& L, const Model& m, Work& W, bool poisson, double* out) {
+  const int p = m.n;
+  build_newton_system(L, m, W, !poisson);
+  const int n = poisson ? p : p + 1;
+  double Lm[NSYS * NSYS];
+  for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+  if (!chol_factor<NSYS>(n, Lm)) {
+    for (int j = 1; j < p; ++j) out[j - 1] = nan("");
+    return;
+  }
+  chol_inverse<NSYS>(n, Lm, W.cov);
+  for (int j = 1; j < p; ++j) {
+    const double var = W.cov[j * NSYS + j];
+    if (poisson) out[j - 1] = W.beta[j] / var;                  // fallback branch: coef / sqrt(diag)^2
+    else out[j - 1] = (W.beta[j] * W.beta[j]) / var;            // (coef / se)^2
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Score sweep algebra (score_fun_glm.R:32-50 for all T knots x {one, both}) from PASS_SWEEP moments.
+// ---------------------------------------------------------------------------------------------
+// Rule 1: exact structural rank check standing in for fastLmPure's NA coefficients.
+SC_HD bool cand_collinear(const Lineage& L, const Model& m, int k, bool both) {
+  bool has_pair = false;
+  for (int j = 1; j < m.n; ++j) {
+    const double tj = L.knots[m.knot[j]];
+    if (tj == L.knots[k] && (m.kind[j] == SCLANE_TERM_TP1 || both)) return true;   // duplicated column
+    if (m.kind[j] == SCLANE_TERM_TP1)
+      for (int l = 1; l < m.n; ++l)
+        if (m.kind[l] == SCLANE_TERM_TP2 && L.knots[m.knot[l]] == tj) has_pair = true;
+  }
+  return both && has_pair;
+}
+
+// A = (B'WB)^-1 via Eigen-style LLT semantics is only needed for well-conditioned B (p <= PMAX);
+// a plain Cholesky inverse is used (the reference's eigenMapMatrixInvert on a PD matrix).
+// Leader computes Ainv into W.cov (NSYS stride); returns false if not PD.
+SC_HD bool sweep_prepare(const Lineage& L, const Model& m, Work& W) {
+  const int p = m.n;
+  double Lm[NSYS * NSYS];
+  for (int j = 0; j < p; ++j)
+    for (int l = 0; l <= j; ++l) {
+      double v = gram2(L, W.acc, 0, m.kind[j], m.knot[j], m.kind[l], m.knot[l]);
+      Lm[j * NSYS + l] = v;
+      Lm[l * NSYS + j] = v;
+    }
+  if (p == 1) { W.cov[0] = 1.0 / Lm[0]; return true; }      // stat_out_score_glm_null.R:33-34
+  if (!chol_factor<NSYS>(p, Lm)) return false;
+  chol_inverse<NSYS>(p, Lm, W.cov);
+  return true;
+}
+
+// score of candidate knot k; both = pair (tp1, tp2) else tp1 only.  Any thread may call it after
+// sweep_prepare + sync.  NaN = NA.
+SC_HD double sweep_score(const Lineage& L, const Model& m, const Work& W, int k, bool both) {
+  if (cand_collinear(L, m, k, both)) return nan("");
+  const int p = m.n;
+  const int c = both ? 2 : 1;
+  double C[2][PMAX], D[2], bvec[2];
+  for (int q = 0; q < c; ++q) {
+    const int kind = q == 0 ? SCLANE_TERM_TP1 : SCLANE_TERM_TP2;
+    for (int j = 0; j < p; ++j) C[q][j] = gram2(L, W.acc, 0, m.kind[j], m.knot[j], kind, k);
+    D[q] = gram2(L, W.acc, 0, kind, k, kind, k);
+    bvec[q] = lin2(L, W.acc, 3, kind, k);
+  }
+  // S = D - C' A C  (the 2x2 D is diagonal: tp1 * tp2 == 0)
+  double S[2][2] = {{0, 0}, {0, 0}};
+  for (int q = 0; q < c; ++q)
+    for (int r = 0; r <= q; ++r) {
+      double t = 0.0;
+      for (int j = 0; j < p; ++j) {
+        double aj = 0.0;
+        for (int l = 0; l < p; ++l) aj += W.cov[j * NSYS + l] * C[r][l];
+        t += C[q][j] * aj;
+      }
+      S[q][r] = (q == r ? D[q] : 0.0) - t;
+    }
+  return llt_quadform(c, S[0][0], S[1][0], S[1][1], bvec[0], bvec[1]);
+}
+
+// R helpers over score vectors (NaN = NA)
+SC_HD double rmax_na(const double* v, int n) {
+  double m = -INFINITY;
+  for (int i = 0; i < n; ++i) if (v[i] == v[i] && v[i] > m) m = v[i];
+  return m;
+}
+SC_HD bool all_na(const double* v, int n) {
+  for (int i = 0; i < n; ++i) if (v[i] == v[i]) return false;
+  return true;
+}
+SC_HD int which_max_round6(const double* v, int n, bool last) {
+  double m = -INFINITY;
+  int idx = -1;
+  for (int i = 0; i < n; ++i) {
+    if (!(v[i] == v[i])) continue;
+    double r = r_round(v[i], 1e6);
+    if (r > m || idx < 0) { m = r; idx = i; }
+    else if (last && r == m) idx = i;
+  }
+  return idx;
+}
+
+// The selection tree of marge2.R:368-587 (q = 1).  one/both: additive score vectors; in_set: 0 for the
+// first iteration (interaction scores are the constant -1e5, :244), 1 afterwards (the "interaction with
+// the intercept" scores duplicate the additive ones, :247-307).  Returns false for the breakFlag exit;
+// else trunc_type (1|2) and knot index (may be -1 = R subscript error).
+SC_HD bool select_candidate(const double* one, const double* both, int T, int in_set, int& trunc_type, int& kidx) {
+  double one_int_c[TMAX], both_int_c[TMAX];
+  for (int i = 0; i < T; ++i) {
+    one_int_c[i] = in_set ? one[i] : -1e5;
+    both_int_c[i] = in_set ? both[i] : -1e5;
+  }
+  const double* one_int = one_int_c;
+  const double* both_int = both_int_c;
+  const bool bi_na = all_na(both_int, T), oi_na = all_na(one_int, T);
+  const bool ba_na = all_na(both, T), oa_na = all_na(one, T);
+  const double mx_bi = rmax_na(both_int, T), mx_oi = rmax_na(one_int, T);
+  const double mx_ba = rmax_na(both, T), mx_oa = rmax_na(one, T);
+#define SEL(tt, vec, last) do { trunc_type = (tt); kidx = which_max_round6((vec), T, (last)); return true; } while (0)
+  if (bi_na && oi_na) {                                            // :368
+    if (!ba_na && !oa_na) { if (mx_ba > mx_oa) SEL(2, both, true); SEL(1, one, true); }
+    if (ba_na && !oa_na) SEL(1, one, false);
+    if (!ba_na && oa_na) SEL(2, one, false);                       // sic (:386): all-NA vector -> error
+    return false;
+  }
+  if (bi_na && !oi_na) {                                           // :392
+    if (ba_na) {
+      if (oa_na) SEL(1, one_int, true);
+      if (mx_oi > mx_oa) SEL(1, one_int, true);
+      SEL(1, one, false);
+    }
+    if (mx_oi > mx_ba) { if (mx_oi > mx_oa) SEL(1, one_int, true); SEL(1, one, true); }
+    if (mx_ba <= mx_oa) SEL(1, one, false);
+    SEL(2, both, false);
+  }
+  if (!bi_na && oi_na) {                                           // :443
+    if (ba_na) { if (mx_bi > mx_oa) SEL(2, both_int, true); SEL(1, one, false); }
+    if (mx_bi > mx_ba) SEL(2, both_int, true);
+    if (mx_ba <= mx_oa) SEL(1, one, false);
+    SEL(2, both, false);
+  }
+  if (mx_bi > mx_oi) {                                             // :494
+    if (!ba_na) {
+      if (mx_ba >= mx_bi) { if (mx_ba > mx_oa) SEL(2, both, false); SEL(1, one, false); }
+      if (mx_bi > mx_oa) SEL(2, both_int, true);
+      SEL(1, one, false);
+    }
+    if (mx_oa >= mx_bi) SEL(1, one, false);
+    SEL(2, both_int, true);
+  }
+  if (!ba_na) {                                                    // :538
+    if (mx_ba >= mx_oi) { if (mx_ba <= mx_oa) SEL(1, one, false); SEL(2, both, false); }
+    if (mx_oi > mx_oa) SEL(1, one_int, true);
+    SEL(1, one, false);
+  }
+  if (oa_na) SEL(1, one_int, true);
+  if (mx_oa >= mx_oi) SEL(1, one, false);
+  SEL(1, one_int, true);
+#undef SEL
+}
+
+// stat_out() (stat_out.R:23-47) for basis m from the unweighted moments: returns GCVq1 (rounded to 10 dp)
+// or NaN when B'B is not PD.  ytb: <column_j, y>.
+SC_HD double stat_out_gcvq1(const Lineage& L, const Model& m, const Work& W, const GeneStats& gs) {
+  const int p = m.n;
+  double Lm[NSYS * NSYS], bty[NSYS], coef[NSYS];
+  for (int j = 0; j < p; ++j) {
+    for (int l = 0; l <= j; ++l) {
+      double v = gram_u(L, m.kind[j], m.knot[j], m.kind[l], m.knot[l]);
+      Lm[j * NSYS + l] = v;
+      Lm[l * NSYS + j] = v;
+    }
+    bty[j] = lin2(L, W.acc, 5, m.kind[j], m.knot[j]);
+  }
+  if (!chol_factor<NSYS>(p, Lm)) return nan("");
+  chol_solve<NSYS>(p, Lm, bty, coef);
+  double fit2 = 0.0;
+  for (int j = 0; j < p; ++j) fit2 += coef[j] * bty[j];
+  const double N = (double)L.N;
+  const double ybar = gs.sum_y / N;
+  const double TSS = gs.sum_y2 - gs.sum_y * ybar;
+  const double GCVnull = TSS / (N * (1.0 - 1.0 / N) * (1.0 - 1.0 / N));
+  const double RSS = gs.sum_y2 - fit2;
+  const double df1a = (double)p + 2.0 * (double)(p - 1) / 2.0;
+  const double GCV1 = RSS / (N * (1.0 - df1a / N) * (1.0 - df1a / N));
+  return r_round(1.0 - GCV1 / GCVnull, 1e10);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-gene state carried between the kernels of the path.
+// ---------------------------------------------------------------------------------------------
+struct GeneState {
+  Model fwd;            // forward-pass basis so far
+  double beta[PMAX];    // last forward null fit (warm start)
+  double sigma;         // sigma of the last forward null fit (0 = Poisson)
+  double s;             // log sigma for warm starts
+  int fwd_done;         // forward pass finished (stop reason in fwd_stop)
+  int fwd_stop;
+  int m_count;          // marge2's m (1, 3, 5, ...)
+  int error;            // SCLANE_NOTE_* bits accumulated
+  int fwd_iters;
+  int passes;
+  double fwd_score[4];
+  double fwd_sigma[4];
+  Model fin;            // final model after the backward pass
+  double wic[PMAX];
+  int n_wic;
+};
+
+// Forward-iteration bookkeeping after a sweep (marge2.R:589-758).  Leader only.  `one`/`both` hold the
+// T scores.  Returns nothing; updates gs (basis, stop flags).
+SC_HD void forward_update(const Lineage& L, GeneState& st, Work& W, const GeneStats& gstat,
+                          const double* one, const double* both, int M, double tols_score) {
+  const int it = st.fwd_iters;
+  st.fwd_iters++;
+  int trunc_type = 0, kidx = -1;
+  const int in_set = st.fwd.n > 1 ? 1 : 0;
+  if (!select_candidate(one, both, L.T, in_set, trunc_type, kidx)) { st.fwd_done = 1; st.fwd_stop = 1; return; }
+  if (kidx < 0) { st.fwd_done = 1; st.fwd_stop = 5; st.error |= SCLANE_NOTE_NUMERIC; return; }
+  const bool pair = trunc_type == 2;
+  const double score2 = pair ? both[kidx] : one[kidx];   // recomputation of the chosen score (:665-675) is the same number
+  if (it < 4) st.fwd_score[it] = score2;
+  if (!(score2 == score2)) { st.fwd_done = 1; st.fwd_stop = 5; st.error |= SCLANE_NOTE_NUMERIC; return; }   // if (NA) -> error
+  Model cand = st.fwd;
+  cand.kind[cand.n] = SCLANE_TERM_TP1; cand.knot[cand.n] = kidx; cand.n++;
+  if (pair) { cand.kind[cand.n] = SCLANE_TERM_TP2; cand.knot[cand.n] = kidx; cand.n++; }
+  const double gcvq1 = stat_out_gcvq1(L, cand, W, gstat);
+  if (!(gcvq1 == gcvq1)) { st.fwd_done = 1; st.fwd_stop = 5; st.error |= SCLANE_NOTE_NUMERIC; return; }
+  if (gcvq1 < -10.0 || r_round(score2, 1e4) <= 0.0) { st.fwd_done = 1; st.fwd_stop = 2; return; }   // :681
+  if (score2 < tols_score) { st.fwd_done = 1; st.fwd_stop = 3; return; }                              // :737
+  for (int j = st.fwd.n; j < cand.n; ++j) st.beta[j] = 0.0;
+  st.fwd = cand;
+  st.m_count += 2;
+  if (L.N <= st.fwd.n + 2 || st.m_count >= M || st.fwd.n + 2 > PMAX) { st.fwd_done = 1; st.fwd_stop = 4; }   // :756
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward pass (marge2.R:763-812) -- a chain of NB refits + Wald statistics.
+// ---------------------------------------------------------------------------------------------
+SC_HD double nanmin(const double* v, int n) {
+  double m = INFINITY;
+  for (int i = 0; i < n; ++i) if (v[i] == v[i] && v[i] < m) m = v[i];
+  return m;
+}
+
+template <class E>
+SC_HDN void backward_pass(E& ex, const Lineage& L, const GeneStats& gstat, GeneState& st, Work& W) {
+  // st and W are visible to all threads; the leader mutates them between syncs.
+  const int ncol = st.fwd.n;
+  ex.sync();
+  if (ncol <= 2) {            // marge2.R:777 / :788 subscript error -> "MARGE model error"
+    if (ex.leader()) { st.error |= SCLANE_NOTE_FWD_EMPTY; st.fin.n = 0; }
+    ex.sync();
+    return;
+  }
+  if (ex.leader()) {
+    W.bw_cur = st.fwd;
+    W.bw_models[0] = st.fwd;
+    W.bw_cum = 0.0;
+    for (int j = 0; j < ncol; ++j) W.beta[j] = st.beta[j];   // warm start: last forward null fit, new columns at 0
+    W.s = st.s;
+  }
+  ex.sync();
+  for (int i = 1; i <= ncol - 1; ++i) {
+    FitResult fr = nb_mle(ex, L, W.bw_cur, gstat, W, true);
+    if (ex.leader()) {
+      double wald[PMAX];
+#ifdef SCLANE_EMU_DEBUG
+      printf("bw step %d: n=%d conv=%d pois=%d sigma=%g beta0=%g passes=%d\n", i, W.bw_cur.n, fr.converged, fr.poisson, W.sigma, W.beta[0], W.passes);
+#endif
+      const Model cur = W.bw_cur;
+      wald_from_fit(L, cur, W, fr.poisson != 0, wald);
+      const int nw = cur.n - 1;
+      const double mn = nanmin(wald, nw);
+      W.bw_cum += mn;
+      W.bw_wic[i - 1] = W.bw_cum + 2.0 * (double)cur.n;
+      if (i != ncol - 1) {
+        // variable.lowest: first column attaining the minimum (:781,:791); drop it, keep the rest as warm start
+        int low = 0;
+        for (int j = 0; j < nw; ++j) if (wald[j] == mn) { low = j; break; }
+        const int drop = low + 1;
+        Model nxt;
+        nxt.n = 0;
+        for (int j = 0; j < cur.n; ++j) if (j != drop) {
+          nxt.kind[nxt.n] = cur.kind[j]; nxt.knot[nxt.n] = cur.knot[j]; nxt.n++;
+        }
+        W.bw_cur = nxt;
+        // the reduced model restarts from the intercept-only point (hinge coefficients of the larger
+        // model are a poor start once a correlated column is gone); log sigma carries over
+        for (int j = 0; j < PMAX; ++j) W.beta[j] = 0.0;
+        W.beta[0] = log(gstat.sum_y / (double)L.N);
+        if (fr.poisson) W.s = log(kSigmaPoisson);
+      } else {
+        W.bw_cur.n = 1;                       // survivor renamed "Intercept" (:798-799)
+      }
+      W.bw_models[i] = W.bw_cur;
+    }
+    ex.sync();
+  }
+  if (ex.leader()) {
+    // which.min(WIC_vec_2): entry 1 is NA (the full model can never win); first minimum, NaN skipped
+    int best = -1;
+    double bm = INFINITY;
+    for (int i = 0; i < ncol - 1; ++i)
+      if (W.bw_wic[i] == W.bw_wic[i] && (best < 0 || W.bw_wic[i] < bm)) { bm = W.bw_wic[i]; best = i; }
+    st.n_wic = ncol - 1;
+    for (int i = 0; i < ncol - 1; ++i) st.wic[i] = W.bw_wic[i];
+    if (best < 0) { st.error |= SCLANE_NOTE_NUMERIC; st.fin.n = 0; }
+    else {
+      const Model sel = W.bw_models[best + 1];
+      // B[, colnames(B) %in% cnames]: forward order, duplicates dropped (:805-812)
+      Model fin;
+      fin.n = 0;
+      for (int j = 0; j < st.fwd.n; ++j) {
+        bool in = false;
+        for (int l = 0; l < sel.n; ++l) if (sel.kind[l] == st.fwd.kind[j] && sel.knot[l] == st.fwd.knot[j]) in = true;
+        for (int l = 0; l < fin.n; ++l) if (fin.kind[l] == st.fwd.kind[j] && fin.knot[l] == st.fwd.knot[j]) in = false;
+        if (in) { fin.kind[fin.n] = st.fwd.kind[j]; fin.knot[fin.n] = st.fwd.knot[j]; fin.n++; }
+      }
+      st.fin = fin;
+    }
+  }
+  ex.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
+// MASS::glm.nb(..., method = "glm.fit2", init.theta = 1, link = log) (marge2.R:841-847,
+// testDynamic.R:254-260): schedule restated from MASS::glm.nb / theta.ml / stats::glm.fit + the glm2
+// step-halving addition (third-party sources, not in the reference tree; pinned by the golden).
+// ---------------------------------------------------------------------------------------------
+struct NbResult {
+  double coef[PMAX];
+  double cov[PMAX * PMAX];   // (X'WX)^-1 of the last WLS solve, row-major p x p (stride PMAX)
+  double theta, se_theta, loglik, deviance;
+  int notes;
+  int alternations, irls_iters;
+  int ok;
+};
+
+// Solve the WLS normal equations of a PASS_IRLS result: G beta = X'Wz.  Leader only.  beta -> W.step,
+// G -> W.gf_G.  false if G is not positive definite or the solution is not finite.
+SC_HD bool wls_from_pass(const Lineage& L, const Model& m, Work& W) {
+  const int p = m.n;
+  double Lm[NSYS * NSYS], z[NSYS];
+  for (int j = 0; j < p; ++j) {
+    for (int l = 0; l <= j; ++l) {
+      double v = gram2(L, W.acc, 0, m.kind[j], m.knot[j], m.kind[l], m.knot[l]);
+      Lm[j * NSYS + l] = v; Lm[l * NSYS + j] = v;
+      W.gf_G[j * PMAX + l] = v; W.gf_G[l * PMAX + j] = v;
+    }
+    z[j] = lin2(L, W.acc, 3, m.kind[j], m.knot[j]);
+  }
+  if (!chol_factor<NSYS>(p, Lm)) return false;
+  chol_solve<NSYS>(p, Lm, z, W.step);
+  for (int j = 0; j < p; ++j) if (!(W.step[j] == W.step[j]) || isinf(W.step[j])) return false;
+  return true;
+}
+
+SC_HD double dev_from_pass(const GeneStats& gstat, const Work& W) { return 2.0 * (gstat.sum_ylogy + W.sc[0]); }
+
+// stats::glm.fit (+ glm2 step-halving) with family negative.binomial(theta, link = log).
+// On entry W.acc / W.sc hold the pass at the starting point (etastart or mustart) under this theta.
+// On exit: W.beta = coefficients, W.acc / W.sc = pass at the final point, W.gf_dev = deviance,
+// W.gf_G = X'WX of the last solve, W.gf_conv = converged.  Returns the number of iterations, or -1
+// on a hard failure ("no valid set of coefficients", non-PD normal equations).
+template <class E>
+SC_HDN int glm_fit2(E& ex, const Lineage& L, const Model& m, const GeneStats& gstat, Work& W, double theta) {
+  const int p = m.n;
+  ex.sync();
+  if (ex.leader()) {
+    W.gf_devold = dev_from_pass(gstat, W);
+    W.gf_have_coefold = 0;        // glm.fit: coefold <- NULL (etastart/mustart start, no `start`)
+    W.gf_conv = 0;
+    W.flag = 0;
+  }
+  ex.sync();
+  int it;
+  for (it = 1; it <= kMaxitGlm; ++it) {
+    if (ex.leader()) {
+      if (!wls_from_pass(L, m, W)) W.flag = 2;
+      else {
+        for (int j = 0; j < p; ++j) W.beta[j] = W.step[j];
+        set_eta(L, m, W.beta, W);
+        W.sigma = 1.0 / theta; W.theta = theta;
+        W.passes++;
+      }
+    }
+    ex.sync();
+    if (W.flag == 2) return -1;
+    ex.template pass<PASS_IRLS>();
+    // (1) non-finite deviance: halve towards coefold until finite
+    if (ex.leader()) { W.gf_dev = dev_from_pass(gstat, W); W.gf_ii = 1; }
+    ex.sync();
+    for (;;) {
+      if (ex.leader()) {
+        const bool finite = (W.gf_dev == W.gf_dev) && !isinf(W.gf_dev);
+        W.flag2 = 0;
+        if (!finite) {
+          if (!W.gf_have_coefold || W.gf_ii > kMaxitGlm) W.flag = 2;
+          else {
+            W.gf_ii++;
+            for (int j = 0; j < p; ++j) W.beta[j] = 0.5 * (W.beta[j] + W.gf_coefold[j]);
+            set_eta(L, m, W.beta, W);
+            W.passes++;
+            W.flag2 = 1;
+          }
+        }
+      }
+      ex.sync();
+      if (W.flag == 2) return -1;
+      if (!W.flag2) break;
+      ex.template pass<PASS_IRLS>();
+      if (ex.leader()) W.gf_dev = dev_from_pass(gstat, W);
+      ex.sync();
+    }
+    // (2) glm2: deviance went up -> halve until it goes down
+    if (ex.leader()) {
+      W.gf_ii = 1;
+      W.bc[0] = ((W.gf_dev - W.gf_devold) / (0.1 + fabs(W.gf_dev)) >= kEpsGlm && it > 1 && W.gf_have_coefold) ? 1.0 : 0.0;
+    }
+    ex.sync();
+    if (W.bc[0] != 0.0) {
+      for (;;) {
+        if (ex.leader()) {
+          W.flag2 = 0;
+          if ((W.gf_dev - W.gf_devold) / (0.1 + fabs(W.gf_dev)) > -kEpsGlm && W.gf_ii <= kMaxitGlm) {
+            W.gf_ii++;
+            for (int j = 0; j < p; ++j) W.beta[j] = 0.5 * (W.beta[j] + W.gf_coefold[j]);
+            set_eta(L, m, W.beta, W);
+            W.passes++;
+            W.flag2 = 1;
+          }
+        }
+        ex.sync();
+        if (!W.flag2) break;
+        ex.template pass<PASS_IRLS>();
+        if (ex.leader()) W.gf_dev = dev_from_pass(gstat, W);
+        ex.sync();
+      }
+    }
+    // (3) convergence
+    if (ex.leader()) {
+      if (fabs(W.gf_dev - W.gf_devold) / (fabs(W.gf_dev) + 0.1) < kEpsGlm) { W.gf_conv = 1; W.flag = 1; }
+      else {
+        W.gf_devold = W.gf_dev;
+        for (int j = 0; j < p; ++j) W.gf_coefold[j] = W.beta[j];
+        W.gf_have_coefold = 1;
+      }
+    }
+    ex.sync();
+    if (W.flag == 1) break;
+  }
+  ex.sync();
+  return it > kMaxitGlm ? kMaxitGlm : it;
+}
+
+// MASS::theta.ml(y, mu, n, limit = 25, eps = .Machine$double.eps^0.25).  mu is defined by the eta
+// parameters currently in W.a / W.c (+ offset).  Result: W.tm_theta, W.tm_info (-> SE), W.tm_notes.
+template <class E>
+SC_HDN void theta_ml(E& ex, const Lineage& L, Work& W, double t0sum) {
+  const double eps = 1.220703125e-4;     // 2^-13 = .Machine$double.eps^0.25
+  ex.sync();
+  if (ex.leader()) {
+    W.tm_theta = (double)L.N / t0sum;
+    W.tm_info = nan("");
+    W.tm_del = 1.0;
+    W.flag = 0;
+  }
+  ex.sync();
+  int it = 0;
+  for (;;) {
+    ++it;
+    if (ex.leader()) {
+      if (!(it < kMaxitGlm && fabs(W.tm_del) > eps)) W.flag = 1;
+      else {
+        W.tm_theta = fabs(W.tm_theta);
+        W.theta = W.tm_theta;
+        W.sigma = 1.0 / W.theta;
+        W.passes++;
+      }
+    }
+    ex.sync();
+    if (W.flag) break;
+    ex.template pass<PASS_THETA>();
+    if (ex.leader()) {
+      W.tm_del = W.sc[0] / W.sc[1];
+      W.tm_theta += W.tm_del;
+      W.tm_info = W.sc[1];
+    }
+    ex.sync();
+  }
+  if (ex.leader()) {
+    int notes = 0;
+    if (W.tm_theta < 0.0) { W.tm_theta = 0.0; notes |= SCLANE_NOTE_TH_TRUNC; }
+    if (it == kMaxitGlm) notes |= SCLANE_NOTE_TH_ITER_LIMIT;
+    W.tm_notes = notes;
+  }
+  ex.sync();
+}
+
+// glm.nb.  `out` is written by the leader only.
+template <class E>
+SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gstat, Work& W, bool use_offset, NbResult* out) {
+  const int p = m.n;
+  const double N = (double)L.N;
+  const double d1 = sqrt(2.0 * fmax(1.0, N - (double)p));
+  ex.sync();
+  if (ex.leader()) {
+    W.use_offset = use_offset ? 1 : 0;
+    W.sigma = 1.0; W.theta = 1.0;       // init.theta = 1
+    for (int b = 0; b <= L.T; ++b) { W.a[b] = 0.0; W.c[b] = 0.0; }
+    W.passes++;
+    out->ok = 0;
+    out->notes = 0;
+  }
+  ex.sync();
+  ex.template pass<PASS_IRLS_START>();
+  int irls = glm_fit2(ex, L, m, gstat, W, 1.0);
+  if (irls < 0) return;
+  // th <- theta.ml(Y, mu) at the fresh mu of the initial fit
+  const double t0sum0 = W.sc[1];
+  theta_ml(ex, L, W, t0sum0);
+  if (ex.leader()) {
+    W.nb_th = W.tm_theta;
+    W.nb_se_th = W.tm_info;
+    W.nb_notes = W.tm_notes;
+    W.nb_dev = W.gf_dev;
+    for (int j = 0; j < p * PMAX; ++j) out->cov[j] = W.gf_G[j];
+    // pass at (beta, th): gives Lm and doubles as the starting pass of the next glm.fit
+    W.theta = W.nb_th; W.sigma = 1.0 / W.nb_th;
+    set_eta(L, m, W.beta, W);
+    W.passes++;
+  }
+  ex.sync();
+  ex.template pass<PASS_IRLS>();
+  if (ex.leader()) {
+    W.nb_Lm = W.sc[2] - gstat.sum_lgamma_y1;
+    W.nb_Lm0 = W.nb_Lm + 2.0 * d1;
+    W.nb_del = 1.0;
+    W.nb_iter = 0;
+  }
+  ex.sync();
+  for (;;) {
+    if (ex.leader()) {
+      W.nb_iter++;
+      W.flag = !(W.nb_iter <= kMaxitGlm && (fabs(W.nb_Lm0 - W.nb_Lm) / d1 + fabs(W.nb_del)) > kEpsGlm) ? 1 : 0;
+      if (!W.flag) {
+        for (int j = 0; j < p; ++j) W.nb_beta_stale[j] = W.beta[j];
+        W.nb_t0sum = W.sc[1];
+      }
+    }
+    ex.sync();
+    if (W.flag) break;
+    const double th_cur = W.nb_th;
+    const int r = glm_fit2(ex, L, m, gstat, W, th_cur);
+    if (r < 0) return;
+    irls += r;
+    if (ex.leader()) {
+      W.nb_dev = W.gf_dev;
+      for (int j = 0; j < p * PMAX; ++j) out->cov[j] = W.gf_G[j];
+      set_eta(L, m, W.nb_beta_stale, W);          // theta.ml at the PREVIOUS mu (MASS quirk)
+    }
+    ex.sync();
+    theta_ml(ex, L, W, W.nb_t0sum);
+    if (ex.leader()) {
+      const double t0 = W.nb_th;
+      W.nb_th = W.tm_theta;
+      W.nb_se_th = W.tm_info;
+      W.nb_notes = W.tm_notes;
+      W.nb_del = t0 - W.nb_th;
+      set_eta(L, m, W.beta, W);
+      W.theta = W.nb_th; W.sigma = 1.0 / W.nb_th;
+      W.passes++;
+    }
+    ex.sync();
+    ex.template pass<PASS_IRLS>();
+    if (ex.leader()) {
+      W.nb_Lm0 = W.nb_Lm;
+      W.nb_Lm = W.sc[2] - gstat.sum_lgamma_y1;
+    }
+    ex.sync();
+  }
+  if (ex.leader()) {
+    out->ok = 1;
+    out->irls_iters = irls;
+    for (int j = 0; j < p; ++j) out->coef[j] = W.beta[j];
+    out->theta = W.nb_th;
+    const double info = W.nb_se_th;
+    out->se_theta = (info == info && info > 0.0) ? sqrt(1.0 / info) : nan("");
+    out->loglik = W.nb_Lm;
+    out->deviance = W.nb_dev;
+    int notes = W.nb_notes;
+    if (W.nb_iter > kMaxitGlm) notes = SCLANE_NOTE_ALT_LIMIT;
+    if (!W.gf_conv) notes |= SCLANE_NOTE_NOT_CONVERGED;
+    out->notes = notes;
+    out->alternations = W.nb_iter - 1;
+    // out->cov holds G = X'WX of the last solve: invert for (X'WX)^-1
+    double Lm[NSYS * NSYS], inv[NSYS * NSYS];
+    for (int j = 0; j < p; ++j) for (int l = 0; l < p; ++l) Lm[j * NSYS + l] = out->cov[j * PMAX + l];
+    if (chol_factor<NSYS>(p, Lm)) {
+      chol_inverse<NSYS>(p, Lm, inv);
+      for (int j = 0; j < p; ++j) for (int l = 0; l < p; ++l) out->cov[j * PMAX + l] = inv[j * NSYS + l];
+    } else {
+      for (int j = 0; j < p * PMAX; ++j) out->cov[j] = nan("");
+    }
+  }
+  ex.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
+// The four per-gene stages as the kernels run them (K1 forward null fit, K2 score sweep,
+// K4 backward pass, K5 final + null glm.nb).  `st` and `W` are CTA-shared on device.
+// ---------------------------------------------------------------------------------------------
+struct ScoreFn {
+  const Lineage* L;
+  const Model* m;
+  Work* W;
+  SC_HD void operator()(int i) const {
+    const int T = L->T;
+    if (i < T) W->sw_one[i] = sweep_score(*L, *m, *W, i, false);
+    else if (i < 2 * T) W->sw_both[i - T] = sweep_score(*L, *m, *W, i - T, true);
+  }
+};
+
+// K1: stat_out_score_glm_null() (stat_out_score_glm_null.R:18-48) for the current forward basis:
+// NB fit, then mu is written out for the sweep.
+template <class E>
+SC_HDN void gene_forward_fit(E& ex, const Lineage& L, const GeneStats& gstat, GeneState& st, Work& W) {
+  ex.sync();
+  if (st.fwd_done || st.error) return;
+  const bool warm = st.fwd_iters > 0;   // later iterations start from the previous null fit (new columns at 0)
+  if (ex.leader()) {
+    for (int j = 0; j < st.fwd.n; ++j) W.beta[j] = st.beta[j];
+    W.s = st.s;
+  }
+  ex.sync();
+  FitResult fr = nb_mle(ex, L, st.fwd, gstat, W, warm);
+  if (ex.leader()) {
+    for (int j = 0; j < st.fwd.n; ++j) st.beta[j] = W.beta[j];
+    st.sigma = fr.poisson ? 0.0 : W.sigma;
+    st.s = fr.poisson ? log(kSigmaPoisson) : W.s;
+    if (st.fwd_iters < 4) st.fwd_sigma[st.fwd_iters] = st.sigma;
+    set_eta(L, st.fwd, W.beta, W);
+    W.passes++;
+  }
+  ex.sync();
+  ex.template pass<PASS_EMIT>();
+}
+
+// K2: the score sweep (score_fun_glm.R:21-54 for every knot and both candidate shapes), the
+// selection tree, the stat_out check and the forward bookkeeping (marge2.R:182-758).
+template <class E>
+SC_HDN void gene_sweep(E& ex, const Lineage& L, const GeneStats& gstat, GeneState& st, Work& W, int M, double tols_score) {
+  ex.sync();
+  if (st.fwd_done || st.error) return;
+  if (ex.leader()) {
+    W.sigma = st.sigma;
+    W.theta = st.sigma > 0.0 ? 1.0 / st.sigma : 0.0;
+    W.use_offset = 0;
+    W.passes++;
+  }
+  ex.sync();
+  ex.template pass<PASS_SWEEP>();
+  if (ex.leader()) W.flag = sweep_prepare(L, st.fwd, W) ? 1 : 0;
+  ex.sync();
+  if (!W.flag) {
+    if (ex.leader()) { st.error |= SCLANE_NOTE_NUMERIC; st.fwd_done = 1; st.fwd_stop = 5; }
+    ex.sync();
+    return;
+  }
+  ScoreFn fn{&L, &st.fwd, &W};
+  ex.par_for(2 * L.T, fn);
+  ex.sync();
+  if (ex.leader()) forward_update(L, st, W, gstat, W.sw_one, W.sw_both, M, tols_score);
+  ex.sync();
+}
+
+// K4
+template <class E>
+SC_HDN void gene_backward(E& ex, const Lineage& L, const GeneStats& gstat, GeneState& st, Work& W) {
+  ex.sync();
+  if (st.error) { if (ex.leader()) st.fin.n = 0; ex.sync(); return; }
+  backward_pass(ex, L, gstat, st, W);
+}
+
+// K5: final glm.nb on the selected basis (marge2.R:841-847) and the intercept-only null glm.nb
+// (testDynamic.R:254-260), both with the size-factor offset when one is given.
+template <class E>
+SC_HDN void gene_final(E& ex, const Lineage& L, const GeneStats& gstat, GeneState& st, Work& W, bool use_offset,
+                       NbResult* alt, NbResult* null) {
+  ex.sync();
+  if (ex.leader()) { alt->ok = 0; null->ok = 0; alt->notes = 0; null->notes = 0; }
+  ex.sync();
+  if (st.error & SCLANE_NOTE_ALL_ZERO) return;
+  if (ex.leader()) { W.bw_cur.n = 1; W.bw_cur.kind[0] = SCLANE_TERM_INTERCEPT; W.bw_cur.knot[0] = 0; }
+  ex.sync();
+  glm_nb(ex, L, W.bw_cur, gstat, W, use_offset, null);
+  ex.sync();
+  if (st.fin.n < 1 || (st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC))) return;
+  if (st.fin.n == 1) {
+    // intercept-only alternative: the same fit as the null model (LRT is exactly 0, modelLRT.R:48-50)
+    if (ex.leader()) *alt = *null;
+    ex.sync();
+    return;
+  }
+  glm_nb(ex, L, st.fin, gstat, W, use_offset, alt);
+}
+
+}  // namespace sclane

@@ -1,0 +1,314 @@
+// sclane_device.cuh -- the CUDA executor of a pass and the per-stage kernels (sm_100a).
+//
+// Mapping: one CTA per gene (grid = genes of the batch, >> 148 SMs for every config of interest),
+// 8 warps per CTA.  The gene's cells are sorted by pseudotime, so the <= 33 knot buckets are
+// contiguous index ranges: each warp streams a contiguous run of 128-cell tiles with 128-bit
+// coalesced loads (int4 counts, double2 x2 coordinates / offsets / means), keeps the running
+// bucket's moments in registers, and only at a bucket boundary (<= 33 + 8 times per pass) does a
+// warp-shuffle reduction into its private shared-memory slot.  Slots are combined across warps in a
+// fixed order, so every sum is bit-reproducible run to run and across GPU counts.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sclane_core.cuh"
+
+namespace sclane {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int MODE> struct PassTraits;
+template <> struct PassTraits<PASS_FIT>        { static constexpr int NA = 7, NS = 3; };
+template <> struct PassTraits<PASS_IRLS>       { static constexpr int NA = 5, NS = 3; };
+template <> struct PassTraits<PASS_IRLS_START> { static constexpr int NA = 5, NS = 3; };
+template <> struct PassTraits<PASS_THETA>      { static constexpr int NA = 0, NS = 2; };
+template <> struct PassTraits<PASS_SWEEP>      { static constexpr int NA = 7, NS = 0; };
+template <> struct PassTraits<PASS_EMIT>       { static constexpr int NA = 0, NS = 0; };
+
+struct DevExec {
+  Work* W;
+  const Lineage* L;
+  const int* __restrict__ y;        // sorted counts of this gene, row padded to Npad
+  const double* __restrict__ u;     // [Npad] bucket-local coordinate (shared by all genes)
+  const double* __restrict__ off;   // [Npad] offset or nullptr
+  double* mu;                       // [Npad] fitted means of this gene (sweep input / emit output)
+  double (*slot)[NBMAX][NACC];      // [kWarps] warp-private partial moments
+  double (*scw)[NSC];               // [kWarps] warp-private partial scalars
+
+  __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  template <class F>
+  __device__ __forceinline__ void par_for(int n, F f) const {
+    for (int i = threadIdx.x; i < n; i += kThreads) f(i);
+  }
+
+  template <int MODE>
+  __device__ __noinline__ void pass() {
+    constexpr int NA = PassTraits<MODE>::NA;
+    constexpr int NS = PassTraits<MODE>::NS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Lineage& Lr = *L;
+    const int N = Lr.N, T = Lr.T;
+    const double sigma = W->sigma, theta = W->theta;
+    const bool use_off = (MODE == PASS_IRLS || MODE == PASS_IRLS_START || MODE == PASS_THETA) && W->use_offset && off != nullptr;
+    double* myslot = &slot[warp][0][0];
+    if (NA > 0) {
+      for (int i = lane; i < (T + 1) * NACC; i += 32) myslot[i] = 0.0;
+      __syncwarp();
+    }
+    double acc[NACC], sc[NSC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NSC; ++k) sc[k] = 0.0;
+
+    const int ntiles = (N + 127) >> 7;
+    const int t0 = (int)(((long long)ntiles * warp) / kWarps);
+    const int t1 = (int)(((long long)ntiles * (warp + 1)) / kWarps);
+    if (t0 < t1) {
+      int cur_b = 0;
+      const int first = t0 << 7;
+      while (cur_b < T && Lr.bstart[cur_b + 1] <= first) ++cur_b;
+      double a = W->a[cur_b], c = W->c[cur_b];
+      int b_hi = Lr.bstart[cur_b + 1];
+      for (int t = t0; t < t1; ++t) {
+        const int tile_lo = t << 7;
+        const int i0 = tile_lo + (lane << 2);
+        const int4 y4 = __ldg(reinterpret_cast<const int4*>(y + i0));
+        const double2 ua = __ldg(reinterpret_cast<const double2*>(u + i0));
+        const double2 ub = __ldg(reinterpret_cast<const double2*>(u + i0 + 2));
+        const int yv[4] = {y4.x, y4.y, y4.z, y4.w};
+        const double uv[4] = {ua.x, ua.y, ub.x, ub.y};
+        double ov[4] = {0.0, 0.0, 0.0, 0.0};
+        double mv[4] = {0.0, 0.0, 0.0, 0.0};
+        if (use_off) {
+          const double2 oa = __ldg(reinterpret_cast<const double2*>(off + i0));
+          const double2 ob = __ldg(reinterpret_cast<const double2*>(off + i0 + 2));
+          ov[0] = oa.x; ov[1] = oa.y; ov[2] = ob.x; ov[3] = ob.y;
+        }
+        if (MODE == PASS_SWEEP) {
+          const double2 ma = *reinterpret_cast<const double2*>(mu + i0);
+          const double2 mb = *reinterpret_cast<const double2*>(mu + i0 + 2);
+          mv[0] = ma.x; mv[1] = ma.y; mv[2] = mb.x; mv[3] = mb.y;
+        }
+        const int tile_end = min(tile_lo + 128, N);
+        if (tile_lo + 128 <= b_hi && tile_lo + 128 <= N) {
+          // whole tile inside the running bucket: no masks
+          double mo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cell_contrib<MODE>(yv[j], uv[j], ov[j], a, c, sigma, theta, mv[j], acc, sc, mo[j]);
+          if (MODE == PASS_EMIT) {
+            *reinterpret_cast<double2*>(mu + i0) = make_double2(mo[0], mo[1]);
+            *reinterpret_cast<double2*>(mu + i0 + 2) = make_double2(mo[2], mo[3]);
+          }
+        } else {
+          // tile straddles a bucket boundary (or is the ragged last tile): masked, bucket by bucket
+          for (;;) {
+            const int lo = Lr.bstart[cur_b];
+            const int hi = min(b_hi, tile_end);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i0 + j;
+              if (i >= lo && i < hi) {
+                double mo;
+                cell_contrib<MODE>(yv[j], uv[j], ov[j], a, c, sigma, theta, mv[j], acc, sc, mo);
+                if (MODE == PASS_EMIT) mu[i] = mo;
+              }
+            }
+            if (hi >= tile_end) break;
+            if (NA > 0) {
+#pragma unroll
+              for (int k = 0; k < NA; ++k) {
+                const double v = warp_sum(acc[k]);
+                if (lane == 0) myslot[cur_b * NACC + k] += v;
+                acc[k] = 0.0;
+              }
+            }
+            ++cur_b;
+            a = W->a[cur_b]; c = W->c[cur_b];
+            b_hi = Lr.bstart[cur_b + 1];
+          }
+        }
+      }
+      if (NA > 0) {
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+          const double v = warp_sum(acc[k]);
+          if (lane == 0) myslot[cur_b * NACC + k] += v;
+        }
+      }
+    }
+    if (NS > 0) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        const double v = warp_sum(sc[k]);
+        if (lane == 0) scw[warp][k] = v;
+      }
+    }
+    __syncthreads();
+    if (NA > 0) {
+      double* out = &W->acc[0][0];
+      for (int i = threadIdx.x; i < (T + 1) * NACC; i += kThreads) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += (&slot[w][0][0])[i];
+        out[i] = s;
+      }
+    }
+    if (NS > 0 && threadIdx.x < NS) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += scw[w][threadIdx.x];
+      W->sc[threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------------------------
+struct GeneOutDev {
+  GeneState st;
+  NbResult alt, null;
+};
+
+struct StageArgs {
+  const Lineage* lineage;      // device copy
+  const int* ys;               // [B][Npad] sorted counts
+  const double* u;             // [Npad]
+  const double* off;           // [Npad] or nullptr
+  double* mu;                  // [B][Npad]
+  const GeneStats* stats;      // [B]
+  GeneOutDev* out;             // [B]
+  double* scores;              // optional [B][2][T] dump of the sweep scores, or nullptr
+  int n_genes;
+  int M;
+  double tols_score;
+  int use_offset;
+};
+
+enum Stage : int { STAGE_FWD_FIT = 0, STAGE_SWEEP = 1, STAGE_BACKWARD = 2, STAGE_FINAL = 3, STAGE_NULLSTATS = 4, STAGE_SCOREONLY = 5 };
+
+template <int STAGE>
+__global__ void __launch_bounds__(kThreads) k_stage(StageArgs A) {
+  __shared__ Work W;
+  __shared__ Lineage Ls;
+  __shared__ GeneState st;
+  __shared__ GeneStats gs;
+  __shared__ double slot[kWarps][NBMAX][NACC];
+  __shared__ double scw[kWarps][NSC];
+  const int g = blockIdx.x;
+  if (g >= A.n_genes) return;
+  {
+    // cooperative word copies of the small per-lineage / per-gene structs
+    const int* src = reinterpret_cast<const int*>(A.lineage);
+    int* dst = reinterpret_cast<int*>(&Ls);
+    for (int i = threadIdx.x; i < (int)(sizeof(Lineage) / sizeof(int)); i += kThreads) dst[i] = src[i];
+    const int* s2 = reinterpret_cast<const int*>(&A.out[g].st);
+    int* d2 = reinterpret_cast<int*>(&st);
+    for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kThreads) d2[i] = s2[i];
+    const int* s3 = reinterpret_cast<const int*>(&A.stats[g]);
+    int* d3 = reinterpret_cast<int*>(&gs);
+    for (int i = threadIdx.x; i < (int)(sizeof(GeneStats) / sizeof(int)); i += kThreads) d3[i] = s3[i];
+    int* w = reinterpret_cast<int*>(&W);
+    for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kThreads) w[i] = 0;
+  }
+  __syncthreads();
+  const size_t row = (size_t)g * (size_t)Ls.Npad;
+  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw};
+  if (STAGE == STAGE_FWD_FIT || STAGE == STAGE_NULLSTATS) {
+    gene_forward_fit(ex, Ls, gs, st, W);
+  } else if (STAGE == STAGE_SWEEP || STAGE == STAGE_SCOREONLY) {
+    gene_sweep(ex, Ls, gs, st, W, A.M, A.tols_score);
+    if (A.scores != nullptr) {
+      __syncthreads();
+      double* o = A.scores + (size_t)g * 2 * Ls.T;
+      for (int i = threadIdx.x; i < Ls.T; i += kThreads) { o[i] = W.sw_one[i]; o[Ls.T + i] = W.sw_both[i]; }
+    }
+  } else if (STAGE == STAGE_BACKWARD) {
+    gene_backward(ex, Ls, gs, st, W);
+  } else if (STAGE == STAGE_FINAL) {
+    gene_final(ex, Ls, gs, st, W, A.use_offset != 0, &A.out[g].alt, &A.out[g].null);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) st.passes += W.passes;
+  __syncthreads();
+  {
+    int* d2 = reinterpret_cast<int*>(&A.out[g].st);
+    const int* s2 = reinterpret_cast<const int*>(&st);
+    for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kThreads) d2[i] = s2[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0b: apply the lineage's sort permutation to a batch of genes and gather the per-gene constants
+// (replaces the per-gene `expr.mat[lineage_cells, i]` column extraction of testDynamic.R:190).
+// raw: [B][ld] gene-major counts in the caller's cell order; ys: [B][Npad] sorted, zero padded.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_gather_stats(const int* __restrict__ raw, long long ld, const int* __restrict__ perm,
+                                                           int N, int Npad, int* __restrict__ ys, GeneStats* __restrict__ stats,
+                                                           GeneOutDev* __restrict__ out, int n_genes) {
+  const int g = blockIdx.x;
+  if (g >= n_genes) return;
+  const int* src = raw + (size_t)g * (size_t)ld;
+  int* dst = ys + (size_t)g * (size_t)Npad;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+  int ymax = 0;
+  for (int i = threadIdx.x; i < Npad; i += kThreads) {
+    int v = 0;
+    if (i < N) v = __ldg(src + __ldg(perm + i));
+    dst[i] = v;
+    if (v > 0) {
+      const double d = (double)v;
+      s1 += d; s2 += d * d;
+      if (v > 1) { s3 += d * log(d); s4 += lgamma(d + 1.0); }
+      ymax = max(ymax, v);
+    }
+  }
+  __shared__ double red[kWarps][4];
+  __shared__ int redm[kWarps];
+  s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3); s4 = warp_sum(s4);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[warp][0] = s1; red[warp][1] = s2; red[warp][2] = s3; red[warp][3] = s4; redm[warp] = ymax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    GeneStats gs;
+    gs.sum_y = gs.sum_y2 = gs.sum_ylogy = gs.sum_lgamma_y1 = 0.0;
+    gs.ymax = 0; gs.pad = 0;
+    for (int w = 0; w < kWarps; ++w) {
+      gs.sum_y += red[w][0]; gs.sum_y2 += red[w][1]; gs.sum_ylogy += red[w][2]; gs.sum_lgamma_y1 += red[w][3];
+      gs.ymax = max(gs.ymax, redm[w]);
+    }
+    stats[g] = gs;
+    GeneState st;
+    int* z = reinterpret_cast<int*>(&st);
+    for (int i = 0; i < (int)(sizeof(GeneState) / sizeof(int)); ++i) z[i] = 0;
+    st.fwd.n = 1;
+    st.fwd.kind[0] = SCLANE_TERM_INTERCEPT;
+    st.m_count = 1;
+    if (gs.sum_y == 0.0) st.error |= SCLANE_NOTE_ALL_ZERO;
+    out[g].st = st;
+    out[g].alt.ok = 0;
+    out[g].null.ok = 0;
+  }
+}
+
+// gather of a double matrix by the same permutation (sclane_score_glm: mu in caller order -> sorted)
+__global__ void k_gather_f64(const double* __restrict__ raw, long long ld, const int* __restrict__ perm, int N, int Npad,
+                             double* __restrict__ dst, int n_genes) {
+  const int g = blockIdx.x;
+  if (g >= n_genes) return;
+  for (int i = threadIdx.x; i < Npad; i += blockDim.x)
+    dst[(size_t)g * Npad + i] = i < N ? raw[(size_t)g * ld + perm[i]] : 0.0;
+}
+
+}  // namespace sclane

@@ -1,0 +1,294 @@
+// sclane_host.hpp -- host-side pieces of the path (plain C++17, no CUDA):
+//   K0: candidate knots + pseudotime sort + bucket tables per lineage (marge2.R:150-173,
+//       min_span.R:15-36, max_span.R:14-26), gene independent, so done once per lineage;
+//   record finalisation: z / p-values, LRT, DF rule and pchisq (modelLRT.R:43-53,
+//       pullMARGESummary.R:70-98, pullNullSummary.R:66-80).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "sclane_core.cuh"
+
+namespace sclane {
+
+// ---- R scalar semantics ------------------------------------------------------------------------
+inline double r_round_digits(double x, int digits) { return r_round(x, std::pow(10.0, digits)); }
+
+inline double r_signif(double x, int digits) {           // nmath/fprec.c for ordinary magnitudes
+  if (x == 0.0 || !std::isfinite(x)) return x;
+  const int e10 = digits - 1 - (int)std::floor(std::log10(std::fabs(x)));
+  if (e10 >= 0) { const double p = std::pow(10.0, e10); return std::nearbyint(x * p) / p; }
+  const double p = std::pow(10.0, -e10);
+  return std::nearbyint(x / p) * p;
+}
+
+// stats::quantile(type = 7) on an unsorted copy (marge2.R:158-159)
+inline double quantile7(std::vector<double> xs, double p) {
+  std::sort(xs.begin(), xs.end());
+  const size_t n = xs.size();
+  const double index = 1.0 + (double)(n > 0 ? n - 1 : 0) * p;
+  const size_t lo = (size_t)std::floor(index), hi = (size_t)std::ceil(index);
+  double q = xs[lo - 1];
+  const double h = index - (double)lo;
+  if (index > (double)lo && xs[hi - 1] != q) q = (1.0 - h) * q + h * xs[hi - 1];
+  return q;
+}
+
+// min_span.R:15-36 (values that would be NA in R -- index past the end -- are simply not produced:
+// the later intersect() drops them anyway)
+inline std::vector<double> min_span(const std::vector<double>& X, int q, int minspan_in, int* minspan_out) {
+  const size_t n = X.size();
+  std::vector<double> x(X);
+  std::sort(x.begin(), x.end());
+  int minspan = minspan_in;
+  if (minspan < 0) minspan = (int)std::nearbyint(-std::log2(-(1.0 / ((double)q * (double)n)) * std::log(1.0 - 0.05)) / 2.5);
+  if (minspan_out) *minspan_out = minspan;
+  std::vector<double> out;
+  out.push_back(x[0]);
+  size_t cc = 1;
+  while (cc + (size_t)minspan <= n) {
+    const size_t idx = cc + (size_t)minspan + 1;   // 1-based
+    if (idx <= n) out.push_back(x[idx - 1]);
+    cc += (size_t)minspan + 1;
+  }
+  std::vector<double> uniq;
+  for (double v : out) if (uniq.empty() || uniq.back() != v) uniq.push_back(v);   // ascending input
+  return uniq;
+}
+
+// max_span.R:14-26
+inline std::vector<double> max_span(const std::vector<double>& X, int q) {
+  std::vector<double> x(X);
+  std::sort(x.begin(), x.end());
+  x.erase(std::unique(x.begin(), x.end()), x.end());
+  const long n = (long)x.size();
+  const long maxspan = (long)std::nearbyint(3.0 - std::log2(0.05 / (double)q));
+  const long tail_from = (long)std::floor((double)(n - maxspan + 1));   // 1-based
+  std::vector<double> out;
+  for (long i = 1; i <= n; ++i) {
+    if (i <= maxspan) continue;
+    if (i >= tail_from) continue;
+    out.push_back(x[(size_t)i - 1]);
+  }
+  if (out.empty()) return x;
+  return out;
+}
+
+// marge2.R:152-166: returns candidate knots (ascending); X_out = round(x, 4)
+inline std::vector<double> candidate_knots(const std::vector<double>& x_pred, bool approx_knot, int n_knot_max,
+                                           int minspan_in, std::vector<double>* X_out, int* minspan_out) {
+  std::vector<double> X(x_pred.size());
+  for (size_t i = 0; i < X.size(); ++i) X[i] = r_round(x_pred[i], 1e4);
+  std::vector<double> r1 = min_span(X, 1, minspan_in, minspan_out);
+  std::vector<double> r2 = max_span(X, 1);
+  std::vector<double> red;
+  for (double v : r1) if (std::binary_search(r2.begin(), r2.end(), v)) red.push_back(v);
+  if (approx_knot) {
+    const double q05 = quantile7(x_pred, 0.05), q95 = quantile7(x_pred, 0.95);
+    std::vector<double> f;
+    for (double v : red) if (v > q05 && v < q95) f.push_back(v);
+    red.swap(f);
+    if ((int)red.size() > n_knot_max) {
+      const double lo = *std::min_element(red.begin(), red.end()), hi = *std::max_element(red.begin(), red.end());
+      std::vector<double> s((size_t)n_knot_max);
+      const double by = (hi - lo) / (double)(n_knot_max - 1);     // seq.default(from, to, length.out)
+      for (int k = 0; k < n_knot_max; ++k) s[(size_t)k] = (k == 0) ? lo : (k == n_knot_max - 1 ? hi : lo + (double)k * by);
+      for (double& v : s) v = r_round(v, 1e4);
+      red.swap(s);
+    }
+  }
+  if (X_out) X_out->swap(X);
+  return red;
+}
+
+// ---- lineage plan ---------------------------------------------------------------------------------
+struct LineagePlan {
+  Lineage L;
+  std::vector<int32_t> perm;      // sorted position -> original cell index (within the full cell axis)
+  std::vector<double> u;          // [Npad] bucket-local coordinate
+  std::vector<double> off;        // [Npad] log(1/size_factor) or empty
+  std::vector<int32_t> bucket;    // [N] bucket of each sorted cell (host harness only)
+  std::vector<double> Xs;         // [N] sorted rounded pseudotime
+  double pt_min = 0, pt_max = 0;
+  int minspan = 0;
+  std::string error;
+};
+
+// pt_col: n_cells doubles with NaN = not in lineage.  size_factor may be null.
+inline bool build_lineage_plan(const double* pt_col, int64_t n_cells, const double* size_factor,
+                               const sclane_opts& o, LineagePlan& P) {
+  std::vector<int32_t> cells;
+  std::vector<double> x;
+  for (int64_t i = 0; i < n_cells; ++i)
+    if (!std::isnan(pt_col[i])) { cells.push_back((int32_t)i); x.push_back(pt_col[i]); }
+  const size_t N = x.size();
+  if (N < 30) { P.error = "lineage has fewer than 30 cells"; return false; }
+  std::vector<double> X;
+  std::vector<double> knots = candidate_knots(x, o.approx_knot != 0, o.n_knot_max, o.minspan, &X, &P.minspan);
+  if (knots.empty()) { P.error = "no candidate knots (pseudotime has too few distinct values)"; return false; }
+  if ((int)knots.size() > TMAX) { P.error = "more than SCLANE_TMAX candidate knots (approx.knot = FALSE is not supported yet)"; return false; }
+  std::sort(knots.begin(), knots.end());
+  Lineage& L = P.L;
+  std::memset(&L, 0, sizeof(L));
+  L.N = (int)N;
+  L.Npad = (int)((N + 127) / 128 * 128);
+  L.T = (int)knots.size();
+  for (int k = 0; k < L.T; ++k) L.knots[k] = knots[(size_t)k];
+  L.ref[0] = L.knots[0];
+  for (int b = 1; b <= L.T; ++b) L.ref[b] = L.knots[b - 1];
+  // stable sort by rounded pseudotime
+  std::vector<int32_t> order(N);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return X[(size_t)a] < X[(size_t)b]; });
+  P.perm.resize(N);
+  P.Xs.resize(N);
+  P.bucket.resize(N);
+  P.u.assign((size_t)L.Npad, 0.0);
+  if (size_factor) P.off.assign((size_t)L.Npad, 0.0); else P.off.clear();
+  for (int b = 0; b <= L.T + 1; ++b) L.bstart[b] = 0;
+  std::vector<int> cnt((size_t)L.T + 1, 0);
+  for (size_t i = 0; i < N; ++i) {
+    const int32_t src = order[i];
+    const double xv = X[(size_t)src];
+    P.perm[i] = cells[(size_t)src];
+    P.Xs[i] = xv;
+    const int b = (int)(std::upper_bound(knots.begin(), knots.end(), xv) - knots.begin());   // #{k: t_k <= x}
+    P.bucket[i] = b;
+    cnt[(size_t)b]++;
+    const double u = xv - L.ref[b];
+    P.u[i] = u;
+    L.U0[b] += 1.0; L.U1[b] += u; L.U2[b] += u * u;
+    if (size_factor) P.off[i] = std::log(1.0 / size_factor[cells[(size_t)src]]);
+  }
+  int acc = 0;
+  for (int b = 0; b <= L.T; ++b) { L.bstart[b] = acc; acc += cnt[(size_t)b]; }
+  L.bstart[L.T + 1] = acc;
+  for (int b = L.T + 2; b <= NBMAX; ++b) L.bstart[b] = acc;
+  P.pt_min = *std::min_element(x.begin(), x.end());
+  P.pt_max = *std::max_element(x.begin(), x.end());
+  return true;
+}
+
+// ---- distribution functions ----------------------------------------------------------------------
+// regularised upper incomplete gamma Q(a, x) (series / Lentz continued fraction)
+inline double gamma_q(double a, double x) {
+  if (std::isnan(a) || std::isnan(x)) return std::numeric_limits<double>::quiet_NaN();
+  if (x <= 0.0) return 1.0;
+  const double gln = std::lgamma(a);
+  if (x < a + 1.0) {
+    double ap = a, sum = 1.0 / a, del = sum;
+    for (int n = 0; n < 10000; ++n) {
+      ap += 1.0; del *= x / ap; sum += del;
+      if (std::fabs(del) < std::fabs(sum) * 1e-17) break;
+    }
+    return 1.0 - sum * std::exp(-x + a * std::log(x) - gln);
+  }
+  const double tiny = 1e-300;
+  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+  for (int i = 1; i < 10000; ++i) {
+    const double an = -(double)i * ((double)i - a);
+    b += 2.0;
+    d = an * d + b; if (std::fabs(d) < tiny) d = tiny;
+    c = b + an / c; if (std::fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (std::fabs(del - 1.0) < 1e-16) break;
+  }
+  return std::exp(-x + a * std::log(x) - gln) * h;
+}
+// stats::pchisq(q, df, lower.tail = FALSE)
+inline double pchisq_upper(double q, double df) {
+  if (std::isnan(q) || std::isnan(df)) return std::numeric_limits<double>::quiet_NaN();
+  if (q <= 0.0) return 1.0;
+  return gamma_q(0.5 * df, 0.5 * q);
+}
+// 2 * pnorm(-|z|)
+inline double pnorm_two_sided(double z) {
+  if (std::isnan(z)) return z;
+  return std::erfc(std::fabs(z) / std::sqrt(2.0));
+}
+
+// ---- record assembly -----------------------------------------------------------------------------
+// Raw per-gene device output
+struct GeneOut {
+  GeneState st;
+  NbResult alt, null;
+};
+
+inline void finalize_record(const GeneOut& g, const Lineage& L, sclane_record& r) {
+  const double NaN = std::numeric_limits<double>::quiet_NaN();
+  std::memset(&r, 0, sizeof(r));
+  const GeneState& st = g.st;
+  const bool marge_ok = (st.fin.n >= 1) && g.alt.ok && !(st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC | SCLANE_NOTE_ALL_ZERO));
+  const bool null_ok = g.null.ok && !(st.error & SCLANE_NOTE_ALL_ZERO);
+  r.status = (marge_ok ? SCLANE_MARGE_OK : 0) | (null_ok ? SCLANE_NULL_OK : 0);
+  r.marge_notes = st.error | (marge_ok ? g.alt.notes : 0);
+  r.null_notes = null_ok ? g.null.notes : (st.error & SCLANE_NOTE_ALL_ZERO);
+  for (int j = 0; j < SCLANE_PMAX; ++j) {
+    r.term_kind[j] = 0; r.term_knot_idx[j] = -1;
+    r.term_knot[j] = r.term_label[j] = r.coef[j] = r.se[j] = r.z[j] = r.p[j] = NaN;
+  }
+  for (int j = 0; j < SCLANE_PMAX * SCLANE_PMAX; ++j) r.cov[j] = NaN;
+  r.theta = r.se_theta = r.loglik = r.deviance = NaN;
+  r.null_coef = r.null_se = r.null_z = r.null_p = r.null_theta = r.null_se_theta = r.null_loglik = r.null_deviance = NaN;
+  r.test_stat = r.df = r.p_val = NaN;
+  if (marge_ok) {
+    const int p = st.fin.n;
+    r.n_terms = p;
+    for (int j = 0; j < p; ++j) {
+      r.term_kind[j] = st.fin.kind[j];
+      r.term_knot_idx[j] = st.fin.kind[j] == SCLANE_TERM_INTERCEPT ? -1 : st.fin.knot[j];
+      if (st.fin.kind[j] != SCLANE_TERM_INTERCEPT) {
+        r.term_knot[j] = L.knots[st.fin.knot[j]];
+        r.term_label[j] = r_signif(r.term_knot[j], 4);
+      }
+      r.coef[j] = g.alt.coef[j];
+      r.se[j] = std::sqrt(g.alt.cov[j * PMAX + j]);
+      r.z[j] = r.coef[j] / r.se[j];
+      r.p[j] = pnorm_two_sided(r.z[j]);
+      for (int l = 0; l < p; ++l) r.cov[j * p + l] = g.alt.cov[j * PMAX + l];
+    }
+    r.theta = g.alt.theta; r.se_theta = g.alt.se_theta;
+    r.loglik = g.alt.loglik; r.deviance = g.alt.deviance;
+    r.alternations = g.alt.alternations; r.irls_iters = g.alt.irls_iters;
+  }
+  if (null_ok) {
+    r.null_coef = g.null.coef[0];
+    r.null_se = std::sqrt(g.null.cov[0]);
+    r.null_z = r.null_coef / r.null_se;
+    r.null_p = pnorm_two_sided(r.null_z);
+    r.null_theta = g.null.theta; r.null_se_theta = g.null.se_theta;
+    r.null_loglik = g.null.loglik; r.null_deviance = g.null.deviance;
+    r.null_alternations = g.null.alternations; r.null_irls_iters = g.null.irls_iters;
+  }
+  if (marge_ok && null_ok) {                      // modelLRT.R:43-53
+    r.test_stat = 2.0 * (r.loglik - r.null_loglik);
+    double df = (double)((r.n_terms + 1) - 2);    // logLik df = rank + 1 (theta) for both models
+    if (df == 0.0) df = 1.0;
+    r.df = df;
+    r.p_val = pchisq_upper(r.test_stat, df);
+  }
+  r.fwd_n_terms = st.fwd.n;
+  for (int j = 0; j < st.fwd.n && j < SCLANE_PMAX; ++j) { r.fwd_kind[j] = st.fwd.kind[j]; r.fwd_knot_idx[j] = st.fwd.kind[j] ? st.fwd.knot[j] : -1; }
+  for (int j = 0; j < 4; ++j) { r.fwd_score[j] = j < st.fwd_iters ? st.fwd_score[j] : NaN; r.fwd_sigma[j] = j < st.fwd_iters ? st.fwd_sigma[j] : NaN; }
+  r.n_wic = st.n_wic;
+  for (int j = 0; j < SCLANE_PMAX; ++j) r.wic[j] = j < st.n_wic ? st.wic[j] : NaN;
+  r.fit_passes = st.passes;
+}
+
+inline void init_gene_state(GeneState& st) {
+  std::memset(&st, 0, sizeof(st));
+  st.fwd.n = 1;
+  st.fwd.kind[0] = SCLANE_TERM_INTERCEPT;
+  st.fwd.knot[0] = 0;
+  st.m_count = 1;
+}
+
+}  // namespace sclane

@@ -1,0 +1,114 @@
+// emu.cpp -- TEST HARNESS ONLY (never linked into libsclane_b200.so).
+// Runs the shared host/device per-gene algorithm (sclane_b200/csrc/sclane_core.cuh) with a serial
+// executor, so the control flow, the bucket-moment algebra and the glm.nb schedule can be checked
+// against the numpy oracle on a machine without a GPU (`pytest -m "not gpu"`).  The product path has
+// no CPU fallback: libsclane_b200.so only contains the CUDA executor.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../sclane_b200/csrc/sclane_host.hpp"
+
+using namespace sclane;
+
+struct HostExec {
+  Work* W;
+  const Lineage* L;
+  const int32_t* y;        // sorted counts of this gene [N]
+  const double* u;
+  const double* off;       // may be null
+  double* mu;              // [N]
+  const int32_t* bucket;
+  bool leader() const { return true; }
+  void sync() const {}
+  template <int MODE>
+  void pass() {
+    const int N = L->N;
+    if (MODE != PASS_EMIT) {
+      for (int b = 0; b <= L->T; ++b) for (int k = 0; k < NACC; ++k) W->acc[b][k] = 0.0;
+      for (int k = 0; k < NSC; ++k) W->sc[k] = 0.0;
+    }
+    for (int i = 0; i < N; ++i) {
+      const int b = bucket[i];
+      double mu_out = 0.0;
+      const double o = (W->use_offset && off) ? off[i] : 0.0;
+      cell_contrib<MODE>(y[i], u[i], o, W->a[b], W->c[b], W->sigma, W->theta, mu ? mu[i] : 0.0, W->acc[b], W->sc, mu_out);
+      if (MODE == PASS_EMIT) mu[i] = mu_out;
+    }
+  }
+  template <class F>
+  void par_for(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
+};
+
+static void gene_stats(const int32_t* y, int N, GeneStats& gs) {
+  gs.sum_y = gs.sum_y2 = gs.sum_ylogy = gs.sum_lgamma_y1 = 0.0;
+  gs.ymax = 0;
+  for (int i = 0; i < N; ++i) {
+    const double v = (double)y[i];
+    gs.sum_y += v; gs.sum_y2 += v * v;
+    if (y[i] > 0) gs.sum_ylogy += v * std::log(v);
+    gs.sum_lgamma_y1 += std::lgamma(v + 1.0);
+    if (y[i] > gs.ymax) gs.ymax = y[i];
+  }
+}
+
+extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
+                                const double* size_factor, const sclane_opts* opts, sclane_record* out,
+                                sclane_lineage_info* lineages) {
+  for (int l = 0; l < n_lineages; ++l) {
+    LineagePlan P;
+    if (!build_lineage_plan(pt + (int64_t)l * n_cells, n_cells, size_factor, *opts, P)) { std::fprintf(stderr, "emu: %s\n", P.error.c_str()); return 1; }
+    const Lineage& L = P.L;
+    if (lineages) {
+      lineages[l].n_cells = L.N; lineages[l].n_knots = L.T; lineages[l].minspan = P.minspan;
+      for (int k = 0; k < L.T; ++k) lineages[l].knots[k] = L.knots[k];
+      lineages[l].pt_min = P.pt_min; lineages[l].pt_max = P.pt_max;
+    }
+    std::vector<int32_t> y((size_t)L.N);
+    std::vector<double> mu((size_t)L.N);
+    for (int64_t g = 0; g < n_genes; ++g) {
+      for (int i = 0; i < L.N; ++i) y[(size_t)i] = counts[g * n_cells + P.perm[(size_t)i]];
+      GeneStats gs;
+      gene_stats(y.data(), L.N, gs);
+      GeneOut go;
+      init_gene_state(go.st);
+      if (gs.sum_y == 0.0) go.st.error |= SCLANE_NOTE_ALL_ZERO;
+      Work W;
+      std::memset(&W, 0, sizeof(W));
+      HostExec ex{&W, &L, y.data(), P.u.data(), P.off.empty() ? nullptr : P.off.data(), mu.data(), P.bucket.data()};
+      for (int it = 0; it < 4 && !go.st.fwd_done && !go.st.error; ++it) {
+        gene_forward_fit(ex, L, gs, go.st, W);
+        gene_sweep(ex, L, gs, go.st, W, opts->M, opts->tols_score);
+      }
+      const int p_fwd = W.passes;
+      gene_backward(ex, L, gs, go.st, W);
+      const int p_bwd = W.passes;
+      gene_final(ex, L, gs, go.st, W, size_factor != nullptr, &go.alt, &go.null);
+      if (std::getenv("SCLANE_EMU_STAGES"))
+        std::fprintf(stderr, "gene %ld passes fwd %d bwd %d final %d (alt: alt=%d irls=%d; null: alt=%d irls=%d)\n", (long)g, p_fwd, p_bwd - p_fwd,
+                     W.passes - p_bwd, go.alt.alternations, go.alt.irls_iters, go.null.alternations, go.null.irls_iters);
+      go.st.passes = W.passes;
+      finalize_record(go, L, out[g * n_lineages + l]);
+    }
+  }
+  return 0;
+}
+
+extern "C" int emu_candidate_knots(const double* x, int64_t n, const sclane_opts* opts, double* knots_out, int32_t* minspan_out) {
+  std::vector<double> xv(x, x + n), X;
+  int ms = 0;
+  std::vector<double> k = candidate_knots(xv, opts->approx_knot != 0, opts->n_knot_max, opts->minspan, &X, &ms);
+  if (minspan_out) *minspan_out = ms;
+  for (size_t i = 0; i < k.size() && i < (size_t)SCLANE_TMAX; ++i) knots_out[i] = k[i];
+  return (int)k.size();
+}
+
+extern "C" double emu_pchisq_upper(double q, double df) { return pchisq_upper(q, df); }
+extern "C" double emu_r_round(double x, int digits) { return r_round_digits(x, digits); }
+extern "C" double emu_digamma(double x) { return digamma_pos(x); }
+extern "C" double emu_trigamma(double x) { return trigamma_pos(x); }
+extern "C" double emu_nb_lambda(int y, double sigma) { return nb_lambda(y, sigma, 1.0 / sigma); }
+extern "C" void emu_default_opts(sclane_opts* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->abi_version = SCLANE_ABI_VERSION; o->mode = 0; o->M = 5; o->approx_knot = 1; o->n_knot_max = 25; o->minspan = -1; o->tols_score = 1e-5;
+}

@@ -1,0 +1,234 @@
+"""Parity of the CUDA path (called through the C ABI) with the oracle and with the reference's golden run.
+Everything here needs a B200 (pytest -m gpu)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_EXCEPTIONS, record_terms, rel
+from oracle import marge as omarge
+from oracle.eigen_helpers import eigen_map_mat_mult, eigen_map_matrix_invert, eigen_map_pseudo_inverse
+from oracle.knots import candidate_knots
+from oracle.nbfit import nb_mle
+from oracle.rmath import p_adjust_bh
+from oracle.test_dynamic import test_dynamic as oracle_test_dynamic
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6   # north_star: coefficients, theta and LRT within 1e-6 relative in fp64
+
+
+def _compare_with_oracle(res, oracle, tol=TOL, theta=True):
+    worst = {}
+    for g, lins in res.items():
+        for ln, r in lins.items():
+            o = oracle[g][ln]
+            assert r["Model_Status"] == o["Model_Status"], (g, ln)
+            if o["MARGE_Summary"] is None:
+                assert r["MARGE_Summary"] is None
+                continue
+            assert r["MARGE_Summary"]["term"] == o["MARGE_Summary"]["term"], (g, ln)
+            assert r["Degrees_Freedom"] == o["Degrees_Freedom"]
+            e = {}
+            if abs(o["Test_Stat"]) > 1e-6:
+                e["lrt"] = rel(r["Test_Stat"], o["Test_Stat"])
+            else:
+                assert abs(r["Test_Stat"]) < 1e-6
+            e["coef"] = max(rel(a, b) for a, b in zip(r["MARGE_Summary"]["estimate"], o["MARGE_Summary"]["estimate"]))
+            e["se"] = max(rel(a, b) for a, b in zip(r["MARGE_Summary"]["std.error"], o["MARGE_Summary"]["std.error"]))
+            e["ll"] = rel(r["LogLik_MARGE"], o["LogLik_MARGE"])
+            e["ll0"] = rel(r["LogLik_Null"], o["LogLik_Null"])
+            e["dev"] = rel(r["Dev_MARGE"], o["Dev_MARGE"])
+            e["dev0"] = rel(r["Dev_Null"], o["Dev_Null"])
+            e["coef0"] = rel(r["Null_Summary"]["estimate"][0], o["Null_Summary"]["estimate"][0])
+            rec = r["record"]
+            if theta and not (rec.marge_notes & 3) and not (rec.null_notes & 3):   # theta only when glm.nb converged (no th.warn)
+                e["theta"] = max(rel(r["Theta"][0], o["_theta"][0]), rel(r["Theta"][1], o["_theta"][1]))
+            for k, v in e.items():
+                if v > worst.get(k, (0.0, ""))[0]:
+                    worst[k] = (v, g)
+    bad = {k: v for k, v in worst.items() if v[0] > tol}
+    assert not bad, bad
+    return worst
+
+
+@pytest.fixture(scope="module")
+def gpu_golden(golden_inputs):
+    import sclane_b200 as sb
+    return sb.testDynamic(golden_inputs["counts"], golden_inputs["pt"], genes=golden_inputs["genes"],
+                          size_factor_offset=golden_inputs["size_factor"], n_gpus=1)
+
+
+@pytest.fixture(scope="module")
+def oracle_golden(golden_inputs):
+    return oracle_test_dynamic(golden_inputs["counts"], golden_inputs["pt"], golden_inputs["genes"], golden_inputs["size_factor"],
+                               keep_preds=False)
+
+
+def test_bundled_vs_oracle(gpu_golden, oracle_golden):
+    """C1 (bundled sim_counts + sim_pseudotime, GLM + offset): CUDA == oracle on every gene, discrete and continuous."""
+    _compare_with_oracle(gpu_golden, oracle_golden)
+    import sclane_b200 as sb
+    assert sb.launch_count() >= 7
+
+
+def test_bundled_vs_reference_golden(gpu_golden, golden_models, golden_preds):
+    """CUDA vs the reference's own bundled testDynamic() output: identical term sets outside the 11 stated
+    platform-dependent genes, statistics within 1e-6, identical dynamic/static calls at FDR 0.01 for all 100 genes."""
+    import sclane_b200 as sb
+    mism = set()
+    for g, gold in golden_models.items():
+        r = gpu_golden[g]["Lineage_A"]
+        assert r["Model_Status"] == gold["Model_Status"]
+        if r["MARGE_Summary"]["term"] != gold["MARGE_Summary"]["term"]:
+            mism.add(g)
+            continue
+        assert rel(r["Test_Stat"], gold["Test_Stat"], 1e-6) < TOL
+        assert r["Degrees_Freedom"] == gold["Degrees_Freedom"]
+        assert rel(r["P_Val"], gold["P_Val"], 1e-300) < 1e-5
+        for k in ("estimate", "std.error", "statistic"):
+            for a, b in zip(r["MARGE_Summary"][k], gold["MARGE_Summary"][k]):
+                assert rel(a, b) < TOL, (g, k)
+        assert rel(r["LogLik_MARGE"], gold["LogLik_MARGE"]) < 1e-8 and rel(r["LogLik_Null"], gold["LogLik_Null"]) < 1e-8
+        assert rel(r["Dev_MARGE"], gold["Dev_MARGE"]) < TOL and rel(r["Dev_Null"], gold["Dev_Null"]) < TOL
+        assert r["MARGE_Slope_Data"]["Direction"] == gold["MARGE_Slope_Data"]["Direction"]
+        assert r["MARGE_Slope_Data"]["Rounded_Breakpoint"] == gold["MARGE_Slope_Data"]["Rounded_Breakpoint"]
+    assert mism == GOLDEN_EXCEPTIONS
+    de = sb.getResultsDE(gpu_golden)
+    calls = dict(zip(de["Gene"], de["Gene_Dynamic_Overall"]))
+    gadj = p_adjust_bh(np.array([golden_models[g]["P_Val"] for g in golden_models]))
+    assert calls == {g: int(a < 0.01) for g, a in zip(golden_models, gadj)}
+    # per-cell predictions (lazy MARGE_Preds / Null_Preds) vs the golden data.frames
+    n = 0
+    for g in sorted({k.split("/")[0] for k in golden_preds.files} - GOLDEN_EXCEPTIONS):
+        r = gpu_golden[g]["Lineage_A"]
+        for key, val in (("marge_link_fit", r["MARGE_Preds"]["marge_link_fit"]), ("marge_link_se", r["MARGE_Preds"]["marge_link_se"]),
+                         ("null_link_fit", r["Null_Preds"]["null_link_fit"]), ("null_link_se", r["Null_Preds"]["null_link_se"])):
+            gold = golden_preds[f"{g}/{key}"]
+            assert np.max(np.abs(val - gold) / (np.abs(gold) + 1e-9)) < TOL, (g, key)
+        n += 1
+    assert n >= 8
+
+
+def test_synthetic_vs_oracle_with_edge_cases():
+    """Seeded synthetic NB counts incl. an all-zero gene, a nearly empty gene, a huge-count gene and a near-Poisson gene."""
+    import sclane_b200 as sb
+    from sclane_b200 import synth
+    counts, pt, _ = synth.make_counts(40, 3000, seed=11)
+    rng = np.random.default_rng(5)
+    counts[3] = 0
+    counts[5] = (np.arange(3000) % 211 == 0).astype(np.int32)
+    counts[7] = rng.poisson(3000.0 * np.exp(1.5 * pt[:, 0]))          # large counts, Poisson
+    counts[9] = rng.poisson(2.0, 3000)                                  # pure Poisson, static
+    genes = [f"g{i}" for i in range(40)]
+    res = sb.testDynamic(counts, pt, genes=genes, n_gpus=1)
+    oracle = oracle_test_dynamic(counts, pt, genes, None, keep_preds=False)
+    assert res["g3"]["Lineage_A"]["Model_Status"] == "MARGE model error, null model error"
+    _compare_with_oracle(res, oracle)
+
+
+def test_two_lineages_with_offsets_vs_oracle():
+    """C4-shaped: two lineages sharing a root (NaN = not in lineage), size-factor offsets from createCellOffset()."""
+    import sclane_b200 as sb
+    from sclane_b200 import synth
+    counts, pt, _ = synth.make_counts(24, 4000, seed=21, n_lineages=2)
+    sf = sb.createCellOffset(counts)
+    genes = [f"g{i}" for i in range(24)]
+    res = sb.testDynamic(counts, pt, genes=genes, size_factor_offset=sf, n_gpus=1)
+    oracle = oracle_test_dynamic(counts, pt, genes, sf, keep_preds=False)
+    assert set(res["g0"].keys()) == {"Lineage_A", "Lineage_B"}
+    _compare_with_oracle(res, oracle)
+    assert res.lineage_info[0]["n_cells"] == int(np.sum(~np.isnan(pt[:, 0])))
+
+
+def test_null_stats_and_score_sweep_vs_dense_oracle(golden_inputs):
+    """K1 (stat_out_score_glm_null) and K2 (score_fun_glm over all knots x {one, both}) through their single-call
+    entry points, against the dense numpy restatement -- all 50 scores per gene, not just the arg-max."""
+    import sclane_b200 as sb
+    X, knots = candidate_knots(golden_inputs["pt"])
+    sel = [1, 3, 10, 17, 42, 63, 77, 90]
+    counts = golden_inputs["counts"][sel]
+    for kinds, kidx in (([0], [-1]), ([0, 1, 2], [-1, 12, 12]), ([0, 1], [-1, 5]), ([0, 1, 2, 1], [-1, 18, 18, 3])):
+        beta, sigma, mu = sb.stat_out_score_glm_null(counts, golden_inputs["pt"], knots, kinds, kidx)
+        terms = [omarge.Term(k, i) for k, i in zip(kinds, kidx)]
+        B = omarge.build_design(terms, X, knots)
+        for gi in range(len(sel)):
+            y = counts[gi].astype(np.float64)
+            fit = nb_mle(B, y)
+            assert (sigma[gi] == 0.0) == fit.poisson
+            assert rel(sigma[gi], fit.sigma, 1e-12) < 1e-6
+            assert np.max(np.abs(beta[gi] - fit.beta) / (np.abs(fit.beta) + 1e-6)) < 1e-6
+            assert np.max(np.abs(mu[gi] - fit.mu) / fit.mu) < 1e-6
+        # sweep with the oracle's mu so that only the sweep itself is compared
+        mus = np.stack([nb_mle(B, counts[gi].astype(np.float64)).mu for gi in range(len(sel))])
+        sig = np.array([nb_mle(B, counts[gi].astype(np.float64)).sigma for gi in range(len(sel))])
+        scores = sb.score_fun_glm_sweep(counts, mus, sig, golden_inputs["pt"], knots, kinds, kidx)
+        for gi in range(len(sel)):
+            y = counts[gi].astype(np.float64)
+            ns = omarge.stat_out_score_glm_null(y, B)
+            for t in range(knots.size):
+                h1, h2 = omarge.tp1(X, knots[t]), omarge.tp2(X, knots[t])
+                one = omarge.score_fun_glm(ns, h1[:, None], omarge._collinear(terms, (1,), t))
+                both = omarge.score_fun_glm(ns, np.stack([h1, h2], 1), omarge._collinear(terms, (1, 2), t))
+                for mine, ref in ((scores[gi, 0, t], one), (scores[gi, 1, t], both)):
+                    if np.isnan(ref):
+                        assert np.isnan(mine)
+                    else:
+                        assert abs(mine - ref) < 1e-7 * max(1.0, abs(ref)), (gi, t, mine, ref)
+
+
+def test_eigen_dropins():
+    """The three RcppEigen helpers (tests/testthat/test_scLANE.R:29-38 checks them on a random 25 x 25 PD matrix)."""
+    import sclane_b200 as sb
+    rng = np.random.default_rng(1)
+    M = rng.normal(size=(25, 25))
+    A = M @ M.T + 25 * np.eye(25)
+    assert np.allclose(sb.eigenMapMatrixInvert(A), eigen_map_matrix_invert(A), rtol=1e-10, atol=1e-12)
+    assert np.allclose(sb.eigenMapMatrixInvert(A), np.linalg.inv(A), rtol=1e-8)
+    B = rng.normal(size=(25, 7))
+    assert np.allclose(sb.eigenMapMatMult(A, B), eigen_map_mat_mult(A, B), rtol=1e-12, atol=1e-12)
+    assert np.allclose(sb.eigenMapPseudoInverse(A), eigen_map_pseudo_inverse(A), rtol=1e-8, atol=1e-10)
+    R = rng.normal(size=(30, 4)) @ rng.normal(size=(4, 12))        # rank 4, tall
+    assert np.allclose(sb.eigenMapPseudoInverse(R), eigen_map_pseudo_inverse(R), rtol=1e-7, atol=1e-9)
+    assert np.allclose(sb.eigenMapPseudoInverse(R.T), eigen_map_pseudo_inverse(R.T), rtol=1e-7, atol=1e-9)
+    # non-PD input: Eigen's LLT stops early and solve() runs on the untouched remainder
+    N = np.array([[4.0, 2.0, 1.0], [2.0, 0.5, 3.0], [1.0, 3.0, 2.0]])
+    assert np.allclose(sb.eigenMapMatrixInvert(N), eigen_map_matrix_invert(N), rtol=1e-12, equal_nan=True)
+    assert np.allclose(sb.eigenMapMatrixInvert(np.array([[-2.0]])), [[0.25]])
+
+
+def test_full_size_properties():
+    """Size-independent properties at BASELINE config 2's cell count (10,000 cells; a gene subset keeps it quick):
+    gene-order independence and batching independence are bit-exact; a permutation of the cells leaves every
+    statistic unchanged to rounding; LRT >= 0 whenever the alternative nests the null; FDR calls are a function of P."""
+    import sclane_b200 as sb
+    from sclane_b200 import synth
+    counts, pt, _ = synth.make_counts(192, 10000, seed=312)
+    base = sb.testDynamic(counts, pt, n_gpus=1)
+    recs = base.records
+    # (1) batching: 192 genes in one batch vs batches of 50
+    small = sb.testDynamic(counts, pt, n_gpus=1, genes_per_batch=50)
+    for i in range(192):
+        assert bytes(recs[i])[:-8] == bytes(small.records[i])[:-8]       # everything but gene_time
+    # (2) gene order
+    perm = np.random.default_rng(0).permutation(192)
+    shuf = sb.testDynamic(counts[perm], pt, n_gpus=1)
+    for j, i in enumerate(perm):
+        assert bytes(shuf.records[j])[:-8] == bytes(recs[int(i)])[:-8]
+    # (3) cell permutation
+    cp = np.random.default_rng(1).permutation(10000)
+    pc = sb.testDynamic(np.ascontiguousarray(counts[:, cp]), pt[cp], n_gpus=1)
+    for i in range(192):
+        a, b = recs[i], pc.records[i]
+        assert a.status == b.status and record_terms(a) == record_terms(b)
+        if a.status == 3:
+            assert rel(a.test_stat, b.test_stat, 1e-6) < 1e-7 and rel(a.loglik, b.loglik) < 1e-10
+    # (4) sanity of the statistics
+    for i in range(192):
+        r = recs[i]
+        if r.status == 3:
+            assert r.test_stat > -1e-6 * abs(r.loglik)
+            assert 0.0 <= r.p_val <= 1.0
+            assert r.df == max(1, r.n_terms - 1)
+            assert r.fwd_n_terms in (1, 3, 4) or r.fwd_n_terms == 2
+    de = sb.getResultsDE(base)
+    assert ((de["P_Val_Adj"] < 0.01).astype(int) == de["Gene_Dynamic_Lineage"]).all()
+    assert 40 < int(de["Gene_Dynamic_Overall"].sum()) <= 192
