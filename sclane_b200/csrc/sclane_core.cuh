@@ -117,23 +117,90 @@ struct Work {
   double bw_wic[PMAX], bw_cum;
   // sweep scores (NaN = NA)
   double sw_one[TMAX], sw_both[TMAX];
+  // alpha/gamma tables of the current model's terms (coop_set_model)
+  double tal[PMAX][NBMAX], tga[PMAX][NBMAX];
+  int want_ll;                 // PASS_IRLS: also accumulate the log-likelihood (sc[2])
+  int sw_trunc, sw_kidx;       // forward selection broadcast
+  double sw_score2;
   // misc broadcast
   double bc[4];
 };
 
-// eta parameters per bucket from beta.
-SC_HD void set_eta(const Lineage& L, const Model& m, const double* beta, Work& W) {
-  for (int b = 0; b <= L.T; ++b) {
-    double a = 0.0, c = 0.0;
-    for (int j = 0; j < m.n; ++j) {
-      double al, ga;
-      term_ab(L, m.kind[j], m.knot[j], b, al, ga);
-      a += beta[j] * al;
-      c += beta[j] * ga;
-    }
-    W.a[b] = a;
-    W.c[b] = c;
+// ---- cooperative small algebra: every thread of the CTA calls these; work is split with E::par_for ----
+// alpha/gamma tables of the model's terms.
+struct SetModelFn {
+  const Lineage* L; const Model* m; Work* W;
+  SC_HD void operator()(int i) const {
+    const int nb = L->T + 1;
+    const int j = i / nb, b = i - j * nb;
+    double al, ga;
+    term_ab(*L, m->kind[j], m->knot[j], b, al, ga);
+    W->tal[j][b] = al;
+    W->tga[j][b] = ga;
   }
+};
+template <class E>
+SC_HD void coop_set_model(E& ex, const Lineage& L, const Model& m, Work& W) {
+  ex.sync();
+  SetModelFn fn{&L, &m, &W};
+  ex.par_for(m.n * (L.T + 1), fn);
+  ex.sync();
+}
+// eta parameters per bucket from beta (beta must live in shared memory).
+struct SetEtaFn {
+  const Model* m; Work* W; const double* beta;
+  SC_HD void operator()(int b) const {
+    double a = 0.0, c = 0.0;
+    for (int j = 0; j < m->n; ++j) { a += beta[j] * W->tal[j][b]; c += beta[j] * W->tga[j][b]; }
+    W->a[b] = a;
+    W->c[b] = c;
+  }
+};
+template <class E>
+SC_HD void coop_set_eta(E& ex, const Lineage& L, const Model& m, Work& W, const double* beta) {
+  ex.sync();
+  SetEtaFn fn{&m, &W, beta};
+  ex.par_for(L.T + 1, fn);
+  ex.sync();
+}
+// Symmetric system from a pass: H[j][l] = <d_j, d_l> with accumulators I0..I0+2, grad[j] = <d_j, .> with J0, J0+1,
+// and (K0 >= 0) the extra column H[j][p] = <d_j, .> with K0, K0+1.  Results in W.H (NSYS stride) / W.grad.
+struct SystemFn {
+  const Lineage* L; const Model* m; Work* W; int I0, J0, K0;
+  SC_HD void operator()(int t) const {
+    const int p = m->n, nb = L->T + 1;
+    const int ntri = p * (p + 1) / 2;
+    if (t < ntri) {
+      int j = 0;
+      while ((j + 1) * (j + 2) / 2 <= t) ++j;
+      const int l = t - j * (j + 1) / 2;
+      double s = 0.0;
+      for (int b = 0; b < nb; ++b) {
+        const double aj = W->tal[j][b], gj = W->tga[j][b], al = W->tal[l][b], gl = W->tga[l][b];
+        s += aj * al * W->acc[b][I0] + (aj * gl + al * gj) * W->acc[b][I0 + 1] + gj * gl * W->acc[b][I0 + 2];
+      }
+      W->H[j * NSYS + l] = s;
+      W->H[l * NSYS + j] = s;
+    } else if (t < ntri + p) {
+      const int j = t - ntri;
+      double s = 0.0;
+      for (int b = 0; b < nb; ++b) s += W->tal[j][b] * W->acc[b][J0] + W->tga[j][b] * W->acc[b][J0 + 1];
+      W->grad[j] = s;
+    } else {
+      const int j = t - ntri - p;
+      double s = 0.0;
+      for (int b = 0; b < nb; ++b) s += W->tal[j][b] * W->acc[b][K0] + W->tga[j][b] * W->acc[b][K0 + 1];
+      W->H[j * NSYS + p] = s;
+      W->H[p * NSYS + j] = s;
+    }
+  }
+};
+template <class E>
+SC_HD void coop_system(E& ex, const Lineage& L, const Model& m, Work& W, int I0, int J0, int K0) {
+  SystemFn fn{&L, &m, &W, I0, J0, K0};
+  const int p = m.n;
+  ex.par_for(p * (p + 1) / 2 + (J0 >= 0 ? p : 0) + (K0 >= 0 ? p : 0), fn);
+  ex.sync();
 }
 
 // <d_j, d_l>_w from accumulators I0..I0+2 and <d_j, v> from I0, I0+1.
@@ -174,7 +241,7 @@ SC_HD double gram_u(const Lineage& L, int kj, int tj, int kl, int tl) {
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double sigma, double theta,
-                        double mu_in, double* acc, double* sc, double& mu_out) {
+                        double mu_in, bool want_ll, double* acc, double* sc, double& mu_out) {
   const double y = (double)yi;
   if (MODE == PASS_EMIT) {
     mu_out = exp(a + c * u);
@@ -204,8 +271,10 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
     const double o = mu * (1.0 + sigma * y) * inv * inv;   // - d2 l / d eta2
     const double cc = sigma * mu * r * inv;                // - d2 l / d eta d(log sigma)
     const double lg = log1p(sigma * mu);
-    const double g = psi_diff(yi, theta) - lg - sigma * r;                                   // d l / d theta
-    const double h = -tri_diff(yi, theta) + sigma - 2.0 * sigma * inv + sigma * (1.0 + sigma * y) * inv * inv;  // d2 l / d theta2
+    double dpsi, dtri;
+    psi_tri_diff(yi, theta, dpsi, dtri);
+    const double g = dpsi - lg - sigma * r;                                                  // d l / d theta
+    const double h = -dtri + sigma - 2.0 * sigma * inv + sigma * (1.0 + sigma * y) * inv * inv;  // d2 l / d theta2
     acc[0] += o; acc[1] += o * u; acc[2] += o * u * u;
     acc[3] += r; acc[4] += r * u;
     acc[5] += cc; acc[6] += cc * u;
@@ -225,10 +294,10 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
     acc[3] += wz; acc[4] += wz * u;
     const double lg = log1p(sigma * mu);
     // dev.resids: 2 (y log(max(1,y)/mu) - (y+th) log((y+th)/(mu+th))); the y log y part is a gene constant
-    sc[0] += -y * eta - (y + theta) * (log1p(sigma * y) - lg);
+    sc[0] += yi > 0 ? (-y * eta - (y + theta) * (log1p(sigma * y) - lg)) : theta * lg;
     const double e = (y - mu) / mu;
     sc[1] += e * e;                                        // theta.ml start: n / sum((y/mu - 1)^2)
-    sc[2] += nb_lambda(yi, sigma, theta) + y * eta - (y + theta) * lg;   // glm.nb loglik() minus sum lgamma(y+1)
+    if (want_ll) sc[2] += nb_lambda(yi, sigma, theta) + y * eta - (y + theta) * lg;   // glm.nb loglik() minus sum lgamma(y+1)
     return;
   }
   if (MODE == PASS_THETA) {
@@ -237,8 +306,10 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
     const double inv = 1.0 / (1.0 + sigma * mu);
     const double r = (y - mu) * inv;
     const double lg = log1p(sigma * mu);
-    sc[0] += psi_diff(yi, theta) - lg - sigma * r;                                            // theta.ml score
-    sc[1] += tri_diff(yi, theta) - sigma + 2.0 * sigma * inv - sigma * (1.0 + sigma * y) * inv * inv;  // theta.ml info
+    double dpsi, dtri;
+    psi_tri_diff(yi, theta, dpsi, dtri);
+    sc[0] += dpsi - lg - sigma * r;                                                           // theta.ml score
+    sc[1] += dtri - sigma + 2.0 * sigma * inv - sigma * (1.0 + sigma * y) * inv * inv;        // theta.ml info
     return;
   }
 }
@@ -257,34 +328,20 @@ struct FitResult {
   int poisson;
 };
 
-// Build -H (joint observed information) and the gradient from a PASS_FIT result.
-SC_HD void build_newton_system(const Lineage& L, const Model& m, Work& W, bool sigma_free) {
+// Joint observed information -H and the gradient from a PASS_FIT result: the beta blocks come from
+// coop_system(I0 = 0, J0 = 3, K0 = 5); this adds the log-sigma entries.  Leader only.
+SC_HD void finish_newton_system(const Model& m, Work& W, bool sigma_free) {
   const int p = m.n;
-  for (int j = 0; j < p; ++j) {
-    for (int l = 0; l <= j; ++l) {
-      double v = gram2(L, W.acc, 0, m.kind[j], m.knot[j], m.kind[l], m.knot[l]);
-      W.H[j * NSYS + l] = v;
-      W.H[l * NSYS + j] = v;
-    }
-    W.grad[j] = lin2(L, W.acc, 3, m.kind[j], m.knot[j]);
-  }
   if (sigma_free) {
     const double th = W.theta;
     const double G = W.sc[0], Hh = W.sc[1];
-    const double d1 = -th * G;                  // d l / d s,  s = log sigma
-    const double d2 = th * G + th * th * Hh;    // d2 l / d s2
-    for (int j = 0; j < p; ++j) {
-      double v = lin2(L, W.acc, 5, m.kind[j], m.knot[j]);   // - d2 l / d beta_j d s
-      W.H[j * NSYS + p] = v;
-      W.H[p * NSYS + j] = v;
-    }
-    W.H[p * NSYS + p] = -d2;
-    W.grad[p] = d1;
+    W.H[p * NSYS + p] = -(th * G + th * th * Hh);   // - d2 l / d s2,  s = log sigma
+    W.grad[p] = -th * G;                             //   d l / d s
   }
 }
 
 // One leader-side Newton decision after a PASS_FIT.  Sets W.flag = 1 when the iteration is over.
-SC_HD void nb_mle_step(const Lineage& L, const Model& m, Work& W, double smin, double smax) {
+SC_HDN void nb_mle_step(const Model& m, Work& W, double smin, double smax) {
   const int p = m.n;
   const bool pois = W.nt_poisson != 0;
   const double ell = W.sc[2];
@@ -295,12 +352,12 @@ SC_HD void nb_mle_step(const Lineage& L, const Model& m, Work& W, double smin, d
     if (!W.nt_have_prev || W.nt_scale < 1e-6) {
       W.flag = 1;                                   // cannot improve: stay at the last accepted point
       if (W.nt_have_prev) {
-        for (int j = 0; j < p; ++j) W.beta[j] = W.nt_prev[j];
+        _Pragma("unroll 1") for (int j = 0; j < p; ++j) W.beta[j] = W.nt_prev[j];
         if (!pois) W.s = W.nt_prev[p];
       }
     } else {                                        // halve the last step and retry
       W.nt_scale *= 0.5;
-      for (int j = 0; j < p; ++j) W.beta[j] = W.nt_prev[j] + W.nt_scale * W.step[j];
+      _Pragma("unroll 1") for (int j = 0; j < p; ++j) W.beta[j] = W.nt_prev[j] + W.nt_scale * W.step[j];
       if (!pois) {
         double s = W.nt_prev[p] + W.nt_scale * W.step[p];
         W.s = s < smin ? smin : (s > smax ? smax : s);
@@ -311,7 +368,7 @@ SC_HD void nb_mle_step(const Lineage& L, const Model& m, Work& W, double smin, d
   W.nt_have_prev = 1;
   W.nt_ell_prev = ell;
   const bool sigma_free = !pois;
-  build_newton_system(L, m, W, sigma_free);
+  finish_newton_system(m, W, sigma_free);
   // active-set treatment of the bounds on s
   const bool at_lo = sigma_free && (W.s <= smin) && (W.grad[p] < 0.0);
   const bool at_hi = sigma_free && (W.s >= smax) && (W.grad[p] > 0.0);
@@ -319,16 +376,16 @@ SC_HD void nb_mle_step(const Lineage& L, const Model& m, Work& W, double smin, d
   double Lm[NSYS * NSYS];
   bool ok = false;
   if (s_moves) {
-    for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+    _Pragma("unroll 1") for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
     ok = chol_factor<NSYS>(p + 1, Lm);
     if (ok) chol_solve<NSYS>(p + 1, Lm, W.grad, W.step);
   }
   if (!ok) {
     // beta block alone (always used when s is fixed); safeguarded 1-D Newton on s otherwise
-    for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+    _Pragma("unroll 1") for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
     const bool okb = chol_factor<NSYS>(p, Lm);
     if (okb) chol_solve<NSYS>(p, Lm, W.grad, W.step);
-    else { for (int j = 0; j < p; ++j) W.step[j] = 0.0; W.flag = 1; }   // singular information: stop here
+    else { _Pragma("unroll 1") for (int j = 0; j < p; ++j) W.step[j] = 0.0; W.flag = 1; }   // singular information: stop here
     W.step[p] = 0.0;
     if (s_moves) {
       const double d2 = W.H[p * NSYS + p];
@@ -338,20 +395,20 @@ SC_HD void nb_mle_step(const Lineage& L, const Model& m, Work& W, double smin, d
   // step limits: |delta s| <= 2, |delta beta_j| <= 5
   double scale = 1.0;
   if (s_moves && fabs(W.step[p]) > 2.0) scale = 2.0 / fabs(W.step[p]);
-  for (int j = 0; j < p; ++j) if (fabs(W.step[j]) * scale > 5.0) scale = 5.0 / fabs(W.step[j]);
-  if (scale < 1.0) for (int j = 0; j <= p; ++j) W.step[j] *= scale;
+  _Pragma("unroll 1") for (int j = 0; j < p; ++j) if (fabs(W.step[j]) * scale > 5.0) scale = 5.0 / fabs(W.step[j]);
+  if (scale < 1.0) _Pragma("unroll 1") for (int j = 0; j <= p; ++j) W.step[j] *= scale;
   double gain = 0.0, dmax = 0.0;
-  for (int j = 0; j < p; ++j) {
+  _Pragma("unroll 1") for (int j = 0; j < p; ++j) {
     gain += W.grad[j] * W.step[j];
     const double d = fabs(W.step[j]) / (1.0 + fabs(W.beta[j]));
     if (d > dmax) dmax = d;
   }
   if (s_moves) { gain += W.grad[p] * W.step[p]; if (fabs(W.step[p]) > dmax) dmax = fabs(W.step[p]); }
-  for (int j = 0; j < p; ++j) W.nt_prev[j] = W.beta[j];
+  _Pragma("unroll 1") for (int j = 0; j < p; ++j) W.nt_prev[j] = W.beta[j];
   W.nt_prev[p] = W.s;
   W.nt_scale = 1.0;
   const bool conv = (dmax <= 1e-8) || (0.5 * gain <= 1e-13 * (1.0 + fabs(ell)));
-  for (int j = 0; j < p; ++j) W.beta[j] += W.step[j];
+  _Pragma("unroll 1") for (int j = 0; j < p; ++j) W.beta[j] += W.step[j];
   if (s_moves) {
     const double s = W.s + W.step[p];
     W.s = s < smin ? smin : (s > smax ? smax : s);
@@ -371,7 +428,7 @@ template <class E>
 SC_HDN FitResult nb_mle(E& ex, const Lineage& L, const Model& m, const GeneStats& gs, Work& W, bool warm) {
   const int p = m.n;
   const double smin = log(kSigmaPoisson), smax = log(kSigmaMax);
-  ex.sync();
+  coop_set_model(ex, L, m, W);
   if (ex.leader()) {
     if (!warm) {
       const double ybar = gs.sum_y / (double)L.N;
@@ -394,19 +451,14 @@ SC_HDN FitResult nb_mle(E& ex, const Lineage& L, const Model& m, const GeneStats
   ex.sync();
   for (int it = 0; it < kMaxNewton; ++it) {
     if (ex.leader()) {
-      set_eta(L, m, W.beta, W);
       if (W.nt_poisson) { W.sigma = 0.0; W.theta = 0.0; }
       else { W.sigma = exp(W.s); W.theta = 1.0 / W.sigma; }
       W.passes++;
     }
-    ex.sync();
+    coop_set_eta(ex, L, m, W, W.beta);
     ex.template pass<PASS_FIT>();
-    if (ex.leader()) {
-#ifdef SCLANE_EMU_DEBUG
-      printf("  it %d ell=%.10g s=%g pois=%d beta=%g %g %g %g | scale=%g\n", it, W.sc[2], W.s, W.nt_poisson, W.beta[0], W.beta[1], W.beta[2], W.beta[3], W.nt_scale);
-#endif
-      nb_mle_step(L, m, W, smin, smax);
-    }
+    coop_system(ex, L, m, W, 0, 3, W.nt_poisson ? -1 : 5);
+    if (ex.leader()) nb_mle_step(m, W, smin, smax);
     ex.sync();
     if (W.flag) break;
   }
@@ -424,10 +476,9 @@ SC_HDN FitResult nb_mle(E& ex, const Lineage& L, const Model& m, const GeneStats
 
 // Wald statistics of the non-intercept columns from the last PASS_FIT of nb_mle
 // (backward_sel_WIC.R:47-52).  Leader only.  out[0..p-2].
-SC_HD void wald_from_fit(const Lineage& L, const Model& m, Work& W, bool poisson, double* out) {
+SC_HDN void wald_from_fit(const Model& m, Work& W, bool poisson, double* out) {
   const int p = m.n;
-  build_newton_system(L, m, W, !poisson);
-  const int n = poisson ? p : p + 1;
+  const int n = poisson ? p : p + 1;      // W.H / W.grad still hold the system of the last pass
   double Lm[NSYS * NSYS];
   for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
   if (!chol_factor<NSYS>(n, Lm)) {
@@ -458,36 +509,43 @@ SC_HD bool cand_collinear(const Lineage& L, const Model& m, int k, bool both) {
   return both && has_pair;
 }
 
-// A = (B'WB)^-1 via Eigen-style LLT semantics is only needed for well-conditioned B (p <= PMAX);
-// a plain Cholesky inverse is used (the reference's eigenMapMatrixInvert on a PD matrix).
-// Leader computes Ainv into W.cov (NSYS stride); returns false if not PD.
-SC_HD bool sweep_prepare(const Lineage& L, const Model& m, Work& W) {
+// A = (B'WB)^-1 (stat_out_score_glm_null.R:33-40; eigenMapMatrixInvert on a PD matrix = plain Cholesky
+// inverse).  W.H holds B'WB (coop_system with I0 = 0); the leader inverts it into W.cov.  false if not PD.
+SC_HDN bool sweep_invert(const Model& m, Work& W) {
   const int p = m.n;
+  if (p == 1) { W.cov[0] = 1.0 / W.H[0]; return true; }      // stat_out_score_glm_null.R:33-34
   double Lm[NSYS * NSYS];
-  for (int j = 0; j < p; ++j)
-    for (int l = 0; l <= j; ++l) {
-      double v = gram2(L, W.acc, 0, m.kind[j], m.knot[j], m.kind[l], m.knot[l]);
-      Lm[j * NSYS + l] = v;
-      Lm[l * NSYS + j] = v;
-    }
-  if (p == 1) { W.cov[0] = 1.0 / Lm[0]; return true; }      // stat_out_score_glm_null.R:33-34
+  for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
   if (!chol_factor<NSYS>(p, Lm)) return false;
   chol_inverse<NSYS>(p, Lm, W.cov);
   return true;
 }
 
-// score of candidate knot k; both = pair (tp1, tp2) else tp1 only.  Any thread may call it after
-// sweep_prepare + sync.  NaN = NA.
-SC_HD double sweep_score(const Lineage& L, const Model& m, const Work& W, int k, bool both) {
+// score of candidate knot k; both = pair (tp1, tp2) else tp1 only.  Any thread may call it once the
+// model tables (coop_set_model) and W.cov (sweep_invert) are in place.  NaN = NA.
+SC_HDN double sweep_score(const Lineage& L, const Model& m, const Work& W, int k, bool both) {
   if (cand_collinear(L, m, k, both)) return nan("");
-  const int p = m.n;
+  const int p = m.n, nb = L.T + 1;
   const int c = both ? 2 : 1;
   double C[2][PMAX], D[2], bvec[2];
   for (int q = 0; q < c; ++q) {
     const int kind = q == 0 ? SCLANE_TERM_TP1 : SCLANE_TERM_TP2;
-    for (int j = 0; j < p; ++j) C[q][j] = gram2(L, W.acc, 0, m.kind[j], m.knot[j], kind, k);
-    D[q] = gram2(L, W.acc, 0, kind, k, kind, k);
-    bvec[q] = lin2(L, W.acc, 3, kind, k);
+    for (int j = 0; j < p; ++j) C[q][j] = 0.0;
+    double d = 0.0, bv = 0.0;
+    // tp1(t_k) lives on buckets > k, tp2(t_k) on buckets <= k
+    const int b0 = q == 0 ? k + 1 : 0, b1 = q == 0 ? nb : k + 1;
+    for (int b = b0; b < b1; ++b) {
+      double al, ga;
+      term_ab(L, kind, k, b, al, ga);
+      const double s0 = W.acc[b][0], s1 = W.acc[b][1], s2 = W.acc[b][2];
+      const double w0 = al * s0 + ga * s1;      // <cand, 1>_w  restricted to the bucket
+      const double w1 = al * s1 + ga * s2;      // <cand, u>_w
+      for (int j = 0; j < p; ++j) C[q][j] += W.tal[j][b] * w0 + W.tga[j][b] * w1;
+      d += al * w0 + ga * w1;
+      bv += al * W.acc[b][3] + ga * W.acc[b][4];
+    }
+    D[q] = d;
+    bvec[q] = bv;
   }
   // S = D - C' A C  (the 2x2 D is diagonal: tp1 * tp2 == 0)
   double S[2][2] = {{0, 0}, {0, 0}};
@@ -530,7 +588,7 @@ SC_HD int which_max_round6(const double* v, int n, bool last) {
 // first iteration (interaction scores are the constant -1e5, :244), 1 afterwards (the "interaction with
 // the intercept" scores duplicate the additive ones, :247-307).  Returns false for the breakFlag exit;
 // else trunc_type (1|2) and knot index (may be -1 = R subscript error).
-SC_HD bool select_candidate(const double* one, const double* both, int T, int in_set, int& trunc_type, int& kidx) {
+SC_HDN bool select_candidate(const double* one, const double* both, int T, int in_set, int& trunc_type, int& kidx) {
   double one_int_c[TMAX], both_int_c[TMAX];
   for (int i = 0; i < T; ++i) {
     one_int_c[i] = in_set ? one[i] : -1e5;
@@ -585,23 +643,35 @@ SC_HD bool select_candidate(const double* one, const double* both, int T, int in
 #undef SEL
 }
 
-// stat_out() (stat_out.R:23-47) for basis m from the unweighted moments: returns GCVq1 (rounded to 10 dp)
-// or NaN when B'B is not PD.  ytb: <column_j, y>.
-SC_HD double stat_out_gcvq1(const Lineage& L, const Model& m, const Work& W, const GeneStats& gs) {
-  const int p = m.n;
-  double Lm[NSYS * NSYS], bty[NSYS], coef[NSYS];
-  for (int j = 0; j < p; ++j) {
-    for (int l = 0; l <= j; ++l) {
-      double v = gram_u(L, m.kind[j], m.knot[j], m.kind[l], m.knot[l]);
-      Lm[j * NSYS + l] = v;
-      Lm[l * NSYS + j] = v;
+// stat_out() (stat_out.R:23-47) for a candidate basis from the unweighted moments.  The Gram B'B and B'y are
+// assembled cooperatively into W.H / W.grad (StatOutFn); the leader solves and returns GCVq1 rounded to 10 dp
+// (NaN when B'B is not PD).
+struct StatOutFn {
+  const Lineage* L; const Model* m; Work* W;
+  SC_HD void operator()(int t) const {
+    const int p = m->n;
+    const int ntri = p * (p + 1) / 2;
+    if (t < ntri) {
+      int j = 0;
+      while ((j + 1) * (j + 2) / 2 <= t) ++j;
+      const int l = t - j * (j + 1) / 2;
+      const double v = gram_u(*L, m->kind[j], m->knot[j], m->kind[l], m->knot[l]);
+      W->H[j * NSYS + l] = v;
+      W->H[l * NSYS + j] = v;
+    } else {
+      const int j = t - ntri;
+      W->grad[j] = lin2(*L, W->acc, 5, m->kind[j], m->knot[j]);
     }
-    bty[j] = lin2(L, W.acc, 5, m.kind[j], m.knot[j]);
   }
+};
+SC_HDN double stat_out_gcvq1(const Lineage& L, const Model& m, const Work& W, const GeneStats& gs) {
+  const int p = m.n;
+  double Lm[NSYS * NSYS], coef[NSYS];
+  for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
   if (!chol_factor<NSYS>(p, Lm)) return nan("");
-  chol_solve<NSYS>(p, Lm, bty, coef);
+  chol_solve<NSYS>(p, Lm, W.grad, coef);
   double fit2 = 0.0;
-  for (int j = 0; j < p; ++j) fit2 += coef[j] * bty[j];
+  for (int j = 0; j < p; ++j) fit2 += coef[j] * W.grad[j];
   const double N = (double)L.N;
   const double ybar = gs.sum_y / N;
   const double TSS = gs.sum_y2 - gs.sum_y * ybar;
@@ -633,23 +703,31 @@ struct GeneState {
   int n_wic;
 };
 
-// Forward-iteration bookkeeping after a sweep (marge2.R:589-758).  Leader only.  `one`/`both` hold the
-// T scores.  Returns nothing; updates gs (basis, stop flags).
-SC_HD void forward_update(const Lineage& L, GeneState& st, Work& W, const GeneStats& gstat,
-                          const double* one, const double* both, int M, double tols_score) {
+// Forward-iteration bookkeeping after a sweep (marge2.R:368-758), in two leader steps around the cooperative
+// stat_out Gram.  Step 1: selection tree -> candidate basis in W.bw_cur (W.flag = 1 when there is one).
+SC_HDN void forward_select(const Lineage& L, GeneState& st, Work& W) {
   const int it = st.fwd_iters;
   st.fwd_iters++;
+  W.flag = 0;
   int trunc_type = 0, kidx = -1;
   const int in_set = st.fwd.n > 1 ? 1 : 0;
-  if (!select_candidate(one, both, L.T, in_set, trunc_type, kidx)) { st.fwd_done = 1; st.fwd_stop = 1; return; }
+  if (!select_candidate(W.sw_one, W.sw_both, L.T, in_set, trunc_type, kidx)) { st.fwd_done = 1; st.fwd_stop = 1; return; }
   if (kidx < 0) { st.fwd_done = 1; st.fwd_stop = 5; st.error |= SCLANE_NOTE_NUMERIC; return; }
   const bool pair = trunc_type == 2;
-  const double score2 = pair ? both[kidx] : one[kidx];   // recomputation of the chosen score (:665-675) is the same number
+  const double score2 = pair ? W.sw_both[kidx] : W.sw_one[kidx];   // the re-scoring at :665-675 recomputes this same number
   if (it < 4) st.fwd_score[it] = score2;
   if (!(score2 == score2)) { st.fwd_done = 1; st.fwd_stop = 5; st.error |= SCLANE_NOTE_NUMERIC; return; }   // if (NA) -> error
   Model cand = st.fwd;
   cand.kind[cand.n] = SCLANE_TERM_TP1; cand.knot[cand.n] = kidx; cand.n++;
   if (pair) { cand.kind[cand.n] = SCLANE_TERM_TP2; cand.knot[cand.n] = kidx; cand.n++; }
+  W.bw_cur = cand;
+  W.sw_score2 = score2;
+  W.flag = 1;
+}
+// Step 2: stat_out check and acceptance (marge2.R:676-758).
+SC_HDN void forward_accept(const Lineage& L, GeneState& st, Work& W, const GeneStats& gstat, int M, double tols_score) {
+  const Model cand = W.bw_cur;
+  const double score2 = W.sw_score2;
   const double gcvq1 = stat_out_gcvq1(L, cand, W, gstat);
   if (!(gcvq1 == gcvq1)) { st.fwd_done = 1; st.fwd_stop = 5; st.error |= SCLANE_NOTE_NUMERIC; return; }
   if (gcvq1 < -10.0 || r_round(score2, 1e4) <= 0.0) { st.fwd_done = 1; st.fwd_stop = 2; return; }   // :681
@@ -695,7 +773,7 @@ SC_HDN void backward_pass(E& ex, const Lineage& L, const GeneStats& gstat, GeneS
       printf("bw step %d: n=%d conv=%d pois=%d sigma=%g beta0=%g passes=%d\n", i, W.bw_cur.n, fr.converged, fr.poisson, W.sigma, W.beta[0], W.passes);
 #endif
       const Model cur = W.bw_cur;
-      wald_from_fit(L, cur, W, fr.poisson != 0, wald);
+      wald_from_fit(cur, W, fr.poisson != 0, wald);
       const int nw = cur.n - 1;
       const double mn = nanmin(wald, nw);
       W.bw_cum += mn;
@@ -763,21 +841,16 @@ struct NbResult {
   int ok;
 };
 
-// Solve the WLS normal equations of a PASS_IRLS result: G beta = X'Wz.  Leader only.  beta -> W.step,
-// G -> W.gf_G.  false if G is not positive definite or the solution is not finite.
-SC_HD bool wls_from_pass(const Lineage& L, const Model& m, Work& W) {
+// Solve the WLS normal equations of a PASS_IRLS result: G beta = X'Wz, with G / X'Wz assembled by
+// coop_system(I0 = 0, J0 = 3) into W.H / W.grad.  Leader only.  beta -> W.step, G -> W.gf_G.
+// false if G is not positive definite or the solution is not finite.
+SC_HDN bool wls_solve(const Model& m, Work& W) {
   const int p = m.n;
-  double Lm[NSYS * NSYS], z[NSYS];
-  for (int j = 0; j < p; ++j) {
-    for (int l = 0; l <= j; ++l) {
-      double v = gram2(L, W.acc, 0, m.kind[j], m.knot[j], m.kind[l], m.knot[l]);
-      Lm[j * NSYS + l] = v; Lm[l * NSYS + j] = v;
-      W.gf_G[j * PMAX + l] = v; W.gf_G[l * PMAX + j] = v;
-    }
-    z[j] = lin2(L, W.acc, 3, m.kind[j], m.knot[j]);
-  }
+  double Lm[NSYS * NSYS];
+  for (int j = 0; j < p; ++j)
+    for (int l = 0; l < p; ++l) { Lm[j * NSYS + l] = W.H[j * NSYS + l]; W.gf_G[j * PMAX + l] = W.H[j * NSYS + l]; }
   if (!chol_factor<NSYS>(p, Lm)) return false;
-  chol_solve<NSYS>(p, Lm, z, W.step);
+  chol_solve<NSYS>(p, Lm, W.grad, W.step);
   for (int j = 0; j < p; ++j) if (!(W.step[j] == W.step[j]) || isinf(W.step[j])) return false;
   return true;
 }
@@ -802,17 +875,19 @@ SC_HDN int glm_fit2(E& ex, const Lineage& L, const Model& m, const GeneStats& gs
   ex.sync();
   int it;
   for (it = 1; it <= kMaxitGlm; ++it) {
+    coop_system(ex, L, m, W, 0, 3, -1);
     if (ex.leader()) {
-      if (!wls_from_pass(L, m, W)) W.flag = 2;
+      if (!wls_solve(m, W)) W.flag = 2;
       else {
         for (int j = 0; j < p; ++j) W.beta[j] = W.step[j];
-        set_eta(L, m, W.beta, W);
         W.sigma = 1.0 / theta; W.theta = theta;
+        W.want_ll = 0;
         W.passes++;
       }
     }
     ex.sync();
     if (W.flag == 2) return -1;
+    coop_set_eta(ex, L, m, W, W.beta);
     ex.template pass<PASS_IRLS>();
     // (1) non-finite deviance: halve towards coefold until finite
     if (ex.leader()) { W.gf_dev = dev_from_pass(gstat, W); W.gf_ii = 1; }
@@ -826,7 +901,6 @@ SC_HDN int glm_fit2(E& ex, const Lineage& L, const Model& m, const GeneStats& gs
           else {
             W.gf_ii++;
             for (int j = 0; j < p; ++j) W.beta[j] = 0.5 * (W.beta[j] + W.gf_coefold[j]);
-            set_eta(L, m, W.beta, W);
             W.passes++;
             W.flag2 = 1;
           }
@@ -835,6 +909,7 @@ SC_HDN int glm_fit2(E& ex, const Lineage& L, const Model& m, const GeneStats& gs
       ex.sync();
       if (W.flag == 2) return -1;
       if (!W.flag2) break;
+      coop_set_eta(ex, L, m, W, W.beta);
       ex.template pass<PASS_IRLS>();
       if (ex.leader()) W.gf_dev = dev_from_pass(gstat, W);
       ex.sync();
@@ -852,13 +927,13 @@ SC_HDN int glm_fit2(E& ex, const Lineage& L, const Model& m, const GeneStats& gs
           if ((W.gf_dev - W.gf_devold) / (0.1 + fabs(W.gf_dev)) > -kEpsGlm && W.gf_ii <= kMaxitGlm) {
             W.gf_ii++;
             for (int j = 0; j < p; ++j) W.beta[j] = 0.5 * (W.beta[j] + W.gf_coefold[j]);
-            set_eta(L, m, W.beta, W);
             W.passes++;
             W.flag2 = 1;
           }
         }
         ex.sync();
         if (!W.flag2) break;
+        coop_set_eta(ex, L, m, W, W.beta);
         ex.template pass<PASS_IRLS>();
         if (ex.leader()) W.gf_dev = dev_from_pass(gstat, W);
         ex.sync();
@@ -930,11 +1005,11 @@ SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gst
   const int p = m.n;
   const double N = (double)L.N;
   const double d1 = sqrt(2.0 * fmax(1.0, N - (double)p));
-  ex.sync();
+  coop_set_model(ex, L, m, W);
   if (ex.leader()) {
     W.use_offset = use_offset ? 1 : 0;
     W.sigma = 1.0; W.theta = 1.0;       // init.theta = 1
-    for (int b = 0; b <= L.T; ++b) { W.a[b] = 0.0; W.c[b] = 0.0; }
+    W.want_ll = 0;
     W.passes++;
     out->ok = 0;
     out->notes = 0;
@@ -943,7 +1018,7 @@ SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gst
   ex.template pass<PASS_IRLS_START>();
   int irls = glm_fit2(ex, L, m, gstat, W, 1.0);
   if (irls < 0) return;
-  // th <- theta.ml(Y, mu) at the fresh mu of the initial fit
+  // th <- theta.ml(Y, mu) at the fresh mu of the initial fit (W.a / W.c still describe it)
   const double t0sum0 = W.sc[1];
   theta_ml(ex, L, W, t0sum0);
   if (ex.leader()) {
@@ -954,7 +1029,7 @@ SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gst
     for (int j = 0; j < p * PMAX; ++j) out->cov[j] = W.gf_G[j];
     // pass at (beta, th): gives Lm and doubles as the starting pass of the next glm.fit
     W.theta = W.nb_th; W.sigma = 1.0 / W.nb_th;
-    set_eta(L, m, W.beta, W);
+    W.want_ll = 1;
     W.passes++;
   }
   ex.sync();
@@ -984,9 +1059,8 @@ SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gst
     if (ex.leader()) {
       W.nb_dev = W.gf_dev;
       for (int j = 0; j < p * PMAX; ++j) out->cov[j] = W.gf_G[j];
-      set_eta(L, m, W.nb_beta_stale, W);          // theta.ml at the PREVIOUS mu (MASS quirk)
     }
-    ex.sync();
+    coop_set_eta(ex, L, m, W, W.nb_beta_stale);     // theta.ml at the PREVIOUS mu (MASS quirk)
     theta_ml(ex, L, W, W.nb_t0sum);
     if (ex.leader()) {
       const double t0 = W.nb_th;
@@ -994,11 +1068,11 @@ SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gst
       W.nb_se_th = W.tm_info;
       W.nb_notes = W.tm_notes;
       W.nb_del = t0 - W.nb_th;
-      set_eta(L, m, W.beta, W);
       W.theta = W.nb_th; W.sigma = 1.0 / W.nb_th;
+      W.want_ll = 1;
       W.passes++;
     }
-    ex.sync();
+    coop_set_eta(ex, L, m, W, W.beta);
     ex.template pass<PASS_IRLS>();
     if (ex.leader()) {
       W.nb_Lm0 = W.nb_Lm;
@@ -1066,10 +1140,9 @@ SC_HDN void gene_forward_fit(E& ex, const Lineage& L, const GeneStats& gstat, Ge
     st.sigma = fr.poisson ? 0.0 : W.sigma;
     st.s = fr.poisson ? log(kSigmaPoisson) : W.s;
     if (st.fwd_iters < 4) st.fwd_sigma[st.fwd_iters] = st.sigma;
-    set_eta(L, st.fwd, W.beta, W);
     W.passes++;
   }
-  ex.sync();
+  coop_set_eta(ex, L, st.fwd, W, W.beta);
   ex.template pass<PASS_EMIT>();
 }
 
@@ -1085,9 +1158,10 @@ SC_HDN void gene_sweep(E& ex, const Lineage& L, const GeneStats& gstat, GeneStat
     W.use_offset = 0;
     W.passes++;
   }
-  ex.sync();
+  coop_set_model(ex, L, st.fwd, W);
   ex.template pass<PASS_SWEEP>();
-  if (ex.leader()) W.flag = sweep_prepare(L, st.fwd, W) ? 1 : 0;
+  coop_system(ex, L, st.fwd, W, 0, -1, -1);                 // B'WB
+  if (ex.leader()) W.flag = sweep_invert(st.fwd, W) ? 1 : 0;
   ex.sync();
   if (!W.flag) {
     if (ex.leader()) { st.error |= SCLANE_NOTE_NUMERIC; st.fwd_done = 1; st.fwd_stop = 5; }
@@ -1097,7 +1171,13 @@ SC_HDN void gene_sweep(E& ex, const Lineage& L, const GeneStats& gstat, GeneStat
   ScoreFn fn{&L, &st.fwd, &W};
   ex.par_for(2 * L.T, fn);
   ex.sync();
-  if (ex.leader()) forward_update(L, st, W, gstat, W.sw_one, W.sw_both, M, tols_score);
+  if (ex.leader()) forward_select(L, st, W);
+  ex.sync();
+  if (!W.flag) return;
+  StatOutFn so{&L, &W.bw_cur, &W};
+  ex.par_for(W.bw_cur.n * (W.bw_cur.n + 1) / 2 + W.bw_cur.n, so);
+  ex.sync();
+  if (ex.leader()) forward_accept(L, st, W, gstat, M, tols_score);
   ex.sync();
 }
 

@@ -40,6 +40,27 @@ struct DevExec {
   double* mu;                       // [Npad] fitted means of this gene (sweep input / emit output)
   double (*slot)[NBMAX][NACC];      // [kWarps] warp-private partial moments
   double (*scw)[NSC];               // [kWarps] warp-private partial scalars
+  double (*stage)[NACC][33];        // [kWarps] staging for the (rare) register -> slot flushes
+  int (*stage_b)[32];               // [kWarps] bucket of each lane during a flush
+
+  // Add every lane's NV values v[k] into the warp's slot of that lane's bucket.  Lanes are summed in lane
+  // order by lane k (fixed order => reproducible).  Called <= ~T + 1 times per pass per warp, so it is kept
+  // compact (a rolled loop through shared memory) instead of fast: the shuffle-tree version dominated the
+  // kernels' instruction footprint.
+  template <int NV>
+  __device__ __noinline__ void flush_lanes(const double* v, int my_b, bool valid, double* dst, int stride) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) stage[warp][k][lane] = valid ? v[k] : 0.0;
+    stage_b[warp][lane] = my_b;
+    __syncwarp();
+    if (lane < NV) {
+#pragma unroll 1
+      for (int l = 0; l < 32; ++l) dst[stage_b[warp][l] * stride + lane] += stage[warp][lane][l];
+    }
+    __syncwarp();
+  }
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -48,109 +69,9 @@ struct DevExec {
     for (int i = threadIdx.x; i < n; i += kThreads) f(i);
   }
 
-  template <int MODE>
-  __device__ __noinline__ void pass() {
-    constexpr int NA = PassTraits<MODE>::NA;
-    constexpr int NS = PassTraits<MODE>::NS;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Lineage& Lr = *L;
-    const int N = Lr.N, T = Lr.T;
-    const double sigma = W->sigma, theta = W->theta;
-    const bool use_off = (MODE == PASS_IRLS || MODE == PASS_IRLS_START || MODE == PASS_THETA) && W->use_offset && off != nullptr;
-    double* myslot = &slot[warp][0][0];
-    if (NA > 0) {
-      for (int i = lane; i < (T + 1) * NACC; i += 32) myslot[i] = 0.0;
-      __syncwarp();
-    }
-    double acc[NACC], sc[NSC];
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < NSC; ++k) sc[k] = 0.0;
-
-    const int ntiles = (N + 127) >> 7;
-    const int t0 = (int)(((long long)ntiles * warp) / kWarps);
-    const int t1 = (int)(((long long)ntiles * (warp + 1)) / kWarps);
-    if (t0 < t1) {
-      int cur_b = 0;
-      const int first = t0 << 7;
-      while (cur_b < T && Lr.bstart[cur_b + 1] <= first) ++cur_b;
-      double a = W->a[cur_b], c = W->c[cur_b];
-      int b_hi = Lr.bstart[cur_b + 1];
-      for (int t = t0; t < t1; ++t) {
-        const int tile_lo = t << 7;
-        const int i0 = tile_lo + (lane << 2);
-        const int4 y4 = __ldg(reinterpret_cast<const int4*>(y + i0));
-        const double2 ua = __ldg(reinterpret_cast<const double2*>(u + i0));
-        const double2 ub = __ldg(reinterpret_cast<const double2*>(u + i0 + 2));
-        const int yv[4] = {y4.x, y4.y, y4.z, y4.w};
-        const double uv[4] = {ua.x, ua.y, ub.x, ub.y};
-        double ov[4] = {0.0, 0.0, 0.0, 0.0};
-        double mv[4] = {0.0, 0.0, 0.0, 0.0};
-        if (use_off) {
-          const double2 oa = __ldg(reinterpret_cast<const double2*>(off + i0));
-          const double2 ob = __ldg(reinterpret_cast<const double2*>(off + i0 + 2));
-          ov[0] = oa.x; ov[1] = oa.y; ov[2] = ob.x; ov[3] = ob.y;
-        }
-        if (MODE == PASS_SWEEP) {
-          const double2 ma = *reinterpret_cast<const double2*>(mu + i0);
-          const double2 mb = *reinterpret_cast<const double2*>(mu + i0 + 2);
-          mv[0] = ma.x; mv[1] = ma.y; mv[2] = mb.x; mv[3] = mb.y;
-        }
-        const int tile_end = min(tile_lo + 128, N);
-        if (tile_lo + 128 <= b_hi && tile_lo + 128 <= N) {
-          // whole tile inside the running bucket: no masks
-          double mo[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) cell_contrib<MODE>(yv[j], uv[j], ov[j], a, c, sigma, theta, mv[j], acc, sc, mo[j]);
-          if (MODE == PASS_EMIT) {
-            *reinterpret_cast<double2*>(mu + i0) = make_double2(mo[0], mo[1]);
-            *reinterpret_cast<double2*>(mu + i0 + 2) = make_double2(mo[2], mo[3]);
-          }
-        } else {
-          // tile straddles a bucket boundary (or is the ragged last tile): masked, bucket by bucket
-          for (;;) {
-            const int lo = Lr.bstart[cur_b];
-            const int hi = min(b_hi, tile_end);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = i0 + j;
-              if (i >= lo && i < hi) {
-                double mo;
-                cell_contrib<MODE>(yv[j], uv[j], ov[j], a, c, sigma, theta, mv[j], acc, sc, mo);
-                if (MODE == PASS_EMIT) mu[i] = mo;
-              }
-            }
-            if (hi >= tile_end) break;
-            if (NA > 0) {
-#pragma unroll
-              for (int k = 0; k < NA; ++k) {
-                const double v = warp_sum(acc[k]);
-                if (lane == 0) myslot[cur_b * NACC + k] += v;
-                acc[k] = 0.0;
-              }
-            }
-            ++cur_b;
-            a = W->a[cur_b]; c = W->c[cur_b];
-            b_hi = Lr.bstart[cur_b + 1];
-          }
-        }
-      }
-      if (NA > 0) {
-#pragma unroll
-        for (int k = 0; k < NA; ++k) {
-          const double v = warp_sum(acc[k]);
-          if (lane == 0) myslot[cur_b * NACC + k] += v;
-        }
-      }
-    }
-    if (NS > 0) {
-#pragma unroll
-      for (int k = 0; k < NS; ++k) {
-        const double v = warp_sum(sc[k]);
-        if (lane == 0) scw[warp][k] = v;
-      }
-    }
+  // Cross-warp combination of the warp-private partial sums, in a fixed order (bit-reproducible).
+  template <int NA, int NS>
+  __device__ __forceinline__ void combine(int T) {
     __syncthreads();
     if (NA > 0) {
       double* out = &W->acc[0][0];
@@ -168,6 +89,156 @@ struct DevExec {
       W->sc[threadIdx.x] = s;
     }
     __syncthreads();
+  }
+
+  // FP64-bound passes (fits, theta.ml, emit): ONE compact copy of the per-cell math, one cell per lane
+  // per iteration (a warp still reads 32 consecutive cells: 128 B of counts, 256 B of coordinates).
+  // The loop body must stay small: these kernels were instruction-fetch bound when it was unrolled.
+  template <int MODE>
+  __device__ __noinline__ void pass_scalar() {
+    constexpr int NA = PassTraits<MODE>::NA;
+    constexpr int NS = PassTraits<MODE>::NS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Lineage& Lr = *L;
+    const int N = Lr.N, T = Lr.T;
+    const double sigma = W->sigma, theta = W->theta;
+    const bool want_ll = W->want_ll != 0;
+    const bool use_off = (MODE == PASS_IRLS || MODE == PASS_IRLS_START || MODE == PASS_THETA) && W->use_offset && off != nullptr;
+    double* myslot = &slot[warp][0][0];
+    if (NA > 0) {
+      for (int i = lane; i < (T + 1) * NACC; i += 32) myslot[i] = 0.0;
+    }
+    if (NS > 0 && lane < NSC) scw[warp][lane] = 0.0;
+    __syncwarp();
+    double acc[NACC], sc[NSC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NSC; ++k) sc[k] = 0.0;
+    // contiguous run of 32-cell groups per warp
+    const int ngroups = (N + 31) >> 5;
+    const int g0 = (int)(((long long)ngroups * warp) / kWarps);
+    const int g1 = (int)(((long long)ngroups * (warp + 1)) / kWarps);
+    if (g0 < g1) {
+      int cur_b = 0;                       // bucket the register accumulators belong to (warp uniform)
+      const int first = g0 << 5;
+      while (cur_b < T && Lr.bstart[cur_b + 1] <= first) ++cur_b;
+#pragma unroll 1
+      for (int g = g0; g < g1; ++g) {
+        const int i = (g << 5) + lane;
+        const bool valid = i < N;
+        const int yi = __ldg(y + i);                   // rows are padded: always in bounds
+        const double ui = __ldg(u + i);
+        const double oi = use_off ? __ldg(off + i) : 0.0;
+        int b = cur_b;                                 // this lane's bucket (cells are sorted: b >= cur_b)
+        while (valid && b < T && i >= Lr.bstart[b + 1]) ++b;
+        double ct[NACC], cs[NSC], mo = 0.0;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) ct[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NSC; ++k) cs[k] = 0.0;
+        if (valid) {                                   // the ONLY copy of the per-cell math in this kernel
+          cell_contrib<MODE>(yi, ui, oi, W->a[b], W->c[b], sigma, theta, 0.0, want_ll, ct, cs, mo);
+          if (MODE == PASS_EMIT) mu[i] = mo;
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) sc[k] += cs[k];
+        if (NA > 0) {
+          if (__all_sync(0xffffffffu, !valid || b == cur_b)) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k) acc[k] += ct[k];
+          } else {
+            // the group straddles a bucket boundary (<= T times per pass): flush the running bucket, then the
+            // group's own contributions lane by lane into their buckets
+            flush_lanes<NA>(acc, cur_b, true, myslot, NACC);
+#pragma unroll
+            for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+            flush_lanes<NA>(ct, valid ? b : cur_b, valid, myslot, NACC);
+            int b_last = valid ? b : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b_last = max(b_last, __shfl_xor_sync(0xffffffffu, b_last, o));
+            cur_b = b_last;
+          }
+        }
+      }
+      if (NA > 0) flush_lanes<NA>(acc, cur_b, true, myslot, NACC);
+    }
+    if (NS > 0) flush_lanes<NS>(sc, 0, true, &scw[warp][0], 0);
+    combine<NA, NS>(T);
+  }
+
+  // HBM-bound pass (the score sweep): 128-cell tiles, 128-bit coalesced loads of counts (int4), coordinates and
+  // fitted means (2 x double2 each), four cells per lane in flight.
+  __device__ __noinline__ void pass_sweep() {
+    constexpr int NA = PassTraits<PASS_SWEEP>::NA;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Lineage& Lr = *L;
+    const int N = Lr.N, T = Lr.T;
+    const double sigma = W->sigma;
+    double* myslot = &slot[warp][0][0];
+    for (int i = lane; i < (T + 1) * NACC; i += 32) myslot[i] = 0.0;
+    __syncwarp();
+    double acc[NACC], sc[NSC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    const int ntiles = (N + 127) >> 7;
+    const int t0 = (int)(((long long)ntiles * warp) / kWarps);
+    const int t1 = (int)(((long long)ntiles * (warp + 1)) / kWarps);
+    if (t0 < t1) {
+      int cur_b = 0;
+      const int first = t0 << 7;
+      while (cur_b < T && Lr.bstart[cur_b + 1] <= first) ++cur_b;
+      int b_hi = Lr.bstart[cur_b + 1];
+      for (int t = t0; t < t1; ++t) {
+        const int tile_lo = t << 7;
+        const int i0 = tile_lo + (lane << 2);
+        const int4 y4 = __ldg(reinterpret_cast<const int4*>(y + i0));
+        const double2 ua = __ldg(reinterpret_cast<const double2*>(u + i0));
+        const double2 ub = __ldg(reinterpret_cast<const double2*>(u + i0 + 2));
+        const double2 ma = __ldg(reinterpret_cast<const double2*>(mu + i0));
+        const double2 mb = __ldg(reinterpret_cast<const double2*>(mu + i0 + 2));
+        const int yv[4] = {y4.x, y4.y, y4.z, y4.w};
+        const double uv[4] = {ua.x, ua.y, ub.x, ub.y};
+        const double mv[4] = {ma.x, ma.y, mb.x, mb.y};
+        const int tile_end = min(tile_lo + 128, N);
+        double mo;
+        if (tile_lo + 128 <= b_hi && tile_lo + 128 <= N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cell_contrib<PASS_SWEEP>(yv[j], uv[j], 0.0, 0.0, 0.0, sigma, 0.0, mv[j], false, acc, sc, mo);
+        } else {
+          for (;;) {
+            const int lo = Lr.bstart[cur_b];
+            const int hi = min(b_hi, tile_end);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i0 + j;
+              if (i >= lo && i < hi) cell_contrib<PASS_SWEEP>(yv[j], uv[j], 0.0, 0.0, 0.0, sigma, 0.0, mv[j], false, acc, sc, mo);
+            }
+            if (hi >= tile_end) break;
+#pragma unroll
+            for (int k = 0; k < NA; ++k) {
+              const double v = warp_sum(acc[k]);
+              if (lane == 0) myslot[cur_b * NACC + k] += v;
+              acc[k] = 0.0;
+            }
+            ++cur_b;
+            b_hi = Lr.bstart[cur_b + 1];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) myslot[cur_b * NACC + k] += v;
+      }
+    }
+    combine<NA, 0>(T);
+  }
+
+  template <int MODE>
+  __device__ __forceinline__ void pass() {
+    if (MODE == PASS_SWEEP) pass_sweep();
+    else pass_scalar<MODE>();
   }
 };
 
@@ -197,13 +268,15 @@ struct StageArgs {
 enum Stage : int { STAGE_FWD_FIT = 0, STAGE_SWEEP = 1, STAGE_BACKWARD = 2, STAGE_FINAL = 3, STAGE_NULLSTATS = 4, STAGE_SCOREONLY = 5 };
 
 template <int STAGE>
-__global__ void __launch_bounds__(kThreads) k_stage(StageArgs A) {
+__global__ void __launch_bounds__(kThreads, 2) k_stage(StageArgs A) {
   __shared__ Work W;
   __shared__ Lineage Ls;
   __shared__ GeneState st;
   __shared__ GeneStats gs;
   __shared__ double slot[kWarps][NBMAX][NACC];
   __shared__ double scw[kWarps][NSC];
+  __shared__ double stage[kWarps][NACC][33];
+  __shared__ int stage_b[kWarps][32];
   const int g = blockIdx.x;
   if (g >= A.n_genes) return;
   {
@@ -222,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) k_stage(StageArgs A) {
   }
   __syncthreads();
   const size_t row = (size_t)g * (size_t)Ls.Npad;
-  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw};
+  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, stage, stage_b};
   if (STAGE == STAGE_FWD_FIT || STAGE == STAGE_NULLSTATS) {
     gene_forward_fit(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_SWEEP || STAGE == STAGE_SCOREONLY) {

@@ -49,24 +49,49 @@ SC_HD double trigamma_pos(double x) {
   return r + 1.0 / x + 0.5 * f + t;
 }
 
-// psi(th + y) - psi(th) and trigamma(th) - trigamma(th + y) for an integer count y >= 0.
-// Small counts (the bulk of single-cell data) use the exact finite sums.
+// psi(th + y) - psi(th) = sum_{k<y} 1/(th+k) and trigamma(th) - trigamma(th + y) = sum_{k<y} 1/(th+k)^2 for an
+// integer count y >= 0.  Small counts (the bulk of single-cell data) use the exact finite sums, accumulated as
+// one rational each (numerator / denominator) so that a cell costs one division per sum instead of y.
 constexpr int kSmallCount = 12;
-SC_HD double psi_diff(int y, double th) {
-  if (y < kSmallCount) {
-    double s = 0.0;
-    for (int k = 0; k < y; ++k) s += 1.0 / (th + (double)k);
-    return s;
+// large counts (rare): out of line so that the streaming loops stay small in the instruction cache
+SC_HDN void psi_tri_diff_big(int y, double th, double& psi, double& tri) {
+  const double yd = (double)y;
+  if (th >= 1e4) {
+    // large theta: the differences of the asymptotic series, term by term (no cancellation); the omitted
+    // terms are below 1e-17 relative for th >= 1e4
+    const double x1 = th, x2 = th + yd, pr = x1 * x2;
+    psi = log1p(yd / th) + yd / (2.0 * pr) + yd * (x1 + x2) / (12.0 * pr * pr);
+    tri = yd / pr + 0.5 * yd * (x1 + x2) / (pr * pr) + yd * (x1 * x1 + pr + x2 * x2) / (6.0 * pr * pr * pr);
+    return;
   }
-  return digamma_pos(th + (double)y) - digamma_pos(th);
+  psi = digamma_pos(th + yd) - digamma_pos(th);
+  tri = trigamma_pos(th) - trigamma_pos(th + yd);
 }
-SC_HD double tri_diff(int y, double th) {
+SC_HDN void psi_tri_diff_sums(int y, double th, double& psi, double& tri) {   // products would overflow: plain sums
+  double s1 = 0.0, s2 = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < y; ++k) { const double d = th + (double)k; s1 += 1.0 / d; s2 += 1.0 / (d * d); }
+  psi = s1; tri = s2;
+}
+SC_HD void psi_tri_diff(int y, double th, double& psi, double& tri) {
+  if (y == 0) { psi = 0.0; tri = 0.0; return; }
   if (y < kSmallCount) {
-    double s = 0.0;
-    for (int k = 0; k < y; ++k) { double d = th + (double)k; s += 1.0 / (d * d); }
-    return s;
+    if (th < 1e10) {
+      double n1 = 1.0, d1 = th, n2 = 1.0, d2 = th * th;      // k = 0
+#pragma unroll 1
+      for (int k = 1; k < y; ++k) {
+        const double x = th + (double)k, x2 = x * x;
+        n1 = n1 * x + d1; d1 *= x;
+        n2 = n2 * x2 + d2; d2 *= x2;
+      }
+      psi = n1 / d1;
+      tri = n2 / d2;
+    } else {
+      psi_tri_diff_sums(y, th, psi, tri);
+    }
+    return;
   }
-  return trigamma_pos(th) - trigamma_pos(th + (double)y);
+  psi_tri_diff_big(y, th, psi, tri);
 }
 
 // Stirling remainder of lgamma: lgamma(x) = (x - 1/2) log x - x + log(2 pi)/2 + stirling_corr(x), x >= 20.
@@ -75,32 +100,41 @@ SC_HD double stirling_corr(double x) {
   return (1.0 / 12.0 + f * (-1.0 / 360.0 + f * (1.0 / 1260.0 + f * (-1.0 / 1680.0 + f * (1.0 / 1188.0))))) / x;
 }
 // Lambda(y, sigma) = lgamma(th + y) - lgamma(th) + y log(sigma) = sum_{k=1}^{y-1} log1p(k sigma), th = 1/sigma.
-// The mu-free part of the NB log-likelihood; cancellation-free for any th.
-SC_HD double nb_lambda(int y, double sigma, double th) {
-  if (y <= 8) {
-    double s = 0.0;
-    for (int k = 1; k < y; ++k) s += log1p((double)k * sigma);
-    return s;
-  }
+// The mu-free part of the NB log-likelihood; cancellation-free for any th.  Small counts: one log of the product.
+SC_HDN double nb_lambda_big(int y, double sigma, double th) {
   double yd = (double)y;
   if (th >= 20.0) {
     return (th + yd - 0.5) * log1p(yd * sigma) - yd + stirling_corr(th + yd) - stirling_corr(th);
   }
   return lgamma(th + yd) - lgamma(th) + yd * log(sigma);
 }
+SC_HD double nb_lambda(int y, double sigma, double th) {
+  if (y <= 1) return 0.0;
+  if (y < kSmallCount && sigma < 1e20) {
+    double prod = 1.0 + sigma;
+#pragma unroll 1
+    for (int k = 2; k < y; ++k) prod *= 1.0 + (double)k * sigma;
+    return log(prod);
+  }
+  return nb_lambda_big(y, sigma, th);
+}
 
 // ---- tiny dense symmetric algebra, n <= NS, row-major a[NS*NS].
 // Cholesky A = L L^T in place (lower); returns false on a non-positive pivot.
 template <int NS>
-SC_HD bool chol_factor(int n, double* a) {
+SC_HDN bool chol_factor(int n, double* a) {
+#pragma unroll 1
   for (int k = 0; k < n; ++k) {
     double x = a[k * NS + k];
+#pragma unroll 1
     for (int j = 0; j < k; ++j) x -= a[k * NS + j] * a[k * NS + j];
     if (!(x > 0.0)) return false;
     x = sqrt(x);
     a[k * NS + k] = x;
+#pragma unroll 1
     for (int i = k + 1; i < n; ++i) {
       double s = a[i * NS + k];
+#pragma unroll 1
       for (int j = 0; j < k; ++j) s -= a[i * NS + j] * a[k * NS + j];
       a[i * NS + k] = s / x;
     }
@@ -108,25 +142,32 @@ SC_HD bool chol_factor(int n, double* a) {
   return true;
 }
 template <int NS>
-SC_HD void chol_solve(int n, const double* l, const double* b, double* x) {
+SC_HDN void chol_solve(int n, const double* l, const double* b, double* x) {
+#pragma unroll 1
   for (int i = 0; i < n; ++i) {
     double s = b[i];
+#pragma unroll 1
     for (int j = 0; j < i; ++j) s -= l[i * NS + j] * x[j];
     x[i] = s / l[i * NS + i];
   }
+#pragma unroll 1
   for (int i = n - 1; i >= 0; --i) {
     double s = x[i];
+#pragma unroll 1
     for (int j = i + 1; j < n; ++j) s -= l[j * NS + i] * x[j];
     x[i] = s / l[i * NS + i];
   }
 }
 // inverse from the Cholesky factor: inv (row-major, full symmetric)
 template <int NS>
-SC_HD void chol_inverse(int n, const double* l, double* inv) {
+SC_HDN void chol_inverse(int n, const double* l, double* inv) {
   double e[NS], col[NS];
+#pragma unroll 1
   for (int c = 0; c < n; ++c) {
+#pragma unroll 1
     for (int i = 0; i < n; ++i) e[i] = (i == c) ? 1.0 : 0.0;
     chol_solve<NS>(n, l, e, col);
+#pragma unroll 1
     for (int i = 0; i < n; ++i) inv[i * NS + c] = col[i];
   }
 }

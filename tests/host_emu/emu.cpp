@@ -32,7 +32,7 @@ struct HostExec {
       const int b = bucket[i];
       double mu_out = 0.0;
       const double o = (W->use_offset && off) ? off[i] : 0.0;
-      cell_contrib<MODE>(y[i], u[i], o, W->a[b], W->c[b], W->sigma, W->theta, mu ? mu[i] : 0.0, W->acc[b], W->sc, mu_out);
+      cell_contrib<MODE>(y[i], u[i], o, W->a[b], W->c[b], W->sigma, W->theta, mu ? mu[i] : 0.0, W->want_ll != 0, W->acc[b], W->sc, mu_out);
       if (MODE == PASS_EMIT) mu[i] = mu_out;
     }
   }
@@ -107,6 +107,7 @@ extern "C" double emu_pchisq_upper(double q, double df) { return pchisq_upper(q,
 extern "C" double emu_r_round(double x, int digits) { return r_round_digits(x, digits); }
 extern "C" double emu_digamma(double x) { return digamma_pos(x); }
 extern "C" double emu_trigamma(double x) { return trigamma_pos(x); }
+extern "C" void emu_psi_tri(int y, double th, double* out) { psi_tri_diff(y, th, out[0], out[1]); }
 extern "C" double emu_nb_lambda(int y, double sigma) { return nb_lambda(y, sigma, 1.0 / sigma); }
 extern "C" void emu_default_opts(sclane_opts* o) {
   std::memset(o, 0, sizeof(*o));

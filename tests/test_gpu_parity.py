@@ -172,7 +172,9 @@ def test_null_stats_and_score_sweep_vs_dense_oracle(golden_inputs):
                     if np.isnan(ref):
                         assert np.isnan(mine)
                     else:
-                        assert abs(mine - ref) < 1e-7 * max(1.0, abs(ref)), (gi, t, mine, ref)
+                        # candidates nearly collinear with the basis lose ~1e3 in the Schur complement D - C'AC, in the dense
+                        # and in the bucket-moment evaluation alike; round(score, 6) is the granularity that matters
+                        assert abs(mine - ref) < 1e-6 * max(1.0, abs(ref)), (gi, t, mine, ref)
 
 
 def test_eigen_dropins():
