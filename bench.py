@@ -33,6 +33,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_sweep_moments launch from the committed ncu --set full capture
+# (profiles/), per config; None until measured.
+TRAFFIC_PER_LAUNCH = {"c2": None, "c5": None}
+
 CONFIGS = {
     "c2": {"genes": 2000, "cells": 10000, "name": "synthetic NB 2,000 genes x 10,000 cells, 1 lineage, GLM (BASELINE configs[1])"},
     "c5": {"genes": 256, "cells": 200000, "name": "synthetic NB, 200,000 cells (BASELINE configs[4] cell count), gene subset per GPU"},
@@ -250,10 +254,13 @@ def main():
             "gpu_launches": int(launches),
             "wall_ms_per_step": wall_step,
             "stage_ms_per_step": {k: v / args.steps for k, v in prof_acc["ms"].items()},
-            "roofline": {"kernel": "k_stage<STAGE_SWEEP> (score sweep, K2)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind, "traffic": None,
+            "roofline": {"kernel": "k_sweep_moments (score sweep streaming kernel, K2a)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind, "traffic": TRAFFIC_PER_LAUNCH.get(args.config),
                          "bytes_per_launch": prof_acc["sweep_bytes"] / max(1, sweep_launches),
-                         "ms_per_launch": sweep_ms / max(1, sweep_launches)},
+                         "ms_per_launch": sweep_ms / max(1, sweep_launches),
+                         "select_kernel_ms_per_launch": prof_acc["ms"]["select"] / max(1, prof_acc["launches"]["select"]),
+                         "note": "achieved = algorithmic bytes (12 B/cell per swept gene-iteration + 8 B/cell per launch) / CUDA-event time "
+                                 "of the k_sweep_moments launches; k_sweep_select (K2b, per-gene O(T p^2) algebra) is timed separately"},
             "clocks": sampler.result(),
         }
         if args.cpu_sample > 0:

@@ -140,13 +140,14 @@ void sclane_reset_launch_count(void);
 
 /* Device-side timing of the last sclane_test_dynamic*() call on this process (CUDA events on the
  * library's own stream, summed over batches / lineages / GPUs): what bench.py's roofline uses. */
-#define SCLANE_NSTAGES 6
-#define SCLANE_STAGE_GATHER 0      /* sort permutation + per-gene constants              */
-#define SCLANE_STAGE_FWD_FIT 1     /* K1 forward null fits (stat_out_score_glm_null)     */
-#define SCLANE_STAGE_SWEEP 2       /* K2 score sweep (score_fun_glm x T x {one, both})   */
-#define SCLANE_STAGE_BACKWARD 3    /* K4 backward WIC pass                               */
-#define SCLANE_STAGE_FINAL 4       /* K5 final + null glm.nb                             */
-#define SCLANE_STAGE_COPY 5        /* H2D of counts + D2H of records                     */
+#define SCLANE_NSTAGES 7
+#define SCLANE_STAGE_GATHER 0      /* sort permutation + per-gene constants                                  */
+#define SCLANE_STAGE_FWD_FIT 1     /* K1 forward null fits (stat_out_score_glm_null)                         */
+#define SCLANE_STAGE_SWEEP 2       /* K2a score sweep, streaming kernel k_sweep_moments (HBM bound)          */
+#define SCLANE_STAGE_BACKWARD 3    /* K4 backward WIC pass                                                   */
+#define SCLANE_STAGE_FINAL 4       /* K5 final + null glm.nb                                                 */
+#define SCLANE_STAGE_COPY 5        /* H2D of counts + D2H of records                                         */
+#define SCLANE_STAGE_SELECT 6      /* K2b score sweep, per-gene algebra + selection tree (k_sweep_select)    */
 typedef struct sclane_profile {
   double  ms[SCLANE_NSTAGES];          /* device milliseconds per stage                                   */
   int64_t launches[SCLANE_NSTAGES];    /* kernel launches (memcpys for SCLANE_STAGE_COPY) per stage        */
@@ -157,6 +158,8 @@ typedef struct sclane_profile {
   double  wall_ms;                     /* host wall clock of the call                                      */
 } sclane_profile;
 void sclane_get_profile(sclane_profile* out);
+/* frees the per-device work buffers the library keeps between calls */
+void sclane_release(void);
 
 /* ---------------------------------------------------------------------------------------
  * The hot path.  Replaces the cluster set-up, FBM creation and the foreach() of

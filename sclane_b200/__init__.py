@@ -10,11 +10,11 @@ lib()  # fail loudly at import time when the CUDA library has not been built
 from .api import (  # noqa: E402
     ScLANE, candidate_knots, createCellOffset, device_count, eigenMapMatMult, eigenMapMatrixInvert,
     eigenMapPseudoInverse, get_profile, getResultsDE, launch_count, link_preds, marge2, modelLRT,
-    reset_launch_count, run_records, score_fun_glm_sweep, stat_out_score_glm_null, testDynamic, testSlope,
+    release, reset_launch_count, run_records, score_fun_glm_sweep, stat_out_score_glm_null, testDynamic, testSlope,
 )
 
 __all__ = [
     "LIB_PATH", "SclaneError", "ScLANE", "candidate_knots", "createCellOffset", "device_count", "eigenMapMatMult",
     "eigenMapMatrixInvert", "eigenMapPseudoInverse", "get_profile", "getResultsDE", "launch_count", "link_preds", "marge2",
-    "modelLRT", "reset_launch_count", "run_records", "score_fun_glm_sweep", "stat_out_score_glm_null", "testDynamic", "testSlope",
+    "modelLRT", "release", "reset_launch_count", "run_records", "score_fun_glm_sweep", "stat_out_score_glm_null", "testDynamic", "testSlope",
 ]

@@ -99,7 +99,7 @@ class SclaneLineageInfo(C.Structure):
 # every symbol include/sclane_b200.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = [
     "sclane_abi_version", "sclane_device_count", "sclane_default_opts", "sclane_record_size",
-    "sclane_launch_count", "sclane_reset_launch_count",
+    "sclane_launch_count", "sclane_reset_launch_count", "sclane_get_profile", "sclane_release",
     "sclane_test_dynamic", "sclane_test_dynamic_device", "sclane_candidate_knots",
     "sclane_null_stats_glm", "sclane_score_glm", "sclane_link_preds",
     "sclane_matmul", "sclane_llt_inverse", "sclane_pinv",

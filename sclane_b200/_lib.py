@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
     L.sclane_default_opts.restype = None
     L.sclane_get_profile.argtypes = [p]
     L.sclane_get_profile.restype = None
+    L.sclane_release.restype = None
     L.sclane_test_dynamic.argtypes = [p, i64, i64, p, i32, p, C.POINTER(_abi.SclaneOpts), p, p, *err]
     L.sclane_test_dynamic.restype = i32
     L.sclane_test_dynamic_device.argtypes = [p, i32, i64, i64, p, i32, p, C.POINTER(_abi.SclaneOpts), p, p, *err]

@@ -107,13 +107,18 @@ def reset_launch_count() -> None:
     lib().sclane_reset_launch_count()
 
 
+def release() -> None:
+    """Free the per-device work buffers the library keeps between calls."""
+    lib().sclane_release()
+
+
 class _Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 6), ("launches", C.c_int64 * 6), ("sweep_bytes", C.c_double),
+    _fields_ = [("ms", C.c_double * 7), ("launches", C.c_int64 * 7), ("sweep_bytes", C.c_double),
                 ("sweep_gene_iters", C.c_int64), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
                 ("wall_ms", C.c_double)]
 
 
-STAGE_NAMES = ["gather", "fwd_fit", "sweep", "backward", "final", "copy"]
+STAGE_NAMES = ["gather", "fwd_fit", "sweep", "backward", "final", "copy", "select"]
 
 
 def get_profile() -> dict:

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <map>
 #include <mutex>
 #include <thread>
 
@@ -60,6 +61,37 @@ struct DevBuf {
   ~DevBuf() { release(); }
 };
 
+// Per-device cache of the large work buffers (and one stream): cudaMalloc / cudaFree cost milliseconds each,
+// which is a visible share of a 2,000-gene call.  Buffers only grow; sclane_release() frees them.
+struct DevicePool {
+  struct Slot { void* p = nullptr; size_t bytes = 0; bool host = false; };
+  std::map<std::string, Slot> slots;
+  cudaStream_t stream = nullptr;
+  void* get(const std::string& name, size_t bytes, bool pinned_host = false) {
+    Slot& sl = slots[name];
+    if (sl.bytes >= bytes && sl.p) return sl.p;
+    if (sl.p) { if (sl.host) cudaFreeHost(sl.p); else cudaFree(sl.p); sl.p = nullptr; sl.bytes = 0; }
+    if (bytes == 0) return nullptr;
+    const size_t want = bytes + bytes / 8;           // a little slack so that slightly larger calls reuse the buffer
+    if (pinned_host) { if (cudaHostAlloc(&sl.p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); CK(cudaHostAlloc(&sl.p, bytes, cudaHostAllocDefault)); sl.bytes = bytes; sl.host = true; return sl.p; } }
+    else { if (cudaMalloc(&sl.p, want) != cudaSuccess) { cudaGetLastError(); sl.p = nullptr; CK(cudaMalloc(&sl.p, bytes)); sl.bytes = bytes; sl.host = false; return sl.p; } }
+    sl.bytes = want; sl.host = pinned_host;
+    return sl.p;
+  }
+  size_t held() const { size_t t = 0; for (auto& kv : slots) if (!kv.second.host) t += kv.second.bytes; return t; }
+  void release() {
+    for (auto& kv : slots) if (kv.second.p) { if (kv.second.host) cudaFreeHost(kv.second.p); else cudaFree(kv.second.p); }
+    slots.clear();
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+  }
+};
+std::mutex g_pool_mu;
+std::map<int, DevicePool> g_pools;
+DevicePool& pool_for(int device) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  return g_pools[device];
+}
+
 struct EventTimer {
   std::vector<cudaEvent_t> ev;
   std::vector<int> stage;     // stage of interval [i, i+1)
@@ -85,19 +117,21 @@ struct EventTimer {
 };
 
 struct DevicePlan {
-  DevBuf<int> perm;
-  DevBuf<double> u, off;
-  DevBuf<Lineage> lin;
-  void upload(const LineagePlan& P, cudaStream_t s) {
-    perm.alloc(P.perm.size());
-    u.alloc(P.u.size());
-    lin.alloc(1);
-    CK(cudaMemcpyAsync(perm.p, P.perm.data(), P.perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(u.p, P.u.data(), P.u.size() * sizeof(double), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(lin.p, &P.L, sizeof(Lineage), cudaMemcpyHostToDevice, s));
+  int* perm = nullptr;
+  double* u = nullptr;
+  double* off = nullptr;
+  Lineage* lin = nullptr;
+  void upload(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
+    perm = (int*)pool.get("perm", P.perm.size() * sizeof(int));
+    u = (double*)pool.get("u", P.u.size() * sizeof(double));
+    lin = (Lineage*)pool.get("lineage", sizeof(Lineage));
+    CK(cudaMemcpyAsync(perm, P.perm.data(), P.perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(u, P.u.data(), P.u.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(lin, &P.L, sizeof(Lineage), cudaMemcpyHostToDevice, s));
+    off = nullptr;
     if (!P.off.empty()) {
-      off.alloc(P.off.size());
-      CK(cudaMemcpyAsync(off.p, P.off.data(), P.off.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+      off = (double*)pool.get("off", P.off.size() * sizeof(double));
+      CK(cudaMemcpyAsync(off, P.off.data(), P.off.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     }
   }
 };
@@ -109,6 +143,9 @@ void launch_stage(const StageArgs& A, cudaStream_t s) {
   g_launches.fetch_add(1);
 }
 
+// K2 = k_sweep_moments (streaming, HBM bound) + k_sweep_select (warp per gene).  `first` also gathers the y moments.
+void launch_sweep(const StageArgs& A, bool first, cudaStream_t s, EventTimer* tm, sclane_profile* prof);
+
 int forward_iterations(int M) { return (M - 1 + 1) / 2; }   // m = 1, 3, 5, ... until m >= M (marge2.R:752-757)
 
 // Run genes [g0, g1) of one lineage on one device.  Exactly one of h_counts / d_counts is non-null;
@@ -118,34 +155,32 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
                int lin_idx, sclane_profile& prof) {
   if (g1 <= g0) return;
   CK(cudaSetDevice(device));
-  cudaStream_t s;
-  CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+  DevicePool& pool = pool_for(device);
+  if (!pool.stream) CK(cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking));
+  cudaStream_t s = pool.stream;
   DevicePlan D;
-  D.upload(P, s);
+  D.upload(P, pool, s);
   const Lineage& L = P.L;
   const int64_t G = g1 - g0;
-  // batch size from free memory: raw (host path) + sorted counts + mu + records
+  // batch size from free memory (+ what the pool already holds): raw (host path) + sorted counts + mu + moments + records
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t per_gene = (h_counts ? (size_t)n_cells * 4 : 0) + (size_t)L.Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats);
-  size_t budget = (size_t)((double)free_b * 0.6);
+  const size_t per_gene = (h_counts ? (size_t)n_cells * 4 : 0) + (size_t)L.Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
+                          (size_t)NBMAX * NACC * 8;
+  size_t budget = (size_t)((double)(free_b + pool.held()) * 0.6);
   const size_t cap = (size_t)24 << 30;
   if (budget > cap) budget = cap;
   int64_t B = (int64_t)(budget / per_gene);
   if (o.genes_per_batch > 0 && o.genes_per_batch < B) B = o.genes_per_batch;
   if (B > G) B = G;
   if (B < 1) throw CudaFail{"not enough free device memory for a single gene"};
-  DevBuf<int> d_raw, d_ys;
-  DevBuf<double> d_mu;
-  DevBuf<GeneStats> d_stats;
-  DevBuf<GeneOutDev> d_out;
-  if (h_counts) d_raw.alloc((size_t)B * (size_t)n_cells);
-  d_ys.alloc((size_t)B * (size_t)L.Npad);
-  d_mu.alloc((size_t)B * (size_t)L.Npad);
-  d_stats.alloc((size_t)B);
-  d_out.alloc((size_t)B);
-  std::vector<GeneOutDev> h_out((size_t)B);
+  int* d_raw = h_counts ? (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4) : nullptr;
+  int* d_ys = (int*)pool.get("ys", (size_t)B * (size_t)L.Npad * 4);
+  double* d_mu = (double*)pool.get("mu", (size_t)B * (size_t)L.Npad * 8);
+  double* d_mom = (double*)pool.get("mom", (size_t)B * (size_t)NBMAX * NACC * 8);
+  GeneStats* d_stats = (GeneStats*)pool.get("stats", (size_t)B * sizeof(GeneStats));
+  GeneOutDev* d_out = (GeneOutDev*)pool.get("out", (size_t)B * sizeof(GeneOutDev));
+  GeneOutDev* h_out = (GeneOutDev*)pool.get("h_out", (size_t)B * sizeof(GeneOutDev), true);
   const int n_iter = forward_iterations(o.M);
   EventTimer tm(s);
   for (int64_t b0 = g0; b0 < g1; b0 += B) {
@@ -154,28 +189,26 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     tm.mark(SCLANE_STAGE_COPY);
     const int* raw = nullptr;
     if (h_counts) {
-      CK(cudaMemcpyAsync(d_raw.p, h_counts + (size_t)b0 * (size_t)n_cells, (size_t)nb * (size_t)n_cells * 4, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_raw, h_counts + (size_t)b0 * (size_t)n_cells, (size_t)nb * (size_t)n_cells * 4, cudaMemcpyHostToDevice, s));
       prof.h2d_bytes += (double)nb * (double)n_cells * 4.0;
       prof.launches[SCLANE_STAGE_COPY]++;
-      raw = d_raw.p;
+      raw = d_raw;
     } else {
       raw = d_counts + (size_t)b0 * (size_t)n_cells;
     }
     tm.mark(SCLANE_STAGE_GATHER);
-    k_gather_stats<<<nb, kThreads, 0, s>>>(raw, (long long)n_cells, D.perm.p, L.N, L.Npad, d_ys.p, d_stats.p, d_out.p, nb);
+    k_gather_stats<<<nb, kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
     CK(cudaGetLastError());
     g_launches.fetch_add(1);
     prof.launches[SCLANE_STAGE_GATHER]++;
     StageArgs A;
-    A.lineage = D.lin.p; A.ys = d_ys.p; A.u = D.u.p; A.off = D.off.p; A.mu = d_mu.p; A.stats = d_stats.p; A.out = d_out.p;
-    A.scores = nullptr; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
+    A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = D.off; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
+    A.scores = nullptr; A.mom = d_mom; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
     for (int it = 0; it < n_iter; ++it) {
       tm.mark(SCLANE_STAGE_FWD_FIT);
       launch_stage<STAGE_FWD_FIT>(A, s);
       prof.launches[SCLANE_STAGE_FWD_FIT]++;
-      tm.mark(SCLANE_STAGE_SWEEP);
-      launch_stage<STAGE_SWEEP>(A, s);
-      prof.launches[SCLANE_STAGE_SWEEP]++;
+      launch_sweep(A, it == 0, s, &tm, &prof);
     }
     tm.mark(SCLANE_STAGE_BACKWARD);
     launch_stage<STAGE_BACKWARD>(A, s);
@@ -184,7 +217,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     launch_stage<STAGE_FINAL>(A, s);
     prof.launches[SCLANE_STAGE_FINAL]++;
     tm.mark(SCLANE_STAGE_COPY);
-    CK(cudaMemcpyAsync(h_out.data(), d_out.p, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_out, d_out, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
     prof.d2h_bytes += (double)nb * sizeof(GeneOutDev);
     prof.launches[SCLANE_STAGE_COPY]++;
     tm.mark(-1);
@@ -192,7 +225,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     tm.collect(prof);
     for (int i = 0; i < nb; ++i) {
       GeneOut go;
-      go.st = h_out[(size_t)i].st; go.alt = h_out[(size_t)i].alt; go.null = h_out[(size_t)i].null;
+      go.st = h_out[i].st; go.alt = h_out[i].alt; go.null = h_out[i].null;
       sclane_record& r = out[((b0 - out_g0) + i) * n_lineages + lin_idx];
       finalize_record(go, L, r);
       // sweeps actually run for this gene: one per forward iteration it entered
@@ -202,6 +235,20 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     }
     prof.sweep_bytes += 8.0 * (double)L.N * (double)n_iter;
   }
+}
+
+void launch_sweep(const StageArgs& A, bool first, cudaStream_t s, EventTimer* tm, sclane_profile* prof) {
+  if (tm) tm->mark(SCLANE_STAGE_SWEEP);
+  if (first) k_sweep_moments<true><<<A.n_genes, kSweepThreads, 0, s>>>(A.lineage, A.ys, A.mu, A.u, A.out, A.mom, A.n_genes);
+  else k_sweep_moments<false><<<A.n_genes, kSweepThreads, 0, s>>>(A.lineage, A.ys, A.mu, A.u, A.out, A.mom, A.n_genes);
+  CK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  if (prof) prof->launches[SCLANE_STAGE_SWEEP]++;
+  if (tm) tm->mark(SCLANE_STAGE_SELECT);
+  k_sweep_select<<<(A.n_genes + kSelectWarps - 1) / kSelectWarps, kSelectWarps * 32, 0, s>>>(A);
+  CK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  if (prof) prof->launches[SCLANE_STAGE_SELECT]++;
 }
 
 int check_opts(const sclane_opts* o, char* errbuf, size_t errlen) {
@@ -551,6 +598,14 @@ void sclane_get_profile(sclane_profile* out) {
   *out = g_prof;
 }
 
+void sclane_release(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (auto& kv : g_pools) {
+    if (cudaSetDevice(kv.first) == cudaSuccess) kv.second.release();
+  }
+  g_pools.clear();
+}
+
 int32_t sclane_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
                             const double* size_factor, const sclane_opts* opts, sclane_record* out,
                             sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
@@ -589,28 +644,33 @@ int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_
   if (!model_from_terms(term_kind, term_knot_idx, n_terms, n_knots, m, errbuf, errlen)) return SCLANE_ERR_ARG;
   try {
     CK(cudaSetDevice(device));
-    cudaStream_t s = 0;
+    DevicePool& pool = pool_for(device);
+    if (!pool.stream) CK(cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking));
+    cudaStream_t s = pool.stream;
     DevicePlan D;
-    D.upload(P, s);
+    D.upload(P, pool, s);
     const Lineage& L = P.L;
     const int nb = (int)n_genes;
-    DevBuf<int> d_raw, d_ys; DevBuf<double> d_mu; DevBuf<GeneStats> d_stats; DevBuf<GeneOutDev> d_out;
-    d_raw.alloc((size_t)nb * n_cells); d_ys.alloc((size_t)nb * L.Npad); d_mu.alloc((size_t)nb * L.Npad); d_stats.alloc(nb); d_out.alloc(nb);
-    CK(cudaMemcpyAsync(d_raw.p, counts, (size_t)nb * n_cells * 4, cudaMemcpyHostToDevice, s));
-    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw.p, (long long)n_cells, D.perm.p, L.N, L.Npad, d_ys.p, d_stats.p, d_out.p, nb);
+    int* d_raw = (int*)pool.get("raw", (size_t)nb * n_cells * 4);
+    int* d_ys = (int*)pool.get("ys", (size_t)nb * L.Npad * 4);
+    double* d_mu = (double*)pool.get("mu", (size_t)nb * L.Npad * 8);
+    GeneStats* d_stats = (GeneStats*)pool.get("stats", (size_t)nb * sizeof(GeneStats));
+    GeneOutDev* d_out = (GeneOutDev*)pool.get("out", (size_t)nb * sizeof(GeneOutDev));
+    CK(cudaMemcpyAsync(d_raw, counts, (size_t)nb * n_cells * 4, cudaMemcpyHostToDevice, s));
+    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
     CK(cudaGetLastError()); g_launches.fetch_add(1);
     std::vector<GeneOutDev> h((size_t)nb);
-    CK(cudaMemcpyAsync(h.data(), d_out.p, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h.data(), d_out, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     for (auto& g : h) g.st.fwd = m;                       // preset basis; fwd_iters = 0 => cold start
-    CK(cudaMemcpyAsync(d_out.p, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_out, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
     StageArgs A;
-    A.lineage = D.lin.p; A.ys = d_ys.p; A.u = D.u.p; A.off = nullptr; A.mu = d_mu.p; A.stats = d_stats.p; A.out = d_out.p;
-    A.scores = nullptr; A.n_genes = nb; A.M = 5; A.tols_score = 1e-5; A.use_offset = 0;
-    launch_stage<STAGE_NULLSTATS>(A, s);
-    CK(cudaMemcpyAsync(h.data(), d_out.p, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
+    A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = nullptr; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
+    A.scores = nullptr; A.mom = nullptr; A.n_genes = nb; A.M = 5; A.tols_score = 1e-5; A.use_offset = 0;
+    launch_stage<STAGE_FWD_FIT>(A, s);
+    CK(cudaMemcpyAsync(h.data(), d_out, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
     std::vector<double> hmu;
-    if (mu_out) { hmu.resize((size_t)nb * L.Npad); CK(cudaMemcpyAsync(hmu.data(), d_mu.p, hmu.size() * 8, cudaMemcpyDeviceToHost, s)); }
+    if (mu_out) { hmu.resize((size_t)nb * L.Npad); CK(cudaMemcpyAsync(hmu.data(), d_mu, hmu.size() * 8, cudaMemcpyDeviceToHost, s)); }
     CK(cudaStreamSynchronize(s));
     for (int g = 0; g < nb; ++g) {
       const bool bad = (h[(size_t)g].st.error != 0);
@@ -635,31 +695,38 @@ int32_t sclane_score_glm(const int32_t* counts, const double* mu, int64_t n_cell
   if (!model_from_terms(term_kind, term_knot_idx, n_terms, n_knots, m, errbuf, errlen)) return SCLANE_ERR_ARG;
   try {
     CK(cudaSetDevice(device));
-    cudaStream_t s = 0;
+    DevicePool& pool = pool_for(device);
+    if (!pool.stream) CK(cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking));
+    cudaStream_t s = pool.stream;
     DevicePlan D;
-    D.upload(P, s);
+    D.upload(P, pool, s);
     const Lineage& L = P.L;
     const int nb = (int)n_genes;
-    DevBuf<int> d_raw, d_ys; DevBuf<double> d_mu_raw, d_mu, d_scores; DevBuf<GeneStats> d_stats; DevBuf<GeneOutDev> d_out;
-    d_raw.alloc((size_t)nb * n_cells); d_ys.alloc((size_t)nb * L.Npad); d_mu_raw.alloc((size_t)nb * n_cells); d_mu.alloc((size_t)nb * L.Npad);
-    d_stats.alloc(nb); d_out.alloc(nb); d_scores.alloc((size_t)nb * 2 * L.T);
-    CK(cudaMemcpyAsync(d_raw.p, counts, (size_t)nb * n_cells * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d_mu_raw.p, mu, (size_t)nb * n_cells * 8, cudaMemcpyHostToDevice, s));
-    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw.p, (long long)n_cells, D.perm.p, L.N, L.Npad, d_ys.p, d_stats.p, d_out.p, nb);
+    int* d_raw = (int*)pool.get("raw", (size_t)nb * n_cells * 4);
+    int* d_ys = (int*)pool.get("ys", (size_t)nb * L.Npad * 4);
+    double* d_mu_raw = (double*)pool.get("mu_raw", (size_t)nb * n_cells * 8);
+    double* d_mu = (double*)pool.get("mu", (size_t)nb * L.Npad * 8);
+    double* d_mom = (double*)pool.get("mom", (size_t)nb * NBMAX * NACC * 8);
+    double* d_scores = (double*)pool.get("scores", (size_t)nb * 2 * L.T * 8);
+    GeneStats* d_stats = (GeneStats*)pool.get("stats", (size_t)nb * sizeof(GeneStats));
+    GeneOutDev* d_out = (GeneOutDev*)pool.get("out", (size_t)nb * sizeof(GeneOutDev));
+    CK(cudaMemcpyAsync(d_raw, counts, (size_t)nb * n_cells * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_mu_raw, mu, (size_t)nb * n_cells * 8, cudaMemcpyHostToDevice, s));
+    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
     CK(cudaGetLastError()); g_launches.fetch_add(1);
-    k_gather_f64<<<nb, 256, 0, s>>>(d_mu_raw.p, (long long)n_cells, D.perm.p, L.N, L.Npad, d_mu.p, nb);
+    k_gather_f64<<<nb, 256, 0, s>>>(d_mu_raw, (long long)n_cells, D.perm, L.N, L.Npad, d_mu, nb);
     CK(cudaGetLastError()); g_launches.fetch_add(1);
     std::vector<GeneOutDev> h((size_t)nb);
-    CK(cudaMemcpyAsync(h.data(), d_out.p, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h.data(), d_out, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     for (int g = 0; g < nb; ++g) { h[(size_t)g].st.fwd = m; h[(size_t)g].st.sigma = sigma[g]; h[(size_t)g].st.error = 0; }
-    CK(cudaMemcpyAsync(d_out.p, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_out, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
     StageArgs A;
-    A.lineage = D.lin.p; A.ys = d_ys.p; A.u = D.u.p; A.off = nullptr; A.mu = d_mu.p; A.stats = d_stats.p; A.out = d_out.p;
-    A.scores = d_scores.p; A.n_genes = nb; A.M = 99; A.tols_score = 1e-5; A.use_offset = 0;
-    launch_stage<STAGE_SCOREONLY>(A, s);
+    A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = nullptr; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
+    A.scores = d_scores; A.mom = d_mom; A.n_genes = nb; A.M = 99; A.tols_score = 1e-5; A.use_offset = 0;
+    launch_sweep(A, true, s, nullptr, nullptr);
     std::vector<double> hs((size_t)nb * 2 * L.T);
-    CK(cudaMemcpyAsync(hs.data(), d_scores.p, hs.size() * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hs.data(), d_scores, hs.size() * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     std::memcpy(scores_out, hs.data(), hs.size() * 8);
   } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }

@@ -117,6 +117,7 @@ struct Work {
   double bw_wic[PMAX], bw_cum;
   // sweep scores (NaN = NA)
   double sw_one[TMAX], sw_both[TMAX];
+  double sw_one_r[TMAX], sw_both_r[TMAX];   // round(score, 6), computed alongside the scores
   // alpha/gamma tables of the current model's terms (coop_set_model)
   double tal[PMAX][NBMAX], tga[PMAX][NBMAX];
   int want_ll;                 // PASS_IRLS: also accumulate the log-likelihood (sc[2])
@@ -572,12 +573,14 @@ SC_HD bool all_na(const double* v, int n) {
   for (int i = 0; i < n; ++i) if (v[i] == v[i]) return false;
   return true;
 }
-SC_HD int which_max_round6(const double* v, int n, bool last) {
+// which.max over round(score, 6) (vr holds the rounded values, NaN = NA): first maximum, or the last one for the
+// `tail(which(max == round(score, 6)), 1)` idiom.
+SC_HD int which_max_round6(const double* vr, int n, bool last) {
   double m = -INFINITY;
   int idx = -1;
   for (int i = 0; i < n; ++i) {
-    if (!(v[i] == v[i])) continue;
-    double r = r_round(v[i], 1e6);
+    const double r = vr[i];
+    if (!(r == r)) continue;
     if (r > m || idx < 0) { m = r; idx = i; }
     else if (last && r == m) idx = i;
   }
@@ -588,19 +591,19 @@ SC_HD int which_max_round6(const double* v, int n, bool last) {
 // first iteration (interaction scores are the constant -1e5, :244), 1 afterwards (the "interaction with
 // the intercept" scores duplicate the additive ones, :247-307).  Returns false for the breakFlag exit;
 // else trunc_type (1|2) and knot index (may be -1 = R subscript error).
-SC_HDN bool select_candidate(const double* one, const double* both, int T, int in_set, int& trunc_type, int& kidx) {
+SC_HDN bool select_candidate(const double* one, const double* both, const double* one_r, const double* both_r, int T, int in_set,
+                             int& trunc_type, int& kidx) {
   double one_int_c[TMAX], both_int_c[TMAX];
-  for (int i = 0; i < T; ++i) {
-    one_int_c[i] = in_set ? one[i] : -1e5;
-    both_int_c[i] = in_set ? both[i] : -1e5;
-  }
-  const double* one_int = one_int_c;
-  const double* both_int = both_int_c;
+  for (int i = 0; i < T; ++i) { one_int_c[i] = -1e5; both_int_c[i] = -1e5; }     // rounds to itself
+  const double* one_int = in_set ? one : one_int_c;
+  const double* both_int = in_set ? both : both_int_c;
+  const double* one_int_r = in_set ? one_r : one_int_c;
+  const double* both_int_r = in_set ? both_r : both_int_c;
   const bool bi_na = all_na(both_int, T), oi_na = all_na(one_int, T);
   const bool ba_na = all_na(both, T), oa_na = all_na(one, T);
   const double mx_bi = rmax_na(both_int, T), mx_oi = rmax_na(one_int, T);
   const double mx_ba = rmax_na(both, T), mx_oa = rmax_na(one, T);
-#define SEL(tt, vec, last) do { trunc_type = (tt); kidx = which_max_round6((vec), T, (last)); return true; } while (0)
+#define SEL(tt, vec, last) do { trunc_type = (tt); kidx = which_max_round6((vec##_r), T, (last)); return true; } while (0)
   if (bi_na && oi_na) {                                            // :368
     if (!ba_na && !oa_na) { if (mx_ba > mx_oa) SEL(2, both, true); SEL(1, one, true); }
     if (ba_na && !oa_na) SEL(1, one, false);
@@ -711,7 +714,7 @@ SC_HDN void forward_select(const Lineage& L, GeneState& st, Work& W) {
   W.flag = 0;
   int trunc_type = 0, kidx = -1;
   const int in_set = st.fwd.n > 1 ? 1 : 0;
-  if (!select_candidate(W.sw_one, W.sw_both, L.T, in_set, trunc_type, kidx)) { st.fwd_done = 1; st.fwd_stop = 1; return; }
+  if (!select_candidate(W.sw_one, W.sw_both, W.sw_one_r, W.sw_both_r, L.T, in_set, trunc_type, kidx)) { st.fwd_done = 1; st.fwd_stop = 1; return; }
   if (kidx < 0) { st.fwd_done = 1; st.fwd_stop = 5; st.error |= SCLANE_NOTE_NUMERIC; return; }
   const bool pair = trunc_type == 2;
   const double score2 = pair ? W.sw_both[kidx] : W.sw_one[kidx];   // the re-scoring at :665-675 recomputes this same number
@@ -1117,8 +1120,8 @@ struct ScoreFn {
   Work* W;
   SC_HD void operator()(int i) const {
     const int T = L->T;
-    if (i < T) W->sw_one[i] = sweep_score(*L, *m, *W, i, false);
-    else if (i < 2 * T) W->sw_both[i - T] = sweep_score(*L, *m, *W, i - T, true);
+    if (i < T) { const double v = sweep_score(*L, *m, *W, i, false); W->sw_one[i] = v; W->sw_one_r[i] = r_round(v, 1e6); }
+    else if (i < 2 * T) { const double v = sweep_score(*L, *m, *W, i - T, true); W->sw_both[i - T] = v; W->sw_both_r[i - T] = r_round(v, 1e6); }
   }
 };
 
@@ -1148,18 +1151,12 @@ SC_HDN void gene_forward_fit(E& ex, const Lineage& L, const GeneStats& gstat, Ge
 
 // K2: the score sweep (score_fun_glm.R:21-54 for every knot and both candidate shapes), the
 // selection tree, the stat_out check and the forward bookkeeping (marge2.R:182-758).
+// The part of K2 after the moments are in W.acc (rows 0..4: weighted moments of this iteration, rows 5..6:
+// the y moments): B'WB inverse, all 2T scores, selection tree, stat_out check, bookkeeping.  Runs on a CTA
+// (host harness / k_stage) or on a single warp (k_sweep_select).
 template <class E>
-SC_HDN void gene_sweep(E& ex, const Lineage& L, const GeneStats& gstat, GeneState& st, Work& W, int M, double tols_score) {
-  ex.sync();
-  if (st.fwd_done || st.error) return;
-  if (ex.leader()) {
-    W.sigma = st.sigma;
-    W.theta = st.sigma > 0.0 ? 1.0 / st.sigma : 0.0;
-    W.use_offset = 0;
-    W.passes++;
-  }
+SC_HDN void gene_sweep_select(E& ex, const Lineage& L, const GeneStats& gstat, GeneState& st, Work& W, int M, double tols_score) {
   coop_set_model(ex, L, st.fwd, W);
-  ex.template pass<PASS_SWEEP>();
   coop_system(ex, L, st.fwd, W, 0, -1, -1);                 // B'WB
   if (ex.leader()) W.flag = sweep_invert(st.fwd, W) ? 1 : 0;
   ex.sync();
@@ -1179,6 +1176,21 @@ SC_HDN void gene_sweep(E& ex, const Lineage& L, const GeneStats& gstat, GeneStat
   ex.sync();
   if (ex.leader()) forward_accept(L, st, W, gstat, M, tols_score);
   ex.sync();
+}
+
+template <class E>
+SC_HDN void gene_sweep(E& ex, const Lineage& L, const GeneStats& gstat, GeneState& st, Work& W, int M, double tols_score) {
+  ex.sync();
+  if (st.fwd_done || st.error) return;
+  if (ex.leader()) {
+    W.sigma = st.sigma;
+    W.theta = st.sigma > 0.0 ? 1.0 / st.sigma : 0.0;
+    W.use_offset = 0;
+    W.passes++;
+  }
+  ex.sync();
+  ex.template pass<PASS_SWEEP>();
+  gene_sweep_select(ex, L, gstat, st, W, M, tols_score);
 }
 
 // K4

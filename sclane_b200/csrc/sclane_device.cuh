@@ -167,78 +167,10 @@ struct DevExec {
     combine<NA, NS>(T);
   }
 
-  // HBM-bound pass (the score sweep): 128-cell tiles, 128-bit coalesced loads of counts (int4), coordinates and
-  // fitted means (2 x double2 each), four cells per lane in flight.
-  __device__ __noinline__ void pass_sweep() {
-    constexpr int NA = PassTraits<PASS_SWEEP>::NA;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Lineage& Lr = *L;
-    const int N = Lr.N, T = Lr.T;
-    const double sigma = W->sigma;
-    double* myslot = &slot[warp][0][0];
-    for (int i = lane; i < (T + 1) * NACC; i += 32) myslot[i] = 0.0;
-    __syncwarp();
-    double acc[NACC], sc[NSC];
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    const int ntiles = (N + 127) >> 7;
-    const int t0 = (int)(((long long)ntiles * warp) / kWarps);
-    const int t1 = (int)(((long long)ntiles * (warp + 1)) / kWarps);
-    if (t0 < t1) {
-      int cur_b = 0;
-      const int first = t0 << 7;
-      while (cur_b < T && Lr.bstart[cur_b + 1] <= first) ++cur_b;
-      int b_hi = Lr.bstart[cur_b + 1];
-      for (int t = t0; t < t1; ++t) {
-        const int tile_lo = t << 7;
-        const int i0 = tile_lo + (lane << 2);
-        const int4 y4 = __ldg(reinterpret_cast<const int4*>(y + i0));
-        const double2 ua = __ldg(reinterpret_cast<const double2*>(u + i0));
-        const double2 ub = __ldg(reinterpret_cast<const double2*>(u + i0 + 2));
-        const double2 ma = __ldg(reinterpret_cast<const double2*>(mu + i0));
-        const double2 mb = __ldg(reinterpret_cast<const double2*>(mu + i0 + 2));
-        const int yv[4] = {y4.x, y4.y, y4.z, y4.w};
-        const double uv[4] = {ua.x, ua.y, ub.x, ub.y};
-        const double mv[4] = {ma.x, ma.y, mb.x, mb.y};
-        const int tile_end = min(tile_lo + 128, N);
-        double mo;
-        if (tile_lo + 128 <= b_hi && tile_lo + 128 <= N) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) cell_contrib<PASS_SWEEP>(yv[j], uv[j], 0.0, 0.0, 0.0, sigma, 0.0, mv[j], false, acc, sc, mo);
-        } else {
-          for (;;) {
-            const int lo = Lr.bstart[cur_b];
-            const int hi = min(b_hi, tile_end);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = i0 + j;
-              if (i >= lo && i < hi) cell_contrib<PASS_SWEEP>(yv[j], uv[j], 0.0, 0.0, 0.0, sigma, 0.0, mv[j], false, acc, sc, mo);
-            }
-            if (hi >= tile_end) break;
-#pragma unroll
-            for (int k = 0; k < NA; ++k) {
-              const double v = warp_sum(acc[k]);
-              if (lane == 0) myslot[cur_b * NACC + k] += v;
-              acc[k] = 0.0;
-            }
-            ++cur_b;
-            b_hi = Lr.bstart[cur_b + 1];
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < NA; ++k) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) myslot[cur_b * NACC + k] += v;
-      }
-    }
-    combine<NA, 0>(T);
-  }
-
   template <int MODE>
   __device__ __forceinline__ void pass() {
-    if (MODE == PASS_SWEEP) pass_sweep();
-    else pass_scalar<MODE>();
+    static_assert(MODE != PASS_SWEEP, "the sweep streams through k_sweep_moments, not through a CTA pass");
+    pass_scalar<MODE>();
   }
 };
 
@@ -258,14 +190,15 @@ struct StageArgs {
   double* mu;                  // [B][Npad]
   const GeneStats* stats;      // [B]
   GeneOutDev* out;             // [B]
-  double* scores;              // optional [B][2][T] dump of the sweep scores, or nullptr
+  double* scores;              // optional [B][2][T] dump of the sweep scores (k_sweep_select), or nullptr
+  double* mom;                 // [B][NBMAX][NACC] sweep moments (k_sweep_moments -> k_sweep_select)
   int n_genes;
   int M;
   double tols_score;
   int use_offset;
 };
 
-enum Stage : int { STAGE_FWD_FIT = 0, STAGE_SWEEP = 1, STAGE_BACKWARD = 2, STAGE_FINAL = 3, STAGE_NULLSTATS = 4, STAGE_SCOREONLY = 5 };
+enum Stage : int { STAGE_FWD_FIT = 0, STAGE_BACKWARD = 2, STAGE_FINAL = 3 };
 
 template <int STAGE>
 __global__ void __launch_bounds__(kThreads, 2) k_stage(StageArgs A) {
@@ -296,15 +229,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_stage(StageArgs A) {
   __syncthreads();
   const size_t row = (size_t)g * (size_t)Ls.Npad;
   DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, stage, stage_b};
-  if (STAGE == STAGE_FWD_FIT || STAGE == STAGE_NULLSTATS) {
+  if (STAGE == STAGE_FWD_FIT) {
     gene_forward_fit(ex, Ls, gs, st, W);
-  } else if (STAGE == STAGE_SWEEP || STAGE == STAGE_SCOREONLY) {
-    gene_sweep(ex, Ls, gs, st, W, A.M, A.tols_score);
-    if (A.scores != nullptr) {
-      __syncthreads();
-      double* o = A.scores + (size_t)g * 2 * Ls.T;
-      for (int i = threadIdx.x; i < Ls.T; i += kThreads) { o[i] = W.sw_one[i]; o[Ls.T + i] = W.sw_both[i]; }
-    }
   } else if (STAGE == STAGE_BACKWARD) {
     gene_backward(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_FINAL) {
@@ -317,6 +243,299 @@ __global__ void __launch_bounds__(kThreads, 2) k_stage(StageArgs A) {
     int* d2 = reinterpret_cast<int*>(&A.out[g].st);
     const int* s2 = reinterpret_cast<const int*>(&st);
     for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kThreads) d2[i] = s2[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2a: the score sweep's streaming kernel.  One CTA per gene; reads the gene's sorted counts (int32) and fitted
+// means (fp64) once -- 12 B per cell, the algorithmic traffic of score_fun_glm -- and reduces them
+// to the per-bucket moments  sum w, sum w u, sum w u^2, sum r, sum r u  (w = mu/(1+mu sigma), r = (y-mu)/(1+mu sigma);
+// stat_out_score_glm_null.R:27-30, score_fun_glm.R:40,44) and, on the first forward iteration (WITH_Y), sum y, sum y u
+// for the OLS check of stat_out().  Nothing else happens here: the O(T p^2) algebra is k_sweep_select's.
+//   * 128-bit coalesced streaming loads (ld.global.nc.L1::no_allocate) for counts and means; the bucket-local
+//     coordinate u is shared by every gene and stays L1/L2 resident;
+//   * four cells per lane per tile, bucket moments in registers, flushed at the <= T bucket boundaries.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int4 ld_stream_i4(const int* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ld_stream_d2(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+// 1/x for x >= 1 (x = 1 + sigma mu): hardware seed + two Newton steps, no special-case handling needed.
+__device__ __forceinline__ double rcp_ge1(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// Tuned on B200 with tools/sweep_ablation.sh (profiles/r01_sweep_ablation.txt): 4 warps per CTA at 8 CTAs/SM, no software
+// prefetch and the plain masked boundary loop beat every other combination tried at 10,000 cells per gene.
+#ifndef SCLANE_SWEEP_WARPS
+#define SCLANE_SWEEP_WARPS 4
+#endif
+#ifndef SCLANE_SWEEP_MINB
+#define SCLANE_SWEEP_MINB 8
+#endif
+#ifndef SCLANE_SWEEP_PREFETCH
+#define SCLANE_SWEEP_PREFETCH 0
+#endif
+// ablation switches for tools/stream_probe.cu (all 1 in the product build)
+#ifndef SCLANE_SWEEP_DO_FLUSH
+#define SCLANE_SWEEP_DO_FLUSH 1
+#endif
+#ifndef SCLANE_SWEEP_DO_BOUNDARY
+#define SCLANE_SWEEP_DO_BOUNDARY 1
+#endif
+#ifndef SCLANE_SWEEP_DO_EPILOGUE
+#define SCLANE_SWEEP_DO_EPILOGUE 1
+#endif
+constexpr int kSweepWarps = SCLANE_SWEEP_WARPS;
+constexpr int kSweepThreads = kSweepWarps * 32;
+
+struct SweepTile {      // one lane's share of a 128-cell tile: 4 consecutive cells
+  int4 y;
+  double2 ma, mb, ua, ub;
+};
+__device__ __forceinline__ SweepTile sweep_load(const int* y, const double* mu, const double* u, int i0) {
+  SweepTile t;
+  t.y = ld_stream_i4(y + i0);
+  t.ma = ld_stream_d2(mu + i0);
+  t.mb = ld_stream_d2(mu + i0 + 2);
+  t.ua = __ldg(reinterpret_cast<const double2*>(u + i0));
+  t.ub = __ldg(reinterpret_cast<const double2*>(u + i0 + 2));
+  return t;
+}
+
+#ifndef SCLANE_SWEEP_CELL2
+#define SCLANE_SWEEP_CELL2 0
+#endif
+// One CTA per gene, kSweepWarps warps; each warp streams a contiguous run of 128-cell tiles with the running
+// bucket's moments in registers and reduces them (shuffle tree) into its shared-memory slot at bucket boundaries.
+// A tile that contains a boundary feeds two register sets in one sweep (running bucket / next bucket).
+template <bool WITH_Y>
+__global__ void __launch_bounds__(kSweepThreads, SCLANE_SWEEP_MINB)
+k_sweep_moments(const Lineage* __restrict__ lineage, const int* __restrict__ ys, const double* __restrict__ mu_all,
+                const double* __restrict__ u, const GeneOutDev* __restrict__ out, double* __restrict__ mom, int n_genes) {
+  constexpr int NA = WITH_Y ? 7 : 5;
+  __shared__ int bstart[NBMAX + 1];
+  __shared__ double slot[kSweepWarps][NBMAX][NACC];
+  const int g = blockIdx.x;
+  if (g >= n_genes) return;
+  const GeneState& st = out[g].st;
+  if (st.fwd_done || st.error) return;                 // block-uniform
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = lineage->N, T = lineage->T, Npad = lineage->Npad;
+  const double sigma = st.sigma;
+  const int* __restrict__ y = ys + (size_t)g * (size_t)Npad;
+  const double* __restrict__ mu = mu_all + (size_t)g * (size_t)Npad;
+  const int ntiles = (N + 127) >> 7;
+  const int t0 = (int)(((long long)ntiles * warp) / kSweepWarps);
+  const int t1 = (int)(((long long)ntiles * (warp + 1)) / kSweepWarps);
+  // the first tile's loads are issued before the shared-memory prologue so that their latency overlaps it
+  SweepTile cur;
+  if (t0 < t1) cur = sweep_load(y, mu, u, (t0 << 7) + (lane << 2));
+  for (int i = threadIdx.x; i <= NBMAX; i += kSweepThreads) bstart[i] = lineage->bstart[i];
+  double* myslot = &slot[warp][0][0];
+  for (int i = lane; i < (T + 1) * NACC; i += 32) myslot[i] = 0.0;
+  __syncthreads();
+  double acc[NA];
+#pragma unroll
+  for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+  auto flush = [&](int b) {                            // bucket boundary: warp-shuffle tree, lane 0 owns the slot
+#if SCLANE_SWEEP_DO_FLUSH
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      const double v = warp_sum(acc[k]);
+      if (lane == 0) myslot[b * NACC + k] += v;
+      acc[k] = 0.0;
+    }
+#endif
+  };
+  auto cell = [&](int yi, double ui, double mi) {
+    const double yd = (double)yi;
+    const double inv = rcp_ge1(fma(sigma, mi, 1.0));
+    const double w = mi * inv, r = (yd - mi) * inv;
+    const double wu = w * ui;
+    acc[0] += w; acc[1] += wu; acc[2] = fma(wu, ui, acc[2]);
+    acc[3] += r; acc[4] = fma(r, ui, acc[4]);
+    if (WITH_Y) { acc[5] += yd; acc[6] = fma(yd, ui, acc[6]); }
+  };
+  if (t0 < t1) {
+    int cur_b = 0;
+    const int first = t0 << 7;
+    while (cur_b < T && bstart[cur_b + 1] <= first) ++cur_b;
+    int b_hi = bstart[cur_b + 1];
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+      const int tile_lo = t << 7;
+      const int i0 = tile_lo + (lane << 2);
+#if SCLANE_SWEEP_PREFETCH
+      SweepTile nxt = cur;
+      if (t + 1 < t1) nxt = sweep_load(y, mu, u, i0 + 128);        // software pipeline: next tile in flight
+#else
+      if (t > t0) cur = sweep_load(y, mu, u, i0);
+#endif
+      if (!SCLANE_SWEEP_DO_BOUNDARY || (tile_lo + 128 <= b_hi && tile_lo + 128 <= N)) {
+        cell(cur.y.x, cur.ua.x, cur.ma.x); cell(cur.y.y, cur.ua.y, cur.ma.y);
+        cell(cur.y.z, cur.ub.x, cur.mb.x); cell(cur.y.w, cur.ub.y, cur.mb.y);
+      } else {
+        const int yv[4] = {cur.y.x, cur.y.y, cur.y.z, cur.y.w};
+        const double uv[4] = {cur.ua.x, cur.ua.y, cur.ub.x, cur.ub.y};
+        const double mv[4] = {cur.ma.x, cur.ma.y, cur.mb.x, cur.mb.y};
+        const int tile_end = min(tile_lo + 128, N);
+#if SCLANE_SWEEP_CELL2
+        // one sweep of the tile: cells below `hi` go to the running bucket, cells in [hi, hi2) to the next one
+        const int hi = min(b_hi, tile_end);
+        const int hi2 = cur_b < T ? min(bstart[cur_b + 2], tile_end) : hi;
+        double nx[NA];
+#pragma unroll
+        for (int k = 0; k < NA; ++k) nx[k] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j;
+          const double ca = (i < hi) ? 1.0 : 0.0, cn = (i >= hi && i < hi2) ? 1.0 : 0.0;
+          const double yd = (double)yv[j];
+          const double inv = rcp_ge1(fma(sigma, mv[j], 1.0));
+          const double w = mv[j] * inv, r = (yd - mv[j]) * inv;
+          const double wu = w * uv[j], wuu = wu * uv[j], ru = r * uv[j];
+          acc[0] = fma(ca, w, acc[0]); acc[1] = fma(ca, wu, acc[1]); acc[2] = fma(ca, wuu, acc[2]);
+          acc[3] = fma(ca, r, acc[3]); acc[4] = fma(ca, ru, acc[4]);
+          nx[0] = fma(cn, w, nx[0]); nx[1] = fma(cn, wu, nx[1]); nx[2] = fma(cn, wuu, nx[2]);
+          nx[3] = fma(cn, r, nx[3]); nx[4] = fma(cn, ru, nx[4]);
+          if (WITH_Y) {
+            const double yu = yd * uv[j];
+            acc[5] = fma(ca, yd, acc[5]); acc[6] = fma(ca, yu, acc[6]);
+            nx[5] = fma(cn, yd, nx[5]); nx[6] = fma(cn, yu, nx[6]);
+          }
+        }
+        if (hi < tile_end) {
+          flush(cur_b);
+#pragma unroll
+          for (int k = 0; k < NA; ++k) acc[k] = nx[k];
+          ++cur_b;
+          b_hi = bstart[cur_b + 1];
+          // buckets narrower than the rest of the tile (rare): masked sweeps, one bucket at a time
+#pragma unroll 1
+          while (b_hi < tile_end) {
+            flush(cur_b);
+            const int lo3 = b_hi;
+            ++cur_b;
+            b_hi = bstart[cur_b + 1];
+            const int hi3 = min(b_hi, tile_end);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = i0 + j;
+              if (i >= lo3 && i < hi3) cell(yv[j], uv[j], mv[j]);
+            }
+          }
+        }
+#else
+#pragma unroll 1
+        for (;;) {
+          const int lo = bstart[cur_b];
+          const int hi = min(b_hi, tile_end);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j;
+            if (i >= lo && i < hi) cell(yv[j], uv[j], mv[j]);
+          }
+          if (hi >= tile_end) break;
+          flush(cur_b);
+          ++cur_b;
+          b_hi = bstart[cur_b + 1];
+        }
+#endif
+      }
+#if SCLANE_SWEEP_PREFETCH
+      cur = nxt;
+#endif
+    }
+#if SCLANE_SWEEP_DO_FLUSH
+    flush(cur_b);
+#else
+    { double s = 0.0; for (int k = 0; k < NA; ++k) s += acc[k]; if (s == 123.456) myslot[0] = s; }
+#endif
+  }
+#if SCLANE_SWEEP_DO_EPILOGUE
+  __syncthreads();
+  double* dst = mom + (size_t)g * (size_t)(NBMAX * NACC);
+  for (int i = threadIdx.x; i < (T + 1) * NACC; i += kSweepThreads) {
+    if ((i % NACC) < NA) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kSweepWarps; ++w) s += (&slot[w][0][0])[i];
+      dst[i] = s;
+    }
+  }
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b: one WARP per gene.  From the moments: A = (B'WB)^-1, the 2T scores (lane = knot), the selection tree of
+// marge2.R:368-587, the stat_out check and the forward bookkeeping.
+// ---------------------------------------------------------------------------------------------
+struct WarpExec {
+  __device__ __forceinline__ bool leader() const { return (threadIdx.x & 31) == 0; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  template <class F>
+  __device__ __forceinline__ void par_for(int n, F f) const {
+    for (int i = threadIdx.x & 31; i < n; i += 32) f(i);
+  }
+};
+
+constexpr int kSelectWarps = 4;
+
+__global__ void __launch_bounds__(kSelectWarps * 32)
+k_sweep_select(StageArgs A) {
+  __shared__ Lineage Ls;
+  __shared__ Work Wall[kSelectWarps];
+  __shared__ GeneState stall[kSelectWarps];
+  {
+    const int* src = reinterpret_cast<const int*>(A.lineage);
+    int* dst = reinterpret_cast<int*>(&Ls);
+    for (int i = threadIdx.x; i < (int)(sizeof(Lineage) / sizeof(int)); i += kSelectWarps * 32) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = blockIdx.x * kSelectWarps + warp;
+  if (g >= A.n_genes) return;                                 // warp-uniform; no block-wide barrier below
+  Work& W = Wall[warp];
+  GeneState& st = stall[warp];
+  {
+    const int* s2 = reinterpret_cast<const int*>(&A.out[g].st);
+    int* d2 = reinterpret_cast<int*>(&st);
+    for (int i = lane; i < (int)(sizeof(GeneState) / sizeof(int)); i += 32) d2[i] = s2[i];
+  }
+  __syncwarp();
+  if (st.fwd_done || st.error) return;                        // warp-uniform
+  const double* m = A.mom + (size_t)g * (size_t)(NBMAX * NACC);
+  double* wacc = &W.acc[0][0];
+  for (int i = lane; i < (Ls.T + 1) * NACC; i += 32) wacc[i] = m[i];
+  if (lane == 0) { W.passes = 0; W.flag = 0; }
+  __syncwarp();
+  WarpExec ex;
+  const GeneStats gs = A.stats[g];
+  gene_sweep_select(ex, Ls, gs, st, W, A.M, A.tols_score);
+  __syncwarp();
+  if (A.scores != nullptr) {
+    double* o = A.scores + (size_t)g * 2 * Ls.T;
+    for (int i = lane; i < Ls.T; i += 32) { o[i] = W.sw_one[i]; o[Ls.T + i] = W.sw_both[i]; }
+  }
+  if (lane == 0) st.passes += 1;
+  __syncwarp();
+  {
+    int* d2 = reinterpret_cast<int*>(&A.out[g].st);
+    const int* s2 = reinterpret_cast<const int*>(&st);
+    for (int i = lane; i < (int)(sizeof(GeneState) / sizeof(int)); i += 32) d2[i] = s2[i];
   }
 }
 
