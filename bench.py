@@ -86,9 +86,11 @@ class ClockSampler(threading.Thread):
 
 def cpu_baseline(counts, pt, n_sample: int):
     """The oracle (kind "port") on the first n_sample genes, single process, on this box's host cores."""
+    from threadpoolctl import threadpool_limits
     from oracle.test_dynamic import test_dynamic as oracle_td
     t0 = time.time()
-    oracle_td(counts[:n_sample], pt, None, None, keep_preds=False)
+    with threadpool_limits(limits=1):
+        oracle_td(counts[:n_sample], pt, None, None, keep_preds=False)
     dt = time.time() - t0
     return {"value": n_sample / dt, "unit": "genes/s", "cores": 1, "kind": "port",
             "sample": f"{n_sample} genes x {counts.shape[1]} cells of the same synthetic workload, numpy oracle, 1 process, {dt:.1f} s"}
@@ -103,7 +105,7 @@ def run_reference(args, cfg):
     from concurrent.futures import ProcessPoolExecutor
     from sclane_b200 import synth
     cores = os.cpu_count() or 1
-    per_step = max(cores, 2 * cores if cfg["cells"] <= 20000 else cores)
+    per_step = 8 * cores if cfg["cells"] <= 20000 else cores
     counts, pt, _ = synth.make_counts(per_step, cfg["cells"], seed=312)
     chunks = [(counts[i::cores], pt) for i in range(cores)]
     times = []
@@ -126,9 +128,12 @@ def run_reference(args, cfg):
 
 
 def _oracle_chunk(a):
+    # one gene per worker at a time, like the reference's PSOCK workers; keep BLAS single-threaded per process
+    from threadpoolctl import threadpool_limits
     from oracle.test_dynamic import test_dynamic as oracle_td
     counts, pt = a
-    oracle_td(counts, pt, None, None, keep_preds=False)
+    with threadpool_limits(limits=1):
+        oracle_td(counts, pt, None, None, keep_preds=False)
     return counts.shape[0]
 
 

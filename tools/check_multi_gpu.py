@@ -1,0 +1,13 @@
+"""In-library gene sharding over all visible GPUs must give records bit-identical to one GPU."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sclane_b200 as sb
+from sclane_b200 import synth
+n = sb.device_count()
+counts, pt, _ = synth.make_counts(301, 5000, seed=5)
+a = sb.testDynamic(counts, pt, n_gpus=1, preds="none")
+b = sb.testDynamic(counts, pt, n_gpus=n, preds="none")
+bad = sum(bytes(a.records[i])[:-8] != bytes(b.records[i])[:-8] for i in range(301))
+print(f"devices {n}: {bad} records differ between 1 and {n} GPUs; profile {b.profile['ms']}")
+assert bad == 0
