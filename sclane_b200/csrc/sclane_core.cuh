@@ -75,6 +75,18 @@ struct GeneStats {
   int pad;
 };
 
+// Count-indexed tables of the mu-free special-function terms of the NB likelihood at the pass's theta / sigma.
+// Most cells of single-cell data have small counts, so a pass looks these up instead of looping / dividing per cell;
+// counts >= kTab fall back to the (out-of-line) direct evaluation.
+constexpr int kTab = 64;
+struct PassTabs {
+  double psi[kTab];    // psi(th + y) - psi(th)            = sum_{k<y} 1/(th+k)
+  double tri[kTab];    // trigamma(th) - trigamma(th + y)  = sum_{k<y} 1/(th+k)^2
+  double lam[kTab];    // lgamma(th+y) - lgamma(th) + y log(sigma) = sum_{k=1}^{y-1} log1p(k sigma)
+  double l1p[kTab];    // log1p(sigma y)
+  double stage[3 * kTab];   // scratch of coop_set_tables
+};
+
 // Shared workspace of one gene (shared memory on device).  The leader thread mutates it between
 // syncs; every thread reads it after a sync to take the same branches.
 struct Work {
@@ -164,6 +176,40 @@ SC_HD void coop_set_eta(E& ex, const Lineage& L, const Model& m, Work& W, const 
   ex.par_for(L.T + 1, fn);
   ex.sync();
 }
+// Tables for the current (W.sigma, W.theta): terms in parallel (W.H is free scratch at this point), then prefix sums
+// in ascending k (the order a serial loop would use).
+struct TabTermFn {
+  const Work* W; PassTabs* tb;
+  SC_HD void operator()(int k) const {
+    const double th = W->theta, sg = W->sigma;
+    const double d = th + (double)k;
+    tb->stage[k] = 1.0 / d;
+    tb->stage[kTab + k] = 1.0 / (d * d);
+    tb->stage[2 * kTab + k] = k >= 1 ? log1p((double)k * sg) : 0.0;
+    tb->l1p[k] = log1p(sg * (double)k);
+  }
+};
+struct TabScanFn {
+  PassTabs* tb;
+  SC_HD void operator()(int y) const {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int k = 0; k < y; ++k) { a += tb->stage[k]; b += tb->stage[kTab + k]; c += tb->stage[2 * kTab + k]; }
+    tb->psi[y] = a; tb->tri[y] = b; tb->lam[y] = c;
+  }
+};
+template <class E>
+SC_HD void coop_set_tables(E& ex, Work& W) {
+  ex.sync();
+  if (W.sigma == 0.0) return;                 // Poisson passes do not use the tables (uniform branch)
+  PassTabs* tb = ex.tabs();
+  TabTermFn t{&W, tb};
+  ex.par_for(kTab, t);
+  ex.sync();
+  TabScanFn sc{tb};
+  ex.par_for(kTab, sc);
+  ex.sync();
+}
+
 // Symmetric system from a pass: H[j][l] = <d_j, d_l> with accumulators I0..I0+2, grad[j] = <d_j, .> with J0, J0+1,
 // and (K0 >= 0) the extra column H[j][p] = <d_j, .> with K0, K0+1.  Results in W.H (NSYS stride) / W.grad.
 struct SystemFn {
@@ -240,8 +286,29 @@ SC_HD double gram_u(const Lineage& L, int kj, int tj, int kl, int tl) {
 // Per-cell contributions.  y: count, u: bucket-local coordinate, off: offset (0 if none),
 // a/c: eta parameters of the cell's bucket.  acc[NACC], sc[NSC] are the running sums.
 // ---------------------------------------------------------------------------------------------
+// reciprocal of a positive, normal-range double: hardware seed + two Newton steps on device (1 ulp), a division on host
+SC_HD double rcp_pos(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / x;
+#endif
+}
+SC_HD void tab_psi_tri(const PassTabs& tb, int y, double th, double& psi, double& tri) {
+  if (y < kTab) { psi = tb.psi[y]; tri = tb.tri[y]; }
+  else psi_tri_diff_big(y, th, psi, tri);
+}
+SC_HD double tab_lambda(const PassTabs& tb, int y, double sigma, double th) {
+  return y < kTab ? tb.lam[y] : nb_lambda_big(y, sigma, th);
+}
+
 template <int MODE>
-SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double sigma, double theta,
+SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double sigma, double theta, const PassTabs& tb,
                         double mu_in, bool want_ll, double* acc, double* sc, double& mu_out) {
   const double y = (double)yi;
   if (MODE == PASS_EMIT) {
@@ -267,27 +334,27 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
       sc[2] += y * eta - mu;
       return;
     }
-    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double inv = rcp_pos(1.0 + sigma * mu);
     const double r = (y - mu) * inv;                       // d l / d eta
     const double o = mu * (1.0 + sigma * y) * inv * inv;   // - d2 l / d eta2
     const double cc = sigma * mu * r * inv;                // - d2 l / d eta d(log sigma)
     const double lg = log1p(sigma * mu);
     double dpsi, dtri;
-    psi_tri_diff(yi, theta, dpsi, dtri);
+    tab_psi_tri(tb, yi, theta, dpsi, dtri);
     const double g = dpsi - lg - sigma * r;                                                  // d l / d theta
     const double h = -dtri + sigma - 2.0 * sigma * inv + sigma * (1.0 + sigma * y) * inv * inv;  // d2 l / d theta2
     acc[0] += o; acc[1] += o * u; acc[2] += o * u * u;
     acc[3] += r; acc[4] += r * u;
     acc[5] += cc; acc[6] += cc * u;
     sc[0] += g; sc[1] += h;
-    sc[2] += nb_lambda(yi, sigma, theta) + y * eta - (y + theta) * lg;
+    sc[2] += tab_lambda(tb, yi, sigma, theta) + y * eta - (y + theta) * lg;
     return;
   }
   if (MODE == PASS_IRLS || MODE == PASS_IRLS_START) {
     double eta, mu;
     if (MODE == PASS_IRLS_START) { mu = y + (yi == 0 ? 1.0 / 6.0 : 0.0); eta = log(mu); }   // negative.binomial()$initialize
     else { eta = a + c * u + off; mu = exp(eta); }
-    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double inv = rcp_pos(1.0 + sigma * mu);
     const double w = mu * inv;                             // mu.eta^2 / variance(mu)
     const double r = (y - mu) * inv;
     const double wz = w * (eta - off) + r;                 // w * z, z = (eta - offset) + (y - mu)/mu.eta
@@ -295,20 +362,21 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
     acc[3] += wz; acc[4] += wz * u;
     const double lg = log1p(sigma * mu);
     // dev.resids: 2 (y log(max(1,y)/mu) - (y+th) log((y+th)/(mu+th))); the y log y part is a gene constant
-    sc[0] += yi > 0 ? (-y * eta - (y + theta) * (log1p(sigma * y) - lg)) : theta * lg;
-    const double e = (y - mu) / mu;
+    const double l1py = yi < kTab ? tb.l1p[yi] : log1p(sigma * y);
+    sc[0] += yi > 0 ? (-y * eta - (y + theta) * (l1py - lg)) : theta * lg;
+    const double e = (y - mu) * rcp_pos(mu);
     sc[1] += e * e;                                        // theta.ml start: n / sum((y/mu - 1)^2)
-    if (want_ll) sc[2] += nb_lambda(yi, sigma, theta) + y * eta - (y + theta) * lg;   // glm.nb loglik() minus sum lgamma(y+1)
+    if (want_ll) sc[2] += tab_lambda(tb, yi, sigma, theta) + y * eta - (y + theta) * lg;   // glm.nb loglik() minus sum lgamma(y+1)
     return;
   }
   if (MODE == PASS_THETA) {
     const double eta = a + c * u + off;
     const double mu = exp(eta);
-    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double inv = rcp_pos(1.0 + sigma * mu);
     const double r = (y - mu) * inv;
     const double lg = log1p(sigma * mu);
     double dpsi, dtri;
-    psi_tri_diff(yi, theta, dpsi, dtri);
+    tab_psi_tri(tb, yi, theta, dpsi, dtri);
     sc[0] += dpsi - lg - sigma * r;                                                           // theta.ml score
     sc[1] += dtri - sigma + 2.0 * sigma * inv - sigma * (1.0 + sigma * y) * inv * inv;        // theta.ml info
     return;
@@ -457,6 +525,7 @@ SC_HDN FitResult nb_mle(E& ex, const Lineage& L, const Model& m, const GeneStats
       W.passes++;
     }
     coop_set_eta(ex, L, m, W, W.beta);
+    coop_set_tables(ex, W);
     ex.template pass<PASS_FIT>();
     coop_system(ex, L, m, W, 0, 3, W.nt_poisson ? -1 : 5);
     if (ex.leader()) nb_mle_step(m, W, smin, smax);
@@ -874,8 +943,10 @@ SC_HDN int glm_fit2(E& ex, const Lineage& L, const Model& m, const GeneStats& gs
     W.gf_have_coefold = 0;        // glm.fit: coefold <- NULL (etastart/mustart start, no `start`)
     W.gf_conv = 0;
     W.flag = 0;
+    W.sigma = 1.0 / theta; W.theta = theta;
   }
   ex.sync();
+  coop_set_tables(ex, W);
   int it;
   for (it = 1; it <= kMaxitGlm; ++it) {
     coop_system(ex, L, m, W, 0, 3, -1);
@@ -985,6 +1056,7 @@ SC_HDN void theta_ml(E& ex, const Lineage& L, Work& W, double t0sum) {
     }
     ex.sync();
     if (W.flag) break;
+    coop_set_tables(ex, W);
     ex.template pass<PASS_THETA>();
     if (ex.leader()) {
       W.tm_del = W.sc[0] / W.sc[1];
@@ -1018,6 +1090,7 @@ SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gst
     out->notes = 0;
   }
   ex.sync();
+  coop_set_tables(ex, W);
   ex.template pass<PASS_IRLS_START>();
   int irls = glm_fit2(ex, L, m, gstat, W, 1.0);
   if (irls < 0) return;
@@ -1036,6 +1109,7 @@ SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gst
     W.passes++;
   }
   ex.sync();
+  coop_set_tables(ex, W);
   ex.template pass<PASS_IRLS>();
   if (ex.leader()) {
     W.nb_Lm = W.sc[2] - gstat.sum_lgamma_y1;
@@ -1076,6 +1150,7 @@ SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gst
       W.passes++;
     }
     coop_set_eta(ex, L, m, W, W.beta);
+    coop_set_tables(ex, W);
     ex.template pass<PASS_IRLS>();
     if (ex.leader()) {
       W.nb_Lm0 = W.nb_Lm;

@@ -40,6 +40,7 @@ struct DevExec {
   double* mu;                       // [Npad] fitted means of this gene (sweep input / emit output)
   double (*slot)[NBMAX][NACC];      // [kWarps] warp-private partial moments
   double (*scw)[NSC];               // [kWarps] warp-private partial scalars
+  PassTabs* tb;                     // count-indexed special-function tables of the current pass
   double (*stage)[NACC][33];        // [kWarps] staging for the (rare) register -> slot flushes
   int (*stage_b)[32];               // [kWarps] bucket of each lane during a flush
 
@@ -64,6 +65,7 @@ struct DevExec {
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ PassTabs* tabs() const { return tb; }
   template <class F>
   __device__ __forceinline__ void par_for(int n, F f) const {
     for (int i = threadIdx.x; i < n; i += kThreads) f(i);
@@ -138,7 +140,7 @@ struct DevExec {
 #pragma unroll
         for (int k = 0; k < NSC; ++k) cs[k] = 0.0;
         if (valid) {                                   // the ONLY copy of the per-cell math in this kernel
-          cell_contrib<MODE>(yi, ui, oi, W->a[b], W->c[b], sigma, theta, 0.0, want_ll, ct, cs, mo);
+          cell_contrib<MODE>(yi, ui, oi, W->a[b], W->c[b], sigma, theta, *tb, 0.0, want_ll, ct, cs, mo);
           if (MODE == PASS_EMIT) mu[i] = mo;
         }
 #pragma unroll
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stage(StageArgs A) {
   __shared__ double scw[kWarps][NSC];
   __shared__ double stage[kWarps][NACC][33];
   __shared__ int stage_b[kWarps][32];
+  __shared__ PassTabs tabs;
   const int g = blockIdx.x;
   if (g >= A.n_genes) return;
   {
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stage(StageArgs A) {
   }
   __syncthreads();
   const size_t row = (size_t)g * (size_t)Ls.Npad;
-  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, stage, stage_b};
+  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs, stage, stage_b};
   if (STAGE == STAGE_FWD_FIT) {
     gene_forward_fit(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_BACKWARD) {
@@ -484,6 +487,7 @@ k_sweep_moments(const Lineage* __restrict__ lineage, const int* __restrict__ ys,
 // marge2.R:368-587, the stat_out check and the forward bookkeeping.
 // ---------------------------------------------------------------------------------------------
 struct WarpExec {
+  __device__ __forceinline__ PassTabs* tabs() const { return nullptr; }     // the select kernel runs no pass
   __device__ __forceinline__ bool leader() const { return (threadIdx.x & 31) == 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
   template <class F>

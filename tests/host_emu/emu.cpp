@@ -19,6 +19,8 @@ struct HostExec {
   const double* off;       // may be null
   double* mu;              // [N]
   const int32_t* bucket;
+  PassTabs tabs_;
+  PassTabs* tabs() { return &tabs_; }
   bool leader() const { return true; }
   void sync() const {}
   template <int MODE>
@@ -32,7 +34,7 @@ struct HostExec {
       const int b = bucket[i];
       double mu_out = 0.0;
       const double o = (W->use_offset && off) ? off[i] : 0.0;
-      cell_contrib<MODE>(y[i], u[i], o, W->a[b], W->c[b], W->sigma, W->theta, mu ? mu[i] : 0.0, W->want_ll != 0, W->acc[b], W->sc, mu_out);
+      cell_contrib<MODE>(y[i], u[i], o, W->a[b], W->c[b], W->sigma, W->theta, tabs_, mu ? mu[i] : 0.0, W->want_ll != 0, W->acc[b], W->sc, mu_out);
       if (MODE == PASS_EMIT) mu[i] = mu_out;
     }
   }
@@ -75,7 +77,7 @@ extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t 
       if (gs.sum_y == 0.0) go.st.error |= SCLANE_NOTE_ALL_ZERO;
       Work W;
       std::memset(&W, 0, sizeof(W));
-      HostExec ex{&W, &L, y.data(), P.u.data(), P.off.empty() ? nullptr : P.off.data(), mu.data(), P.bucket.data()};
+      HostExec ex{&W, &L, y.data(), P.u.data(), P.off.empty() ? nullptr : P.off.data(), mu.data(), P.bucket.data(), PassTabs()};
       for (int it = 0; it < 4 && !go.st.fwd_done && !go.st.error; ++it) {
         gene_forward_fit(ex, L, gs, go.st, W);
         gene_sweep(ex, L, gs, go.st, W, opts->M, opts->tols_score);
