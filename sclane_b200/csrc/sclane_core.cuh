@@ -383,6 +383,71 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
   }
 }
 
+// Per-cell contributions inside a bucket where the linear predictor is constant (gamma-coefficient c_b == 0 and no
+// offset: intercept-only fits, and every bucket on the flat side of the model's hinges).  mu, 1/(1+sigma mu),
+// log1p(sigma mu) and 1/mu are computed ONCE per bucket (FlatBucket) -- no transcendental per cell.
+struct FlatBucket {
+  double eta, mu, inv, lg, rmu;
+};
+SC_HD FlatBucket make_flat_bucket(double a, double sigma) {
+  FlatBucket f;
+  f.eta = a;
+  f.mu = exp(a);
+  f.inv = sigma == 0.0 ? 1.0 : 1.0 / (1.0 + sigma * f.mu);
+  f.lg = sigma == 0.0 ? 0.0 : log1p(sigma * f.mu);
+  f.rmu = 1.0 / f.mu;
+  return f;
+}
+template <int MODE>
+SC_HD void cell_contrib_flat(int yi, double u, const FlatBucket& f, double sigma, double theta, const PassTabs& tb,
+                             bool want_ll, double* acc, double* sc, double& mu_out) {
+  const double y = (double)yi;
+  if (MODE == PASS_EMIT) { mu_out = f.mu; return; }
+  if (MODE == PASS_FIT) {
+    if (sigma == 0.0) {
+      const double r = y - f.mu;
+      acc[0] += f.mu; acc[1] += f.mu * u; acc[2] += f.mu * u * u;
+      acc[3] += r; acc[4] += r * u;
+      sc[2] += y * f.eta - f.mu;
+      return;
+    }
+    const double r = (y - f.mu) * f.inv;
+    const double o = f.mu * (1.0 + sigma * y) * f.inv * f.inv;
+    const double cc = sigma * f.mu * r * f.inv;
+    double dpsi, dtri;
+    tab_psi_tri(tb, yi, theta, dpsi, dtri);
+    const double g = dpsi - f.lg - sigma * r;
+    const double h = -dtri + sigma - 2.0 * sigma * f.inv + sigma * (1.0 + sigma * y) * f.inv * f.inv;
+    acc[0] += o; acc[1] += o * u; acc[2] += o * u * u;
+    acc[3] += r; acc[4] += r * u;
+    acc[5] += cc; acc[6] += cc * u;
+    sc[0] += g; sc[1] += h;
+    sc[2] += tab_lambda(tb, yi, sigma, theta) + y * f.eta - (y + theta) * f.lg;
+    return;
+  }
+  if (MODE == PASS_IRLS) {
+    const double w = f.mu * f.inv;
+    const double r = (y - f.mu) * f.inv;
+    const double wz = w * f.eta + r;
+    acc[0] += w; acc[1] += w * u; acc[2] += w * u * u;
+    acc[3] += wz; acc[4] += wz * u;
+    const double l1py = yi < kTab ? tb.l1p[yi] : log1p(sigma * y);
+    sc[0] += yi > 0 ? (-y * f.eta - (y + theta) * (l1py - f.lg)) : theta * f.lg;
+    const double e = (y - f.mu) * f.rmu;
+    sc[1] += e * e;
+    if (want_ll) sc[2] += tab_lambda(tb, yi, sigma, theta) + y * f.eta - (y + theta) * f.lg;
+    return;
+  }
+  if (MODE == PASS_THETA) {
+    const double r = (y - f.mu) * f.inv;
+    double dpsi, dtri;
+    tab_psi_tri(tb, yi, theta, dpsi, dtri);
+    sc[0] += dpsi - f.lg - sigma * r;
+    sc[1] += dtri - sigma + 2.0 * sigma * f.inv - sigma * (1.0 + sigma * y) * f.inv * f.inv;
+    return;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // NB maximum-likelihood fit of y ~ B - 1 (no offset): stands in for gamlss NBI
 // (stat_out_score_glm_null.R:22-25, backward_sel_WIC.R:44-47).  Joint Newton on (beta, log sigma)

@@ -14,6 +14,12 @@
 
 namespace sclane {
 
+#ifndef SCLANE_PASS_ILP2
+#define SCLANE_PASS_ILP2 0
+#endif
+#ifndef SCLANE_STAGE_MINB
+#define SCLANE_STAGE_MINB 3
+#endif
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 
@@ -117,6 +123,13 @@ struct DevExec {
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < NSC; ++k) sc[k] = 0.0;
+#if SCLANE_PASS_ILP2
+    double acc2[NACC], sc2[NSC];                       // second, independent accumulation chain
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc2[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NSC; ++k) sc2[k] = 0.0;
+#endif
     // contiguous run of 32-cell groups per warp
     const int ngroups = (N + 31) >> 5;
     const int g0 = (int)(((long long)ngroups * warp) / kWarps);
@@ -125,44 +138,85 @@ struct DevExec {
       int cur_b = 0;                       // bucket the register accumulators belong to (warp uniform)
       const int first = g0 << 5;
       while (cur_b < T && Lr.bstart[cur_b + 1] <= first) ++cur_b;
+      int b_hi = Lr.bstart[cur_b + 1];
+      double a = W->a[cur_b], c = W->c[cur_b];
+      // constant linear predictor inside the bucket (no slope term, no offset): hoist exp / log1p / reciprocals
+      constexpr bool kCanFlat = (MODE == PASS_FIT || MODE == PASS_IRLS || MODE == PASS_THETA || MODE == PASS_EMIT);
+      bool flat = kCanFlat && !use_off && c == 0.0;
+      FlatBucket fb = make_flat_bucket(flat ? a : 0.0, sigma);
+      int g = g0;
 #pragma unroll 1
-      for (int g = g0; g < g1; ++g) {
+      while (g < g1) {
         const int i = (g << 5) + lane;
+#if SCLANE_PASS_ILP2
+        if (g + 1 < g1 && (g << 5) + 64 <= b_hi) {
+          // two groups inside the running bucket (b_hi <= N: every lane valid): two independent cells per lane
+          const int y0 = __ldg(y + i), y1 = __ldg(y + i + 32);
+          const double u0 = __ldg(u + i), u1 = __ldg(u + i + 32);
+          const double o0 = use_off ? __ldg(off + i) : 0.0, o1 = use_off ? __ldg(off + i + 32) : 0.0;
+          double m0, m1;
+          cell_contrib<MODE>(y0, u0, o0, a, c, sigma, theta, *tb, 0.0, want_ll, acc, sc, m0);
+          cell_contrib<MODE>(y1, u1, o1, a, c, sigma, theta, *tb, 0.0, want_ll, acc2, sc2, m1);
+          if (MODE == PASS_EMIT) { mu[i] = m0; mu[i + 32] = m1; }
+          g += 2;
+          continue;
+        }
+#endif
+        if ((g << 5) + 32 <= b_hi) {
+          // the whole group lies inside the running bucket (b_hi <= N, so every lane is valid)
+          const int yi = __ldg(y + i);
+          const double ui = __ldg(u + i);
+          double mo;
+          if (flat) {
+            cell_contrib_flat<MODE>(yi, ui, fb, sigma, theta, *tb, want_ll, acc, sc, mo);
+          } else {
+            const double oi = use_off ? __ldg(off + i) : 0.0;
+            cell_contrib<MODE>(yi, ui, oi, a, c, sigma, theta, *tb, 0.0, want_ll, acc, sc, mo);
+          }
+          if (MODE == PASS_EMIT) mu[i] = mo;
+          g += 1;
+          continue;
+        }
+        // the group straddles a bucket boundary and/or the end of the gene (<= T + 1 times per pass)
         const bool valid = i < N;
         const int yi = __ldg(y + i);                   // rows are padded: always in bounds
         const double ui = __ldg(u + i);
         const double oi = use_off ? __ldg(off + i) : 0.0;
         int b = cur_b;                                 // this lane's bucket (cells are sorted: b >= cur_b)
         while (valid && b < T && i >= Lr.bstart[b + 1]) ++b;
-        double ct[NACC], cs[NSC], mo = 0.0;
+        double ct[NACC], mo = 0.0;
 #pragma unroll
         for (int k = 0; k < NACC; ++k) ct[k] = 0.0;
-#pragma unroll
-        for (int k = 0; k < NSC; ++k) cs[k] = 0.0;
-        if (valid) {                                   // the ONLY copy of the per-cell math in this kernel
-          cell_contrib<MODE>(yi, ui, oi, W->a[b], W->c[b], sigma, theta, *tb, 0.0, want_ll, ct, cs, mo);
+        if (valid) {
+          cell_contrib<MODE>(yi, ui, oi, W->a[b], W->c[b], sigma, theta, *tb, 0.0, want_ll, ct, sc, mo);
           if (MODE == PASS_EMIT) mu[i] = mo;
         }
-#pragma unroll
-        for (int k = 0; k < NS; ++k) sc[k] += cs[k];
         if (NA > 0) {
-          if (__all_sync(0xffffffffu, !valid || b == cur_b)) {
+#if SCLANE_PASS_ILP2
 #pragma unroll
-            for (int k = 0; k < NA; ++k) acc[k] += ct[k];
-          } else {
-            // the group straddles a bucket boundary (<= T times per pass): flush the running bucket, then the
-            // group's own contributions lane by lane into their buckets
-            flush_lanes<NA>(acc, cur_b, true, myslot, NACC);
+          for (int k = 0; k < NA; ++k) { acc[k] += acc2[k]; acc2[k] = 0.0; }
+#endif
+          flush_lanes<NA>(acc, cur_b, true, myslot, NACC);
 #pragma unroll
-            for (int k = 0; k < NA; ++k) acc[k] = 0.0;
-            flush_lanes<NA>(ct, valid ? b : cur_b, valid, myslot, NACC);
-            int b_last = valid ? b : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) b_last = max(b_last, __shfl_xor_sync(0xffffffffu, b_last, o));
-            cur_b = b_last;
-          }
+          for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+          flush_lanes<NA>(ct, valid ? b : cur_b, valid, myslot, NACC);
         }
+        int b_last = valid ? b : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b_last = max(b_last, __shfl_xor_sync(0xffffffffu, b_last, o));
+        cur_b = b_last;
+        b_hi = Lr.bstart[cur_b + 1];
+        a = W->a[cur_b]; c = W->c[cur_b];
+        flat = kCanFlat && !use_off && c == 0.0;
+        if (flat) fb = make_flat_bucket(a, sigma);
+        g += 1;
       }
+#if SCLANE_PASS_ILP2
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] += acc2[k];
+#pragma unroll
+      for (int k = 0; k < NSC; ++k) sc[k] += sc2[k];
+#endif
       if (NA > 0) flush_lanes<NA>(acc, cur_b, true, myslot, NACC);
     }
     if (NS > 0) flush_lanes<NS>(sc, 0, true, &scw[warp][0], 0);
@@ -203,7 +257,7 @@ struct StageArgs {
 enum Stage : int { STAGE_FWD_FIT = 0, STAGE_BACKWARD = 2, STAGE_FINAL = 3 };
 
 template <int STAGE>
-__global__ void __launch_bounds__(kThreads, 2) k_stage(StageArgs A) {
+__global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs A) {
   __shared__ Work W;
   __shared__ Lineage Ls;
   __shared__ GeneState st;
