@@ -47,27 +47,6 @@ struct DevExec {
   double (*slot)[NBMAX][NACC];      // [kWarps] warp-private partial moments
   double (*scw)[NSC];               // [kWarps] warp-private partial scalars
   PassTabs* tb;                     // count-indexed special-function tables of the current pass
-  double (*stage)[NACC][33];        // [kWarps] staging for the (rare) register -> slot flushes
-  int (*stage_b)[32];               // [kWarps] bucket of each lane during a flush
-
-  // Add every lane's NV values v[k] into the warp's slot of that lane's bucket.  Lanes are summed in lane
-  // order by lane k (fixed order => reproducible).  Called <= ~T + 1 times per pass per warp, so it is kept
-  // compact (a rolled loop through shared memory) instead of fast: the shuffle-tree version dominated the
-  // kernels' instruction footprint.
-  template <int NV>
-  __device__ __noinline__ void flush_lanes(const double* v, int my_b, bool valid, double* dst, int stride) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < NV; ++k) stage[warp][k][lane] = valid ? v[k] : 0.0;
-    stage_b[warp][lane] = my_b;
-    __syncwarp();
-    if (lane < NV) {
-#pragma unroll 1
-      for (int l = 0; l < 32; ++l) dst[stage_b[warp][l] * stride + lane] += stage[warp][lane][l];
-    }
-    __syncwarp();
-  }
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -75,6 +54,31 @@ struct DevExec {
   template <class F>
   __device__ __forceinline__ void par_for(int n, F f) const {
     for (int i = threadIdx.x; i < n; i += kThreads) f(i);
+  }
+
+  // Register accumulators -> the warp's shared-memory slot.  flush_uniform: every lane belongs to bucket b (shuffle
+  // tree, lane 0 adds).  flush_mixed: the lanes of a boundary group belong to buckets b_lo..b_hi (usually two): one
+  // masked shuffle tree per bucket.  Both run <= ~T + 1 times per pass per warp and sum in a fixed order.
+  template <int NV>
+  __device__ __noinline__ void flush_uniform(const double* v, int b, double* dst, int stride) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double t = warp_sum(v[k]);
+      if (lane == 0) dst[b * stride + k] += t;
+    }
+  }
+  template <int NV>
+  __device__ __noinline__ void flush_mixed(const double* v, int my_b, bool valid, int b_lo, int b_hi, double* dst, int stride) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int bb = b_lo; bb <= b_hi; ++bb) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const double t = warp_sum((valid && my_b == bb) ? v[k] : 0.0);
+        if (lane == 0) dst[bb * stride + k] += t;
+      }
+    }
   }
 
   // Cross-warp combination of the warp-private partial sums, in a fixed order (bit-reproducible).
@@ -196,14 +200,14 @@ struct DevExec {
 #pragma unroll
           for (int k = 0; k < NA; ++k) { acc[k] += acc2[k]; acc2[k] = 0.0; }
 #endif
-          flush_lanes<NA>(acc, cur_b, true, myslot, NACC);
+          flush_uniform<NA>(acc, cur_b, myslot, NACC);
 #pragma unroll
           for (int k = 0; k < NA; ++k) acc[k] = 0.0;
-          flush_lanes<NA>(ct, valid ? b : cur_b, valid, myslot, NACC);
         }
         int b_last = valid ? b : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) b_last = max(b_last, __shfl_xor_sync(0xffffffffu, b_last, o));
+        if (NA > 0) flush_mixed<NA>(ct, b, valid, cur_b, b_last, myslot, NACC);
         cur_b = b_last;
         b_hi = Lr.bstart[cur_b + 1];
         a = W->a[cur_b]; c = W->c[cur_b];
@@ -217,9 +221,9 @@ struct DevExec {
 #pragma unroll
       for (int k = 0; k < NSC; ++k) sc[k] += sc2[k];
 #endif
-      if (NA > 0) flush_lanes<NA>(acc, cur_b, true, myslot, NACC);
+      if (NA > 0) flush_uniform<NA>(acc, cur_b, myslot, NACC);
     }
-    if (NS > 0) flush_lanes<NS>(sc, 0, true, &scw[warp][0], 0);
+    if (NS > 0) flush_uniform<NS>(sc, 0, &scw[warp][0], 0);
     combine<NA, NS>(T);
   }
 
@@ -264,8 +268,6 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   __shared__ GeneStats gs;
   __shared__ double slot[kWarps][NBMAX][NACC];
   __shared__ double scw[kWarps][NSC];
-  __shared__ double stage[kWarps][NACC][33];
-  __shared__ int stage_b[kWarps][32];
   __shared__ PassTabs tabs;
   const int g = blockIdx.x;
   if (g >= A.n_genes) return;
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   }
   __syncthreads();
   const size_t row = (size_t)g * (size_t)Ls.Npad;
-  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs, stage, stage_b};
+  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs};
   if (STAGE == STAGE_FWD_FIT) {
     gene_forward_fit(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_BACKWARD) {
