@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SCLANE_ABI_VERSION 1
+#define SCLANE_ABI_VERSION 2
 #define SCLANE_PMAX 7          /* max columns of a model (intercept + hinges): M <= 7 (marge2.R:756) */
 #define SCLANE_TMAX 32         /* max candidate knots per lineage (n.knot.max, marge2.R:66; default 25) */
 #define SCLANE_MAX_GPUS 16
@@ -53,6 +53,13 @@ extern "C" {
 #define SCLANE_NOTE_ALL_ZERO 32         /* all counts zero in this lineage                         */
 #define SCLANE_NOTE_NUMERIC 64          /* non-finite intermediate (R: "missing value where TRUE/FALSE needed") */
 
+/* sclane_opts.gee_cor: working correlation of the GEE mode (stat_out_score_gee_null.R:51-60) */
+#define SCLANE_COR_INDEPENDENCE 0
+#define SCLANE_COR_EXCHANGEABLE 1
+#define SCLANE_COR_AR1 2
+#define SCLANE_GEE_PMAX 5       /* GEE mode: M <= 5 */
+#define SCLANE_GEE_SMAX 64      /* GEE mode: subjects per lineage */
+
 /* hinge direction of a model term */
 #define SCLANE_TERM_INTERCEPT 0
 #define SCLANE_TERM_TP1 1               /* (x - t)+  "Right", name h_<Lineage>_<knot>  (tp1.R:17, marge2.R:593) */
@@ -61,7 +68,8 @@ extern "C" {
 /* Arguments of testDynamic() (testDynamic.R:60-75) and marge2() (marge2.R:56-72) that reach the path. */
 typedef struct sclane_opts {
   int32_t abi_version;        /* must be SCLANE_ABI_VERSION */
-  int32_t mode;               /* 0 = GLM (is.gee = FALSE, is.glmm = FALSE).  1 = GEE: not built yet -> SCLANE_ERR_UNSUPPORTED */
+  int32_t mode;               /* 0 = GLM (is.gee = FALSE, is.glmm = FALSE).  1 = GEE (is.gee = TRUE, gee.test = "wald");
+                                 GEE needs subject ids: use sclane_test_dynamic_gee().  2 (GLMM) -> SCLANE_ERR_UNSUPPORTED */
   int32_t M;                  /* n.potential.basis.fns / marge2 M, default 5, 3 <= M <= SCLANE_PMAX */
   int32_t approx_knot;        /* approx.knot, default 1 (0 -> SCLANE_ERR_UNSUPPORTED for now) */
   int32_t n_knot_max;         /* n.knot.max, default 25, <= SCLANE_TMAX */
@@ -71,7 +79,8 @@ typedef struct sclane_opts {
   int32_t gpu_ids[SCLANE_MAX_GPUS]; /* used when n_gpus > 0 */
   int32_t genes_per_batch;    /* 0 = automatic (bounded by free device memory) */
   int32_t verbose;
-  int32_t reserved[8];
+  int32_t gee_cor;            /* cor.structure (testDynamic.R:66): SCLANE_COR_* ; default ar1 */
+  int32_t reserved[7];
 } sclane_opts;
 
 /* One record per (gene, lineage): everything testDynamic() returns for that pair except the
@@ -114,6 +123,12 @@ typedef struct sclane_record {
   int32_t n_wic;
   int32_t fit_passes;                   /* passes over the cells spent on this record */
   double  gene_time;                    /* Gene_Time surrogate: seconds of device time / genes in the batch */
+  /* GEE mode only (NaN / 0 in GLM mode).  In GEE mode se/z/p/cov are the model-based ("naive") ones of geeM::geem,
+   * test_stat/df/p_val are waldTestGEE()'s (waldTestGEE.R:24-93) and theta/loglik/deviance are NaN. */
+  double  gee_alpha, gee_phi;           /* working correlation parameter and scale of the final model */
+  double  null_gee_alpha, null_gee_phi;
+  int32_t gee_converged, gee_iters;     /* geem outer iterations of the final model */
+  int32_t null_gee_converged, null_gee_iters;
 } sclane_record;
 
 /* Per-lineage description returned to the caller (knots, cell membership). */
@@ -140,7 +155,7 @@ void sclane_reset_launch_count(void);
 
 /* Device-side timing of the last sclane_test_dynamic*() call on this process (CUDA events on the
  * library's own stream, summed over batches / lineages / GPUs): what bench.py's roofline uses. */
-#define SCLANE_NSTAGES 7
+#define SCLANE_NSTAGES 8
 #define SCLANE_STAGE_GATHER 0      /* sort permutation + per-gene constants                                  */
 #define SCLANE_STAGE_FWD_FIT 1     /* K1 forward null fits (stat_out_score_glm_null)                         */
 #define SCLANE_STAGE_SWEEP 2       /* K2a score sweep, streaming kernel k_sweep_moments (HBM bound)          */
@@ -148,6 +163,7 @@ void sclane_reset_launch_count(void);
 #define SCLANE_STAGE_FINAL 4       /* K5 final + null glm.nb                                                 */
 #define SCLANE_STAGE_COPY 5        /* H2D of counts + D2H of records                                         */
 #define SCLANE_STAGE_SELECT 6      /* K2b score sweep, per-gene algebra + selection tree (k_sweep_select)    */
+#define SCLANE_STAGE_GEE 7         /* GEE mode: the whole per-gene path (k_gee)                              */
 typedef struct sclane_profile {
   double  ms[SCLANE_NSTAGES];          /* device milliseconds per stage                                   */
   int64_t launches[SCLANE_NSTAGES];    /* kernel launches (memcpys for SCLANE_STAGE_COPY) per stage        */
@@ -194,6 +210,22 @@ int32_t sclane_test_dynamic_device(const int32_t* d_counts, int32_t device,
                                    const sclane_opts* opts,
                                    sclane_record* out, sclane_lineage_info* lineages,
                                    char* errbuf, size_t errlen);
+
+/* GEE mode of the same path (testDynamic(is.gee = TRUE, gee.test = "wald"), testDynamic.R:66-70,235-244,
+ * 296-301; marge2.R:258-268 (stat_out_score_gee_null), :438-448/:520-530 (score_fun_gee), :831-838 (final geem);
+ * backward_sel_WIC.R:36-42; waldTestGEE.R:24-93).  Same arguments as sclane_test_dynamic() plus
+ * subject_id   n_cells int32 subject labels; the cells MUST be ordered by subject (testDynamic.R:115 stops
+ *              otherwise) -> SCLANE_ERR_ARG if a label re-appears after a different one.  HOST pointer.
+ * opts->gee_cor selects the working correlation; opts->M <= SCLANE_GEE_PMAX; <= SCLANE_GEE_SMAX subjects per
+ * lineage.  gee.test = "score" and gee.bias.correct = TRUE are not built -> use the defaults.
+ * Records: see the GEE note in sclane_record. */
+int32_t sclane_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t n_genes,
+                                const double* pt, int32_t n_lineages,
+                                const int32_t* subject_id,
+                                const double* size_factor,
+                                const sclane_opts* opts,
+                                sclane_record* out, sclane_lineage_info* lineages,
+                                char* errbuf, size_t errlen);
 
 /* Candidate knots of one lineage (marge2.R:150-173 with min_span.R / max_span.R): host-side,
  * no GPU needed.  x: n doubles without NaN.  Returns the number of knots (<= SCLANE_TMAX)

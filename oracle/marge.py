@@ -319,6 +319,15 @@ def backward_sel_wic(Y, B):
     return wald, fit
 
 
+def _first_min(wic1) -> int:
+    """which(wic1 == min(wic1, na.rm = TRUE))[1] - 1; with every entry NA, R's NA subscript turns the basis into NAs and
+    the next refit fails inside try() -> "MARGE model error" (marge2.R:781-783)."""
+    hit = np.flatnonzero(np.asarray(wic1) == _nanmin(wic1))
+    if hit.size == 0:
+        raise RuntimeError("missing value where TRUE/FALSE needed (all Wald statistics NA)")
+    return int(hit[0])
+
+
 def _nanmin(v):
     ok = ~np.isnan(v)
     return float(np.min(v[ok])) if ok.any() else float("inf")
@@ -338,7 +347,7 @@ def backward_pass(Y, X, knots, terms, trace: MargeTrace | None = None):
         trace.wald_steps.append(np.array(wic1))
     cum = _nanmin(wic1)
     WIC_vec.append(cum + 2.0 * len(cur))
-    lowest = int(np.flatnonzero(wic1 == _nanmin(wic1))[0]) + 1      # 1-based position among non-intercept cols
+    lowest = _first_min(wic1) + 1      # 1-based position among non-intercept cols
     cur = [t for j, t in enumerate(cur) if j != lowest]
     models.append(list(cur))
     for i in range(2, ncol_B):
@@ -348,7 +357,7 @@ def backward_pass(Y, X, knots, terms, trace: MargeTrace | None = None):
         cum += _nanmin(wic1)
         WIC_vec.append(cum + 2.0 * len(cur))
         if i != ncol_B - 1:
-            lowest = int(np.flatnonzero(wic1 == _nanmin(wic1))[0]) + 1
+            lowest = _first_min(wic1) + 1
             cur = [t for j, t in enumerate(cur) if j != lowest]
         else:
             cur = [Term(0)]                                       # renamed "Intercept" (:798-799)

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-SCLANE_ABI_VERSION = 1
+SCLANE_ABI_VERSION = 2
 SCLANE_PMAX = 7
 SCLANE_TMAX = 32
 SCLANE_MAX_GPUS = 16
@@ -21,6 +21,11 @@ NOTE_NUMERIC = 64
 
 TERM_INTERCEPT, TERM_TP1, TERM_TP2 = 0, 1, 2
 
+COR_INDEPENDENCE, COR_EXCHANGEABLE, COR_AR1 = 0, 1, 2
+COR_CODES = {"independence": COR_INDEPENDENCE, "exchangeable": COR_EXCHANGEABLE, "ar1": COR_AR1}
+SCLANE_GEE_PMAX = 5
+SCLANE_GEE_SMAX = 64
+
 
 class SclaneOpts(C.Structure):
     _fields_ = [
@@ -35,7 +40,8 @@ class SclaneOpts(C.Structure):
         ("gpu_ids", C.c_int32 * SCLANE_MAX_GPUS),
         ("genes_per_batch", C.c_int32),
         ("verbose", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("gee_cor", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -82,6 +88,14 @@ class SclaneRecord(C.Structure):
         ("n_wic", C.c_int32),
         ("fit_passes", C.c_int32),
         ("gene_time", C.c_double),
+        ("gee_alpha", C.c_double),
+        ("gee_phi", C.c_double),
+        ("null_gee_alpha", C.c_double),
+        ("null_gee_phi", C.c_double),
+        ("gee_converged", C.c_int32),
+        ("gee_iters", C.c_int32),
+        ("null_gee_converged", C.c_int32),
+        ("null_gee_iters", C.c_int32),
     ]
 
 
@@ -100,7 +114,7 @@ class SclaneLineageInfo(C.Structure):
 EXPORTED_SYMBOLS = [
     "sclane_abi_version", "sclane_device_count", "sclane_default_opts", "sclane_record_size",
     "sclane_launch_count", "sclane_reset_launch_count", "sclane_get_profile", "sclane_release",
-    "sclane_test_dynamic", "sclane_test_dynamic_device", "sclane_candidate_knots",
+    "sclane_test_dynamic", "sclane_test_dynamic_device", "sclane_test_dynamic_gee", "sclane_candidate_knots",
     "sclane_null_stats_glm", "sclane_score_glm", "sclane_link_preds",
     "sclane_matmul", "sclane_llt_inverse", "sclane_pinv",
 ]
@@ -119,4 +133,5 @@ def default_opts() -> SclaneOpts:
     o.n_gpus = 0
     o.genes_per_batch = 0
     o.verbose = 0
+    o.gee_cor = COR_AR1
     return o

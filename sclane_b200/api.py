@@ -113,12 +113,12 @@ def release() -> None:
 
 
 class _Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 7), ("launches", C.c_int64 * 7), ("sweep_bytes", C.c_double),
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("sweep_bytes", C.c_double),
                 ("sweep_gene_iters", C.c_int64), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
                 ("wall_ms", C.c_double)]
 
 
-STAGE_NAMES = ["gather", "fwd_fit", "sweep", "backward", "final", "copy", "select"]
+STAGE_NAMES = ["gather", "fwd_fit", "sweep", "backward", "final", "copy", "select", "gee"]
 
 
 def get_profile() -> dict:
@@ -152,9 +152,10 @@ def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None
 
 
 def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = None, device_ptr: int | None = None,
-                device: int = 0):
-    """Thin call of sclane_test_dynamic[_device]: counts int32 [genes, cells] C-contiguous (gene-major), pt float64
-    [cells, lineages].  Returns (records ctypes array [genes * lineages], lineage infos)."""
+                device: int = 0, subject_id=None):
+    """Thin call of sclane_test_dynamic[_device|_gee]: counts int32 [genes, cells] C-contiguous (gene-major), pt float64
+    [cells, lineages]; subject_id (GEE mode, opts.mode = 1): int32 per cell, cells ordered by subject.
+    Returns (records ctypes array [genes * lineages], lineage infos)."""
     L = lib()
     pt = np.asarray(pt, dtype=np.float64)
     if pt.ndim == 1:
@@ -174,8 +175,15 @@ def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = Non
         n_genes = counts.shape[0]
         recs = (_abi.SclaneRecord * (n_genes * n_lin))()
         infos = (_abi.SclaneLineageInfo * n_lin)()
-        rc = L.sclane_test_dynamic(counts.ctypes.data, n_cells, n_genes, pt_cm.ctypes.data, n_lin,
-                                   None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
+        if subject_id is not None:
+            sid = np.ascontiguousarray(subject_id, dtype=np.int32)
+            if sid.shape != (n_cells,):
+                raise ValueError("id.vec must have one entry per cell")
+            rc = L.sclane_test_dynamic_gee(counts.ctypes.data, n_cells, n_genes, pt_cm.ctypes.data, n_lin, sid.ctypes.data,
+                                           None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
+        else:
+            rc = L.sclane_test_dynamic(counts.ctypes.data, n_cells, n_genes, pt_cm.ctypes.data, n_lin,
+                                       None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
     else:
         n_genes = int(counts)  # when a device pointer is given, `counts` is the number of genes
         recs = (_abi.SclaneRecord * (n_genes * n_lin))()
@@ -364,14 +372,14 @@ def _summarize_model(rec, pt_min, pt_max):
     return {"Breakpoint": uniq, "Slope.Segment": slopes, "Trend.Segment": trends}
 
 
-def _record_to_list(rec, gene, lin_idx, info, pt_lineage, x_lineage, sf_lineage, preds, device):
+def _record_to_list(rec, gene, lin_idx, info, pt_lineage, x_lineage, sf_lineage, preds, device, is_gee=False):
     letter = LETTERS[lin_idx]
     m_ok = bool(rec.status & _abi.SCLANE_MARGE_OK)
     n_ok = bool(rec.status & _abi.SCLANE_NULL_OK)
     names = _term_names(rec, letter) if m_ok else []
     out = {
         "Gene": gene, "Lineage": letter,
-        "Test_Stat": _na(rec.test_stat), "Test_Stat_Type": "LRT",
+        "Test_Stat": _na(rec.test_stat), "Test_Stat_Type": "Wald" if is_gee else "LRT",
         "Test_Stat_Note": None if (m_ok and n_ok) else "No test performed due to model failure.",
         "Degrees_Freedom": _na(rec.df), "P_Val": _na(rec.p_val),
         "LogLik_MARGE": _na(rec.loglik), "LogLik_Null": _na(rec.null_loglik),
@@ -390,8 +398,10 @@ def _record_to_list(rec, gene, lin_idx, info, pt_lineage, x_lineage, sf_lineage,
         out["MARGE_Preds"] = None
         out["Null_Preds"] = None
     else:
-        out["MARGE_Preds"] = LazyPreds(rec, x_lineage, sf_lineage, "marge", device) if m_ok else None
-        out["Null_Preds"] = LazyPreds(rec, x_lineage, sf_lineage, "null", device) if n_ok else None
+        # GEE mode: predict.geem() returns X %*% beta without the offset (pullMARGESummary.R:38-41); se from naiv.var
+        sf_p = None if is_gee else sf_lineage
+        out["MARGE_Preds"] = LazyPreds(rec, x_lineage, sf_p, "marge", device) if m_ok else None
+        out["Null_Preds"] = LazyPreds(rec, x_lineage, sf_p, "null", device) if n_ok else None
         if preds == "eager":
             for k in ("MARGE_Preds", "Null_Preds"):
                 if out[k] is not None:
@@ -409,6 +419,9 @@ def _record_to_list(rec, gene, lin_idx, info, pt_lineage, x_lineage, sf_lineage,
     out["Gene_Dynamics"] = flat
     # extras (not in the reference's list): fitted dispersion and the record itself
     out["Theta"] = (_na(rec.theta), _na(rec.null_theta))
+    if is_gee:
+        out["GEE_Working_Correlation"] = (_na(rec.gee_alpha), _na(rec.null_gee_alpha))
+        out["GEE_Scale"] = (_na(rec.gee_phi), _na(rec.null_gee_phi))
     out["record"] = rec
     return out
 
@@ -431,15 +444,33 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
                 is_glmm: bool = False, glmm_adaptive: bool = True, id_vec=None, n_potential_basis_fns: int = 5,
                 n_cores: int = 4, approx_knot: bool = True, verbose: bool = False, random_seed: int = 312,
                 n_gpus: int = 0, gpu_ids=None, genes_per_batch: int = 0, preds: str = "lazy") -> ScLANE:
-    """testDynamic.R:60-448, GLM mode.  expr_mat: genes x cells integer counts (rows named by `genes`); pt: cells x
+    """testDynamic.R:60-448, GLM mode and GEE mode (is_gee = True with id_vec, cor_structure in {"ar1", "exchangeable",
+    "independence"}, gee_test = "wald").  expr_mat: genes x cells integer counts (rows named by `genes`); pt: cells x
     lineages pseudotime (NaN = cell not in the lineage).  `n_cores` is kept for signature compatibility; the work is
     sharded over `n_gpus` B200s instead (0 = all visible).  Returns a ScLANE dict of per-gene, per-lineage lists."""
     if expr_mat is None or pt is None:
         raise ValueError("You forgot some inputs to testDynamic().")
+    subject_id = None
     if is_gee or is_glmm:
         if id_vec is None:
             raise ValueError("You must provide a vector of IDs if you're using GEE / GLMM modes.")
-        raise SclaneError(_abi_unsupported(), "GEE / GLMM modes are not built into sclane_b200 yet; only GLM mode runs on the GPU")
+        if is_gee and is_glmm:
+            raise ValueError("is.gee and is.glmm cannot both be specified.")
+        if is_glmm:
+            raise SclaneError(_abi_unsupported(), "GLMM mode is not built into sclane_b200; GLM and GEE modes run on the GPU")
+        cor_structure = str(cor_structure).lower()
+        if cor_structure not in _abi.COR_CODES:
+            raise ValueError("GEE models require a specified correlation structure.")
+        if str(gee_test).lower() != "wald":
+            raise SclaneError(_abi_unsupported(), 'gee.test = "score" is not built into sclane_b200; use gee.test = "wald"')
+        if gee_bias_correction_method is not None:
+            raise SclaneError(_abi_unsupported(), "GEE bias correction (sandwich variance) is not built into sclane_b200")
+        ids = np.asarray(id_vec)
+        _, first = np.unique(ids, return_index=True)
+        subject_id = np.unique(ids, return_inverse=True)[1].astype(np.int32)
+        # testDynamic.R:107-118: the data must be ordered by subject
+        if np.count_nonzero(np.diff(subject_id) != 0) != len(first) - 1:
+            raise ValueError("Data must be ordered by subject, please do so before running testDynamic() with is.gee = TRUE.")
     counts = np.ascontiguousarray(expr_mat, dtype=np.int32)
     if counts.ndim != 2:
         raise ValueError("Input expr.mat must be coerceable to a matrix of integer counts.")
@@ -454,7 +485,10 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
         raise ValueError("genes must name every row of expr.mat")
     t0 = time.time()
     o = _opts(n_potential_basis_fns, approx_knot, 25, None, 1e-5, n_gpus, gpu_ids, genes_per_batch, verbose)
-    recs, infos = run_records(counts, pt_arr, size_factor_offset, o)
+    if is_gee:
+        o.mode = 1
+        o.gee_cor = _abi.COR_CODES[cor_structure]
+    recs, infos = run_records(counts, pt_arr, size_factor_offset, o, subject_id=subject_id)
     n_lin = pt_arr.shape[1]
     res = ScLANE()
     dev0 = int(gpu_ids[0]) if gpu_ids else 0
@@ -468,7 +502,7 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
         per_l = {}
         for l in range(n_lin):
             ptl, sfl = lin_cache[l]
-            per_l[f"Lineage_{LETTERS[l]}"] = _record_to_list(recs[g * n_lin + l], genes[g], l, infos[l], ptl, ptl, sfl, preds, dev0)
+            per_l[f"Lineage_{LETTERS[l]}"] = _record_to_list(recs[g * n_lin + l], genes[g], l, infos[l], ptl, ptl, sfl, preds, dev0, is_gee)
         res[genes[g]] = per_l
     res.lineage_info = [{"n_cells": int(i.n_cells), "knots": [i.knots[k] for k in range(i.n_knots)], "minspan": int(i.minspan),
                          "pt_min": i.pt_min, "pt_max": i.pt_max} for i in infos]
@@ -476,7 +510,7 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
     res.records = recs
     if verbose:
         dt = time.time() - t0
-        print(f"scLANE testing in GLM mode completed for {n_genes} genes across {n_lin} "
+        print(f"scLANE testing in {'GEE' if is_gee else 'GLM'} mode completed for {n_genes} genes across {n_lin} "
               f"{'lineage' if n_lin == 1 else 'lineages'} in {dt:.3f} secs")
     return res
 
@@ -493,7 +527,7 @@ def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False,
     if X_pred is None or Y is None:
         raise ValueError("Some required inputs to marge2() are missing.")
     if is_gee:
-        raise SclaneError(4, "GEE mode is not built into sclane_b200 yet")
+        raise SclaneError(4, "marge2(is.gee = TRUE) as a stand-alone call is not built; use testDynamic(is_gee = True)")
     y = np.ascontiguousarray(np.asarray(Y).reshape(1, -1), dtype=np.int32)
     x = np.asarray(X_pred, dtype=np.float64).reshape(-1)
     o = _opts(M, approx_knot, n_knot_max, minspan, tols_score, gpu_ids=[device])

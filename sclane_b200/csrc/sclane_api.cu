@@ -13,6 +13,8 @@
 #include <thread>
 
 #include "sclane_device.cuh"
+#include "sclane_gee_device.cuh"
+#include "sclane_gee_host.hpp"
 #include "sclane_host.hpp"
 
 using namespace sclane;
@@ -237,6 +239,87 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   }
 }
 
+// GEE mode: genes [g0, g1) of one lineage on one device.  Same batching as run_shard; one k_gee launch per batch.
+void run_shard_gee(int device, const int32_t* h_counts, int64_t n_cells, int64_t g0, int64_t g1, const LineagePlan& P,
+                   const GeePlan& GP, const sclane_opts& o, bool use_offset, sclane_record* out, int n_lineages, int lin_idx,
+                   sclane_profile& prof) {
+  if (g1 <= g0) return;
+  CK(cudaSetDevice(device));
+  DevicePool& pool = pool_for(device);
+  if (!pool.stream) CK(cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking));
+  cudaStream_t s = pool.stream;
+  const Lineage& L = P.L;
+  int* d_cells = (int*)pool.get("gee_cells", GP.cells.size() * sizeof(int));
+  unsigned char* d_bid = (unsigned char*)pool.get("gee_bid", GP.bid.size());
+  double* d_u = (double*)pool.get("gee_u", GP.u.size() * sizeof(double));
+  Lineage* d_lin = (Lineage*)pool.get("lineage", sizeof(Lineage));
+  GeeLineage* d_glin = (GeeLineage*)pool.get("gee_lineage", sizeof(GeeLineage));
+  double* d_off = nullptr;
+  CK(cudaMemcpyAsync(d_cells, GP.cells.data(), GP.cells.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_bid, GP.bid.data(), GP.bid.size(), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_u, GP.u.data(), GP.u.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_lin, &L, sizeof(Lineage), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_glin, &GP.GL, sizeof(GeeLineage), cudaMemcpyHostToDevice, s));
+  if (!GP.off.empty()) {
+    d_off = (double*)pool.get("gee_off", GP.off.size() * sizeof(double));
+    CK(cudaMemcpyAsync(d_off, GP.off.data(), GP.off.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
+  static std::once_flag attr_once[SCLANE_MAX_GPUS];
+  std::call_once(attr_once[device % SCLANE_MAX_GPUS], [] {
+    CK(cudaFuncSetAttribute(k_gee, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GeeShared)));
+  });
+  const int64_t G = g1 - g0;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t per_gene = (size_t)n_cells * 4 + (size_t)L.Npad * 4 + sizeof(GeeGeneOutDev) + sizeof(GeneStats);
+  size_t budget = (size_t)((double)(free_b + pool.held()) * 0.6);
+  const size_t cap = (size_t)24 << 30;
+  if (budget > cap) budget = cap;
+  int64_t B = (int64_t)(budget / per_gene);
+  if (o.genes_per_batch > 0 && o.genes_per_batch < B) B = o.genes_per_batch;
+  if (B > G) B = G;
+  if (B < 1) throw CudaFail{"not enough free device memory for a single gene"};
+  int* d_raw = (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4);
+  int* d_ys = (int*)pool.get("ys", (size_t)B * (size_t)L.Npad * 4);
+  GeneStats* d_stats = (GeneStats*)pool.get("stats", (size_t)B * sizeof(GeneStats));
+  GeeGeneOutDev* d_out = (GeeGeneOutDev*)pool.get("gee_out", (size_t)B * sizeof(GeeGeneOutDev));
+  GeeGeneOutDev* h_out = (GeeGeneOutDev*)pool.get("gee_h_out", (size_t)B * sizeof(GeeGeneOutDev), true);
+  EventTimer tm(s);
+  for (int64_t b0 = g0; b0 < g1; b0 += B) {
+    const int64_t b1 = std::min<int64_t>(b0 + B, g1);
+    const int nb = (int)(b1 - b0);
+    tm.mark(SCLANE_STAGE_COPY);
+    CK(cudaMemcpyAsync(d_raw, h_counts + (size_t)b0 * (size_t)n_cells, (size_t)nb * (size_t)n_cells * 4, cudaMemcpyHostToDevice, s));
+    prof.h2d_bytes += (double)nb * (double)n_cells * 4.0;
+    prof.launches[SCLANE_STAGE_COPY]++;
+    tm.mark(SCLANE_STAGE_GATHER);
+    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, d_cells, L.N, L.Npad, d_ys, d_stats, nullptr, nb);
+    CK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    prof.launches[SCLANE_STAGE_GATHER]++;
+    GeeArgs A;
+    A.lineage = d_lin; A.glin = d_glin; A.ys = d_ys; A.bid = d_bid; A.u = d_u; A.off = d_off; A.stats = d_stats; A.out = d_out;
+    A.n_genes = nb; A.M = o.M; A.use_offset = use_offset ? 1 : 0; A.cor = o.gee_cor; A.tols_score = o.tols_score; A.mean_off = GP.mean_off;
+    tm.mark(SCLANE_STAGE_GEE);
+    k_gee<<<nb, kThreads, sizeof(GeeShared), s>>>(A);
+    CK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    prof.launches[SCLANE_STAGE_GEE]++;
+    tm.mark(SCLANE_STAGE_COPY);
+    CK(cudaMemcpyAsync(h_out, d_out, (size_t)nb * sizeof(GeeGeneOutDev), cudaMemcpyDeviceToHost, s));
+    prof.d2h_bytes += (double)nb * sizeof(GeeGeneOutDev);
+    prof.launches[SCLANE_STAGE_COPY]++;
+    tm.mark(-1);
+    CK(cudaStreamSynchronize(s));
+    tm.collect(prof);
+    for (int i = 0; i < nb; ++i) {
+      GeeGeneOut go;
+      go.st = h_out[i].st; go.alt = h_out[i].alt; go.null = h_out[i].null;
+      finalize_record_gee(go, L, out[(b0 + i) * n_lineages + lin_idx]);
+    }
+  }
+}
+
 void launch_sweep(const StageArgs& A, bool first, cudaStream_t s, EventTimer* tm, sclane_profile* prof) {
   if (tm) tm->mark(SCLANE_STAGE_SWEEP);
   if (first) k_sweep_moments<true><<<A.n_genes, kSweepThreads, 0, s>>>(A.lineage, A.ys, A.mu, A.u, A.out, A.mom, A.n_genes);
@@ -254,7 +337,7 @@ void launch_sweep(const StageArgs& A, bool first, cudaStream_t s, EventTimer* tm
 int check_opts(const sclane_opts* o, char* errbuf, size_t errlen) {
   if (!o) { set_err(errbuf, errlen, "opts is NULL"); return SCLANE_ERR_ARG; }
   if (o->abi_version != SCLANE_ABI_VERSION) { set_err(errbuf, errlen, "ABI version mismatch: caller %d, library %d", o->abi_version, SCLANE_ABI_VERSION); return SCLANE_ERR_ARG; }
-  if (o->mode != 0) { set_err(errbuf, errlen, "mode %d (GEE) is not built yet; only GLM mode (0)", o->mode); return SCLANE_ERR_UNSUPPORTED; }
+  if (o->mode != 0 && o->mode != 1) { set_err(errbuf, errlen, "mode %d is not built; 0 = GLM, 1 = GEE", o->mode); return SCLANE_ERR_UNSUPPORTED; }
   if (o->M < 3 || o->M > SCLANE_PMAX) { set_err(errbuf, errlen, "M must be in [3, %d]", SCLANE_PMAX); return SCLANE_ERR_ARG; }
   if (!o->approx_knot) { set_err(errbuf, errlen, "approx_knot = 0 is not supported yet"); return SCLANE_ERR_UNSUPPORTED; }
   if (o->n_knot_max < 1 || o->n_knot_max > SCLANE_TMAX) { set_err(errbuf, errlen, "n_knot_max must be in [1, %d]", SCLANE_TMAX); return SCLANE_ERR_ARG; }
@@ -278,9 +361,16 @@ void merge_profile(const sclane_profile& p) {
 
 int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int device_for_d, int64_t n_cells, int64_t n_genes,
                       const double* pt, int32_t n_lineages, const double* size_factor, const sclane_opts* opts,
-                      sclane_record* out, sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+                      sclane_record* out, sclane_lineage_info* lineages, char* errbuf, size_t errlen,
+                      const int32_t* subject_id = nullptr) {
   int rc = check_opts(opts, errbuf, errlen);
   if (rc) return rc;
+  const bool gee = opts->mode == 1;
+  if (gee) {
+    if (!subject_id || !h_counts) { set_err(errbuf, errlen, "GEE mode needs subject ids and host counts: call sclane_test_dynamic_gee()"); return SCLANE_ERR_ARG; }
+    if (opts->M > SCLANE_GEE_PMAX) { set_err(errbuf, errlen, "GEE mode: M must be <= %d", SCLANE_GEE_PMAX); return SCLANE_ERR_ARG; }
+    if (opts->gee_cor < SCLANE_COR_INDEPENDENCE || opts->gee_cor > SCLANE_COR_AR1) { set_err(errbuf, errlen, "Currently unsupported correlation structure."); return SCLANE_ERR_ARG; }
+  } else if (subject_id) { set_err(errbuf, errlen, "subject ids given but opts->mode is not 1 (GEE)"); return SCLANE_ERR_ARG; }
   if ((!h_counts && !d_counts) || !pt || !out || n_cells <= 0 || n_genes <= 0 || n_lineages <= 0) {
     set_err(errbuf, errlen, "bad arguments (null pointer or non-positive size)");
     return SCLANE_ERR_ARG;
@@ -311,6 +401,11 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
       for (int k = 0; k < P.L.T; ++k) li.knots[k] = P.L.knots[k];
       li.pt_min = P.pt_min; li.pt_max = P.pt_max;
     }
+    GeePlan GPl;
+    if (gee && !build_gee_plan(P, pt + (int64_t)l * n_cells, n_cells, subject_id, size_factor, GPl)) {
+      set_err(errbuf, errlen, "lineage %d: %s", l, GPl.error.c_str());
+      return SCLANE_ERR_ARG;
+    }
     const int nd = (int)devs.size();
     std::vector<std::string> errs((size_t)nd);
     std::vector<sclane_profile> profs((size_t)nd);
@@ -319,7 +414,8 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
       // contiguous gene blocks per device (gene-major matrix => contiguous memory per shard)
       const int64_t g0 = n_genes * di / nd, g1 = n_genes * (di + 1) / nd;
       try {
-        run_shard(devs[(size_t)di], h_counts, d_counts, n_cells, g0, g1, P, *opts, size_factor != nullptr, out, 0, n_lineages, l, profs[(size_t)di]);
+        if (gee) run_shard_gee(devs[(size_t)di], h_counts, n_cells, g0, g1, P, GPl, *opts, size_factor != nullptr, out, n_lineages, l, profs[(size_t)di]);
+        else run_shard(devs[(size_t)di], h_counts, d_counts, n_cells, g0, g1, P, *opts, size_factor != nullptr, out, 0, n_lineages, l, profs[(size_t)di]);
       } catch (const CudaFail& f) {
         errs[(size_t)di] = f.msg;
       } catch (const std::exception& e) {
@@ -585,6 +681,7 @@ void sclane_default_opts(sclane_opts* o) {
   std::memset(o, 0, sizeof(*o));
   o->abi_version = SCLANE_ABI_VERSION;
   o->mode = 0;
+  o->gee_cor = SCLANE_COR_AR1;
   o->M = 5;
   o->approx_knot = 1;
   o->n_knot_max = 25;
@@ -610,6 +707,14 @@ int32_t sclane_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t n_ge
                             const double* size_factor, const sclane_opts* opts, sclane_record* out,
                             sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
   return test_dynamic_impl(counts, nullptr, -1, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen);
+}
+
+int32_t sclane_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
+                                const int32_t* subject_id, const double* size_factor, const sclane_opts* opts, sclane_record* out,
+                                sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  if (!subject_id) { set_err(errbuf, errlen, "subject_id is NULL"); return SCLANE_ERR_ARG; }
+  if (opts && opts->mode != 1) { set_err(errbuf, errlen, "sclane_test_dynamic_gee() needs opts->mode = 1"); return SCLANE_ERR_ARG; }
+  return test_dynamic_impl(counts, nullptr, -1, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen, subject_id);
 }
 
 int32_t sclane_test_dynamic_device(const int32_t* d_counts, int32_t device, int64_t n_cells, int64_t n_genes, const double* pt,

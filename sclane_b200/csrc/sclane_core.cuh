@@ -133,6 +133,7 @@ struct Work {
   // alpha/gamma tables of the current model's terms (coop_set_model)
   double tal[PMAX][NBMAX], tga[PMAX][NBMAX];
   int want_ll;                 // PASS_IRLS: also accumulate the log-likelihood (sc[2])
+  int gee_p;                   // GEE passes: columns of the current model
   int sw_trunc, sw_kidx;       // forward selection broadcast
   double sw_score2;
   // misc broadcast
@@ -917,8 +918,9 @@ SC_HDN void backward_pass(E& ex, const Lineage& L, const GeneStats& gstat, GeneS
       W.bw_wic[i - 1] = W.bw_cum + 2.0 * (double)cur.n;
       if (i != ncol - 1) {
         // variable.lowest: first column attaining the minimum (:781,:791); drop it, keep the rest as warm start
-        int low = 0;
+        int low = -1;
         for (int j = 0; j < nw; ++j) if (wald[j] == mn) { low = j; break; }
+        if (low < 0) { st.error |= SCLANE_NOTE_NUMERIC; low = 0; }         // every Wald statistic NA: R fails inside try()
         const int drop = low + 1;
         Model nxt;
         nxt.n = 0;

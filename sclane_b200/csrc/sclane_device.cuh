@@ -641,6 +641,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_stats(const int* __restrict
       gs.ymax = max(gs.ymax, redm[w]);
     }
     stats[g] = gs;
+    if (!out) return;                       // GEE mode initialises its own per-gene state (k_gee)
     GeneState st;
     int* z = reinterpret_cast<int*>(&st);
     for (int i = 0; i < (int)(sizeof(GeneState) / sizeof(int)); ++i) z[i] = 0;

@@ -239,6 +239,7 @@ inline void finalize_record(const GeneOut& g, const Lineage& L, sclane_record& r
   r.theta = r.se_theta = r.loglik = r.deviance = NaN;
   r.null_coef = r.null_se = r.null_z = r.null_p = r.null_theta = r.null_se_theta = r.null_loglik = r.null_deviance = NaN;
   r.test_stat = r.df = r.p_val = NaN;
+  r.gee_alpha = r.gee_phi = r.null_gee_alpha = r.null_gee_phi = NaN;
   if (marge_ok) {
     const int p = st.fin.n;
     r.n_terms = p;

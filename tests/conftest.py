@@ -92,7 +92,29 @@ def emu():
         assert rc == 0
         return recs, infos
 
+    def run_gee(counts, pt, subject, size_factor=None, cor="ar1", M=5):
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        pt = np.asarray(pt, dtype=np.float64)
+        if pt.ndim == 1:
+            pt = pt[:, None]
+        G, N = counts.shape
+        nl = pt.shape[1]
+        ptc = np.ascontiguousarray(pt.T)
+        o = _abi.default_opts()
+        o.M = M
+        o.mode = 1
+        o.gee_cor = _abi.COR_CODES[cor]
+        sid = np.ascontiguousarray(np.unique(np.asarray(subject), return_inverse=True)[1], dtype=np.int32)
+        recs = (_abi.SclaneRecord * (G * nl))()
+        infos = (_abi.SclaneLineageInfo * nl)()
+        sf = None if size_factor is None else np.ascontiguousarray(size_factor, dtype=np.float64)
+        rc = lib.emu_test_dynamic_gee(C.c_void_p(counts.ctypes.data), C.c_int64(N), C.c_int64(G), C.c_void_p(ptc.ctypes.data), nl,
+                                      C.c_void_p(sid.ctypes.data), C.c_void_p(None if sf is None else sf.ctypes.data), C.byref(o), recs, infos)
+        assert rc == 0
+        return recs, infos
+
     lib.run = run
+    lib.run_gee = run_gee
     return lib
 
 

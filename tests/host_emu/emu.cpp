@@ -7,7 +7,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "../../sclane_b200/csrc/sclane_host.hpp"
+#include "../../sclane_b200/csrc/sclane_gee_host.hpp"
 
 using namespace sclane;
 
@@ -96,6 +96,153 @@ extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t 
   return 0;
 }
 
+// ---- GEE mode: serial executor over the subject-ordered cells (defines the semantics of the GEE passes) ----
+struct GeeHostExec {
+  Work* W;
+  GeeWork* G;
+  const Lineage* L;
+  const GeeLineage* GL;
+  const int32_t* y;        // [N] lineage order
+  const uint8_t* bid;
+  const double* u;
+  const double* off;       // may be null
+  PassTabs tabs_;
+  PassTabs* tabs() { return &tabs_; }
+  bool leader() const { return true; }
+  void sync() const {}
+  template <class F>
+  void par_for(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
+  double offset(int j) const { return (W->use_offset && off) ? off[j] : 0.0; }
+  template <int GP>
+  void gee_pass() {
+    const int pp = W->gee_p;
+    if (GP == GPASS_YMOM) {
+      for (int b = 0; b <= L->T; ++b) for (int k = 0; k < NACC; ++k) W->acc[b][k] = 0.0;
+      for (int j = 0; j < L->N; ++j) { W->acc[bid[j]][5] += (double)y[j]; W->acc[bid[j]][6] += (double)y[j] * u[j]; }
+      return;
+    }
+    if (GP == GPASS_RESID) {
+      G->sc[0] = G->sc[1] = 0.0;
+      for (int i = 0; i < GL->S; ++i) {
+        G->ssum[i][0] = 0.0;
+        double prev = 0.0;
+        for (int j = GL->sstart[i]; j < GL->sstart[i + 1]; ++j) {
+          GeeCell c;
+          gee_cell<false>(*W, *G, 0, y[j], bid[j], u[j], offset(j), c);
+          G->sc[0] += c.r * c.r;
+          if (j > GL->sstart[i]) G->sc[1] += prev * c.r;
+          G->ssum[i][0] += c.r;
+          prev = c.r;
+        }
+      }
+      return;
+    }
+    if (GP == GPASS_BETA) {
+      for (int k = 0; k < GEE_NSYM; ++k) { G->A1[k] = 0.0; G->A2[k] = 0.0; }
+      for (int k = 0; k < GEE_PMAX; ++k) { G->e1[k] = 0.0; G->e2[k] = 0.0; }
+      for (int i = 0; i < GL->S; ++i) {
+        for (int k = 0; k <= GEE_PMAX; ++k) G->ssum[i][k] = 0.0;
+        const int s0 = GL->sstart[i], n = GL->sstart[i + 1] - s0;
+        GeeCell pc;
+        for (int q = 0; q < n; ++q) {
+          const int j = s0 + q;
+          GeeCell c;
+          gee_cell<false>(*W, *G, pp, y[j], bid[j], u[j], offset(j), c);
+          const double cj = G->cor == GEE_AR1 ? ar1_cj(q, n, G->alpha) : 1.0;
+          for (int a = 0; a < pp; ++a) {
+            for (int l = 0; l <= a; ++l) G->A1[sym_idx(a, l)] += cj * c.z[a] * c.z[l];
+            G->e1[a] += cj * c.z[a] * c.r;
+          }
+          if (G->cor == GEE_AR1 && q > 0)
+            for (int a = 0; a < pp; ++a) {
+              for (int l = 0; l <= a; ++l) G->A2[sym_idx(a, l)] += c.z[a] * pc.z[l] + pc.z[a] * c.z[l];
+              G->e2[a] += c.z[a] * pc.r + pc.z[a] * c.r;
+            }
+          if (G->cor == GEE_EXCH) { for (int a = 0; a < pp; ++a) G->ssum[i][a] += c.z[a]; G->ssum[i][pp] += c.r; }
+          pc = c;
+        }
+      }
+      return;
+    }
+    if (GP == GPASS_PREP1) {
+      for (int i = 0; i < GL->S; ++i) {
+        for (int k = 0; k <= GEE_PMAX; ++k) G->ssum[i][k] = 0.0;
+        for (int j = GL->sstart[i]; j < GL->sstart[i + 1]; ++j) {
+          GeeCell c;
+          gee_cell<true>(*W, *G, pp, y[j], bid[j], u[j], 0.0, c);
+          G->ssum[i][0] += c.r;
+          for (int a = 0; a < pp; ++a) G->ssum[i][1 + a] += c.z[a];
+        }
+      }
+      return;
+    }
+    if (GP == GPASS_PREP2) {
+      const int i = G->subject;
+      const int s0 = GL->sstart[i], n = GL->sstart[i + 1] - s0;
+      for (int b = 0; b <= L->T; ++b) G->Gm[b][0] = G->Gm[b][1] = 0.0;
+      for (int k = 0; k < GEE_PMAX; ++k) G->e1[k] = 0.0;
+      for (int q = 0; q < n; ++q) {
+        const int j = s0 + q;
+        GeeCell c, cp, cn;
+        gee_cell<true>(*W, *G, pp, y[j], bid[j], u[j], 0.0, c);
+        const bool hp = q > 0, hn = q < n - 1;
+        if (G->cor == GEE_AR1) {
+          if (hp) gee_cell<true>(*W, *G, pp, y[j - 1], bid[j - 1], u[j - 1], 0.0, cp);
+          if (hn) gee_cell<true>(*W, *G, pp, y[j + 1], bid[j + 1], u[j + 1], 0.0, cn);
+        }
+        GeePrepOut o;
+        gee_prep_cell(*W, *G, pp, i, n, q, bid[j], u[j], c, hp ? &cp : nullptr, hn ? &cn : nullptr, o);
+        const int b = bid[j];
+        for (int a = 0; a < pp; ++a) {
+          for (int l2 = 0; l2 <= a; ++l2) G->A1[sym_idx(a, l2)] += o.xm[a] * o.q[l2];
+          G->e1[a] += o.xm[a] * o.uvec;
+          G->Hm[b][2 * a] += o.h[a];
+          G->Hm[b][2 * a + 1] += o.h[a] * u[j];
+        }
+        G->Gm[b][0] += o.g;
+        G->Gm[b][1] += o.g * u[j];
+      }
+      return;
+    }
+  }
+};
+
+extern "C" int emu_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
+                                    const int32_t* subject_id, const double* size_factor, const sclane_opts* opts, sclane_record* out,
+                                    sclane_lineage_info* lineages) {
+  for (int l = 0; l < n_lineages; ++l) {
+    LineagePlan P;
+    if (!build_lineage_plan(pt + (int64_t)l * n_cells, n_cells, size_factor, *opts, P)) { std::fprintf(stderr, "emu: %s\n", P.error.c_str()); return 1; }
+    GeePlan GP;
+    if (!build_gee_plan(P, pt + (int64_t)l * n_cells, n_cells, subject_id, size_factor, GP)) { std::fprintf(stderr, "emu: %s\n", GP.error.c_str()); return 1; }
+    const Lineage& L = P.L;
+    if (lineages) {
+      lineages[l].n_cells = L.N; lineages[l].n_knots = L.T; lineages[l].minspan = P.minspan;
+      for (int k = 0; k < L.T; ++k) lineages[l].knots[k] = L.knots[k];
+      lineages[l].pt_min = P.pt_min; lineages[l].pt_max = P.pt_max;
+    }
+    std::vector<int32_t> y((size_t)L.N);
+    for (int64_t g = 0; g < n_genes; ++g) {
+      for (int i = 0; i < L.N; ++i) y[(size_t)i] = counts[g * n_cells + GP.cells[(size_t)i]];
+      GeneStats gs;
+      gene_stats(y.data(), L.N, gs);
+      GeeGeneOut go;
+      init_gene_state(go.st);
+      if (gs.sum_y == 0.0) go.st.error |= SCLANE_NOTE_ALL_ZERO;
+      Work W;
+      std::memset(&W, 0, sizeof(W));
+      GeeWork G;
+      std::memset(&G, 0, sizeof(G));
+      G.cor = opts->gee_cor;
+      GeeHostExec ex{&W, &G, &L, &GP.GL, y.data(), GP.bid.data(), GP.u.data(), GP.off.empty() ? nullptr : GP.off.data(), PassTabs()};
+      gene_gee(ex, L, GP.GL, gs, go.st, W, G, opts->M, opts->tols_score, size_factor != nullptr, GP.mean_off, &go.alt, &go.null);
+      go.st.passes = W.passes;
+      finalize_record_gee(go, L, out[g * n_lineages + l]);
+    }
+  }
+  return 0;
+}
+
 extern "C" int emu_candidate_knots(const double* x, int64_t n, const sclane_opts* opts, double* knots_out, int32_t* minspan_out) {
   std::vector<double> xv(x, x + n), X;
   int ms = 0;
@@ -113,5 +260,5 @@ extern "C" void emu_psi_tri(int y, double th, double* out) { psi_tri_diff(y, th,
 extern "C" double emu_nb_lambda(int y, double sigma) { return nb_lambda(y, sigma, 1.0 / sigma); }
 extern "C" void emu_default_opts(sclane_opts* o) {
   std::memset(o, 0, sizeof(*o));
-  o->abi_version = SCLANE_ABI_VERSION; o->mode = 0; o->M = 5; o->approx_knot = 1; o->n_knot_max = 25; o->minspan = -1; o->tols_score = 1e-5;
+  o->abi_version = SCLANE_ABI_VERSION; o->mode = 0; o->M = 5; o->approx_knot = 1; o->n_knot_max = 25; o->minspan = -1; o->tols_score = 1e-5; o->gee_cor = SCLANE_COR_AR1;
 }

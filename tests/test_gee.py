@@ -1,0 +1,137 @@
+"""GEE mode (testDynamic(is.gee = TRUE, gee.test = "wald")): the O(n) closed-form core against the dense oracle
+(oracle/gee.py, which builds and inverts the n_i x n_i working covariances like the reference does), on the CPU through
+the host emulation harness and on the GPU through the C ABI.
+
+PARITY UNPINNED: the reference ships no GEE outputs and geeM::geem is third-party code outside the reference tree, so
+these tests pin the CUDA path to the restated algorithm, not to numbers produced by R."""
+import numpy as np
+import pytest
+
+from conftest import record_terms, rel
+
+from oracle.gee import test_dynamic_gee as oracle_gee
+
+TOL = 1e-6          # relative, fp64 statistics (north_star tolerance); discrete choices (term sets) must be identical
+
+
+def _gee_data(seed=5, sizes=(150, 1, 120, 89), n_genes=6, sorted_within=False):
+    from sclane_b200 import synth
+    n = int(sum(sizes))
+    counts, pt, _ = synth.make_counts(n_genes=n_genes, n_cells=n, seed=seed)
+    pt = np.asarray(pt, dtype=np.float64).reshape(-1)
+    rng = np.random.default_rng(seed)
+    subject = np.repeat(np.arange(len(sizes)), sizes)
+    if sorted_within:
+        start = 0
+        order = []
+        for s in sizes:
+            idx = np.arange(start, start + s)
+            order.append(idx[np.argsort(pt[idx], kind="stable")])
+            start += s
+        order = np.concatenate(order)
+        counts, pt = counts[:, order], pt[order]
+    sf = rng.uniform(0.6, 1.6, n)
+    return np.ascontiguousarray(counts, dtype=np.int32), pt, subject, sf
+
+
+def _compare(recs, ref, genes, tol=TOL):
+    bad = []
+    for g, name in enumerate(genes):
+        r, b = recs[g], ref[name]["Lineage_A"]
+        ok_ref = b["MARGE_Summary"] is not None
+        if bool(r.status & 1) != ok_ref:
+            bad.append((name, "status", r.status, b["Model_Status"]))
+            continue
+        if not ok_ref:
+            continue
+        if record_terms(r) != b["MARGE_Summary"]["term"]:
+            bad.append((name, "terms", record_terms(r), b["MARGE_Summary"]["term"]))
+            continue
+        for j in range(r.n_terms):
+            if rel(r.coef[j], b["MARGE_Summary"]["estimate"][j], 1e-6) > tol or rel(r.se[j], b["MARGE_Summary"]["std.error"][j], 1e-6) > tol:
+                bad.append((name, "coef/se", j, r.coef[j], b["MARGE_Summary"]["estimate"][j]))
+        if rel(r.test_stat, b["Test_Stat"], 1e-6) > tol or r.df != b["Degrees_Freedom"]:
+            bad.append((name, "wald", r.test_stat, b["Test_Stat"]))
+        if abs(r.p_val - b["P_Val"]) > tol * max(b["P_Val"], 1e-12) + 1e-15:
+            bad.append((name, "p", r.p_val, b["P_Val"]))
+        if rel(r.gee_alpha, b["alpha"], 1e-4) > 1e-5 or rel(r.gee_phi, b["phi"], 1e-6) > tol or r.gee_iters != b["niter"]:
+            bad.append((name, "alpha/phi/iters", r.gee_alpha, b["alpha"], r.gee_phi, b["phi"], r.gee_iters, b["niter"]))
+        if rel(r.null_coef, b["Null_Summary"]["estimate"][0], 1e-6) > tol or rel(r.null_se, b["Null_Summary"]["std.error"][0], 1e-6) > tol:
+            bad.append((name, "null", r.null_coef, b["Null_Summary"]["estimate"][0]))
+    return bad
+
+
+@pytest.mark.parametrize("cor", ["ar1", "exchangeable", "independence"])
+def test_gee_core_vs_dense_oracle(emu, cor):
+    counts, pt, subject, sf = _gee_data()
+    genes = [f"G{i}" for i in range(counts.shape[0])]
+    recs, _ = emu.run_gee(counts, pt, subject, sf, cor)
+    ref = oracle_gee(counts, pt, subject, genes, sf, cor)
+    assert sum(ref[g]["Lineage_A"]["MARGE_Summary"] is not None for g in genes) >= 3
+    assert _compare(recs, ref, genes) == []
+
+
+def test_gee_core_no_offset_and_all_zero_gene(emu):
+    counts, pt, subject, _ = _gee_data(seed=9, sizes=(100, 100, 100), sorted_within=True)
+    counts[2] = 0
+    genes = [f"G{i}" for i in range(counts.shape[0])]
+    recs, _ = emu.run_gee(counts, pt, subject, None, "ar1")
+    ref = oracle_gee(counts, pt, subject, genes, None, "ar1")
+    assert recs[2].status == 0 and ref["G2"]["Lineage_A"]["Model_Status"] == "MARGE model error, null model error"
+    assert _compare(recs, ref, genes) == []
+
+
+def test_gee_core_bundled_genes(emu, golden_inputs):
+    """Two genes of the bundled data set with its real subject structure (3 subjects x ~400 cells), AR-1."""
+    sel = [1, 4]
+    counts = golden_inputs["counts"][sel]
+    genes = [golden_inputs["genes"][i] for i in sel]
+    recs, _ = emu.run_gee(counts, golden_inputs["pt"], golden_inputs["subject"], golden_inputs["size_factor"], "ar1")
+    ref = oracle_gee(counts, golden_inputs["pt"].reshape(-1), golden_inputs["subject"], genes, golden_inputs["size_factor"], "ar1")
+    assert _compare(recs, ref, genes) == []
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("cor", ["ar1", "exchangeable", "independence"])
+def test_gee_gpu_vs_dense_oracle(cor):
+    import sclane_b200 as sb
+    from sclane_b200 import _abi, api
+    counts, pt, subject, sf = _gee_data()
+    genes = [f"G{i}" for i in range(counts.shape[0])]
+    o = api._opts(gpu_ids=[0])
+    o.mode = 1
+    o.gee_cor = _abi.COR_CODES[cor]
+    n0 = sb.launch_count()
+    recs, _ = api.run_records(counts, pt, sf, o, subject_id=subject.astype(np.int32))
+    assert sb.launch_count() > n0
+    ref = oracle_gee(counts, pt, subject, genes, sf, cor)
+    assert _compare(recs, ref, genes) == []
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cor", ["ar1", "exchangeable"])
+def test_gee_gpu_vs_core_bundled(emu, golden_inputs, cor):
+    """All 100 bundled genes: CUDA path vs the same algorithm run serially on the host (fast), which the CPU tests pin to
+    the dense oracle.  Also exercises the public testDynamic(is_gee = True) wrapper."""
+    import sclane_b200 as sb
+    counts, pt, subject, sf = golden_inputs["counts"], golden_inputs["pt"], golden_inputs["subject"], golden_inputs["size_factor"]
+    res = sb.testDynamic(counts, pt, genes=golden_inputs["genes"], size_factor_offset=sf, is_gee=True, id_vec=subject,
+                         cor_structure=cor, n_gpus=1)
+    recs, _ = emu.run_gee(counts, pt, subject, sf, cor)
+    n_ok = 0
+    for g, name in enumerate(golden_inputs["genes"]):
+        a, b = res.records[g], recs[g]
+        assert a.status == b.status, name
+        assert record_terms(a) == record_terms(b), name
+        if a.status & 1:
+            n_ok += 1
+            for j in range(a.n_terms):
+                assert rel(a.coef[j], b.coef[j], 1e-6) < TOL and rel(a.se[j], b.se[j], 1e-6) < TOL, name
+            assert rel(a.test_stat, b.test_stat, 1e-6) < TOL and a.df == b.df, name
+            assert a.gee_iters == b.gee_iters, name
+        rec = res[name]["Lineage_A"]
+        assert rec["Test_Stat_Type"] == "Wald"
+    assert n_ok >= 80
+    de = sb.getResultsDE(res)
+    assert len(de["Gene"]) == 100
