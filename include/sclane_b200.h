@@ -80,7 +80,8 @@ typedef struct sclane_opts {
   int32_t genes_per_batch;    /* 0 = automatic (bounded by free device memory) */
   int32_t verbose;
   int32_t gee_cor;            /* cor.structure (testDynamic.R:66): SCLANE_COR_* ; default ar1 */
-  int32_t reserved[7];
+  int32_t gee_test;           /* gee.test (testDynamic.R:68): 0 = "wald" (waldTestGEE.R), 1 = "score" (scoreTestGEE.R) */
+  int32_t reserved[6];
 } sclane_opts;
 
 /* One record per (gene, lineage): everything testDynamic() returns for that pair except the
@@ -124,7 +125,8 @@ typedef struct sclane_record {
   int32_t fit_passes;                   /* passes over the cells spent on this record */
   double  gene_time;                    /* Gene_Time surrogate: seconds of device time / genes in the batch */
   /* GEE mode only (NaN / 0 in GLM mode).  In GEE mode se/z/p/cov are the model-based ("naive") ones of geeM::geem,
-   * test_stat/df/p_val are waldTestGEE()'s (waldTestGEE.R:24-93) and theta/loglik/deviance are NaN. */
+   * test_stat/df/p_val are waldTestGEE()'s (waldTestGEE.R:24-93) or scoreTestGEE()'s (scoreTestGEE.R:26-139) and
+   * theta/loglik/deviance are NaN. */
   double  gee_alpha, gee_phi;           /* working correlation parameter and scale of the final model */
   double  null_gee_alpha, null_gee_phi;
   int32_t gee_converged, gee_iters;     /* geem outer iterations of the final model */
@@ -217,7 +219,8 @@ int32_t sclane_test_dynamic_device(const int32_t* d_counts, int32_t device,
  * subject_id   n_cells int32 subject labels; the cells MUST be ordered by subject (testDynamic.R:115 stops
  *              otherwise) -> SCLANE_ERR_ARG if a label re-appears after a different one.  HOST pointer.
  * opts->gee_cor selects the working correlation; opts->M <= SCLANE_GEE_PMAX; <= SCLANE_GEE_SMAX subjects per
- * lineage.  gee.test = "score" and gee.bias.correct = TRUE are not built -> use the defaults.
+ * lineage.  opts->gee_test selects waldTestGEE() or scoreTestGEE(); gee.bias.correction.method (sandwich variance with
+ * small-sample corrections) is not built.
  * Records: see the GEE note in sclane_record. */
 int32_t sclane_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t n_genes,
                                 const double* pt, int32_t n_lineages,

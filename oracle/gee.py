@@ -58,6 +58,19 @@ def _rinv_blocks(cor: str, alpha: float, n_vec) -> list[np.ndarray]:
     return out
 
 
+def _rcond_ok(A: np.ndarray) -> np.ndarray:
+    """Inverse of a small system matrix with the reciprocal-condition-number guard of R's solve(): 1-norm rcond below
+    .Machine$double.eps (or a non-finite entry) is an error ("system is computationally singular"), which try() turns
+    into a model failure.  rcond is computed exactly here (LAPACK estimates it); DESIGN.md section 7."""
+    if not np.all(np.isfinite(A)):
+        raise RuntimeError("system is computationally singular (non-finite entries)")
+    Ainv = np.linalg.inv(A)
+    n1 = np.abs(A).sum(axis=0).max() * np.abs(Ainv).sum(axis=0).max()
+    if not np.isfinite(n1) or 1.0 / n1 < np.finfo(float).eps:
+        raise RuntimeError("system is computationally singular")
+    return Ainv
+
+
 @dataclass
 class GeemFit:
     beta: np.ndarray
@@ -118,6 +131,7 @@ def geem(X, y, n_vec, cor: str, offset=None, maxit: int = 20, tol: float = 1e-5)
             for (a, b), Ri in zip(zip(starts[:-1], starts[1:]), rinv):
                 hess += Z[a:b].T @ (Ri / phi) @ Z[a:b]
                 esteq += Z[a:b].T @ (Ri / phi) @ rr[a:b]
+            _rcond_ok(hess)
             update = np.linalg.solve(hess, esteq)
             bnew = bnew + update
             with np.errstate(all="ignore"):
@@ -132,7 +146,7 @@ def geem(X, y, n_vec, cor: str, offset=None, maxit: int = 20, tol: float = 1e-5)
             break
         beta_old = beta.copy()
     eta = X @ beta + off
-    return GeemFit(beta=beta, alpha=float(alpha), phi=float(phi), naiv_var=np.linalg.inv(hess), eta=eta, mu=np.exp(eta),
+    return GeemFit(beta=beta, alpha=float(alpha), phi=float(phi), naiv_var=_rcond_ok(hess), eta=eta, mu=np.exp(eta),
                    converged=converged, niter=count)
 
 
@@ -313,7 +327,38 @@ def wald_test_gee(fit: GeemFit):
     return {"Wald_Stat": w, "DF": p - 1, "P_Val": 1.0 - (1.0 - pchisq_upper(w, p - 1))}
 
 
-def test_dynamic_gee(counts, pt, subject, genes=None, size_factor_offset=None, cor="ar1", M=5):
+def score_test_gee(X_alt: np.ndarray, y: np.ndarray, null: GeemFit, n_vec, cor: str):
+    """scoreTestGEE.R:26-139, dense like the reference: per-subject V_i = A^1/2 R(rho) A^1/2 with the NB(50) variance
+    function at the null fit, W_i = K V_i^-1 K, U = t(X) W K^-1 r / phi, V_U = t(X) W X, all inverses through
+    eigenMapMatrixInvert (LLT)."""
+    p_alt = X_alt.shape[1]
+    if p_alt <= 1:
+        return {"Score_Stat": 0.0, "DF": 0, "P_Val": 1.0}
+    rho, phi = null.alpha, null.phi
+    mu = np.exp(null.eta)
+    r_null = y - mu
+    starts = np.concatenate([[0], np.cumsum(n_vec)]).astype(int)
+    U = np.zeros((p_alt, 1))
+    V_U = np.zeros((p_alt, p_alt))
+    for a, b in zip(starts[:-1], starts[1:]):
+        n = b - a
+        R = _corr_matrix(cor, rho, n)
+        A_sqrt = np.diag(np.sqrt(mu[a:b] + mu[a:b] ** 2 / NB_THETA))
+        V_inv = llt_inv(A_sqrt @ R @ A_sqrt)
+        K = np.diag(mu[a:b])                                   # mu.eta of the log link
+        W = K @ V_inv @ K
+        K_inv = np.diag(1.0 / mu[a:b])
+        U += X_alt[a:b].T @ W @ K_inv @ r_null[a:b, None] / phi
+        V_U += X_alt[a:b].T @ W @ X_alt[a:b]
+    VarM = phi * llt_inv(V_U)
+    Lp = np.eye(p_alt)[1:]
+    mid_inv = llt_inv(Lp @ VarM @ Lp.T)
+    full_mid = VarM @ Lp.T @ mid_inv @ Lp @ VarM
+    S = float((U.T @ full_mid @ U)[0, 0])
+    return {"Score_Stat": S, "DF": p_alt - 1, "P_Val": 1.0 - (1.0 - pchisq_upper(S, p_alt - 1))}
+
+
+def test_dynamic_gee(counts, pt, subject, genes=None, size_factor_offset=None, cor="ar1", M=5, gee_test="wald"):
     """testDynamic(is.gee = TRUE, gee.test = "wald") for one lineage; `subject` must be sorted (testDynamic.R:115)."""
     counts = np.asarray(counts)
     pt = np.asarray(pt, dtype=np.float64).reshape(-1)
@@ -329,28 +374,42 @@ def test_dynamic_gee(counts, pt, subject, genes=None, size_factor_offset=None, c
         y = counts[g].astype(np.float64)
         rec = {"Gene": genes[g], "Lineage": "A", "Test_Stat_Type": "Wald"}
         trace = MargeTrace()
+        null = None
+        try:
+            if y.sum() == 0:
+                raise RuntimeError("all counts are zero")
+            null = geem(np.ones((y.size, 1)), y, n_vec, cor, off)
+        except (RuntimeError, np.linalg.LinAlgError, FloatingPointError):
+            null = None
         try:
             if y.sum() == 0:
                 raise RuntimeError("all counts are zero")
             terms = forward_pass_gee(y, X, knots, n_vec, cor, M, trace=trace)
             final = backward_pass_gee(y, X, knots, terms, n_vec, cor, trace)
             fit = geem(build_design(final, X, knots), y, n_vec, cor, off)
-            null = geem(np.ones((y.size, 1)), y, n_vec, cor, off)
             se = np.sqrt(np.diag(fit.naiv_var))
             z = fit.beta / se
-            rec.update({"Model_Status": "MARGE model OK, null model OK",
+            rec.update({"Model_Status": f"MARGE model OK, null model {'OK' if null is not None else 'error'}",
                         "MARGE_Summary": {"term": [term_name(t, knots, "Lineage_A") for t in final],
                                           "estimate": list(fit.beta), "std.error": list(se), "statistic": list(z),
                                           "p.value": [pnorm_two_sided(v) for v in z]},
-                        "Null_Summary": {"term": ["Intercept"], "estimate": [float(null.beta[0])],
-                                         "std.error": [float(np.sqrt(null.naiv_var[0, 0]))]},
-                        "alpha": fit.alpha, "phi": fit.phi, "null_alpha": null.alpha, "null_phi": null.phi,
-                        "converged": fit.converged, "niter": fit.niter})
-            w = wald_test_gee(fit)
+                        "alpha": fit.alpha, "phi": fit.phi, "converged": fit.converged, "niter": fit.niter})
+            if gee_test == "score":
+                if null is None:
+                    w = {"Wald_Stat": np.nan, "DF": np.nan, "P_Val": np.nan}
+                else:
+                    sc = score_test_gee(build_design(final, X, knots), y, null, n_vec, cor)
+                    w = {"Wald_Stat": sc["Score_Stat"], "DF": sc["DF"], "P_Val": sc["P_Val"]}
+                rec["Test_Stat_Type"] = "Score"
+            else:
+                w = wald_test_gee(fit)
             rec.update({"Test_Stat": w["Wald_Stat"], "Degrees_Freedom": w["DF"], "P_Val": w["P_Val"]})
         except (RuntimeError, np.linalg.LinAlgError, FloatingPointError) as e:
-            rec.update({"Model_Status": "MARGE model error, null model error" if "zero" in str(e) else "MARGE model error, null model OK",
+            rec.update({"Model_Status": f"MARGE model error, null model {'OK' if null is not None else 'error'}",
                         "MARGE_Summary": None, "Test_Stat": np.nan, "Degrees_Freedom": np.nan, "P_Val": np.nan, "error": str(e)})
+        rec["Null_Summary"] = (None if null is None else
+                               {"term": ["Intercept"], "estimate": [float(null.beta[0])], "std.error": [float(np.sqrt(null.naiv_var[0, 0]))],
+                                "alpha": null.alpha, "phi": null.phi})
         rec["_trace"] = trace
         out[genes[g]] = {"Lineage_A": rec}
     return out

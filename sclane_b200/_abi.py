@@ -41,7 +41,8 @@ class SclaneOpts(C.Structure):
         ("genes_per_batch", C.c_int32),
         ("verbose", C.c_int32),
         ("gee_cor", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("gee_test", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -372,14 +372,14 @@ def _summarize_model(rec, pt_min, pt_max):
     return {"Breakpoint": uniq, "Slope.Segment": slopes, "Trend.Segment": trends}
 
 
-def _record_to_list(rec, gene, lin_idx, info, pt_lineage, x_lineage, sf_lineage, preds, device, is_gee=False):
+def _record_to_list(rec, gene, lin_idx, info, pt_lineage, x_lineage, sf_lineage, preds, device, is_gee=False, gee_test="wald"):
     letter = LETTERS[lin_idx]
     m_ok = bool(rec.status & _abi.SCLANE_MARGE_OK)
     n_ok = bool(rec.status & _abi.SCLANE_NULL_OK)
     names = _term_names(rec, letter) if m_ok else []
     out = {
         "Gene": gene, "Lineage": letter,
-        "Test_Stat": _na(rec.test_stat), "Test_Stat_Type": "Wald" if is_gee else "LRT",
+        "Test_Stat": _na(rec.test_stat), "Test_Stat_Type": ("Score" if gee_test == "score" else "Wald") if is_gee else "LRT",
         "Test_Stat_Note": None if (m_ok and n_ok) else "No test performed due to model failure.",
         "Degrees_Freedom": _na(rec.df), "P_Val": _na(rec.p_val),
         "LogLik_MARGE": _na(rec.loglik), "LogLik_Null": _na(rec.null_loglik),
@@ -461,8 +461,9 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
         cor_structure = str(cor_structure).lower()
         if cor_structure not in _abi.COR_CODES:
             raise ValueError("GEE models require a specified correlation structure.")
-        if str(gee_test).lower() != "wald":
-            raise SclaneError(_abi_unsupported(), 'gee.test = "score" is not built into sclane_b200; use gee.test = "wald"')
+        gee_test = str(gee_test).lower()
+        if gee_test not in ("wald", "score"):
+            raise ValueError('gee.test must be one of "wald" or "score".')
         if gee_bias_correction_method is not None:
             raise SclaneError(_abi_unsupported(), "GEE bias correction (sandwich variance) is not built into sclane_b200")
         ids = np.asarray(id_vec)
@@ -488,6 +489,7 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
     if is_gee:
         o.mode = 1
         o.gee_cor = _abi.COR_CODES[cor_structure]
+        o.gee_test = 1 if gee_test == "score" else 0
     recs, infos = run_records(counts, pt_arr, size_factor_offset, o, subject_id=subject_id)
     n_lin = pt_arr.shape[1]
     res = ScLANE()
@@ -502,7 +504,7 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
         per_l = {}
         for l in range(n_lin):
             ptl, sfl = lin_cache[l]
-            per_l[f"Lineage_{LETTERS[l]}"] = _record_to_list(recs[g * n_lin + l], genes[g], l, infos[l], ptl, ptl, sfl, preds, dev0, is_gee)
+            per_l[f"Lineage_{LETTERS[l]}"] = _record_to_list(recs[g * n_lin + l], genes[g], l, infos[l], ptl, ptl, sfl, preds, dev0, is_gee, gee_test if is_gee else "wald")
         res[genes[g]] = per_l
     res.lineage_info = [{"n_cells": int(i.n_cells), "knots": [i.knots[k] for k in range(i.n_knots)], "minspan": int(i.minspan),
                          "pt_min": i.pt_min, "pt_max": i.pt_max} for i in infos]

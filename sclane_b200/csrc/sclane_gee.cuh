@@ -194,14 +194,26 @@ SC_HDN bool gee_solve(int n, const double* A, const double* b, double* x) {
   for (int i = 0; i < n; ++i) if (!(x[i] == x[i]) || isinf(x[i])) return false;
   return true;
 }
-// inverse of a general small matrix (solve(hess)); out row-major GEE_PMAX stride
+// inverse of a general small matrix (solve(hess)); out row-major GEE_PMAX stride.  R's solve() refuses a system whose
+// 1-norm reciprocal condition number is below .Machine$double.eps ("computationally singular"); try() turns that into a
+// model failure.  rcond is computed exactly here (LAPACK estimates it) -- DESIGN.md section 7.
 SC_HDN bool gee_invert(int n, const double* A, double* out) {
   double e[GEE_PMAX], col[GEE_PMAX];
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { const double v = A[i * GEE_PMAX + j]; if (!(v == v) || isinf(v)) return false; }
   for (int c = 0; c < n; ++c) {
     for (int i = 0; i < n; ++i) e[i] = i == c ? 1.0 : 0.0;
     if (!gee_solve(n, A, e, col)) return false;
     for (int i = 0; i < n; ++i) out[i * GEE_PMAX + c] = col[i];
   }
+  double na = 0.0, ni = 0.0;
+  for (int c = 0; c < n; ++c) {
+    double sa = 0.0, si = 0.0;
+    for (int i = 0; i < n; ++i) { sa += fabs(A[i * GEE_PMAX + c]); si += fabs(out[i * GEE_PMAX + c]); }
+    if (sa > na) na = sa;
+    if (si > ni) ni = si;
+  }
+  const double prod = na * ni;
+  if (!(prod == prod) || isinf(prod) || 1.0 / prod < 2.220446049250313e-16) return false;
   return true;
 }
 
@@ -252,7 +264,8 @@ SC_HDN bool geem_fit(E& ex, const Lineage& L, const GeeLineage& GL, const Model&
       if (ex.leader()) {
         gee_assemble_beta(GL, m, W, G);
         W.flag2 = 0;
-        if (!gee_solve(p, G.hess, W.grad, W.step)) W.flag = 2;
+        double inv_scratch[GEE_PMAX * GEE_PMAX];
+        if (!gee_invert(p, G.hess, inv_scratch) || !gee_solve(p, G.hess, W.grad, W.step)) W.flag = 2;
         else {
           double mx = -INFINITY;
           for (int j = 0; j < p; ++j) {
@@ -452,6 +465,7 @@ struct GeeResult {
   double coef[GEE_PMAX];
   double cov[GEE_PMAX * GEE_PMAX];     // naiv.var, row-major p x p (stride GEE_PMAX)
   double alpha, phi;
+  double score_stat;                   // scoreTestGEE statistic (alt only, gee_test = 1); NaN when not computed
   int converged, niter, ok;
 };
 
@@ -461,6 +475,7 @@ SC_HDN void gee_store_fit(E& ex, const Model& m, Work& W, GeeWork& G, GeeResult*
     out->ok = gee_invert(m.n, G.hess, out->cov) ? 1 : 0;
     for (int j = 0; j < m.n; ++j) out->coef[j] = W.beta[j];
     out->alpha = G.alpha; out->phi = G.phi; out->converged = G.converged; out->niter = G.niter;
+    out->score_stat = nan("");
   }
   ex.sync();
 }
@@ -470,7 +485,7 @@ SC_HDN void gee_store_fit(E& ex, const Model& m, Work& W, GeeWork& G, GeeResult*
 // executor provides in W.acc[b][5..6] (sum y, sum y u) before the call.
 template <class E>
 SC_HDN void gene_gee(E& ex, const Lineage& L, const GeeLineage& GL, const GeneStats& gstat, GeneState& st, Work& W, GeeWork& G,
-                     int M, double tols_score, bool use_offset, double mean_offset, GeeResult* alt, GeeResult* null) {
+                     int M, double tols_score, bool use_offset, double mean_offset, int gee_test, GeeResult* alt, GeeResult* null) {
   ex.sync();
   if (ex.leader()) { alt->ok = 0; null->ok = 0; st.fin.n = 0; W.use_offset = 0; }
   ex.sync();
@@ -512,6 +527,7 @@ SC_HDN void gene_gee(E& ex, const Lineage& L, const GeeLineage& GL, const GeneSt
         const Model cur = W.bw_cur;
         const int nw = cur.n - 1;
         const bool inv_ok = ok && gee_invert(cur.n, G.hess, cov);
+        if (!inv_ok) st.error |= SCLANE_NOTE_NUMERIC;                   // geem / solve() error inside try() -> MARGE model error
         for (int j = 1; j < cur.n; ++j) {
           const double se = sqrt(cov[j * GEE_PMAX + j]);
           wald[j - 1] = inv_ok ? (W.beta[j] / se) * (W.beta[j] / se) : nan("");
@@ -562,6 +578,37 @@ SC_HDN void gene_gee(E& ex, const Lineage& L, const GeeLineage& GL, const GeneSt
   if (st.fin.n >= 1 && !(st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC))) {
     if (st.fin.n == 1) { if (ex.leader()) *alt = *null; ex.sync(); }
     else if (geem_fit(ex, L, GL, st.fin, gstat, W, G, use_offset ? mean_offset : 0.0)) gee_store_fit(ex, st.fin, W, G, alt);
+    ex.sync();
+    // scoreTestGEE (scoreTestGEE.R:50-128): with K = diag(mu), V = A^1/2 R A^1/2 at the NULL fit, U = X'K V^-1 r / phi and
+    // V_U = X'K V^-1 K X are exactly geem's estimating equation and (phi x) hessian for the alternative design evaluated at
+    // beta = (null intercept, 0, ...), alpha = rho_null, phi = phi_null: one GPASS_BETA over the cells.
+    if (gee_test == 1 && st.fin.n > 1 && alt->ok && null->ok) {
+      const int p = st.fin.n;
+      coop_set_model(ex, L, st.fin, W);
+      if (ex.leader()) {
+        for (int j = 0; j < p; ++j) W.beta[j] = 0.0;
+        W.beta[0] = null->coef[0];
+        G.alpha = null->alpha; G.phi = null->phi;
+        W.gee_p = p;
+        W.passes++;
+      }
+      coop_set_eta(ex, L, st.fin, W, W.beta);
+      ex.template gee_pass<GPASS_BETA>();
+      if (ex.leader()) {
+        gee_assemble_beta(GL, st.fin, W, G);                      // G.hess = V_U / phi, W.grad = U
+        double VU[GEE_PMAX * GEE_PMAX], VarM[GEE_PMAX * GEE_PMAX], mid[GEE_PMAX * GEE_PMAX], midinv[GEE_PMAX * GEE_PMAX], v[GEE_PMAX];
+        for (int j = 0; j < p; ++j) for (int l = 0; l < p; ++l) VU[j * GEE_PMAX + l] = G.phi * G.hess[j * GEE_PMAX + l];
+        gee_llt_inverse(p, VU, VarM);
+        for (int j = 0; j < p; ++j) for (int l = 0; l < p; ++l) VarM[j * GEE_PMAX + l] *= G.phi;
+        for (int j = 1; j < p; ++j) for (int l = 1; l < p; ++l) mid[(j - 1) * GEE_PMAX + (l - 1)] = VarM[j * GEE_PMAX + l];
+        gee_llt_inverse(p - 1, mid, midinv);
+        for (int j = 0; j < p; ++j) { double s = 0.0; for (int l = 0; l < p; ++l) s += VarM[j * GEE_PMAX + l] * W.grad[l]; v[j] = s; }
+        double S = 0.0;
+        for (int j = 1; j < p; ++j) for (int l = 1; l < p; ++l) S += v[j] * midinv[(j - 1) * GEE_PMAX + (l - 1)] * v[l];
+        alt->score_stat = S;
+      }
+      ex.sync();
+    }
   }
   ex.sync();
 }

@@ -30,7 +30,7 @@ struct GeeArgs {
   const double* off;             // [Npad] or nullptr
   const GeneStats* stats;
   GeeGeneOutDev* out;
-  int n_genes, M, use_offset, cor;
+  int n_genes, M, use_offset, cor, gee_test;
   double tols_score, mean_off;
 };
 
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gee(GeeArgs A) {
   __syncthreads();
   const size_t row = (size_t)g * (size_t)S->L.Npad;
   GeeDevExec ex{S, A.ys + row, A.bid, A.u, A.off};
-  gene_gee(ex, S->L, S->GL, S->gs, S->st, S->W, S->G, A.M, A.tols_score, A.use_offset != 0, A.mean_off, &A.out[g].alt, &A.out[g].null);
+  gene_gee(ex, S->L, S->GL, S->gs, S->st, S->W, S->G, A.M, A.tols_score, A.use_offset != 0, A.mean_off, A.gee_test, &A.out[g].alt, &A.out[g].null);
   __syncthreads();
   if (threadIdx.x == 0) S->st.passes += S->W.passes;
   __syncthreads();

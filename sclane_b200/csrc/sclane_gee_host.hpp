@@ -57,7 +57,7 @@ struct GeeGeneOut {
   GeeResult alt, null;
 };
 
-inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, sclane_record& r) {
+inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_test, sclane_record& r) {
   const double NaN = std::numeric_limits<double>::quiet_NaN();
   GeneOut dummy;
   std::memset(&dummy, 0, sizeof(dummy));
@@ -90,7 +90,10 @@ inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, sclane_re
     r.gee_converged = g.alt.converged; r.gee_iters = g.alt.niter;
     // waldTestGEE(): W = b' (L V L')^-1 b over the non-intercept coefficients, naive variance
     if (p <= 1) { r.test_stat = 0.0; r.df = 0.0; r.p_val = 1.0; }
-    else {
+    else if (gee_test == 1) {
+      // scoreTestGEE(): statistic from the device; NA when the null model failed (scoreTestGEE.R:34-39)
+      if (null_ok) { r.test_stat = g.alt.score_stat; r.df = (double)(p - 1); r.p_val = 1.0 - (1.0 - pchisq_upper(r.test_stat, r.df)); }
+    } else {
       double mid[GEE_PMAX * GEE_PMAX], inv[GEE_PMAX * GEE_PMAX];
       for (int j = 1; j < p; ++j) for (int l = 1; l < p; ++l) mid[(j - 1) * GEE_PMAX + (l - 1)] = g.alt.cov[j * GEE_PMAX + l];
       gee_llt_inverse(p - 1, mid, inv);

@@ -92,7 +92,7 @@ def emu():
         assert rc == 0
         return recs, infos
 
-    def run_gee(counts, pt, subject, size_factor=None, cor="ar1", M=5):
+    def run_gee(counts, pt, subject, size_factor=None, cor="ar1", M=5, gee_test="wald"):
         counts = np.ascontiguousarray(counts, dtype=np.int32)
         pt = np.asarray(pt, dtype=np.float64)
         if pt.ndim == 1:
@@ -104,6 +104,7 @@ def emu():
         o.M = M
         o.mode = 1
         o.gee_cor = _abi.COR_CODES[cor]
+        o.gee_test = 1 if gee_test == "score" else 0
         sid = np.ascontiguousarray(np.unique(np.asarray(subject), return_inverse=True)[1], dtype=np.int32)
         recs = (_abi.SclaneRecord * (G * nl))()
         infos = (_abi.SclaneLineageInfo * nl)()

@@ -235,9 +235,9 @@ extern "C" int emu_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int6
       std::memset(&G, 0, sizeof(G));
       G.cor = opts->gee_cor;
       GeeHostExec ex{&W, &G, &L, &GP.GL, y.data(), GP.bid.data(), GP.u.data(), GP.off.empty() ? nullptr : GP.off.data(), PassTabs()};
-      gene_gee(ex, L, GP.GL, gs, go.st, W, G, opts->M, opts->tols_score, size_factor != nullptr, GP.mean_off, &go.alt, &go.null);
+      gene_gee(ex, L, GP.GL, gs, go.st, W, G, opts->M, opts->tols_score, size_factor != nullptr, GP.mean_off, opts->gee_test, &go.alt, &go.null);
       go.st.passes = W.passes;
-      finalize_record_gee(go, L, out[g * n_lineages + l]);
+      finalize_record_gee(go, L, opts->gee_test, out[g * n_lineages + l]);
     }
   }
   return 0;

@@ -39,9 +39,13 @@ def _compare(recs, ref, genes, tol=TOL):
     for g, name in enumerate(genes):
         r, b = recs[g], ref[name]["Lineage_A"]
         ok_ref = b["MARGE_Summary"] is not None
-        if bool(r.status & 1) != ok_ref:
+        null_ref = b["Null_Summary"] is not None
+        if bool(r.status & 1) != ok_ref or bool(r.status & 2) != null_ref:
             bad.append((name, "status", r.status, b["Model_Status"]))
             continue
+        if null_ref and (rel(r.null_coef, b["Null_Summary"]["estimate"][0], 1e-6) > tol or rel(r.null_se, b["Null_Summary"]["std.error"][0], 1e-6) > tol
+                         or rel(r.null_gee_phi, b["Null_Summary"]["phi"], 1e-6) > tol):
+            bad.append((name, "null", r.null_coef, b["Null_Summary"]["estimate"][0]))
         if not ok_ref:
             continue
         if record_terms(r) != b["MARGE_Summary"]["term"]:
@@ -50,14 +54,16 @@ def _compare(recs, ref, genes, tol=TOL):
         for j in range(r.n_terms):
             if rel(r.coef[j], b["MARGE_Summary"]["estimate"][j], 1e-6) > tol or rel(r.se[j], b["MARGE_Summary"]["std.error"][j], 1e-6) > tol:
                 bad.append((name, "coef/se", j, r.coef[j], b["MARGE_Summary"]["estimate"][j]))
-        if rel(r.test_stat, b["Test_Stat"], 1e-6) > tol or r.df != b["Degrees_Freedom"]:
-            bad.append((name, "wald", r.test_stat, b["Test_Stat"]))
-        if abs(r.p_val - b["P_Val"]) > tol * max(b["P_Val"], 1e-12) + 1e-15:
-            bad.append((name, "p", r.p_val, b["P_Val"]))
+        if np.isnan(b["Test_Stat"]):                 # score test without a null model: NA statistic on both sides
+            if not (np.isnan(r.test_stat) and np.isnan(r.df) and np.isnan(r.p_val)):
+                bad.append((name, "test should be NA", r.test_stat, r.df))
+        else:
+            if rel(r.test_stat, b["Test_Stat"], 1e-6) > tol or r.df != b["Degrees_Freedom"]:
+                bad.append((name, "test stat", r.test_stat, b["Test_Stat"]))
+            if abs(r.p_val - b["P_Val"]) > tol * max(b["P_Val"], 1e-12) + 1e-15:
+                bad.append((name, "p", r.p_val, b["P_Val"]))
         if rel(r.gee_alpha, b["alpha"], 1e-4) > 1e-5 or rel(r.gee_phi, b["phi"], 1e-6) > tol or r.gee_iters != b["niter"]:
             bad.append((name, "alpha/phi/iters", r.gee_alpha, b["alpha"], r.gee_phi, b["phi"], r.gee_iters, b["niter"]))
-        if rel(r.null_coef, b["Null_Summary"]["estimate"][0], 1e-6) > tol or rel(r.null_se, b["Null_Summary"]["std.error"][0], 1e-6) > tol:
-            bad.append((name, "null", r.null_coef, b["Null_Summary"]["estimate"][0]))
     return bad
 
 
@@ -135,3 +141,27 @@ def test_gee_gpu_vs_core_bundled(emu, golden_inputs, cor):
     assert n_ok >= 80
     de = sb.getResultsDE(res)
     assert len(de["Gene"]) == 100
+
+
+def test_gee_score_test_core_vs_dense_oracle(emu):
+    """gee.test = "score": scoreTestGEE() as one estimating-equation pass at the null fit vs the dense restatement."""
+    counts, pt, subject, sf = _gee_data(seed=11, sizes=(140, 90, 130))
+    genes = [f"G{i}" for i in range(counts.shape[0])]
+    for cor in ("ar1", "exchangeable"):
+        recs, _ = emu.run_gee(counts, pt, subject, sf, cor, gee_test="score")
+        ref = oracle_gee(counts, pt, subject, genes, sf, cor, gee_test="score")
+        assert _compare(recs, ref, genes) == []
+
+
+@pytest.mark.gpu
+def test_gee_score_test_gpu_vs_dense_oracle():
+    from sclane_b200 import _abi, api
+    counts, pt, subject, sf = _gee_data(seed=11, sizes=(140, 90, 130))
+    genes = [f"G{i}" for i in range(counts.shape[0])]
+    o = api._opts(gpu_ids=[0])
+    o.mode = 1
+    o.gee_cor = _abi.COR_AR1
+    o.gee_test = 1
+    recs, _ = api.run_records(counts, pt, sf, o, subject_id=subject.astype(np.int32))
+    ref = oracle_gee(counts, pt, subject, genes, sf, "ar1", gee_test="score")
+    assert _compare(recs, ref, genes) == []
