@@ -81,7 +81,8 @@ typedef struct sclane_opts {
   int32_t verbose;
   int32_t gee_cor;            /* cor.structure (testDynamic.R:66): SCLANE_COR_* ; default ar1 */
   int32_t gee_test;           /* gee.test (testDynamic.R:68): 0 = "wald" (waldTestGEE.R), 1 = "score" (scoreTestGEE.R) */
-  int32_t reserved[6];
+  int32_t force_per_cell;     /* 1 = never use the X-compressed kernels (testing / profiling of the per-cell kernels) */
+  int32_t reserved[5];
 } sclane_opts;
 
 /* One record per (gene, lineage): everything testDynamic() returns for that pair except the
@@ -157,7 +158,7 @@ void sclane_reset_launch_count(void);
 
 /* Device-side timing of the last sclane_test_dynamic*() call on this process (CUDA events on the
  * library's own stream, summed over batches / lineages / GPUs): what bench.py's roofline uses. */
-#define SCLANE_NSTAGES 8
+#define SCLANE_NSTAGES 12
 #define SCLANE_STAGE_GATHER 0      /* sort permutation + per-gene constants                                  */
 #define SCLANE_STAGE_FWD_FIT 1     /* K1 forward null fits (stat_out_score_glm_null)                         */
 #define SCLANE_STAGE_SWEEP 2       /* K2a score sweep, streaming kernel k_sweep_moments (HBM bound)          */
@@ -166,6 +167,10 @@ void sclane_reset_launch_count(void);
 #define SCLANE_STAGE_COPY 5        /* H2D of counts + D2H of records                                         */
 #define SCLANE_STAGE_SELECT 6      /* K2b score sweep, per-gene algebra + selection tree (k_sweep_select)    */
 #define SCLANE_STAGE_GEE 7         /* GEE mode: the whole per-gene path (k_gee)                              */
+#define SCLANE_STAGE_AGGREGATE 8   /* X-compressed path: per-point sums + count histogram (k_aggregate)      */
+#define SCLANE_STAGE_COMP_FWD 9    /* X-compressed forward pass: null fits + score sweep + selection         */
+#define SCLANE_STAGE_COMP_BWD 10   /* X-compressed backward WIC pass                                         */
+#define SCLANE_STAGE_COMP_FINAL 11 /* X-compressed final + null glm.nb (no offset)                            */
 typedef struct sclane_profile {
   double  ms[SCLANE_NSTAGES];          /* device milliseconds per stage                                   */
   int64_t launches[SCLANE_NSTAGES];    /* kernel launches (memcpys for SCLANE_STAGE_COPY) per stage        */

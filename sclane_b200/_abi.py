@@ -42,7 +42,8 @@ class SclaneOpts(C.Structure):
         ("verbose", C.c_int32),
         ("gee_cor", C.c_int32),
         ("gee_test", C.c_int32),
-        ("reserved", C.c_int32 * 6),
+        ("force_per_cell", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 

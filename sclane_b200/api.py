@@ -113,12 +113,13 @@ def release() -> None:
 
 
 class _Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("sweep_bytes", C.c_double),
+    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_int64 * 12), ("sweep_bytes", C.c_double),
                 ("sweep_gene_iters", C.c_int64), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
                 ("wall_ms", C.c_double)]
 
 
-STAGE_NAMES = ["gather", "fwd_fit", "sweep", "backward", "final", "copy", "select", "gee"]
+STAGE_NAMES = ["gather", "fwd_fit", "sweep", "backward", "final", "copy", "select", "gee", "aggregate", "comp_forward",
+               "comp_backward", "comp_final"]
 
 
 def get_profile() -> dict:
@@ -131,7 +132,7 @@ def get_profile() -> dict:
 
 
 def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None, tols_score=1e-5,
-          n_gpus=0, gpu_ids=None, genes_per_batch=0, verbose=False) -> _abi.SclaneOpts:
+          n_gpus=0, gpu_ids=None, genes_per_batch=0, verbose=False, force_per_cell=False) -> _abi.SclaneOpts:
     o = _abi.default_opts()
     o.M = int(n_potential_basis_fns)
     o.approx_knot = 1 if approx_knot else 0
@@ -148,6 +149,7 @@ def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None
             o.gpu_ids[i] = i
     o.genes_per_batch = int(genes_per_batch)
     o.verbose = 1 if verbose else 0
+    o.force_per_cell = 1 if force_per_cell else 0
     return o
 
 
@@ -443,7 +445,8 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
                 cor_structure: str = "ar1", gee_bias_correction_method=None, gee_test: str = "wald",
                 is_glmm: bool = False, glmm_adaptive: bool = True, id_vec=None, n_potential_basis_fns: int = 5,
                 n_cores: int = 4, approx_knot: bool = True, verbose: bool = False, random_seed: int = 312,
-                n_gpus: int = 0, gpu_ids=None, genes_per_batch: int = 0, preds: str = "lazy") -> ScLANE:
+                n_gpus: int = 0, gpu_ids=None, genes_per_batch: int = 0, preds: str = "lazy",
+                force_per_cell: bool = False) -> ScLANE:
     """testDynamic.R:60-448, GLM mode and GEE mode (is_gee = True with id_vec, cor_structure in {"ar1", "exchangeable",
     "independence"}, gee_test = "wald").  expr_mat: genes x cells integer counts (rows named by `genes`); pt: cells x
     lineages pseudotime (NaN = cell not in the lineage).  `n_cores` is kept for signature compatibility; the work is
@@ -485,7 +488,7 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
     if len(genes) != n_genes:
         raise ValueError("genes must name every row of expr.mat")
     t0 = time.time()
-    o = _opts(n_potential_basis_fns, approx_knot, 25, None, 1e-5, n_gpus, gpu_ids, genes_per_batch, verbose)
+    o = _opts(n_potential_basis_fns, approx_knot, 25, None, 1e-5, n_gpus, gpu_ids, genes_per_batch, verbose, force_per_cell)
     if is_gee:
         o.mode = 1
         o.gee_cor = _abi.COR_CODES[cor_structure]

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <thread>
 
+#include "sclane_comp_device.cuh"
 #include "sclane_device.cuh"
 #include "sclane_gee_device.cuh"
 #include "sclane_gee_host.hpp"
@@ -123,6 +124,20 @@ struct DevicePlan {
   double* u = nullptr;
   double* off = nullptr;
   Lineage* lin = nullptr;
+  int* pstart = nullptr;          // X-compressed layout (sclane_comp.cuh)
+  double* pn = nullptr;
+  double* pu = nullptr;
+  unsigned char* pb = nullptr;
+  void upload_points(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
+    pstart = (int*)pool.get("pstart", P.pstart.size() * sizeof(int));
+    pn = (double*)pool.get("pn", P.pn.size() * sizeof(double));
+    pu = (double*)pool.get("pu", P.pu.size() * sizeof(double));
+    pb = (unsigned char*)pool.get("pb", P.pb.size());
+    CK(cudaMemcpyAsync(pstart, P.pstart.data(), P.pstart.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(pn, P.pn.data(), P.pn.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(pu, P.pu.data(), P.pu.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(pb, P.pb.data(), P.pb.size(), cudaMemcpyHostToDevice, s));
+  }
   void upload(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
     perm = (int*)pool.get("perm", P.perm.size() * sizeof(int));
     u = (double*)pool.get("u", P.u.size() * sizeof(double));
@@ -164,11 +179,15 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   D.upload(P, pool, s);
   const Lineage& L = P.L;
   const int64_t G = g1 - g0;
+  // X-compressed path (sclane_comp.cuh): worth it when the 4-decimal rounding leaves clearly fewer abscissae than cells
+  const bool use_comp = !o.force_per_cell && P.D > 0 && (double)P.D <= 0.8 * (double)L.N;
+  const int Dpad = (P.D + 31) / 32 * 32;
+  if (use_comp) D.upload_points(P, pool, s);
   // batch size from free memory (+ what the pool already holds): raw (host path) + sorted counts + mu + moments + records
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t per_gene = (h_counts ? (size_t)n_cells * 4 : 0) + (size_t)L.Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
-                          (size_t)NBMAX * NACC * 8;
+                          (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + sizeof(CompGeneDev) : 0);
   size_t budget = (size_t)((double)(free_b + pool.held()) * 0.6);
   const size_t cap = (size_t)24 << 30;
   if (budget > cap) budget = cap;
@@ -183,6 +202,10 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   GeneStats* d_stats = (GeneStats*)pool.get("stats", (size_t)B * sizeof(GeneStats));
   GeneOutDev* d_out = (GeneOutDev*)pool.get("out", (size_t)B * sizeof(GeneOutDev));
   GeneOutDev* h_out = (GeneOutDev*)pool.get("h_out", (size_t)B * sizeof(GeneOutDev), true);
+  double* d_s1 = use_comp ? (double*)pool.get("comp_s1", (size_t)B * (size_t)Dpad * 8) : nullptr;
+  double* d_q = use_comp ? (double*)pool.get("comp_q", (size_t)B * (size_t)Dpad * 8) : nullptr;
+  int* d_tail = use_comp ? (int*)pool.get("comp_tail", (size_t)B * (size_t)kHistCap * 4) : nullptr;
+  CompGeneDev* d_cg = use_comp ? (CompGeneDev*)pool.get("comp_hdr", (size_t)B * sizeof(CompGeneDev)) : nullptr;
   const int n_iter = forward_iterations(o.M);
   EventTimer tm(s);
   for (int64_t b0 = g0; b0 < g1; b0 += B) {
@@ -206,15 +229,47 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = D.off; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
     A.scores = nullptr; A.mom = d_mom; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
+    CompArgs CA;
+    if (use_comp) {
+      CA.lineage = D.lin; CA.pstart = D.pstart; CA.pn = D.pn; CA.pu = D.pu; CA.pb = D.pb; CA.D = P.D; CA.Dpad = Dpad; CA.ys = d_ys;
+      CA.s1 = d_s1; CA.q = d_q; CA.tail = d_tail; CA.cg = d_cg; CA.stats = d_stats; CA.out = d_out; CA.n_genes = nb; CA.M = o.M;
+      CA.n_iter = n_iter; CA.tols_score = o.tols_score;
+      tm.mark(SCLANE_STAGE_AGGREGATE);
+      k_aggregate<<<nb, kThreads, 0, s>>>(CA);
+      CK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      prof.launches[SCLANE_STAGE_AGGREGATE]++;
+      tm.mark(SCLANE_STAGE_COMP_FWD);
+      k_comp_stage<CSTAGE_FORWARD><<<nb, kThreads, 0, s>>>(CA);
+      CK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      prof.launches[SCLANE_STAGE_COMP_FWD]++;
+    }
+    // per-cell kernels: every gene when the compressed path is off, otherwise only the genes k_aggregate routed away
+    // (counts >= kHistCap); genes that already finished a stage return at once
     for (int it = 0; it < n_iter; ++it) {
       tm.mark(SCLANE_STAGE_FWD_FIT);
       launch_stage<STAGE_FWD_FIT>(A, s);
       prof.launches[SCLANE_STAGE_FWD_FIT]++;
       launch_sweep(A, it == 0, s, &tm, &prof);
     }
+    if (use_comp) {
+      tm.mark(SCLANE_STAGE_COMP_BWD);
+      k_comp_stage<CSTAGE_BACKWARD><<<nb, kThreads, 0, s>>>(CA);
+      CK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      prof.launches[SCLANE_STAGE_COMP_BWD]++;
+    }
     tm.mark(SCLANE_STAGE_BACKWARD);
     launch_stage<STAGE_BACKWARD>(A, s);
     prof.launches[SCLANE_STAGE_BACKWARD]++;
+    if (use_comp && !use_offset) {
+      tm.mark(SCLANE_STAGE_COMP_FINAL);
+      k_comp_stage<CSTAGE_FINAL><<<nb, kThreads, 0, s>>>(CA);
+      CK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      prof.launches[SCLANE_STAGE_COMP_FINAL]++;
+    }
     tm.mark(SCLANE_STAGE_FINAL);
     launch_stage<STAGE_FINAL>(A, s);
     prof.launches[SCLANE_STAGE_FINAL]++;

@@ -1,0 +1,197 @@
+// sclane_comp.cuh -- the X-compressed form of the GLM passes (shared host/device).
+//
+// marge2() rounds pseudotime to 4 decimals (marge2.R:154), so a lineage with N cells has only D <= ~10^4 distinct
+// abscissae when pseudotime lives in [0, 1] (D = 10,000 at N = 200,000).  Without an offset the fitted mean of a cell
+// depends on its abscissa only, and every sum the NB fits and the score sweep need is either
+//   * linear in y at fixed abscissa  -> needs per point d:  n_d (cells), s_d = sum y, q_d = sum y^2, or
+//   * free of mu                      -> needs the gene's count histogram only:
+//       sum_i [psi(th + y_i) - psi(th)]        = sum_k C_k / (th + k),       C_k = #{i : y_i > k}
+//       sum_i [trigamma(th) - trigamma(th+y_i)] = sum_k C_k / (th + k)^2
+//       sum_i [lgamma(th+y_i) - lgamma(th) + y_i log sigma] = sum_{k>=1} C_k log1p(k sigma)
+//       sum_{y_i>0} (y_i + th) log1p(sigma y_i) = sum_{y>=1} hist[y] (y + th) log1p(sigma y)
+// (glm.fit's mustart pass is the one place that is non-linear in y at fixed abscissa; its two sums are functions of y
+// alone because init.theta = 1, so they are aggregated once per gene: a0_d, b0_d.)
+// A pass therefore costs D point evaluations + ymax histogram terms instead of N cell evaluations, and a bucket in which
+// the linear predictor is flat is one closed-form evaluation from its bucket totals.  The executor that implements
+// pass<MODE>() this way produces the same W.acc / W.sc as the per-cell executor (to rounding), so the whole algorithm in
+// sclane_core.cuh runs unchanged on top of it.  Used for every fit without offset (all forward / backward fits, and the
+// final fits when size.factor.offset is NULL); fits with an offset stay on the per-cell path.
+#pragma once
+#include "sclane_core.cuh"
+
+namespace sclane {
+
+constexpr int kHistCap = 4096;          // genes with a count >= kHistCap take the per-cell path
+
+// gene-independent tables of the compressed layout (pointers are device or host memory, depending on the executor)
+struct CompTables {
+  int D;
+  const int* pstart;        // [D + 1] range of the point's cells in the pseudotime-sorted cell order
+  const double* pn;         // [D] number of cells of the point
+  const double* pu;         // [D] bucket-local coordinate x - ref[bucket]
+  int pbstart[NBMAX + 1];   // point index range of bucket b: [pbstart[b], pbstart[b + 1])
+};
+
+// per-gene aggregates
+struct CompGeneHdr {
+  int ymax;                 // largest count
+  int n_zero;               // cells with y == 0
+  int route;                // 1 = compressed path usable (ymax < kHistCap)
+  int pad;
+  double SB[NBMAX], SBu[NBMAX], SBuu[NBMAX], QB[NBMAX];     // per bucket: sum y, sum y u, sum y u^2, sum y^2
+};
+
+// One point of the compressed layout: n cells, s = sum y, q = sum y^2, all with the same mean mu = exp(a + c u).
+template <int MODE>
+SC_HD void point_contrib(double n, double s, double q, double u, double a, double c, double sigma, double theta, bool want_ll,
+                         double* acc, double* sc) {
+  const double eta = a + c * u;
+  const double mu = exp(eta);
+  if (MODE == PASS_SWEEP) {
+    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double w = n * mu * inv, r = (s - n * mu) * inv;
+    acc[0] += w; acc[1] += w * u; acc[2] += w * u * u;
+    acc[3] += r; acc[4] += r * u;
+    return;
+  }
+  if (MODE == PASS_FIT) {
+    if (sigma == 0.0) {
+      const double m = n * mu, r = s - m;
+      acc[0] += m; acc[1] += m * u; acc[2] += m * u * u;
+      acc[3] += r; acc[4] += r * u;
+      sc[2] += s * eta - m;
+      return;
+    }
+    const double inv = rcp_pos(1.0 + sigma * mu);
+    const double r = (s - n * mu) * inv;
+    const double ns = n + sigma * s;
+    const double o = mu * ns * inv * inv;
+    const double cc = sigma * mu * r * inv;
+    const double lg = log1p(sigma * mu);
+    acc[0] += o; acc[1] += o * u; acc[2] += o * u * u;
+    acc[3] += r; acc[4] += r * u;
+    acc[5] += cc; acc[6] += cc * u;
+    sc[0] += -n * lg - sigma * r;
+    sc[1] += n * sigma - 2.0 * sigma * n * inv + sigma * ns * inv * inv;
+    sc[2] += s * eta - (s + n * theta) * lg;
+    return;
+  }
+  if (MODE == PASS_IRLS) {
+    const double inv = rcp_pos(1.0 + sigma * mu);
+    const double w = n * mu * inv;
+    const double r = (s - n * mu) * inv;
+    const double wz = w * eta + r;
+    acc[0] += w; acc[1] += w * u; acc[2] += w * u * u;
+    acc[3] += wz; acc[4] += wz * u;
+    const double lg = log1p(sigma * mu);
+    const double t = s * eta - (s + n * theta) * lg;
+    sc[0] -= t;
+    const double rmu = rcp_pos(mu);
+    sc[1] += (q - 2.0 * s * mu + n * mu * mu) * rmu * rmu;
+    if (want_ll) sc[2] += t;
+    return;
+  }
+  if (MODE == PASS_THETA) {
+    const double inv = rcp_pos(1.0 + sigma * mu);
+    const double r = (s - n * mu) * inv;
+    const double lg = log1p(sigma * mu);
+    sc[0] += -n * lg - sigma * r;
+    sc[1] += -n * sigma + 2.0 * sigma * n * inv - sigma * (n + sigma * s) * inv * inv;
+    return;
+  }
+}
+
+// A whole bucket with a flat linear predictor (c_b == 0): the point sums collapse to the bucket totals
+// (N_b, U1, U2 from the lineage; SB, SBu, SBuu, QB from the gene).
+template <int MODE>
+SC_HD void flat_bucket_contrib(double Nb, double U1, double U2, double SB, double SBu, double SBuu, double QB, double a,
+                               double sigma, double theta, bool want_ll, double* acc, double* sc) {
+  if (Nb == 0.0) return;
+  const double eta = a;
+  const double mu = exp(eta);
+  if (MODE == PASS_SWEEP) {
+    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double w = mu * inv;
+    acc[0] += w * Nb; acc[1] += w * U1; acc[2] += w * U2;
+    acc[3] += (SB - Nb * mu) * inv; acc[4] += (SBu - U1 * mu) * inv;
+    return;
+  }
+  if (MODE == PASS_FIT) {
+    if (sigma == 0.0) {
+      acc[0] += mu * Nb; acc[1] += mu * U1; acc[2] += mu * U2;
+      acc[3] += SB - Nb * mu; acc[4] += SBu - U1 * mu;
+      sc[2] += SB * eta - Nb * mu;
+      return;
+    }
+    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double f = mu * inv * inv;
+    const double r0 = (SB - Nb * mu) * inv, r1 = (SBu - U1 * mu) * inv;
+    const double lg = log1p(sigma * mu);
+    const double g = sigma * mu * inv;
+    acc[0] += f * (Nb + sigma * SB); acc[1] += f * (U1 + sigma * SBu); acc[2] += f * (U2 + sigma * SBuu);
+    acc[3] += r0; acc[4] += r1;
+    acc[5] += g * r0; acc[6] += g * r1;
+    sc[0] += -Nb * lg - sigma * r0;
+    sc[1] += Nb * sigma - 2.0 * sigma * Nb * inv + sigma * (Nb + sigma * SB) * inv * inv;
+    sc[2] += SB * eta - (SB + Nb * theta) * lg;
+    return;
+  }
+  if (MODE == PASS_IRLS) {
+    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double w = mu * inv;
+    const double r0 = (SB - Nb * mu) * inv, r1 = (SBu - U1 * mu) * inv;
+    acc[0] += w * Nb; acc[1] += w * U1; acc[2] += w * U2;
+    acc[3] += w * eta * Nb + r0; acc[4] += w * eta * U1 + r1;
+    const double lg = log1p(sigma * mu);
+    const double t = SB * eta - (SB + Nb * theta) * lg;
+    sc[0] -= t;
+    sc[1] += (QB - 2.0 * SB * mu + Nb * mu * mu) / (mu * mu);
+    if (want_ll) sc[2] += t;
+    return;
+  }
+  if (MODE == PASS_THETA) {
+    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double r0 = (SB - Nb * mu) * inv;
+    const double lg = log1p(sigma * mu);
+    sc[0] += -Nb * lg - sigma * r0;
+    sc[1] += -Nb * sigma + 2.0 * sigma * Nb * inv - sigma * (Nb + sigma * SB) * inv * inv;
+    return;
+  }
+}
+
+// The mu-free part of a pass, term k of the sum over the gene's tail counts: Ck = #{y > k}, Ck1 = #{y > k + 1}.
+template <int MODE>
+SC_HD void hist_contrib(int k, double Ck, double Ck1, double sigma, double theta, bool want_ll, double* sc) {
+  if (MODE == PASS_FIT) {
+    if (sigma == 0.0) return;
+    const double d = 1.0 / (theta + (double)k);
+    sc[0] += Ck * d;
+    sc[1] -= Ck * d * d;
+    if (k >= 1) sc[2] += Ck * log1p((double)k * sigma);
+    return;
+  }
+  if (MODE == PASS_IRLS) {
+    const double y = (double)(k + 1);
+    sc[0] -= (Ck - Ck1) * (y + theta) * log1p(sigma * y);
+    if (want_ll && k >= 1) sc[2] += Ck * log1p((double)k * sigma);
+    return;
+  }
+  if (MODE == PASS_THETA) {
+    const double d = 1.0 / (theta + (double)k);
+    sc[0] += Ck * d;
+    sc[1] += Ck * d * d;
+    return;
+  }
+}
+
+// negative.binomial(theta = 1)$initialize start of glm.fit: per cell mu = y + (y == 0)/6, eta = log(mu), sigma = 1.
+// w = mu / (1 + mu), w z = w eta + (y - mu)/(1 + mu).
+SC_HD void start_cell(int yi, double& w, double& wz) {
+  const double y = (double)yi;
+  const double mu = y + (yi == 0 ? 1.0 / 6.0 : 0.0);
+  const double inv = 1.0 / (1.0 + mu);
+  w = mu * inv;
+  wz = w * log(mu) + (y - mu) * inv;
+}
+
+}  // namespace sclane

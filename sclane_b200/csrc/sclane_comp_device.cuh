@@ -1,0 +1,374 @@
+// sclane_comp_device.cuh -- CUDA side of the X-compressed GLM path (see sclane_comp.cuh for the algebra).
+//
+//   k_aggregate      one CTA per gene: reads the gene's pseudotime-sorted counts once (4 B / cell) and reduces them to
+//                    the per-point sums s_d = sum y, q_d = sum y^2, the gene's tail counts C_k = #{y > k}, the per-bucket
+//                    totals and the glm.fit mustart sums.  All sums run in a fixed order (integer atomics for the
+//                    histogram), so the result is bit-reproducible.
+//   k_comp_stage<S>  one CTA per gene: the same per-gene algorithm as k_stage (sclane_core.cuh), driven by CompDevExec,
+//                    whose pass<MODE>() walks the D distinct abscissae (not the N cells) plus ymax histogram terms, with a
+//                    closed form for buckets where the linear predictor is flat.  S = forward pass (all iterations: null
+//                    fit, score sweep, selection), backward pass, final + null glm.nb.
+// Genes whose largest count is >= kHistCap keep route = 0 and run through the per-cell kernels instead.
+#pragma once
+#include "sclane_comp.cuh"
+#include "sclane_device.cuh"
+
+namespace sclane {
+
+struct CompGeneDev {
+  CompGeneHdr hdr;
+  double ST[NBMAX][5];          // glm.fit mustart pass per bucket: sum w, sum w u, sum w u^2, sum w z, sum w z u
+};
+
+struct CompArgs {
+  const Lineage* lineage;
+  const int* pstart;            // [D + 1]
+  const double* pn;             // [D]
+  const double* pu;             // [D]
+  const unsigned char* pb;      // [D] bucket of the point
+  int D, Dpad;
+  const int* ys;                // [B][Npad] sorted counts (k_aggregate input)
+  double* s1;                   // [B][Dpad]
+  double* q;                    // [B][Dpad]
+  int* tail;                    // [B][kHistCap]
+  CompGeneDev* cg;              // [B]
+  const GeneStats* stats;
+  GeneOutDev* out;
+  int n_genes, M, n_iter;
+  double tols_score;
+};
+
+constexpr int kAggV = 9;        // per-bucket totals gathered by k_aggregate
+
+// add NV per-lane values into slot[b] (warp-private), lanes of a 32-point group usually share the bucket
+template <int NV>
+__device__ __forceinline__ void warp_bucket_add(const double (&v)[NV], int b, bool valid, double* myslot, int stride) {
+  const int lane = threadIdx.x & 31;
+  const int b0 = __shfl_sync(0xffffffffu, b, 0);
+  if (__all_sync(0xffffffffu, !valid || b == b0)) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double t = warp_sum(valid ? v[k] : 0.0);
+      if (lane == 0) myslot[b0 * stride + k] += t;
+    }
+  } else {
+    unsigned rem = __ballot_sync(0xffffffffu, valid);
+    while (rem) {
+      const int ld = __ffs(rem) - 1;
+      const int bb = __shfl_sync(0xffffffffu, b, ld);
+      const bool mine = valid && b == bb;
+      const unsigned same = __ballot_sync(0xffffffffu, mine);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const double t = warp_sum(mine ? v[k] : 0.0);
+        if (lane == 0) myslot[bb * stride + k] += t;
+      }
+      rem &= ~same;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
+  __shared__ int hist[kHistCap];
+  __shared__ double slot[kWarps][NBMAX][kAggV];
+  __shared__ double wtab[64], wztab[64];
+  __shared__ int chunk_sum[kThreads];
+  const int g = blockIdx.x;
+  if (g >= A.n_genes) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = A.lineage->T, Npad = A.lineage->Npad;
+  const int ymax = A.stats[g].ymax;
+  const int* __restrict__ y = A.ys + (size_t)g * (size_t)Npad;
+  double* __restrict__ s1 = A.s1 + (size_t)g * (size_t)A.Dpad;
+  double* __restrict__ q = A.q + (size_t)g * (size_t)A.Dpad;
+  for (int i = threadIdx.x; i < kHistCap; i += kThreads) hist[i] = 0;
+  for (int i = threadIdx.x; i < kWarps * NBMAX * kAggV; i += kThreads) (&slot[0][0][0])[i] = 0.0;
+  if (threadIdx.x < 64) start_cell(threadIdx.x, wtab[threadIdx.x], wztab[threadIdx.x]);
+  __syncthreads();
+  double* myslot = &slot[warp][0][0];
+  for (int base = warp * 32; base < A.D; base += kThreads) {
+    const int d = base + lane;
+    const bool valid = d < A.D;
+    double v[kAggV];
+#pragma unroll
+    for (int k = 0; k < kAggV; ++k) v[k] = 0.0;
+    int b = 0;
+    if (valid) {
+      const int i0 = A.pstart[d], i1 = A.pstart[d + 1];
+      long long s = 0, qq = 0;
+      double a0 = 0.0, b0 = 0.0;
+      for (int i = i0; i < i1; ++i) {
+        const int yi = y[i];
+        s += yi;
+        qq += (long long)yi * yi;
+        if (yi < kHistCap) atomicAdd(&hist[yi], 1);
+        double w, wz;
+        if (yi < 64) { w = wtab[yi]; wz = wztab[yi]; } else start_cell(yi, w, wz);
+        a0 += w; b0 += wz;
+      }
+      const double sd = (double)s, qd = (double)qq, u = A.pu[d];
+      s1[d] = sd; q[d] = qd;
+      b = A.pb[d];
+      v[0] = sd; v[1] = sd * u; v[2] = sd * u * u; v[3] = qd;
+      v[4] = a0; v[5] = a0 * u; v[6] = a0 * u * u; v[7] = b0; v[8] = b0 * u;
+    }
+    warp_bucket_add<kAggV>(v, b, valid, myslot, kAggV);
+  }
+  __syncthreads();
+  CompGeneDev& cg = A.cg[g];
+  for (int idx = threadIdx.x; idx < (T + 1) * kAggV; idx += kThreads) {
+    const int b = idx / kAggV, k = idx - b * kAggV;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += slot[w][b][k];
+    if (k == 0) cg.hdr.SB[b] = s;
+    else if (k == 1) cg.hdr.SBu[b] = s;
+    else if (k == 2) cg.hdr.SBuu[b] = s;
+    else if (k == 3) cg.hdr.QB[b] = s;
+    else cg.ST[b][k - 4] = s;
+  }
+  // tail counts: tail[k] = #{y > k} = sum_{j > k} hist[j]; suffix sums in chunks of kHistCap / kThreads
+  constexpr int CH = kHistCap / kThreads;
+  int local = 0;
+  for (int j = 0; j < CH; ++j) local += hist[threadIdx.x * CH + j];
+  chunk_sum[threadIdx.x] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = kThreads - 1; t >= 0; --t) { const int c = chunk_sum[t]; chunk_sum[t] = run; run += c; }   // sum of later chunks
+    cg.hdr.ymax = ymax;
+    cg.hdr.n_zero = hist[0];
+    cg.hdr.route = ymax < kHistCap ? 1 : 0;
+    cg.hdr.pad = 0;
+  }
+  __syncthreads();
+  if (ymax < kHistCap) {
+    int* __restrict__ tail = A.tail + (size_t)g * (size_t)kHistCap;
+    int run = chunk_sum[threadIdx.x];
+    for (int j = CH - 1; j >= 0; --j) {
+      const int k = threadIdx.x * CH + j;
+      if (k <= ymax) tail[k] = run;
+      run += hist[k];
+    }
+  }
+}
+
+template <int MODE> struct CompTraits;
+template <> struct CompTraits<PASS_FIT>        { static constexpr int NA = 7, NS = 3; };
+template <> struct CompTraits<PASS_IRLS>       { static constexpr int NA = 5, NS = 3; };
+template <> struct CompTraits<PASS_IRLS_START> { static constexpr int NA = 5, NS = 2; };
+template <> struct CompTraits<PASS_THETA>      { static constexpr int NA = 0, NS = 2; };
+template <> struct CompTraits<PASS_SWEEP>      { static constexpr int NA = 5, NS = 0; };
+template <> struct CompTraits<PASS_EMIT>       { static constexpr int NA = 0, NS = 0; };
+
+struct CompDevExec {
+  Work* W;
+  const Lineage* L;
+  const CompGeneDev* cg;            // shared-memory copy
+  const GeneStats* gs;
+  int D;
+  const double* __restrict__ pn;
+  const double* __restrict__ pu;
+  const unsigned char* __restrict__ pb;
+  const double* __restrict__ s1;
+  const double* __restrict__ q;
+  const int* __restrict__ tail;
+  double (*slot)[NBMAX][NACC];
+  double (*scw)[NSC];
+
+  __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ PassTabs* tabs() const { return nullptr; }
+  template <class F>
+  __device__ __forceinline__ void par_for(int n, F f) const {
+    for (int i = threadIdx.x; i < n; i += kThreads) f(i);
+  }
+
+  template <int NV>
+  __device__ __forceinline__ void flush(double (&acc)[NACC], int b, double* myslot) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double t = warp_sum(acc[k]);
+      if (lane == 0) myslot[b * NACC + k] += t;
+      acc[k] = 0.0;
+    }
+  }
+
+  template <int MODE>
+  __device__ __noinline__ void pass() {
+    if (MODE == PASS_EMIT) return;                 // the compressed sweep recomputes mu from the eta parameters
+    constexpr int NA = CompTraits<MODE>::NA;
+    constexpr int NS = CompTraits<MODE>::NS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int T = L->T;
+    const double sigma = W->sigma, theta = W->theta;
+    const bool want_ll = W->want_ll != 0;
+    __syncthreads();
+    if (MODE == PASS_IRLS_START) {
+      for (int idx = threadIdx.x; idx < (T + 1) * 5; idx += kThreads) { const int b = idx / 5, k = idx - b * 5; W->acc[b][k] = cg->ST[b][k]; }
+      if (threadIdx.x == 0) {
+        W->sc[0] = -gs->sum_ylogy + (double)cg->hdr.n_zero * theta * log1p(sigma / 6.0);
+        W->sc[1] = (double)cg->hdr.n_zero;
+        W->sc[2] = 0.0;
+      }
+      __syncthreads();
+      return;
+    }
+    double* myslot = &slot[warp][0][0];
+    if (NA > 0) for (int i = lane; i < (T + 1) * NACC; i += 32) myslot[i] = 0.0;
+    __syncwarp();
+    double acc[NACC], sc[NSC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NSC; ++k) sc[k] = 0.0;
+    // buckets with a flat linear predictor: one closed-form evaluation each (thread b owns bucket b)
+    if (threadIdx.x <= T && W->c[threadIdx.x] == 0.0) {
+      const int b = threadIdx.x;
+      double fa[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) fa[k] = 0.0;
+      flat_bucket_contrib<MODE>(L->U0[b], L->U1[b], L->U2[b], cg->hdr.SB[b], cg->hdr.SBu[b], cg->hdr.SBuu[b], cg->hdr.QB[b], W->a[b], sigma, theta,
+                                want_ll, fa, sc);
+#pragma unroll
+      for (int k = 0; k < NA; ++k) W->acc[b][k] = fa[k];
+    }
+    // the points of the remaining buckets: contiguous run of 32-point groups per warp
+    {
+      const int ngroups = (D + 31) >> 5;
+      const int g0 = (int)(((long long)ngroups * warp) / kWarps);
+      const int g1 = (int)(((long long)ngroups * (warp + 1)) / kWarps);
+      int cur_b = -1;
+      double a = 0.0, c = 0.0;
+#pragma unroll 1
+      for (int g = g0; g < g1; ++g) {
+        const int d = (g << 5) + lane;
+        const bool valid = d < D;
+        const int b = valid ? (int)pb[d] : 0;
+        const int b0 = __shfl_sync(0xffffffffu, b, 0);
+        if (__all_sync(0xffffffffu, !valid || b == b0)) {
+          if (b0 != cur_b) {
+            if (NA > 0 && cur_b >= 0) flush<NA>(acc, cur_b, myslot);
+            cur_b = b0;
+            a = W->a[b0]; c = W->c[b0];
+          }
+          if (c != 0.0 && valid)
+            point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], a, c, sigma, theta, want_ll, acc, sc);
+        } else {
+          if (NA > 0 && cur_b >= 0) flush<NA>(acc, cur_b, myslot);
+          cur_b = -1;
+          double ct[NACC];
+#pragma unroll
+          for (int k = 0; k < NACC; ++k) ct[k] = 0.0;
+          const double cb = W->c[b];
+          if (valid && cb != 0.0)
+            point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], W->a[b], cb, sigma, theta, want_ll, ct, sc);
+          if (NA > 0) {
+            double cv[NA > 0 ? NA : 1];
+#pragma unroll
+            for (int k = 0; k < NA; ++k) cv[k] = ct[k];
+            warp_bucket_add<(NA > 0 ? NA : 1)>(cv, b, valid, myslot, NACC);
+          }
+        }
+      }
+      if (NA > 0 && cur_b >= 0) flush<NA>(acc, cur_b, myslot);
+    }
+    // the mu-free histogram terms
+    if (NS > 0 && MODE != PASS_SWEEP) {
+      const int ymax = cg->hdr.ymax;
+      for (int k = threadIdx.x; k < ymax; k += kThreads)
+        hist_contrib<MODE>(k, (double)tail[k], (double)tail[k + 1], sigma, theta, want_ll, sc);
+    }
+    if (NS > 0) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        const double t = warp_sum(sc[k]);
+        if (lane == 0) scw[warp][k] = t;
+      }
+    }
+    __syncthreads();
+    if (NA > 0) {
+      constexpr int NAd = NA > 0 ? NA : 1;
+      for (int idx = threadIdx.x; idx < (T + 1) * NA; idx += kThreads) {
+        const int b = idx / NAd, k = idx - b * NAd;
+        if (W->c[b] != 0.0) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) s += slot[w][b][k];
+          W->acc[b][k] = s;
+        }
+      }
+    }
+    if (MODE == PASS_SWEEP)
+      for (int b = threadIdx.x; b <= T; b += kThreads) { W->acc[b][5] = cg->hdr.SB[b]; W->acc[b][6] = cg->hdr.SBu[b]; }
+    if (NS > 0 && threadIdx.x < NS) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += scw[w][threadIdx.x];
+      W->sc[threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+};
+
+enum CompStage : int { CSTAGE_FORWARD = 0, CSTAGE_BACKWARD = 1, CSTAGE_FINAL = 2 };
+
+template <int STAGE>
+__global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_comp_stage(CompArgs A) {
+  __shared__ Work W;
+  __shared__ Lineage Ls;
+  __shared__ GeneState st;
+  __shared__ GeneStats gs;
+  __shared__ CompGeneDev cg;
+  __shared__ double slot[kWarps][NBMAX][NACC];
+  __shared__ double scw[kWarps][NSC];
+  const int g = blockIdx.x;
+  if (g >= A.n_genes) return;
+  if (A.cg[g].hdr.route == 0) return;                     // block-uniform: this gene takes the per-cell kernels
+  {
+    const int* src = reinterpret_cast<const int*>(A.lineage);
+    int* dst = reinterpret_cast<int*>(&Ls);
+    for (int i = threadIdx.x; i < (int)(sizeof(Lineage) / sizeof(int)); i += kThreads) dst[i] = src[i];
+    const int* s2 = reinterpret_cast<const int*>(&A.out[g].st);
+    int* d2 = reinterpret_cast<int*>(&st);
+    for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kThreads) d2[i] = s2[i];
+    const int* s3 = reinterpret_cast<const int*>(&A.stats[g]);
+    int* d3 = reinterpret_cast<int*>(&gs);
+    for (int i = threadIdx.x; i < (int)(sizeof(GeneStats) / sizeof(int)); i += kThreads) d3[i] = s3[i];
+    const int* s4 = reinterpret_cast<const int*>(&A.cg[g]);
+    int* d4 = reinterpret_cast<int*>(&cg);
+    for (int i = threadIdx.x; i < (int)(sizeof(CompGeneDev) / sizeof(int)); i += kThreads) d4[i] = s4[i];
+    int* w = reinterpret_cast<int*>(&W);
+    for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kThreads) w[i] = 0;
+  }
+  __syncthreads();
+  CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, A.pb, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
+                 A.tail + (size_t)g * (size_t)kHistCap, slot, scw};
+  if (STAGE == CSTAGE_FORWARD) {
+    for (int it = 0; it < A.n_iter; ++it) {
+      gene_forward_fit(ex, Ls, gs, st, W);
+      gene_sweep(ex, Ls, gs, st, W, A.M, A.tols_score);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !st.fwd_done) { st.fwd_done = 1; st.fwd_stop = 4; }
+  } else if (STAGE == CSTAGE_BACKWARD) {
+    gene_backward(ex, Ls, gs, st, W);
+    __syncthreads();
+    if (threadIdx.x == 0) st.done |= 1;
+  } else {
+    gene_final(ex, Ls, gs, st, W, false, &A.out[g].alt, &A.out[g].null);
+    __syncthreads();
+    if (threadIdx.x == 0) st.done |= 2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) st.passes += W.passes;
+  __syncthreads();
+  {
+    int* d2 = reinterpret_cast<int*>(&A.out[g].st);
+    const int* s2 = reinterpret_cast<const int*>(&st);
+    for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kThreads) d2[i] = s2[i];
+  }
+}
+
+}  // namespace sclane

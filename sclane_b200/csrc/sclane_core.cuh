@@ -203,6 +203,7 @@ SC_HD void coop_set_tables(E& ex, Work& W) {
   ex.sync();
   if (W.sigma == 0.0) return;                 // Poisson passes do not use the tables (uniform branch)
   PassTabs* tb = ex.tabs();
+  if (tb == nullptr) return;                  // executors without per-cell special functions (X-compressed, GEE)
   TabTermFn t{&W, tb};
   ex.par_for(kTab, t);
   ex.sync();
@@ -839,6 +840,8 @@ struct GeneState {
   Model fin;            // final model after the backward pass
   double wic[PMAX];
   int n_wic;
+  int done;             // bit 0: backward pass done, bit 1: final fits done (set by the X-compressed kernels; the per-cell
+                        // kernels skip genes that already went through a stage)
 };
 
 // Forward-iteration bookkeeping after a sweep (marge2.R:368-758), in two leader steps around the cooperative

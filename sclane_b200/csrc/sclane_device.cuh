@@ -286,6 +286,8 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
     for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kThreads) w[i] = 0;
   }
   __syncthreads();
+  if (STAGE == STAGE_BACKWARD && (st.done & 1)) return;      // block-uniform: already handled by k_comp_stage
+  if (STAGE == STAGE_FINAL && (st.done & 2)) return;
   const size_t row = (size_t)g * (size_t)Ls.Npad;
   DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs};
   if (STAGE == STAGE_FWD_FIT) {

@@ -115,10 +115,39 @@ struct LineagePlan {
   std::vector<double> off;        // [Npad] log(1/size_factor) or empty
   std::vector<int32_t> bucket;    // [N] bucket of each sorted cell (host harness only)
   std::vector<double> Xs;         // [N] sorted rounded pseudotime
+  // X-compressed layout (sclane_comp.cuh): distinct rounded pseudotime values of the sorted cells
+  int D = 0;
+  std::vector<int32_t> pstart;    // [D + 1] range of sorted cells of point d
+  std::vector<double> pn, pu;     // [D] cells per point, bucket-local coordinate
+  std::vector<uint8_t> pb;        // [D] bucket of the point
+  int pbstart[NBMAX + 1] = {0};   // point index range per bucket
   double pt_min = 0, pt_max = 0;
   int minspan = 0;
   std::string error;
 };
+
+// distinct abscissae of the sorted cells (a point never straddles a bucket: buckets are defined by the abscissa)
+inline void build_points(LineagePlan& P) {
+  const Lineage& L = P.L;
+  P.pstart.clear(); P.pn.clear(); P.pu.clear();
+  for (int b = 0; b <= NBMAX; ++b) P.pbstart[b] = 0;
+  int b_cur = 0;
+  for (int i = 0; i < L.N; ++i) {
+    if (i == 0 || P.Xs[(size_t)i] != P.Xs[(size_t)i - 1]) {
+      const int d = (int)P.pstart.size();
+      while (b_cur <= L.T && i >= L.bstart[b_cur + 1]) { ++b_cur; P.pbstart[b_cur] = d; }
+      P.pstart.push_back(i);
+      P.pu.push_back(P.u[(size_t)i]);
+    }
+  }
+  P.D = (int)P.pstart.size();
+  P.pstart.push_back(L.N);
+  for (int b = b_cur + 1; b <= NBMAX; ++b) P.pbstart[b] = P.D;
+  P.pn.resize((size_t)P.D);
+  P.pb.resize((size_t)P.D);
+  for (int d = 0; d < P.D; ++d) P.pn[(size_t)d] = (double)(P.pstart[(size_t)d + 1] - P.pstart[(size_t)d]);
+  for (int b = 0; b <= L.T; ++b) for (int d = P.pbstart[b]; d < P.pbstart[b + 1]; ++d) P.pb[(size_t)d] = (uint8_t)b;
+}
 
 // pt_col: n_cells doubles with NaN = not in lineage.  size_factor may be null.
 inline bool build_lineage_plan(const double* pt_col, int64_t n_cells, const double* size_factor,
@@ -170,6 +199,7 @@ inline bool build_lineage_plan(const double* pt_col, int64_t n_cells, const doub
   for (int b = 0; b <= L.T; ++b) { L.bstart[b] = acc; acc += cnt[(size_t)b]; }
   L.bstart[L.T + 1] = acc;
   for (int b = L.T + 2; b <= NBMAX; ++b) L.bstart[b] = acc;
+  build_points(P);
   P.pt_min = *std::min_element(x.begin(), x.end());
   P.pt_max = *std::max_element(x.begin(), x.end());
   return true;

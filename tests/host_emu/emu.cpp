@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "../../sclane_b200/csrc/sclane_comp.cuh"
 #include "../../sclane_b200/csrc/sclane_gee_host.hpp"
 
 using namespace sclane;
@@ -40,6 +41,74 @@ struct HostExec {
   }
   template <class F>
   void par_for(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
+};
+
+// ---- X-compressed executor (sclane_comp.cuh), serial: defines the semantics of the compressed passes ----
+struct CompHostExec {
+  Work* W;
+  const Lineage* L;
+  const LineagePlan* P;
+  std::vector<double> s1, q, a0, b0, tail;     // per point / per count
+  CompGeneHdr H;
+  double sum_ylogy;
+  PassTabs* tabs() { return nullptr; }
+  bool leader() const { return true; }
+  void sync() const {}
+  template <class F>
+  void par_for(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
+  void aggregate(const int32_t* y) {                       // y: sorted counts
+    const int D = P->D;
+    s1.assign((size_t)D, 0.0); q.assign((size_t)D, 0.0); a0.assign((size_t)D, 0.0); b0.assign((size_t)D, 0.0);
+    std::memset(&H, 0, sizeof(H));
+    sum_ylogy = 0.0;
+    for (int i = 0; i < L->N; ++i) { if (y[i] > H.ymax) H.ymax = y[i]; if (y[i] == 0) H.n_zero++; if (y[i] > 0) sum_ylogy += (double)y[i] * std::log((double)y[i]); }
+    H.route = H.ymax < kHistCap ? 1 : 0;
+    std::vector<double> hist((size_t)H.ymax + 2, 0.0);
+    for (int b = 0; b <= L->T; ++b)
+      for (int d = P->pbstart[b]; d < P->pbstart[b + 1]; ++d) {
+        const double u = P->pu[(size_t)d];
+        for (int i = P->pstart[(size_t)d]; i < P->pstart[(size_t)d + 1]; ++i) {
+          const double v = (double)y[i];
+          double w, wz;
+          start_cell(y[i], w, wz);
+          s1[(size_t)d] += v; q[(size_t)d] += v * v; a0[(size_t)d] += w; b0[(size_t)d] += wz;
+          hist[(size_t)y[i]] += 1.0;
+        }
+        H.SB[b] += s1[(size_t)d]; H.SBu[b] += s1[(size_t)d] * u; H.SBuu[b] += s1[(size_t)d] * u * u; H.QB[b] += q[(size_t)d];
+      }
+    tail.assign((size_t)H.ymax + 1, 0.0);                  // tail[k] = #{y > k}, k = 0..ymax (tail[ymax] = 0)
+    double c = 0.0;
+    for (int k = H.ymax; k >= 0; --k) { tail[(size_t)k] = c; c += hist[(size_t)k]; }
+  }
+  template <int MODE>
+  void pass() {
+    if (MODE == PASS_EMIT) return;                         // the compressed sweep recomputes mu from the eta parameters
+    for (int b = 0; b <= L->T; ++b) for (int k = 0; k < (MODE == PASS_SWEEP ? 5 : NACC); ++k) W->acc[b][k] = 0.0;
+    for (int k = 0; k < NSC; ++k) W->sc[k] = 0.0;
+    if (MODE == PASS_IRLS_START) {
+      for (int b = 0; b <= L->T; ++b)
+        for (int d = P->pbstart[b]; d < P->pbstart[b + 1]; ++d) {
+          const double u = P->pu[(size_t)d];
+          W->acc[b][0] += a0[(size_t)d]; W->acc[b][1] += a0[(size_t)d] * u; W->acc[b][2] += a0[(size_t)d] * u * u;
+          W->acc[b][3] += b0[(size_t)d]; W->acc[b][4] += b0[(size_t)d] * u;
+        }
+      W->sc[0] = -sum_ylogy + (double)H.n_zero * W->theta * log1p(W->sigma / 6.0);
+      W->sc[1] = (double)H.n_zero;
+      return;
+    }
+    const bool want_ll = W->want_ll != 0;
+    for (int b = 0; b <= L->T; ++b) {
+      if (W->c[b] == 0.0) {
+        flat_bucket_contrib<MODE>(L->U0[b], L->U1[b], L->U2[b], H.SB[b], H.SBu[b], H.SBuu[b], H.QB[b], W->a[b], W->sigma, W->theta, want_ll, W->acc[b], W->sc);
+      } else {
+        for (int d = P->pbstart[b]; d < P->pbstart[b + 1]; ++d)
+          point_contrib<MODE>(P->pn[(size_t)d], s1[(size_t)d], q[(size_t)d], P->pu[(size_t)d], W->a[b], W->c[b], W->sigma, W->theta, want_ll, W->acc[b], W->sc);
+      }
+      if (MODE == PASS_SWEEP) { W->acc[b][5] = H.SB[b]; W->acc[b][6] = H.SBu[b]; }
+    }
+    if (MODE != PASS_SWEEP)
+      for (int k = 0; k < H.ymax; ++k) hist_contrib<MODE>(k, tail[(size_t)k], tail[(size_t)k + 1], W->sigma, W->theta, want_ll, W->sc);
+  }
 };
 
 static void gene_stats(const int32_t* y, int N, GeneStats& gs) {
@@ -78,14 +147,21 @@ extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t 
       Work W;
       std::memset(&W, 0, sizeof(W));
       HostExec ex{&W, &L, y.data(), P.u.data(), P.off.empty() ? nullptr : P.off.data(), mu.data(), P.bucket.data(), PassTabs()};
+      // opts->force_per_cell == 1: per-cell executor everywhere; otherwise the X-compressed executor runs every fit without
+      // an offset (the routing the CUDA path uses)
+      const bool comp = opts->force_per_cell != 1;
+      CompHostExec cx{&W, &L, &P};
+      if (comp) cx.aggregate(y.data());
+      const bool use_comp = comp && cx.H.route;
       for (int it = 0; it < 4 && !go.st.fwd_done && !go.st.error; ++it) {
-        gene_forward_fit(ex, L, gs, go.st, W);
-        gene_sweep(ex, L, gs, go.st, W, opts->M, opts->tols_score);
+        if (use_comp) { gene_forward_fit(cx, L, gs, go.st, W); gene_sweep(cx, L, gs, go.st, W, opts->M, opts->tols_score); }
+        else { gene_forward_fit(ex, L, gs, go.st, W); gene_sweep(ex, L, gs, go.st, W, opts->M, opts->tols_score); }
       }
       const int p_fwd = W.passes;
-      gene_backward(ex, L, gs, go.st, W);
+      if (use_comp) gene_backward(cx, L, gs, go.st, W); else gene_backward(ex, L, gs, go.st, W);
       const int p_bwd = W.passes;
-      gene_final(ex, L, gs, go.st, W, size_factor != nullptr, &go.alt, &go.null);
+      if (use_comp && size_factor == nullptr) gene_final(cx, L, gs, go.st, W, false, &go.alt, &go.null);
+      else gene_final(ex, L, gs, go.st, W, size_factor != nullptr, &go.alt, &go.null);
       if (std::getenv("SCLANE_EMU_STAGES"))
         std::fprintf(stderr, "gene %ld passes fwd %d bwd %d final %d (alt: alt=%d irls=%d; null: alt=%d irls=%d)\n", (long)g, p_fwd, p_bwd - p_fwd,
                      W.passes - p_bwd, go.alt.alternations, go.alt.irls_iters, go.null.alternations, go.null.irls_iters);

@@ -257,3 +257,29 @@ def test_full_size_properties():
     de = sb.getResultsDE(base)
     assert ((de["P_Val_Adj"] < 0.01).astype(int) == de["Gene_Dynamic_Lineage"]).all()
     assert 40 < int(de["Gene_Dynamic_Overall"].sum()) <= 192
+
+
+def test_compressed_path_vs_per_cell_path():
+    """The X-compressed kernels (default when 4-dp rounding leaves <= 0.8 N abscissae) and the per-cell kernels run the
+    same algorithm: identical discrete choices, statistics within the fp64 tolerance.  One gene carries a count >=
+    kHistCap (4096) and must be routed to the per-cell kernels inside the compressed run."""
+    import sclane_b200 as sb
+    from sclane_b200 import synth
+    counts, pt, _ = synth.make_counts(96, 20000, seed=21)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    counts[5, 17] = 5000
+    sf = sb.createCellOffset(counts)
+    for offs in (None, sf):
+        a = sb.testDynamic(counts, pt, size_factor_offset=offs, n_gpus=1, preds="none")
+        b = sb.testDynamic(counts, pt, size_factor_offset=offs, n_gpus=1, preds="none", force_per_cell=True)
+        assert a.profile["ms"]["comp_forward"] > 0 and b.profile["ms"]["comp_forward"] == 0
+        assert _rec_bytes(a.records[5]) == _rec_bytes(b.records[5])        # the routed gene ran the very same kernels
+        for i in range(96):
+            x, y = a.records[i], b.records[i]
+            assert x.status == y.status and record_terms(x) == record_terms(y), i
+            assert x.fwd_n_terms == y.fwd_n_terms and list(x.fwd_knot_idx) == list(y.fwd_knot_idx), i
+            if x.status == 3:
+                for j in range(x.n_terms):
+                    assert rel(x.coef[j], y.coef[j], 1e-6) < 1e-6 and rel(x.se[j], y.se[j], 1e-6) < 1e-6, i
+                assert rel(x.theta, y.theta) < 1e-6 and rel(x.loglik, y.loglik) < 1e-9, i
+                assert abs(x.test_stat - y.test_stat) < 1e-6 * (abs(y.test_stat) + 1e-3), i
