@@ -187,7 +187,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t per_gene = (h_counts ? (size_t)n_cells * 4 : 0) + (size_t)L.Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
-                          (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + sizeof(CompGeneDev) : 0);
+                          (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0);
   size_t budget = (size_t)((double)(free_b + pool.held()) * 0.6);
   const size_t cap = (size_t)24 << 30;
   if (budget > cap) budget = cap;
@@ -205,6 +205,8 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   double* d_s1 = use_comp ? (double*)pool.get("comp_s1", (size_t)B * (size_t)Dpad * 8) : nullptr;
   double* d_q = use_comp ? (double*)pool.get("comp_q", (size_t)B * (size_t)Dpad * 8) : nullptr;
   int* d_tail = use_comp ? (int*)pool.get("comp_tail", (size_t)B * (size_t)kHistCap * 4) : nullptr;
+  int* d_big = use_comp ? (int*)pool.get("comp_big", (size_t)B * (size_t)kBigCap * 4) : nullptr;
+  int* d_big_tmp = use_comp ? (int*)pool.get("comp_big_tmp", (size_t)B * (size_t)kBigCap * 4) : nullptr;
   CompGeneDev* d_cg = use_comp ? (CompGeneDev*)pool.get("comp_hdr", (size_t)B * sizeof(CompGeneDev)) : nullptr;
   const int n_iter = forward_iterations(o.M);
   EventTimer tm(s);
@@ -232,7 +234,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     CompArgs CA;
     if (use_comp) {
       CA.lineage = D.lin; CA.pstart = D.pstart; CA.pn = D.pn; CA.pu = D.pu; CA.pb = D.pb; CA.D = P.D; CA.Dpad = Dpad; CA.ys = d_ys;
-      CA.s1 = d_s1; CA.q = d_q; CA.tail = d_tail; CA.cg = d_cg; CA.stats = d_stats; CA.out = d_out; CA.n_genes = nb; CA.M = o.M;
+      CA.s1 = d_s1; CA.q = d_q; CA.tail = d_tail; CA.big = d_big; CA.big_tmp = d_big_tmp; CA.cg = d_cg; CA.stats = d_stats; CA.out = d_out; CA.n_genes = nb; CA.M = o.M;
       CA.n_iter = n_iter; CA.tols_score = o.tols_score;
       tm.mark(SCLANE_STAGE_AGGREGATE);
       k_aggregate<<<nb, kThreads, 0, s>>>(CA);

@@ -21,7 +21,9 @@
 
 namespace sclane {
 
-constexpr int kHistCap = 4096;          // genes with a count >= kHistCap take the per-cell path
+constexpr int kHistCap = 4096;          // counts below this go through the gene's histogram (tail counts)
+constexpr int kBigCap = 8192;           // counts >= kHistCap are kept as a sorted per-gene list of at most kBigCap cells, whose
+                                        // mu-free terms are evaluated directly; a gene with more such cells takes the per-cell path
 
 // gene-independent tables of the compressed layout (pointers are device or host memory, depending on the executor)
 struct CompTables {
@@ -36,8 +38,8 @@ struct CompTables {
 struct CompGeneHdr {
   int ymax;                 // largest count
   int n_zero;               // cells with y == 0
-  int route;                // 1 = compressed path usable (ymax < kHistCap)
-  int pad;
+  int route;                // 1 = compressed path usable (at most kBigCap cells with a count >= kHistCap)
+  int n_big;                // cells with a count >= kHistCap (listed in ascending order)
   double SB[NBMAX], SBu[NBMAX], SBuu[NBMAX], QB[NBMAX];     // per bucket: sum y, sum y u, sum y u^2, sum y^2
 };
 
@@ -180,6 +182,33 @@ SC_HD void hist_contrib(int k, double Ck, double Ck1, double sigma, double theta
     const double d = 1.0 / (theta + (double)k);
     sc[0] += Ck * d;
     sc[1] += Ck * d * d;
+    return;
+  }
+}
+
+// The mu-free part of a pass for one cell with a large count (not in the histogram): direct special-function evaluation.
+template <int MODE>
+SC_HD void big_contrib(int yi, double sigma, double theta, bool want_ll, double* sc) {
+  const double y = (double)yi;
+  if (MODE == PASS_FIT) {
+    if (sigma == 0.0) return;
+    double dpsi, dtri;
+    psi_tri_diff_big(yi, theta, dpsi, dtri);
+    sc[0] += dpsi;
+    sc[1] -= dtri;
+    sc[2] += nb_lambda_big(yi, sigma, theta);
+    return;
+  }
+  if (MODE == PASS_IRLS) {
+    sc[0] -= (y + theta) * log1p(sigma * y);
+    if (want_ll) sc[2] += nb_lambda_big(yi, sigma, theta);
+    return;
+  }
+  if (MODE == PASS_THETA) {
+    double dpsi, dtri;
+    psi_tri_diff_big(yi, theta, dpsi, dtri);
+    sc[0] += dpsi;
+    sc[1] += dtri;
     return;
   }
 }

@@ -8,7 +8,8 @@
 //                    whose pass<MODE>() walks the D distinct abscissae (not the N cells) plus ymax histogram terms, with a
 //                    closed form for buckets where the linear predictor is flat.  S = forward pass (all iterations: null
 //                    fit, score sweep, selection), backward pass, final + null glm.nb.
-// Genes whose largest count is >= kHistCap keep route = 0 and run through the per-cell kernels instead.
+// Counts >= kHistCap are kept as a short sorted list per gene; a gene with more than kBigCap such cells keeps route = 0 and
+// runs through the per-cell kernels instead.
 #pragma once
 #include "sclane_comp.cuh"
 #include "sclane_device.cuh"
@@ -31,6 +32,8 @@ struct CompArgs {
   double* s1;                   // [B][Dpad]
   double* q;                    // [B][Dpad]
   int* tail;                    // [B][kHistCap]
+  int* big;                     // [B][kBigCap] counts >= kHistCap of the gene, ascending
+  int* big_tmp;                 // [B][kBigCap] unsorted staging
   CompGeneDev* cg;              // [B]
   const GeneStats* stats;
   GeneOutDev* out;
@@ -73,8 +76,11 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
   __shared__ double slot[kWarps][NBMAX][kAggV];
   __shared__ double wtab[64], wztab[64];
   __shared__ int chunk_sum[kThreads];
+  __shared__ int n_big_s;
   const int g = blockIdx.x;
   if (g >= A.n_genes) return;
+  if (threadIdx.x == 0) n_big_s = 0;
+  int* __restrict__ big_tmp = A.big_tmp + (size_t)g * (size_t)kBigCap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = A.lineage->T, Npad = A.lineage->Npad;
   const int ymax = A.stats[g].ymax;
@@ -102,6 +108,7 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
         s += yi;
         qq += (long long)yi * yi;
         if (yi < kHistCap) atomicAdd(&hist[yi], 1);
+        else { const int slot_i = atomicAdd(&n_big_s, 1); if (slot_i < kBigCap) big_tmp[slot_i] = yi; }
         double w, wz;
         if (yi < 64) { w = wtab[yi]; wz = wztab[yi]; } else start_cell(yi, w, wz);
         a0 += w; b0 += wz;
@@ -138,17 +145,33 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
     for (int t = kThreads - 1; t >= 0; --t) { const int c = chunk_sum[t]; chunk_sum[t] = run; run += c; }   // sum of later chunks
     cg.hdr.ymax = ymax;
     cg.hdr.n_zero = hist[0];
-    cg.hdr.route = ymax < kHistCap ? 1 : 0;
-    cg.hdr.pad = 0;
+    cg.hdr.route = n_big_s <= kBigCap ? 1 : 0;
+    cg.hdr.n_big = n_big_s;
   }
   __syncthreads();
-  if (ymax < kHistCap) {
+  const int n_big = n_big_s;
+  if (n_big > kBigCap) return;                            // block-uniform: the gene takes the per-cell kernels
+  {
+    // tail[k] = #{k < y < kHistCap} for k <= hmax, the largest count that goes through the histogram
+    const int hmax = ymax < kHistCap ? ymax : kHistCap - 1;
     int* __restrict__ tail = A.tail + (size_t)g * (size_t)kHistCap;
     int run = chunk_sum[threadIdx.x];
     for (int j = CH - 1; j >= 0; --j) {
       const int k = threadIdx.x * CH + j;
-      if (k <= ymax) tail[k] = run;
+      if (k <= hmax) tail[k] = run;
       run += hist[k];
+    }
+  }
+  if (n_big > 0) {
+    // the append order above is arbitrary: rank sort (ties are equal values) makes the list -- and every sum taken
+    // over it -- reproducible
+    __threadfence_block();
+    int* __restrict__ big = A.big + (size_t)g * (size_t)kBigCap;
+    for (int i = threadIdx.x; i < n_big; i += kThreads) {
+      const int v = big_tmp[i];
+      int rank = 0;
+      for (int j = 0; j < n_big; ++j) { const int w = big_tmp[j]; rank += (w < v || (w == v && j < i)) ? 1 : 0; }
+      big[rank] = v;
     }
   }
 }
@@ -173,6 +196,7 @@ struct CompDevExec {
   const double* __restrict__ s1;
   const double* __restrict__ q;
   const int* __restrict__ tail;
+  const int* __restrict__ big;
   double (*slot)[NBMAX][NACC];
   double (*scw)[NSC];
 
@@ -276,9 +300,11 @@ struct CompDevExec {
     }
     // the mu-free histogram terms
     if (NS > 0 && MODE != PASS_SWEEP) {
-      const int ymax = cg->hdr.ymax;
-      for (int k = threadIdx.x; k < ymax; k += kThreads)
+      const int hmax = cg->hdr.ymax < kHistCap ? cg->hdr.ymax : kHistCap - 1;
+      for (int k = threadIdx.x; k < hmax; k += kThreads)
         hist_contrib<MODE>(k, (double)tail[k], (double)tail[k + 1], sigma, theta, want_ll, sc);
+      const int n_big = cg->hdr.n_big;
+      for (int e = threadIdx.x; e < n_big; e += kThreads) big_contrib<MODE>(big[e], sigma, theta, want_ll, sc);
     }
     if (NS > 0) {
 #pragma unroll
@@ -344,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_comp_stage(Comp
   }
   __syncthreads();
   CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, A.pb, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
-                 A.tail + (size_t)g * (size_t)kHistCap, slot, scw};
+                 A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, slot, scw};
   if (STAGE == CSTAGE_FORWARD) {
     for (int it = 0; it < A.n_iter; ++it) {
       gene_forward_fit(ex, Ls, gs, st, W);

@@ -49,8 +49,10 @@ struct CompHostExec {
   const Lineage* L;
   const LineagePlan* P;
   std::vector<double> s1, q, a0, b0, tail;     // per point / per count
+  std::vector<int32_t> big;                    // counts >= kHistCap, ascending
   CompGeneHdr H;
   double sum_ylogy;
+  int hmax_ = 0;
   PassTabs* tabs() { return nullptr; }
   bool leader() const { return true; }
   void sync() const {}
@@ -62,8 +64,13 @@ struct CompHostExec {
     std::memset(&H, 0, sizeof(H));
     sum_ylogy = 0.0;
     for (int i = 0; i < L->N; ++i) { if (y[i] > H.ymax) H.ymax = y[i]; if (y[i] == 0) H.n_zero++; if (y[i] > 0) sum_ylogy += (double)y[i] * std::log((double)y[i]); }
-    H.route = H.ymax < kHistCap ? 1 : 0;
-    std::vector<double> hist((size_t)H.ymax + 2, 0.0);
+    big.clear();
+    for (int i = 0; i < L->N; ++i) if (y[i] >= kHistCap) big.push_back(y[i]);
+    std::sort(big.begin(), big.end());
+    H.n_big = (int)big.size();
+    H.route = H.n_big <= kBigCap ? 1 : 0;
+    const int hmax = H.ymax < kHistCap ? H.ymax : kHistCap - 1;     // largest count that goes through the histogram
+    std::vector<double> hist((size_t)hmax + 2, 0.0);
     for (int b = 0; b <= L->T; ++b)
       for (int d = P->pbstart[b]; d < P->pbstart[b + 1]; ++d) {
         const double u = P->pu[(size_t)d];
@@ -72,13 +79,14 @@ struct CompHostExec {
           double w, wz;
           start_cell(y[i], w, wz);
           s1[(size_t)d] += v; q[(size_t)d] += v * v; a0[(size_t)d] += w; b0[(size_t)d] += wz;
-          hist[(size_t)y[i]] += 1.0;
+          if (y[i] < kHistCap) hist[(size_t)y[i]] += 1.0;
         }
         H.SB[b] += s1[(size_t)d]; H.SBu[b] += s1[(size_t)d] * u; H.SBuu[b] += s1[(size_t)d] * u * u; H.QB[b] += q[(size_t)d];
       }
-    tail.assign((size_t)H.ymax + 1, 0.0);                  // tail[k] = #{y > k}, k = 0..ymax (tail[ymax] = 0)
+    tail.assign((size_t)hmax + 1, 0.0);                    // tail[k] = #{k < y < kHistCap}, k = 0..hmax (tail[hmax] = 0)
     double c = 0.0;
-    for (int k = H.ymax; k >= 0; --k) { tail[(size_t)k] = c; c += hist[(size_t)k]; }
+    for (int k = hmax; k >= 0; --k) { tail[(size_t)k] = c; c += hist[(size_t)k]; }
+    hmax_ = hmax;
   }
   template <int MODE>
   void pass() {
@@ -106,8 +114,10 @@ struct CompHostExec {
       }
       if (MODE == PASS_SWEEP) { W->acc[b][5] = H.SB[b]; W->acc[b][6] = H.SBu[b]; }
     }
-    if (MODE != PASS_SWEEP)
-      for (int k = 0; k < H.ymax; ++k) hist_contrib<MODE>(k, tail[(size_t)k], tail[(size_t)k + 1], W->sigma, W->theta, want_ll, W->sc);
+    if (MODE != PASS_SWEEP) {
+      for (int k = 0; k < hmax_; ++k) hist_contrib<MODE>(k, tail[(size_t)k], tail[(size_t)k + 1], W->sigma, W->theta, want_ll, W->sc);
+      for (int32_t v : big) big_contrib<MODE>(v, W->sigma, W->theta, want_ll, W->sc);
+    }
   }
 };
 

@@ -261,13 +261,15 @@ def test_full_size_properties():
 
 def test_compressed_path_vs_per_cell_path():
     """The X-compressed kernels (default when 4-dp rounding leaves <= 0.8 N abscissae) and the per-cell kernels run the
-    same algorithm: identical discrete choices, statistics within the fp64 tolerance.  One gene carries a count >=
-    kHistCap (4096) and must be routed to the per-cell kernels inside the compressed run."""
+    same algorithm: identical discrete choices, statistics within the fp64 tolerance.  Gene 6 carries a few counts >=
+    kHistCap (4096; kept as a sorted list), gene 5 more than kBigCap (8192) of them, which routes it to the per-cell
+    kernels inside the compressed run."""
     import sclane_b200 as sb
     from sclane_b200 import synth
     counts, pt, _ = synth.make_counts(96, 20000, seed=21)
     counts = np.ascontiguousarray(counts, dtype=np.int32)
-    counts[5, 17] = 5000
+    counts[5, :9000] = 4100 + (np.arange(9000) % 900)
+    counts[6, 100:130] += 6000
     sf = sb.createCellOffset(counts)
     for offs in (None, sf):
         a = sb.testDynamic(counts, pt, size_factor_offset=offs, n_gpus=1, preds="none")
