@@ -70,6 +70,7 @@ struct DevicePool {
   struct Slot { void* p = nullptr; size_t bytes = 0; bool host = false; };
   std::map<std::string, Slot> slots;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;      // H2D of the next batch overlaps the kernels of the current one
   void* get(const std::string& name, size_t bytes, bool pinned_host = false) {
     Slot& sl = slots[name];
     if (sl.bytes >= bytes && sl.p) return sl.p;
@@ -86,6 +87,7 @@ struct DevicePool {
     for (auto& kv : slots) if (kv.second.p) { if (kv.second.host) cudaFreeHost(kv.second.p); else cudaFree(kv.second.p); }
     slots.clear();
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = nullptr; }
   }
 };
 std::mutex g_pool_mu;
@@ -128,6 +130,7 @@ struct DevicePlan {
   double* pn = nullptr;
   double* pu = nullptr;
   unsigned char* pb = nullptr;
+  int* pbstart = nullptr;
   void upload_points(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
     pstart = (int*)pool.get("pstart", P.pstart.size() * sizeof(int));
     pn = (double*)pool.get("pn", P.pn.size() * sizeof(double));
@@ -137,6 +140,8 @@ struct DevicePlan {
     CK(cudaMemcpyAsync(pn, P.pn.data(), P.pn.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(pu, P.pu.data(), P.pu.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(pb, P.pb.data(), P.pb.size(), cudaMemcpyHostToDevice, s));
+    pbstart = (int*)pool.get("pbstart", sizeof(P.pbstart));
+    CK(cudaMemcpyAsync(pbstart, P.pbstart, sizeof(P.pbstart), cudaMemcpyHostToDevice, s));
   }
   void upload(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
     perm = (int*)pool.get("perm", P.perm.size() * sizeof(int));
@@ -186,16 +191,50 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   // batch size from free memory (+ what the pool already holds): raw (host path) + sorted counts + mu + moments + records
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t per_gene = (h_counts ? (size_t)n_cells * 4 : 0) + (size_t)L.Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
+  const size_t per_gene = (h_counts ? (size_t)n_cells * 8 : 0) + (size_t)L.Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
                           (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0);
   size_t budget = (size_t)((double)(free_b + pool.held()) * 0.6);
   const size_t cap = (size_t)24 << 30;
   if (budget > cap) budget = cap;
   int64_t B = (int64_t)(budget / per_gene);
+  // host counts: aim for ~8 batches (but >= 2048 genes each, several waves of CTAs) so that the H2D copy of batch k + 1
+  // runs on the copy stream while the kernels of batch k execute
+  if (h_counts) { const int64_t want = std::max<int64_t>(2048, (G + 7) / 8); if (want < B) B = want; }
   if (o.genes_per_batch > 0 && o.genes_per_batch < B) B = o.genes_per_batch;
   if (B > G) B = G;
   if (B < 1) throw CudaFail{"not enough free device memory for a single gene"};
-  int* d_raw = h_counts ? (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4) : nullptr;
+  const int64_t n_batches = (G + B - 1) / B;
+  int* d_raw2[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  cudaStream_t cs = nullptr;
+  if (h_counts) {
+    if (!pool.copy_stream) CK(cudaStreamCreateWithFlags(&pool.copy_stream, cudaStreamNonBlocking));
+    cs = pool.copy_stream;
+    d_raw2[0] = (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4);
+    d_raw2[1] = n_batches > 1 ? (int*)pool.get("raw_b", (size_t)B * (size_t)n_cells * 4) : d_raw2[0];
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  struct EventGuard {
+    cudaEvent_t* a; cudaEvent_t* b;
+    ~EventGuard() { for (int i = 0; i < 2; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); } }
+  } ev_guard{ev_h2d, ev_free};
+  auto issue_h2d = [&](int64_t k) {
+    const int buf = (int)(k & 1);
+    const int64_t kb0 = g0 + k * B, kb1 = std::min<int64_t>(kb0 + B, g1);
+    if (k >= 2) CK(cudaStreamWaitEvent(cs, ev_free[buf], 0));          // the gather of batch k - 2 has consumed this buffer
+    CK(cudaMemcpyAsync(d_raw2[buf], h_counts + (size_t)kb0 * (size_t)n_cells, (size_t)(kb1 - kb0) * (size_t)n_cells * 4,
+                       cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(ev_h2d[buf], cs));
+    prof.h2d_bytes += (double)(kb1 - kb0) * (double)n_cells * 4.0;
+    prof.launches[SCLANE_STAGE_COPY]++;
+  };
+  if (h_counts) {
+    CK(cudaStreamSynchronize(s));                                       // plan tables are in place before anything overlaps
+    issue_h2d(0);
+  }
   int* d_ys = (int*)pool.get("ys", (size_t)B * (size_t)L.Npad * 4);
   double* d_mu = (double*)pool.get("mu", (size_t)B * (size_t)L.Npad * 8);
   double* d_mom = (double*)pool.get("mom", (size_t)B * (size_t)NBMAX * NACC * 8);
@@ -210,22 +249,22 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   CompGeneDev* d_cg = use_comp ? (CompGeneDev*)pool.get("comp_hdr", (size_t)B * sizeof(CompGeneDev)) : nullptr;
   const int n_iter = forward_iterations(o.M);
   EventTimer tm(s);
-  for (int64_t b0 = g0; b0 < g1; b0 += B) {
+  for (int64_t b0 = g0, kb = 0; b0 < g1; b0 += B, ++kb) {
     const int64_t b1 = std::min<int64_t>(b0 + B, g1);
     const int nb = (int)(b1 - b0);
-    tm.mark(SCLANE_STAGE_COPY);
+    tm.mark(SCLANE_STAGE_COPY);             // on the compute stream this interval is the EXPOSED wait for the batch's H2D
     const int* raw = nullptr;
     if (h_counts) {
-      CK(cudaMemcpyAsync(d_raw, h_counts + (size_t)b0 * (size_t)n_cells, (size_t)nb * (size_t)n_cells * 4, cudaMemcpyHostToDevice, s));
-      prof.h2d_bytes += (double)nb * (double)n_cells * 4.0;
-      prof.launches[SCLANE_STAGE_COPY]++;
-      raw = d_raw;
+      if (kb + 1 < n_batches) issue_h2d(kb + 1);
+      CK(cudaStreamWaitEvent(s, ev_h2d[kb & 1], 0));
+      raw = d_raw2[kb & 1];
     } else {
       raw = d_counts + (size_t)b0 * (size_t)n_cells;
     }
     tm.mark(SCLANE_STAGE_GATHER);
     k_gather_stats<<<nb, kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
     CK(cudaGetLastError());
+    if (h_counts) CK(cudaEventRecord(ev_free[kb & 1], s));
     g_launches.fetch_add(1);
     prof.launches[SCLANE_STAGE_GATHER]++;
     StageArgs A;
@@ -233,7 +272,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     A.scores = nullptr; A.mom = d_mom; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
     CompArgs CA;
     if (use_comp) {
-      CA.lineage = D.lin; CA.pstart = D.pstart; CA.pn = D.pn; CA.pu = D.pu; CA.pb = D.pb; CA.D = P.D; CA.Dpad = Dpad; CA.ys = d_ys;
+      CA.lineage = D.lin; CA.pstart = D.pstart; CA.pn = D.pn; CA.pu = D.pu; CA.pb = D.pb; CA.pbstart = D.pbstart; CA.D = P.D; CA.Dpad = Dpad; CA.ys = d_ys;
       CA.s1 = d_s1; CA.q = d_q; CA.tail = d_tail; CA.big = d_big; CA.big_tmp = d_big_tmp; CA.cg = d_cg; CA.stats = d_stats; CA.out = d_out; CA.n_genes = nb; CA.M = o.M;
       CA.n_iter = n_iter; CA.tols_score = o.tols_score;
       tm.mark(SCLANE_STAGE_AGGREGATE);

@@ -27,6 +27,7 @@ struct CompArgs {
   const double* pn;             // [D]
   const double* pu;             // [D]
   const unsigned char* pb;      // [D] bucket of the point
+  const int* pbstart;           // [NBMAX + 1] point range per bucket
   int D, Dpad;
   const int* ys;                // [B][Npad] sorted counts (k_aggregate input)
   double* s1;                   // [B][Dpad]
@@ -192,12 +193,11 @@ struct CompDevExec {
   int D;
   const double* __restrict__ pn;
   const double* __restrict__ pu;
-  const unsigned char* __restrict__ pb;
+  const int* pbstart;               // [NBMAX + 1] point range per bucket (shared memory)
   const double* __restrict__ s1;
   const double* __restrict__ q;
   const int* __restrict__ tail;
   const int* __restrict__ big;
-  double (*slot)[NBMAX][NACC];
   double (*scw)[NSC];
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
@@ -208,17 +208,11 @@ struct CompDevExec {
     for (int i = threadIdx.x; i < n; i += kThreads) f(i);
   }
 
-  template <int NV>
-  __device__ __forceinline__ void flush(double (&acc)[NACC], int b, double* myslot) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const double t = warp_sum(acc[k]);
-      if (lane == 0) myslot[b * NACC + k] += t;
-      acc[k] = 0.0;
-    }
-  }
-
+  // One pass.  Work unit = one knot bucket, owned by one warp: a bucket with a flat linear predictor is a single closed-form
+  // evaluation (lane 0); otherwise the bucket's points are walked lane-strided with independent iterations (the loads of
+  // the next points are in flight while the current ones are evaluated), reduced with one shuffle tree per accumulator
+  // and written straight to W.acc[b] -- no cross-warp combine, fixed summation order.  Non-flat buckets are dealt
+  // round-robin to the 8 warps.  The mu-free histogram terms are thread-strided; the scalars are reduced across warps.
   template <int MODE>
   __device__ __noinline__ void pass() {
     if (MODE == PASS_EMIT) return;                 // the compressed sweep recomputes mu from the eta parameters
@@ -237,66 +231,56 @@ struct CompDevExec {
         W->sc[2] = 0.0;
       }
       __syncthreads();
-      return;
+      (void)NA; (void)NS; (void)lane; (void)warp; (void)want_ll;
+    } else {
+      pass_points<MODE>();
     }
-    double* myslot = &slot[warp][0][0];
-    if (NA > 0) for (int i = lane; i < (T + 1) * NACC; i += 32) myslot[i] = 0.0;
-    __syncwarp();
-    double acc[NACC], sc[NSC];
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  }
+
+  template <int MODE>
+  __device__ __forceinline__ void pass_points() {
+    constexpr int NA = CompTraits<MODE>::NA;
+    constexpr int NS = CompTraits<MODE>::NS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int T = L->T;
+    const double sigma = W->sigma, theta = W->theta;
+    const bool want_ll = W->want_ll != 0;
+    double sc[NSC];
 #pragma unroll
     for (int k = 0; k < NSC; ++k) sc[k] = 0.0;
-    // buckets with a flat linear predictor: one closed-form evaluation each (thread b owns bucket b)
-    if (threadIdx.x <= T && W->c[threadIdx.x] == 0.0) {
-      const int b = threadIdx.x;
-      double fa[NACC];
-#pragma unroll
-      for (int k = 0; k < NACC; ++k) fa[k] = 0.0;
-      flat_bucket_contrib<MODE>(L->U0[b], L->U1[b], L->U2[b], cg->hdr.SB[b], cg->hdr.SBu[b], cg->hdr.SBuu[b], cg->hdr.QB[b], W->a[b], sigma, theta,
-                                want_ll, fa, sc);
-#pragma unroll
-      for (int k = 0; k < NA; ++k) W->acc[b][k] = fa[k];
-    }
-    // the points of the remaining buckets: contiguous run of 32-point groups per warp
-    {
-      const int ngroups = (D + 31) >> 5;
-      const int g0 = (int)(((long long)ngroups * warp) / kWarps);
-      const int g1 = (int)(((long long)ngroups * (warp + 1)) / kWarps);
-      int cur_b = -1;
-      double a = 0.0, c = 0.0;
+    int n_sloped = 0;                               // running index among the non-flat buckets (warp-uniform)
 #pragma unroll 1
-      for (int g = g0; g < g1; ++g) {
-        const int d = (g << 5) + lane;
-        const bool valid = d < D;
-        const int b = valid ? (int)pb[d] : 0;
-        const int b0 = __shfl_sync(0xffffffffu, b, 0);
-        if (__all_sync(0xffffffffu, !valid || b == b0)) {
-          if (b0 != cur_b) {
-            if (NA > 0 && cur_b >= 0) flush<NA>(acc, cur_b, myslot);
-            cur_b = b0;
-            a = W->a[b0]; c = W->c[b0];
-          }
-          if (c != 0.0 && valid)
-            point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], a, c, sigma, theta, want_ll, acc, sc);
-        } else {
-          if (NA > 0 && cur_b >= 0) flush<NA>(acc, cur_b, myslot);
-          cur_b = -1;
-          double ct[NACC];
+    for (int b = 0; b <= T; ++b) {
+      const double c = W->c[b];
+      if (c == 0.0) {
+        if ((b & (kWarps - 1)) != warp) continue;
+        double fa[NACC];
 #pragma unroll
-          for (int k = 0; k < NACC; ++k) ct[k] = 0.0;
-          const double cb = W->c[b];
-          if (valid && cb != 0.0)
-            point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], W->a[b], cb, sigma, theta, want_ll, ct, sc);
-          if (NA > 0) {
-            double cv[NA > 0 ? NA : 1];
+        for (int k = 0; k < NACC; ++k) fa[k] = 0.0;
+        if (lane == 0) {
+          flat_bucket_contrib<MODE>(L->U0[b], L->U1[b], L->U2[b], cg->hdr.SB[b], cg->hdr.SBu[b], cg->hdr.SBuu[b], cg->hdr.QB[b], W->a[b], sigma,
+                                    theta, want_ll, fa, sc);
 #pragma unroll
-            for (int k = 0; k < NA; ++k) cv[k] = ct[k];
-            warp_bucket_add<(NA > 0 ? NA : 1)>(cv, b, valid, myslot, NACC);
-          }
+          for (int k = 0; k < NA; ++k) W->acc[b][k] = fa[k];
         }
+        continue;
       }
-      if (NA > 0 && cur_b >= 0) flush<NA>(acc, cur_b, myslot);
+      const int owner = n_sloped & (kWarps - 1);
+      ++n_sloped;
+      if (owner != warp) continue;
+      const double a = W->a[b];
+      double acc[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+      const int p1 = pbstart[b + 1];
+#pragma unroll 2
+      for (int d = pbstart[b] + lane; d < p1; d += 32)
+        point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], a, c, sigma, theta, want_ll, acc, sc);
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        const double t = warp_sum(acc[k]);
+        if (lane == 0) W->acc[b][k] = t;
+      }
     }
     // the mu-free histogram terms
     if (NS > 0 && MODE != PASS_SWEEP) {
@@ -313,21 +297,9 @@ struct CompDevExec {
         if (lane == 0) scw[warp][k] = t;
       }
     }
-    __syncthreads();
-    if (NA > 0) {
-      constexpr int NAd = NA > 0 ? NA : 1;
-      for (int idx = threadIdx.x; idx < (T + 1) * NA; idx += kThreads) {
-        const int b = idx / NAd, k = idx - b * NAd;
-        if (W->c[b] != 0.0) {
-          double s = 0.0;
-#pragma unroll
-          for (int w = 0; w < kWarps; ++w) s += slot[w][b][k];
-          W->acc[b][k] = s;
-        }
-      }
-    }
     if (MODE == PASS_SWEEP)
       for (int b = threadIdx.x; b <= T; b += kThreads) { W->acc[b][5] = cg->hdr.SB[b]; W->acc[b][6] = cg->hdr.SBu[b]; }
+    __syncthreads();
     if (NS > 0 && threadIdx.x < NS) {
       double s = 0.0;
 #pragma unroll
@@ -347,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_comp_stage(Comp
   __shared__ GeneState st;
   __shared__ GeneStats gs;
   __shared__ CompGeneDev cg;
-  __shared__ double slot[kWarps][NBMAX][NACC];
+  __shared__ int pbs[NBMAX + 1];
   __shared__ double scw[kWarps][NSC];
   const int g = blockIdx.x;
   if (g >= A.n_genes) return;
@@ -367,10 +339,11 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_comp_stage(Comp
     for (int i = threadIdx.x; i < (int)(sizeof(CompGeneDev) / sizeof(int)); i += kThreads) d4[i] = s4[i];
     int* w = reinterpret_cast<int*>(&W);
     for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kThreads) w[i] = 0;
+    if (threadIdx.x <= NBMAX) pbs[threadIdx.x] = A.pbstart[threadIdx.x];
   }
   __syncthreads();
-  CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, A.pb, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
-                 A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, slot, scw};
+  CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, pbs, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
+                 A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, scw};
   if (STAGE == CSTAGE_FORWARD) {
     for (int it = 0; it < A.n_iter; ++it) {
       gene_forward_fit(ex, Ls, gs, st, W);
