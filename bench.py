@@ -14,8 +14,11 @@ null glm.nb, LRT) over the rank's gene shard.
            library around every stage on its own stream, summed, max over ranks
   e2e    = genes/s through the reference-facing call with HOST buffers (sclane_test_dynamic): pinned-host -> device copy of
            the counts and device -> host copy of the records inside the timed region (wall clock around the call)
-  roofline = score-sweep streaming kernel k_sweep_moments: algorithmic bytes (12 B per cell per swept gene-iteration + 8 B per
-           cell per launch) / CUDA-event time of its launches, vs the measured HBM copy bandwidth
+  roofline = the kernel that performs the score sweep: algorithmic bytes (12 B per cell per swept gene-iteration + 8 B per
+           cell per launch) / CUDA-event time of its launches, vs the measured HBM copy bandwidth.  On the default
+           route that kernel is k_comp_stage<FORWARD> (X-compressed: null fits + sweep + selection of ALL forward iterations in
+           one launch; it no longer reads those bytes, so `traffic` << algorithmic bytes); with --per-cell it is the
+           streaming kernel k_sweep_moments, which does read them (97.7 % of the measured HBM peak, profiles/)
   cpu_baseline = the numpy oracle ("port": R is not installable here) on a bounded gene sample on this box's host cores
 
 `--impl reference` times the reference algorithm's CPU restatement (the oracle, one process per core -- the reference's own
@@ -42,6 +45,8 @@ sys.path.insert(0, ROOT)
 #     25.73 GB; scaled to the average launch of the default run (two batches, 24.0 GB algorithmic each).
 # c2: profiles/r01_ncu_sweep_v1.txt -- 243.2 MB read + 7.4 MB written per 2,000-gene launch (240.1 MB algorithmic).
 TRAFFIC_PER_LAUNCH = {"c2": 250.6e6, "c5": 24.02e9}
+# same for the X-compressed forward kernel k_comp_stage<0> (profiles/r01_ncu_comp_forward_*.txt); filled from the capture
+TRAFFIC_PER_LAUNCH_COMP = {"c2": None, "c5": None}
 
 CONFIGS = {
     "c5": {"genes": 20000, "cells": 200000,
@@ -195,6 +200,7 @@ def main():
     ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
     ap.add_argument("--genes", type=int, default=0, help="total genes (default: the config's)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="genes of the CPU-baseline sample (0 = skip, -1 = automatic)")
+    ap.add_argument("--per-cell", action="store_true", help="force the per-cell kernels (no X-compression): profiling of k_sweep_moments")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.genes:
@@ -220,7 +226,7 @@ def main():
     G = g1 - g0
     d_counts, pt = make_counts_gpu(g0, g1, N, dev)
     torch.cuda.synchronize()
-    opts = sb.api._opts(gpu_ids=[local])
+    opts = sb.api._opts(gpu_ids=[local], force_per_cell=args.per_cell)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
@@ -304,10 +310,27 @@ def main():
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
-        sweep_ms = prof_acc["ms"]["sweep"]
-        sweep_launches = prof_acc["launches"]["sweep"]
+        comp = prof_acc["ms"]["comp_forward"] > 0
+        if comp:
+            # default route: the sweep of every forward iteration runs inside k_comp_stage<FORWARD>
+            sweep_ms = prof_acc["ms"]["comp_forward"]
+            sweep_launches = prof_acc["launches"]["comp_forward"]
+            kernel = "k_comp_stage<FORWARD> (X-compressed forward pass: NB null fits + score sweep + selection, all iterations)"
+            note = ("achieved = ALGORITHMIC sweep bytes (12 B/cell per swept gene-iteration + 8 B/cell per forward iteration) / CUDA-event "
+                    "time of the k_comp_stage<FORWARD> launches (rank 0) -- the whole forward stage incl. the NB null fits is charged to the "
+                    "sweep's bytes.  The kernel works on per-abscissa aggregates (k_aggregate), so its DRAM traffic is far below the "
+                    "algorithmic bytes; the streaming per-cell kernel k_sweep_moments (--per-cell) moves them at 97.7 % of peak")
+            traffic = TRAFFIC_PER_LAUNCH_COMP.get(args.config) if (world == 1 and not args.genes) else None
+        else:
+            sweep_ms = prof_acc["ms"]["sweep"]
+            sweep_launches = prof_acc["launches"]["sweep"]
+            kernel = "k_sweep_moments (score sweep streaming kernel, K2a)"
+            note = ("achieved = algorithmic bytes (12 B/cell per swept gene-iteration + 8 B/cell per launch) / CUDA-event time "
+                    "of the k_sweep_moments launches (rank 0); k_sweep_select (K2b, per-gene O(T p^2) algebra) is timed separately")
+            traffic = TRAFFIC_PER_LAUNCH.get(args.config) if (world == 1 and not args.genes) else None
         achieved = (prof_acc["sweep_bytes"] / 1e9) / (sweep_ms / 1000.0) if sweep_ms > 0 else 0.0
-        traffic = TRAFFIC_PER_LAUNCH.get(args.config) if (world == 1 and not args.genes) else None
+        gather_ms = prof_acc["ms"]["gather"] + prof_acc["ms"]["aggregate"]
+        gather_bytes = args.steps * (float(G) * N * (8.0 if not comp else 12.0))   # read 4 B + write 4 B (+ read 4 B in k_aggregate) per cell
         line = {
             "metric": "genes/sec for testDynamic GLM mode", "value": value, "unit": "genes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -320,13 +343,16 @@ def main():
             "gpu_launches": int(launches),
             "wall_ms_per_step": wall_step,
             "stage_ms_per_step": {k: v / args.steps for k, v in prof_acc["ms"].items()},
-            "roofline": {"kernel": "k_sweep_moments (score sweep streaming kernel, K2a)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_kind, "traffic": traffic,
                          "bytes_per_launch": prof_acc["sweep_bytes"] / max(1, sweep_launches),
                          "ms_per_launch": sweep_ms / max(1, sweep_launches),
                          "select_kernel_ms_per_launch": prof_acc["ms"]["select"] / max(1, prof_acc["launches"]["select"]),
-                         "note": "achieved = algorithmic bytes (12 B/cell per swept gene-iteration + 8 B/cell per launch) / CUDA-event time "
-                                 "of the k_sweep_moments launches (rank 0); k_sweep_select (K2b, per-gene O(T p^2) algebra) is timed separately"},
+                         "note": note,
+                         "gather_aggregate": {"kernels": "k_gather_stats + k_aggregate (sort by pseudotime, per-abscissa sums)",
+                                              "achieved": gather_bytes / 1e9 / (gather_ms / 1000.0) if gather_ms > 0 else None,
+                                              "unit": "GB/s", "ms_per_step": gather_ms / args.steps,
+                                              "bytes": "4 B read + 4 B written per cell (gather)" + (" + 4 B read per cell (aggregate)" if comp else "")}},
             "clocks": sampler.result(),
         }
         n_cpu = args.cpu_sample if args.cpu_sample >= 0 else (24 if N <= 20000 else 4)

@@ -262,7 +262,16 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       raw = d_counts + (size_t)b0 * (size_t)n_cells;
     }
     tm.mark(SCLANE_STAGE_GATHER);
-    k_gather_stats<<<nb, kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
+    if (use_comp) {
+      // compressed route: plain permutation copy, K CTAs per gene; k_aggregate derives the per-gene constants
+      int K = (int)((L.N + 8191) / 8192);
+      if (K < 1) K = 1;
+      if (K > 32) K = 32;
+      while (K > 1 && (((L.Npad / K + 127) / 128) * 128) * (K - 1) >= L.Npad) --K;      // no empty trailing part
+      k_gather_copy<<<(unsigned)((size_t)nb * K), kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, nb, K);
+    } else {
+      k_gather_stats<<<nb, kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
+    }
     CK(cudaGetLastError());
     if (h_counts) CK(cudaEventRecord(ev_free[kb & 1], s));
     g_launches.fetch_add(1);
@@ -274,7 +283,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     if (use_comp) {
       CA.lineage = D.lin; CA.pstart = D.pstart; CA.pn = D.pn; CA.pu = D.pu; CA.pb = D.pb; CA.pbstart = D.pbstart; CA.D = P.D; CA.Dpad = Dpad; CA.ys = d_ys;
       CA.s1 = d_s1; CA.q = d_q; CA.tail = d_tail; CA.big = d_big; CA.big_tmp = d_big_tmp; CA.cg = d_cg; CA.stats = d_stats; CA.out = d_out; CA.n_genes = nb; CA.M = o.M;
-      CA.n_iter = n_iter; CA.tols_score = o.tols_score;
+      CA.n_iter = n_iter; CA.tols_score = o.tols_score; CA.compute_stats = 1;
       tm.mark(SCLANE_STAGE_AGGREGATE);
       k_aggregate<<<nb, kThreads, 0, s>>>(CA);
       CK(cudaGetLastError());

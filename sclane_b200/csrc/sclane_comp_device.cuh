@@ -36,9 +36,10 @@ struct CompArgs {
   int* big;                     // [B][kBigCap] counts >= kHistCap of the gene, ascending
   int* big_tmp;                 // [B][kBigCap] unsorted staging
   CompGeneDev* cg;              // [B]
-  const GeneStats* stats;
+  GeneStats* stats;             // written by k_aggregate when compute_stats != 0 (k_gather_copy route)
   GeneOutDev* out;
   int n_genes, M, n_iter;
+  int compute_stats;
   double tols_score;
 };
 
@@ -77,14 +78,15 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
   __shared__ double slot[kWarps][NBMAX][kAggV];
   __shared__ double wtab[64], wztab[64];
   __shared__ int chunk_sum[kThreads];
-  __shared__ int n_big_s;
+  __shared__ int n_big_s, ymax_s;
+  __shared__ double red_s[kWarps][2];
   const int g = blockIdx.x;
   if (g >= A.n_genes) return;
-  if (threadIdx.x == 0) n_big_s = 0;
+  if (threadIdx.x == 0) { n_big_s = 0; ymax_s = 0; }
   int* __restrict__ big_tmp = A.big_tmp + (size_t)g * (size_t)kBigCap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = A.lineage->T, Npad = A.lineage->Npad;
-  const int ymax = A.stats[g].ymax;
+  int my_max = 0;
   const int* __restrict__ y = A.ys + (size_t)g * (size_t)Npad;
   double* __restrict__ s1 = A.s1 + (size_t)g * (size_t)A.Dpad;
   double* __restrict__ q = A.q + (size_t)g * (size_t)A.Dpad;
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
       double a0 = 0.0, b0 = 0.0;
       for (int i = i0; i < i1; ++i) {
         const int yi = y[i];
+        my_max = max(my_max, yi);
         s += yi;
         qq += (long long)yi * yi;
         if (yi < kHistCap) atomicAdd(&hist[yi], 1);
@@ -122,7 +125,11 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
     }
     warp_bucket_add<kAggV>(v, b, valid, myslot, kAggV);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
+  if (lane == 0) atomicMax(&ymax_s, my_max);
   __syncthreads();
+  const int ymax = ymax_s;
   CompGeneDev& cg = A.cg[g];
   for (int idx = threadIdx.x; idx < (T + 1) * kAggV; idx += kThreads) {
     const int b = idx / kAggV, k = idx - b * kAggV;
@@ -151,8 +158,8 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
   }
   __syncthreads();
   const int n_big = n_big_s;
-  if (n_big > kBigCap) return;                            // block-uniform: the gene takes the per-cell kernels
-  {
+  const bool routed = n_big <= kBigCap;                   // block-uniform; otherwise the gene takes the per-cell kernels
+  if (routed) {
     // tail[k] = #{k < y < kHistCap} for k <= hmax, the largest count that goes through the histogram
     const int hmax = ymax < kHistCap ? ymax : kHistCap - 1;
     int* __restrict__ tail = A.tail + (size_t)g * (size_t)kHistCap;
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
       run += hist[k];
     }
   }
-  if (n_big > 0) {
+  if (routed && n_big > 0) {
     // the append order above is arbitrary: rank sort (ties are equal values) makes the list -- and every sum taken
     // over it -- reproducible
     __threadfence_block();
@@ -175,6 +182,65 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
       big[rank] = v;
     }
   }
+  if (!A.compute_stats) return;
+  // per-gene constants (what k_gather_stats provides on the per-cell route) from the histogram and the sorted big list,
+  // plus the initial per-gene state
+  __syncthreads();
+  {
+    const int hmax = ymax < kHistCap ? ymax : kHistCap - 1;
+    double t0 = 0.0, t1 = 0.0;
+    if (routed) {
+      for (int yv = 2 + (int)threadIdx.x; yv <= hmax; yv += kThreads) {
+        const double c = (double)hist[yv], d = (double)yv;
+        if (c != 0.0) { t0 += c * d * log(d); t1 += c * lgamma(d + 1.0); }
+      }
+      if (n_big > 0) {
+        const int* __restrict__ big = A.big + (size_t)g * (size_t)kBigCap;
+        for (int e = threadIdx.x; e < n_big; e += kThreads) { const double d = (double)big[e]; t0 += d * log(d); t1 += lgamma(d + 1.0); }
+      }
+    } else {
+      const int N = A.lineage->N;
+      for (int i = threadIdx.x; i < N; i += kThreads) {
+        const int v = y[i];
+        if (v > 1) { const double d = (double)v; t0 += d * log(d); t1 += lgamma(d + 1.0); }
+      }
+    }
+    t0 = warp_sum(t0); t1 = warp_sum(t1);
+    if (lane == 0) { red_s[warp][0] = t0; red_s[warp][1] = t1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      GeneStats gs;
+      gs.sum_y = 0.0; gs.sum_y2 = 0.0; gs.sum_ylogy = 0.0; gs.sum_lgamma_y1 = 0.0;
+      for (int b = 0; b <= T; ++b) { gs.sum_y += cg.hdr.SB[b]; gs.sum_y2 += cg.hdr.QB[b]; }
+      for (int w = 0; w < kWarps; ++w) { gs.sum_ylogy += red_s[w][0]; gs.sum_lgamma_y1 += red_s[w][1]; }
+      gs.ymax = ymax; gs.pad = 0;
+      A.stats[g] = gs;
+      GeneState st;
+      int* z = reinterpret_cast<int*>(&st);
+      for (int i = 0; i < (int)(sizeof(GeneState) / sizeof(int)); ++i) z[i] = 0;
+      st.fwd.n = 1;
+      st.fwd.kind[0] = SCLANE_TERM_INTERCEPT;
+      st.m_count = 1;
+      if (gs.sum_y == 0.0) st.error |= SCLANE_NOTE_ALL_ZERO;
+      A.out[g].st = st;
+      A.out[g].alt.ok = 0;
+      A.out[g].null.ok = 0;
+    }
+  }
+}
+
+// Pure permutation copy (the compressed route's replacement of k_gather_stats): K CTAs per gene, so that the rows being
+// gathered at any moment fit in L2 and the 4-byte random reads of a row are served from there instead of costing a
+// 32-byte DRAM sector each.
+__global__ void __launch_bounds__(kThreads) k_gather_copy(const int* __restrict__ raw, long long ld, const int* __restrict__ perm, int N,
+                                                          int Npad, int* __restrict__ ys, int n_genes, int K) {
+  const int g = blockIdx.x / K, part = blockIdx.x - g * K;
+  if (g >= n_genes) return;
+  const int chunk = ((Npad / K + 127) / 128) * 128;
+  const int i0 = part * chunk, i1 = min(Npad, i0 + chunk);
+  const int* src = raw + (size_t)g * (size_t)ld;
+  int* dst = ys + (size_t)g * (size_t)Npad;
+  for (int i = i0 + threadIdx.x; i < i1; i += kThreads) dst[i] = i < N ? __ldg(src + __ldg(perm + i)) : 0;
 }
 
 template <int MODE> struct CompTraits;
