@@ -42,6 +42,35 @@ SEXP C_sclane_test_dynamic(SEXP counts, SEXP pt, SEXP sf, SEXP opts_) {
   return out;
 }
 
+/* GEE mode (testDynamic(is.gee = TRUE), testDynamic.R:66-70,235-244,296-301).
+ * ids:   integer vector, one subject id per cell (as.integer(factor(id.vec))); cells ordered by subject (testDynamic.R:115)
+ * opts:  integer vector c(M, approx_knot, n_gpus, cor_structure [0 independence, 1 exchangeable, 2 ar1], gee_test [0 wald, 1 score]) */
+SEXP C_sclane_test_dynamic_gee(SEXP counts, SEXP pt, SEXP ids, SEXP sf, SEXP opts_) {
+  if (!isInteger(counts) || !isMatrix(counts)) Rf_error("expr.mat must be an integer matrix (cells x genes)");
+  if (!isReal(pt) || !isMatrix(pt)) Rf_error("pt must be a double matrix (cells x lineages)");
+  const int64_t n_cells = nrows(counts), n_genes = ncols(counts);
+  const int n_lin = ncols(pt);
+  if (nrows(pt) != n_cells) Rf_error("pt must have one row per cell");
+  if (!isInteger(ids) || XLENGTH(ids) != n_cells) Rf_error("id.vec must be an integer vector with one entry per cell");
+  if (sf != R_NilValue && (!isReal(sf) || XLENGTH(sf) != n_cells)) Rf_error("size.factor.offset must have one entry per cell");
+  sclane_opts o;
+  sclane_default_opts(&o);
+  o.mode = 1;
+  if (LENGTH(opts_) >= 5) { o.M = INTEGER(opts_)[0]; o.approx_knot = INTEGER(opts_)[1]; o.n_gpus = INTEGER(opts_)[2];
+                            o.gee_cor = INTEGER(opts_)[3]; o.gee_test = INTEGER(opts_)[4];
+                            for (int i = 0; i < o.n_gpus && i < SCLANE_MAX_GPUS; ++i) o.gpu_ids[i] = i; }
+  SEXP out = PROTECT(allocVector(RAWSXP, (R_xlen_t)(n_genes * n_lin) * (R_xlen_t)sizeof(sclane_record)));
+  SEXP info = PROTECT(allocVector(RAWSXP, (R_xlen_t)n_lin * (R_xlen_t)sizeof(sclane_lineage_info)));
+  char err[1024]; err[0] = 0;
+  const int rc = sclane_test_dynamic_gee(INTEGER(counts), n_cells, n_genes, REAL(pt), n_lin, INTEGER(ids),
+                                         sf == R_NilValue ? NULL : REAL(sf), &o,
+                                         (sclane_record*)RAW(out), (sclane_lineage_info*)RAW(info), err, sizeof(err));
+  if (rc != SCLANE_OK) { UNPROTECT(2); Rf_error("sclane_b200: %s", err); }
+  setAttrib(out, install("lineage_info"), info);
+  UNPROTECT(2);
+  return out;
+}
+
 /* Drop-ins with the signatures of the reference's Rcpp exports (R/RcppExports.R:4-14). */
 SEXP C_eigenMapMatMult(SEXP A, SEXP B, SEXP n_cores) {
   const int m = nrows(A), k = ncols(A), n = ncols(B);
@@ -71,6 +100,7 @@ SEXP C_eigenMapPseudoInverse(SEXP A, SEXP tol, SEXP n_cores) {
 
 static const R_CallMethodDef CallEntries[] = {
   {"C_sclane_test_dynamic", (DL_FUNC)&C_sclane_test_dynamic, 4},
+  {"C_sclane_test_dynamic_gee", (DL_FUNC)&C_sclane_test_dynamic_gee, 5},
   {"C_eigenMapMatMult", (DL_FUNC)&C_eigenMapMatMult, 3},
   {"C_eigenMapMatrixInvert", (DL_FUNC)&C_eigenMapMatrixInvert, 2},
   {"C_eigenMapPseudoInverse", (DL_FUNC)&C_eigenMapPseudoInverse, 3},

@@ -5,13 +5,24 @@
 # Everything before (input coercion, :76-121) and after (class, message, :386-447) stays as in the reference, so the
 # signature of testDynamic() is unchanged; `n.cores` is kept for compatibility and a new `n.gpus` picks the devices.
 
-testDynamicB200 <- function(expr.mat, pt, genes, size.factor.offset = NULL, n.potential.basis.fns = 5,
+testDynamicB200 <- function(expr.mat, pt, genes, size.factor.offset = NULL, is.gee = FALSE, id.vec = NULL,
+                            cor.structure = "ar1", gee.test = "wald", n.potential.basis.fns = 5,
                             approx.knot = TRUE, n.gpus = 0L) {
   # expr.mat: dense cells x genes integer matrix exactly as built at testDynamic.R:97
   storage.mode(expr.mat) <- "integer"
   pt_mat <- as.matrix(pt); storage.mode(pt_mat) <- "double"
-  raw <- .Call("C_sclane_test_dynamic", expr.mat, pt_mat, size.factor.offset,
-               c(as.integer(n.potential.basis.fns), as.integer(approx.knot), as.integer(n.gpus)))
+  if (is.gee) {
+    # testDynamic.R:107-118 has already checked that the cells are ordered by subject
+    cor_code <- match(tolower(cor.structure), c("independence", "exchangeable", "ar1")) - 1L
+    if (is.na(cor_code)) stop("GEE models require a specified correlation structure.")
+    raw <- .Call("C_sclane_test_dynamic_gee", expr.mat, pt_mat, as.integer(factor(id.vec, levels = unique(id.vec))),
+                 size.factor.offset,
+                 c(as.integer(n.potential.basis.fns), as.integer(approx.knot), as.integer(n.gpus), cor_code,
+                   as.integer(tolower(gee.test) == "score")))
+  } else {
+    raw <- .Call("C_sclane_test_dynamic", expr.mat, pt_mat, size.factor.offset,
+                 c(as.integer(n.potential.basis.fns), as.integer(approx.knot), as.integer(n.gpus)))
+  }
   recs <- sclane_unpack_records(raw, n_genes = ncol(expr.mat), n_lineages = ncol(pt_mat))   # readBin() over the struct layout
   n_lineages <- ncol(pt_mat)
   test_stats <- lapply(seq_along(genes), function(i) {
@@ -24,7 +35,8 @@ testDynamicB200 <- function(expr.mat, pt, genes, size.factor.offset = NULL, n.po
         if (r$term_kind[k] == 1L) paste0("h_Lineage_", lin, "_", lab) else paste0("h_", lab, "_Lineage_", lin)
       }, character(1))) else character(0)
       list(Gene = genes[i], Lineage = lin,
-           Test_Stat = r$test_stat, Test_Stat_Type = "LRT",
+           Test_Stat = r$test_stat,
+           Test_Stat_Type = if (is.gee) ifelse(tolower(gee.test) == "score", "Score", "Wald") else "LRT",   # testDynamic.R:324
            Test_Stat_Note = if (marge_ok && null_ok) NA_character_ else "No test performed due to model failure.",
            Degrees_Freedom = r$df, P_Val = r$p_val,
            LogLik_MARGE = r$loglik, LogLik_Null = r$null_loglik, Dev_MARGE = r$deviance, Dev_Null = r$null_deviance,

@@ -290,7 +290,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_AGGREGATE]++;
       tm.mark(SCLANE_STAGE_COMP_FWD);
-      k_comp_stage<CSTAGE_FORWARD><<<nb, kThreads, 0, s>>>(CA);
+      k_comp_stage<CSTAGE_FORWARD><<<nb, kCompThreads, 0, s>>>(CA);
       CK(cudaGetLastError());
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_COMP_FWD]++;
@@ -305,7 +305,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     }
     if (use_comp) {
       tm.mark(SCLANE_STAGE_COMP_BWD);
-      k_comp_stage<CSTAGE_BACKWARD><<<nb, kThreads, 0, s>>>(CA);
+      k_comp_stage<CSTAGE_BACKWARD><<<nb, kCompThreads, 0, s>>>(CA);
       CK(cudaGetLastError());
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_COMP_BWD]++;
@@ -315,7 +315,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.launches[SCLANE_STAGE_BACKWARD]++;
     if (use_comp && !use_offset) {
       tm.mark(SCLANE_STAGE_COMP_FINAL);
-      k_comp_stage<CSTAGE_FINAL><<<nb, kThreads, 0, s>>>(CA);
+      k_comp_stage<CSTAGE_FINAL><<<nb, kCompThreads, 0, s>>>(CA);
       CK(cudaGetLastError());
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_COMP_FINAL]++;

@@ -43,6 +43,16 @@ struct CompArgs {
   double tols_score;
 };
 
+#ifndef SCLANE_COMP_WARPS
+#define SCLANE_COMP_WARPS 8
+#endif
+#ifndef SCLANE_COMP_MINB
+#define SCLANE_COMP_MINB 3
+#endif
+// CTA shape of k_comp_stage.  Measured on B200 (C5 / C2 ms per step): 8 warps x 3 CTAs/SM 144.4 / 12.7, 4 x 6 150.0 / 13.6,
+// 4 x 4 154.8 / 14.1, 8 x 2 167.8 / 13.7, 2 x 12 178.6 / 17.6 -- the passes are throughput bound, not leader-latency bound.
+constexpr int kCompWarps = SCLANE_COMP_WARPS;
+constexpr int kCompThreads = kCompWarps * 32;
 constexpr int kAggV = 9;        // per-bucket totals gathered by k_aggregate
 
 // add NV per-lane values into slot[b] (warp-private), lanes of a 32-point group usually share the bucket
@@ -271,7 +281,7 @@ struct CompDevExec {
   __device__ __forceinline__ PassTabs* tabs() const { return nullptr; }
   template <class F>
   __device__ __forceinline__ void par_for(int n, F f) const {
-    for (int i = threadIdx.x; i < n; i += kThreads) f(i);
+    for (int i = threadIdx.x; i < n; i += kCompThreads) f(i);
   }
 
   // One pass.  Work unit = one knot bucket, owned by one warp: a bucket with a flat linear predictor is a single closed-form
@@ -290,7 +300,7 @@ struct CompDevExec {
     const bool want_ll = W->want_ll != 0;
     __syncthreads();
     if (MODE == PASS_IRLS_START) {
-      for (int idx = threadIdx.x; idx < (T + 1) * 5; idx += kThreads) { const int b = idx / 5, k = idx - b * 5; W->acc[b][k] = cg->ST[b][k]; }
+      for (int idx = threadIdx.x; idx < (T + 1) * 5; idx += kCompThreads) { const int b = idx / 5, k = idx - b * 5; W->acc[b][k] = cg->ST[b][k]; }
       if (threadIdx.x == 0) {
         W->sc[0] = -gs->sum_ylogy + (double)cg->hdr.n_zero * theta * log1p(sigma / 6.0);
         W->sc[1] = (double)cg->hdr.n_zero;
@@ -319,7 +329,7 @@ struct CompDevExec {
     for (int b = 0; b <= T; ++b) {
       const double c = W->c[b];
       if (c == 0.0) {
-        if ((b & (kWarps - 1)) != warp) continue;
+        if ((b & (kCompWarps - 1)) != warp) continue;
         double fa[NACC];
 #pragma unroll
         for (int k = 0; k < NACC; ++k) fa[k] = 0.0;
@@ -331,7 +341,7 @@ struct CompDevExec {
         }
         continue;
       }
-      const int owner = n_sloped & (kWarps - 1);
+      const int owner = n_sloped & (kCompWarps - 1);
       ++n_sloped;
       if (owner != warp) continue;
       const double a = W->a[b];
@@ -351,10 +361,10 @@ struct CompDevExec {
     // the mu-free histogram terms
     if (NS > 0 && MODE != PASS_SWEEP) {
       const int hmax = cg->hdr.ymax < kHistCap ? cg->hdr.ymax : kHistCap - 1;
-      for (int k = threadIdx.x; k < hmax; k += kThreads)
+      for (int k = threadIdx.x; k < hmax; k += kCompThreads)
         hist_contrib<MODE>(k, (double)tail[k], (double)tail[k + 1], sigma, theta, want_ll, sc);
       const int n_big = cg->hdr.n_big;
-      for (int e = threadIdx.x; e < n_big; e += kThreads) big_contrib<MODE>(big[e], sigma, theta, want_ll, sc);
+      for (int e = threadIdx.x; e < n_big; e += kCompThreads) big_contrib<MODE>(big[e], sigma, theta, want_ll, sc);
     }
     if (NS > 0) {
 #pragma unroll
@@ -364,12 +374,12 @@ struct CompDevExec {
       }
     }
     if (MODE == PASS_SWEEP)
-      for (int b = threadIdx.x; b <= T; b += kThreads) { W->acc[b][5] = cg->hdr.SB[b]; W->acc[b][6] = cg->hdr.SBu[b]; }
+      for (int b = threadIdx.x; b <= T; b += kCompThreads) { W->acc[b][5] = cg->hdr.SB[b]; W->acc[b][6] = cg->hdr.SBu[b]; }
     __syncthreads();
     if (NS > 0 && threadIdx.x < NS) {
       double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) s += scw[w][threadIdx.x];
+      for (int w = 0; w < kCompWarps; ++w) s += scw[w][threadIdx.x];
       W->sc[threadIdx.x] = s;
     }
     __syncthreads();
@@ -379,33 +389,33 @@ struct CompDevExec {
 enum CompStage : int { CSTAGE_FORWARD = 0, CSTAGE_BACKWARD = 1, CSTAGE_FINAL = 2 };
 
 template <int STAGE>
-__global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_comp_stage(CompArgs A) {
+__global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(CompArgs A) {
   __shared__ Work W;
   __shared__ Lineage Ls;
   __shared__ GeneState st;
   __shared__ GeneStats gs;
   __shared__ CompGeneDev cg;
   __shared__ int pbs[NBMAX + 1];
-  __shared__ double scw[kWarps][NSC];
+  __shared__ double scw[kCompWarps][NSC];
   const int g = blockIdx.x;
   if (g >= A.n_genes) return;
   if (A.cg[g].hdr.route == 0) return;                     // block-uniform: this gene takes the per-cell kernels
   {
     const int* src = reinterpret_cast<const int*>(A.lineage);
     int* dst = reinterpret_cast<int*>(&Ls);
-    for (int i = threadIdx.x; i < (int)(sizeof(Lineage) / sizeof(int)); i += kThreads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(Lineage) / sizeof(int)); i += kCompThreads) dst[i] = src[i];
     const int* s2 = reinterpret_cast<const int*>(&A.out[g].st);
     int* d2 = reinterpret_cast<int*>(&st);
-    for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kThreads) d2[i] = s2[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kCompThreads) d2[i] = s2[i];
     const int* s3 = reinterpret_cast<const int*>(&A.stats[g]);
     int* d3 = reinterpret_cast<int*>(&gs);
-    for (int i = threadIdx.x; i < (int)(sizeof(GeneStats) / sizeof(int)); i += kThreads) d3[i] = s3[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(GeneStats) / sizeof(int)); i += kCompThreads) d3[i] = s3[i];
     const int* s4 = reinterpret_cast<const int*>(&A.cg[g]);
     int* d4 = reinterpret_cast<int*>(&cg);
-    for (int i = threadIdx.x; i < (int)(sizeof(CompGeneDev) / sizeof(int)); i += kThreads) d4[i] = s4[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(CompGeneDev) / sizeof(int)); i += kCompThreads) d4[i] = s4[i];
     int* w = reinterpret_cast<int*>(&W);
-    for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kThreads) w[i] = 0;
-    if (threadIdx.x <= NBMAX) pbs[threadIdx.x] = A.pbstart[threadIdx.x];
+    for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kCompThreads) w[i] = 0;
+    for (int i = threadIdx.x; i <= NBMAX; i += kCompThreads) pbs[i] = A.pbstart[i];
   }
   __syncthreads();
   CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, pbs, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
@@ -432,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_comp_stage(Comp
   {
     int* d2 = reinterpret_cast<int*>(&A.out[g].st);
     const int* s2 = reinterpret_cast<const int*>(&st);
-    for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kThreads) d2[i] = s2[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kCompThreads) d2[i] = s2[i];
   }
 }
 
