@@ -52,6 +52,7 @@ extern "C" {
 #define SCLANE_NOTE_FWD_EMPTY 16        /* forward pass added < 2 columns -> marge2 subscript error (marge2.R:777) */
 #define SCLANE_NOTE_ALL_ZERO 32         /* all counts zero in this lineage                         */
 #define SCLANE_NOTE_NUMERIC 64          /* non-finite intermediate (R: "missing value where TRUE/FALSE needed") */
+#define SCLANE_NOTE_BAD_COUNTS 128      /* a negative count in this lineage: both models fail (glm.nb: "negative values not allowed") */
 
 /* sclane_opts.gee_cor: working correlation of the GEE mode (stat_out_score_gee_null.R:51-60) */
 #define SCLANE_COR_INDEPENDENCE 0

@@ -18,6 +18,7 @@ NOTE_NOT_CONVERGED = 8
 NOTE_FWD_EMPTY = 16
 NOTE_ALL_ZERO = 32
 NOTE_NUMERIC = 64
+NOTE_BAD_COUNTS = 128
 
 TERM_INTERCEPT, TERM_TP1, TERM_TP2 = 0, 1, 2
 

@@ -321,6 +321,8 @@ def _notes(bits: int, ok: bool) -> str | None:
         msgs.append("Error in wic_mat_2[...] : subscript out of bounds (forward pass added fewer than two basis functions)")
     if bits & _abi.NOTE_ALL_ZERO:
         msgs.append("all counts are zero")
+    if bits & _abi.NOTE_BAD_COUNTS:
+        msgs.append("negative values not allowed for the 'Negative Binomial' family")
     if bits & _abi.NOTE_NUMERIC:
         msgs.append("missing value where TRUE/FALSE needed")
     return "; ".join(msgs) if msgs else "model fit failed"

@@ -88,11 +88,11 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
   __shared__ double slot[kWarps][NBMAX][kAggV];
   __shared__ double wtab[64], wztab[64];
   __shared__ int chunk_sum[kThreads];
-  __shared__ int n_big_s, ymax_s;
+  __shared__ int n_big_s, ymax_s, neg_s;
   __shared__ double red_s[kWarps][2];
   const int g = blockIdx.x;
   if (g >= A.n_genes) return;
-  if (threadIdx.x == 0) { n_big_s = 0; ymax_s = 0; }
+  if (threadIdx.x == 0) { n_big_s = 0; ymax_s = 0; neg_s = 0; }
   int* __restrict__ big_tmp = A.big_tmp + (size_t)g * (size_t)kBigCap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = A.lineage->T, Npad = A.lineage->Npad;
@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
       long long s = 0, qq = 0;
       double a0 = 0.0, b0 = 0.0;
       for (int i = i0; i < i1; ++i) {
-        const int yi = y[i];
+        int yi = y[i];
+        if (yi < 0) { yi = 0; neg_s = 1; }               // negative count: the gene fails (SCLANE_NOTE_BAD_COUNTS), summed as 0
         my_max = max(my_max, yi);
         s += yi;
         qq += (long long)yi * yi;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
       gs.sum_y = 0.0; gs.sum_y2 = 0.0; gs.sum_ylogy = 0.0; gs.sum_lgamma_y1 = 0.0;
       for (int b = 0; b <= T; ++b) { gs.sum_y += cg.hdr.SB[b]; gs.sum_y2 += cg.hdr.QB[b]; }
       for (int w = 0; w < kWarps; ++w) { gs.sum_ylogy += red_s[w][0]; gs.sum_lgamma_y1 += red_s[w][1]; }
-      gs.ymax = ymax; gs.pad = 0;
+      gs.ymax = ymax; gs.pad = neg_s;
       A.stats[g] = gs;
       GeneState st;
       int* z = reinterpret_cast<int*>(&st);
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
       st.fwd.kind[0] = SCLANE_TERM_INTERCEPT;
       st.m_count = 1;
       if (gs.sum_y == 0.0) st.error |= SCLANE_NOTE_ALL_ZERO;
+      if (neg_s) st.error |= SCLANE_NOTE_BAD_COUNTS;
       A.out[g].st = st;
       A.out[g].alt.ok = 0;
       A.out[g].null.ok = 0;

@@ -1354,7 +1354,7 @@ SC_HDN void gene_final(E& ex, const Lineage& L, const GeneStats& gstat, GeneStat
   ex.sync();
   if (ex.leader()) { alt->ok = 0; null->ok = 0; alt->notes = 0; null->notes = 0; }
   ex.sync();
-  if (st.error & SCLANE_NOTE_ALL_ZERO) return;
+  if (st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS)) return;
   if (ex.leader()) { W.bw_cur.n = 1; W.bw_cur.kind[0] = SCLANE_TERM_INTERCEPT; W.bw_cur.knot[0] = 0; }
   ex.sync();
   glm_nb(ex, L, W.bw_cur, gstat, W, use_offset, null);

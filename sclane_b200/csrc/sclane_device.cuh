@@ -618,6 +618,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_stats(const int* __restrict
   for (int i = threadIdx.x; i < Npad; i += kThreads) {
     int v = 0;
     if (i < N) v = __ldg(src + __ldg(perm + i));
+    if (v < 0) { v = 0; ymax = 0x7fffffff; }          // negative count: flagged through ymax, stored as 0
     dst[i] = v;
     if (v > 0) {
       const double d = (double)v;
@@ -642,6 +643,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_stats(const int* __restrict
       gs.sum_y += red[w][0]; gs.sum_y2 += red[w][1]; gs.sum_ylogy += red[w][2]; gs.sum_lgamma_y1 += red[w][3];
       gs.ymax = max(gs.ymax, redm[w]);
     }
+    if (gs.ymax == 0x7fffffff) { gs.pad = 1; gs.ymax = 0; }   // pad = 1: the gene has a negative count (SCLANE_NOTE_BAD_COUNTS)
     stats[g] = gs;
     if (!out) return;                       // GEE mode initialises its own per-gene state (k_gee)
     GeneState st;
@@ -651,6 +653,7 @@ __global__ void __launch_bounds__(kThreads) k_gather_stats(const int* __restrict
     st.fwd.kind[0] = SCLANE_TERM_INTERCEPT;
     st.m_count = 1;
     if (gs.sum_y == 0.0) st.error |= SCLANE_NOTE_ALL_ZERO;
+    if (gs.pad) st.error |= SCLANE_NOTE_BAD_COUNTS;
     out[g].st = st;
     out[g].alt.ok = 0;
     out[g].null.ok = 0;

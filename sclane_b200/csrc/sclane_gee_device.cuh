@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gee(GeeArgs A) {
     S->st.fwd.kind[0] = SCLANE_TERM_INTERCEPT;
     S->st.m_count = 1;
     if (S->gs.sum_y == 0.0) S->st.error |= SCLANE_NOTE_ALL_ZERO;
+    if (S->gs.pad) S->st.error |= SCLANE_NOTE_BAD_COUNTS;
     S->G.cor = A.cor;
   }
   __syncthreads();

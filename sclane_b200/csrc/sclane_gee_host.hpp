@@ -65,11 +65,11 @@ inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_t
   dummy.st.fin.n = 0;
   finalize_record(dummy, L, r);                 // trace fields + NaN defaults
   const GeneState& st = g.st;
-  const bool marge_ok = (st.fin.n >= 1) && g.alt.ok && !(st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC | SCLANE_NOTE_ALL_ZERO));
-  const bool null_ok = g.null.ok && !(st.error & SCLANE_NOTE_ALL_ZERO);
+  const bool marge_ok = (st.fin.n >= 1) && g.alt.ok && !(st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC | SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
+  const bool null_ok = g.null.ok && !(st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
   r.status = (marge_ok ? SCLANE_MARGE_OK : 0) | (null_ok ? SCLANE_NULL_OK : 0);
   r.marge_notes = st.error | ((marge_ok && !g.alt.converged) ? SCLANE_NOTE_NOT_CONVERGED : 0);
-  r.null_notes = null_ok ? (g.null.converged ? 0 : SCLANE_NOTE_NOT_CONVERGED) : (st.error & SCLANE_NOTE_ALL_ZERO);
+  r.null_notes = null_ok ? (g.null.converged ? 0 : SCLANE_NOTE_NOT_CONVERGED) : (st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
   if (marge_ok) {
     const int p = st.fin.n;
     r.n_terms = p;

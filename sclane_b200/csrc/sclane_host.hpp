@@ -256,11 +256,11 @@ inline void finalize_record(const GeneOut& g, const Lineage& L, sclane_record& r
   const double NaN = std::numeric_limits<double>::quiet_NaN();
   std::memset(&r, 0, sizeof(r));
   const GeneState& st = g.st;
-  const bool marge_ok = (st.fin.n >= 1) && g.alt.ok && !(st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC | SCLANE_NOTE_ALL_ZERO));
-  const bool null_ok = g.null.ok && !(st.error & SCLANE_NOTE_ALL_ZERO);
+  const bool marge_ok = (st.fin.n >= 1) && g.alt.ok && !(st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC | SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
+  const bool null_ok = g.null.ok && !(st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
   r.status = (marge_ok ? SCLANE_MARGE_OK : 0) | (null_ok ? SCLANE_NULL_OK : 0);
   r.marge_notes = st.error | (marge_ok ? g.alt.notes : 0);
-  r.null_notes = null_ok ? g.null.notes : (st.error & SCLANE_NOTE_ALL_ZERO);
+  r.null_notes = null_ok ? g.null.notes : (st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
   for (int j = 0; j < SCLANE_PMAX; ++j) {
     r.term_kind[j] = 0; r.term_knot_idx[j] = -1;
     r.term_knot[j] = r.term_label[j] = r.coef[j] = r.se[j] = r.z[j] = r.p[j] = NaN;

@@ -285,3 +285,25 @@ def test_compressed_path_vs_per_cell_path():
                     assert rel(x.coef[j], y.coef[j], 1e-6) < 1e-6 and rel(x.se[j], y.se[j], 1e-6) < 1e-6, i
                 assert rel(x.theta, y.theta) < 1e-6 and rel(x.loglik, y.loglik) < 1e-9, i
                 assert abs(x.test_stat - y.test_stat) < 1e-6 * (abs(y.test_stat) + 1e-3), i
+
+
+def test_negative_counts_fail_the_gene_only():
+    """A negative count makes both models of that gene fail (glm.nb: 'negative values not allowed'), on every route, and
+    leaves the other genes untouched."""
+    import sclane_b200 as sb
+    from sclane_b200 import _abi, synth
+    counts, pt, _ = synth.make_counts(12, 3000, seed=4)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    ref = sb.testDynamic(counts, pt, n_gpus=1, preds="none")
+    bad = counts.copy()
+    bad[3, 77] = -2
+    subject = np.arange(3000) * 3 // 3000
+    for kw in ({}, {"force_per_cell": True}, {"is_gee": True, "id_vec": subject}):
+        res = sb.testDynamic(bad, pt, n_gpus=1, preds="none", **kw)
+        r = res.records[3]
+        assert r.status == 0 and (r.marge_notes & _abi.NOTE_BAD_COUNTS) and (r.null_notes & _abi.NOTE_BAD_COUNTS)
+        assert res.records[4].status == 3
+    res = sb.testDynamic(bad, pt, n_gpus=1, preds="none")
+    for i in range(12):
+        if i != 3:
+            assert _rec_bytes(res.records[i]) == _rec_bytes(ref.records[i])
