@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sclane_b200 as sb
 from sclane_b200 import synth
 n = sb.device_count()
-counts, pt, _ = synth.make_counts(301, 5000, seed=5)
+counts, pt, _ = synth.make_counts(301, 20000, seed=5)      # D = 10,000 abscissae: the X-compressed route
 a = sb.testDynamic(counts, pt, n_gpus=1, preds="none")
 b = sb.testDynamic(counts, pt, n_gpus=n, preds="none")
 off = sb._abi.SclaneRecord.gene_time.offset
