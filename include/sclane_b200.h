@@ -282,6 +282,17 @@ int32_t sclane_link_preds(const sclane_record* rec, const double* x, int64_t n,
                           double* null_link_fit, double* null_link_se,
                           char* errbuf, size_t errlen);
 
+/* smoothedCountsMatrix() (smoothedCountsMatrix.R:27-74) for one lineage, all genes in one launch: the fitted mean of every
+ * cell under every gene's final model, exp(marge_link_fit) (* size_factor when one is given, :57-61), optionally log1p
+ * (:65-67).  recs: the n_genes x n_lineages records of sclane_test_dynamic*(); lineage: which one; x / size_factor: the
+ * lineage's n cells (pseudotime unrounded, rounded internally).  is_gee: the link fit of a GEE record has no offset
+ * (predict.geem).  out: n x n_genes column-major (gene g's cells at out[g*n ..)); genes whose model failed get NaN (the
+ * reference drops them from the matrix, :50-52).  HOST pointers. */
+int32_t sclane_smoothed_counts(const sclane_record* recs, int64_t n_genes, int32_t n_lineages, int32_t lineage,
+                               const double* x, int64_t n, const double* size_factor,
+                               int32_t is_gee, int32_t log1p_norm, int32_t device,
+                               double* out, char* errbuf, size_t errlen);
+
 /* ---------------------------------------------------------------------------------------
  * Drop-ins for the reference's three RcppEigen helpers (column-major doubles, HOST pointers).
  * ------------------------------------------------------------------------------------- */

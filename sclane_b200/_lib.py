@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
     L.sclane_score_glm.restype = i32
     L.sclane_link_preds.argtypes = [p, p, i64, p, i32, p, p, p, p, *err]
     L.sclane_link_preds.restype = i32
+    L.sclane_smoothed_counts.argtypes = [p, i64, i32, i32, p, i64, p, i32, i32, i32, p, *err]
+    L.sclane_smoothed_counts.restype = i32
     L.sclane_matmul.argtypes = [p, p, p, i64, i64, i64, i32, *err]
     L.sclane_matmul.restype = i32
     L.sclane_llt_inverse.argtypes = [p, p, i64, i32, *err]

@@ -515,6 +515,8 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
                          "pt_min": i.pt_min, "pt_max": i.pt_max} for i in infos]
     res.profile = get_profile()
     res.records = recs
+    res.is_gee = bool(is_gee)
+    res.genes = genes
     if verbose:
         dt = time.time() - t0
         print(f"scLANE testing in {'GEE' if is_gee else 'GLM'} mode completed for {n_genes} genes across {n_lin} "
@@ -579,6 +581,92 @@ def modelLRT(mod_1=None, mod_0=None, is_glmm: bool = False) -> dict:
         df = 1
     return {"Alt_Mod_LL": ll1, "Null_Mod_LL": ll0, "LRT_Stat": lrt, "DF": df, "P_Val": float(chi2.sf(lrt, df)),
             "Model_Type": "GLM", "Notes": None}
+
+
+def smoothedCountsMatrix(test_dyn_res=None, size_factor_offset=None, pt=None, genes=None, log1p_norm: bool = False,
+                         n_cores: int = 2, device: int = 0) -> dict:
+    """smoothedCountsMatrix.R:27-74: per lineage a cells x genes matrix of fitted means exp(marge_link_fit) (times the size
+    factor when one is given), for every gene whose MARGE model fitted; one kernel launch per lineage
+    (sclane_smoothed_counts).  Returns {"Lineage_A": {"matrix": ndarray [cells of the lineage, genes kept], "genes": [...]}}.
+    `n_cores` is kept for signature compatibility."""
+    if test_dyn_res is None or pt is None:
+        raise ValueError("Please provide the scLANE output from testDynamic().")
+    pt_arr = np.asarray(pt, dtype=np.float64)
+    if pt_arr.ndim == 1:
+        pt_arr = pt_arr[:, None]
+    all_genes = list(test_dyn_res.keys())
+    genes = all_genes if genes is None else [str(g) for g in genes]
+    n_lin = pt_arr.shape[1]
+    recs = (_abi.SclaneRecord * (len(genes) * n_lin))()
+    for gi, g in enumerate(genes):
+        for l in range(n_lin):
+            recs[gi * n_lin + l] = test_dyn_res[g][f"Lineage_{LETTERS[l]}"]["record"]
+    sf_all = None if size_factor_offset is None else np.asarray(size_factor_offset, dtype=np.float64)
+    is_gee = bool(getattr(test_dyn_res, "is_gee", False))
+    out = {}
+    err = C.create_string_buffer(_ERRLEN)
+    for l in range(n_lin):
+        cells = np.flatnonzero(~np.isnan(pt_arr[:, l]))
+        x = np.ascontiguousarray(pt_arr[cells, l])
+        sfl = None if sf_all is None else np.ascontiguousarray(sf_all[cells])
+        mat = np.empty((len(genes), x.size), dtype=np.float64)            # gene-major == column-major cells x genes
+        rc = lib().sclane_smoothed_counts(recs, len(genes), n_lin, l, x.ctypes.data, x.size, None if sfl is None else sfl.ctypes.data,
+                                          1 if is_gee else 0, 1 if log1p_norm else 0, device, mat.ctypes.data, err, _ERRLEN)
+        check(rc, err)
+        keep = [gi for gi in range(len(genes)) if recs[gi * n_lin + l].status & _abi.SCLANE_MARGE_OK]
+        out[f"Lineage_{LETTERS[l]}"] = {"matrix": np.ascontiguousarray(mat[keep].T), "genes": [genes[gi] for gi in keep]}
+    return out
+
+
+def getFittedValues(test_dyn_res=None, genes=None, pt=None, expr_mat=None, size_factor_offset=None, log1p_norm: bool = False,
+                    cell_meta_data=None, id_vec=None, ci_alpha: float = 0.05, filter_lineage=None, device: int = 0):
+    """getFittedValues.R:45-150: long table (one row per cell, lineage and gene) of counts, link-scale fit / SE / CI and the
+    response-scale fit / CI (multiplied by the size factor in GLM mode, :112-115).  expr_mat: genes x cells counts."""
+    import pandas as pd
+    from scipy.stats import norm
+    if test_dyn_res is None or genes is None or pt is None or expr_mat is None:
+        raise ValueError("You forgot one or more of the arguments to getFittedValues().")
+    pt_arr = np.asarray(pt, dtype=np.float64)
+    if pt_arr.ndim == 1:
+        pt_arr = pt_arr[:, None]
+    counts = np.asarray(expr_mat)
+    all_genes = list(test_dyn_res.keys())
+    z = float(norm.isf(ci_alpha / 2.0))
+    is_gee = bool(getattr(test_dyn_res, "is_gee", False))
+    sf_all = None if size_factor_offset is None else np.asarray(size_factor_offset, dtype=np.float64)
+    frames = []
+    for l in range(pt_arr.shape[1]):
+        letter = LETTERS[l]
+        if filter_lineage is not None and letter in filter_lineage:
+            continue
+        cells = np.flatnonzero(~np.isnan(pt_arr[:, l]))
+        for g in [str(v) for v in genes]:
+            rec = test_dyn_res[g][f"Lineage_{letter}"]
+            df = {"cell": cells, "lineage": letter, "pt": pt_arr[cells, l], "gene": g,
+                  "rna": counts[all_genes.index(g), cells].astype(np.float64)}
+            if id_vec is not None:
+                df["subj_id"] = np.asarray(id_vec)[cells]
+            if sf_all is not None:
+                df["size_factor"] = sf_all[cells]
+                df["model_offset"] = np.log(1.0 / sf_all[cells])
+            preds = rec["MARGE_Preds"]
+            if preds is None:
+                fit = se = np.full(cells.size, np.nan)
+            else:
+                fit, se = np.asarray(preds["marge_link_fit"]), np.asarray(preds["marge_link_se"])
+            df.update({"scLANE_pred_link": fit, "scLANE_se_link": se, "scLANE_ci_ll_link": fit - z * se, "scLANE_ci_ul_link": fit + z * se,
+                       "scLANE_pred": np.exp(fit), "scLANE_ci_ll": np.exp(fit - z * se), "scLANE_ci_ul": np.exp(fit + z * se)})
+            if sf_all is not None and not is_gee:
+                for k in ("rna", "scLANE_pred", "scLANE_ci_ll", "scLANE_ci_ul"):
+                    df[k] = df[k] * sf_all[cells]
+            if log1p_norm:
+                for k in ("rna", "scLANE_pred", "scLANE_ci_ll", "scLANE_ci_ul"):
+                    df[k + "_log1p"] = np.log1p(df[k])
+            frame = pd.DataFrame(df)
+            if cell_meta_data is not None:
+                frame = pd.concat([frame, pd.DataFrame(cell_meta_data).iloc[cells].reset_index(drop=True)], axis=1)
+            frames.append(frame)
+    return pd.concat(frames, ignore_index=True)
 
 
 def getResultsDE(test_dyn_res=None, p_adj_method: str = "fdr", fdr_cutoff: float = 0.01):

@@ -719,6 +719,40 @@ __global__ void k_link_preds(PredModel M, const double* __restrict__ x, const do
   }
 }
 
+// smoothedCountsMatrix(): fitted means of every cell under every gene's final model (smoothedCountsMatrix.R:44-67)
+struct SmoothModel {
+  int n_alt;                 // 0 = model failed -> NaN column
+  int kind[PMAX];
+  double knot[PMAX];
+  double coef[PMAX];
+};
+__global__ void k_smoothed_counts(const SmoothModel* __restrict__ models, const double* __restrict__ x, const double* __restrict__ sf,
+                                  long long n, int add_offset, int log1p_norm, double* __restrict__ out) {
+  __shared__ SmoothModel M;
+  const int g = blockIdx.y;
+  if (threadIdx.x == 0) M = models[g];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = nan("");
+  if (M.n_alt > 0) {
+    const double X = r_round(x[i], 1e4);                 // marge2.R:154
+    double eta = 0.0;
+    for (int j = 0; j < M.n_alt; ++j) {
+      double c;
+      if (M.kind[j] == SCLANE_TERM_INTERCEPT) c = 1.0;
+      else if (M.kind[j] == SCLANE_TERM_TP1) c = X > M.knot[j] ? X - M.knot[j] : 0.0;
+      else c = X < M.knot[j] ? M.knot[j] - X : 0.0;
+      eta += c * M.coef[j];
+    }
+    if (sf && add_offset) eta += log(1.0 / sf[i]);       // marge_link_fit of a GLM record includes the offset
+    v = exp(eta);
+    if (sf) v *= sf[i];
+    if (log1p_norm) v = log1p(v);
+  }
+  out[(size_t)g * (size_t)n + (size_t)i] = v;
+}
+
 // explicit-knot lineage plan for the single-step entry points
 bool plan_from_knots(const double* x, int64_t n, const double* knots, int n_knots, LineagePlan& P, char* errbuf, size_t errlen) {
   if (n_knots < 1 || n_knots > SCLANE_TMAX) { set_err(errbuf, errlen, "n_knots must be in [1, %d]", SCLANE_TMAX); return false; }
@@ -968,6 +1002,38 @@ int32_t sclane_link_preds(const sclane_record* rec, const double* x, int64_t n, 
     k_link_preds<<<(unsigned)((n + 255) / 256), 256>>>(M, dx.p, dsf.p, (long long)n, o[0].p, o[1].p, o[2].p, o[3].p);
     CK(cudaGetLastError()); g_launches.fetch_add(1);
     for (int k = 0; k < 4; ++k) if (host[k]) CK(cudaMemcpy(host[k], o[k].p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }
+  return SCLANE_OK;
+}
+
+int32_t sclane_smoothed_counts(const sclane_record* recs, int64_t n_genes, int32_t n_lineages, int32_t lineage, const double* x, int64_t n,
+                               const double* size_factor, int32_t is_gee, int32_t log1p_norm, int32_t device, double* out,
+                               char* errbuf, size_t errlen) {
+  if (!recs || !x || !out || n < 1 || n_genes < 1 || n_lineages < 1 || lineage < 0 || lineage >= n_lineages) { set_err(errbuf, errlen, "bad arguments"); return SCLANE_ERR_ARG; }
+  if (n_genes > 65535) { set_err(errbuf, errlen, "at most 65535 genes per call"); return SCLANE_ERR_ARG; }
+  if (usable_devices() <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
+  std::vector<SmoothModel> models((size_t)n_genes);
+  for (int64_t g = 0; g < n_genes; ++g) {
+    const sclane_record& r = recs[g * n_lineages + lineage];
+    SmoothModel& M = models[(size_t)g];
+    std::memset(&M, 0, sizeof(M));
+    if (r.status & SCLANE_MARGE_OK) {
+      M.n_alt = r.n_terms;
+      for (int j = 0; j < r.n_terms; ++j) { M.kind[j] = r.term_kind[j]; M.knot[j] = r.term_knot[j]; M.coef[j] = r.coef[j]; }
+    }
+  }
+  try {
+    CK(cudaSetDevice(device));
+    DevBuf<double> dx, dsf, dout;
+    DevBuf<SmoothModel> dm;
+    dx.alloc((size_t)n); dout.alloc((size_t)n * (size_t)n_genes); dm.alloc((size_t)n_genes);
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dm.p, models.data(), (size_t)n_genes * sizeof(SmoothModel), cudaMemcpyHostToDevice));
+    if (size_factor) { dsf.alloc((size_t)n); CK(cudaMemcpy(dsf.p, size_factor, (size_t)n * 8, cudaMemcpyHostToDevice)); }
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_genes);
+    k_smoothed_counts<<<grid, 256>>>(dm.p, dx.p, dsf.p, (long long)n, is_gee ? 0 : 1, log1p_norm, dout.p);
+    CK(cudaGetLastError()); g_launches.fetch_add(1);
+    CK(cudaMemcpy(out, dout.p, (size_t)n * (size_t)n_genes * 8, cudaMemcpyDeviceToHost));
   } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }
   return SCLANE_OK;
 }

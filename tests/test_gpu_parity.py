@@ -307,3 +307,25 @@ def test_negative_counts_fail_the_gene_only():
     for i in range(12):
         if i != 3:
             assert _rec_bytes(res.records[i]) == _rec_bytes(ref.records[i])
+
+
+def test_smoothed_counts_and_fitted_values_vs_golden(gpu_golden, golden_inputs, golden_preds):
+    """smoothedCountsMatrix() / getFittedValues() (the per-cell consumers of the fitted models, smoothedCountsMatrix.R:27-74,
+    getFittedValues.R:45-150) against the reference's bundled per-cell predictions: exp(marge_link_fit) * size factor."""
+    import sclane_b200 as sb
+    sf = golden_inputs["size_factor"]
+    sm = sb.smoothedCountsMatrix(gpu_golden, size_factor_offset=sf, pt=golden_inputs["pt"])
+    mat, names = sm["Lineage_A"]["matrix"], sm["Lineage_A"]["genes"]
+    assert mat.shape == (golden_inputs["pt"].shape[0], len(names)) and len(names) == 100
+    checked = sorted({k.split("/")[0] for k in golden_preds.files} - GOLDEN_EXCEPTIONS)
+    for g in checked:
+        gold = np.exp(golden_preds[f"{g}/marge_link_fit"]) * sf
+        assert np.max(np.abs(mat[:, names.index(g)] - gold) / gold) < TOL, g
+    lg = sb.smoothedCountsMatrix(gpu_golden, size_factor_offset=sf, pt=golden_inputs["pt"], genes=checked[:3], log1p_norm=True)
+    assert np.allclose(lg["Lineage_A"]["matrix"], np.log1p(mat[:, [names.index(g) for g in checked[:3]]]), rtol=1e-12)
+    fv = sb.getFittedValues(gpu_golden, genes=checked[:2], pt=golden_inputs["pt"], expr_mat=golden_inputs["counts"], size_factor_offset=sf)
+    assert len(fv) == 2 * golden_inputs["pt"].shape[0]
+    sub = fv[fv["gene"] == checked[0]]
+    gold = np.exp(golden_preds[f"{checked[0]}/marge_link_fit"]) * sf
+    assert np.max(np.abs(sub["scLANE_pred"].to_numpy() - gold) / gold) < TOL
+    assert np.all(sub["scLANE_ci_ll"].to_numpy() <= sub["scLANE_pred"].to_numpy())
