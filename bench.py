@@ -45,8 +45,10 @@ sys.path.insert(0, ROOT)
 #     25.73 GB; scaled to the average launch of the default run (two batches, 24.0 GB algorithmic each).
 # c2: profiles/r01_ncu_sweep_v1.txt -- 243.2 MB read + 7.4 MB written per 2,000-gene launch (240.1 MB algorithmic).
 TRAFFIC_PER_LAUNCH = {"c2": 250.6e6, "c5": 24.02e9}
-# same for the X-compressed forward kernel k_comp_stage<0> (profiles/r01_ncu_comp_forward_*.txt); filled from the capture
-TRAFFIC_PER_LAUNCH_COMP = {"c2": None, "c5": None}
+# same for the X-compressed forward kernel k_comp_stage<0>, PER GENE (the launch size follows the free device memory):
+# profiles/r01_ncu_comp_forward_c5.txt -- 859.3 MB read + 122.1 MB written by a 9,729-gene launch = 100.9 KB per gene
+# (vs 4.8 MB of algorithmic sweep bytes per gene: 2 iterations x 12 B x 200,000 cells).
+TRAFFIC_PER_GENE_COMP = {"c2": None, "c5": 100.9e3}
 
 CONFIGS = {
     "c5": {"genes": 20000, "cells": 200000,
@@ -320,7 +322,8 @@ def main():
                     "time of the k_comp_stage<FORWARD> launches (rank 0) -- the whole forward stage incl. the NB null fits is charged to the "
                     "sweep's bytes.  The kernel works on per-abscissa aggregates (k_aggregate), so its DRAM traffic is far below the "
                     "algorithmic bytes; the streaming per-cell kernel k_sweep_moments (--per-cell) moves them at 97.7 % of peak")
-            traffic = TRAFFIC_PER_LAUNCH_COMP.get(args.config) if (world == 1 and not args.genes) else None
+            per_gene = TRAFFIC_PER_GENE_COMP.get(args.config)
+            traffic = per_gene * G * args.steps / max(1, sweep_launches) if per_gene else None
         else:
             sweep_ms = prof_acc["ms"]["sweep"]
             sweep_launches = prof_acc["launches"]["sweep"]
