@@ -219,6 +219,20 @@ int32_t sclane_test_dynamic_device(const int32_t* d_counts, int32_t device,
                                    sclane_record* out, sclane_lineage_info* lineages,
                                    char* errbuf, size_t errlen);
 
+/* Same computation from a SPARSE count matrix in the layout Seurat / SingleCellExperiment hold it: a genes x cells
+ * dgCMatrix (compressed by cell column), i.e. what testDynamic.R:80-97 densifies and transposes on the host.
+ * indptr  = dgCMatrix@p  (n_cells + 1 int32),  indices = dgCMatrix@i  (nnz int32 gene rows),  data = dgCMatrix@x (nnz
+ * doubles holding integer counts).  HOST pointers.  12 B per non-zero cross PCIe instead of 4 B per cell and gene (real
+ * scRNA-seq matrices are ~90 % zeros); every GPU expands its own gene shard to the dense gene-major layout on the device.
+ * GLM mode only. */
+int32_t sclane_test_dynamic_csc(const int32_t* indptr, const int32_t* indices, const double* data,
+                                int64_t n_cells, int64_t n_genes,
+                                const double* pt, int32_t n_lineages,
+                                const double* size_factor,
+                                const sclane_opts* opts,
+                                sclane_record* out, sclane_lineage_info* lineages,
+                                char* errbuf, size_t errlen);
+
 /* GEE mode of the same path (testDynamic(is.gee = TRUE, gee.test = "wald"), testDynamic.R:66-70,235-244,
  * 296-301; marge2.R:258-268 (stat_out_score_gee_null), :438-448/:520-530 (score_fun_gee), :831-838 (final geem);
  * backward_sel_WIC.R:36-42; waldTestGEE.R:24-93).  Same arguments as sclane_test_dynamic() plus

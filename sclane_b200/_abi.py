@@ -117,7 +117,7 @@ class SclaneLineageInfo(C.Structure):
 EXPORTED_SYMBOLS = [
     "sclane_abi_version", "sclane_device_count", "sclane_default_opts", "sclane_record_size",
     "sclane_launch_count", "sclane_reset_launch_count", "sclane_get_profile", "sclane_release",
-    "sclane_test_dynamic", "sclane_test_dynamic_device", "sclane_test_dynamic_gee", "sclane_candidate_knots",
+    "sclane_test_dynamic", "sclane_test_dynamic_device", "sclane_test_dynamic_gee", "sclane_test_dynamic_csc", "sclane_candidate_knots",
     "sclane_null_stats_glm", "sclane_score_glm", "sclane_link_preds", "sclane_smoothed_counts",
     "sclane_matmul", "sclane_llt_inverse", "sclane_pinv",
 ]

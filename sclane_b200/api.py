@@ -153,6 +153,10 @@ def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None
     return o
 
 
+def _is_sparse(m) -> bool:
+    return hasattr(m, "tocsc") and hasattr(m, "nnz")
+
+
 def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = None, device_ptr: int | None = None,
                 device: int = 0, subject_id=None):
     """Thin call of sclane_test_dynamic[_device|_gee]: counts int32 [genes, cells] C-contiguous (gene-major), pt float64
@@ -170,7 +174,23 @@ def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = Non
     if sf is not None and sf.shape != (n_cells,):
         raise ValueError("size.factor.offset must have one entry per cell")
     err = C.create_string_buffer(_ERRLEN)
-    if device_ptr is None:
+    if device_ptr is None and _is_sparse(counts):
+        # genes x cells sparse matrix (dgCMatrix layout = scipy CSC): sclane_test_dynamic_csc
+        csc = counts.tocsc()
+        if csc.shape[1] != n_cells:
+            raise ValueError("expr.mat must be genes x cells with one column per row of pt")
+        if subject_id is not None:
+            raise SclaneError(4, "sparse input is built for GLM mode only")
+        csc.sort_indices()
+        n_genes = csc.shape[0]
+        indptr = np.ascontiguousarray(csc.indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(csc.indices, dtype=np.int32)
+        data = np.ascontiguousarray(csc.data, dtype=np.float64)
+        recs = (_abi.SclaneRecord * (n_genes * n_lin))()
+        infos = (_abi.SclaneLineageInfo * n_lin)()
+        rc = L.sclane_test_dynamic_csc(indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, n_cells, n_genes, pt_cm.ctypes.data,
+                                       n_lin, None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
+    elif device_ptr is None:
         counts = np.ascontiguousarray(counts, dtype=np.int32)
         if counts.ndim != 2 or counts.shape[1] != n_cells:
             raise ValueError("expr.mat must be genes x cells with one column per row of pt")
@@ -437,6 +457,8 @@ def createCellOffset(expr_mat, scale_factor: float = 1e4) -> np.ndarray:
     """createCellOffset.R:19-38: scale.factor / colSums(counts); expr.mat is genes x cells."""
     if expr_mat is None:
         raise ValueError("Please provide expr.mat to createCellOffset().")
+    if _is_sparse(expr_mat):
+        return float(scale_factor) / np.asarray(expr_mat.sum(axis=0), dtype=np.float64).reshape(-1)
     m = np.asarray(expr_mat)
     if m.ndim != 2:
         raise ValueError("Input expr.mat must be coerceable to a matrix of integer counts.")
@@ -477,13 +499,13 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
         # testDynamic.R:107-118: the data must be ordered by subject
         if np.count_nonzero(np.diff(subject_id) != 0) != len(first) - 1:
             raise ValueError("Data must be ordered by subject, please do so before running testDynamic() with is.gee = TRUE.")
-    counts = np.ascontiguousarray(expr_mat, dtype=np.int32)
+    counts = expr_mat if _is_sparse(expr_mat) else np.ascontiguousarray(expr_mat, dtype=np.int32)
     if counts.ndim != 2:
         raise ValueError("Input expr.mat must be coerceable to a matrix of integer counts.")
     pt_arr = np.asarray(pt, dtype=np.float64)
     if pt_arr.ndim == 1:
         pt_arr = pt_arr[:, None]
-    n_genes = counts.shape[0]
+    n_genes = int(counts.shape[0])
     if genes is None:
         genes = [f"Gene_{i + 1}" for i in range(n_genes)]
     genes = [str(g) for g in genes]

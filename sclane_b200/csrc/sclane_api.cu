@@ -464,10 +464,51 @@ void merge_profile(const sclane_profile& p) {
   g_prof.d2h_bytes += p.d2h_bytes;
 }
 
+// ---- sparse ingestion: dgCMatrix (genes x cells, compressed by cell) -> dense gene-major int32 shard on the device ----
+struct CscInput {
+  const int32_t* indptr;     // [n_cells + 1]   dgCMatrix@p
+  const int32_t* indices;    // [nnz] gene row  dgCMatrix@i
+  const double* data;        // [nnz]           dgCMatrix@x
+  int64_t nnz;
+};
+
+// one thread per cell column: scatter its non-zeros that fall into [g0, g1) into the dense shard
+__global__ void k_csc_expand(const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ data,
+                             long long n_cells, int g0, int g1, int* __restrict__ dense) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_cells) return;
+  const int k1 = indptr[j + 1];
+  for (int k = indptr[j]; k < k1; ++k) {
+    const int g = indices[k];
+    if (g >= g0 && g < g1) dense[(size_t)(g - g0) * (size_t)n_cells + (size_t)j] = (int)llrint(data[k]);
+  }
+}
+
+const int32_t* expand_csc_shard(int device, const CscInput& c, int64_t n_cells, int64_t g0, int64_t g1, double& h2d_bytes) {
+  CK(cudaSetDevice(device));
+  DevicePool& pool = pool_for(device);
+  if (!pool.stream) CK(cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking));
+  cudaStream_t s = pool.stream;
+  int* d_ptr = (int*)pool.get("csc_indptr", (size_t)(n_cells + 1) * 4);
+  int* d_idx = (int*)pool.get("csc_indices", (size_t)c.nnz * 4);
+  double* d_val = (double*)pool.get("csc_data", (size_t)c.nnz * 8);
+  int* dense = (int*)pool.get("csc_dense", (size_t)(g1 - g0) * (size_t)n_cells * 4);
+  CK(cudaMemcpyAsync(d_ptr, c.indptr, (size_t)(n_cells + 1) * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_idx, c.indices, (size_t)c.nnz * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_val, c.data, (size_t)c.nnz * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(dense, 0, (size_t)(g1 - g0) * (size_t)n_cells * 4, s));
+  k_csc_expand<<<(unsigned)((n_cells + 255) / 256), 256, 0, s>>>(d_ptr, d_idx, d_val, (long long)n_cells, (int)g0, (int)g1, dense);
+  CK(cudaGetLastError());
+  g_launches.fetch_add(1);
+  CK(cudaStreamSynchronize(s));
+  h2d_bytes = (double)(n_cells + 1) * 4.0 + (double)c.nnz * 12.0;
+  return dense;
+}
+
 int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int device_for_d, int64_t n_cells, int64_t n_genes,
                       const double* pt, int32_t n_lineages, const double* size_factor, const sclane_opts* opts,
                       sclane_record* out, sclane_lineage_info* lineages, char* errbuf, size_t errlen,
-                      const int32_t* subject_id = nullptr) {
+                      const int32_t* subject_id = nullptr, const CscInput* csc = nullptr) {
   int rc = check_opts(opts, errbuf, errlen);
   if (rc) return rc;
   const bool gee = opts->mode == 1;
@@ -477,7 +518,7 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
     if (opts->gee_test != 0 && opts->gee_test != 1) { set_err(errbuf, errlen, "gee_test must be 0 (wald) or 1 (score)"); return SCLANE_ERR_ARG; }
     if (opts->gee_cor < SCLANE_COR_INDEPENDENCE || opts->gee_cor > SCLANE_COR_AR1) { set_err(errbuf, errlen, "Currently unsupported correlation structure."); return SCLANE_ERR_ARG; }
   } else if (subject_id) { set_err(errbuf, errlen, "subject ids given but opts->mode is not 1 (GEE)"); return SCLANE_ERR_ARG; }
-  if ((!h_counts && !d_counts) || !pt || !out || n_cells <= 0 || n_genes <= 0 || n_lineages <= 0) {
+  if ((!h_counts && !d_counts && !csc) || !pt || !out || n_cells <= 0 || n_genes <= 0 || n_lineages <= 0) {
     set_err(errbuf, errlen, "bad arguments (null pointer or non-positive size)");
     return SCLANE_ERR_ARG;
   }
@@ -493,6 +534,26 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
   {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     std::memset(&g_prof, 0, sizeof(g_prof));
+  }
+  // sparse input: every device expands ITS gene shard to the dense gene-major layout once (all lineages reuse it)
+  std::vector<const int32_t*> shard_base(devs.size(), nullptr);
+  if (csc) {
+    const int nd0 = (int)devs.size();
+    std::vector<std::string> errs0((size_t)nd0);
+    std::vector<double> h2d0((size_t)nd0, 0.0);
+    auto expand = [&](int di) {
+      const int64_t g0 = n_genes * di / nd0, g1 = n_genes * (di + 1) / nd0;
+      try { shard_base[(size_t)di] = expand_csc_shard(devs[(size_t)di], *csc, n_cells, g0, g1, h2d0[(size_t)di]); }
+      catch (const CudaFail& f) { errs0[(size_t)di] = f.msg; }
+      catch (const std::exception& e) { errs0[(size_t)di] = e.what(); }
+    };
+    if (nd0 == 1) expand(0);
+    else { std::vector<std::thread> th; for (int di = 0; di < nd0; ++di) th.emplace_back(expand, di); for (auto& t : th) t.join(); }
+    for (int di = 0; di < nd0; ++di) {
+      if (!errs0[(size_t)di].empty()) { set_err(errbuf, errlen, "device %d: %s", devs[(size_t)di], errs0[(size_t)di].c_str()); return SCLANE_ERR_CUDA; }
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_prof.h2d_bytes += h2d0[(size_t)di];
+    }
   }
   for (int l = 0; l < n_lineages; ++l) {
     LineagePlan P;
@@ -521,7 +582,11 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
       const int64_t g0 = n_genes * di / nd, g1 = n_genes * (di + 1) / nd;
       try {
         if (gee) run_shard_gee(devs[(size_t)di], h_counts, n_cells, g0, g1, P, GPl, *opts, size_factor != nullptr, out, n_lineages, l, profs[(size_t)di]);
-        else run_shard(devs[(size_t)di], h_counts, d_counts, n_cells, g0, g1, P, *opts, size_factor != nullptr, out, 0, n_lineages, l, profs[(size_t)di]);
+        else {
+          // a CSC shard is dense on the device with local gene index 0 = global gene g0
+          const int32_t* dc = csc ? shard_base[(size_t)di] - (ptrdiff_t)g0 * (ptrdiff_t)n_cells : d_counts;
+          run_shard(devs[(size_t)di], h_counts, dc, n_cells, g0, g1, P, *opts, size_factor != nullptr, out, 0, n_lineages, l, profs[(size_t)di]);
+        }
       } catch (const CudaFail& f) {
         errs[(size_t)di] = f.msg;
       } catch (const std::exception& e) {
@@ -855,6 +920,19 @@ int32_t sclane_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t 
   if (!subject_id) { set_err(errbuf, errlen, "subject_id is NULL"); return SCLANE_ERR_ARG; }
   if (opts && opts->mode != 1) { set_err(errbuf, errlen, "sclane_test_dynamic_gee() needs opts->mode = 1"); return SCLANE_ERR_ARG; }
   return test_dynamic_impl(counts, nullptr, -1, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen, subject_id);
+}
+
+int32_t sclane_test_dynamic_csc(const int32_t* indptr, const int32_t* indices, const double* data, int64_t n_cells, int64_t n_genes,
+                                const double* pt, int32_t n_lineages, const double* size_factor, const sclane_opts* opts,
+                                sclane_record* out, sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  if (!indptr || !indices || !data || n_cells <= 0) { set_err(errbuf, errlen, "bad arguments (null CSC pointer)"); return SCLANE_ERR_ARG; }
+  if (opts && opts->mode != 0) { set_err(errbuf, errlen, "sparse input is built for GLM mode only"); return SCLANE_ERR_UNSUPPORTED; }
+  if (indptr[0] != 0 || indptr[n_cells] < 0) { set_err(errbuf, errlen, "indptr must start at 0"); return SCLANE_ERR_ARG; }
+  const int64_t nnz = indptr[n_cells];
+  for (int64_t j = 0; j < n_cells; ++j) if (indptr[j + 1] < indptr[j]) { set_err(errbuf, errlen, "indptr must be non-decreasing"); return SCLANE_ERR_ARG; }
+  for (int64_t k = 0; k < nnz; ++k) if (indices[k] < 0 || indices[k] >= n_genes) { set_err(errbuf, errlen, "row index %d out of range at entry %lld", indices[k], (long long)k); return SCLANE_ERR_ARG; }
+  CscInput c{indptr, indices, data, nnz};
+  return test_dynamic_impl(nullptr, nullptr, -1, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen, nullptr, &c);
 }
 
 int32_t sclane_test_dynamic_device(const int32_t* d_counts, int32_t device, int64_t n_cells, int64_t n_genes, const double* pt,

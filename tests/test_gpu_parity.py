@@ -329,3 +329,39 @@ def test_smoothed_counts_and_fitted_values_vs_golden(gpu_golden, golden_inputs, 
     gold = np.exp(golden_preds[f"{checked[0]}/marge_link_fit"]) * sf
     assert np.max(np.abs(sub["scLANE_pred"].to_numpy() - gold) / gold) < TOL
     assert np.all(sub["scLANE_ci_ll"].to_numpy() <= sub["scLANE_pred"].to_numpy())
+
+
+def test_sparse_csc_input_equals_dense():
+    """sclane_test_dynamic_csc (genes x cells dgCMatrix layout, expanded on the device) gives byte-identical records to the
+    dense entry point, with offsets and two lineages; bad indices are rejected."""
+    import scipy.sparse as sp
+    import sclane_b200 as sb
+    from sclane_b200 import _abi, api, synth
+    counts, pt, _ = synth.make_counts(40, 6000, seed=8)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    counts[:, ::3] = 0                                           # sparser than the generator makes it
+    pt = np.asarray(pt, dtype=np.float64).reshape(-1)
+    pt2 = np.stack([np.where(np.arange(6000) % 4 == 0, np.nan, pt), np.where(np.arange(6000) % 7 == 0, np.nan, 1.0 - pt)], 1)
+    m = sp.csc_matrix(counts)
+    assert np.allclose(sb.createCellOffset(m), sb.createCellOffset(counts))
+    sf = sb.createCellOffset(counts)
+    for offs in (None, sf):
+        a = sb.testDynamic(counts, pt2, size_factor_offset=offs, n_gpus=1, preds="none")
+        b = sb.testDynamic(m, pt2, size_factor_offset=offs, n_gpus=1, preds="none")
+        assert len(b.records) == len(a.records) == 80
+        for i in range(80):
+            assert _rec_bytes(a.records[i]) == _rec_bytes(b.records[i]), i
+    # a row index outside [0, n_genes) is a global argument error, reported through errbuf
+    import ctypes as C
+    from sclane_b200._lib import lib
+    indptr = np.ascontiguousarray(m.indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(m.indices, dtype=np.int32).copy()
+    data = np.ascontiguousarray(m.data, dtype=np.float64)
+    indices[5] = 40
+    o = api._opts(gpu_ids=[0])
+    recs = (_abi.SclaneRecord * 80)()
+    err = C.create_string_buffer(512)
+    ptc = np.ascontiguousarray(pt2.T)
+    rc = lib().sclane_test_dynamic_csc(indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, 6000, 40, ptc.ctypes.data, 2, None,
+                                       C.byref(o), recs, None, err, 512)
+    assert rc == 1 and b"out of range" in err.value
