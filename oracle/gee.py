@@ -392,7 +392,7 @@ def test_dynamic_gee(counts, pt, subject, genes=None, size_factor_offset=None, c
             rec.update({"Model_Status": f"MARGE model OK, null model {'OK' if null is not None else 'error'}",
                         "MARGE_Summary": {"term": [term_name(t, knots, "Lineage_A") for t in final],
                                           "estimate": list(fit.beta), "std.error": list(se), "statistic": list(z),
-                                          "p.value": [pnorm_two_sided(v) for v in z]},
+                                          "p.value": [r_round(pnorm_two_sided(v), 8) for v in z]},       # summary.geem rounds to 8 digits
                         "alpha": fit.alpha, "phi": fit.phi, "converged": fit.converged, "niter": fit.niter})
             if gee_test == "score":
                 if null is None:

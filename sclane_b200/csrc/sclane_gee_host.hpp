@@ -83,7 +83,7 @@ inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_t
       r.coef[j] = g.alt.coef[j];
       r.se[j] = std::sqrt(g.alt.cov[j * GEE_PMAX + j]);
       r.z[j] = r.coef[j] / r.se[j];
-      r.p[j] = pnorm_two_sided(r.z[j]);
+      r.p[j] = r_round(pnorm_two_sided(r.z[j]), 1e8);         // summary.geem() rounds its p-values to 8 digits
       for (int l = 0; l < p; ++l) r.cov[j * p + l] = g.alt.cov[j * GEE_PMAX + l];
     }
     r.gee_alpha = g.alt.alpha; r.gee_phi = g.alt.phi;
@@ -108,7 +108,7 @@ inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_t
     r.null_coef = g.null.coef[0];
     r.null_se = std::sqrt(g.null.cov[0]);
     r.null_z = r.null_coef / r.null_se;
-    r.null_p = pnorm_two_sided(r.null_z);
+    r.null_p = r_round(pnorm_two_sided(r.null_z), 1e8);
     r.null_gee_alpha = g.null.alpha; r.null_gee_phi = g.null.phi;
     r.null_gee_converged = g.null.converged; r.null_gee_iters = g.null.niter;
   }

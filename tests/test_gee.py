@@ -54,6 +54,9 @@ def _compare(recs, ref, genes, tol=TOL):
         for j in range(r.n_terms):
             if rel(r.coef[j], b["MARGE_Summary"]["estimate"][j], 1e-6) > tol or rel(r.se[j], b["MARGE_Summary"]["std.error"][j], 1e-6) > tol:
                 bad.append((name, "coef/se", j, r.coef[j], b["MARGE_Summary"]["estimate"][j]))
+        for j in range(r.n_terms):
+            if r.p[j] != b["MARGE_Summary"]["p.value"][j] and abs(r.p[j] - b["MARGE_Summary"]["p.value"][j]) > 2e-8:
+                bad.append((name, "coef p", j, r.p[j], b["MARGE_Summary"]["p.value"][j]))
         if np.isnan(b["Test_Stat"]):                 # score test without a null model: NA statistic on both sides
             if not (np.isnan(r.test_stat) and np.isnan(r.df) and np.isnan(r.p_val)):
                 bad.append((name, "test should be NA", r.test_stat, r.df))
