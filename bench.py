@@ -352,7 +352,7 @@ def main():
                          "ms_per_launch": sweep_ms / max(1, sweep_launches),
                          "select_kernel_ms_per_launch": prof_acc["ms"]["select"] / max(1, prof_acc["launches"]["select"]),
                          "note": note,
-                         "gather_aggregate": {"kernels": "k_gather_stats + k_aggregate (sort by pseudotime, per-abscissa sums)",
+                         "gather_aggregate": {"kernels": ("k_gather_copy + k_aggregate" if comp else "k_gather_stats") + " (sort by pseudotime; per-abscissa sums)",
                                               "achieved": gather_bytes / 1e9 / (gather_ms / 1000.0) if gather_ms > 0 else None,
                                               "unit": "GB/s", "ms_per_step": gather_ms / args.steps,
                                               "bytes": "4 B read + 4 B written per cell (gather)" + (" + 4 B read per cell (aggregate)" if comp else "")}},
