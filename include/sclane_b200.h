@@ -83,7 +83,10 @@ typedef struct sclane_opts {
   int32_t gee_cor;            /* cor.structure (testDynamic.R:66): SCLANE_COR_* ; default ar1 */
   int32_t gee_test;           /* gee.test (testDynamic.R:68): 0 = "wald" (waldTestGEE.R), 1 = "score" (scoreTestGEE.R) */
   int32_t force_per_cell;     /* 1 = never use the X-compressed kernels (testing / profiling of the per-cell kernels) */
-  int32_t reserved[5];
+  int32_t gee_bias_correction; /* gee.bias.correction.method (testDynamic.R:67): 0 = NULL (model-based variance), 1 = "kc",
+                                 2 = "df"; != 0 switches every GEE fit of the path to the sandwich variance
+                                 (testDynamic.R:195,243,286) and waldTestGEE() to biasCorrectGEE() (ar1 / exchangeable only) */
+  int32_t reserved[4];
 } sclane_opts;
 
 /* One record per (gene, lineage): everything testDynamic() returns for that pair except the
@@ -239,8 +242,8 @@ int32_t sclane_test_dynamic_csc(const int32_t* indptr, const int32_t* indices, c
  * subject_id   n_cells int32 subject labels; the cells MUST be ordered by subject (testDynamic.R:115 stops
  *              otherwise) -> SCLANE_ERR_ARG if a label re-appears after a different one.  HOST pointer.
  * opts->gee_cor selects the working correlation; opts->M <= SCLANE_GEE_PMAX; <= SCLANE_GEE_SMAX subjects per
- * lineage.  opts->gee_test selects waldTestGEE() or scoreTestGEE(); gee.bias.correction.method (sandwich variance with
- * small-sample corrections) is not built.
+ * lineage.  opts->gee_test selects waldTestGEE() or scoreTestGEE(); opts->gee_bias_correction the sandwich variance with
+ * the "kc" / "df" small-sample correction of biasCorrectGEE.R.
  * Records: see the GEE note in sclane_record. */
 int32_t sclane_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t n_genes,
                                 const double* pt, int32_t n_lineages,

@@ -77,13 +77,14 @@ class GeemFit:
     alpha: float
     phi: float
     naiv_var: np.ndarray
+    var: np.ndarray | None      # robust (sandwich) variance when sandwich = TRUE
     eta: np.ndarray
     mu: np.ndarray
     converged: bool
     niter: int
 
 
-def geem(X, y, n_vec, cor: str, offset=None, maxit: int = 20, tol: float = 1e-5) -> GeemFit:
+def geem(X, y, n_vec, cor: str, offset=None, maxit: int = 20, tol: float = 1e-5, sandwich: bool = False) -> GeemFit:
     """geeM::geem(y ~ X - 1, id, family = negative.binomial(50), corstr = cor, scale.fix = FALSE) [3P, from memory]."""
     y = np.asarray(y, dtype=np.float64)
     N, p = X.shape
@@ -146,7 +147,21 @@ def geem(X, y, n_vec, cor: str, offset=None, maxit: int = 20, tol: float = 1e-5)
             break
         beta_old = beta.copy()
     eta = X @ beta + off
-    return GeemFit(beta=beta, alpha=float(alpha), phi=float(phi), naiv_var=_rcond_ok(hess), eta=eta, mu=np.exp(eta),
+    naiv = _rcond_ok(hess)
+    var_rob = None
+    if sandwich:
+        # geeM getSandwich(): numsand = sum_i e_i e_i', e_i = Z_i' (R_i^-1 / phi) rr_i at the FINAL eta with the alpha / phi
+        # of the last outer iteration; var = hess^-1 numsand hess^-T with the hessian of the last inner step
+        mu = np.exp(eta)
+        se = np.sqrt(1.0 / var(mu))
+        Z = (se * mu)[:, None] * X
+        rr = se * (y - mu)
+        numsand = np.zeros((p, p))
+        for (a, b), Ri in zip(zip(starts[:-1], starts[1:]), rinv):
+            e = Z[a:b].T @ (Ri / phi) @ rr[a:b]
+            numsand += np.outer(e, e)
+        var_rob = naiv @ numsand @ naiv.T
+    return GeemFit(beta=beta, alpha=float(alpha), phi=float(phi), naiv_var=naiv, var=var_rob, eta=eta, mu=np.exp(eta),
                    converged=converged, niter=count)
 
 
@@ -273,14 +288,15 @@ def forward_pass_gee(Y, X, knots, n_vec, cor, M=5, tols_score=1e-5, trace=None):
     return terms
 
 
-def backward_sel_wic_gee(Y, B, n_vec, cor):
-    """backward_sel_WIC.R:36-42: geem refit, (beta / se.model)^2 of the non-intercept columns (sandwich = FALSE)."""
-    fit = geem(B, Y, n_vec, cor)
-    se = np.sqrt(np.diag(fit.naiv_var))
+def backward_sel_wic_gee(Y, B, n_vec, cor, sandwich=False):
+    """backward_sel_WIC.R:36-42: geem refit, summary(fit)$wald.test[-1]^2 -- beta / se.model, or beta / se.robust when the
+    fit carries a sandwich variance (summary.geem)."""
+    fit = geem(B, Y, n_vec, cor, sandwich=sandwich)
+    se = np.sqrt(np.diag(fit.var if sandwich else fit.naiv_var))
     return (fit.beta / se)[1:] ** 2, fit
 
 
-def backward_pass_gee(Y, X, knots, terms, n_vec, cor, trace=None):
+def backward_pass_gee(Y, X, knots, terms, n_vec, cor, trace=None, sandwich=False):
     """marge2.R:763-812 (same bookkeeping as the GLM branch)."""
     ncol_B = len(terms)
     if ncol_B <= 2:
@@ -291,7 +307,7 @@ def backward_pass_gee(Y, X, knots, terms, n_vec, cor, trace=None):
     cum = 0.0
     lowest = 0
     for i in range(1, ncol_B):
-        wic1, _ = backward_sel_wic_gee(Y, build_design(cur, X, knots), n_vec, cor)
+        wic1, _ = backward_sel_wic_gee(Y, build_design(cur, X, knots), n_vec, cor, sandwich)
         if trace is not None:
             trace.wald_steps.append(np.array(wic1))
         cum += _nanmin(wic1)
@@ -315,13 +331,25 @@ def backward_pass_gee(Y, X, knots, terms, n_vec, cor, trace=None):
     return out
 
 
-def wald_test_gee(fit: GeemFit):
-    """waldTestGEE.R:24-93 (correction.method = NULL => naive variance)."""
+def bias_correct_gee(fit: GeemFit, method: str, n_subjects: int, n_obs: int) -> np.ndarray:
+    """biasCorrectGEE.R:17-158.  "df": n_s / (n_s - p) x sandwich (unchanged when p >= n_s, :36-38).  "kc":
+    (n_s / (n_s - 1)) / (1 - tr(H) / n) x sandwich with H = X (X'WX)^-1 X'W a projection of rank p, so tr(H) = p whatever
+    the per-subject correlation estimates in W are (:125-137)."""
+    p = fit.beta.size
+    if method == "df":
+        return fit.var if p >= n_subjects else (n_subjects / (n_subjects - p)) * fit.var
+    if method == "kc":
+        return ((n_subjects / (n_subjects - 1.0)) / (1.0 - p / n_obs)) * fit.var
+    raise ValueError("Unsupported bias correction method in waldTestGEE().")
+
+
+def wald_test_gee(fit: GeemFit, vcov=None):
+    """waldTestGEE.R:24-93 (correction.method = NULL => naive variance; otherwise the bias-corrected sandwich)."""
     p = fit.beta.size
     if p <= 1:
         return {"Wald_Stat": 0.0, "DF": 0, "P_Val": 1.0}
     L = np.eye(p)[1:]
-    middle = L @ fit.naiv_var @ L.T
+    middle = L @ (fit.naiv_var if vcov is None else vcov) @ L.T
     sides = L @ fit.beta
     w = float(sides @ llt_inv(middle) @ sides)
     return {"Wald_Stat": w, "DF": p - 1, "P_Val": 1.0 - (1.0 - pchisq_upper(w, p - 1))}
@@ -358,7 +386,7 @@ def score_test_gee(X_alt: np.ndarray, y: np.ndarray, null: GeemFit, n_vec, cor: 
     return {"Score_Stat": S, "DF": p_alt - 1, "P_Val": 1.0 - (1.0 - pchisq_upper(S, p_alt - 1))}
 
 
-def test_dynamic_gee(counts, pt, subject, genes=None, size_factor_offset=None, cor="ar1", M=5, gee_test="wald"):
+def test_dynamic_gee(counts, pt, subject, genes=None, size_factor_offset=None, cor="ar1", M=5, gee_test="wald", bias_correction=None):
     """testDynamic(is.gee = TRUE, gee.test = "wald") for one lineage; `subject` must be sorted (testDynamic.R:115)."""
     counts = np.asarray(counts)
     pt = np.asarray(pt, dtype=np.float64).reshape(-1)
@@ -369,6 +397,9 @@ def test_dynamic_gee(counts, pt, subject, genes=None, size_factor_offset=None, c
     off = None if size_factor_offset is None else np.log(1.0 / np.asarray(size_factor_offset, dtype=np.float64))
     G = counts.shape[0]
     genes = genes or [f"G{i}" for i in range(G)]
+    sandwich = bias_correction is not None          # testDynamic.R:195,243,286
+    if sandwich and cor not in ("ar1", "exchangeable"):
+        raise ValueError("Unrecognized correlation structure in biasCorrectGEE().")
     out = {}
     for g in range(G):
         y = counts[g].astype(np.float64)
@@ -378,16 +409,16 @@ def test_dynamic_gee(counts, pt, subject, genes=None, size_factor_offset=None, c
         try:
             if y.sum() == 0:
                 raise RuntimeError("all counts are zero")
-            null = geem(np.ones((y.size, 1)), y, n_vec, cor, off)
+            null = geem(np.ones((y.size, 1)), y, n_vec, cor, off, sandwich=sandwich)
         except (RuntimeError, np.linalg.LinAlgError, FloatingPointError):
             null = None
         try:
             if y.sum() == 0:
                 raise RuntimeError("all counts are zero")
             terms = forward_pass_gee(y, X, knots, n_vec, cor, M, trace=trace)
-            final = backward_pass_gee(y, X, knots, terms, n_vec, cor, trace)
-            fit = geem(build_design(final, X, knots), y, n_vec, cor, off)
-            se = np.sqrt(np.diag(fit.naiv_var))
+            final = backward_pass_gee(y, X, knots, terms, n_vec, cor, trace, sandwich)
+            fit = geem(build_design(final, X, knots), y, n_vec, cor, off, sandwich=sandwich)
+            se = np.sqrt(np.diag(fit.var if sandwich else fit.naiv_var))
             z = fit.beta / se
             rec.update({"Model_Status": f"MARGE model OK, null model {'OK' if null is not None else 'error'}",
                         "MARGE_Summary": {"term": [term_name(t, knots, "Lineage_A") for t in final],
@@ -402,13 +433,14 @@ def test_dynamic_gee(counts, pt, subject, genes=None, size_factor_offset=None, c
                     w = {"Wald_Stat": sc["Score_Stat"], "DF": sc["DF"], "P_Val": sc["P_Val"]}
                 rec["Test_Stat_Type"] = "Score"
             else:
-                w = wald_test_gee(fit)
+                w = wald_test_gee(fit, None if not sandwich else bias_correct_gee(fit, bias_correction, len(n_vec), y.size))
             rec.update({"Test_Stat": w["Wald_Stat"], "Degrees_Freedom": w["DF"], "P_Val": w["P_Val"]})
         except (RuntimeError, np.linalg.LinAlgError, FloatingPointError) as e:
             rec.update({"Model_Status": f"MARGE model error, null model {'OK' if null is not None else 'error'}",
                         "MARGE_Summary": None, "Test_Stat": np.nan, "Degrees_Freedom": np.nan, "P_Val": np.nan, "error": str(e)})
         rec["Null_Summary"] = (None if null is None else
-                               {"term": ["Intercept"], "estimate": [float(null.beta[0])], "std.error": [float(np.sqrt(null.naiv_var[0, 0]))],
+                               {"term": ["Intercept"], "estimate": [float(null.beta[0])],
+                                "std.error": [float(np.sqrt((null.var if sandwich else null.naiv_var)[0, 0]))],
                                 "alpha": null.alpha, "phi": null.phi})
         rec["_trace"] = trace
         out[genes[g]] = {"Lineage_A": rec}

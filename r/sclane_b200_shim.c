@@ -44,7 +44,8 @@ SEXP C_sclane_test_dynamic(SEXP counts, SEXP pt, SEXP sf, SEXP opts_) {
 
 /* GEE mode (testDynamic(is.gee = TRUE), testDynamic.R:66-70,235-244,296-301).
  * ids:   integer vector, one subject id per cell (as.integer(factor(id.vec))); cells ordered by subject (testDynamic.R:115)
- * opts:  integer vector c(M, approx_knot, n_gpus, cor_structure [0 independence, 1 exchangeable, 2 ar1], gee_test [0 wald, 1 score]) */
+ * opts:  integer vector c(M, approx_knot, n_gpus, cor_structure [0 independence, 1 exchangeable, 2 ar1], gee_test [0 wald, 1 score],
+ *        bias_correction [0 NULL, 1 kc, 2 df]) */
 SEXP C_sclane_test_dynamic_gee(SEXP counts, SEXP pt, SEXP ids, SEXP sf, SEXP opts_) {
   if (!isInteger(counts) || !isMatrix(counts)) Rf_error("expr.mat must be an integer matrix (cells x genes)");
   if (!isReal(pt) || !isMatrix(pt)) Rf_error("pt must be a double matrix (cells x lineages)");
@@ -58,6 +59,7 @@ SEXP C_sclane_test_dynamic_gee(SEXP counts, SEXP pt, SEXP ids, SEXP sf, SEXP opt
   o.mode = 1;
   if (LENGTH(opts_) >= 5) { o.M = INTEGER(opts_)[0]; o.approx_knot = INTEGER(opts_)[1]; o.n_gpus = INTEGER(opts_)[2];
                             o.gee_cor = INTEGER(opts_)[3]; o.gee_test = INTEGER(opts_)[4];
+                            if (LENGTH(opts_) >= 6) o.gee_bias_correction = INTEGER(opts_)[5];
                             for (int i = 0; i < o.n_gpus && i < SCLANE_MAX_GPUS; ++i) o.gpu_ids[i] = i; }
   SEXP out = PROTECT(allocVector(RAWSXP, (R_xlen_t)(n_genes * n_lin) * (R_xlen_t)sizeof(sclane_record)));
   SEXP info = PROTECT(allocVector(RAWSXP, (R_xlen_t)n_lin * (R_xlen_t)sizeof(sclane_lineage_info)));

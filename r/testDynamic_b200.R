@@ -6,7 +6,7 @@
 # signature of testDynamic() is unchanged; `n.cores` is kept for compatibility and a new `n.gpus` picks the devices.
 
 testDynamicB200 <- function(expr.mat, pt, genes, size.factor.offset = NULL, is.gee = FALSE, id.vec = NULL,
-                            cor.structure = "ar1", gee.test = "wald", n.potential.basis.fns = 5,
+                            cor.structure = "ar1", gee.test = "wald", gee.bias.correction.method = NULL, n.potential.basis.fns = 5,
                             approx.knot = TRUE, n.gpus = 0L) {
   # expr.mat: dense cells x genes integer matrix exactly as built at testDynamic.R:97
   storage.mode(expr.mat) <- "integer"
@@ -18,7 +18,8 @@ testDynamicB200 <- function(expr.mat, pt, genes, size.factor.offset = NULL, is.g
     raw <- .Call("C_sclane_test_dynamic_gee", expr.mat, pt_mat, as.integer(factor(id.vec, levels = unique(id.vec))),
                  size.factor.offset,
                  c(as.integer(n.potential.basis.fns), as.integer(approx.knot), as.integer(n.gpus), cor_code,
-                   as.integer(tolower(gee.test) == "score")))
+                   as.integer(tolower(gee.test) == "score"),
+                   if (is.null(gee.bias.correction.method)) 0L else match(tolower(gee.bias.correction.method), c("kc", "df"))))
   } else {
     raw <- .Call("C_sclane_test_dynamic", expr.mat, pt_mat, size.factor.offset,
                  c(as.integer(n.potential.basis.fns), as.integer(approx.knot), as.integer(n.gpus)))

@@ -44,7 +44,8 @@ class SclaneOpts(C.Structure):
         ("gee_cor", C.c_int32),
         ("gee_test", C.c_int32),
         ("force_per_cell", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("gee_bias_correction", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 

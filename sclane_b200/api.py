@@ -492,7 +492,9 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
         if gee_test not in ("wald", "score"):
             raise ValueError('gee.test must be one of "wald" or "score".')
         if gee_bias_correction_method is not None:
-            raise SclaneError(_abi_unsupported(), "GEE bias correction (sandwich variance) is not built into sclane_b200")
+            gee_bias_correction_method = str(gee_bias_correction_method).lower()
+            if gee_bias_correction_method not in ("kc", "df"):
+                raise ValueError("Unsupported bias correction method in waldTestGEE().")
         ids = np.asarray(id_vec)
         _, first = np.unique(ids, return_index=True)
         subject_id = np.unique(ids, return_inverse=True)[1].astype(np.int32)
@@ -517,6 +519,7 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
         o.mode = 1
         o.gee_cor = _abi.COR_CODES[cor_structure]
         o.gee_test = 1 if gee_test == "score" else 0
+        o.gee_bias_correction = {None: 0, "kc": 1, "df": 2}[gee_bias_correction_method]
     recs, infos = run_records(counts, pt_arr, size_factor_offset, o, subject_id=subject_id)
     n_lin = pt_arr.shape[1]
     res = ScLANE()

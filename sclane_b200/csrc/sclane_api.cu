@@ -404,7 +404,7 @@ void run_shard_gee(int device, const int32_t* h_counts, int64_t n_cells, int64_t
     prof.launches[SCLANE_STAGE_GATHER]++;
     GeeArgs A;
     A.lineage = d_lin; A.glin = d_glin; A.ys = d_ys; A.bid = d_bid; A.u = d_u; A.off = d_off; A.stats = d_stats; A.out = d_out;
-    A.n_genes = nb; A.M = o.M; A.use_offset = use_offset ? 1 : 0; A.cor = o.gee_cor; A.gee_test = o.gee_test; A.tols_score = o.tols_score; A.mean_off = GP.mean_off;
+    A.n_genes = nb; A.M = o.M; A.use_offset = use_offset ? 1 : 0; A.cor = o.gee_cor; A.gee_test = o.gee_test; A.sandwich = o.gee_bias_correction != 0 ? 1 : 0; A.tols_score = o.tols_score; A.mean_off = GP.mean_off;
     tm.mark(SCLANE_STAGE_GEE);
     k_gee<<<nb, kThreads, sizeof(GeeShared), s>>>(A);
     CK(cudaGetLastError());
@@ -420,7 +420,7 @@ void run_shard_gee(int device, const int32_t* h_counts, int64_t n_cells, int64_t
     for (int i = 0; i < nb; ++i) {
       GeeGeneOut go;
       go.st = h_out[i].st; go.alt = h_out[i].alt; go.null = h_out[i].null;
-      finalize_record_gee(go, L, o.gee_test, out[(b0 + i) * n_lineages + lin_idx]);
+      finalize_record_gee(go, L, o.gee_test, o.gee_bias_correction, GP.GL.S, out[(b0 + i) * n_lineages + lin_idx]);
     }
   }
 }
@@ -516,6 +516,8 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
     if (!subject_id || !h_counts) { set_err(errbuf, errlen, "GEE mode needs subject ids and host counts: call sclane_test_dynamic_gee()"); return SCLANE_ERR_ARG; }
     if (opts->M > SCLANE_GEE_PMAX) { set_err(errbuf, errlen, "GEE mode: M must be <= %d", SCLANE_GEE_PMAX); return SCLANE_ERR_ARG; }
     if (opts->gee_test != 0 && opts->gee_test != 1) { set_err(errbuf, errlen, "gee_test must be 0 (wald) or 1 (score)"); return SCLANE_ERR_ARG; }
+    if (opts->gee_bias_correction < 0 || opts->gee_bias_correction > 2) { set_err(errbuf, errlen, "Unsupported bias correction method in waldTestGEE()."); return SCLANE_ERR_ARG; }
+    if (opts->gee_bias_correction != 0 && opts->gee_cor == SCLANE_COR_INDEPENDENCE) { set_err(errbuf, errlen, "Unrecognized correlation structure in biasCorrectGEE()."); return SCLANE_ERR_ARG; }
     if (opts->gee_cor < SCLANE_COR_INDEPENDENCE || opts->gee_cor > SCLANE_COR_AR1) { set_err(errbuf, errlen, "Currently unsupported correlation structure."); return SCLANE_ERR_ARG; }
   } else if (subject_id) { set_err(errbuf, errlen, "subject ids given but opts->mode is not 1 (GEE)"); return SCLANE_ERR_ARG; }
   if ((!h_counts && !d_counts && !csc) || !pt || !out || n_cells <= 0 || n_genes <= 0 || n_lineages <= 0) {

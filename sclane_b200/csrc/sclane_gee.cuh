@@ -31,7 +31,9 @@ enum GeePass : int {
   GPASS_BETA = 1,     // updateBeta ingredients at beta: Z'R^-1 Z and Z'R^-1 r pieces
   GPASS_PREP1 = 2,    // exchangeable only: per-subject sums of t = sv * (S, mu B_1..)
   GPASS_PREP2 = 3,    // one subject: u = V^-1 S, Q = V^-1 Dn -> J11, a_i, bucket moments for the candidates
-  GPASS_YMOM = 4      // per-bucket sum y, sum y u into W.acc[b][5..6] (stat_out's B'y), once per gene
+  GPASS_YMOM = 4,     // per-bucket sum y, sum y u into W.acc[b][5..6] (stat_out's B'y), once per gene
+  GPASS_SAND = 5      // per-subject pieces of Z_i' R_i^-1 rr_i at beta (geeM getSandwich): ssum[i][0..p) = sum c_j z_j r_j,
+                      // [p..2p) = AR-1 neighbour sums / exchangeable sum z, [2p] = exchangeable sum r
 };
 
 struct GeeLineage {
@@ -52,7 +54,7 @@ struct GeeWork {
   double e1[GEE_PMAX];         // sum c_j z_j r_j             (PREP2: a_i of this subject)
   double e2[GEE_PMAX];         // sum_adj (z_j r_{j+1} + z_{j+1} r_j)
   double sc[4];                // RESID: [0] sum e^2, [1] sum_adj e_j e_{j+1}
-  double ssum[GEE_SMAX][GEE_PMAX + 1];   // per-subject sums: RESID [.][0] = sum e; BETA (exch) z (p) and r; PREP1 t (1 + p)
+  double ssum[GEE_SMAX][2 * GEE_PMAX + 1];   // per-subject sums: RESID [.][0] = sum e; BETA (exch) z (p) and r; PREP1 t (1 + p); SAND
   double Gm[NBMAX][2];         // PREP2, this subject: sum g, sum g u per bucket, g = mu * u_vec
   double Hm[NBMAX][2 * GEE_PMAX];   // PREP2, all subjects so far: sum h_l, sum h_l u per bucket, h_l = mu * Q_l
   // ---- geem state
@@ -217,9 +219,43 @@ SC_HDN bool gee_invert(int n, const double* A, double* out) {
   return true;
 }
 
+// Robust (sandwich) variance of geeM::geem(sandwich = TRUE): var = hess^-1 (sum_i e_i e_i') hess^-T with
+// e_i = Z_i' (R_i^-1 / phi) rr_i from a GPASS_SAND pass at the final beta and hess the hessian of the last inner step.
+// out: row-major p x p (stride GEE_PMAX).  Leader only.  false if hess is computationally singular.
+SC_HDN bool gee_sandwich(const GeeLineage& GL, const Model& m, const GeeWork& G, double* out) {
+  const int p = m.n;
+  const double al = G.alpha, ph = G.phi;
+  double num[GEE_PMAX * GEE_PMAX], Hinv[GEE_PMAX * GEE_PMAX], tmp[GEE_PMAX * GEE_PMAX];
+  for (int j = 0; j < p * GEE_PMAX; ++j) num[j] = 0.0;
+  for (int i = 0; i < GL.S; ++i) {
+    double e[GEE_PMAX];
+    const int n = GL.sstart[i + 1] - GL.sstart[i];
+    for (int j = 0; j < p; ++j) {
+      if (G.cor == GEE_AR1) e[j] = (G.ssum[i][j] - al * G.ssum[i][p + j]) / ((1.0 - al * al) * ph);
+      else if (G.cor == GEE_EXCH) {
+        const double kap = al / (1.0 + (double)(n - 1) * al);
+        e[j] = (G.ssum[i][j] - kap * G.ssum[i][p + j] * G.ssum[i][2 * p]) / ((1.0 - al) * ph);
+      } else e[j] = G.ssum[i][j] / ph;
+    }
+    for (int j = 0; j < p; ++j) for (int l = 0; l < p; ++l) num[j * GEE_PMAX + l] += e[j] * e[l];
+  }
+  if (!gee_invert(p, G.hess, Hinv)) return false;
+  for (int j = 0; j < p; ++j) for (int l = 0; l < p; ++l) {
+    double s = 0.0;
+    for (int q = 0; q < p; ++q) s += Hinv[j * GEE_PMAX + q] * num[q * GEE_PMAX + l];
+    tmp[j * GEE_PMAX + l] = s;
+  }
+  for (int j = 0; j < p; ++j) for (int l = 0; l < p; ++l) {
+    double s = 0.0;
+    for (int q = 0; q < p; ++q) s += tmp[j * GEE_PMAX + q] * Hinv[l * GEE_PMAX + q];     // x hess^-T
+    out[j * GEE_PMAX + l] = s;
+  }
+  return true;
+}
+
 template <class E>
 SC_HDN bool geem_fit(E& ex, const Lineage& L, const GeeLineage& GL, const Model& m, const GeneStats& gs, Work& W, GeeWork& G,
-                     double mean_offset) {
+                     double mean_offset, bool sandwich = false) {
   const int p = m.n;
   const double N = (double)L.N;
   coop_set_model(ex, L, m, W);
@@ -293,6 +329,11 @@ SC_HDN bool geem_fit(E& ex, const Lineage& L, const GeeLineage& GL, const Model&
     if (W.flag == 1) break;
   }
   ex.sync();
+  if (sandwich) {
+    coop_set_eta(ex, L, m, W, W.beta);
+    if (ex.leader()) W.passes++;
+    ex.template gee_pass<GPASS_SAND>();
+  }
   return true;
 }
 
@@ -464,15 +505,17 @@ SC_HDN void gee_sweep(E& ex, const Lineage& L, const GeeLineage& GL, const Model
 struct GeeResult {
   double coef[GEE_PMAX];
   double cov[GEE_PMAX * GEE_PMAX];     // naiv.var, row-major p x p (stride GEE_PMAX)
+  double cov_robust[GEE_PMAX * GEE_PMAX];   // geem $var (sandwich), only when the fit was made with sandwich = TRUE
   double alpha, phi;
   double score_stat;                   // scoreTestGEE statistic (alt only, gee_test = 1); NaN when not computed
   int converged, niter, ok;
 };
 
 template <class E>
-SC_HDN void gee_store_fit(E& ex, const Model& m, Work& W, GeeWork& G, GeeResult* out) {
+SC_HDN void gee_store_fit(E& ex, const GeeLineage& GL, const Model& m, Work& W, GeeWork& G, bool sandwich, GeeResult* out) {
   if (ex.leader()) {
     out->ok = gee_invert(m.n, G.hess, out->cov) ? 1 : 0;
+    if (sandwich && out->ok) out->ok = gee_sandwich(GL, m, G, out->cov_robust) ? 1 : 0;
     for (int j = 0; j < m.n; ++j) out->coef[j] = W.beta[j];
     out->alpha = G.alpha; out->phi = G.phi; out->converged = G.converged; out->niter = G.niter;
     out->score_stat = nan("");
@@ -485,7 +528,8 @@ SC_HDN void gee_store_fit(E& ex, const Model& m, Work& W, GeeWork& G, GeeResult*
 // executor provides in W.acc[b][5..6] (sum y, sum y u) before the call.
 template <class E>
 SC_HDN void gene_gee(E& ex, const Lineage& L, const GeeLineage& GL, const GeneStats& gstat, GeneState& st, Work& W, GeeWork& G,
-                     int M, double tols_score, bool use_offset, double mean_offset, int gee_test, GeeResult* alt, GeeResult* null) {
+                     int M, double tols_score, bool use_offset, double mean_offset, int gee_test, bool sandwich, GeeResult* alt,
+                     GeeResult* null) {
   ex.sync();
   if (ex.leader()) { alt->ok = 0; null->ok = 0; st.fin.n = 0; W.use_offset = 0; }
   ex.sync();
@@ -521,12 +565,13 @@ SC_HDN void gene_gee(E& ex, const Lineage& L, const GeeLineage& GL, const GeneSt
     if (ex.leader()) { W.bw_cur = st.fwd; W.bw_models[0] = st.fwd; W.bw_cum = 0.0; }
     ex.sync();
     for (int i = 1; i <= ncol - 1; ++i) {
-      const bool ok = geem_fit(ex, L, GL, W.bw_cur, gstat, W, G, 0.0);
+      const bool ok = geem_fit(ex, L, GL, W.bw_cur, gstat, W, G, 0.0, sandwich);
       if (ex.leader()) {
         double wald[PMAX], cov[GEE_PMAX * GEE_PMAX];
         const Model cur = W.bw_cur;
         const int nw = cur.n - 1;
-        const bool inv_ok = ok && gee_invert(cur.n, G.hess, cov);
+        // summary(fit)$wald.test: beta / se.model, or beta / se.robust for a fit with a sandwich variance
+        const bool inv_ok = ok && (sandwich ? gee_sandwich(GL, cur, G, cov) : gee_invert(cur.n, G.hess, cov));
         if (!inv_ok) st.error |= SCLANE_NOTE_NUMERIC;                   // geem / solve() error inside try() -> MARGE model error
         for (int j = 1; j < cur.n; ++j) {
           const double se = sqrt(cov[j * GEE_PMAX + j]);
@@ -574,10 +619,10 @@ SC_HDN void gene_gee(E& ex, const Lineage& L, const GeeLineage& GL, const GeneSt
   // ---- null model (testDynamic.R:235-244) and final model (marge2.R:831-838), both with the offset
   if (ex.leader()) { W.use_offset = use_offset ? 1 : 0; W.bw_cur.n = 1; W.bw_cur.kind[0] = SCLANE_TERM_INTERCEPT; W.bw_cur.knot[0] = 0; }
   ex.sync();
-  if (geem_fit(ex, L, GL, W.bw_cur, gstat, W, G, use_offset ? mean_offset : 0.0)) gee_store_fit(ex, W.bw_cur, W, G, null);
+  if (geem_fit(ex, L, GL, W.bw_cur, gstat, W, G, use_offset ? mean_offset : 0.0, sandwich)) gee_store_fit(ex, GL, W.bw_cur, W, G, sandwich, null);
   if (st.fin.n >= 1 && !(st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC))) {
     if (st.fin.n == 1) { if (ex.leader()) *alt = *null; ex.sync(); }
-    else if (geem_fit(ex, L, GL, st.fin, gstat, W, G, use_offset ? mean_offset : 0.0)) gee_store_fit(ex, st.fin, W, G, alt);
+    else if (geem_fit(ex, L, GL, st.fin, gstat, W, G, use_offset ? mean_offset : 0.0, sandwich)) gee_store_fit(ex, GL, st.fin, W, G, sandwich, alt);
     ex.sync();
     // scoreTestGEE (scoreTestGEE.R:50-128): with K = diag(mu), V = A^1/2 R A^1/2 at the NULL fit, U = X'K V^-1 r / phi and
     // V_U = X'K V^-1 K X are exactly geem's estimating equation and (phi x) hessian for the alternative design evaluated at

@@ -30,7 +30,7 @@ struct GeeArgs {
   const double* off;             // [Npad] or nullptr
   const GeneStats* stats;
   GeeGeneOutDev* out;
-  int n_genes, M, use_offset, cor, gee_test;
+  int n_genes, M, use_offset, cor, gee_test, sandwich;
   double tols_score, mean_off;
 };
 
@@ -218,6 +218,43 @@ struct GeeDevExec {
     }
   }
 
+  // per-subject pieces of the sandwich's e_i = Z_i' R_i^-1 rr_i (combined by gee_sandwich)
+  template <int P>
+  __device__ __noinline__ void pass_sand() {
+    const Work& W = S->W;
+    GeeWork& G = S->G;
+    const GeeLineage& GL = S->GL;
+    const bool exch = G.cor == GEE_EXCH, ar1 = G.cor == GEE_AR1;
+    for (int i = 0; i < GL.S; ++i) {
+      const int s0 = GL.sstart[i], s1 = GL.sstart[i + 1], n = s1 - s0;
+      double v1[P], v2[P + 1];
+#pragma unroll
+      for (int k = 0; k < P; ++k) v1[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k <= P; ++k) v2[k] = 0.0;
+      for (int j = s0 + threadIdx.x; j < s1; j += kThreads) {
+        GeeCell c;
+        gee_cell<false>(W, G, P, y[j], bid[j], u[j], offset(j), c);
+        const double cj = ar1 ? ar1_cj(j - s0, n, G.alpha) : 1.0;
+#pragma unroll
+        for (int a = 0; a < P; ++a) v1[a] += cj * c.z[a] * c.r;
+        if (ar1 && j > s0) {
+          GeeCell cp;
+          gee_cell<false>(W, G, P, y[j - 1], bid[j - 1], u[j - 1], offset(j - 1), cp);
+#pragma unroll
+          for (int a = 0; a < P; ++a) v2[a] += c.z[a] * cp.r + cp.z[a] * c.r;
+        }
+        if (exch) {
+#pragma unroll
+          for (int a = 0; a < P; ++a) v2[a] += c.z[a];
+          v2[P] += c.r;
+        }
+      }
+      block_reduce<P>(v1, &G.ssum[i][0], false);
+      block_reduce<P + 1>(v2, &G.ssum[i][P], false);
+    }
+  }
+
   template <int P>
   __device__ __noinline__ void pass_prep1() {
     const Work& W = S->W;
@@ -310,6 +347,14 @@ struct GeeDevExec {
         case 4: pass_beta<4>(); break;
         default: pass_beta<5>(); break;
       }
+    } else if (GP == GPASS_SAND) {
+      switch (p) {
+        case 1: pass_sand<1>(); break;
+        case 2: pass_sand<2>(); break;
+        case 3: pass_sand<3>(); break;
+        case 4: pass_sand<4>(); break;
+        default: pass_sand<5>(); break;
+      }
     } else if (GP == GPASS_PREP1) {
       switch (p) {
         case 1: pass_prep1<1>(); break;
@@ -365,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gee(GeeArgs A) {
   __syncthreads();
   const size_t row = (size_t)g * (size_t)S->L.Npad;
   GeeDevExec ex{S, A.ys + row, A.bid, A.u, A.off};
-  gene_gee(ex, S->L, S->GL, S->gs, S->st, S->W, S->G, A.M, A.tols_score, A.use_offset != 0, A.mean_off, A.gee_test, &A.out[g].alt, &A.out[g].null);
+  gene_gee(ex, S->L, S->GL, S->gs, S->st, S->W, S->G, A.M, A.tols_score, A.use_offset != 0, A.mean_off, A.gee_test, A.sandwich != 0, &A.out[g].alt, &A.out[g].null);
   __syncthreads();
   if (threadIdx.x == 0) S->st.passes += S->W.passes;
   __syncthreads();

@@ -57,7 +57,7 @@ struct GeeGeneOut {
   GeeResult alt, null;
 };
 
-inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_test, sclane_record& r) {
+inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_test, int bias_correction, int n_subjects, sclane_record& r) {
   const double NaN = std::numeric_limits<double>::quiet_NaN();
   GeneOut dummy;
   std::memset(&dummy, 0, sizeof(dummy));
@@ -70,8 +70,10 @@ inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_t
   r.status = (marge_ok ? SCLANE_MARGE_OK : 0) | (null_ok ? SCLANE_NULL_OK : 0);
   r.marge_notes = st.error | ((marge_ok && !g.alt.converged) ? SCLANE_NOTE_NOT_CONVERGED : 0);
   r.null_notes = null_ok ? (g.null.converged ? 0 : SCLANE_NOTE_NOT_CONVERGED) : (st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
+  const bool sandwich = bias_correction != 0;          // testDynamic.R:195,243,286: sandwich.var = !is.null(gee.bias.correction.method)
   if (marge_ok) {
     const int p = st.fin.n;
+    const double* V = sandwich ? g.alt.cov_robust : g.alt.cov;      // pullMARGESummary.R:33-37,46: $var / se.robust, else naive
     r.n_terms = p;
     for (int j = 0; j < p; ++j) {
       r.term_kind[j] = st.fin.kind[j];
@@ -81,10 +83,10 @@ inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_t
         r.term_label[j] = r_signif(r.term_knot[j], 4);
       }
       r.coef[j] = g.alt.coef[j];
-      r.se[j] = std::sqrt(g.alt.cov[j * GEE_PMAX + j]);
+      r.se[j] = std::sqrt(V[j * GEE_PMAX + j]);
       r.z[j] = r.coef[j] / r.se[j];
       r.p[j] = r_round(pnorm_two_sided(r.z[j]), 1e8);         // summary.geem() rounds its p-values to 8 digits
-      for (int l = 0; l < p; ++l) r.cov[j * p + l] = g.alt.cov[j * GEE_PMAX + l];
+      for (int l = 0; l < p; ++l) r.cov[j * p + l] = V[j * GEE_PMAX + l];
     }
     r.gee_alpha = g.alt.alpha; r.gee_phi = g.alt.phi;
     r.gee_converged = g.alt.converged; r.gee_iters = g.alt.niter;
@@ -94,8 +96,13 @@ inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_t
       // scoreTestGEE(): statistic from the device; NA when the null model failed (scoreTestGEE.R:34-39)
       if (null_ok) { r.test_stat = g.alt.score_stat; r.df = (double)(p - 1); r.p_val = 1.0 - (1.0 - pchisq_upper(r.test_stat, r.df)); }
     } else {
+      // biasCorrectGEE.R: "df" n_s / (n_s - p) (unchanged when p >= n_s); "kc" (n_s / (n_s - 1)) / (1 - tr(H) / n) with
+      // tr(H) = p (H is a rank-p projection); both scale the sandwich variance
+      double factor = 1.0;
+      if (bias_correction == 2 && p < n_subjects) factor = (double)n_subjects / (double)(n_subjects - p);
+      if (bias_correction == 1) factor = ((double)n_subjects / ((double)n_subjects - 1.0)) / (1.0 - (double)p / (double)L.N);
       double mid[GEE_PMAX * GEE_PMAX], inv[GEE_PMAX * GEE_PMAX];
-      for (int j = 1; j < p; ++j) for (int l = 1; l < p; ++l) mid[(j - 1) * GEE_PMAX + (l - 1)] = g.alt.cov[j * GEE_PMAX + l];
+      for (int j = 1; j < p; ++j) for (int l = 1; l < p; ++l) mid[(j - 1) * GEE_PMAX + (l - 1)] = factor * V[j * GEE_PMAX + l];
       gee_llt_inverse(p - 1, mid, inv);
       double w = 0.0;
       for (int j = 1; j < p; ++j) for (int l = 1; l < p; ++l) w += g.alt.coef[j] * inv[(j - 1) * GEE_PMAX + (l - 1)] * g.alt.coef[l];
@@ -106,7 +113,7 @@ inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_t
   }
   if (null_ok) {
     r.null_coef = g.null.coef[0];
-    r.null_se = std::sqrt(g.null.cov[0]);
+    r.null_se = std::sqrt(sandwich ? g.null.cov_robust[0] : g.null.cov[0]);
     r.null_z = r.null_coef / r.null_se;
     r.null_p = r_round(pnorm_two_sided(r.null_z), 1e8);
     r.null_gee_alpha = g.null.alpha; r.null_gee_phi = g.null.phi;

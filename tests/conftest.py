@@ -92,7 +92,7 @@ def emu():
         assert rc == 0
         return recs, infos
 
-    def run_gee(counts, pt, subject, size_factor=None, cor="ar1", M=5, gee_test="wald"):
+    def run_gee(counts, pt, subject, size_factor=None, cor="ar1", M=5, gee_test="wald", bias_correction=None):
         counts = np.ascontiguousarray(counts, dtype=np.int32)
         pt = np.asarray(pt, dtype=np.float64)
         if pt.ndim == 1:
@@ -105,6 +105,7 @@ def emu():
         o.mode = 1
         o.gee_cor = _abi.COR_CODES[cor]
         o.gee_test = 1 if gee_test == "score" else 0
+        o.gee_bias_correction = {None: 0, "kc": 1, "df": 2}[bias_correction]
         sid = np.ascontiguousarray(np.unique(np.asarray(subject), return_inverse=True)[1], dtype=np.int32)
         recs = (_abi.SclaneRecord * (G * nl))()
         infos = (_abi.SclaneLineageInfo * nl)()

@@ -250,6 +250,24 @@ struct GeeHostExec {
       }
       return;
     }
+    if (GP == GPASS_SAND) {
+      for (int i = 0; i < GL->S; ++i) {
+        for (int k = 0; k <= 2 * GEE_PMAX; ++k) G->ssum[i][k] = 0.0;
+        const int s0 = GL->sstart[i], n = GL->sstart[i + 1] - s0;
+        GeeCell pc;
+        for (int q = 0; q < n; ++q) {
+          const int j = s0 + q;
+          GeeCell c;
+          gee_cell<false>(*W, *G, pp, y[j], bid[j], u[j], offset(j), c);
+          const double cj = G->cor == GEE_AR1 ? ar1_cj(q, n, G->alpha) : 1.0;
+          for (int a = 0; a < pp; ++a) G->ssum[i][a] += cj * c.z[a] * c.r;
+          if (G->cor == GEE_AR1 && q > 0) for (int a = 0; a < pp; ++a) G->ssum[i][pp + a] += c.z[a] * pc.r + pc.z[a] * c.r;
+          if (G->cor == GEE_EXCH) { for (int a = 0; a < pp; ++a) G->ssum[i][pp + a] += c.z[a]; G->ssum[i][2 * pp] += c.r; }
+          pc = c;
+        }
+      }
+      return;
+    }
     if (GP == GPASS_PREP1) {
       for (int i = 0; i < GL->S; ++i) {
         for (int k = 0; k <= GEE_PMAX; ++k) G->ssum[i][k] = 0.0;
@@ -321,9 +339,9 @@ extern "C" int emu_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int6
       std::memset(&G, 0, sizeof(G));
       G.cor = opts->gee_cor;
       GeeHostExec ex{&W, &G, &L, &GP.GL, y.data(), GP.bid.data(), GP.u.data(), GP.off.empty() ? nullptr : GP.off.data(), PassTabs()};
-      gene_gee(ex, L, GP.GL, gs, go.st, W, G, opts->M, opts->tols_score, size_factor != nullptr, GP.mean_off, opts->gee_test, &go.alt, &go.null);
+      gene_gee(ex, L, GP.GL, gs, go.st, W, G, opts->M, opts->tols_score, size_factor != nullptr, GP.mean_off, opts->gee_test, opts->gee_bias_correction != 0, &go.alt, &go.null);
       go.st.passes = W.passes;
-      finalize_record_gee(go, L, opts->gee_test, out[g * n_lineages + l]);
+      finalize_record_gee(go, L, opts->gee_test, opts->gee_bias_correction, GP.GL.S, out[g * n_lineages + l]);
     }
   }
   return 0;

@@ -168,3 +168,30 @@ def test_gee_score_test_gpu_vs_dense_oracle():
     recs, _ = api.run_records(counts, pt, sf, o, subject_id=subject.astype(np.int32))
     ref = oracle_gee(counts, pt, subject, genes, sf, "ar1", gee_test="score")
     assert _compare(recs, ref, genes) == []
+
+
+@pytest.mark.parametrize("method,cor", [("kc", "ar1"), ("df", "exchangeable")])
+def test_gee_bias_corrected_sandwich_core_vs_dense_oracle(emu, method, cor):
+    """gee.bias.correction.method: every geem fit of the path carries geeM's sandwich variance (backward Wald, summaries) and
+    waldTestGEE() uses biasCorrectGEE()'s scaled sandwich."""
+    counts, pt, subject, sf = _gee_data(seed=13, sizes=(120, 100, 90, 110, 80), n_genes=5)
+    genes = [f"G{i}" for i in range(counts.shape[0])]
+    recs, _ = emu.run_gee(counts, pt, subject, sf, cor, bias_correction=method)
+    ref = oracle_gee(counts, pt, subject, genes, sf, cor, bias_correction=method)
+    assert sum(ref[g]["Lineage_A"]["MARGE_Summary"] is not None for g in genes) >= 3
+    assert _compare(recs, ref, genes) == []
+
+
+@pytest.mark.gpu
+def test_gee_bias_corrected_sandwich_gpu_vs_dense_oracle():
+    from sclane_b200 import _abi, api
+    counts, pt, subject, sf = _gee_data(seed=13, sizes=(120, 100, 90, 110, 80), n_genes=5)
+    genes = [f"G{i}" for i in range(counts.shape[0])]
+    for method, code, cor in (("kc", 1, "ar1"), ("df", 2, "exchangeable")):
+        o = api._opts(gpu_ids=[0])
+        o.mode = 1
+        o.gee_cor = _abi.COR_CODES[cor]
+        o.gee_bias_correction = code
+        recs, _ = api.run_records(counts, pt, sf, o, subject_id=subject.astype(np.int32))
+        ref = oracle_gee(counts, pt, subject, genes, sf, cor, bias_correction=method)
+        assert _compare(recs, ref, genes) == []
