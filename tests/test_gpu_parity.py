@@ -365,3 +365,15 @@ def test_sparse_csc_input_equals_dense():
     rc = lib().sclane_test_dynamic_csc(indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, 6000, 40, ptc.ctypes.data, 2, None,
                                        C.byref(o), recs, None, err, 512)
     assert rc == 1 and b"out of range" in err.value
+
+
+def test_default_workload_cell_count_vs_oracle():
+    """BASELINE configs[4]'s cell count (200,000 cells, 10,000 distinct abscissae -> X-compressed route): six genes of the
+    bench generator against the dense oracle (about 7 s of numpy per gene)."""
+    import sclane_b200 as sb
+    from sclane_b200 import synth
+    counts, pt, _ = synth.make_counts(6, 200000, seed=312)
+    res = sb.testDynamic(counts, pt, n_gpus=1, preds="none")
+    assert res.profile["ms"]["comp_final"] > 0
+    ref = oracle_test_dynamic(np.asarray(counts), np.asarray(pt, dtype=np.float64).reshape(-1), list(res.keys()), None, keep_preds=False)
+    _compare_with_oracle(res, ref)
