@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
     ap.add_argument("--genes", type=int, default=0, help="total genes (default: the config's)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="genes of the CPU-baseline sample (0 = skip, -1 = automatic)")
+    ap.add_argument("--pageable", action="store_true", help="e2e from pageable (not pinned) host memory, like an R caller's matrix")
+    ap.add_argument("--h2d-mode", type=int, default=0, help="sclane_opts.h2d_mode for the e2e call: 0 auto, 1 direct int32, 2 staged uint16")
     ap.add_argument("--per-cell", action="store_true", help="force the per-cell kernels (no X-compression): profiling of k_sweep_moments")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
@@ -272,7 +274,7 @@ def main():
     # ---- end-to-end measurement (e2e): host buffers, copies inside the timed region ----------------
     e2e_note = None
     try:
-        h_counts = torch.empty((G, N), dtype=torch.int32, pin_memory=True)
+        h_counts = torch.empty((G, N), dtype=torch.int32, pin_memory=not args.pageable)
         h_counts.copy_(d_counts)
         Ge = G
     except RuntimeError as exc:       # pinned allocation refused: measure e2e on a bounded prefix of the shard
@@ -282,8 +284,10 @@ def main():
     torch.cuda.synchronize()
     h_np = h_counts.numpy()
 
+    opts_host = sb.api._opts(gpu_ids=[local], force_per_cell=args.per_cell, h2d_mode=args.h2d_mode)
+
     def step_host():
-        return sb.run_records(h_np, pt, None, opts)
+        return sb.run_records(h_np, pt, None, opts_host)
 
     step_host()
     barrier()
@@ -342,6 +346,7 @@ def main():
                        "sharding": f"contiguous gene blocks x{world}, no collective",
                        "l2": "flushed between timed steps (256 MiB write); per-step working set >> 126 MB L2"},
             "e2e": {"value": e2e_val, "unit": "genes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d / args.steps,
+                    "host_buffer": "pageable" if args.pageable else "pinned", "h2d_mode": args.h2d_mode,
                     "d2h_bytes_per_step": d2h / args.steps, **({"note": e2e_note} if e2e_note else {})},
             "gpu_launches": int(launches),
             "wall_ms_per_step": wall_step,

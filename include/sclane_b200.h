@@ -86,7 +86,11 @@ typedef struct sclane_opts {
   int32_t gee_bias_correction; /* gee.bias.correction.method (testDynamic.R:67): 0 = NULL (model-based variance), 1 = "kc",
                                  2 = "df"; != 0 switches every GEE fit of the path to the sandwich variance
                                  (testDynamic.R:195,243,286) and waldTestGEE() to biasCorrectGEE() (ar1 / exchangeable only) */
-  int32_t reserved[4];
+  int32_t h2d_mode;           /* host -> device transfer of the counts: 0 = automatic (staged for a large pageable buffer, else direct), 1 = direct (int32, straight from the caller's
+                                 buffer), 2 = staged (host threads narrow each gene batch to uint16 into pinned staging buffers while
+                                 the previous batch is in flight: half the PCIe bytes, and full PCIe speed from pageable R memory);
+                                 a batch holding a count > 65534 or < 0 always goes direct */
+  int32_t reserved[3];
 } sclane_opts;
 
 /* One record per (gene, lineage): everything testDynamic() returns for that pair except the

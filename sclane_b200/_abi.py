@@ -45,7 +45,8 @@ class SclaneOpts(C.Structure):
         ("gee_test", C.c_int32),
         ("force_per_cell", C.c_int32),
         ("gee_bias_correction", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("h2d_mode", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 

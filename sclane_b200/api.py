@@ -132,7 +132,7 @@ def get_profile() -> dict:
 
 
 def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None, tols_score=1e-5,
-          n_gpus=0, gpu_ids=None, genes_per_batch=0, verbose=False, force_per_cell=False) -> _abi.SclaneOpts:
+          n_gpus=0, gpu_ids=None, genes_per_batch=0, verbose=False, force_per_cell=False, h2d_mode=0) -> _abi.SclaneOpts:
     o = _abi.default_opts()
     o.M = int(n_potential_basis_fns)
     o.approx_knot = 1 if approx_knot else 0
@@ -150,6 +150,7 @@ def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None
     o.genes_per_batch = int(genes_per_batch)
     o.verbose = 1 if verbose else 0
     o.force_per_cell = 1 if force_per_cell else 0
+    o.h2d_mode = int(h2d_mode)
     return o
 
 

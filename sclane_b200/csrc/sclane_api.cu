@@ -170,6 +170,25 @@ void launch_sweep(const StageArgs& A, bool first, cudaStream_t s, EventTimer* tm
 
 int forward_iterations(int M) { return (M - 1 + 1) / 2; }   // m = 1, 3, 5, ... until m >= M (marge2.R:752-757)
 
+// Host side of the staged transfer: int32 -> uint16 with a pool of threads.  Returns false (and the caller sends the batch
+// as int32) when a value does not fit.
+bool narrow_to_u16(const int32_t* src, size_t n, uint16_t* dst) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = hw == 0 ? 4 : std::min<unsigned>(hw, 16);
+  if (n < ((size_t)1 << 22)) nt = 1;
+  std::vector<int> bad(nt, 0);
+  auto work = [&](size_t t) {
+    const size_t a = n * t / nt, b = n * (t + 1) / nt;
+    unsigned acc = 0;
+    for (size_t i = a; i < b; ++i) { const uint32_t v = (uint32_t)src[i]; acc |= (v > 65534u) ? 1u : 0u; dst[i] = (uint16_t)v; }
+    bad[t] = (int)acc;
+  };
+  if (nt == 1) work(0);
+  else { std::vector<std::thread> th; for (size_t t = 0; t < nt; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+  for (int b : bad) if (b) return false;
+  return true;
+}
+
 // Run genes [g0, g1) of one lineage on one device.  Exactly one of h_counts / d_counts is non-null;
 // both are gene-major with leading dimension n_cells.  Records go to out[(g - out_g0) * n_lineages + lin_idx].
 void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int64_t n_cells, int64_t g0, int64_t g1,
@@ -204,6 +223,19 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   if (B > G) B = G;
   if (B < 1) throw CudaFail{"not enough free device memory for a single gene"};
   const int64_t n_batches = (G + B - 1) / B;
+  // staged transfer (see sclane_opts.h2d_mode): automatic = when the copy is big enough to matter and pipelined
+  // automatic = pageable caller memory (an R integer matrix): cudaMemcpyAsync from it is staged by the driver at ~12 GB/s,
+  // the library's own threads + pinned buffers reach the PCIe rate; a pinned caller buffer (bench.py) is copied directly --
+  // narrowing 16 GB on this box's 16 host cores is no faster than sending it
+  bool pageable = false;
+  if (h_counts && o.h2d_mode == 0) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h_counts) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+  }
+  const bool staged = h_counts && (o.h2d_mode == 2 || (o.h2d_mode == 0 && pageable && n_batches >= 2 && (double)G * (double)n_cells * 4.0 >= 256e6));
+  uint16_t* h_stage[2] = {nullptr, nullptr};
+  int fmt16[2] = {0, 0};
   int* d_raw2[2] = {nullptr, nullptr};
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   cudaStream_t cs = nullptr;
@@ -212,6 +244,10 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     cs = pool.copy_stream;
     d_raw2[0] = (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4);
     d_raw2[1] = n_batches > 1 ? (int*)pool.get("raw_b", (size_t)B * (size_t)n_cells * 4) : d_raw2[0];
+    if (staged) {
+      h_stage[0] = (uint16_t*)pool.get("stage_a", (size_t)B * (size_t)n_cells * 2, true);
+      h_stage[1] = n_batches > 1 ? (uint16_t*)pool.get("stage_b", (size_t)B * (size_t)n_cells * 2, true) : h_stage[0];
+    }
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
@@ -224,11 +260,18 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   auto issue_h2d = [&](int64_t k) {
     const int buf = (int)(k & 1);
     const int64_t kb0 = g0 + k * B, kb1 = std::min<int64_t>(kb0 + B, g1);
+    const size_t n_el = (size_t)(kb1 - kb0) * (size_t)n_cells;
+    const int32_t* src = h_counts + (size_t)kb0 * (size_t)n_cells;
+    fmt16[buf] = 0;
+    if (staged) {
+      if (k >= 2) CK(cudaEventSynchronize(ev_h2d[buf]));                // the H2D of batch k - 2 has left this staging buffer
+      fmt16[buf] = narrow_to_u16(src, n_el, h_stage[buf]) ? 1 : 0;
+    }
     if (k >= 2) CK(cudaStreamWaitEvent(cs, ev_free[buf], 0));          // the gather of batch k - 2 has consumed this buffer
-    CK(cudaMemcpyAsync(d_raw2[buf], h_counts + (size_t)kb0 * (size_t)n_cells, (size_t)(kb1 - kb0) * (size_t)n_cells * 4,
-                       cudaMemcpyHostToDevice, cs));
+    if (fmt16[buf]) CK(cudaMemcpyAsync(d_raw2[buf], h_stage[buf], n_el * 2, cudaMemcpyHostToDevice, cs));
+    else CK(cudaMemcpyAsync(d_raw2[buf], src, n_el * 4, cudaMemcpyHostToDevice, cs));
     CK(cudaEventRecord(ev_h2d[buf], cs));
-    prof.h2d_bytes += (double)(kb1 - kb0) * (double)n_cells * 4.0;
+    prof.h2d_bytes += (double)n_el * (fmt16[buf] ? 2.0 : 4.0);
     prof.launches[SCLANE_STAGE_COPY]++;
   };
   if (h_counts) {
@@ -254,8 +297,8 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     const int nb = (int)(b1 - b0);
     tm.mark(SCLANE_STAGE_COPY);             // on the compute stream this interval is the EXPOSED wait for the batch's H2D
     const int* raw = nullptr;
+    const bool raw16 = h_counts && fmt16[kb & 1];
     if (h_counts) {
-      if (kb + 1 < n_batches) issue_h2d(kb + 1);
       CK(cudaStreamWaitEvent(s, ev_h2d[kb & 1], 0));
       raw = d_raw2[kb & 1];
     } else {
@@ -268,9 +311,11 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       if (K < 1) K = 1;
       if (K > 32) K = 32;
       while (K > 1 && (((L.Npad / K + 127) / 128) * 128) * (K - 1) >= L.Npad) --K;      // no empty trailing part
-      k_gather_copy<<<(unsigned)((size_t)nb * K), kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, nb, K);
+      if (raw16) k_gather_copy<unsigned short><<<(unsigned)((size_t)nb * K), kThreads, 0, s>>>((const unsigned short*)raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, nb, K);
+      else k_gather_copy<int><<<(unsigned)((size_t)nb * K), kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, nb, K);
     } else {
-      k_gather_stats<<<nb, kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
+      if (raw16) k_gather_stats<unsigned short><<<nb, kThreads, 0, s>>>((const unsigned short*)raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
+      else k_gather_stats<int><<<nb, kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
     }
     CK(cudaGetLastError());
     if (h_counts) CK(cudaEventRecord(ev_free[kb & 1], s));
@@ -328,6 +373,8 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.d2h_bytes += (double)nb * sizeof(GeneOutDev);
     prof.launches[SCLANE_STAGE_COPY]++;
     tm.mark(-1);
+    // everything of batch kb is queued: prepare and send batch kb + 1 while the GPU works (host narrowing + copy stream)
+    if (h_counts && kb + 1 < n_batches) issue_h2d(kb + 1);
     CK(cudaStreamSynchronize(s));
     tm.collect(prof);
     for (int i = 0; i < nb; ++i) {
@@ -398,7 +445,7 @@ void run_shard_gee(int device, const int32_t* h_counts, int64_t n_cells, int64_t
     prof.h2d_bytes += (double)nb * (double)n_cells * 4.0;
     prof.launches[SCLANE_STAGE_COPY]++;
     tm.mark(SCLANE_STAGE_GATHER);
-    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, d_cells, L.N, L.Npad, d_ys, d_stats, nullptr, nb);
+    k_gather_stats<int><<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, d_cells, L.N, L.Npad, d_ys, d_stats, nullptr, nb);
     CK(cudaGetLastError());
     g_launches.fetch_add(1);
     prof.launches[SCLANE_STAGE_GATHER]++;
@@ -444,6 +491,7 @@ int check_opts(const sclane_opts* o, char* errbuf, size_t errlen) {
   if (o->abi_version != SCLANE_ABI_VERSION) { set_err(errbuf, errlen, "ABI version mismatch: caller %d, library %d", o->abi_version, SCLANE_ABI_VERSION); return SCLANE_ERR_ARG; }
   if (o->mode != 0 && o->mode != 1) { set_err(errbuf, errlen, "mode %d is not built; 0 = GLM, 1 = GEE", o->mode); return SCLANE_ERR_UNSUPPORTED; }
   if (o->M < 3 || o->M > SCLANE_PMAX) { set_err(errbuf, errlen, "M must be in [3, %d]", SCLANE_PMAX); return SCLANE_ERR_ARG; }
+  if (o->h2d_mode < 0 || o->h2d_mode > 2) { set_err(errbuf, errlen, "h2d_mode must be 0, 1 or 2"); return SCLANE_ERR_ARG; }
   if (!o->approx_knot) { set_err(errbuf, errlen, "approx_knot = 0 is not supported yet"); return SCLANE_ERR_UNSUPPORTED; }
   if (o->n_knot_max < 1 || o->n_knot_max > SCLANE_TMAX) { set_err(errbuf, errlen, "n_knot_max must be in [1, %d]", SCLANE_TMAX); return SCLANE_ERR_ARG; }
   return SCLANE_OK;
@@ -982,7 +1030,7 @@ int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_
     GeneStats* d_stats = (GeneStats*)pool.get("stats", (size_t)nb * sizeof(GeneStats));
     GeneOutDev* d_out = (GeneOutDev*)pool.get("out", (size_t)nb * sizeof(GeneOutDev));
     CK(cudaMemcpyAsync(d_raw, counts, (size_t)nb * n_cells * 4, cudaMemcpyHostToDevice, s));
-    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
+    k_gather_stats<int><<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
     CK(cudaGetLastError()); g_launches.fetch_add(1);
     std::vector<GeneOutDev> h((size_t)nb);
     CK(cudaMemcpyAsync(h.data(), d_out, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
@@ -1037,7 +1085,7 @@ int32_t sclane_score_glm(const int32_t* counts, const double* mu, int64_t n_cell
     GeneOutDev* d_out = (GeneOutDev*)pool.get("out", (size_t)nb * sizeof(GeneOutDev));
     CK(cudaMemcpyAsync(d_raw, counts, (size_t)nb * n_cells * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_mu_raw, mu, (size_t)nb * n_cells * 8, cudaMemcpyHostToDevice, s));
-    k_gather_stats<<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
+    k_gather_stats<int><<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
     CK(cudaGetLastError()); g_launches.fetch_add(1);
     k_gather_f64<<<nb, 256, 0, s>>>(d_mu_raw, (long long)n_cells, D.perm, L.N, L.Npad, d_mu, nb);
     CK(cudaGetLastError()); g_launches.fetch_add(1);

@@ -248,15 +248,17 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
 // Pure permutation copy (the compressed route's replacement of k_gather_stats): K CTAs per gene, so that the rows being
 // gathered at any moment fit in L2 and the 4-byte random reads of a row are served from there instead of costing a
 // 32-byte DRAM sector each.
-__global__ void __launch_bounds__(kThreads) k_gather_copy(const int* __restrict__ raw, long long ld, const int* __restrict__ perm, int N,
+// RAW = int (the caller's counts) or unsigned short (counts narrowed on the host for the PCIe transfer).
+template <class RAW>
+__global__ void __launch_bounds__(kThreads) k_gather_copy(const RAW* __restrict__ raw, long long ld, const int* __restrict__ perm, int N,
                                                           int Npad, int* __restrict__ ys, int n_genes, int K) {
   const int g = blockIdx.x / K, part = blockIdx.x - g * K;
   if (g >= n_genes) return;
   const int chunk = ((Npad / K + 127) / 128) * 128;
   const int i0 = part * chunk, i1 = min(Npad, i0 + chunk);
-  const int* src = raw + (size_t)g * (size_t)ld;
+  const RAW* src = raw + (size_t)g * (size_t)ld;
   int* dst = ys + (size_t)g * (size_t)Npad;
-  for (int i = i0 + threadIdx.x; i < i1; i += kThreads) dst[i] = i < N ? __ldg(src + __ldg(perm + i)) : 0;
+  for (int i = i0 + threadIdx.x; i < i1; i += kThreads) dst[i] = i < N ? (int)__ldg(src + __ldg(perm + i)) : 0;
 }
 
 template <int MODE> struct CompTraits;

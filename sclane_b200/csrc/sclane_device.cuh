@@ -606,18 +606,19 @@ k_sweep_select(StageArgs A) {
 // (replaces the per-gene `expr.mat[lineage_cells, i]` column extraction of testDynamic.R:190).
 // raw: [B][ld] gene-major counts in the caller's cell order; ys: [B][Npad] sorted, zero padded.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_gather_stats(const int* __restrict__ raw, long long ld, const int* __restrict__ perm,
+template <class RAW>
+__global__ void __launch_bounds__(kThreads) k_gather_stats(const RAW* __restrict__ raw, long long ld, const int* __restrict__ perm,
                                                            int N, int Npad, int* __restrict__ ys, GeneStats* __restrict__ stats,
                                                            GeneOutDev* __restrict__ out, int n_genes) {
   const int g = blockIdx.x;
   if (g >= n_genes) return;
-  const int* src = raw + (size_t)g * (size_t)ld;
+  const RAW* src = raw + (size_t)g * (size_t)ld;
   int* dst = ys + (size_t)g * (size_t)Npad;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
   int ymax = 0;
   for (int i = threadIdx.x; i < Npad; i += kThreads) {
     int v = 0;
-    if (i < N) v = __ldg(src + __ldg(perm + i));
+    if (i < N) v = (int)__ldg(src + __ldg(perm + i));
     if (v < 0) { v = 0; ymax = 0x7fffffff; }          // negative count: flagged through ymax, stored as 0
     dst[i] = v;
     if (v > 0) {

@@ -377,3 +377,24 @@ def test_default_workload_cell_count_vs_oracle():
     assert res.profile["ms"]["comp_final"] > 0
     ref = oracle_test_dynamic(np.asarray(counts), np.asarray(pt, dtype=np.float64).reshape(-1), list(res.keys()), None, keep_preds=False)
     _compare_with_oracle(res, ref)
+
+
+def test_staged_uint16_transfer_equals_direct():
+    """h2d_mode = 2 (host threads narrow every gene batch to uint16 into pinned staging, double buffered) gives byte-identical
+    records to the direct int32 copy, on both routes; a batch holding a count > 65534 or a negative count falls back to int32."""
+    from sclane_b200 import api, synth
+    counts, pt, _ = synth.make_counts(90, 9000, seed=17)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    counts[33, 100] = 70000            # does not fit uint16 -> its batch goes direct
+    counts[61, 5] = -1                 # negative -> its batch goes direct, the gene fails
+    for per_cell in (False, True):
+        out = []
+        for mode in (1, 2):
+            o = api._opts(gpu_ids=[0], genes_per_batch=16, force_per_cell=per_cell, h2d_mode=mode)
+            recs, _ = api.run_records(counts, pt, None, o)
+            out.append(recs)
+            p = api.get_profile()
+            assert p["h2d_bytes"] == (90 * 9000 * 4 if mode == 1 else (90 - 32) * 9000 * 2 + 32 * 9000 * 4)
+        for i in range(90):
+            assert _rec_bytes(out[0][i]) == _rec_bytes(out[1][i]), (per_cell, i)
+        assert out[1][61].status == 0 and out[1][33].status == 3
