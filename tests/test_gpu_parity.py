@@ -398,3 +398,20 @@ def test_staged_uint16_transfer_equals_direct():
         for i in range(90):
             assert _rec_bytes(out[0][i]) == _rec_bytes(out[1][i]), (per_cell, i)
         assert out[1][61].status == 0 and out[1][33].status == 3
+
+
+@pytest.mark.parametrize("M", [3, 7])
+def test_other_basis_budgets_vs_oracle(M):
+    """n.potential.basis.fns = 3 (one forward iteration) and 7 (three iterations, up to seven columns -- SCLANE_PMAX), both
+    routes, against the oracle."""
+    import sclane_b200 as sb
+    from sclane_b200 import synth
+    counts, pt, _ = synth.make_counts(20, 16000, seed=29)
+    ref = oracle_test_dynamic(np.asarray(counts), np.asarray(pt, dtype=np.float64).reshape(-1), None, None, n_potential_basis_fns=M,
+                              keep_preds=False)
+    genes = list(ref.keys())
+    for per_cell in (False, True):
+        res = sb.testDynamic(counts, pt, genes=genes, n_potential_basis_fns=M, n_gpus=1, preds="none", force_per_cell=per_cell)
+        _compare_with_oracle(res, ref)
+    sizes = {res.records[i].n_terms for i in range(20)}
+    assert max(sizes) <= M and (M == 3 or max(sizes) >= 4)
