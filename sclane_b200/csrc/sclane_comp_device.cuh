@@ -54,7 +54,8 @@ struct CompArgs {
 // Also measured and rejected (same units; baseline 144.7 / 12.7): an exactly balanced split of the sloped points over the
 // warps with per-warp partial sums 153.9 / 13.9; two points per lane per iteration 161.4 / 14.9 (80 registers) and
 // 170.0 / 14.0 (128 registers, 2 CTAs/SM); backward + final fused into one launch 162.0 / 15.2;
-// flat buckets evaluated in parallel by the lanes of warp 0 + least-loaded assignment of the sloped buckets 149.7 / 12.7.
+// flat buckets evaluated in parallel by the lanes of warp 0 + least-loaded assignment of the sloped buckets 149.7 / 12.7;
+// means cached in global memory across the Newton iterations of theta.ml (41 of 56 passes per gene) 146.9 / 12.9.
 constexpr int kCompWarps = SCLANE_COMP_WARPS;
 constexpr int kCompThreads = kCompWarps * 32;
 constexpr int kAggV = 9;        // per-bucket totals gathered by k_aggregate
