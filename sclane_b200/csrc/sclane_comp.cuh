@@ -25,15 +25,6 @@ constexpr int kHistCap = 4096;          // counts below this go through the gene
 constexpr int kBigCap = 8192;           // counts >= kHistCap are kept as a sorted per-gene list of at most kBigCap cells, whose
                                         // mu-free terms are evaluated directly; a gene with more such cells takes the per-cell path
 
-// gene-independent tables of the compressed layout (pointers are device or host memory, depending on the executor)
-struct CompTables {
-  int D;
-  const int* pstart;        // [D + 1] range of the point's cells in the pseudotime-sorted cell order
-  const double* pn;         // [D] number of cells of the point
-  const double* pu;         // [D] bucket-local coordinate x - ref[bucket]
-  int pbstart[NBMAX + 1];   // point index range of bucket b: [pbstart[b], pbstart[b + 1])
-};
-
 // per-gene aggregates
 struct CompGeneHdr {
   int ymax;                 // largest count
