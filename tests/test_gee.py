@@ -195,3 +195,36 @@ def test_gee_bias_corrected_sandwich_gpu_vs_dense_oracle():
         recs, _ = api.run_records(counts, pt, sf, o, subject_id=subject.astype(np.int32))
         ref = oracle_gee(counts, pt, subject, genes, sf, cor, bias_correction=method)
         assert _compare(recs, ref, genes) == []
+
+
+@pytest.mark.gpu
+def test_gee_gpu_vs_core_at_config3_subject_size(emu):
+    """BASELINE configs[2]'s shape per subject (3 subjects x 10,000 cells, AR-1; pseudotime-sorted within subject for the
+    first half of the genes' run, arbitrary order for the second): k_gee vs the serial run of the same core."""
+    from sclane_b200 import _abi, api, synth
+    counts, pt, _ = synth.make_counts(8, 30000, seed=23)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    pt = np.asarray(pt, dtype=np.float64).reshape(-1)
+    subject = (np.arange(30000) * 3 // 30000).astype(np.int32)
+    sf = np.random.default_rng(23).uniform(0.6, 1.6, 30000)
+    for order in ("sorted", "random"):
+        if order == "sorted":
+            idx = np.lexsort((pt, subject))
+            c, x, s = np.ascontiguousarray(counts[:, idx]), pt[idx], sf[idx]
+        else:
+            c, x, s = counts, pt, sf
+        o = api._opts(gpu_ids=[0])
+        o.mode = 1
+        o.gee_cor = _abi.COR_AR1
+        recs, _ = api.run_records(c, x, s, o, subject_id=subject)
+        ref, _ = emu.run_gee(c, x, subject, s, "ar1")
+        n_ok = 0
+        for i in range(8):
+            a, b = recs[i], ref[i]
+            assert a.status == b.status and record_terms(a) == record_terms(b), (order, i)
+            if a.status & 1:
+                n_ok += 1
+                for j in range(a.n_terms):
+                    assert rel(a.coef[j], b.coef[j], 1e-6) < TOL and rel(a.se[j], b.se[j], 1e-6) < TOL, (order, i, j)
+                assert rel(a.test_stat, b.test_stat, 1e-6) < TOL and rel(a.gee_phi, b.gee_phi) < TOL, (order, i)
+        assert n_ok >= 6
