@@ -255,7 +255,7 @@ def main():
     for _ in range(args.steps):
         flush.zero_()                                   # evict the previous step's working set from L2
         torch.cuda.synchronize()
-        step_device()
+        last_recs, _ = step_device()
         p = sb.get_profile()
         dev_ms += sum(v for k, v in p["ms"].items())
         if prof_acc is None:
@@ -336,6 +336,13 @@ def main():
                     "of the k_sweep_moments launches (rank 0); k_sweep_select (K2b, per-gene O(T p^2) algebra) is timed separately")
             traffic = TRAFFIC_PER_LAUNCH.get(args.config) if (world == 1 and not args.genes) else None
         achieved = (prof_acc["sweep_bytes"] / 1e9) / (sweep_ms / 1000.0) if sweep_ms > 0 else 0.0
+        # the fit kernels ("bytes = passes x 4 N per gene", FP64 bound): passes counted by the kernels themselves
+        fit_stages = ["fwd_fit", "backward", "final", "comp_forward", "comp_backward", "comp_final", "select"]
+        fit_ms = sum(prof_acc["ms"][k] for k in fit_stages) / args.steps
+        passes = float(np.mean(np.frombuffer(last_recs, dtype=np.uint8).reshape(G, -1)[:, type(last_recs[0]).fit_passes.offset:
+                                                                                        type(last_recs[0]).fit_passes.offset + 4]
+                               .copy().view(np.int32)))
+        dom = max(prof_acc["ms"], key=lambda k: prof_acc["ms"][k])
         gather_ms = prof_acc["ms"]["gather"] + prof_acc["ms"]["aggregate"]
         gather_bytes = args.steps * (float(G) * N * (8.0 if not comp else 12.0))   # read 4 B + write 4 B (+ read 4 B in k_aggregate) per cell
         line = {
@@ -357,6 +364,14 @@ def main():
                          "ms_per_launch": sweep_ms / max(1, sweep_launches),
                          "select_kernel_ms_per_launch": prof_acc["ms"]["select"] / max(1, prof_acc["launches"]["select"]),
                          "note": note,
+                         "fits": {"kernels": "k_comp_stage<FORWARD|BACKWARD|FINAL>" if comp else "k_stage<FWD_FIT|BACKWARD|FINAL> + sweep",
+                                  "dominant_stage": dom, "dominant_share_of_step": prof_acc["ms"][dom] / args.steps / ms_step,
+                                  "bound": "fp64 pipe", "passes_per_gene": passes, "ms_per_step": fit_ms,
+                                  "algorithmic_GBps": passes * 4.0 * N * G / 1e9 / (fit_ms / 1000.0) if fit_ms > 0 else None,
+                                  "ncu": "profiles/r01_ncu_comp_final.txt: FP64 pipe 35 % of peak, issue slots 49 % busy, DRAM 0.3 %"
+                                         if comp else "profiles/r01_ncu_final_v2.txt",
+                                  "note": "algorithmic bytes = passes x 4 B x cells per gene (SURVEY.md 8d); the compressed kernels walk "
+                                          "the distinct abscissae instead (at 200,000 cells this figure exceeds the HBM peak) -- the stage is FP64 bound"},
                          "gather_aggregate": {"kernels": ("k_gather_copy + k_aggregate" if comp else "k_gather_stats") + " (sort by pseudotime; per-abscissa sums)",
                                               "achieved": gather_bytes / 1e9 / (gather_ms / 1000.0) if gather_ms > 0 else None,
                                               "unit": "GB/s", "ms_per_step": gather_ms / args.steps,
