@@ -53,7 +53,7 @@ struct CompArgs {
 #define SCLANE_COMP_MINB 3
 #endif
 // CTA shape of k_comp_stage.  Measured on B200 (C5 / C2 ms per step): 8 warps x 3 CTAs/SM 144.4 / 12.7, 4 x 6 150.0 / 13.6,
-// 4 x 4 154.8 / 14.1, 8 x 2 167.8 / 13.7, 2 x 12 178.6 / 17.6 -- the passes are throughput bound, not leader-latency bound.
+// 8 x 4 (64 registers) 143.3 / 13.2, 4 x 4 154.8 / 14.1, 8 x 2 167.8 / 13.7, 2 x 12 178.6 / 17.6 -- the passes are throughput bound, not leader-latency bound.
 // Also measured and rejected (same units; baseline 144.7 / 12.7): an exactly balanced split of the sloped points over the
 // warps with per-warp partial sums 153.9 / 13.9; two points per lane per iteration 161.4 / 14.9 (80 registers) and
 // 170.0 / 14.0 (128 registers, 2 CTAs/SM); backward + final fused into one launch 162.0 / 15.2;
