@@ -428,25 +428,53 @@ void run_shard_gee(int device, const int32_t* h_counts, int64_t n_cells, int64_t
   const size_t cap = (size_t)24 << 30;
   if (budget > cap) budget = cap;
   int64_t B = (int64_t)(budget / per_gene);
+  // a few batches (>= 1024 genes each) so that the H2D copy of batch k + 1 runs on the copy stream under k_gee of batch k
+  if ((double)G * (double)n_cells * 4.0 >= 128e6) { const int64_t want = std::max<int64_t>(1024, (G + 3) / 4); if (want < B) B = want; }
   if (o.genes_per_batch > 0 && o.genes_per_batch < B) B = o.genes_per_batch;
   if (B > G) B = G;
   if (B < 1) throw CudaFail{"not enough free device memory for a single gene"};
-  int* d_raw = (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4);
+  const int64_t n_batches = (G + B - 1) / B;
+  if (!pool.copy_stream) CK(cudaStreamCreateWithFlags(&pool.copy_stream, cudaStreamNonBlocking));
+  cudaStream_t cs = pool.copy_stream;
+  int* d_raw2[2];
+  d_raw2[0] = (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4);
+  d_raw2[1] = n_batches > 1 ? (int*)pool.get("raw_b", (size_t)B * (size_t)n_cells * 4) : d_raw2[0];
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+  }
+  struct EventGuard {
+    cudaEvent_t* a; cudaEvent_t* b;
+    ~EventGuard() { for (int i = 0; i < 2; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); } }
+  } ev_guard{ev_h2d, ev_free};
+  auto issue_h2d = [&](int64_t k) {
+    const int buf = (int)(k & 1);
+    const int64_t kb0 = g0 + k * B, kb1 = std::min<int64_t>(kb0 + B, g1);
+    if (k >= 2) CK(cudaStreamWaitEvent(cs, ev_free[buf], 0));          // the gather of batch k - 2 has consumed this buffer
+    CK(cudaMemcpyAsync(d_raw2[buf], h_counts + (size_t)kb0 * (size_t)n_cells, (size_t)(kb1 - kb0) * (size_t)n_cells * 4,
+                       cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(ev_h2d[buf], cs));
+    prof.h2d_bytes += (double)(kb1 - kb0) * (double)n_cells * 4.0;
+    prof.launches[SCLANE_STAGE_COPY]++;
+  };
+  CK(cudaStreamSynchronize(s));                                         // plan tables are in place before anything overlaps
+  issue_h2d(0);
   int* d_ys = (int*)pool.get("ys", (size_t)B * (size_t)L.Npad * 4);
   GeneStats* d_stats = (GeneStats*)pool.get("stats", (size_t)B * sizeof(GeneStats));
   GeeGeneOutDev* d_out = (GeeGeneOutDev*)pool.get("gee_out", (size_t)B * sizeof(GeeGeneOutDev));
   GeeGeneOutDev* h_out = (GeeGeneOutDev*)pool.get("gee_h_out", (size_t)B * sizeof(GeeGeneOutDev), true);
   EventTimer tm(s);
-  for (int64_t b0 = g0; b0 < g1; b0 += B) {
+  for (int64_t b0 = g0, kb = 0; b0 < g1; b0 += B, ++kb) {
     const int64_t b1 = std::min<int64_t>(b0 + B, g1);
     const int nb = (int)(b1 - b0);
-    tm.mark(SCLANE_STAGE_COPY);
-    CK(cudaMemcpyAsync(d_raw, h_counts + (size_t)b0 * (size_t)n_cells, (size_t)nb * (size_t)n_cells * 4, cudaMemcpyHostToDevice, s));
-    prof.h2d_bytes += (double)nb * (double)n_cells * 4.0;
-    prof.launches[SCLANE_STAGE_COPY]++;
+    tm.mark(SCLANE_STAGE_COPY);             // exposed wait for the batch's H2D
+    CK(cudaStreamWaitEvent(s, ev_h2d[kb & 1], 0));
+    const int* d_raw = d_raw2[kb & 1];
     tm.mark(SCLANE_STAGE_GATHER);
     k_gather_stats<int><<<nb, kThreads, 0, s>>>(d_raw, (long long)n_cells, d_cells, L.N, L.Npad, d_ys, d_stats, nullptr, nb);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ev_free[kb & 1], s));
     g_launches.fetch_add(1);
     prof.launches[SCLANE_STAGE_GATHER]++;
     GeeArgs A;
@@ -462,6 +490,7 @@ void run_shard_gee(int device, const int32_t* h_counts, int64_t n_cells, int64_t
     prof.d2h_bytes += (double)nb * sizeof(GeeGeneOutDev);
     prof.launches[SCLANE_STAGE_COPY]++;
     tm.mark(-1);
+    if (kb + 1 < n_batches) issue_h2d(kb + 1);                // next batch's transfer while the GPU works on this one
     CK(cudaStreamSynchronize(s));
     tm.collect(prof);
     for (int i = 0; i < nb; ++i) {
