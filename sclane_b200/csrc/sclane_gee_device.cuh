@@ -379,7 +379,10 @@ struct GeeDevExec {
   }
 };
 
-__global__ void __launch_bounds__(kThreads, 2) k_gee(GeeArgs A) {
+#ifndef SCLANE_GEE_MINB
+#define SCLANE_GEE_MINB 2
+#endif
+__global__ void __launch_bounds__(kThreads, SCLANE_GEE_MINB) k_gee(GeeArgs A) {
   extern __shared__ __align__(16) unsigned char gee_smem[];
   GeeShared* S = reinterpret_cast<GeeShared*>(gee_smem);
   const int g = blockIdx.x;
