@@ -218,8 +218,14 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   int64_t B = (int64_t)(budget / per_gene);
   // host counts: aim for ~8 batches (but >= 2048 genes each, several waves of CTAs) so that the H2D copy of batch k + 1
   // runs on the copy stream while the kernels of batch k execute
-  if (h_counts) { const int64_t want = std::max<int64_t>(2048, (G + 7) / 8); if (want < B) B = want; }
-  if (o.genes_per_batch > 0 && o.genes_per_batch < B) B = o.genes_per_batch;
+  if (o.genes_per_batch > 0) { if (o.genes_per_batch < B) B = o.genes_per_batch; }
+  else if (h_counts) {
+    // per-cell final fits (offsets) are compute bound and every launch ends in a tail of slow genes (~160 ms at 30,000 cells):
+    // two batches are enough to hide the transfer; otherwise ~8 batches keep the PCIe link busy
+    const bool heavy_final = use_offset || !use_comp;
+    const int64_t want = std::max<int64_t>(2048, heavy_final ? (G + 1) / 2 : (G + 7) / 8);
+    if (want < B) B = want;
+  }
   if (B > G) B = G;
   if (B < 1) throw CudaFail{"not enough free device memory for a single gene"};
   const int64_t n_batches = (G + B - 1) / B;
@@ -289,6 +295,8 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   int* d_tail = use_comp ? (int*)pool.get("comp_tail", (size_t)B * (size_t)kHistCap * 4) : nullptr;
   int* d_big = use_comp ? (int*)pool.get("comp_big", (size_t)B * (size_t)kBigCap * 4) : nullptr;
   int* d_big_tmp = use_comp ? (int*)pool.get("comp_big_tmp", (size_t)B * (size_t)kBigCap * 4) : nullptr;
+  double* d_okeys = (double*)pool.get("order_keys", (size_t)B * 8);
+  int* d_order = (int*)pool.get("order", (size_t)B * 4);
   CompGeneDev* d_cg = use_comp ? (CompGeneDev*)pool.get("comp_hdr", (size_t)B * sizeof(CompGeneDev)) : nullptr;
   const int n_iter = forward_iterations(o.M);
   EventTimer tm(s);
@@ -324,7 +332,9 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = D.off; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
     A.scores = nullptr; A.mom = d_mom; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
+    A.order = nullptr;
     CompArgs CA;
+    CA.order = nullptr;
     if (use_comp) {
       CA.lineage = D.lin; CA.pstart = D.pstart; CA.pn = D.pn; CA.pu = D.pu; CA.pb = D.pb; CA.pbstart = D.pbstart; CA.D = P.D; CA.Dpad = Dpad; CA.ys = d_ys;
       CA.s1 = d_s1; CA.q = d_q; CA.tail = d_tail; CA.big = d_big; CA.big_tmp = d_big_tmp; CA.cg = d_cg; CA.stats = d_stats; CA.out = d_out; CA.n_genes = nb; CA.M = o.M;
@@ -358,6 +368,15 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     tm.mark(SCLANE_STAGE_BACKWARD);
     launch_stage<STAGE_BACKWARD>(A, s);
     prof.launches[SCLANE_STAGE_BACKWARD]++;
+    // final stage: expensive (near-Poisson) genes first, so that no slow CTA is left running alone at the end of the launch
+    tm.mark(SCLANE_STAGE_SELECT);
+    k_order_final<<<(nb + 255) / 256, 256, 0, s>>>(d_out, nb, d_okeys, d_order, 0);
+    k_order_final<<<(nb + 255) / 256, 256, 0, s>>>(d_out, nb, d_okeys, d_order, 1);
+    CK(cudaGetLastError());
+    g_launches.fetch_add(2);
+    prof.launches[SCLANE_STAGE_SELECT] += 2;
+    A.order = d_order;
+    CA.order = d_order;
     if (use_comp && !use_offset) {
       tm.mark(SCLANE_STAGE_COMP_FINAL);
       k_comp_stage<CSTAGE_FINAL><<<nb, kCompThreads, 0, s>>>(CA);
@@ -1068,7 +1087,7 @@ int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_
     CK(cudaMemcpyAsync(d_out, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = nullptr; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
-    A.scores = nullptr; A.mom = nullptr; A.n_genes = nb; A.M = 5; A.tols_score = 1e-5; A.use_offset = 0;
+    A.scores = nullptr; A.mom = nullptr; A.n_genes = nb; A.M = 5; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr;
     launch_stage<STAGE_FWD_FIT>(A, s);
     CK(cudaMemcpyAsync(h.data(), d_out, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
     std::vector<double> hmu;
@@ -1125,7 +1144,7 @@ int32_t sclane_score_glm(const int32_t* counts, const double* mu, int64_t n_cell
     CK(cudaMemcpyAsync(d_out, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = nullptr; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
-    A.scores = d_scores; A.mom = d_mom; A.n_genes = nb; A.M = 99; A.tols_score = 1e-5; A.use_offset = 0;
+    A.scores = d_scores; A.mom = d_mom; A.n_genes = nb; A.M = 99; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr;
     launch_sweep(A, true, s, nullptr, nullptr);
     std::vector<double> hs((size_t)nb * 2 * L.T);
     CK(cudaMemcpyAsync(hs.data(), d_scores, hs.size() * 8, cudaMemcpyDeviceToHost, s));

@@ -44,6 +44,7 @@ struct CompArgs {
   int n_genes, M, n_iter;
   int compute_stats;
   double tols_score;
+  const int* order;             // optional CTA -> gene map of the final stage (k_order_final), or nullptr
 };
 
 #ifndef SCLANE_COMP_WARPS
@@ -409,8 +410,8 @@ __global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(C
   __shared__ CompGeneDev cg;
   __shared__ int pbs[NBMAX + 1];
   __shared__ double scw[kCompWarps][NSC];
-  const int g = blockIdx.x;
-  if (g >= A.n_genes) return;
+  if ((int)blockIdx.x >= A.n_genes) return;
+  const int g = (STAGE == CSTAGE_FINAL && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
   if (A.cg[g].hdr.route == 0) return;                     // block-uniform: this gene takes the per-cell kernels
   {
     const int* src = reinterpret_cast<const int*>(A.lineage);

@@ -256,6 +256,7 @@ struct StageArgs {
   int M;
   double tols_score;
   int use_offset;
+  const int* order;            // optional CTA -> gene map of the final stage (k_order_final: expensive genes first), or nullptr
 };
 
 enum Stage : int { STAGE_FWD_FIT = 0, STAGE_BACKWARD = 2, STAGE_FINAL = 3 };
@@ -269,8 +270,8 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   __shared__ double slot[kWarps][NBMAX][NACC];
   __shared__ double scw[kWarps][NSC];
   __shared__ PassTabs tabs;
-  const int g = blockIdx.x;
-  if (g >= A.n_genes) return;
+  if ((int)blockIdx.x >= A.n_genes) return;
+  const int g = (STAGE == STAGE_FINAL && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
   {
     // cooperative word copies of the small per-lineage / per-gene structs
     const int* src = reinterpret_cast<const int*>(A.lineage);
@@ -659,6 +660,25 @@ __global__ void __launch_bounds__(kThreads) k_gather_stats(const RAW* __restrict
     out[g].alt.ok = 0;
     out[g].null.ok = 0;
   }
+}
+
+// Launch order of the final stage.  The cost of glm.nb varies ~10x between genes and the few near-Poisson genes (theta runs
+// away: up to 25 alternations of IRLS + theta.ml) take 5-15x the median; when such a gene starts late its CTA runs alone at
+// the end of the launch (measured: SMs 45 % active in a 2,048-gene launch of k_stage<FINAL>).  The forward pass already
+// knows them -- sigma of the last forward null fit is ~0 -- so the final stage visits the genes in ascending sigma
+// (rank sort, ties by index: a deterministic permutation; which CTA fits which gene does not change any result).
+__global__ void k_order_final(const GeneOutDev* __restrict__ out, int n, double* __restrict__ keys, int* __restrict__ order, int phase) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (phase == 0) {
+    const GeneState& st = out[i].st;
+    keys[i] = st.error ? 1e300 : st.sigma;        // failed genes return at once: last
+    return;
+  }
+  const double k = keys[i];
+  int rank = 0;
+  for (int j = 0; j < n; ++j) { const double kj = keys[j]; rank += (kj < k || (kj == k && j < i)) ? 1 : 0; }
+  order[rank] = i;
 }
 
 // gather of a double matrix by the same permutation (sclane_score_glm: mu in caller order -> sorted)

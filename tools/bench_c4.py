@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--h2d-mode", type=int, default=0)
+    ap.add_argument("--genes-per-batch", type=int, default=0)
     args = ap.parse_args()
     import torch
     import bench
@@ -47,7 +48,7 @@ def main():
 
     pt2 = np.stack([rank01(pt, in_a), rank01(1.0 - pt, in_b)], 1)
     sf = api.createCellOffset(counts)
-    o = api._opts(gpu_ids=[0], h2d_mode=args.h2d_mode)
+    o = api._opts(gpu_ids=[0], h2d_mode=args.h2d_mode, genes_per_batch=args.genes_per_batch)
     for _ in range(args.warmup):
         recs, _ = api.run_records(counts, pt2, sf, o)
     sb.reset_launch_count()
