@@ -358,6 +358,15 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       prof.launches[SCLANE_STAGE_FWD_FIT]++;
       launch_sweep(A, it == 0, s, &tm, &prof);
     }
+    // backward stage: widest forward models first (same reason as the final stage's order below)
+    tm.mark(SCLANE_STAGE_SELECT);
+    k_order_final<<<(nb + 255) / 256, 256, 0, s>>>(d_out, nb, d_okeys, d_order, 2);
+    k_order_final<<<(nb + 255) / 256, 256, 0, s>>>(d_out, nb, d_okeys, d_order, 1);
+    CK(cudaGetLastError());
+    g_launches.fetch_add(2);
+    prof.launches[SCLANE_STAGE_SELECT] += 2;
+    A.order = d_order;
+    CA.order = d_order;
     if (use_comp) {
       tm.mark(SCLANE_STAGE_COMP_BWD);
       k_comp_stage<CSTAGE_BACKWARD><<<nb, kCompThreads, 0, s>>>(CA);

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(C
   __shared__ int pbs[NBMAX + 1];
   __shared__ double scw[kCompWarps][NSC];
   if ((int)blockIdx.x >= A.n_genes) return;
-  const int g = (STAGE == CSTAGE_FINAL && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
+  const int g = ((STAGE == CSTAGE_FINAL || STAGE == CSTAGE_BACKWARD) && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
   if (A.cg[g].hdr.route == 0) return;                     // block-uniform: this gene takes the per-cell kernels
   {
     const int* src = reinterpret_cast<const int*>(A.lineage);

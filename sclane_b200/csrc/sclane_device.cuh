@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   __shared__ double scw[kWarps][NSC];
   __shared__ PassTabs tabs;
   if ((int)blockIdx.x >= A.n_genes) return;
-  const int g = (STAGE == STAGE_FINAL && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
+  const int g = ((STAGE == STAGE_FINAL || STAGE == STAGE_BACKWARD) && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
   {
     // cooperative word copies of the small per-lineage / per-gene structs
     const int* src = reinterpret_cast<const int*>(A.lineage);
@@ -665,14 +665,32 @@ __global__ void __launch_bounds__(kThreads) k_gather_stats(const RAW* __restrict
 // Launch order of the final stage.  The cost of glm.nb varies ~10x between genes and the few near-Poisson genes (theta runs
 // away: up to 25 alternations of IRLS + theta.ml) take 5-15x the median; when such a gene starts late its CTA runs alone at
 // the end of the launch (measured: SMs 45 % active in a 2,048-gene launch of k_stage<FINAL>).  The forward pass already
-// knows them -- sigma of the last forward null fit is ~0 -- so the final stage visits the genes in ascending sigma
-// (rank sort, ties by index: a deterministic permutation; which CTA fits which gene does not change any result).
+// knows them -- sigma of the last forward null fit is ~0 -- so the final stage visits those first and the rest by descending
+// forward score (rank sort, ties by index: a deterministic permutation; which CTA fits which gene does not change any result).
 __global__ void k_order_final(const GeneOutDev* __restrict__ out, int n, double* __restrict__ keys, int* __restrict__ order, int phase) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (phase == 2) {
+    // backward pass: one NB refit per column of the forward model -> widest models first, then by forward score
+    const GeneState& st = out[i].st;
+    double sc = 0.0;
+    for (int t = 0; t < st.fwd_iters && t < 4; ++t) if (st.fwd_score[t] == st.fwd_score[t] && st.fwd_score[t] > sc) sc = st.fwd_score[t];
+    keys[i] = st.error ? 1e300 : -((double)st.fwd.n * 1e12 + (sc < 1e11 ? sc : 1e11));
+    return;
+  }
   if (phase == 0) {
     const GeneState& st = out[i].st;
-    keys[i] = st.error ? 1e300 : st.sigma;        // failed genes return at once: last
+    double k;
+    if (st.error) k = 1e300;                      // failed genes return at once: last
+    else if (st.sigma < 1e-6) k = -1e300;         // Poisson regime / near-Poisson: theta runs away, up to 25 alternations: first
+    else {
+      // then by descending forward score: strongly dynamic genes need more alternations (Spearman 0.8 with the final
+      // stage's iteration count on the bench generator; sigma alone 0.2)
+      double sc = 0.0;
+      for (int t = 0; t < st.fwd_iters && t < 4; ++t) if (st.fwd_score[t] == st.fwd_score[t] && st.fwd_score[t] > sc) sc = st.fwd_score[t];
+      k = -sc;
+    }
+    keys[i] = k;
     return;
   }
   const double k = keys[i];

@@ -18,3 +18,9 @@ print("quantiles of passes", np.quantile(passes, [0.5, 0.9, 0.99, 1.0]))
 for thr in (1e-3, 1e-2, 3e-2):
     m = last < thr
     print("sigma <", thr, ": n", m.sum(), "mean passes", passes[m].mean() if m.any() else None, "| others mean", passes[~m].mean(), "max", passes[~m].max())
+from scipy.stats import spearmanr
+nt = np.array([r.n_terms for r in recs]); mean_y = counts.mean(axis=1); fs = np.array([np.nanmax(np.array(list(r.fwd_score))) if np.isfinite(np.array(list(r.fwd_score))).any() else 0 for r in recs])
+final_passes = np.array([r.alternations + r.null_alternations for r in recs]) * 1.0 + np.array([r.irls_iters + r.null_irls_iters for r in recs])
+for name, key in (("last sigma", last), ("mean y", mean_y), ("n_terms", nt), ("fwd score", fs), ("sigma*mean", last * mean_y), ("log mean y", np.log(mean_y + 1e-9))):
+    ok = np.isfinite(key)
+    print(name, "spearman with passes", round(spearmanr(key[ok], passes[ok]).correlation, 3), "with alternations+irls", round(spearmanr(key[ok], final_passes[ok]).correlation, 3))
