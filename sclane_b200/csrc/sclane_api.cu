@@ -379,7 +379,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.launches[SCLANE_STAGE_BACKWARD]++;
     // final stage: expensive (near-Poisson) genes first, so that no slow CTA is left running alone at the end of the launch
     tm.mark(SCLANE_STAGE_SELECT);
-    k_order_final<<<(nb + 255) / 256, 256, 0, s>>>(d_out, nb, d_okeys, d_order, 0);
+    k_order_final<<<(nb + 255) / 256, 256, 0, s>>>(d_out, nb, d_okeys, d_order, use_offset ? 3 : 0);
     k_order_final<<<(nb + 255) / 256, 256, 0, s>>>(d_out, nb, d_okeys, d_order, 1);
     CK(cudaGetLastError());
     g_launches.fetch_add(2);

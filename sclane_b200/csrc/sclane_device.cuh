@@ -678,6 +678,14 @@ __global__ void k_order_final(const GeneOutDev* __restrict__ out, int n, double*
     keys[i] = st.error ? 1e300 : -((double)st.fwd.n * 1e12 + (sc < 1e11 ? sc : 1e11));
     return;
   }
+  if (phase == 3) {
+    // final fits WITH an offset: the forward fits ran without it, so a gene whose forward sigma is small is one whose
+    // dispersion is mostly depth variation -- with the offset its theta runs away and glm.nb goes to the alternation limit
+    // (bench generator: Spearman -0.71 between forward sigma and the final stage's passes; the score only 0.43)
+    const GeneState& st = out[i].st;
+    keys[i] = st.error ? 1e300 : st.sigma;
+    return;
+  }
   if (phase == 0) {
     const GeneState& st = out[i].st;
     double k;
