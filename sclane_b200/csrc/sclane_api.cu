@@ -228,6 +228,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   }
   if (B > G) B = G;
   if (B < 1) throw CudaFail{"not enough free device memory for a single gene"};
+  B = (G + ((G + B - 1) / B) - 1) / ((G + B - 1) / B);      // equal batches: a short last batch is mostly launch tail
   const int64_t n_batches = (G + B - 1) / B;
   // staged transfer (see sclane_opts.h2d_mode): automatic = when the copy is big enough to matter and pipelined
   // automatic = pageable caller memory (an R integer matrix): cudaMemcpyAsync from it is staged by the driver at ~12 GB/s,
