@@ -20,6 +20,10 @@
 
 using namespace sclane;
 
+#ifndef SCLANE_BATCH_CAP_GB
+#define SCLANE_BATCH_CAP_GB 24          // upper bound of the per-batch work buffers of one run_shard (the counts are extra)
+#endif
+
 namespace {
 
 std::atomic<long long> g_launches{0};
@@ -213,7 +217,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   const size_t per_gene = (h_counts ? (size_t)n_cells * 8 : 0) + (size_t)L.Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
                           (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0);
   size_t budget = (size_t)((double)(free_b + pool.held()) * 0.6);
-  const size_t cap = (size_t)24 << 30;
+  const size_t cap = (size_t)SCLANE_BATCH_CAP_GB << 30;
   if (budget > cap) budget = cap;
   int64_t B = (int64_t)(budget / per_gene);
   // host counts: aim for ~8 batches (but >= 2048 genes each, several waves of CTAs) so that the H2D copy of batch k + 1
