@@ -701,9 +701,15 @@ __global__ void k_order_final(const GeneOutDev* __restrict__ out, int n, double*
     keys[i] = k;
     return;
   }
-  const double k = keys[i];
+  // NaN keys would break the strict weak order (and with it the permutation): they sort with the failed genes
+  double k = keys[i];
+  if (!(k == k)) k = 1e300;
   int rank = 0;
-  for (int j = 0; j < n; ++j) { const double kj = keys[j]; rank += (kj < k || (kj == k && j < i)) ? 1 : 0; }
+  for (int j = 0; j < n; ++j) {
+    double kj = keys[j];
+    if (!(kj == kj)) kj = 1e300;
+    rank += (kj < k || (kj == k && j < i)) ? 1 : 0;
+  }
   order[rank] = i;
 }
 
