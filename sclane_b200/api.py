@@ -554,24 +554,42 @@ def _abi_unsupported() -> int:
     return 4
 
 
-def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False, approx_knot: bool = True,
-           n_knot_max: int = 25, tols_score: float = 1e-5, minspan=None, device: int = 0) -> dict:
-    """marge2.R:56-889 for one gene (GLM mode): X_pred = pseudotime of the lineage's cells, Y = counts, Y_offset =
-    size factors.  Returns final_mod-like fields (coefficients, SEs, theta, logLik, deviance), coef_names,
-    marge_coef_names, model_type."""
+def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False, id_vec=None, cor_structure: str = "ar1",
+           sandwich_var: bool = False, approx_knot: bool = True, n_knot_max: int = 25, tols_score: float = 1e-5, minspan=None,
+           device: int = 0) -> dict:
+    """marge2.R:56-889 for one gene: X_pred = pseudotime of the lineage's cells, Y = counts, Y_offset = size factors; GEE mode
+    with is_gee / id_vec / cor_structure / sandwich_var as in the reference.  Returns final_mod-like fields (coefficients,
+    SEs, theta, logLik, deviance -- or the geem fields alpha / phi in GEE mode), coef_names, marge_coef_names, model_type."""
     if X_pred is None or Y is None:
         raise ValueError("Some required inputs to marge2() are missing.")
-    if is_gee:
-        raise SclaneError(4, "marge2(is.gee = TRUE) as a stand-alone call is not built; use testDynamic(is_gee = True)")
     y = np.ascontiguousarray(np.asarray(Y).reshape(1, -1), dtype=np.int32)
     x = np.asarray(X_pred, dtype=np.float64).reshape(-1)
     o = _opts(M, approx_knot, n_knot_max, minspan, tols_score, gpu_ids=[device])
-    recs, infos = run_records(y, x[:, None], Y_offset, o)
+    sid = None
+    if is_gee:
+        if id_vec is None:
+            raise ValueError("id.vec in marge2() must be non-null if is.gee = TRUE.")
+        cor_structure = str(cor_structure).lower()
+        if cor_structure not in _abi.COR_CODES:
+            raise ValueError("cor.structure in marge2() must be a known type if is.gee = TRUE.")
+        o.mode = 1
+        o.gee_cor = _abi.COR_CODES[cor_structure]
+        o.gee_bias_correction = 2 if sandwich_var else 0      # any non-zero value switches the fits to the sandwich variance
+        sid = np.unique(np.asarray(id_vec), return_inverse=True)[1].astype(np.int32)
+    recs, infos = run_records(y, x[:, None], Y_offset, o, subject_id=sid)
     rec = recs[0]
     if not (rec.status & _abi.SCLANE_MARGE_OK):
         raise SclaneError(0, _notes(rec.marge_notes, False))
     names = _term_names(rec, "A")
     p = rec.n_terms
+    if is_gee:
+        return {"final_mod": {"coefficients": dict(zip(names, [rec.coef[j] for j in range(p)])),
+                              "std.error": [rec.se[j] for j in range(p)], "alpha": rec.gee_alpha, "phi": rec.gee_phi,
+                              "converged": bool(rec.gee_converged), "niter": int(rec.gee_iters),
+                              ("var" if sandwich_var else "naiv.var"): np.array([rec.cov[j] for j in range(p * p)]).reshape(p, p)},
+                "basis_mtx": None, "WIC_mtx": None, "GCV": None, "model_type": "GEE",
+                "coef_names": names, "marge_coef_names": names, "record": rec,
+                "knots": [infos[0].knots[k] for k in range(infos[0].n_knots)]}
     return {"final_mod": {"coefficients": dict(zip(names, [rec.coef[j] for j in range(p)])),
                           "std.error": [rec.se[j] for j in range(p)], "theta": rec.theta, "SE.theta": rec.se_theta,
                           "twologlik": 2.0 * rec.loglik, "logLik": rec.loglik, "df": p + 1, "deviance": rec.deviance,

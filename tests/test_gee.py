@@ -144,6 +144,11 @@ def test_gee_gpu_vs_core_bundled(emu, golden_inputs, cor):
     assert n_ok >= 80
     de = sb.getResultsDE(res)
     assert len(de["Gene"]) == 100
+    # marge2(is.gee = TRUE) stand-alone on one gene == the same gene inside testDynamic (the final fit carries the offset)
+    g = golden_inputs["genes"][1]
+    one = sb.marge2(pt.reshape(-1), counts[1], Y_offset=sf, is_gee=True, id_vec=subject, cor_structure=cor)
+    assert one["model_type"] == "GEE" and one["coef_names"] == res[g]["Lineage_A"]["MARGE_Summary"]["term"]
+    assert np.allclose(list(one["final_mod"]["coefficients"].values()), res[g]["Lineage_A"]["MARGE_Summary"]["estimate"], rtol=1e-12)
 
 
 def test_gee_score_test_core_vs_dense_oracle(emu):
