@@ -28,24 +28,24 @@ inline double r_signif(double x, int digits) {           // nmath/fprec.c for or
   return std::nearbyint(x / p) * p;
 }
 
-// stats::quantile(type = 7) on an unsorted copy (marge2.R:158-159)
+// stats::quantile(type = 7) (marge2.R:158-159): the two neighbouring order statistics by selection (O(n), no full sort)
 inline double quantile7(std::vector<double> xs, double p) {
-  std::sort(xs.begin(), xs.end());
   const size_t n = xs.size();
   const double index = 1.0 + (double)(n > 0 ? n - 1 : 0) * p;
   const size_t lo = (size_t)std::floor(index), hi = (size_t)std::ceil(index);
+  std::nth_element(xs.begin(), xs.begin() + (lo - 1), xs.end());
   double q = xs[lo - 1];
   const double h = index - (double)lo;
-  if (index > (double)lo && xs[hi - 1] != q) q = (1.0 - h) * q + h * xs[hi - 1];
+  if (hi > lo) {
+    const double xhi = *std::min_element(xs.begin() + lo, xs.end());      // the next order statistic
+    if (index > (double)lo && xhi != q) q = (1.0 - h) * q + h * xhi;
+  }
   return q;
 }
 
-// min_span.R:15-36 (values that would be NA in R -- index past the end -- are simply not produced:
-// the later intersect() drops them anyway)
-inline std::vector<double> min_span(const std::vector<double>& X, int q, int minspan_in, int* minspan_out) {
-  const size_t n = X.size();
-  std::vector<double> x(X);
-  std::sort(x.begin(), x.end());
+// min_span.R:15-36 on an ASCENDING copy of round(x, 4)
+inline std::vector<double> min_span_sorted(const std::vector<double>& x, int q, int minspan_in, int* minspan_out) {
+  const size_t n = x.size();
   int minspan = minspan_in;
   if (minspan < 0) minspan = (int)std::nearbyint(-std::log2(-(1.0 / ((double)q * (double)n)) * std::log(1.0 - 0.05)) / 2.5);
   if (minspan_out) *minspan_out = minspan;
@@ -62,11 +62,8 @@ inline std::vector<double> min_span(const std::vector<double>& X, int q, int min
   return uniq;
 }
 
-// max_span.R:14-26
-inline std::vector<double> max_span(const std::vector<double>& X, int q) {
-  std::vector<double> x(X);
-  std::sort(x.begin(), x.end());
-  x.erase(std::unique(x.begin(), x.end()), x.end());
+// max_span.R:14-26 on the ASCENDING UNIQUE values of round(x, 4)
+inline std::vector<double> max_span_sorted_unique(const std::vector<double>& x, int q) {
   const long n = (long)x.size();
   const long maxspan = (long)std::nearbyint(3.0 - std::log2(0.05 / (double)q));
   const long tail_from = (long)std::floor((double)(n - maxspan + 1));   // 1-based
@@ -80,13 +77,26 @@ inline std::vector<double> max_span(const std::vector<double>& X, int q) {
   return out;
 }
 
-// marge2.R:152-166: returns candidate knots (ascending); X_out = round(x, 4)
-inline std::vector<double> candidate_knots(const std::vector<double>& x_pred, bool approx_knot, int n_knot_max,
-                                           int minspan_in, std::vector<double>* X_out, int* minspan_out) {
-  std::vector<double> X(x_pred.size());
-  for (size_t i = 0; i < X.size(); ++i) X[i] = r_round(x_pred[i], 1e4);
-  std::vector<double> r1 = min_span(X, 1, minspan_in, minspan_out);
-  std::vector<double> r2 = max_span(X, 1);
+inline std::vector<double> min_span(const std::vector<double>& X, int q, int minspan_in, int* minspan_out) {
+  std::vector<double> x(X);
+  std::sort(x.begin(), x.end());
+  return min_span_sorted(x, q, minspan_in, minspan_out);
+}
+
+// max_span.R:14-26
+inline std::vector<double> max_span(const std::vector<double>& X, int q) {
+  std::vector<double> x(X);
+  std::sort(x.begin(), x.end());
+  x.erase(std::unique(x.begin(), x.end()), x.end());
+  return max_span_sorted_unique(x, q);
+}
+
+// marge2.R:152-166 given xs = ASCENDING round(x, 4): returns the candidate knots (ascending)
+inline std::vector<double> candidate_knots_sorted(const std::vector<double>& x_pred, std::vector<double> xs, bool approx_knot,
+                                                  int n_knot_max, int minspan_in, int* minspan_out) {
+  std::vector<double> r1 = min_span_sorted(xs, 1, minspan_in, minspan_out);
+  xs.erase(std::unique(xs.begin(), xs.end()), xs.end());
+  std::vector<double> r2 = max_span_sorted_unique(xs, 1);
   std::vector<double> red;
   for (double v : r1) if (std::binary_search(r2.begin(), r2.end(), v)) red.push_back(v);
   if (approx_knot) {
@@ -103,8 +113,45 @@ inline std::vector<double> candidate_knots(const std::vector<double>& x_pred, bo
       red.swap(s);
     }
   }
+  return red;
+}
+
+// marge2.R:152-166: returns candidate knots (ascending); X_out = round(x, 4)
+inline std::vector<double> candidate_knots(const std::vector<double>& x_pred, bool approx_knot, int n_knot_max,
+                                           int minspan_in, std::vector<double>* X_out, int* minspan_out) {
+  std::vector<double> X(x_pred.size());
+  for (size_t i = 0; i < X.size(); ++i) X[i] = r_round(x_pred[i], 1e4);
+  std::vector<double> xs(X);
+  std::sort(xs.begin(), xs.end());
+  std::vector<double> red = candidate_knots_sorted(x_pred, std::move(xs), approx_knot, n_knot_max, minspan_in, minspan_out);
   if (X_out) X_out->swap(X);
   return red;
+}
+
+// Stable order of the cells by X = round(x, 4).  X is a multiple of 1e-4, so llround(1e4 X) is an order-preserving integer
+// key and a counting sort does it in O(N) when the key range is small (pseudotime in [0, 1]: 10,001 keys); otherwise a
+// comparison sort of (X, index) pairs -- both give exactly the order of a stable sort by X.
+inline std::vector<int32_t> stable_order_by_x(const std::vector<double>& X) {
+  const size_t N = X.size();
+  std::vector<int32_t> order(N);
+  double lo = X[0], hi = X[0];
+  for (double v : X) { if (v < lo) lo = v; if (v > hi) hi = v; }
+  const double span = (hi - lo) * 1e4;
+  if (std::isfinite(span) && span <= 4.0 * (double)N + 1024.0 && std::fabs(lo) < 1e8 && std::fabs(hi) < 1e8) {
+    const long long k0 = std::llround(lo * 1e4);
+    const size_t R = (size_t)(std::llround(hi * 1e4) - k0) + 1;
+    std::vector<int32_t> start(R + 1, 0);
+    std::vector<int32_t> key(N);
+    for (size_t i = 0; i < N; ++i) { key[i] = (int32_t)(std::llround(X[i] * 1e4) - k0); start[(size_t)key[i] + 1]++; }
+    for (size_t k = 0; k < R; ++k) start[k + 1] += start[k];
+    for (size_t i = 0; i < N; ++i) order[(size_t)start[(size_t)key[i]]++] = (int32_t)i;
+    return order;
+  }
+  std::vector<std::pair<double, int32_t>> keyed(N);
+  for (size_t i = 0; i < N; ++i) keyed[i] = {X[i], (int32_t)i};
+  std::sort(keyed.begin(), keyed.end());
+  for (size_t i = 0; i < N; ++i) order[i] = keyed[i].second;
+  return order;
 }
 
 // ---- lineage plan ---------------------------------------------------------------------------------
@@ -158,8 +205,12 @@ inline bool build_lineage_plan(const double* pt_col, int64_t n_cells, const doub
     if (!std::isnan(pt_col[i])) { cells.push_back((int32_t)i); x.push_back(pt_col[i]); }
   const size_t N = x.size();
   if (N < 30) { P.error = "lineage has fewer than 30 cells"; return false; }
-  std::vector<double> X;
-  std::vector<double> knots = candidate_knots(x, o.approx_knot != 0, o.n_knot_max, o.minspan, &X, &P.minspan);
+  std::vector<double> X(N);
+  for (size_t i = 0; i < N; ++i) X[i] = r_round(x[i], 1e4);
+  std::vector<int32_t> order = stable_order_by_x(X);
+  std::vector<double> xs_sorted(N);
+  for (size_t i = 0; i < N; ++i) xs_sorted[i] = X[(size_t)order[i]];
+  std::vector<double> knots = candidate_knots_sorted(x, std::move(xs_sorted), o.approx_knot != 0, o.n_knot_max, o.minspan, &P.minspan);
   if (knots.empty()) { P.error = "no candidate knots (pseudotime has too few distinct values)"; return false; }
   if ((int)knots.size() > TMAX) { P.error = "more than SCLANE_TMAX candidate knots (approx.knot = FALSE is not supported yet)"; return false; }
   std::sort(knots.begin(), knots.end());
@@ -172,9 +223,6 @@ inline bool build_lineage_plan(const double* pt_col, int64_t n_cells, const doub
   L.ref[0] = L.knots[0];
   for (int b = 1; b <= L.T; ++b) L.ref[b] = L.knots[b - 1];
   // stable sort by rounded pseudotime
-  std::vector<int32_t> order(N);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return X[(size_t)a] < X[(size_t)b]; });
   P.perm.resize(N);
   P.Xs.resize(N);
   P.bucket.resize(N);
