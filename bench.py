@@ -292,12 +292,13 @@ def main():
     step_host()
     barrier()
     t1 = time.perf_counter()
-    h2d = d2h = 0.0
+    h2d = d2h = lib_wall = 0.0
     for _ in range(args.steps):
         step_host()
         p = sb.get_profile()
         h2d += p["h2d_bytes"]
         d2h += p["d2h_bytes"]
+        lib_wall += p["wall_ms"]
     barrier()
     e2e_ms = 1000.0 * (time.perf_counter() - t1) / args.steps
     sampler.stop_flag.set()
@@ -354,6 +355,7 @@ def main():
                        "l2": "flushed between timed steps (256 MiB write); per-step working set >> 126 MB L2"},
             "e2e": {"value": e2e_val, "unit": "genes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d / args.steps,
                     "host_buffer": "pageable" if args.pageable else "pinned", "h2d_mode": args.h2d_mode,
+                    "library_wall_ms_per_step": lib_wall / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps, **({"note": e2e_note} if e2e_note else {})},
             "gpu_launches": int(launches),
             "wall_ms_per_step": wall_step,
