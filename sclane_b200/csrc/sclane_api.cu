@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <future>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -39,6 +40,9 @@ void set_err(char* errbuf, size_t errlen, const char* fmt, ...) {
 }
 
 struct CudaFail {
+  std::string msg;
+};
+struct PlanFail {
   std::string msg;
 };
 #define CK(call)                                                                                   \
@@ -193,47 +197,58 @@ bool narrow_to_u16(const int32_t* src, size_t n, uint16_t* dst) {
   return true;
 }
 
+// The lineage plan (host: knots, sort, buckets, points) is built on a background thread while the first batch of counts is
+// already on its way to the device; get() joins it.
+struct PlanSource {
+  const LineagePlan* plan = nullptr;
+  std::shared_future<bool> ready;          // false = the plan could not be built (plan->error says why)
+  const LineagePlan& get() {
+    if (ready.valid() && !ready.get()) throw PlanFail{plan->error};
+    return *plan;
+  }
+};
+
 // Run genes [g0, g1) of one lineage on one device.  Exactly one of h_counts / d_counts is non-null;
 // both are gene-major with leading dimension n_cells.  Records go to out[(g - out_g0) * n_lineages + lin_idx].
 void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int64_t n_cells, int64_t g0, int64_t g1,
-               const LineagePlan& P, const sclane_opts& o, bool use_offset, sclane_record* out, int64_t out_g0, int n_lineages,
+               PlanSource& PS, const sclane_opts& o, bool use_offset, sclane_record* out, int64_t out_g0, int n_lineages,
                int lin_idx, sclane_profile& prof) {
-  if (g1 <= g0) return;
+  if (g1 <= g0) { PS.get(); return; }
   CK(cudaSetDevice(device));
   DevicePool& pool = pool_for(device);
   if (!pool.stream) CK(cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking));
   cudaStream_t s = pool.stream;
-  DevicePlan D;
-  D.upload(P, pool, s);
-  const Lineage& L = P.L;
   const int64_t G = g1 - g0;
-  // X-compressed path (sclane_comp.cuh): worth it when the 4-decimal rounding leaves clearly fewer abscissae than cells
-  const bool use_comp = !o.force_per_cell && P.D > 0 && (double)P.D <= 0.8 * (double)L.N;
-  const int Dpad = (P.D + 31) / 32 * 32;
-  if (use_comp) D.upload_points(P, pool, s);
   // batch size from free memory (+ what the pool already holds): raw (host path) + sorted counts + mu + moments + records
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t per_gene = (h_counts ? (size_t)n_cells * 8 : 0) + (size_t)L.Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
-                          (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0);
-  size_t budget = (size_t)((double)(free_b + pool.held()) * 0.6);
-  const size_t cap = (size_t)SCLANE_BATCH_CAP_GB << 30;
-  if (budget > cap) budget = cap;
-  int64_t B = (int64_t)(budget / per_gene);
-  // host counts: aim for ~8 batches (but >= 2048 genes each, several waves of CTAs) so that the H2D copy of batch k + 1
-  // runs on the copy stream while the kernels of batch k execute
-  if (o.genes_per_batch > 0) { if (o.genes_per_batch < B) B = o.genes_per_batch; }
-  else if (h_counts) {
-    // per-cell final fits (offsets) are compute bound and every launch ends in a tail of slow genes (~160 ms at 30,000 cells):
-    // two batches are enough to hide the transfer; otherwise ~8 batches keep the PCIe link busy
-    const bool heavy_final = use_offset || !use_comp;
-    const int64_t want = std::max<int64_t>(2048, heavy_final ? (G + 1) / 2 : (G + 7) / 8);
-    if (want < B) B = want;
-  }
-  if (B > G) B = G;
-  if (B < 1) throw CudaFail{"not enough free device memory for a single gene"};
-  B = (G + ((G + B - 1) / B) - 1) / ((G + B - 1) / B);      // equal batches: a short last batch is mostly launch tail
-  const int64_t n_batches = (G + B - 1) / B;
+  const size_t pool_held = pool.held();
+  auto batch_size = [&](int Npad, int Dpad, bool use_comp) -> int64_t {
+    const size_t per_gene = (h_counts ? (size_t)n_cells * 8 : 0) + (size_t)Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
+                            (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0);
+    size_t budget = (size_t)((double)(free_b + pool_held) * 0.6);
+    const size_t cap = (size_t)SCLANE_BATCH_CAP_GB << 30;
+    if (budget > cap) budget = cap;
+    int64_t Bv = (int64_t)(budget / per_gene);
+    // host counts: aim for ~8 batches (but >= 2048 genes each, several waves of CTAs) so that the H2D copy of batch k + 1
+    // runs on the copy stream while the kernels of batch k execute
+    if (o.genes_per_batch > 0) { if (o.genes_per_batch < Bv) Bv = o.genes_per_batch; }
+    else if (h_counts) {
+      // per-cell final fits (offsets) are compute bound and every launch ends in a tail of slow genes (~160 ms at 30,000
+      // cells): two batches are enough to hide the transfer; otherwise ~8 batches keep the PCIe link busy
+      const bool heavy_final = use_offset || !use_comp;
+      const int64_t want = std::max<int64_t>(2048, heavy_final ? (G + 1) / 2 : (G + 7) / 8);
+      if (want < Bv) Bv = want;
+    }
+    if (Bv > G) Bv = G;
+    if (Bv < 1) throw CudaFail{"not enough free device memory for a single gene"};
+    return (G + ((G + Bv - 1) / Bv) - 1) / ((G + Bv - 1) / Bv);      // equal batches: a short last batch is mostly launch tail
+  };
+  // Before the plan exists only its size bounds are known: guess the common case (pseudotime in [0, 1]: X-compressed route,
+  // <= 10,001 abscissae), start the first transfer, and redo it in the rare case the real plan asks for a smaller batch.
+  const int Npad_guess = (int)((n_cells + 127) / 128 * 128);
+  int64_t B = batch_size(Npad_guess, 10016, o.force_per_cell == 0);
+  int64_t n_batches = (G + B - 1) / B;
   // staged transfer (see sclane_opts.h2d_mode): automatic = when the copy is big enough to matter and pipelined
   // automatic = pageable caller memory (an R integer matrix): cudaMemcpyAsync from it is staged by the driver at ~12 GB/s,
   // the library's own threads + pinned buffers reach the PCIe rate; a pinned caller buffer (bench.py) is copied directly --
@@ -244,21 +259,25 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     if (cudaPointerGetAttributes(&at, h_counts) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
     else cudaGetLastError();
   }
-  const bool staged = h_counts && (o.h2d_mode == 2 || (o.h2d_mode == 0 && pageable && n_batches >= 2 && (double)G * (double)n_cells * 4.0 >= 256e6));
+  bool staged = false;
   uint16_t* h_stage[2] = {nullptr, nullptr};
   int fmt16[2] = {0, 0};
   int* d_raw2[2] = {nullptr, nullptr};
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   cudaStream_t cs = nullptr;
-  if (h_counts) {
-    if (!pool.copy_stream) CK(cudaStreamCreateWithFlags(&pool.copy_stream, cudaStreamNonBlocking));
-    cs = pool.copy_stream;
+  auto setup_transfer = [&]() {                     // (re)sizes the transfer buffers for the current B
+    staged = h_counts && (o.h2d_mode == 2 || (o.h2d_mode == 0 && pageable && n_batches >= 2 && (double)G * (double)n_cells * 4.0 >= 256e6));
     d_raw2[0] = (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4);
     d_raw2[1] = n_batches > 1 ? (int*)pool.get("raw_b", (size_t)B * (size_t)n_cells * 4) : d_raw2[0];
     if (staged) {
       h_stage[0] = (uint16_t*)pool.get("stage_a", (size_t)B * (size_t)n_cells * 2, true);
       h_stage[1] = n_batches > 1 ? (uint16_t*)pool.get("stage_b", (size_t)B * (size_t)n_cells * 2, true) : h_stage[0];
     }
+  };
+  if (h_counts) {
+    if (!pool.copy_stream) CK(cudaStreamCreateWithFlags(&pool.copy_stream, cudaStreamNonBlocking));
+    cs = pool.copy_stream;
+    setup_transfer();
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
@@ -285,10 +304,30 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.h2d_bytes += (double)n_el * (fmt16[buf] ? 2.0 : 4.0);
     prof.launches[SCLANE_STAGE_COPY]++;
   };
-  if (h_counts) {
-    CK(cudaStreamSynchronize(s));                                       // plan tables are in place before anything overlaps
-    issue_h2d(0);
+  const double h2d_before = prof.h2d_bytes;
+  const long long copies_before = prof.launches[SCLANE_STAGE_COPY];
+  if (h_counts) issue_h2d(0);                      // the first batch travels while the plan is being built
+  const LineagePlan* Pp = nullptr;
+  try { Pp = &PS.get(); }
+  catch (...) { if (h_counts) cudaStreamSynchronize(cs); throw; }      // nothing may be in flight when the caller sees the error
+  const LineagePlan& P = *Pp;
+  const Lineage& L = P.L;
+  // X-compressed path (sclane_comp.cuh): worth it when the 4-decimal rounding leaves clearly fewer abscissae than cells
+  const bool use_comp = !o.force_per_cell && P.D > 0 && (double)P.D <= 0.8 * (double)L.N;
+  const int Dpad = (P.D + 31) / 32 * 32;
+  {
+    const int64_t B_real = batch_size(L.Npad, Dpad, use_comp);
+    if (B_real != B) {                              // the guess was off (other route / more abscissae): restart the transfer
+      if (h_counts) CK(cudaStreamSynchronize(cs));
+      B = B_real;
+      n_batches = (G + B - 1) / B;
+      if (h_counts) { setup_transfer(); prof.h2d_bytes = h2d_before; prof.launches[SCLANE_STAGE_COPY] = copies_before; issue_h2d(0); }
+    }
   }
+  DevicePlan D;
+  D.upload(P, pool, s);
+  if (use_comp) D.upload_points(P, pool, s);
+  CK(cudaStreamSynchronize(s));                     // plan tables are in place before the kernels start
   int* d_ys = (int*)pool.get("ys", (size_t)B * (size_t)L.Npad * 4);
   double* d_mu = (double*)pool.get("mu", (size_t)B * (size_t)L.Npad * 8);
   double* d_mom = (double*)pool.get("mom", (size_t)B * (size_t)NBMAX * NACC * 8);
@@ -668,22 +707,18 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
     }
   }
   for (int l = 0; l < n_lineages; ++l) {
+    // the plan is built on a background thread; in GLM mode the device threads start the first H2D right away and join it
     LineagePlan P;
-    if (!build_lineage_plan(pt + (int64_t)l * n_cells, n_cells, size_factor, *opts, P)) {
-      set_err(errbuf, errlen, "lineage %d: %s", l, P.error.c_str());
-      return SCLANE_ERR_ARG;
-    }
-    if (lineages) {
-      sclane_lineage_info& li = lineages[l];
-      std::memset(&li, 0, sizeof(li));
-      li.n_cells = P.L.N; li.n_knots = P.L.T; li.minspan = P.minspan;
-      for (int k = 0; k < P.L.T; ++k) li.knots[k] = P.L.knots[k];
-      li.pt_min = P.pt_min; li.pt_max = P.pt_max;
-    }
+    std::shared_future<bool> plan_ready = std::async(std::launch::async, [&P, pt, l, n_cells, size_factor, opts]() {
+      return build_lineage_plan(pt + (int64_t)l * n_cells, n_cells, size_factor, *opts, P);
+    }).share();
     GeePlan GPl;
-    if (gee && !build_gee_plan(P, pt + (int64_t)l * n_cells, n_cells, subject_id, size_factor, GPl)) {
-      set_err(errbuf, errlen, "lineage %d: %s", l, GPl.error.c_str());
-      return SCLANE_ERR_ARG;
+    if (gee) {
+      if (!plan_ready.get()) { set_err(errbuf, errlen, "lineage %d: %s", l, P.error.c_str()); return SCLANE_ERR_ARG; }
+      if (!build_gee_plan(P, pt + (int64_t)l * n_cells, n_cells, subject_id, size_factor, GPl)) {
+        set_err(errbuf, errlen, "lineage %d: %s", l, GPl.error.c_str());
+        return SCLANE_ERR_ARG;
+      }
     }
     const int nd = (int)devs.size();
     std::vector<std::string> errs((size_t)nd);
@@ -697,8 +732,12 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
         else {
           // a CSC shard is dense on the device with local gene index 0 = global gene g0
           const int32_t* dc = csc ? shard_base[(size_t)di] - (ptrdiff_t)g0 * (ptrdiff_t)n_cells : d_counts;
-          run_shard(devs[(size_t)di], h_counts, dc, n_cells, g0, g1, P, *opts, size_factor != nullptr, out, 0, n_lineages, l, profs[(size_t)di]);
+          PlanSource PS;
+          PS.plan = &P; PS.ready = plan_ready;
+          run_shard(devs[(size_t)di], h_counts, dc, n_cells, g0, g1, PS, *opts, size_factor != nullptr, out, 0, n_lineages, l, profs[(size_t)di]);
         }
+      } catch (const PlanFail&) {
+        // reported once below, as an argument error
       } catch (const CudaFail& f) {
         errs[(size_t)di] = f.msg;
       } catch (const std::exception& e) {
@@ -710,6 +749,14 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
       std::vector<std::thread> th;
       for (int di = 0; di < nd; ++di) th.emplace_back(work, di);
       for (auto& t : th) t.join();
+    }
+    if (!plan_ready.get()) { set_err(errbuf, errlen, "lineage %d: %s", l, P.error.c_str()); return SCLANE_ERR_ARG; }
+    if (lineages) {
+      sclane_lineage_info& li = lineages[l];
+      std::memset(&li, 0, sizeof(li));
+      li.n_cells = P.L.N; li.n_knots = P.L.T; li.minspan = P.minspan;
+      for (int k = 0; k < P.L.T; ++k) li.knots[k] = P.L.knots[k];
+      li.pt_min = P.pt_min; li.pt_max = P.pt_max;
     }
     for (int di = 0; di < nd; ++di) {
       if (!errs[(size_t)di].empty()) {
