@@ -706,12 +706,19 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
       g_prof.h2d_bytes += h2d0[(size_t)di];
     }
   }
+  // every lineage's plan is built on a background thread, all started now: lineage 0's overlaps the first H2D, the others
+  // are ready long before their turn
+  std::vector<LineagePlan> plans((size_t)n_lineages);
+  std::vector<std::shared_future<bool>> plans_ready((size_t)n_lineages);
   for (int l = 0; l < n_lineages; ++l) {
-    // the plan is built on a background thread; in GLM mode the device threads start the first H2D right away and join it
-    LineagePlan P;
-    std::shared_future<bool> plan_ready = std::async(std::launch::async, [&P, pt, l, n_cells, size_factor, opts]() {
-      return build_lineage_plan(pt + (int64_t)l * n_cells, n_cells, size_factor, *opts, P);
+    LineagePlan* Pl = &plans[(size_t)l];
+    plans_ready[(size_t)l] = std::async(std::launch::async, [Pl, pt, l, n_cells, size_factor, opts]() {
+      return build_lineage_plan(pt + (int64_t)l * n_cells, n_cells, size_factor, *opts, *Pl);
     }).share();
+  }
+  for (int l = 0; l < n_lineages; ++l) {
+    LineagePlan& P = plans[(size_t)l];
+    std::shared_future<bool> plan_ready = plans_ready[(size_t)l];
     GeePlan GPl;
     if (gee) {
       if (!plan_ready.get()) { set_err(errbuf, errlen, "lineage %d: %s", l, P.error.c_str()); return SCLANE_ERR_ARG; }
