@@ -140,7 +140,7 @@ class ClockSampler(threading.Thread):
 def cpu_baseline(counts, pt, n_sample: int):
     """The oracle (kind "port") on the first n_sample genes, single process, on this box's host cores."""
     from threadpoolctl import threadpool_limits
-    from oracle.test_dynamic import test_dynamic as oracle_td
+    from oracle.testdynamic import test_dynamic as oracle_td
     t0 = time.time()
     with threadpool_limits(limits=1):
         oracle_td(counts[:n_sample], pt, None, None, keep_preds=False)
@@ -152,7 +152,7 @@ def cpu_baseline(counts, pt, n_sample: int):
 def _oracle_chunk(a):
     # one gene per worker at a time, like the reference's PSOCK workers; keep BLAS single-threaded per process
     from threadpoolctl import threadpool_limits
-    from oracle.test_dynamic import test_dynamic as oracle_td
+    from oracle.testdynamic import test_dynamic as oracle_td
     counts, pt = a
     with threadpool_limits(limits=1):
         oracle_td(counts, pt, None, None, keep_preds=False)
@@ -167,7 +167,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     from concurrent.futures import ProcessPoolExecutor
-    from sclane_b200 import synth
+    from tools import synth
     cores = os.cpu_count() or 1
     per_core = 8 if cfg["cells"] <= 20000 else 1
     per_step = per_core * cores

@@ -15,6 +15,9 @@
  *     a message is written to errbuf (NUL terminated).  The library never exits, never throws
  *     across the boundary and has NO CPU fallback: without a usable CUDA device every compute
  *     entry point fails with SCLANE_ERR_CUDA.
+ *   - NOT re-entrant: the per-device work buffers, streams and the last-call profile are process-wide.  Every compute
+ *     entry point and sclane_release() take one internal lock, so concurrent callers are serialised (R is single
+ *     threaded, testDynamic.R never calls the path concurrently); do not call the library from a signal handler.
  *   - NA_real_ inputs are NaN (tested with isnan); NaN is emitted for NA outputs.
  *   - all matrices of the eigenMap* drop-ins are column-major doubles, as R/Eigen::Map hand them over.
  */
@@ -39,6 +42,7 @@ extern "C" {
 #define SCLANE_ERR_CUDA 2
 #define SCLANE_ERR_NOMEM 3
 #define SCLANE_ERR_UNSUPPORTED 4
+#define SCLANE_ERR_INTERNAL 5      /* an unexpected C++ exception was caught at the boundary (message in errbuf) */
 
 /* sclane_record.status bits (the four Model_Status strings of testDynamic.R:266-278) */
 #define SCLANE_MARGE_OK 1

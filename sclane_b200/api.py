@@ -39,19 +39,60 @@ def _fmt_num(x: float) -> str:
     return f"{x:.15g}"
 
 
-def _p_adjust_bh(p: np.ndarray) -> np.ndarray:
-    """stats::p.adjust(method = "fdr"); NA stays NA and is not counted."""
+def _p_adjust(p: np.ndarray, method: str = "fdr") -> np.ndarray:
+    """stats::p.adjust(p, method) for every method of stats::p.adjust.methods (getResultsDE.R:25,39; testSlope.R:24,31);
+    NA stays NA and is not counted in n."""
+    if method not in ("holm", "hochberg", "hommel", "bonferroni", "BH", "BY", "fdr", "none"):
+        raise ValueError("Please choose a valid p-value adjustment method.")
     p = np.asarray(p, dtype=np.float64)
     out = np.full(p.shape, np.nan)
     ok = ~np.isnan(p)
     pv = p[ok]
     n = pv.size
-    if n:
+    if n == 0 or method == "none":
+        out[ok] = pv
+        return out
+    if method == "bonferroni":
+        adj = np.minimum(1.0, n * pv)
+    elif method == "holm":
+        o = np.argsort(pv, kind="stable")
+        ro = np.argsort(o, kind="stable")
+        adj = np.minimum(1.0, np.maximum.accumulate((n - np.arange(n)) * pv[o]))[ro]
+    elif method == "hochberg":
         o = np.argsort(-pv, kind="stable")
         ro = np.argsort(o, kind="stable")
         i = np.arange(n, 0, -1, dtype=np.float64)
-        out[ok] = np.minimum(1.0, np.minimum.accumulate(n / i * pv[o]))[ro]
+        adj = np.minimum(1.0, np.minimum.accumulate((n - i + 1.0) * pv[o]))[ro]
+    elif method in ("BH", "fdr", "BY"):
+        o = np.argsort(-pv, kind="stable")
+        ro = np.argsort(o, kind="stable")
+        i = np.arange(n, 0, -1, dtype=np.float64)
+        q = float(np.sum(1.0 / np.arange(1, n + 1))) if method == "BY" else 1.0
+        adj = np.minimum(1.0, np.minimum.accumulate(q * n / i * pv[o]))[ro]
+    else:   # hommel (stats::p.adjust source, restated)
+        if n > 1:
+            o = np.argsort(pv, kind="stable")
+            ps = pv[o]
+            ro = np.argsort(o, kind="stable")
+            i = np.arange(1, n + 1, dtype=np.float64)
+            q = pa = np.full(n, np.min(n * ps / i))
+            for m in range(n - 1, 1, -1):
+                i1 = np.arange(0, n - m + 1)
+                i2 = np.arange(n - m + 1, n)
+                q1 = np.min(m * ps[i2] / np.arange(2, m + 1))
+                q = q.copy()
+                q[i1] = np.minimum(m * ps[i1], q1)
+                q[i2] = q[n - m]
+                pa = np.maximum(pa, q)
+            adj = np.maximum(pa, ps)[ro]
+        else:
+            adj = pv.copy()
+    out[ok] = adj
     return out
+
+
+def _p_adjust_bh(p: np.ndarray) -> np.ndarray:
+    return _p_adjust(p, "fdr")
 
 
 def _na(x):
@@ -184,6 +225,8 @@ def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = Non
             raise SclaneError(4, "sparse input is built for GLM mode only")
         csc.sort_indices()
         n_genes = csc.shape[0]
+        if int(csc.indptr[-1]) > np.iinfo(np.int32).max:
+            raise ValueError("sparse expr.mat has more than 2^31 - 1 non-zeros: split the genes into several calls")
         indptr = np.ascontiguousarray(csc.indptr, dtype=np.int32)
         indices = np.ascontiguousarray(csc.indices, dtype=np.int32)
         data = np.ascontiguousarray(csc.data, dtype=np.float64)
@@ -718,15 +761,13 @@ def getResultsDE(test_dyn_res=None, p_adj_method: str = "fdr", fdr_cutoff: float
     P_Val_Adj < cutoff (NA -> 0), per-gene max over lineages.  Returns a pandas DataFrame."""
     if test_dyn_res is None:
         raise ValueError("Please provide a result list from testDynamic().")
-    if p_adj_method not in ("fdr", "BH"):
-        raise ValueError("Please choose a valid p-value adjustment method.")
     import pandas as pd
     keys = ["Gene", "Lineage", "Test_Stat", "Test_Stat_Type", "Test_Stat_Note", "Degrees_Freedom", "P_Val", "LogLik_MARGE",
             "LogLik_Null", "Dev_MARGE", "Dev_Null", "Model_Status", "MARGE_Fit_Notes", "Null_Fit_Notes", "Gene_Time"]
     rows = [{k: r[k] for k in keys} for lins in test_dyn_res.values() for r in lins.values()]
     df = pd.DataFrame(rows, columns=keys)
     df = df.sort_values("Test_Stat", ascending=False, kind="stable", na_position="last").reset_index(drop=True)
-    padj = _p_adjust_bh(df["P_Val"].to_numpy(dtype=np.float64, na_value=np.nan))
+    padj = _p_adjust(df["P_Val"].to_numpy(dtype=np.float64, na_value=np.nan), p_adj_method)
     df["P_Val_Adj"] = padj
     df["Gene_Dynamic_Lineage"] = np.where(np.isnan(padj), 0, (padj < fdr_cutoff).astype(int))
     df["Gene_Dynamic_Overall"] = df.groupby("Gene")["Gene_Dynamic_Lineage"].transform("max")
@@ -743,7 +784,7 @@ def testSlope(test_dyn_res=None, p_adj_method: str = "fdr", fdr_cutoff: float = 
     df = pd.concat(frames, ignore_index=True)
     df["_abs"] = df["Test_Stat"].astype(float).abs()
     df = df.sort_values("_abs", ascending=False, kind="stable", na_position="last").drop(columns="_abs")
-    df["P_Val_Adj"] = _p_adjust_bh(df["P_Val"].to_numpy(dtype=np.float64, na_value=np.nan))
+    df["P_Val_Adj"] = _p_adjust(df["P_Val"].to_numpy(dtype=np.float64, na_value=np.nan), p_adj_method)
     df = df.sort_values(["Gene", "Breakpoint"], kind="stable", na_position="last").reset_index(drop=True)
     padj = df["P_Val_Adj"].to_numpy(dtype=np.float64)
     df["Gene_Dynamic_Lineage_Slope"] = np.where(np.isnan(padj), 0, (padj < fdr_cutoff).astype(int))

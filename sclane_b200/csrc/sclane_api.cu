@@ -45,6 +45,41 @@ struct CudaFail {
 struct PlanFail {
   std::string msg;
 };
+
+// The library is NOT re-entrant: the per-device buffer pools, their streams and the profile of the last call are process-wide.
+// Every exported compute entry point (and sclane_release) therefore runs under this one lock -- concurrent callers are
+// serialised, never corrupted -- and inside a try block: nothing is ever thrown across the C ABI.
+std::mutex g_call_mu;
+template <class F>
+int32_t guarded(char* errbuf, size_t errlen, F&& body) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  try {
+    return body();
+  } catch (const CudaFail& f) {
+    set_err(errbuf, errlen, "%s", f.msg.c_str());
+    return SCLANE_ERR_CUDA;
+  } catch (const PlanFail& f) {
+    set_err(errbuf, errlen, "%s", f.msg.c_str());
+    return SCLANE_ERR_ARG;
+  } catch (const std::bad_alloc&) {
+    set_err(errbuf, errlen, "out of host memory");
+    return SCLANE_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    set_err(errbuf, errlen, "internal error: %s", e.what());
+    return SCLANE_ERR_INTERNAL;
+  } catch (...) {
+    set_err(errbuf, errlen, "internal error (unknown exception)");
+    return SCLANE_ERR_INTERNAL;
+  }
+}
+
+// joins its threads on every exit path (an exception between creation and join would otherwise terminate the host)
+struct ThreadGroup {
+  std::vector<std::thread> th;
+  template <class F, class... A> void run(F&& f, A&&... a) { th.emplace_back(std::forward<F>(f), std::forward<A>(a)...); }
+  void join() { for (auto& t : th) if (t.joinable()) t.join(); th.clear(); }
+  ~ThreadGroup() { join(); }
+};
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
@@ -192,7 +227,7 @@ bool narrow_to_u16(const int32_t* src, size_t n, uint16_t* dst) {
     bad[t] = (int)acc;
   };
   if (nt == 1) work(0);
-  else { std::vector<std::thread> th; for (size_t t = 0; t < nt; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+  else { ThreadGroup tg; for (size_t t = 0; t < nt; ++t) tg.run(work, t); tg.join(); }
   for (int b : bad) if (b) return false;
   return true;
 }
@@ -654,6 +689,14 @@ const int32_t* expand_csc_shard(int device, const CscInput& c, int64_t n_cells, 
   return dense;
 }
 
+void drain_device(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
+  DevicePool& pool = pool_for(device);
+  if (pool.copy_stream) cudaStreamSynchronize(pool.copy_stream);
+  if (pool.stream) cudaStreamSynchronize(pool.stream);
+  cudaGetLastError();
+}
+
 int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int device_for_d, int64_t n_cells, int64_t n_genes,
                       const double* pt, int32_t n_lineages, const double* size_factor, const sclane_opts* opts,
                       sclane_record* out, sclane_lineage_info* lineages, char* errbuf, size_t errlen,
@@ -697,9 +740,10 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
       try { shard_base[(size_t)di] = expand_csc_shard(devs[(size_t)di], *csc, n_cells, g0, g1, h2d0[(size_t)di]); }
       catch (const CudaFail& f) { errs0[(size_t)di] = f.msg; }
       catch (const std::exception& e) { errs0[(size_t)di] = e.what(); }
+      catch (...) { errs0[(size_t)di] = "unknown exception"; }
     };
     if (nd0 == 1) expand(0);
-    else { std::vector<std::thread> th; for (int di = 0; di < nd0; ++di) th.emplace_back(expand, di); for (auto& t : th) t.join(); }
+    else { ThreadGroup tg; for (int di = 0; di < nd0; ++di) tg.run(expand, di); tg.join(); }
     for (int di = 0; di < nd0; ++di) {
       if (!errs0[(size_t)di].empty()) { set_err(errbuf, errlen, "device %d: %s", devs[(size_t)di], errs0[(size_t)di].c_str()); return SCLANE_ERR_CUDA; }
       std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -749,13 +793,18 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
         errs[(size_t)di] = f.msg;
       } catch (const std::exception& e) {
         errs[(size_t)di] = e.what();
+      } catch (...) {
+        errs[(size_t)di] = "unknown exception";
       }
+      // whatever happened, nothing of this shard may still be in flight (an async H2D out of the caller's buffer, a kernel
+      // writing the pooled buffers) when the caller sees the return code
+      drain_device(devs[(size_t)di]);
     };
     if (nd == 1) work(0);
     else {
-      std::vector<std::thread> th;
-      for (int di = 0; di < nd; ++di) th.emplace_back(work, di);
-      for (auto& t : th) t.join();
+      ThreadGroup tg;
+      for (int di = 0; di < nd; ++di) tg.run(work, di);
+      tg.join();
     }
     if (!plan_ready.get()) { set_err(errbuf, errlen, "lineage %d: %s", l, P.error.c_str()); return SCLANE_ERR_ARG; }
     if (lineages) {
@@ -1037,15 +1086,10 @@ bool model_from_terms(const int32_t* kind, const int32_t* knot_idx, int n_terms,
 }  // namespace
 
 // =====================================================================================================
-// exported C ABI
+// entry point bodies (the exported symbols at the end of the file wrap them in guarded(): lock + try/catch)
 // =====================================================================================================
-extern "C" {
+namespace impl {
 
-int32_t sclane_abi_version(void) { return SCLANE_ABI_VERSION; }
-int32_t sclane_device_count(void) { return usable_devices(); }
-size_t sclane_record_size(void) { return sizeof(sclane_record); }
-int64_t sclane_launch_count(void) { return g_launches.load(); }
-void sclane_reset_launch_count(void) { g_launches.store(0); }
 
 void sclane_default_opts(sclane_opts* o) {
   if (!o) return;
@@ -1284,6 +1328,9 @@ int32_t sclane_smoothed_counts(const sclane_record* recs, int64_t n_genes, int32
 
 int32_t sclane_matmul(const double* A, const double* B, double* C, int64_t m, int64_t k, int64_t n, int32_t device, char* errbuf, size_t errlen) {
   if (!A || !B || !C || m < 1 || k < 1 || n < 1) { set_err(errbuf, errlen, "bad arguments"); return SCLANE_ERR_ARG; }
+  if (m > 0x7fffffff || k > 0x7fffffff || n > 0x7fffffff || (m + 15) / 16 > 0x7fffffff || (n + 15) / 16 > 65535) {
+    set_err(errbuf, errlen, "matrix dimensions out of range (m, k < 2^31; n <= 1,048,560)"); return SCLANE_ERR_ARG;
+  }
   if (usable_devices() <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
   try {
     CK(cudaSetDevice(device));
@@ -1340,6 +1387,96 @@ int32_t sclane_pinv(const double* A, double* Apinv, int64_t m, int64_t n, double
     else for (int64_t r = 0; r < n; ++r) for (int64_t c = 0; c < m; ++c) Apinv[(size_t)(c * n + r)] = P[(size_t)(r * nn + c)];   // transpose back: (m x n)^T
   } catch (const CudaFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_CUDA; }
   return SCLANE_OK;
+}
+
+}  // namespace impl
+
+// =====================================================================================================
+// exported C ABI: every body runs under the library lock and inside a try block (see guarded())
+// =====================================================================================================
+extern "C" {
+
+int32_t sclane_abi_version(void) { return SCLANE_ABI_VERSION; }
+int32_t sclane_device_count(void) { return usable_devices(); }
+size_t sclane_record_size(void) { return sizeof(sclane_record); }
+int64_t sclane_launch_count(void) { return g_launches.load(); }
+void sclane_reset_launch_count(void) { g_launches.store(0); }
+void sclane_default_opts(sclane_opts* o) { impl::sclane_default_opts(o); }
+void sclane_get_profile(sclane_profile* out) { impl::sclane_get_profile(out); }
+void sclane_release(void) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  try { impl::sclane_release(); } catch (...) {}
+}
+
+int32_t sclane_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
+                            const double* size_factor, const sclane_opts* opts, sclane_record* out,
+                            sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_test_dynamic(counts, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen);
+  });
+}
+int32_t sclane_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
+                                const int32_t* subject_id, const double* size_factor, const sclane_opts* opts, sclane_record* out,
+                                sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_test_dynamic_gee(counts, n_cells, n_genes, pt, n_lineages, subject_id, size_factor, opts, out, lineages, errbuf, errlen);
+  });
+}
+int32_t sclane_test_dynamic_csc(const int32_t* indptr, const int32_t* indices, const double* data, int64_t n_cells, int64_t n_genes,
+                                const double* pt, int32_t n_lineages, const double* size_factor, const sclane_opts* opts,
+                                sclane_record* out, sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_test_dynamic_csc(indptr, indices, data, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen);
+  });
+}
+int32_t sclane_test_dynamic_device(const int32_t* d_counts, int32_t device, int64_t n_cells, int64_t n_genes, const double* pt,
+                                   int32_t n_lineages, const double* size_factor, const sclane_opts* opts, sclane_record* out,
+                                   sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_test_dynamic_device(d_counts, device, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen);
+  });
+}
+int32_t sclane_candidate_knots(const double* x, int64_t n, const sclane_opts* opts, double* knots_out, int32_t* minspan_out) {
+  try { return impl::sclane_candidate_knots(x, n, opts, knots_out, minspan_out); }
+  catch (const std::bad_alloc&) { return -SCLANE_ERR_NOMEM; }
+  catch (...) { return -SCLANE_ERR_INTERNAL; }
+}
+int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* x, const double* knots,
+                              int32_t n_knots, const int32_t* term_kind, const int32_t* term_knot_idx, int32_t n_terms,
+                              int32_t device, double* beta_out, double* sigma_out, double* mu_out, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_null_stats_glm(counts, n_cells, n_genes, x, knots, n_knots, term_kind, term_knot_idx, n_terms, device, beta_out, sigma_out, mu_out, errbuf, errlen);
+  });
+}
+int32_t sclane_score_glm(const int32_t* counts, const double* mu, int64_t n_cells, int64_t n_genes, const double* x,
+                         const double* knots, int32_t n_knots, const int32_t* term_kind, const int32_t* term_knot_idx,
+                         int32_t n_terms, const double* sigma, int32_t device, double* scores_out, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_score_glm(counts, mu, n_cells, n_genes, x, knots, n_knots, term_kind, term_knot_idx, n_terms, sigma, device, scores_out, errbuf, errlen);
+  });
+}
+int32_t sclane_link_preds(const sclane_record* rec, const double* x, int64_t n, const double* size_factor, int32_t device,
+                          double* marge_link_fit, double* marge_link_se, double* null_link_fit, double* null_link_se,
+                          char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_link_preds(rec, x, n, size_factor, device, marge_link_fit, marge_link_se, null_link_fit, null_link_se, errbuf, errlen);
+  });
+}
+int32_t sclane_smoothed_counts(const sclane_record* recs, int64_t n_genes, int32_t n_lineages, int32_t lineage, const double* x, int64_t n,
+                               const double* size_factor, int32_t is_gee, int32_t log1p_norm, int32_t device, double* out,
+                               char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_smoothed_counts(recs, n_genes, n_lineages, lineage, x, n, size_factor, is_gee, log1p_norm, device, out, errbuf, errlen);
+  });
+}
+int32_t sclane_matmul(const double* A, const double* B, double* C, int64_t m, int64_t k, int64_t n, int32_t device, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t { return impl::sclane_matmul(A, B, C, m, k, n, device, errbuf, errlen); });
+}
+int32_t sclane_llt_inverse(const double* A, double* Ainv, int64_t n, int32_t device, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t { return impl::sclane_llt_inverse(A, Ainv, n, device, errbuf, errlen); });
+}
+int32_t sclane_pinv(const double* A, double* Apinv, int64_t m, int64_t n, double tolerance, int32_t device, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t { return impl::sclane_pinv(A, Apinv, m, n, tolerance, device, errbuf, errlen); });
 }
 
 }  // extern "C"

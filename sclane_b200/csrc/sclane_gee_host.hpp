@@ -90,11 +90,13 @@ inline void finalize_record_gee(const GeeGeneOut& g, const Lineage& L, int gee_t
     }
     r.gee_alpha = g.alt.alpha; r.gee_phi = g.alt.phi;
     r.gee_converged = g.alt.converged; r.gee_iters = g.alt.niter;
-    // waldTestGEE(): W = b' (L V L')^-1 b over the non-intercept coefficients, naive variance
-    if (p <= 1) { r.test_stat = 0.0; r.df = 0.0; r.p_val = 1.0; }
+    // waldTestGEE(): W = b' (L V L')^-1 b over the non-intercept coefficients, naive variance.  Both tests return NA for
+    // Wald_Stat / DF / P_Val when EITHER model is a try-error (waldTestGEE.R:31-37, scoreTestGEE.R:34-39)
+    if (!null_ok) { /* test_stat, df, p_val stay NaN */ }
+    else if (p <= 1) { r.test_stat = 0.0; r.df = 0.0; r.p_val = 1.0; }
     else if (gee_test == 1) {
       // scoreTestGEE(): statistic from the device; NA when the null model failed (scoreTestGEE.R:34-39)
-      if (null_ok) { r.test_stat = g.alt.score_stat; r.df = (double)(p - 1); r.p_val = 1.0 - (1.0 - pchisq_upper(r.test_stat, r.df)); }
+      r.test_stat = g.alt.score_stat; r.df = (double)(p - 1); r.p_val = 1.0 - (1.0 - pchisq_upper(r.test_stat, r.df));
     } else {
       // biasCorrectGEE.R: "df" n_s / (n_s - p) (unchanged when p >= n_s); "kc" (n_s / (n_s - 1)) / (1 - tr(H) / n) with
       // tr(H) = p (H is a rank-p projection); both scale the sandwich variance

@@ -15,7 +15,7 @@ TOL = 1e-6          # relative, fp64 statistics (north_star tolerance); discrete
 
 
 def _gee_data(seed=5, sizes=(150, 1, 120, 89), n_genes=6, sorted_within=False):
-    from sclane_b200 import synth
+    from tools import synth
     n = int(sum(sizes))
     counts, pt, _ = synth.make_counts(n_genes=n_genes, n_cells=n, seed=seed)
     pt = np.asarray(pt, dtype=np.float64).reshape(-1)
@@ -206,7 +206,8 @@ def test_gee_bias_corrected_sandwich_gpu_vs_dense_oracle():
 def test_gee_gpu_vs_core_at_config3_subject_size(emu):
     """BASELINE configs[2]'s shape per subject (3 subjects x 10,000 cells, AR-1; pseudotime-sorted within subject for the
     first half of the genes' run, arbitrary order for the second): k_gee vs the serial run of the same core."""
-    from sclane_b200 import _abi, api, synth
+    from sclane_b200 import _abi, api
+    from tools import synth
     counts, pt, _ = synth.make_counts(8, 30000, seed=23)
     counts = np.ascontiguousarray(counts, dtype=np.int32)
     pt = np.asarray(pt, dtype=np.float64).reshape(-1)

@@ -11,7 +11,7 @@ from oracle.eigen_helpers import eigen_map_mat_mult, eigen_map_matrix_invert, ei
 from oracle.knots import candidate_knots
 from oracle.nbfit import nb_mle
 from oracle.rmath import p_adjust_bh
-from oracle.test_dynamic import test_dynamic as oracle_test_dynamic
+from oracle.testdynamic import test_dynamic as oracle_test_dynamic
 
 pytestmark = pytest.mark.gpu
 
@@ -113,7 +113,7 @@ def test_bundled_vs_reference_golden(gpu_golden, golden_models, golden_preds):
 def test_synthetic_vs_oracle_with_edge_cases():
     """Seeded synthetic NB counts incl. an all-zero gene, a nearly empty gene, a huge-count gene and a near-Poisson gene."""
     import sclane_b200 as sb
-    from sclane_b200 import synth
+    from tools import synth
     counts, pt, _ = synth.make_counts(40, 3000, seed=11)
     rng = np.random.default_rng(5)
     counts[3] = 0
@@ -130,7 +130,7 @@ def test_synthetic_vs_oracle_with_edge_cases():
 def test_two_lineages_with_offsets_vs_oracle():
     """C4-shaped: two lineages sharing a root (NaN = not in lineage), size-factor offsets from createCellOffset()."""
     import sclane_b200 as sb
-    from sclane_b200 import synth
+    from tools import synth
     counts, pt, _ = synth.make_counts(24, 4000, seed=21, n_lineages=2)
     sf = sb.createCellOffset(counts)
     genes = [f"g{i}" for i in range(24)]
@@ -225,7 +225,7 @@ def test_full_size_properties():
     gene-order independence and batching independence are bit-exact; a permutation of the cells leaves every
     statistic unchanged to rounding; LRT >= 0 whenever the alternative nests the null; FDR calls are a function of P."""
     import sclane_b200 as sb
-    from sclane_b200 import synth
+    from tools import synth
     counts, pt, _ = synth.make_counts(192, 10000, seed=312)
     base = sb.testDynamic(counts, pt, n_gpus=1)
     recs = base.records
@@ -265,7 +265,7 @@ def test_compressed_path_vs_per_cell_path():
     kHistCap (4096; kept as a sorted list), gene 5 more than kBigCap (8192) of them, which routes it to the per-cell
     kernels inside the compressed run."""
     import sclane_b200 as sb
-    from sclane_b200 import synth
+    from tools import synth
     counts, pt, _ = synth.make_counts(96, 20000, seed=21)
     counts = np.ascontiguousarray(counts, dtype=np.int32)
     counts[5, :9000] = 4100 + (np.arange(9000) % 900)
@@ -291,7 +291,8 @@ def test_negative_counts_fail_the_gene_only():
     """A negative count makes both models of that gene fail (glm.nb: 'negative values not allowed'), on every route, and
     leaves the other genes untouched."""
     import sclane_b200 as sb
-    from sclane_b200 import _abi, synth
+    from sclane_b200 import _abi
+    from tools import synth
     counts, pt, _ = synth.make_counts(12, 3000, seed=4)
     counts = np.ascontiguousarray(counts, dtype=np.int32)
     ref = sb.testDynamic(counts, pt, n_gpus=1, preds="none")
@@ -336,7 +337,8 @@ def test_sparse_csc_input_equals_dense():
     dense entry point, with offsets and two lineages; bad indices are rejected."""
     import scipy.sparse as sp
     import sclane_b200 as sb
-    from sclane_b200 import _abi, api, synth
+    from sclane_b200 import _abi, api
+    from tools import synth
     counts, pt, _ = synth.make_counts(40, 6000, seed=8)
     counts = np.ascontiguousarray(counts, dtype=np.int32)
     counts[:, ::3] = 0                                           # sparser than the generator makes it
@@ -371,7 +373,7 @@ def test_default_workload_cell_count_vs_oracle():
     """BASELINE configs[4]'s cell count (200,000 cells, 10,000 distinct abscissae -> X-compressed route): six genes of the
     bench generator against the dense oracle (about 7 s of numpy per gene)."""
     import sclane_b200 as sb
-    from sclane_b200 import synth
+    from tools import synth
     counts, pt, _ = synth.make_counts(6, 200000, seed=312)
     res = sb.testDynamic(counts, pt, n_gpus=1, preds="none")
     assert res.profile["ms"]["comp_final"] > 0
@@ -382,7 +384,8 @@ def test_default_workload_cell_count_vs_oracle():
 def test_staged_uint16_transfer_equals_direct():
     """h2d_mode = 2 (host threads narrow every gene batch to uint16 into pinned staging, double buffered) gives byte-identical
     records to the direct int32 copy, on both routes; a batch holding a count > 65534 or a negative count falls back to int32."""
-    from sclane_b200 import api, synth
+    from sclane_b200 import api
+    from tools import synth
     counts, pt, _ = synth.make_counts(90, 9000, seed=17)
     counts = np.ascontiguousarray(counts, dtype=np.int32)
     counts[33, 100] = 70000            # does not fit uint16 -> its batch goes direct
@@ -406,7 +409,7 @@ def test_other_basis_budgets_vs_oracle(M):
     """n.potential.basis.fns = 3 (one forward iteration) and 7 (three iterations, up to seven columns -- SCLANE_PMAX), both
     routes, against the oracle."""
     import sclane_b200 as sb
-    from sclane_b200 import synth
+    from tools import synth
     counts, pt, _ = synth.make_counts(20, 16000, seed=29)
     ref = oracle_test_dynamic(np.asarray(counts), np.asarray(pt, dtype=np.float64).reshape(-1), None, None, n_potential_basis_fns=M,
                               keep_preds=False)

@@ -10,7 +10,7 @@ import pytest
 from conftest import ROOT, has_gpu, record_terms, rel
 from oracle import knots as oknots
 from oracle import rmath
-from oracle.test_dynamic import test_dynamic as oracle_test_dynamic
+from oracle.testdynamic import test_dynamic as oracle_test_dynamic
 
 
 def test_library_exports_every_declared_symbol():
@@ -117,7 +117,7 @@ def test_core_algorithm_vs_oracle_bundled(emu, golden_inputs):
 
 
 def test_core_algorithm_vs_oracle_synthetic(emu):
-    from sclane_b200 import synth
+    from tools import synth
     counts, pt, _ = synth.make_counts(16, 2500, seed=7)
     counts[3] = 0                      # all-zero gene
     counts[5] = (np.arange(2500) % 97 == 0).astype(np.int32)   # nearly empty gene

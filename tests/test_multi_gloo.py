@@ -21,7 +21,8 @@ def _worker(rank, world, port, n_genes, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import ctypes as C
     import __graft_entry__ as ge
-    from sclane_b200 import _abi, shard, synth
+    from sclane_b200 import _abi, shard
+    from tools import synth
     counts, pt, _ = synth.make_counts(n_genes, 1500, seed=99)
     g0, g1 = shard.gene_shard(rank, world, n_genes)
     lib = C.CDLL(ge.EMU)
@@ -58,7 +59,8 @@ def test_gene_shards_cover_and_are_contiguous():
 
 
 def test_two_rank_gloo_matches_single_rank(tmp_path, emu):
-    from sclane_b200 import _abi, synth
+    from sclane_b200 import _abi
+    from tools import synth
     import ctypes as C
     n_genes = 10
     port = 29500 + (os.getpid() % 2000)

@@ -6,7 +6,7 @@ from conftest import GOLDEN_EXCEPTIONS, rel
 from oracle.knots import candidate_knots, tp1, tp2
 from oracle.nbfit import glm_nb
 from oracle.rmath import p_adjust_bh, quantile7, r_round, r_signif
-from oracle.test_dynamic import create_cell_offset, get_results_de, test_dynamic as oracle_test_dynamic
+from oracle.testdynamic import create_cell_offset, get_results_de, test_dynamic as oracle_test_dynamic
 
 GOLDEN_KNOTS = [0.055, 0.0922, 0.1294, 0.1666, 0.2037, 0.2409, 0.2781, 0.3153, 0.3525, 0.3897, 0.4269, 0.4641, 0.5012,
                 0.5384, 0.5756, 0.6128, 0.65, 0.6872, 0.7244, 0.7616, 0.7988, 0.8359, 0.8731, 0.9103, 0.9475]

@@ -3,7 +3,7 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sclane_b200 as sb
-from sclane_b200 import synth
+from tools import synth
 n = sb.device_count()
 counts, pt, _ = synth.make_counts(301, 20000, seed=5)      # D = 10,000 abscissae: the X-compressed route
 a = sb.testDynamic(counts, pt, n_gpus=1, preds="none")

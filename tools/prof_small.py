@@ -8,7 +8,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sclane_b200 as sb
-from sclane_b200 import synth
+from tools import synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--genes", type=int, default=296)

@@ -7,7 +7,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sclane_b200 as sb
-from sclane_b200 import synth
+from tools import synth
 
 counts, pt, _ = synth.make_counts(24, 4000, seed=3)
 counts = np.ascontiguousarray(counts, dtype=np.int32)
