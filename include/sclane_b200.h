@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SCLANE_ABI_VERSION 2
+#define SCLANE_ABI_VERSION 3
 #define SCLANE_PMAX 7          /* max columns of a model (intercept + hinges): M <= 7 (marge2.R:756) */
 #define SCLANE_TMAX 32         /* max candidate knots per lineage (n.knot.max, marge2.R:66; default 25) */
 #define SCLANE_MAX_GPUS 16
@@ -94,7 +94,13 @@ typedef struct sclane_opts {
                                  buffer), 2 = staged (host threads narrow each gene batch to uint16 into pinned staging buffers while
                                  the previous batch is in flight: half the PCIe bytes, and full PCIe speed from pageable R memory);
                                  a batch holding a count > 65534 or < 0 always goes direct */
-  int32_t reserved[3];
+  int32_t comp_warp_per_gene; /* testing / profiling only: 1 = run the X-compressed fits (no offset) on the warp-per-gene persistent
+                                 kernels instead of the CTA-per-gene ones (same records; measured: 1.2-1.45x the steady-state
+                                 throughput but the slowest gene runs 5x longer on one warp, so the launch is tail bound --
+                                 profiles/r02_tail_cycles.txt).  The offset quadrature always runs warp per gene. */
+  int32_t offset_per_cell;    /* testing / profiling only: 1 = fit the intercept-only models with an offset per cell instead of
+                                 through the offset quadrature */
+  int32_t reserved[1];
 } sclane_opts;
 
 /* One record per (gene, lineage): everything testDynamic() returns for that pair except the
@@ -144,6 +150,9 @@ typedef struct sclane_record {
   double  null_gee_alpha, null_gee_phi;
   int32_t gee_converged, gee_iters;     /* geem outer iterations of the final model */
   int32_t null_gee_converged, null_gee_iters;
+  /* profiling: SM clock cycles (clock64) the gene spent in the forward / backward / final kernels (whatever unit -- warp or
+   * CTA -- fitted it); 0 where a stage did not run.  Used by tools/tail_analysis.py; not part of the reference's record. */
+  double  stage_cycles[3];
 } sclane_record;
 
 /* Per-lineage description returned to the caller (knots, cell membership). */
@@ -170,7 +179,7 @@ void sclane_reset_launch_count(void);
 
 /* Device-side timing of the last sclane_test_dynamic*() call on this process (CUDA events on the
  * library's own stream, summed over batches / lineages / GPUs): what bench.py's roofline uses. */
-#define SCLANE_NSTAGES 12
+#define SCLANE_NSTAGES 14
 #define SCLANE_STAGE_GATHER 0      /* sort permutation + per-gene constants                                  */
 #define SCLANE_STAGE_FWD_FIT 1     /* K1 forward null fits (stat_out_score_glm_null)                         */
 #define SCLANE_STAGE_SWEEP 2       /* K2a score sweep, streaming kernel k_sweep_moments (HBM bound)          */
@@ -183,6 +192,8 @@ void sclane_reset_launch_count(void);
 #define SCLANE_STAGE_COMP_FWD 9    /* X-compressed forward pass: null fits + score sweep + selection         */
 #define SCLANE_STAGE_COMP_BWD 10   /* X-compressed backward WIC pass                                         */
 #define SCLANE_STAGE_COMP_FINAL 11 /* X-compressed final + null glm.nb (no offset)                            */
+#define SCLANE_STAGE_OFF_AGG 12    /* offset quadrature: per-gene node weights (k_off_aggregate)               */
+#define SCLANE_STAGE_OFF_NULL 13   /* offset quadrature: intercept-only glm.nb with the size-factor offset     */
 typedef struct sclane_profile {
   double  ms[SCLANE_NSTAGES];          /* device milliseconds per stage                                   */
   int64_t launches[SCLANE_NSTAGES];    /* kernel launches (memcpys for SCLANE_STAGE_COPY) per stage        */

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-SCLANE_ABI_VERSION = 2
+SCLANE_ABI_VERSION = 3
 SCLANE_PMAX = 7
 SCLANE_TMAX = 32
 SCLANE_MAX_GPUS = 16
@@ -46,7 +46,9 @@ class SclaneOpts(C.Structure):
         ("force_per_cell", C.c_int32),
         ("gee_bias_correction", C.c_int32),
         ("h2d_mode", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("comp_warp_per_gene", C.c_int32),
+        ("offset_per_cell", C.c_int32),
+        ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -101,6 +103,7 @@ class SclaneRecord(C.Structure):
         ("gee_iters", C.c_int32),
         ("null_gee_converged", C.c_int32),
         ("null_gee_iters", C.c_int32),
+        ("stage_cycles", C.c_double * 3),
     ]
 
 

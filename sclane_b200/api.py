@@ -154,13 +154,13 @@ def release() -> None:
 
 
 class _Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_int64 * 12), ("sweep_bytes", C.c_double),
+    _fields_ = [("ms", C.c_double * 14), ("launches", C.c_int64 * 14), ("sweep_bytes", C.c_double),
                 ("sweep_gene_iters", C.c_int64), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
                 ("wall_ms", C.c_double)]
 
 
 STAGE_NAMES = ["gather", "fwd_fit", "sweep", "backward", "final", "copy", "select", "gee", "aggregate", "comp_forward",
-               "comp_backward", "comp_final"]
+               "comp_backward", "comp_final", "off_aggregate", "off_null"]
 
 
 def get_profile() -> dict:
@@ -173,7 +173,8 @@ def get_profile() -> dict:
 
 
 def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None, tols_score=1e-5,
-          n_gpus=0, gpu_ids=None, genes_per_batch=0, verbose=False, force_per_cell=False, h2d_mode=0) -> _abi.SclaneOpts:
+          n_gpus=0, gpu_ids=None, genes_per_batch=0, verbose=False, force_per_cell=False, h2d_mode=0,
+          comp_warp_per_gene=False, offset_per_cell=False) -> _abi.SclaneOpts:
     o = _abi.default_opts()
     o.M = int(n_potential_basis_fns)
     o.approx_knot = 1 if approx_knot else 0
@@ -192,6 +193,8 @@ def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None
     o.verbose = 1 if verbose else 0
     o.force_per_cell = 1 if force_per_cell else 0
     o.h2d_mode = int(h2d_mode)
+    o.comp_warp_per_gene = 1 if comp_warp_per_gene else 0
+    o.offset_per_cell = 1 if offset_per_cell else 0
     return o
 
 

@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "sclane_comp_device.cuh"
+#include "sclane_wg_device.cuh"
 #include "sclane_device.cuh"
 #include "sclane_gee_device.cuh"
 #include "sclane_gee_host.hpp"
@@ -185,6 +186,25 @@ struct DevicePlan {
     CK(cudaMemcpyAsync(pb, P.pb.data(), P.pb.size(), cudaMemcpyHostToDevice, s));
     pbstart = (int*)pool.get("pbstart", sizeof(P.pbstart));
     CK(cudaMemcpyAsync(pbstart, P.pbstart, sizeof(P.pbstart), cudaMemcpyHostToDevice, s));
+  }
+  // offset quadrature tables
+  OffsetNodes* on = nullptr;
+  int* oord = nullptr;
+  double* oxi_ord = nullptr;
+  double* off_ord = nullptr;
+  std::vector<double> h_oxi_ord, h_off_ord;        // staging (must outlive the async copies: DevicePlan lives until the shard is done)
+  void upload_offset_nodes(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
+    const size_t N = (size_t)P.L.N;
+    on = (OffsetNodes*)pool.get("off_nodes", sizeof(OffsetNodes));
+    oord = (int*)pool.get("off_oord", N * sizeof(int));
+    oxi_ord = (double*)pool.get("off_oxi_ord", N * sizeof(double));
+    off_ord = (double*)pool.get("off_off_ord", N * sizeof(double));
+    h_oxi_ord.resize(N); h_off_ord.resize(N);
+    for (size_t i = 0; i < N; ++i) { const size_t p = (size_t)P.oord[i]; h_oxi_ord[i] = P.oxi[p]; h_off_ord[i] = P.off[p]; }
+    CK(cudaMemcpyAsync(on, &P.ON, sizeof(OffsetNodes), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(oord, P.oord.data(), N * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(oxi_ord, h_oxi_ord.data(), N * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(off_ord, h_off_ord.data(), N * sizeof(double), cudaMemcpyHostToDevice, s));
   }
   void upload(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
     perm = (int*)pool.get("perm", P.perm.size() * sizeof(int));
@@ -362,6 +382,9 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   DevicePlan D;
   D.upload(P, pool, s);
   if (use_comp) D.upload_points(P, pool, s);
+  // fits with an offset: intercept-only models through the offset quadrature (needs the histogram of k_aggregate)
+  const bool use_offq = use_comp && use_offset && P.ON.on && !o.offset_per_cell;
+  if (use_offq) D.upload_offset_nodes(P, pool, s);
   CK(cudaStreamSynchronize(s));                     // plan tables are in place before the kernels start
   int* d_ys = (int*)pool.get("ys", (size_t)B * (size_t)L.Npad * 4);
   double* d_mu = (double*)pool.get("mu", (size_t)B * (size_t)L.Npad * 8);
@@ -377,6 +400,15 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   double* d_okeys = (double*)pool.get("order_keys", (size_t)B * 8);
   int* d_order = (int*)pool.get("order", (size_t)B * 4);
   CompGeneDev* d_cg = use_comp ? (CompGeneDev*)pool.get("comp_hdr", (size_t)B * sizeof(CompGeneDev)) : nullptr;
+  double* d_off_s = use_offq ? (double*)pool.get("off_s", (size_t)B * (size_t)(kOffKMax * kOffJ) * 8) : nullptr;
+  double* d_off_q = use_offq ? (double*)pool.get("off_q", (size_t)B * (size_t)(kOffKMax * kOffJ) * 8) : nullptr;
+  OffGeneDev* d_offg = use_offq ? (OffGeneDev*)pool.get("off_gene", (size_t)B * sizeof(OffGeneDev)) : nullptr;
+  int* d_counters = (int*)pool.get("wg_counters", 8 * sizeof(int));
+  // persistent warp-per-gene kernels: one CTA slot per resident CTA of the device
+  static int sm_count[SCLANE_MAX_GPUS] = {0};
+  if (sm_count[device % SCLANE_MAX_GPUS] == 0) { int v = 0; CK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); sm_count[device % SCLANE_MAX_GPUS] = v; }
+  const int wg_slots = sm_count[device % SCLANE_MAX_GPUS] * SCLANE_WG_MINB;
+  const bool use_wg = use_comp && o.comp_warp_per_gene;
   const int n_iter = forward_iterations(o.M);
   EventTimer tm(s);
   for (int64_t b0 = g0, kb = 0; b0 < g1; b0 += B, ++kb) {
@@ -414,6 +446,9 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     A.order = nullptr;
     CompArgs CA;
     CA.order = nullptr;
+    WgArgs WA;
+    WA.on = D.on; WA.off_s = d_off_s; WA.off_q = d_off_q; WA.offg = d_offg; WA.counter = d_counters;
+    auto wg_grid = [&](int n) { const int want = (n + kWgWarps - 1) / kWgWarps; return want < wg_slots ? want : wg_slots; };
     if (use_comp) {
       CA.lineage = D.lin; CA.pstart = D.pstart; CA.pn = D.pn; CA.pu = D.pu; CA.pb = D.pb; CA.pbstart = D.pbstart; CA.D = P.D; CA.Dpad = Dpad; CA.ys = d_ys;
       CA.s1 = d_s1; CA.q = d_q; CA.tail = d_tail; CA.big = d_big; CA.big_tmp = d_big_tmp; CA.cg = d_cg; CA.stats = d_stats; CA.out = d_out; CA.n_genes = nb; CA.M = o.M;
@@ -424,7 +459,11 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_AGGREGATE]++;
       tm.mark(SCLANE_STAGE_COMP_FWD);
-      k_comp_stage<CSTAGE_FORWARD><<<nb, kCompThreads, 0, s>>>(CA);
+      if (use_wg) {
+        CK(cudaMemsetAsync(d_counters, 0, 8 * sizeof(int), s));
+        WA.C = CA; WA.counter = d_counters + 0;
+        k_wg_stage<WG_FORWARD><<<wg_grid(nb), kWgThreads, 0, s>>>(WA);
+      } else k_comp_stage<CSTAGE_FORWARD><<<nb, kCompThreads, 0, s>>>(CA);
       CK(cudaGetLastError());
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_COMP_FWD]++;
@@ -448,7 +487,10 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     CA.order = d_order;
     if (use_comp) {
       tm.mark(SCLANE_STAGE_COMP_BWD);
-      k_comp_stage<CSTAGE_BACKWARD><<<nb, kCompThreads, 0, s>>>(CA);
+      if (use_wg) {
+        WA.C = CA; WA.counter = d_counters + 1;
+        k_wg_stage<WG_BACKWARD><<<wg_grid(nb), kWgThreads, 0, s>>>(WA);
+      } else k_comp_stage<CSTAGE_BACKWARD><<<nb, kCompThreads, 0, s>>>(CA);
       CK(cudaGetLastError());
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_COMP_BWD]++;
@@ -467,10 +509,32 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     CA.order = d_order;
     if (use_comp && !use_offset) {
       tm.mark(SCLANE_STAGE_COMP_FINAL);
-      k_comp_stage<CSTAGE_FINAL><<<nb, kCompThreads, 0, s>>>(CA);
+      if (use_wg) {
+        WA.C = CA; WA.counter = d_counters + 2;
+        k_wg_stage<WG_FINAL><<<wg_grid(nb), kWgThreads, 0, s>>>(WA);
+      } else k_comp_stage<CSTAGE_FINAL><<<nb, kCompThreads, 0, s>>>(CA);
       CK(cudaGetLastError());
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_COMP_FINAL]++;
+    }
+    if (use_offq) {
+      // offsets: node weights of every gene, then the intercept-only fits on the nodes (warp per gene); the per-cell kernel
+      // below then only fits the alternatives that kept a hinge
+      tm.mark(SCLANE_STAGE_OFF_AGG);
+      OffAggArgs OA;
+      OA.lineage = D.lin; OA.on = D.on; OA.oord = D.oord; OA.oxi_ord = D.oxi_ord; OA.off_ord = D.off_ord; OA.ys = d_ys; OA.cg = d_cg;
+      OA.off_s = d_off_s; OA.off_q = d_off_q; OA.offg = d_offg; OA.n_genes = nb;
+      k_off_aggregate<<<nb, kThreads, 0, s>>>(OA);
+      CK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      prof.launches[SCLANE_STAGE_OFF_AGG]++;
+      tm.mark(SCLANE_STAGE_OFF_NULL);
+      if (!use_wg) CK(cudaMemsetAsync(d_counters, 0, 8 * sizeof(int), s));      // (the warp-per-gene forward launch zeroes them otherwise)
+      WA.C = CA; WA.counter = d_counters + 3;
+      k_wg_stage<WG_OFFNULL><<<wg_grid(nb), kWgThreads, 0, s>>>(WA);
+      CK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      prof.launches[SCLANE_STAGE_OFF_NULL]++;
     }
     tm.mark(SCLANE_STAGE_FINAL);
     launch_stage<STAGE_FINAL>(A, s);

@@ -37,11 +37,11 @@ struct CompGeneHdr {
 // One point of the compressed layout: n cells, s = sum y, q = sum y^2, all with the same mean mu = exp(a + c u).
 template <int MODE>
 SC_HD void point_contrib(double n, double s, double q, double u, double a, double c, double sigma, double theta, bool want_ll,
-                         double* acc, double* sc) {
+                         const FastTabs* ft, double* acc, double* sc) {
   const double eta = a + c * u;
-  const double mu = exp(eta);
+  const double mu = sc_exp(eta, ft);
   if (MODE == PASS_SWEEP) {
-    const double inv = 1.0 / (1.0 + sigma * mu);
+    const double inv = rcp_pos(1.0 + sigma * mu);
     const double w = n * mu * inv, r = (s - n * mu) * inv;
     acc[0] += w; acc[1] += w * u; acc[2] += w * u * u;
     acc[3] += r; acc[4] += r * u;
@@ -55,12 +55,13 @@ SC_HD void point_contrib(double n, double s, double q, double u, double a, doubl
       sc[2] += s * eta - m;
       return;
     }
-    const double inv = rcp_pos(1.0 + sigma * mu);
+    const double sm = sigma * mu, t1 = 1.0 + sm;
+    const double inv = rcp_pos(t1);
     const double r = (s - n * mu) * inv;
     const double ns = n + sigma * s;
     const double o = mu * ns * inv * inv;
-    const double cc = sigma * mu * r * inv;
-    const double lg = log1p(sigma * mu);
+    const double cc = sm * r * inv;
+    const double lg = sc_log1p_pos(sm, t1, inv, ft);
     acc[0] += o; acc[1] += o * u; acc[2] += o * u * u;
     acc[3] += r; acc[4] += r * u;
     acc[5] += cc; acc[6] += cc * u;
@@ -70,13 +71,14 @@ SC_HD void point_contrib(double n, double s, double q, double u, double a, doubl
     return;
   }
   if (MODE == PASS_IRLS) {
-    const double inv = rcp_pos(1.0 + sigma * mu);
+    const double sm = sigma * mu, t1 = 1.0 + sm;
+    const double inv = rcp_pos(t1);
     const double w = n * mu * inv;
     const double r = (s - n * mu) * inv;
     const double wz = w * eta + r;
     acc[0] += w; acc[1] += w * u; acc[2] += w * u * u;
     acc[3] += wz; acc[4] += wz * u;
-    const double lg = log1p(sigma * mu);
+    const double lg = sc_log1p_pos(sm, t1, inv, ft);
     const double t = s * eta - (s + n * theta) * lg;
     sc[0] -= t;
     const double rmu = rcp_pos(mu);
@@ -85,9 +87,10 @@ SC_HD void point_contrib(double n, double s, double q, double u, double a, doubl
     return;
   }
   if (MODE == PASS_THETA) {
-    const double inv = rcp_pos(1.0 + sigma * mu);
+    const double sm = sigma * mu, t1 = 1.0 + sm;
+    const double inv = rcp_pos(t1);
     const double r = (s - n * mu) * inv;
-    const double lg = log1p(sigma * mu);
+    const double lg = sc_log1p_pos(sm, t1, inv, ft);
     sc[0] += -n * lg - sigma * r;
     sc[1] += -n * sigma + 2.0 * sigma * n * inv - sigma * (n + sigma * s) * inv * inv;
     return;
@@ -98,29 +101,29 @@ SC_HD void point_contrib(double n, double s, double q, double u, double a, doubl
 // (N_b, U1, U2 from the lineage; SB, SBu, SBuu, QB from the gene).
 template <int MODE>
 SC_HD void flat_bucket_contrib(double Nb, double U1, double U2, double SB, double SBu, double SBuu, double QB, double a,
-                               double sigma, double theta, bool want_ll, double* acc, double* sc) {
+                               double sigma, double theta, bool want_ll, const FastTabs* ft, double* acc, double* sc) {
   if (Nb == 0.0) return;
   const double eta = a;
-  const double mu = exp(eta);
+  const double mu = sc_exp(eta, ft);
+  if (MODE == PASS_FIT && sigma == 0.0) {
+    acc[0] += mu * Nb; acc[1] += mu * U1; acc[2] += mu * U2;
+    acc[3] += SB - Nb * mu; acc[4] += SBu - U1 * mu;
+    sc[2] += SB * eta - Nb * mu;
+    return;
+  }
+  const double sm = sigma * mu, t1 = 1.0 + sm;
+  const double inv = rcp_pos(t1);
   if (MODE == PASS_SWEEP) {
-    const double inv = 1.0 / (1.0 + sigma * mu);
     const double w = mu * inv;
     acc[0] += w * Nb; acc[1] += w * U1; acc[2] += w * U2;
     acc[3] += (SB - Nb * mu) * inv; acc[4] += (SBu - U1 * mu) * inv;
     return;
   }
+  const double lg = sc_log1p_pos(sm, t1, inv, ft);
   if (MODE == PASS_FIT) {
-    if (sigma == 0.0) {
-      acc[0] += mu * Nb; acc[1] += mu * U1; acc[2] += mu * U2;
-      acc[3] += SB - Nb * mu; acc[4] += SBu - U1 * mu;
-      sc[2] += SB * eta - Nb * mu;
-      return;
-    }
-    const double inv = 1.0 / (1.0 + sigma * mu);
     const double f = mu * inv * inv;
     const double r0 = (SB - Nb * mu) * inv, r1 = (SBu - U1 * mu) * inv;
-    const double lg = log1p(sigma * mu);
-    const double g = sigma * mu * inv;
+    const double g = sm * inv;
     acc[0] += f * (Nb + sigma * SB); acc[1] += f * (U1 + sigma * SBu); acc[2] += f * (U2 + sigma * SBuu);
     acc[3] += r0; acc[4] += r1;
     acc[5] += g * r0; acc[6] += g * r1;
@@ -130,22 +133,19 @@ SC_HD void flat_bucket_contrib(double Nb, double U1, double U2, double SB, doubl
     return;
   }
   if (MODE == PASS_IRLS) {
-    const double inv = 1.0 / (1.0 + sigma * mu);
     const double w = mu * inv;
     const double r0 = (SB - Nb * mu) * inv, r1 = (SBu - U1 * mu) * inv;
     acc[0] += w * Nb; acc[1] += w * U1; acc[2] += w * U2;
     acc[3] += w * eta * Nb + r0; acc[4] += w * eta * U1 + r1;
-    const double lg = log1p(sigma * mu);
     const double t = SB * eta - (SB + Nb * theta) * lg;
     sc[0] -= t;
-    sc[1] += (QB - 2.0 * SB * mu + Nb * mu * mu) / (mu * mu);
+    const double rmu = rcp_pos(mu);
+    sc[1] += (QB - 2.0 * SB * mu + Nb * mu * mu) * rmu * rmu;
     if (want_ll) sc[2] += t;
     return;
   }
   if (MODE == PASS_THETA) {
-    const double inv = 1.0 / (1.0 + sigma * mu);
     const double r0 = (SB - Nb * mu) * inv;
-    const double lg = log1p(sigma * mu);
     sc[0] += -Nb * lg - sigma * r0;
     sc[1] += -Nb * sigma + 2.0 * sigma * Nb * inv - sigma * (Nb + sigma * SB) * inv * inv;
     return;
@@ -157,7 +157,7 @@ template <int MODE>
 SC_HD void hist_contrib(int k, double Ck, double Ck1, double sigma, double theta, bool want_ll, double* sc) {
   if (MODE == PASS_FIT) {
     if (sigma == 0.0) return;
-    const double d = 1.0 / (theta + (double)k);
+    const double d = rcp_pos(theta + (double)k);
     sc[0] += Ck * d;
     sc[1] -= Ck * d * d;
     if (k >= 1) sc[2] += Ck * log1p((double)k * sigma);
@@ -170,7 +170,7 @@ SC_HD void hist_contrib(int k, double Ck, double Ck1, double sigma, double theta
     return;
   }
   if (MODE == PASS_THETA) {
-    const double d = 1.0 / (theta + (double)k);
+    const double d = rcp_pos(theta + (double)k);
     sc[0] += Ck * d;
     sc[1] += Ck * d * d;
     return;
@@ -200,6 +200,77 @@ SC_HD void big_contrib(int yi, double sigma, double theta, bool want_ll, double*
     psi_tri_diff_big(yi, theta, dpsi, dtri);
     sc[0] += dpsi;
     sc[1] += dtri;
+    return;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Offset quadrature: the intercept-only glm.nb WITH a size-factor offset (testDynamic.R:228-260; also an intercept-only
+// alternative model, marge2.R:826-847) without a pass over the cells.
+//
+// With the offset o_i = log(1/sf_i) the null model's mean is mu_i = exp(b0 + o_i): every sum of every IRLS / theta.ml /
+// log-likelihood pass is  sum_i [A(b0 + o_i) + y_i B(b0 + o_i) + y_i^2 C(b0 + o_i)]  with A, B, C analytic in o (their
+// only singularities sit at Im o = +-pi, where 1 + sigma mu = 0).  The o axis is cut into K bins of width w <= 1/2 and
+// inside each bin the integrand is replaced by its degree-15 interpolant at the kOffJ = 16 Chebyshev nodes of the bin.
+// Interpolation is linear in the function values, so the sums over cells collapse ONCE per gene into node weights
+//     n_kj = sum_{i in bin k} l_j(xi_i),   s_kj = sum y_i l_j(xi_i),   q_kj = sum y_i^2 l_j(xi_i)
+// (l_j = Lagrange basis at the Chebyshev nodes = (1/J) [1 + 2 sum_{m>=1} T_m(xi_j) T_m(xi)], i.e. Chebyshev moments of the
+// cells followed by a J x J cosine transform), and a pass is K*J "node" evaluations -- the same algebra as a point of the
+// X-compressed layout with (n, s, q) replaced by the node weights.  Error: for f analytic inside the Bernstein ellipse
+// of parameter rho the interpolation error is <= 4 M rho^-J / (rho - 1); with half-width h = 1/4 and the ellipse through
+// Im o = pi/2 (where |1 + sigma mu| >= 1, so M is of the size of f on the real axis) rho = 12.5: 4 * 12.5^-16 / 11.5 ~ 1e-18
+// relative -- below fp64 rounding.  Measured: records equal to the per-cell fits to ~1e-13 (tests/test_host_logic.py,
+// tests/test_gpu_parity.py).
+// ---------------------------------------------------------------------------------------------
+constexpr int kOffJ = 16;               // Chebyshev nodes per bin
+constexpr int kOffKMax = 64;            // bins: offsets may span e^32
+constexpr double kOffBinWidth = 0.5;
+
+struct OffsetNodes {
+  int on;                               // 0 = not built (no offset, or offsets out of range): per-cell fits
+  int K;
+  double omin, w;
+  double sum_o;                         // sum of the offsets over the lineage's cells
+  int kstart[kOffKMax + 1];             // range of bin k in the bin-ordered cell list
+  double ctab[kOffJ][kOffJ];            // T_m(xi_j) = cos(m (2j + 1) pi / (2J))
+  double node_o[kOffKMax * kOffJ];      // node abscissae
+  double node_n[kOffKMax * kOffJ];      // gene independent node weights (cells)
+};
+
+// Chebyshev moments of one bin (cm[m] = sum_i v_i T_m(xi_i)) -> node weights (out[j] = sum_i v_i l_j(xi_i))
+SC_HD void off_moments_to_nodes(const OffsetNodes& O, const double* cm, double* out) {
+  for (int j = 0; j < kOffJ; ++j) {
+    double s = 0.0;
+    for (int m = kOffJ - 1; m >= 1; --m) s += O.ctab[m][j] * cm[m];
+    out[j] = (cm[0] + 2.0 * s) / (double)kOffJ;
+  }
+}
+
+// One node of the offset quadrature: weights (n, s, q), offset o, intercept a (the fits that run here have no other column).
+// Same sums as point_contrib() at u = 0 with eta = a + o and the working response taken off the offset.
+template <int MODE>
+SC_HD void offnode_contrib(double n, double s, double q, double o, double a, double sigma, double theta, bool want_ll,
+                           const FastTabs* ft, double* acc, double* sc) {
+  const double eta = a + o;
+  const double mu = sc_exp(eta, ft);
+  const double sm = sigma * mu, t1 = 1.0 + sm;
+  const double inv = rcp_pos(t1);
+  const double r = (s - n * mu) * inv;
+  const double lg = sc_log1p_pos(sm, t1, inv, ft);
+  if (MODE == PASS_IRLS) {
+    const double w = n * mu * inv;
+    acc[0] += w;
+    acc[3] += w * a + r;                                   // w z, z = (eta - offset) + (y - mu)/mu
+    const double t = s * eta - (s + n * theta) * lg;
+    sc[0] -= t;
+    const double rmu = rcp_pos(mu);
+    sc[1] += (q - 2.0 * s * mu + n * mu * mu) * rmu * rmu;
+    if (want_ll) sc[2] += t;
+    return;
+  }
+  if (MODE == PASS_THETA) {
+    sc[0] += -n * lg - sigma * r;
+    sc[1] += -n * sigma + 2.0 * sigma * n * inv - sigma * (n + sigma * s) * inv * inv;
     return;
   }
 }

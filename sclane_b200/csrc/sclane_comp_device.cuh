@@ -288,6 +288,7 @@ struct CompDevExec {
   const int* __restrict__ tail;
   const int* __restrict__ big;
   double (*scw)[NSC];
+  const FastTabs* ft;               // exp / log1p tables in shared memory (sclane_fastmath.cuh)
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -348,7 +349,7 @@ struct CompDevExec {
         for (int k = 0; k < NACC; ++k) fa[k] = 0.0;
         if (lane == 0) {
           flat_bucket_contrib<MODE>(L->U0[b], L->U1[b], L->U2[b], cg->hdr.SB[b], cg->hdr.SBu[b], cg->hdr.SBuu[b], cg->hdr.QB[b], W->a[b], sigma,
-                                    theta, want_ll, fa, sc);
+                                    theta, want_ll, ft, fa, sc);
 #pragma unroll
           for (int k = 0; k < NA; ++k) W->acc[b][k] = fa[k];
         }
@@ -364,7 +365,7 @@ struct CompDevExec {
       const int p1 = pbstart[b + 1];
 #pragma unroll 2
       for (int d = pbstart[b] + lane; d < p1; d += 32)
-        point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], a, c, sigma, theta, want_ll, acc, sc);
+        point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], a, c, sigma, theta, want_ll, ft, acc, sc);
 #pragma unroll
       for (int k = 0; k < NA; ++k) {
         const double t = warp_sum(acc[k]);
@@ -410,6 +411,8 @@ __global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(C
   __shared__ CompGeneDev cg;
   __shared__ int pbs[NBMAX + 1];
   __shared__ double scw[kCompWarps][NSC];
+  __shared__ FastTabs ftab;
+  __shared__ TermTabs ttab;
   if ((int)blockIdx.x >= A.n_genes) return;
   const int g = ((STAGE == CSTAGE_FINAL || STAGE == CSTAGE_BACKWARD) && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
   if (A.cg[g].hdr.route == 0) return;                     // block-uniform: this gene takes the per-cell kernels
@@ -429,10 +432,14 @@ __global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(C
     int* w = reinterpret_cast<int*>(&W);
     for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kCompThreads) w[i] = 0;
     for (int i = threadIdx.x; i <= NBMAX; i += kCompThreads) pbs[i] = A.pbstart[i];
+    fast_tabs_load(&ftab, threadIdx.x, kCompThreads);
   }
   __syncthreads();
+  if (threadIdx.x == 0) work_attach_tabs(W, &ttab);
+  __syncthreads();
+  const long long t_start = clock64();
   CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, pbs, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
-                 A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, scw};
+                 A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, scw, &ftab};
   if (STAGE == CSTAGE_FORWARD) {
     for (int it = 0; it < A.n_iter; ++it) {
       gene_forward_fit(ex, Ls, gs, st, W);
@@ -445,12 +452,12 @@ __global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(C
     __syncthreads();
     if (threadIdx.x == 0) st.done |= 1;
   } else {
-    gene_final(ex, Ls, gs, st, W, false, &A.out[g].alt, &A.out[g].null);
+    gene_final(ex, Ls, gs, st, W, false, &A.out[g].alt, &A.out[g].null, 3);
     __syncthreads();
     if (threadIdx.x == 0) st.done |= 2;
   }
   __syncthreads();
-  if (threadIdx.x == 0) st.passes += W.passes;
+  if (threadIdx.x == 0) { st.passes += W.passes; st.cycles[STAGE] += clock64() - t_start; }
   __syncthreads();
   {
     int* d2 = reinterpret_cast<int*>(&A.out[g].st);

@@ -16,6 +16,7 @@
 #pragma once
 #include "../../include/sclane_b200.h"
 #include "sclane_math.cuh"
+#include "sclane_fastmath.cuh"
 
 namespace sclane {
 
@@ -130,8 +131,10 @@ struct Work {
   // sweep scores (NaN = NA)
   double sw_one[TMAX], sw_both[TMAX];
   double sw_one_r[TMAX], sw_both_r[TMAX];   // round(score, 6), computed alongside the scores
-  // alpha/gamma tables of the current model's terms (coop_set_model)
-  double tal[PMAX][NBMAX], tga[PMAX][NBMAX];
+  // alpha/gamma tables of the current model's terms (coop_set_model): storage is provided by the kernel / harness
+  // (TermTabs) or absent (nullptr: the warp-per-gene kernels compute term_ab() on the fly and keep Work small)
+  double (*tal)[NBMAX];
+  double (*tga)[NBMAX];
   int want_ll;                 // PASS_IRLS: also accumulate the log-likelihood (sc[2])
   int gee_p;                   // GEE passes: columns of the current model
   int sw_trunc, sw_kidx;       // forward selection broadcast
@@ -139,6 +142,20 @@ struct Work {
   // misc broadcast
   double bc[4];
 };
+
+// storage of the alpha/gamma tables (Work.tal / Work.tga point here)
+struct TermTabs {
+  double tal[PMAX][NBMAX], tga[PMAX][NBMAX];
+};
+SC_HD void work_attach_tabs(Work& W, TermTabs* tt) {
+  W.tal = tt ? tt->tal : nullptr;
+  W.tga = tt ? tt->tga : nullptr;
+}
+// alpha/gamma of term j of model m in bucket b: from the tables when they exist, else on the fly
+SC_HD void term_coef(const Lineage& L, const Model& m, const Work& W, int j, int b, double& al, double& ga) {
+  if (W.tal) { al = W.tal[j][b]; ga = W.tga[j][b]; }
+  else term_ab(L, m.kind[j], m.knot[j], b, al, ga);
+}
 
 // ---- cooperative small algebra: every thread of the CTA calls these; work is split with E::par_for ----
 // alpha/gamma tables of the model's terms.
@@ -156,16 +173,17 @@ struct SetModelFn {
 template <class E>
 SC_HD void coop_set_model(E& ex, const Lineage& L, const Model& m, Work& W) {
   ex.sync();
+  if (W.tal == nullptr) return;                   // no tables: term_coef() computes on the fly (uniform branch)
   SetModelFn fn{&L, &m, &W};
   ex.par_for(m.n * (L.T + 1), fn);
   ex.sync();
 }
 // eta parameters per bucket from beta (beta must live in shared memory).
 struct SetEtaFn {
-  const Model* m; Work* W; const double* beta;
+  const Lineage* L; const Model* m; Work* W; const double* beta;
   SC_HD void operator()(int b) const {
     double a = 0.0, c = 0.0;
-    for (int j = 0; j < m->n; ++j) { a += beta[j] * W->tal[j][b]; c += beta[j] * W->tga[j][b]; }
+    for (int j = 0; j < m->n; ++j) { double al, ga; term_coef(*L, *m, *W, j, b, al, ga); a += beta[j] * al; c += beta[j] * ga; }
     W->a[b] = a;
     W->c[b] = c;
   }
@@ -173,7 +191,7 @@ struct SetEtaFn {
 template <class E>
 SC_HD void coop_set_eta(E& ex, const Lineage& L, const Model& m, Work& W, const double* beta) {
   ex.sync();
-  SetEtaFn fn{&m, &W, beta};
+  SetEtaFn fn{&L, &m, &W, beta};
   ex.par_for(L.T + 1, fn);
   ex.sync();
 }
@@ -225,7 +243,9 @@ struct SystemFn {
       const int l = t - j * (j + 1) / 2;
       double s = 0.0;
       for (int b = 0; b < nb; ++b) {
-        const double aj = W->tal[j][b], gj = W->tga[j][b], al = W->tal[l][b], gl = W->tga[l][b];
+        double aj, gj, al, gl;
+        term_coef(*L, *m, *W, j, b, aj, gj);
+        term_coef(*L, *m, *W, l, b, al, gl);
         s += aj * al * W->acc[b][I0] + (aj * gl + al * gj) * W->acc[b][I0 + 1] + gj * gl * W->acc[b][I0 + 2];
       }
       W->H[j * NSYS + l] = s;
@@ -233,12 +253,12 @@ struct SystemFn {
     } else if (t < ntri + p) {
       const int j = t - ntri;
       double s = 0.0;
-      for (int b = 0; b < nb; ++b) s += W->tal[j][b] * W->acc[b][J0] + W->tga[j][b] * W->acc[b][J0 + 1];
+      for (int b = 0; b < nb; ++b) { double al, ga; term_coef(*L, *m, *W, j, b, al, ga); s += al * W->acc[b][J0] + ga * W->acc[b][J0 + 1]; }
       W->grad[j] = s;
     } else {
       const int j = t - ntri - p;
       double s = 0.0;
-      for (int b = 0; b < nb; ++b) s += W->tal[j][b] * W->acc[b][K0] + W->tga[j][b] * W->acc[b][K0 + 1];
+      for (int b = 0; b < nb; ++b) { double al, ga; term_coef(*L, *m, *W, j, b, al, ga); s += al * W->acc[b][K0] + ga * W->acc[b][K0 + 1]; }
       W->H[j * NSYS + p] = s;
       W->H[p * NSYS + j] = s;
     }
@@ -311,10 +331,10 @@ SC_HD double tab_lambda(const PassTabs& tb, int y, double sigma, double th) {
 
 template <int MODE>
 SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double sigma, double theta, const PassTabs& tb,
-                        double mu_in, bool want_ll, double* acc, double* sc, double& mu_out) {
+                        const FastTabs* ft, double mu_in, bool want_ll, double* acc, double* sc, double& mu_out) {
   const double y = (double)yi;
   if (MODE == PASS_EMIT) {
-    mu_out = exp(a + c * u);
+    mu_out = sc_exp(a + c * u, ft);
     return;
   }
   if (MODE == PASS_SWEEP) {
@@ -328,7 +348,7 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
   }
   if (MODE == PASS_FIT) {
     const double eta = a + c * u;
-    const double mu = exp(eta);
+    const double mu = sc_exp(eta, ft);
     if (sigma == 0.0) {   // Poisson
       const double r = y - mu;
       acc[0] += mu; acc[1] += mu * u; acc[2] += mu * u * u;
@@ -336,11 +356,12 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
       sc[2] += y * eta - mu;
       return;
     }
-    const double inv = rcp_pos(1.0 + sigma * mu);
+    const double sm = sigma * mu, t1 = 1.0 + sm;
+    const double inv = rcp_pos(t1);
     const double r = (y - mu) * inv;                       // d l / d eta
     const double o = mu * (1.0 + sigma * y) * inv * inv;   // - d2 l / d eta2
-    const double cc = sigma * mu * r * inv;                // - d2 l / d eta d(log sigma)
-    const double lg = log1p(sigma * mu);
+    const double cc = sm * r * inv;                        // - d2 l / d eta d(log sigma)
+    const double lg = sc_log1p_pos(sm, t1, inv, ft);
     double dpsi, dtri;
     tab_psi_tri(tb, yi, theta, dpsi, dtri);
     const double g = dpsi - lg - sigma * r;                                                  // d l / d theta
@@ -355,14 +376,15 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
   if (MODE == PASS_IRLS || MODE == PASS_IRLS_START) {
     double eta, mu;
     if (MODE == PASS_IRLS_START) { mu = y + (yi == 0 ? 1.0 / 6.0 : 0.0); eta = log(mu); }   // negative.binomial()$initialize
-    else { eta = a + c * u + off; mu = exp(eta); }
-    const double inv = rcp_pos(1.0 + sigma * mu);
+    else { eta = a + c * u + off; mu = sc_exp(eta, ft); }
+    const double sm = sigma * mu, t1 = 1.0 + sm;
+    const double inv = rcp_pos(t1);
     const double w = mu * inv;                             // mu.eta^2 / variance(mu)
     const double r = (y - mu) * inv;
     const double wz = w * (eta - off) + r;                 // w * z, z = (eta - offset) + (y - mu)/mu.eta
     acc[0] += w; acc[1] += w * u; acc[2] += w * u * u;
     acc[3] += wz; acc[4] += wz * u;
-    const double lg = log1p(sigma * mu);
+    const double lg = sc_log1p_pos(sm, t1, inv, ft);
     // dev.resids: 2 (y log(max(1,y)/mu) - (y+th) log((y+th)/(mu+th))); the y log y part is a gene constant
     const double l1py = yi < kTab ? tb.l1p[yi] : log1p(sigma * y);
     sc[0] += yi > 0 ? (-y * eta - (y + theta) * (l1py - lg)) : theta * lg;
@@ -373,10 +395,11 @@ SC_HD void cell_contrib(int yi, double u, double off, double a, double c, double
   }
   if (MODE == PASS_THETA) {
     const double eta = a + c * u + off;
-    const double mu = exp(eta);
-    const double inv = rcp_pos(1.0 + sigma * mu);
+    const double mu = sc_exp(eta, ft);
+    const double sm = sigma * mu, t1 = 1.0 + sm;
+    const double inv = rcp_pos(t1);
     const double r = (y - mu) * inv;
-    const double lg = log1p(sigma * mu);
+    const double lg = sc_log1p_pos(sm, t1, inv, ft);
     double dpsi, dtri;
     tab_psi_tri(tb, yi, theta, dpsi, dtri);
     sc[0] += dpsi - lg - sigma * r;                                                           // theta.ml score
@@ -677,7 +700,7 @@ SC_HDN double sweep_score(const Lineage& L, const Model& m, const Work& W, int k
       const double s0 = W.acc[b][0], s1 = W.acc[b][1], s2 = W.acc[b][2];
       const double w0 = al * s0 + ga * s1;      // <cand, 1>_w  restricted to the bucket
       const double w1 = al * s1 + ga * s2;      // <cand, u>_w
-      for (int j = 0; j < p; ++j) C[q][j] += W.tal[j][b] * w0 + W.tga[j][b] * w1;
+      for (int j = 0; j < p; ++j) { double tj, gj; term_coef(L, m, W, j, b, tj, gj); C[q][j] += tj * w0 + gj * w1; }
       d += al * w0 + ga * w1;
       bv += al * W.acc[b][3] + ga * W.acc[b][4];
     }
@@ -840,6 +863,7 @@ struct GeneState {
   Model fin;            // final model after the backward pass
   double wic[PMAX];
   int n_wic;
+  long long cycles[3];  // profiling: clock64 ticks spent in the forward / backward / final kernels
   int done;             // bit 0: backward pass done, bit 1: final fits done (set by the X-compressed kernels; the per-cell
                         // kernels skip genes that already went through a stage)
 };
@@ -1348,25 +1372,31 @@ SC_HDN void gene_backward(E& ex, const Lineage& L, const GeneStats& gstat, GeneS
 
 // K5: final glm.nb on the selected basis (marge2.R:841-847) and the intercept-only null glm.nb
 // (testDynamic.R:254-260), both with the size-factor offset when one is given.
+// parts: bit 0 = the intercept-only fits (the null model, copied to the alternative when only the intercept survived the
+// backward pass), bit 1 = an alternative with hinges.  The two parts may run in different kernels / executors (with an
+// offset: part 1 on the offset quadrature, part 2 per cell); 3 = both here.
 template <class E>
 SC_HDN void gene_final(E& ex, const Lineage& L, const GeneStats& gstat, GeneState& st, Work& W, bool use_offset,
-                       NbResult* alt, NbResult* null) {
+                       NbResult* alt, NbResult* null, int parts) {
   ex.sync();
-  if (ex.leader()) { alt->ok = 0; null->ok = 0; alt->notes = 0; null->notes = 0; }
-  ex.sync();
-  if (st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS)) return;
-  if (ex.leader()) { W.bw_cur.n = 1; W.bw_cur.kind[0] = SCLANE_TERM_INTERCEPT; W.bw_cur.knot[0] = 0; }
-  ex.sync();
-  glm_nb(ex, L, W.bw_cur, gstat, W, use_offset, null);
-  ex.sync();
-  if (st.fin.n < 1 || (st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC))) return;
-  if (st.fin.n == 1) {
-    // intercept-only alternative: the same fit as the null model (LRT is exactly 0, modelLRT.R:48-50)
-    if (ex.leader()) *alt = *null;
+  if (parts & 1) {
+    if (ex.leader()) { alt->ok = 0; null->ok = 0; alt->notes = 0; null->notes = 0; }
     ex.sync();
-    return;
   }
-  glm_nb(ex, L, st.fin, gstat, W, use_offset, alt);
+  if (st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS)) return;
+  const bool alt_usable = !(st.fin.n < 1 || (st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC)));
+  if (parts & 1) {
+    if (ex.leader()) { W.bw_cur.n = 1; W.bw_cur.kind[0] = SCLANE_TERM_INTERCEPT; W.bw_cur.knot[0] = 0; }
+    ex.sync();
+    glm_nb(ex, L, W.bw_cur, gstat, W, use_offset, null);
+    ex.sync();
+    if (alt_usable && st.fin.n == 1) {
+      // intercept-only alternative: the same fit as the null model (LRT is exactly 0, modelLRT.R:48-50)
+      if (ex.leader()) *alt = *null;
+      ex.sync();
+    }
+  }
+  if ((parts & 2) && alt_usable && st.fin.n > 1) glm_nb(ex, L, st.fin, gstat, W, use_offset, alt);
 }
 
 }  // namespace sclane

@@ -47,6 +47,7 @@ struct DevExec {
   double (*slot)[NBMAX][NACC];      // [kWarps] warp-private partial moments
   double (*scw)[NSC];               // [kWarps] warp-private partial scalars
   PassTabs* tb;                     // count-indexed special-function tables of the current pass
+  const FastTabs* ft;               // exp / log1p tables in shared memory (sclane_fastmath.cuh)
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -159,8 +160,8 @@ struct DevExec {
           const double u0 = __ldg(u + i), u1 = __ldg(u + i + 32);
           const double o0 = use_off ? __ldg(off + i) : 0.0, o1 = use_off ? __ldg(off + i + 32) : 0.0;
           double m0, m1;
-          cell_contrib<MODE>(y0, u0, o0, a, c, sigma, theta, *tb, 0.0, want_ll, acc, sc, m0);
-          cell_contrib<MODE>(y1, u1, o1, a, c, sigma, theta, *tb, 0.0, want_ll, acc2, sc2, m1);
+          cell_contrib<MODE>(y0, u0, o0, a, c, sigma, theta, *tb, ft, 0.0, want_ll, acc, sc, m0);
+          cell_contrib<MODE>(y1, u1, o1, a, c, sigma, theta, *tb, ft, 0.0, want_ll, acc2, sc2, m1);
           if (MODE == PASS_EMIT) { mu[i] = m0; mu[i + 32] = m1; }
           g += 2;
           continue;
@@ -175,7 +176,7 @@ struct DevExec {
             cell_contrib_flat<MODE>(yi, ui, fb, sigma, theta, *tb, want_ll, acc, sc, mo);
           } else {
             const double oi = use_off ? __ldg(off + i) : 0.0;
-            cell_contrib<MODE>(yi, ui, oi, a, c, sigma, theta, *tb, 0.0, want_ll, acc, sc, mo);
+            cell_contrib<MODE>(yi, ui, oi, a, c, sigma, theta, *tb, ft, 0.0, want_ll, acc, sc, mo);
           }
           if (MODE == PASS_EMIT) mu[i] = mo;
           g += 1;
@@ -192,7 +193,7 @@ struct DevExec {
 #pragma unroll
         for (int k = 0; k < NACC; ++k) ct[k] = 0.0;
         if (valid) {
-          cell_contrib<MODE>(yi, ui, oi, W->a[b], W->c[b], sigma, theta, *tb, 0.0, want_ll, ct, sc, mo);
+          cell_contrib<MODE>(yi, ui, oi, W->a[b], W->c[b], sigma, theta, *tb, ft, 0.0, want_ll, ct, sc, mo);
           if (MODE == PASS_EMIT) mu[i] = mo;
         }
         if (NA > 0) {
@@ -270,6 +271,8 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   __shared__ double slot[kWarps][NBMAX][NACC];
   __shared__ double scw[kWarps][NSC];
   __shared__ PassTabs tabs;
+  __shared__ FastTabs ftab;
+  __shared__ TermTabs ttab;
   if ((int)blockIdx.x >= A.n_genes) return;
   const int g = ((STAGE == STAGE_FINAL || STAGE == STAGE_BACKWARD) && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
   {
@@ -285,21 +288,26 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
     for (int i = threadIdx.x; i < (int)(sizeof(GeneStats) / sizeof(int)); i += kThreads) d3[i] = s3[i];
     int* w = reinterpret_cast<int*>(&W);
     for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kThreads) w[i] = 0;
+    fast_tabs_load(&ftab, threadIdx.x, kThreads);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) work_attach_tabs(W, &ttab);
   __syncthreads();
   if (STAGE == STAGE_BACKWARD && (st.done & 1)) return;      // block-uniform: already handled by k_comp_stage
   if (STAGE == STAGE_FINAL && (st.done & 2)) return;
   const size_t row = (size_t)g * (size_t)Ls.Npad;
-  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs};
+  const long long t_start = clock64();
+  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs, &ftab};
   if (STAGE == STAGE_FWD_FIT) {
     gene_forward_fit(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_BACKWARD) {
     gene_backward(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_FINAL) {
-    gene_final(ex, Ls, gs, st, W, A.use_offset != 0, &A.out[g].alt, &A.out[g].null);
+    // genes whose intercept-only fits already ran on the offset quadrature (done bit 2) only need the alternative with hinges
+    gene_final(ex, Ls, gs, st, W, A.use_offset != 0, &A.out[g].alt, &A.out[g].null, (st.done & 4) ? 2 : 3);
   }
   __syncthreads();
-  if (threadIdx.x == 0) st.passes += W.passes;
+  if (threadIdx.x == 0) { st.passes += W.passes; st.cycles[STAGE == STAGE_FWD_FIT ? 0 : (STAGE == STAGE_BACKWARD ? 1 : 2)] += clock64() - t_start; }
   __syncthreads();
   {
     int* d2 = reinterpret_cast<int*>(&A.out[g].st);
@@ -583,7 +591,7 @@ k_sweep_select(StageArgs A) {
   const double* m = A.mom + (size_t)g * (size_t)(NBMAX * NACC);
   double* wacc = &W.acc[0][0];
   for (int i = lane; i < (Ls.T + 1) * NACC; i += 32) wacc[i] = m[i];
-  if (lane == 0) { W.passes = 0; W.flag = 0; }
+  if (lane == 0) { W.passes = 0; W.flag = 0; work_attach_tabs(W, nullptr); }      // no term tables: term_coef() on the fly
   __syncwarp();
   WarpExec ex;
   const GeneStats gs = A.stats[g];
@@ -683,7 +691,7 @@ __global__ void k_order_final(const GeneOutDev* __restrict__ out, int n, double*
     // dispersion is mostly depth variation -- with the offset its theta runs away and glm.nb goes to the alternation limit
     // (bench generator: Spearman -0.71 between forward sigma and the final stage's passes; the score only 0.43)
     const GeneState& st = out[i].st;
-    keys[i] = st.error ? 1e300 : st.sigma;
+    keys[i] = (st.error || st.fin.n <= 1) ? 1e300 : st.sigma;      // intercept-only alternatives are not fitted per cell: last
     return;
   }
   if (phase == 0) {

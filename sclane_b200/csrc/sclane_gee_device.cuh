@@ -39,6 +39,7 @@ struct GeeArgs {
 
 struct GeeShared {
   Work W;
+  TermTabs tt;
   GeeWork G;
   Lineage L;
   GeeLineage GL;
@@ -406,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, SCLANE_GEE_MINB) k_gee(GeeArgs A) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    work_attach_tabs(S->W, &S->tt);
     S->st.fwd.n = 1;
     S->st.fwd.kind[0] = SCLANE_TERM_INTERCEPT;
     S->st.m_count = 1;

@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "sclane_core.cuh"
+#include "sclane_comp.cuh"
 
 namespace sclane {
 
@@ -171,6 +171,12 @@ struct LineagePlan {
   double pt_min = 0, pt_max = 0;
   int minspan = 0;
   std::string error;
+  // Offset quadrature (sclane_comp.cuh, "offset nodes"): the lineage's offsets o_i = log(1/sf_i) binned into K intervals of
+  // width <= kOffBinWidth, each carrying kOffJ Chebyshev nodes.  Filled by build_offset_nodes() when a size factor is given.
+  OffsetNodes ON;
+  std::vector<double> oxi;        // [Npad] position of o_i inside its bin, in [-1, 1] (sorted-cell order)
+  std::vector<uint8_t> obin;      // [Npad] bin of o_i
+  std::vector<int32_t> oord;      // [N] sorted-cell positions ordered by (bin, position)
 };
 
 // distinct abscissae of the sorted cells (a point never straddles a bucket: buckets are defined by the abscissa)
@@ -194,6 +200,57 @@ inline void build_points(LineagePlan& P) {
   P.pb.resize((size_t)P.D);
   for (int d = 0; d < P.D; ++d) P.pn[(size_t)d] = (double)(P.pstart[(size_t)d + 1] - P.pstart[(size_t)d]);
   for (int b = 0; b <= L.T; ++b) for (int d = P.pbstart[b]; d < P.pbstart[b + 1]; ++d) P.pb[(size_t)d] = (uint8_t)b;
+}
+
+// Offset quadrature plan (see sclane_comp.cuh): bins, per-cell Chebyshev coordinate, bin-ordered cell list, node abscissae
+// and the gene-independent node weights n_kj = sum_i l_j(xi_i) over the cells of bin k.
+inline void build_offset_nodes(LineagePlan& P) {
+  OffsetNodes& O = P.ON;
+  std::memset(&O, 0, sizeof(O));
+  const int N = P.L.N;
+  if (P.off.empty() || N < 1) return;
+  double lo = P.off[0], hi = P.off[0], so = 0.0;
+  for (int i = 0; i < N; ++i) { const double o = P.off[(size_t)i]; if (!(o == o) || std::isinf(o)) return; if (o < lo) lo = o; if (o > hi) hi = o; so += o; }
+  const double R = hi - lo;
+  int K = R > 0.0 ? (int)std::ceil(R / kOffBinWidth) : 1;
+  if (K < 1) K = 1;
+  if (K > kOffKMax) return;                                 // offsets spanning more than e^32: keep the per-cell fits
+  const double w = R > 0.0 ? R / (double)K : 1.0;
+  O.on = 1; O.K = K; O.omin = lo; O.w = w; O.sum_o = so;
+  const double PI = 3.14159265358979323846;
+  for (int m = 0; m < kOffJ; ++m)
+    for (int j = 0; j < kOffJ; ++j) O.ctab[m][j] = std::cos((double)m * (2.0 * j + 1.0) * PI / (2.0 * kOffJ));
+  for (int k = 0; k < K; ++k)
+    for (int j = 0; j < kOffJ; ++j) O.node_o[k * kOffJ + j] = lo + ((double)k + 0.5) * w + 0.5 * w * O.ctab[1][j];
+  P.oxi.assign((size_t)P.L.Npad, 0.0);
+  P.obin.assign((size_t)P.L.Npad, 0);
+  std::vector<int32_t> cnt((size_t)K + 1, 0);
+  std::vector<double> cm((size_t)K * kOffJ, 0.0);            // Chebyshev moments sum_i T_m(xi_i) per bin
+  for (int i = 0; i < N; ++i) {
+    const double o = P.off[(size_t)i];
+    int k = (int)std::floor((o - lo) / w);
+    if (k < 0) k = 0;
+    if (k > K - 1) k = K - 1;
+    double xi = 2.0 * (o - (lo + ((double)k + 0.5) * w)) / w;
+    if (xi < -1.0) xi = -1.0;
+    if (xi > 1.0) xi = 1.0;
+    P.oxi[(size_t)i] = xi;
+    P.obin[(size_t)i] = (uint8_t)k;
+    cnt[(size_t)k + 1]++;
+    double t0 = 1.0, t1 = xi;
+    cm[(size_t)k * kOffJ] += 1.0;
+    cm[(size_t)k * kOffJ + 1] += xi;
+    for (int m = 2; m < kOffJ; ++m) { const double t2 = 2.0 * xi * t1 - t0; cm[(size_t)k * kOffJ + m] += t2; t0 = t1; t1 = t2; }
+  }
+  for (int k = 0; k < K; ++k) cnt[(size_t)k + 1] += cnt[(size_t)k];
+  for (int k = 0; k <= K; ++k) O.kstart[k] = cnt[(size_t)k];
+  for (int k = K + 1; k <= kOffKMax; ++k) O.kstart[k] = N;
+  P.oord.assign((size_t)N, 0);
+  {
+    std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+    for (int i = 0; i < N; ++i) P.oord[(size_t)pos[P.obin[(size_t)i]]++] = i;
+  }
+  for (int k = 0; k < K; ++k) off_moments_to_nodes(O, &cm[(size_t)k * kOffJ], &O.node_n[k * kOffJ]);
 }
 
 // pt_col: n_cells doubles with NaN = not in lineage.  size_factor may be null.
@@ -248,6 +305,7 @@ inline bool build_lineage_plan(const double* pt_col, int64_t n_cells, const doub
   L.bstart[L.T + 1] = acc;
   for (int b = L.T + 2; b <= NBMAX; ++b) L.bstart[b] = acc;
   build_points(P);
+  build_offset_nodes(P);
   P.pt_min = *std::min_element(x.begin(), x.end());
   P.pt_max = *std::max_element(x.begin(), x.end());
   return true;
@@ -360,6 +418,7 @@ inline void finalize_record(const GeneOut& g, const Lineage& L, sclane_record& r
   r.n_wic = st.n_wic;
   for (int j = 0; j < SCLANE_PMAX; ++j) r.wic[j] = j < st.n_wic ? st.wic[j] : NaN;
   r.fit_passes = st.passes;
+  for (int j = 0; j < 3; ++j) r.stage_cycles[j] = (double)st.cycles[j];
 }
 
 inline void init_gene_state(GeneState& st) {

@@ -35,7 +35,7 @@ struct HostExec {
       const int b = bucket[i];
       double mu_out = 0.0;
       const double o = (W->use_offset && off) ? off[i] : 0.0;
-      cell_contrib<MODE>(y[i], u[i], o, W->a[b], W->c[b], W->sigma, W->theta, tabs_, mu ? mu[i] : 0.0, W->want_ll != 0, W->acc[b], W->sc, mu_out);
+      cell_contrib<MODE>(y[i], u[i], o, W->a[b], W->c[b], W->sigma, W->theta, tabs_, nullptr, mu ? mu[i] : 0.0, W->want_ll != 0, W->acc[b], W->sc, mu_out);
       if (MODE == PASS_EMIT) mu[i] = mu_out;
     }
   }
@@ -53,6 +53,50 @@ struct CompHostExec {
   CompGeneHdr H;
   double sum_ylogy;
   int hmax_ = 0;
+  // offset quadrature (intercept-only fits with an offset): node weights of this gene
+  bool offnull = false;
+  std::vector<double> ons, onq;
+  double a0tot = 0.0, b0tot = 0.0, wo = 0.0;
+  void aggregate_off(const int32_t* y) {                   // y: sorted counts; P->ON.on must be set
+    const OffsetNodes& O = P->ON;
+    std::vector<double> cy((size_t)O.K * kOffJ, 0.0), cq((size_t)O.K * kOffJ, 0.0);
+    a0tot = b0tot = wo = 0.0;
+    for (int i = 0; i < L->N; ++i) {
+      double w, wz;
+      start_cell(y[i], w, wz);
+      a0tot += w; b0tot += wz; wo += w * P->off[(size_t)i];
+      if (y[i] == 0) continue;
+      const double v = (double)y[i], xi = P->oxi[(size_t)i];
+      const size_t base = (size_t)P->obin[(size_t)i] * kOffJ;
+      double t0 = 1.0, t1 = xi;
+      cy[base] += v; cq[base] += v * v;
+      cy[base + 1] += v * xi; cq[base + 1] += v * v * xi;
+      for (int m = 2; m < kOffJ; ++m) { const double t2 = 2.0 * xi * t1 - t0; cy[base + m] += v * t2; cq[base + m] += v * v * t2; t0 = t1; t1 = t2; }
+    }
+    ons.assign((size_t)O.K * kOffJ, 0.0); onq.assign((size_t)O.K * kOffJ, 0.0);
+    for (int k = 0; k < O.K; ++k) {
+      off_moments_to_nodes(O, &cy[(size_t)k * kOffJ], &ons[(size_t)k * kOffJ]);
+      off_moments_to_nodes(O, &cq[(size_t)k * kOffJ], &onq[(size_t)k * kOffJ]);
+    }
+  }
+  template <int MODE>
+  void pass_offnull() {
+    const OffsetNodes& O = P->ON;
+    for (int b = 0; b <= L->T; ++b) for (int k = 0; k < NACC; ++k) W->acc[b][k] = 0.0;
+    for (int k = 0; k < NSC; ++k) W->sc[k] = 0.0;
+    if (MODE == PASS_IRLS_START) {
+      W->acc[0][0] = a0tot;
+      W->acc[0][3] = b0tot - wo;
+      W->sc[0] = -sum_ylogy + (double)H.n_zero * W->theta * log1p(W->sigma / 6.0);
+      W->sc[1] = (double)H.n_zero;
+      return;
+    }
+    const bool want_ll = W->want_ll != 0;
+    for (int e = 0; e < O.K * kOffJ; ++e)
+      offnode_contrib<MODE>(O.node_n[e], ons[(size_t)e], onq[(size_t)e], O.node_o[e], W->a[0], W->sigma, W->theta, want_ll, nullptr, W->acc[0], W->sc);
+    for (int k = 0; k < hmax_; ++k) hist_contrib<MODE>(k, tail[(size_t)k], tail[(size_t)k + 1], W->sigma, W->theta, want_ll, W->sc);
+    for (int32_t v : big) big_contrib<MODE>(v, W->sigma, W->theta, want_ll, W->sc);
+  }
   PassTabs* tabs() { return nullptr; }
   bool leader() const { return true; }
   void sync() const {}
@@ -91,6 +135,7 @@ struct CompHostExec {
   template <int MODE>
   void pass() {
     if (MODE == PASS_EMIT) return;                         // the compressed sweep recomputes mu from the eta parameters
+    if (offnull && (MODE == PASS_IRLS || MODE == PASS_THETA || MODE == PASS_IRLS_START)) { pass_offnull<MODE>(); return; }
     for (int b = 0; b <= L->T; ++b) for (int k = 0; k < (MODE == PASS_SWEEP ? 5 : NACC); ++k) W->acc[b][k] = 0.0;
     for (int k = 0; k < NSC; ++k) W->sc[k] = 0.0;
     if (MODE == PASS_IRLS_START) {
@@ -107,10 +152,10 @@ struct CompHostExec {
     const bool want_ll = W->want_ll != 0;
     for (int b = 0; b <= L->T; ++b) {
       if (W->c[b] == 0.0) {
-        flat_bucket_contrib<MODE>(L->U0[b], L->U1[b], L->U2[b], H.SB[b], H.SBu[b], H.SBuu[b], H.QB[b], W->a[b], W->sigma, W->theta, want_ll, W->acc[b], W->sc);
+        flat_bucket_contrib<MODE>(L->U0[b], L->U1[b], L->U2[b], H.SB[b], H.SBu[b], H.SBuu[b], H.QB[b], W->a[b], W->sigma, W->theta, want_ll, nullptr, W->acc[b], W->sc);
       } else {
         for (int d = P->pbstart[b]; d < P->pbstart[b + 1]; ++d)
-          point_contrib<MODE>(P->pn[(size_t)d], s1[(size_t)d], q[(size_t)d], P->pu[(size_t)d], W->a[b], W->c[b], W->sigma, W->theta, want_ll, W->acc[b], W->sc);
+          point_contrib<MODE>(P->pn[(size_t)d], s1[(size_t)d], q[(size_t)d], P->pu[(size_t)d], W->a[b], W->c[b], W->sigma, W->theta, want_ll, nullptr, W->acc[b], W->sc);
       }
       if (MODE == PASS_SWEEP) { W->acc[b][5] = H.SB[b]; W->acc[b][6] = H.SBu[b]; }
     }
@@ -156,6 +201,9 @@ extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t 
       if (gs.sum_y == 0.0) go.st.error |= SCLANE_NOTE_ALL_ZERO;
       Work W;
       std::memset(&W, 0, sizeof(W));
+      TermTabs tt;
+      // force_per_cell: term tables (as k_stage has them); otherwise none -> term_coef() on the fly (as the warp-per-gene kernels)
+      work_attach_tabs(W, opts->force_per_cell == 1 ? &tt : nullptr);
       HostExec ex{&W, &L, y.data(), P.u.data(), P.off.empty() ? nullptr : P.off.data(), mu.data(), P.bucket.data(), PassTabs()};
       // opts->force_per_cell == 1: per-cell executor everywhere; otherwise the X-compressed executor runs every fit without
       // an offset (the routing the CUDA path uses)
@@ -170,8 +218,17 @@ extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t 
       const int p_fwd = W.passes;
       if (use_comp) gene_backward(cx, L, gs, go.st, W); else gene_backward(ex, L, gs, go.st, W);
       const int p_bwd = W.passes;
-      if (use_comp && size_factor == nullptr) gene_final(cx, L, gs, go.st, W, false, &go.alt, &go.null);
-      else gene_final(ex, L, gs, go.st, W, size_factor != nullptr, &go.alt, &go.null);
+      if (use_comp && size_factor == nullptr) gene_final(cx, L, gs, go.st, W, false, &go.alt, &go.null, 3);
+      else if (use_comp && P.ON.on) {
+        // offsets: the intercept-only fits (null model; alternative when nothing but the intercept survived) through the
+        // offset quadrature, the alternative with hinges per cell -- the routing of the CUDA path
+        cx.aggregate_off(y.data());
+        cx.offnull = true;
+        gene_final(cx, L, gs, go.st, W, true, &go.alt, &go.null, 1);
+        cx.offnull = false;
+        gene_final(ex, L, gs, go.st, W, true, &go.alt, &go.null, 2);
+      }
+      else gene_final(ex, L, gs, go.st, W, size_factor != nullptr, &go.alt, &go.null, 3);
       if (std::getenv("SCLANE_EMU_STAGES"))
         std::fprintf(stderr, "gene %ld passes fwd %d bwd %d final %d (alt: alt=%d irls=%d; null: alt=%d irls=%d)\n", (long)g, p_fwd, p_bwd - p_fwd,
                      W.passes - p_bwd, go.alt.alternations, go.alt.irls_iters, go.null.alternations, go.null.irls_iters);
@@ -335,6 +392,8 @@ extern "C" int emu_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int6
       if (gs.sum_y == 0.0) go.st.error |= SCLANE_NOTE_ALL_ZERO;
       Work W;
       std::memset(&W, 0, sizeof(W));
+      TermTabs tt;
+      work_attach_tabs(W, &tt);
       GeeWork G;
       std::memset(&G, 0, sizeof(G));
       G.cor = opts->gee_cor;
