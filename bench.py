@@ -248,7 +248,7 @@ def cpu_baseline(cfg):
         counts = np.ascontiguousarray(d["counts"], dtype=np.int32)
         with open(os.path.join(ROOT, "tests", "golden", "sclane_models.json")) as fh:
             gold = json.load(fh)
-        gt = [v["Lineage_A"]["Gene_Time"] for v in gold.values() if isinstance(v["Lineage_A"].get("Gene_Time"), (int, float))]
+        gt = [v["Gene_Time"] for v in gold.values() if isinstance(v.get("Gene_Time"), (int, float))]
         n_c1 = 12
         t0 = time.time()
         with threadpool_limits(limits=1):

@@ -100,7 +100,9 @@ typedef struct sclane_opts {
                                  profiles/r02_tail_cycles.txt).  The offset quadrature always runs warp per gene. */
   int32_t offset_per_cell;    /* testing / profiling only: 1 = fit the intercept-only models with an offset per cell instead of
                                  through the offset quadrature */
-  int32_t reserved[1];
+  int32_t basis_only;         /* 1 = stop after the backward pass and return the selected basis only (marge2(is.glmm = TRUE),
+                                 marge2.R:871-879): records carry n_terms / term_* and SCLANE_MARGE_OK, every fitted quantity is NaN.
+                                 Set by sclane_marge_basis(). */
 } sclane_opts;
 
 /* One record per (gene, lineage): everything testDynamic() returns for that pair except the
@@ -254,6 +256,17 @@ int32_t sclane_test_dynamic_csc(const int32_t* indptr, const int32_t* indices, c
                                 const sclane_opts* opts,
                                 sclane_record* out, sclane_lineage_info* lineages,
                                 char* errbuf, size_t errlen);
+
+/* marge2(..., is.glmm = TRUE) for every (gene, column of pt): forward pass + WIC backward pass only, no final fit -- the knot
+ * harvesting of fitGLMM() (fitGLMM.R:54-64 calls it once per subject with M = M.glm = 3: pass one pt column per subject, NaN
+ * outside the subject's cells).  Records: status & SCLANE_MARGE_OK when a basis was selected, n_terms / term_kind / term_knot /
+ * term_label / term_knot_idx filled (marge_coef_names of marge2.R:877), all fitted quantities NaN.  The offset plays no role in
+ * the forward / backward pass (marge2.R:826-829 adds it to the final fit only).  Same arguments as sclane_test_dynamic(). */
+int32_t sclane_marge_basis(const int32_t* counts, int64_t n_cells, int64_t n_genes,
+                           const double* pt, int32_t n_lineages,
+                           const sclane_opts* opts,
+                           sclane_record* out, sclane_lineage_info* lineages,
+                           char* errbuf, size_t errlen);
 
 /* GEE mode of the same path (testDynamic(is.gee = TRUE, gee.test = "wald"), testDynamic.R:66-70,235-244,
  * 296-301; marge2.R:258-268 (stat_out_score_gee_null), :438-448/:520-530 (score_fun_gee), :831-838 (final geem);

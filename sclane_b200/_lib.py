@@ -48,6 +48,8 @@ def lib() -> C.CDLL:
     L.sclane_test_dynamic_gee.restype = i32
     L.sclane_test_dynamic_csc.argtypes = [p, p, p, i64, i64, p, i32, p, C.POINTER(_abi.SclaneOpts), p, p, *err]
     L.sclane_test_dynamic_csc.restype = i32
+    L.sclane_marge_basis.argtypes = [p, i64, i64, p, i32, C.POINTER(_abi.SclaneOpts), p, p, *err]
+    L.sclane_marge_basis.restype = i32
     L.sclane_test_dynamic_device.argtypes = [p, i32, i64, i64, p, i32, p, C.POINTER(_abi.SclaneOpts), p, p, *err]
     L.sclane_test_dynamic_device.restype = i32
     L.sclane_candidate_knots.argtypes = [p, i64, C.POINTER(_abi.SclaneOpts), p, p]

@@ -203,7 +203,7 @@ def _is_sparse(m) -> bool:
 
 
 def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = None, device_ptr: int | None = None,
-                device: int = 0, subject_id=None):
+                device: int = 0, subject_id=None, basis_only: bool = False):
     """Thin call of sclane_test_dynamic[_device|_gee]: counts int32 [genes, cells] C-contiguous (gene-major), pt float64
     [cells, lineages]; subject_id (GEE mode, opts.mode = 1): int32 per cell, cells ordered by subject.
     Returns (records ctypes array [genes * lineages], lineage infos)."""
@@ -250,6 +250,8 @@ def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = Non
                 raise ValueError("id.vec must have one entry per cell")
             rc = L.sclane_test_dynamic_gee(counts.ctypes.data, n_cells, n_genes, pt_cm.ctypes.data, n_lin, sid.ctypes.data,
                                            None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
+        elif basis_only:
+            rc = L.sclane_marge_basis(counts.ctypes.data, n_cells, n_genes, pt_cm.ctypes.data, n_lin, C.byref(opts), recs, infos, err, _ERRLEN)
         else:
             rc = L.sclane_test_dynamic(counts.ctypes.data, n_cells, n_genes, pt_cm.ctypes.data, n_lin,
                                        None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
@@ -600,9 +602,18 @@ def _abi_unsupported() -> int:
     return 4
 
 
+def _raw_term_names(rec, var: str) -> list[str]:
+    """colnames(B_final) (marge2.R:593-594): "Intercept", "(<var>-<knot>)" (tp1), "(<knot>-<var>)" (tp2)."""
+    names = ["Intercept"]
+    for j in range(1, rec.n_terms):
+        lab = _fmt_num(rec.term_label[j])
+        names.append(f"({var}-{lab})" if rec.term_kind[j] == _abi.TERM_TP1 else f"({lab}-{var})")
+    return names
+
+
 def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False, id_vec=None, cor_structure: str = "ar1",
            sandwich_var: bool = False, approx_knot: bool = True, n_knot_max: int = 25, tols_score: float = 1e-5, minspan=None,
-           device: int = 0) -> dict:
+           device: int = 0, is_glmm: bool = False) -> dict:
     """marge2.R:56-889 for one gene: X_pred = pseudotime of the lineage's cells, Y = counts, Y_offset = size factors; GEE mode
     with is_gee / id_vec / cor_structure / sandwich_var as in the reference.  Returns final_mod-like fields (coefficients,
     SEs, theta, logLik, deviance -- or the geem fields alpha / phi in GEE mode), coef_names, marge_coef_names, model_type."""
@@ -612,6 +623,17 @@ def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False,
     x = np.asarray(X_pred, dtype=np.float64).reshape(-1)
     o = _opts(M, approx_knot, n_knot_max, minspan, tols_score, gpu_ids=[device])
     sid = None
+    if is_glmm:
+        # marge2.R:871-879: forward + backward pass only; the caller (fitGLMM) harvests the knots
+        if is_gee:
+            raise ValueError("is.gee and is.glmm cannot both be specified.")
+        recs, infos = run_records(y, x[:, None], None, o, basis_only=True)
+        rec = recs[0]
+        if not (rec.status & _abi.SCLANE_MARGE_OK):
+            raise SclaneError(0, _notes(rec.marge_notes, False))
+        return {"final_mod": None, "basis_mtx": None, "WIC_mtx": None, "GCV": None, "model_type": "GLMM",
+                "coef_names": _term_names(rec, "A"), "marge_coef_names": _raw_term_names(rec, "Lineage_A"), "record": rec,
+                "knots": [infos[0].knots[k] for k in range(infos[0].n_knots)]}
     if is_gee:
         if id_vec is None:
             raise ValueError("id.vec in marge2() must be non-null if is.gee = TRUE.")
@@ -645,6 +667,38 @@ def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False,
             "basis_mtx": None, "WIC_mtx": None, "GCV": None, "model_type": "GLM",
             "coef_names": names, "marge_coef_names": names, "record": rec,
             "knots": [infos[0].knots[k] for k in range(infos[0].n_knots)]}
+
+
+def glmmKnots(X_pred=None, Y=None, id_vec=None, M_glm: int = 3, approx_knot: bool = True, device: int = 0) -> dict:
+    """The adaptive knot harvesting of fitGLMM() (fitGLMM.R:54-75): marge2(is.glmm = TRUE, M = M.glm) on every subject's cells --
+    ONE library call, a pt column per subject -- then the table of (knot, coef, old_coef, tp_fun) over the subjects whose model kept
+    a hinge.  The GLMM fit itself (glmmTMB) is out of scope."""
+    if X_pred is None or Y is None or id_vec is None:
+        raise ValueError("You forgot some inputs to fitGLMM().")
+    ids = np.asarray(id_vec)
+    x = np.asarray(X_pred, dtype=np.float64).reshape(-1)
+    if np.any(ids[1:] != ids[:-1]) and len(np.unique(ids)) != 1 + np.count_nonzero(ids[1:] != ids[:-1]):
+        raise ValueError("Your data must be ordered by subject, please do so before running fitGLMM().")
+    subjects = list(dict.fromkeys(ids.tolist()))
+    pt = np.full((x.size, len(subjects)), np.nan)
+    for k, sname in enumerate(subjects):
+        pt[ids == sname, k] = x[ids == sname]
+    y = np.ascontiguousarray(np.asarray(Y).reshape(1, -1), dtype=np.int32)
+    o = _opts(M_glm, approx_knot, gpu_ids=[device])
+    recs, _ = run_records(y, pt, None, o, basis_only=True)
+    out = {"knot": [], "coef": [], "old_coef": [], "tp_fun": [], "subject": []}
+    for k, sname in enumerate(subjects):
+        rec = recs[k]
+        if not (rec.status & _abi.SCLANE_MARGE_OK) or rec.n_terms <= 1:
+            continue                                      # keepmods: only models with more than the intercept (fitGLMM.R:65-66)
+        clean, raw = _term_names(rec, "A"), _raw_term_names(rec, "Lineage_A")
+        for j in range(1, rec.n_terms):
+            out["knot"].append(float(rec.term_label[j]))
+            out["coef"].append(clean[j])
+            out["old_coef"].append("B_final" + raw[j])
+            out["tp_fun"].append("tp1" if rec.term_kind[j] == _abi.TERM_TP1 else "tp2")
+            out["subject"].append(sname)
+    return out
 
 
 def _th_warn(bits: int):

@@ -221,9 +221,9 @@ struct DevicePlan {
   }
 };
 
-template <int STAGE>
+template <int STAGE, bool HYB = false>
 void launch_stage(const StageArgs& A, cudaStream_t s) {
-  k_stage<STAGE><<<A.n_genes, kThreads, 0, s>>>(A);
+  k_stage<STAGE, HYB><<<A.n_genes, kThreads, 0, s>>>(A);
   CK(cudaGetLastError());
   g_launches.fetch_add(1);
 }
@@ -383,7 +383,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   D.upload(P, pool, s);
   if (use_comp) D.upload_points(P, pool, s);
   // fits with an offset: intercept-only models through the offset quadrature (needs the histogram of k_aggregate)
-  const bool use_offq = use_comp && use_offset && P.ON.on && !o.offset_per_cell;
+  const bool use_offq = use_comp && use_offset && P.ON.on && !o.offset_per_cell && !o.basis_only;
   if (use_offq) D.upload_offset_nodes(P, pool, s);
   CK(cudaStreamSynchronize(s));                     // plan tables are in place before the kernels start
   int* d_ys = (int*)pool.get("ys", (size_t)B * (size_t)L.Npad * 4);
@@ -443,7 +443,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = D.off; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
     A.scores = nullptr; A.mom = d_mom; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
-    A.order = nullptr;
+    A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr;
     CompArgs CA;
     CA.order = nullptr;
     WgArgs WA;
@@ -498,6 +498,26 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     tm.mark(SCLANE_STAGE_BACKWARD);
     launch_stage<STAGE_BACKWARD>(A, s);
     prof.launches[SCLANE_STAGE_BACKWARD]++;
+    if (!o.basis_only) {
+    if (use_offq) {
+      // offsets: node weights of every gene, then the intercept-only fits on the nodes (warp per gene); the per-cell kernel
+      // below then only fits the alternatives that kept a hinge
+      tm.mark(SCLANE_STAGE_OFF_AGG);
+      OffAggArgs OA;
+      OA.lineage = D.lin; OA.on = D.on; OA.oord = D.oord; OA.oxi_ord = D.oxi_ord; OA.off_ord = D.off_ord; OA.ys = d_ys; OA.cg = d_cg;
+      OA.off_s = d_off_s; OA.off_q = d_off_q; OA.offg = d_offg; OA.n_genes = nb;
+      k_off_aggregate<<<nb, kThreads, 0, s>>>(OA);
+      CK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      prof.launches[SCLANE_STAGE_OFF_AGG]++;
+      tm.mark(SCLANE_STAGE_OFF_NULL);
+      if (!use_wg) CK(cudaMemsetAsync(d_counters, 0, 8 * sizeof(int), s));      // (the warp-per-gene forward launch zeroes them otherwise)
+      WA.C = CA; WA.C.order = nullptr; WA.counter = d_counters + 3;
+      k_wg_stage<WG_OFFNULL><<<wg_grid(nb), kWgThreads, 0, s>>>(WA);
+      CK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      prof.launches[SCLANE_STAGE_OFF_NULL]++;
+    }
     // final stage: expensive (near-Poisson) genes first, so that no slow CTA is left running alone at the end of the launch
     tm.mark(SCLANE_STAGE_SELECT);
     k_order_final<<<(nb + 255) / 256, 256, 0, s>>>(d_out, nb, d_okeys, d_order, use_offset ? 3 : 0);
@@ -517,28 +537,17 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_COMP_FINAL]++;
     }
-    if (use_offq) {
-      // offsets: node weights of every gene, then the intercept-only fits on the nodes (warp per gene); the per-cell kernel
-      // below then only fits the alternatives that kept a hinge
-      tm.mark(SCLANE_STAGE_OFF_AGG);
-      OffAggArgs OA;
-      OA.lineage = D.lin; OA.on = D.on; OA.oord = D.oord; OA.oxi_ord = D.oxi_ord; OA.off_ord = D.off_ord; OA.ys = d_ys; OA.cg = d_cg;
-      OA.off_s = d_off_s; OA.off_q = d_off_q; OA.offg = d_offg; OA.n_genes = nb;
-      k_off_aggregate<<<nb, kThreads, 0, s>>>(OA);
-      CK(cudaGetLastError());
-      g_launches.fetch_add(1);
-      prof.launches[SCLANE_STAGE_OFF_AGG]++;
-      tm.mark(SCLANE_STAGE_OFF_NULL);
-      if (!use_wg) CK(cudaMemsetAsync(d_counters, 0, 8 * sizeof(int), s));      // (the warp-per-gene forward launch zeroes them otherwise)
-      WA.C = CA; WA.counter = d_counters + 3;
-      k_wg_stage<WG_OFFNULL><<<wg_grid(nb), kWgThreads, 0, s>>>(WA);
-      CK(cudaGetLastError());
-      g_launches.fetch_add(1);
-      prof.launches[SCLANE_STAGE_OFF_NULL]++;
-    }
     tm.mark(SCLANE_STAGE_FINAL);
+    if (use_offq) {
+      // alternatives with hinges: hybrid per-cell passes (mu-free terms from the histogram); genes without a histogram
+      // (route 0) are left to the plain per-cell launch below, which skips everything already done
+      A.cg = d_cg; A.tail = d_tail; A.big = d_big;
+      launch_stage<STAGE_FINAL, true>(A, s);
+      prof.launches[SCLANE_STAGE_FINAL]++;
+    }
     launch_stage<STAGE_FINAL>(A, s);
     prof.launches[SCLANE_STAGE_FINAL]++;
+    }
     tm.mark(SCLANE_STAGE_COPY);
     CK(cudaMemcpyAsync(h_out, d_out, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
     prof.d2h_bytes += (double)nb * sizeof(GeneOutDev);
@@ -552,7 +561,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       GeneOut go;
       go.st = h_out[i].st; go.alt = h_out[i].alt; go.null = h_out[i].null;
       sclane_record& r = out[((b0 - out_g0) + i) * n_lineages + lin_idx];
-      finalize_record(go, L, r);
+      finalize_record(go, L, r, o.basis_only != 0);
       // sweeps actually run for this gene: one per forward iteration it entered
       const int sw = go.st.fwd_iters;
       prof.sweep_gene_iters += sw;
@@ -1188,6 +1197,15 @@ int32_t sclane_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t n_ge
   return test_dynamic_impl(counts, nullptr, -1, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen);
 }
 
+int32_t sclane_marge_basis(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
+                           const sclane_opts* opts, sclane_record* out, sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  if (!opts) { set_err(errbuf, errlen, "opts is NULL"); return SCLANE_ERR_ARG; }
+  if (opts->mode != 0) { set_err(errbuf, errlen, "sclane_marge_basis() runs the GLM forward / backward pass (opts->mode = 0)"); return SCLANE_ERR_ARG; }
+  sclane_opts o = *opts;
+  o.basis_only = 1;
+  return test_dynamic_impl(counts, nullptr, -1, n_cells, n_genes, pt, n_lineages, nullptr, &o, out, lineages, errbuf, errlen);
+}
+
 int32_t sclane_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
                                 const int32_t* subject_id, const double* size_factor, const sclane_opts* opts, sclane_record* out,
                                 sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
@@ -1263,7 +1281,7 @@ int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_
     CK(cudaMemcpyAsync(d_out, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = nullptr; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
-    A.scores = nullptr; A.mom = nullptr; A.n_genes = nb; A.M = 5; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr;
+    A.scores = nullptr; A.mom = nullptr; A.n_genes = nb; A.M = 5; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr;
     launch_stage<STAGE_FWD_FIT>(A, s);
     CK(cudaMemcpyAsync(h.data(), d_out, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
     std::vector<double> hmu;
@@ -1320,7 +1338,7 @@ int32_t sclane_score_glm(const int32_t* counts, const double* mu, int64_t n_cell
     CK(cudaMemcpyAsync(d_out, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = nullptr; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
-    A.scores = d_scores; A.mom = d_mom; A.n_genes = nb; A.M = 99; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr;
+    A.scores = d_scores; A.mom = d_mom; A.n_genes = nb; A.M = 99; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr;
     launch_sweep(A, true, s, nullptr, nullptr);
     std::vector<double> hs((size_t)nb * 2 * L.T);
     CK(cudaMemcpyAsync(hs.data(), d_scores, hs.size() * 8, cudaMemcpyDeviceToHost, s));
@@ -1477,6 +1495,12 @@ int32_t sclane_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t n_ge
                             sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
   return guarded(errbuf, errlen, [&]() -> int32_t {
     return impl::sclane_test_dynamic(counts, n_cells, n_genes, pt, n_lineages, size_factor, opts, out, lineages, errbuf, errlen);
+  });
+}
+int32_t sclane_marge_basis(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,
+                           const sclane_opts* opts, sclane_record* out, sclane_lineage_info* lineages, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_marge_basis(counts, n_cells, n_genes, pt, n_lineages, opts, out, lineages, errbuf, errlen);
   });
 }
 int32_t sclane_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* pt, int32_t n_lineages,

@@ -34,11 +34,18 @@ struct CompGeneHdr {
   double SB[NBMAX], SBu[NBMAX], SBuu[NBMAX], QB[NBMAX];     // per bucket: sum y, sum y u, sum y u^2, sum y^2
 };
 
+// per-gene aggregates as the device holds them (k_aggregate)
+struct CompGeneDev {
+  CompGeneHdr hdr;
+  double ST[NBMAX][5];          // glm.fit mustart pass per bucket: sum w, sum w u, sum w u^2, sum w z, sum w z u
+};
+
 // One point of the compressed layout: n cells, s = sum y, q = sum y^2, all with the same mean mu = exp(a + c u).
 template <int MODE>
 SC_HD void point_contrib(double n, double s, double q, double u, double a, double c, double sigma, double theta, bool want_ll,
-                         const FastTabs* ft, double* acc, double* sc) {
-  const double eta = a + c * u;
+                         const FastTabs* ft, double* acc, double* sc, double off = 0.0) {
+  // off: offset of the point (only the per-cell hybrid passes of the fits with a size-factor offset pass one: n = 1, s = y)
+  const double eta = a + c * u + off;
   const double mu = sc_exp(eta, ft);
   if (MODE == PASS_SWEEP) {
     const double inv = rcp_pos(1.0 + sigma * mu);
@@ -75,7 +82,7 @@ SC_HD void point_contrib(double n, double s, double q, double u, double a, doubl
     const double inv = rcp_pos(t1);
     const double w = n * mu * inv;
     const double r = (s - n * mu) * inv;
-    const double wz = w * eta + r;
+    const double wz = w * (eta - off) + r;                 // w z, z = (eta - offset) + (y - mu)/mu
     acc[0] += w; acc[1] += w * u; acc[2] += w * u * u;
     acc[3] += wz; acc[4] += wz * u;
     const double lg = sc_log1p_pos(sm, t1, inv, ft);

@@ -19,11 +19,6 @@
 
 namespace sclane {
 
-struct CompGeneDev {
-  CompGeneHdr hdr;
-  double ST[NBMAX][5];          // glm.fit mustart pass per bucket: sum w, sum w u, sum w u^2, sum w z, sum w z u
-};
-
 struct CompArgs {
   const Lineage* lineage;
   const int* pstart;            // [D + 1]
@@ -60,6 +55,10 @@ struct CompArgs {
 // 170.0 / 14.0 (128 registers, 2 CTAs/SM); backward + final fused into one launch 162.0 / 15.2;
 // flat buckets evaluated in parallel by the lanes of warp 0 + least-loaded assignment of the sloped buckets 149.7 / 12.7;
 // means cached in global memory across the Newton iterations of theta.ml (41 of 56 passes per gene) 146.9 / 12.9.
+#ifndef SCLANE_COMP_UNROLL
+#define SCLANE_COMP_UNROLL 2            // independent points per lane in flight in the sloped-bucket loops
+#endif
+constexpr int kCompUnroll = SCLANE_COMP_UNROLL;
 constexpr int kCompWarps = SCLANE_COMP_WARPS;
 constexpr int kCompThreads = kCompWarps * 32;
 constexpr int kAggV = 9;        // per-bucket totals gathered by k_aggregate
@@ -363,7 +362,7 @@ struct CompDevExec {
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
       const int p1 = pbstart[b + 1];
-#pragma unroll 2
+#pragma unroll kCompUnroll
       for (int d = pbstart[b] + lane; d < p1; d += 32)
         point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], a, c, sigma, theta, want_ll, ft, acc, sc);
 #pragma unroll

@@ -10,12 +10,15 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "sclane_core.cuh"
+#include "sclane_comp.cuh"
 
 namespace sclane {
 
+// two independent cells per lane per iteration of the per-cell pass loops.  Measured on B200 (C4-shaped final stage, 8,000
+// gene-lineage fits): 208 -> 163 ms once fast_exp() was made branch free (before that the rare-path call split the loop body
+// into basic blocks and the two cells were not interleaved: no gain)
 #ifndef SCLANE_PASS_ILP2
-#define SCLANE_PASS_ILP2 0
+#define SCLANE_PASS_ILP2 1
 #endif
 #ifndef SCLANE_STAGE_MINB
 #define SCLANE_STAGE_MINB 3
@@ -37,7 +40,13 @@ template <> struct PassTraits<PASS_THETA>      { static constexpr int NA = 0, NS
 template <> struct PassTraits<PASS_SWEEP>      { static constexpr int NA = 7, NS = 0; };
 template <> struct PassTraits<PASS_EMIT>       { static constexpr int NA = 0, NS = 0; };
 
-struct DevExec {
+// HYB = false: the per-cell executor (every term per cell, count-indexed special-function tables).
+// HYB = true:  the hybrid executor of the fits WITH an offset (alternatives with hinges): the mu-dependent terms per cell --
+//              mu_i = exp(a_b + c_b u_i + o_i) differs from cell to cell -- but every mu-free term (psi / trigamma / lgamma
+//              differences, (y + theta) log1p(sigma y)) from the gene's count histogram, exactly as the X-compressed passes do
+//              (sclane_comp.cuh): no per-pass tables, no table look-ups and no large-count branch in the cell loop.
+template <bool HYB>
+struct DevExecT {
   Work* W;
   const Lineage* L;
   const int* __restrict__ y;        // sorted counts of this gene, row padded to Npad
@@ -48,10 +57,17 @@ struct DevExec {
   double (*scw)[NSC];               // [kWarps] warp-private partial scalars
   PassTabs* tb;                     // count-indexed special-function tables of the current pass
   const FastTabs* ft;               // exp / log1p tables in shared memory (sclane_fastmath.cuh)
+  // hybrid mode only: the gene's aggregates of k_aggregate
+  const CompGeneDev* cg;
+  const GeneStats* gs;
+  const int* __restrict__ tail;
+  const int* __restrict__ big;
+  const double* wtab;               // [64] glm.fit start weights by count (shared memory)
+  const double* wztab;
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
-  __device__ __forceinline__ PassTabs* tabs() const { return tb; }
+  __device__ __forceinline__ PassTabs* tabs() const { return HYB ? nullptr : tb; }
   template <class F>
   __device__ __forceinline__ void par_for(int n, F f) const {
     for (int i = threadIdx.x; i < n; i += kThreads) f(i);
@@ -104,6 +120,26 @@ struct DevExec {
     __syncthreads();
   }
 
+  // one cell of a pass
+  template <int MODE>
+  __device__ __forceinline__ void cell(int yi, double ui, double oi, double a, double c, double sigma, double theta, bool want_ll,
+                                       double* acc, double* sc, double& mo) const {
+    if (HYB) {
+      if (MODE == PASS_IRLS_START) {
+        double w, wz;
+        if (yi < 64) { w = wtab[yi]; wz = wztab[yi]; } else start_cell(yi, w, wz);
+        wz -= w * oi;                                  // z = (log(mustart) - offset) + (y - mu)/mu
+        acc[0] += w; acc[1] += w * ui; acc[2] += w * ui * ui;
+        acc[3] += wz; acc[4] += wz * ui;
+      } else if (MODE == PASS_IRLS || MODE == PASS_THETA) {
+        const double y = (double)yi;
+        point_contrib<MODE>(1.0, y, y * y, ui, a, c, sigma, theta, want_ll, ft, acc, sc, oi);
+      }
+    } else {
+      cell_contrib<MODE>(yi, ui, oi, a, c, sigma, theta, *tb, ft, 0.0, want_ll, acc, sc, mo);
+    }
+  }
+
   // FP64-bound passes (fits, theta.ml, emit): ONE compact copy of the per-cell math, one cell per lane
   // per iteration (a warp still reads 32 consecutive cells: 128 B of counts, 256 B of coordinates).
   // The loop body must stay small: these kernels were instruction-fetch bound when it was unrolled.
@@ -147,8 +183,9 @@ struct DevExec {
       double a = W->a[cur_b], c = W->c[cur_b];
       // constant linear predictor inside the bucket (no slope term, no offset): hoist exp / log1p / reciprocals
       constexpr bool kCanFlat = (MODE == PASS_FIT || MODE == PASS_IRLS || MODE == PASS_THETA || MODE == PASS_EMIT);
-      bool flat = kCanFlat && !use_off && c == 0.0;
-      FlatBucket fb = make_flat_bucket(flat ? a : 0.0, sigma);
+      bool flat = !HYB && kCanFlat && !use_off && c == 0.0;
+      FlatBucket fb;
+      if (!HYB) fb = make_flat_bucket(flat ? a : 0.0, sigma);
       int g = g0;
 #pragma unroll 1
       while (g < g1) {
@@ -160,8 +197,8 @@ struct DevExec {
           const double u0 = __ldg(u + i), u1 = __ldg(u + i + 32);
           const double o0 = use_off ? __ldg(off + i) : 0.0, o1 = use_off ? __ldg(off + i + 32) : 0.0;
           double m0, m1;
-          cell_contrib<MODE>(y0, u0, o0, a, c, sigma, theta, *tb, ft, 0.0, want_ll, acc, sc, m0);
-          cell_contrib<MODE>(y1, u1, o1, a, c, sigma, theta, *tb, ft, 0.0, want_ll, acc2, sc2, m1);
+          cell<MODE>(y0, u0, o0, a, c, sigma, theta, want_ll, acc, sc, m0);
+          cell<MODE>(y1, u1, o1, a, c, sigma, theta, want_ll, acc2, sc2, m1);
           if (MODE == PASS_EMIT) { mu[i] = m0; mu[i + 32] = m1; }
           g += 2;
           continue;
@@ -173,10 +210,10 @@ struct DevExec {
           const double ui = __ldg(u + i);
           double mo;
           if (flat) {
-            cell_contrib_flat<MODE>(yi, ui, fb, sigma, theta, *tb, want_ll, acc, sc, mo);
+            if (!HYB) cell_contrib_flat<MODE>(yi, ui, fb, sigma, theta, *tb, want_ll, acc, sc, mo);
           } else {
             const double oi = use_off ? __ldg(off + i) : 0.0;
-            cell_contrib<MODE>(yi, ui, oi, a, c, sigma, theta, *tb, ft, 0.0, want_ll, acc, sc, mo);
+            cell<MODE>(yi, ui, oi, a, c, sigma, theta, want_ll, acc, sc, mo);
           }
           if (MODE == PASS_EMIT) mu[i] = mo;
           g += 1;
@@ -193,7 +230,7 @@ struct DevExec {
 #pragma unroll
         for (int k = 0; k < NACC; ++k) ct[k] = 0.0;
         if (valid) {
-          cell_contrib<MODE>(yi, ui, oi, W->a[b], W->c[b], sigma, theta, *tb, ft, 0.0, want_ll, ct, sc, mo);
+          cell<MODE>(yi, ui, oi, W->a[b], W->c[b], sigma, theta, want_ll, ct, sc, mo);
           if (MODE == PASS_EMIT) mu[i] = mo;
         }
         if (NA > 0) {
@@ -212,7 +249,7 @@ struct DevExec {
         cur_b = b_last;
         b_hi = Lr.bstart[cur_b + 1];
         a = W->a[cur_b]; c = W->c[cur_b];
-        flat = kCanFlat && !use_off && c == 0.0;
+        flat = !HYB && kCanFlat && !use_off && c == 0.0;
         if (flat) fb = make_flat_bucket(a, sigma);
         g += 1;
       }
@@ -224,8 +261,25 @@ struct DevExec {
 #endif
       if (NA > 0) flush_uniform<NA>(acc, cur_b, myslot, NACC);
     }
+    if (HYB && NS > 0 && (MODE == PASS_IRLS || MODE == PASS_THETA)) {
+      // the mu-free terms of the pass from the gene's tail counts and its list of large counts (sclane_comp.cuh)
+      const int ymax = cg->hdr.ymax;
+      const int hmax = ymax < kHistCap ? ymax : kHistCap - 1;
+      for (int k = threadIdx.x; k < hmax; k += kThreads) hist_contrib<MODE>(k, (double)tail[k], (double)tail[k + 1], sigma, theta, want_ll, sc);
+      const int n_big = cg->hdr.n_big;
+      for (int e = threadIdx.x; e < n_big; e += kThreads) big_contrib<MODE>(big[e], sigma, theta, want_ll, sc);
+    }
     if (NS > 0) flush_uniform<NS>(sc, 0, &scw[warp][0], 0);
     combine<NA, NS>(T);
+    if (HYB && MODE == PASS_IRLS_START) {
+      // deviance and theta.ml start sums at mustart do not involve the offset: gene constants (as the compressed start pass)
+      if (threadIdx.x == 0) {
+        W->sc[0] = -gs->sum_ylogy + (double)cg->hdr.n_zero * theta * log1p(sigma / 6.0);
+        W->sc[1] = (double)cg->hdr.n_zero;
+        W->sc[2] = 0.0;
+      }
+      __syncthreads();
+    }
   }
 
   template <int MODE>
@@ -234,6 +288,7 @@ struct DevExec {
     pass_scalar<MODE>();
   }
 };
+using DevExec = DevExecT<false>;
 
 // ---------------------------------------------------------------------------------------------
 // kernel arguments
@@ -257,12 +312,16 @@ struct StageArgs {
   int M;
   double tols_score;
   int use_offset;
+  // hybrid final stage (k_stage<STAGE_FINAL, true>): the gene aggregates of k_aggregate
+  const CompGeneDev* cg;       // [B]
+  const int* tail;             // [B][kHistCap]
+  const int* big;              // [B][kBigCap]
   const int* order;            // optional CTA -> gene map of the final stage (k_order_final: expensive genes first), or nullptr
 };
 
 enum Stage : int { STAGE_FWD_FIT = 0, STAGE_BACKWARD = 2, STAGE_FINAL = 3 };
 
-template <int STAGE>
+template <int STAGE, bool HYB = false>
 __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs A) {
   __shared__ Work W;
   __shared__ Lineage Ls;
@@ -273,9 +332,12 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   __shared__ PassTabs tabs;
   __shared__ FastTabs ftab;
   __shared__ TermTabs ttab;
+  __shared__ double wtab[HYB ? 64 : 1], wztab[HYB ? 64 : 1];
   if ((int)blockIdx.x >= A.n_genes) return;
   const int g = ((STAGE == STAGE_FINAL || STAGE == STAGE_BACKWARD) && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
+  if (HYB && A.cg[g].hdr.route == 0) return;          // block-uniform: this gene has no histogram (plain per-cell kernel fits it)
   {
+    if (HYB && threadIdx.x < 64) start_cell(threadIdx.x, wtab[threadIdx.x], wztab[threadIdx.x]);
     // cooperative word copies of the small per-lineage / per-gene structs
     const int* src = reinterpret_cast<const int*>(A.lineage);
     int* dst = reinterpret_cast<int*>(&Ls);
@@ -297,7 +359,9 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   if (STAGE == STAGE_FINAL && (st.done & 2)) return;
   const size_t row = (size_t)g * (size_t)Ls.Npad;
   const long long t_start = clock64();
-  DevExec ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs, &ftab};
+  DevExecT<HYB> ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs, &ftab,
+                   HYB ? A.cg + g : nullptr, &gs, HYB ? A.tail + (size_t)g * (size_t)kHistCap : nullptr, HYB ? A.big + (size_t)g * (size_t)kBigCap : nullptr,
+                   wtab, wztab};
   if (STAGE == STAGE_FWD_FIT) {
     gene_forward_fit(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_BACKWARD) {
@@ -305,6 +369,8 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   } else if (STAGE == STAGE_FINAL) {
     // genes whose intercept-only fits already ran on the offset quadrature (done bit 2) only need the alternative with hinges
     gene_final(ex, Ls, gs, st, W, A.use_offset != 0, &A.out[g].alt, &A.out[g].null, (st.done & 4) ? 2 : 3);
+    __syncthreads();
+    if (threadIdx.x == 0) st.done |= 2;
   }
   __syncthreads();
   if (threadIdx.x == 0) { st.passes += W.passes; st.cycles[STAGE == STAGE_FWD_FIT ? 0 : (STAGE == STAGE_BACKWARD ? 1 : 2)] += clock64() - t_start; }
@@ -690,8 +756,11 @@ __global__ void k_order_final(const GeneOutDev* __restrict__ out, int n, double*
     // final fits WITH an offset: the forward fits ran without it, so a gene whose forward sigma is small is one whose
     // dispersion is mostly depth variation -- with the offset its theta runs away and glm.nb goes to the alternation limit
     // (bench generator: Spearman -0.71 between forward sigma and the final stage's passes; the score only 0.43)
+    // The offset quadrature has fitted the null model by now: a null fit that ran to the alternation limit (theta runs away
+    // once the depth variation is in the offset) predicts the same for the alternative -- those genes cost 5-10x the median.
     const GeneState& st = out[i].st;
-    keys[i] = (st.error || st.fin.n <= 1) ? 1e300 : st.sigma;      // intercept-only alternatives are not fitted per cell: last
+    const double sg = st.sigma < 1e5 ? st.sigma : 1e5;
+    keys[i] = (st.error || st.fin.n <= 1) ? 1e300 : (out[i].null.ok ? -1e6 * (double)out[i].null.alternations : 0.0) + sg;
     return;
   }
   if (phase == 0) {

@@ -11,7 +11,7 @@
 //                             j = 0 has rc = 1, lc = 0: full RELATIVE accuracy as t -> 1.
 //   fast_log1p_pos(x, t, inv) = fast_log_ge1(t) + (x - (t - 1)) * inv     (the rounding error of t = fl(1 + x) put back:
 //                             relative accuracy for tiny x, i.e. for the near-Poisson fits with theta ~ 1e6)
-//   fast_exp(x), |x| < 700:   k = rint(64 x / ln2), r = x - k ln2/64 (two-term Cody-Waite, |r| <= 0.0055),
+//   fast_exp(x):              k = rint(64 x / ln2), r = x - k ln2/64 (two-term Cody-Waite, |r| <= 0.0055),
 //                             exp x = 2^(k >> 6) * 2^((k & 63)/64) * (1 + r + r^2/2 + ... + r^6/720)
 //
 // Errors (checked against 60-digit arithmetic in tests/test_host_logic.py through the host twin below): <= 1 ulp.
@@ -93,14 +93,16 @@ SC_HD double fast_log1p_pos(double x, double t, double inv, const FastTabs& ft) 
   return fma(x - (t - 1.0), inv, fast_log_ge1(t, ft));
 }
 
-SC_HDN double slow_exp(double x) { return exp(x); }
-
+// Branch free (a rare-path call would split the loop body into basic blocks and stop the compiler from interleaving the
+// independent cells / points of an unrolled pass loop): the argument is clamped to +-700 for the arithmetic and the IEEE
+// results of the out-of-range cases are put back with selects: x > 700 -> +inf (exp overflows at 709.78; mu > 1e304 is a
+// diverged fit either way), x < -700 -> 0, NaN -> NaN.
 SC_HD double fast_exp(double x, const FastTabs& ft) {
-  if (!(fabs(x) < 700.0)) return slow_exp(x);                           // overflow / underflow / NaN: the library's handling
-  double kd = fma(x, SCLANE_64_LN2, 6755399441055744.0);                // 1.5 * 2^52: round to nearest integer in the low word
+  const double xc = fmin(fmax(x, -700.0), 700.0);
+  double kd = fma(xc, SCLANE_64_LN2, 6755399441055744.0);               // 1.5 * 2^52: round to nearest integer in the low word
   const int k = fm_lo(kd);
   kd -= 6755399441055744.0;
-  double r = fma(kd, -SCLANE_LN2_64_HI, x);
+  double r = fma(kd, -SCLANE_LN2_64_HI, xc);
   r = fma(kd, -SCLANE_LN2_64_LO, r);
   double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
   q = fma(r, q, 1.0 / 24.0);
@@ -108,8 +110,11 @@ SC_HD double fast_exp(double x, const FastTabs& ft) {
   q = fma(r, q, 0.5);
   const double p = fma(r * r, q, r);
   const double s0 = ft.ex[k & 63];
-  const double s = fm_make(fm_hi(s0) + ((k >> 6) << 20), fm_lo(s0));     // * 2^(k >> 6): exponent stays in the normal range for |x| < 700
-  return fma(s, p, s);
+  const double s = fm_make(fm_hi(s0) + ((k >> 6) << 20), fm_lo(s0));     // * 2^(k >> 6): exponent stays in the normal range for |x| <= 700
+  double res = fma(s, p, s);
+  res = x > 700.0 ? (double)INFINITY : res;
+  res = x < -700.0 ? 0.0 : res;
+  return x != x ? x : res;
 }
 
 // The math policy of the pass bodies: with tables (device kernels, host tests of the tables) the fast versions, without

@@ -358,14 +358,16 @@ struct GeneOut {
   NbResult alt, null;
 };
 
-inline void finalize_record(const GeneOut& g, const Lineage& L, sclane_record& r) {
+inline void finalize_record(const GeneOut& g, const Lineage& L, sclane_record& r, bool basis_only = false) {
   const double NaN = std::numeric_limits<double>::quiet_NaN();
   std::memset(&r, 0, sizeof(r));
   const GeneState& st = g.st;
-  const bool marge_ok = (st.fin.n >= 1) && g.alt.ok && !(st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC | SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
-  const bool null_ok = g.null.ok && !(st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
+  // basis_only (marge2(is.glmm = TRUE)): the record is OK when the backward pass selected a basis; nothing was fitted
+  const bool basis_ok = (st.fin.n >= 1) && !(st.error & (SCLANE_NOTE_FWD_EMPTY | SCLANE_NOTE_NUMERIC | SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
+  const bool marge_ok = basis_only ? basis_ok : (basis_ok && g.alt.ok);
+  const bool null_ok = !basis_only && g.null.ok && !(st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
   r.status = (marge_ok ? SCLANE_MARGE_OK : 0) | (null_ok ? SCLANE_NULL_OK : 0);
-  r.marge_notes = st.error | (marge_ok ? g.alt.notes : 0);
+  r.marge_notes = st.error | ((marge_ok && !basis_only) ? g.alt.notes : 0);
   r.null_notes = null_ok ? g.null.notes : (st.error & (SCLANE_NOTE_ALL_ZERO | SCLANE_NOTE_BAD_COUNTS));
   for (int j = 0; j < SCLANE_PMAX; ++j) {
     r.term_kind[j] = 0; r.term_knot_idx[j] = -1;
@@ -386,15 +388,18 @@ inline void finalize_record(const GeneOut& g, const Lineage& L, sclane_record& r
         r.term_knot[j] = L.knots[st.fin.knot[j]];
         r.term_label[j] = r_signif(r.term_knot[j], 4);
       }
+      if (basis_only) continue;
       r.coef[j] = g.alt.coef[j];
       r.se[j] = std::sqrt(g.alt.cov[j * PMAX + j]);
       r.z[j] = r.coef[j] / r.se[j];
       r.p[j] = pnorm_two_sided(r.z[j]);
       for (int l = 0; l < p; ++l) r.cov[j * p + l] = g.alt.cov[j * PMAX + l];
     }
+    if (!basis_only) {
     r.theta = g.alt.theta; r.se_theta = g.alt.se_theta;
     r.loglik = g.alt.loglik; r.deviance = g.alt.deviance;
     r.alternations = g.alt.alternations; r.irls_iters = g.alt.irls_iters;
+    }
   }
   if (null_ok) {
     r.null_coef = g.null.coef[0];

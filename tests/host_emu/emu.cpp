@@ -425,3 +425,21 @@ extern "C" void emu_default_opts(sclane_opts* o) {
   std::memset(o, 0, sizeof(*o));
   o->abi_version = SCLANE_ABI_VERSION; o->mode = 0; o->M = 5; o->approx_knot = 1; o->n_knot_max = 25; o->minspan = -1; o->tols_score = 1e-5; o->gee_cor = SCLANE_COR_AR1;
 }
+
+// finalize_record_gee() on a hand-made device result: alternative fitted (3 terms), null geem fit failed
+extern "C" void emu_finalize_gee_null_failed(int gee_test, sclane_record* out) {
+  Lineage L;
+  std::memset(&L, 0, sizeof(L));
+  L.N = 300; L.T = 3; L.knots[0] = 0.25; L.knots[1] = 0.5; L.knots[2] = 0.75;
+  GeeGeneOut go;
+  std::memset(&go, 0, sizeof(go));
+  init_gene_state(go.st);
+  go.st.fin.n = 3;
+  go.st.fin.kind[0] = SCLANE_TERM_INTERCEPT; go.st.fin.kind[1] = SCLANE_TERM_TP1; go.st.fin.kind[2] = SCLANE_TERM_TP2;
+  go.st.fin.knot[1] = 1; go.st.fin.knot[2] = 1;
+  go.alt.ok = 1; go.alt.converged = 1; go.alt.niter = 4; go.alt.alpha = 0.3; go.alt.phi = 1.2; go.alt.score_stat = 7.0;
+  go.alt.coef[0] = 1.0; go.alt.coef[1] = 0.5; go.alt.coef[2] = -0.25;
+  for (int j = 0; j < 3; ++j) { go.alt.cov[j * GEE_PMAX + j] = 0.01; go.alt.cov_robust[j * GEE_PMAX + j] = 0.02; }
+  go.null.ok = 0;
+  finalize_record_gee(go, L, gee_test, 0, 3, *out);
+}

@@ -234,3 +234,84 @@ def test_gee_gpu_vs_core_at_config3_subject_size(emu):
                     assert rel(a.coef[j], b.coef[j], 1e-6) < TOL and rel(a.se[j], b.se[j], 1e-6) < TOL, (order, i, j)
                 assert rel(a.test_stat, b.test_stat, 1e-6) < TOL and rel(a.gee_phi, b.gee_phi) < TOL, (order, i)
         assert n_ok >= 6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Round 2: the CUDA path against the INDEPENDENT dense oracle at subject sizes where the AR-1 / exchangeable conditioning
+# (alpha -> 1, chains of > 1,000 cells) can bite.  The dense oracle builds and inverts n_i x n_i matrices like the reference
+# (O(n_i^3)): ~75 s per gene at 3,300 cells, so the genes are spread over the box's cores.
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_gee_one(a):
+    from threadpoolctl import threadpool_limits
+    counts, pt, subject, gene, sf, cor = a
+    with threadpool_limits(limits=1):
+        return oracle_gee(counts, pt, subject, [gene], sf, cor)
+
+
+def _correlated_counts(n_genes, sizes, seed, rho):
+    """NB counts whose mean carries a slowly varying AR(1) log-factor per subject (lag-1 correlation rho): the working
+    correlation the geem fits estimate comes out close to 1."""
+    from tools import synth
+    n = int(sum(sizes))
+    rng = np.random.default_rng(seed)
+    pt = np.concatenate([np.sort(rng.random(s)) for s in sizes])            # cells ordered by pseudotime inside each subject
+    subject = np.repeat(np.arange(len(sizes)), sizes)
+    counts = np.empty((n_genes, n), dtype=np.int32)
+    for g in range(n_genes):
+        z = np.empty(n)
+        start = 0
+        for s in sizes:
+            e = rng.normal(0.0, 1.0, s)
+            zz = np.empty(s)
+            zz[0] = e[0]
+            for j in range(1, s):
+                zz[j] = rho * zz[j - 1] + np.sqrt(1.0 - rho * rho) * e[j]
+            z[start:start + s] = zz
+            start += s
+        eta = rng.normal(3.0, 0.3) + rng.normal(0.0, 2.0) * np.maximum(pt - rng.uniform(0.2, 0.8), 0.0) + 1.0 * z
+        counts[g] = rng.poisson(np.exp(np.clip(eta, -6, 7)))
+    del synth
+    return counts, pt, subject
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cor,rho", [("ar1", 0.0), ("ar1", 0.995), ("exchangeable", 0.0)])
+def test_gee_gpu_vs_dense_oracle_large_subjects(cor, rho):
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    from sclane_b200 import _abi, api
+    sizes = (700, 1100, 1500)                                            # unequal subjects, 3,300 cells
+    n_genes = min(12, max(4, (os.cpu_count() or 4)))
+    if rho > 0:
+        counts, pt, subject = _correlated_counts(n_genes, sizes, 41, rho)
+        sf = None
+    else:
+        counts, pt, subject, sf = _gee_data(seed=43, sizes=sizes, n_genes=n_genes, sorted_within=True)
+    genes = [f"G{i}" for i in range(n_genes)]
+    o = api._opts(gpu_ids=[0])
+    o.mode = 1
+    o.gee_cor = _abi.COR_CODES[cor]
+    recs, _ = api.run_records(counts, pt, sf, o, subject_id=subject.astype(np.int32))
+    ref = {}
+    with ProcessPoolExecutor(max_workers=min(os.cpu_count() or 1, n_genes)) as ex:
+        for part in ex.map(_oracle_gee_one, [(counts[i:i + 1], pt, subject, genes[i], sf, cor) for i in range(n_genes)]):
+            ref.update(part)
+    assert _compare(recs, ref, genes) == []
+    alphas = [r.gee_alpha for r in recs if r.status & 1]
+    if rho > 0.9:
+        assert max(alphas) > 0.9, alphas                                  # the case the test is about: alpha close to 1
+    print(f"{cor} rho={rho}: fitted alpha range {min(alphas):.3f} .. {max(alphas):.3f}, genes with a fitted model {len(alphas)}")
+
+
+def test_gee_tests_are_na_when_the_null_model_failed(emu):
+    """waldTestGEE.R:31-37 / scoreTestGEE.R:34-39: Wald_Stat, DF and P_Val are NA when EITHER model is a try-error (the test
+    must not reach getResultsDE's FDR adjustment with a real-looking p-value)."""
+    import ctypes as C
+    from sclane_b200 import _abi
+    for gee_test in (0, 1):
+        rec = _abi.SclaneRecord()
+        emu.emu_finalize_gee_null_failed.argtypes = [C.c_int, C.POINTER(_abi.SclaneRecord)]
+        emu.emu_finalize_gee_null_failed(gee_test, C.byref(rec))
+        assert rec.status == 1 and rec.n_terms == 3                       # MARGE model OK, null model error
+        assert np.isnan(rec.test_stat) and np.isnan(rec.df) and np.isnan(rec.p_val)
+        assert rec.coef[1] == 0.5 and np.isnan(rec.null_coef)

@@ -1,0 +1,280 @@
+"""Round-2 parity tests of the CUDA path (through the C ABI) against the independent dense oracle at the BASELINE shapes and on
+the edge cases the selection rules of marge2.R care about.  Everything here needs a B200 (pytest -m gpu)."""
+import os
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_EXCEPTIONS, rel
+from oracle import marge as omarge
+from oracle.testdynamic import test_dynamic as oracle_test_dynamic
+from test_gpu_parity import TOL, _compare_with_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_chunk(a):
+    from threadpoolctl import threadpool_limits
+    counts, pt, genes, sf = a
+    with threadpool_limits(limits=1):
+        return oracle_test_dynamic(counts, pt, genes, sf, keep_preds=False)
+
+
+def oracle_parallel(counts, pt, genes, sf=None):
+    """The oracle over a process pool (one chunk of genes per core)."""
+    cores = min(os.cpu_count() or 1, 16, len(genes))
+    chunks = [(counts[i::cores], pt, genes[i::cores], sf) for i in range(cores)]
+    out = {}
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        for part in ex.map(_oracle_chunk, chunks):
+            out.update(part)
+    return {g: out[g] for g in genes}
+
+
+def test_c2_shape_208_genes_vs_oracle():
+    """BASELINE configs[1] shape (10,000 cells, M = 5, no offset), 208 genes of the bench generator: default (X-compressed) route
+    against the dense oracle -- term sets, LRT, coefficients, SEs, log-likelihoods, deviances, theta."""
+    import sclane_b200 as sb
+    from tools import synth
+    counts, pt, _ = synth.make_counts(208, 10000, seed=312)
+    genes = [f"g{i}" for i in range(counts.shape[0])]
+    res = sb.testDynamic(counts, pt, genes=genes, n_gpus=1, preds="none")
+    assert res.profile["ms"]["comp_forward"] > 0
+    worst = _compare_with_oracle(res, oracle_parallel(counts, pt.reshape(-1), genes))
+    print("C2 shape, worst relative differences:", worst)
+
+
+def test_c4_shape_two_lineages_offsets_vs_oracle():
+    """BASELINE configs[3] shape: 50,000 cells, 2 lineages (60 % of the cells each, NaN outside), createCellOffset() offsets;
+    64 genes = 128 gene-lineage fits.  Exercises the offset quadrature (intercept-only fits) and the hybrid per-cell passes."""
+    import bench
+    import sclane_b200 as sb
+    from tools import synth
+    counts, pt, _ = synth.make_counts(64, 50000, seed=5)
+    pt2 = bench.two_lineages(pt.reshape(-1))
+    sf = sb.createCellOffset(counts)
+    genes = [f"g{i}" for i in range(counts.shape[0])]
+    res = sb.testDynamic(counts, pt2, genes=genes, size_factor_offset=sf, n_gpus=1, preds="none")
+    assert res.profile["ms"]["off_null"] > 0 and res.profile["launches"]["off_aggregate"] == 2
+    worst = _compare_with_oracle(res, oracle_parallel(counts, pt2, genes, sf))
+    print("C4 shape, worst relative differences:", worst)
+
+
+def _records_close(a, b, tol, what):
+    assert len(a) == len(b)
+    worst = 0.0
+    for i, (ra, rb) in enumerate(zip(a, b)):
+        assert ra.status == rb.status and ra.n_terms == rb.n_terms, (what, i)
+        assert [ra.term_kind[j] for j in range(ra.n_terms)] == [rb.term_kind[j] for j in range(rb.n_terms)], (what, i)
+        assert [ra.term_knot_idx[j] for j in range(ra.n_terms)] == [rb.term_knot_idx[j] for j in range(rb.n_terms)], (what, i)
+        assert (ra.alternations, ra.null_alternations, ra.irls_iters, ra.null_irls_iters) == (rb.alternations, rb.null_alternations, rb.irls_iters, rb.null_irls_iters), (what, i)
+        for f in ("loglik", "null_loglik", "deviance", "null_deviance", "null_coef", "null_se", "theta", "null_theta", "se_theta"):
+            va, vb = getattr(ra, f), getattr(rb, f)
+            if va == va or vb == vb:
+                worst = max(worst, rel(va, vb))
+        if ra.test_stat == ra.test_stat:
+            worst = max(worst, abs(ra.test_stat - rb.test_stat) / (abs(rb.test_stat) + 1e-3))
+        for j in range(ra.n_terms):
+            worst = max(worst, rel(ra.coef[j], rb.coef[j]), rel(ra.se[j], rb.se[j]))
+    assert worst < tol, (what, worst)
+    return worst
+
+
+def test_offset_quadrature_equals_per_cell_fits():
+    """The intercept-only glm.nb with an offset through the offset quadrature (K bins x 16 Chebyshev nodes) against the same
+    fits per cell: identical iteration counts, every statistic within 1e-10 -- incl. offsets spanning e^7."""
+    import sclane_b200 as sb
+    from sclane_b200 import api
+    from tools import synth
+    counts, pt, _ = synth.make_counts(96, 20000, seed=17)         # D = 10,001 abscissae <= 0.8 N: the X-compressed route
+    rng = np.random.default_rng(3)
+    for spread in (0.0, 1.0):
+        sf = 1e4 / np.maximum(counts.sum(axis=0), 1) * np.exp(rng.normal(0.0, spread, counts.shape[1]))
+        a, _ = api.run_records(counts, pt, sf, api._opts(gpu_ids=[0]))
+        assert sb.get_profile()["ms"]["off_null"] > 0
+        b, _ = api.run_records(counts, pt, sf, api._opts(gpu_ids=[0], offset_per_cell=True))
+        assert sb.get_profile()["ms"]["off_null"] == 0
+        w = _records_close(a, b, 1e-10, f"offset spread {spread}")
+        print(f"offset quadrature vs per cell, log-offset range {np.ptp(np.log(sf)):.2f}: worst relative difference {w:.2e}")
+
+
+def test_warp_per_gene_kernels_equal_cta_per_gene():
+    """The opt-in warp-per-gene persistent kernels (work queue) give the records of the CTA-per-gene kernels."""
+    from sclane_b200 import api
+    from tools import synth
+    counts, pt, _ = synth.make_counts(300, 20000, seed=23)
+    a, _ = api.run_records(counts, pt, None, api._opts(gpu_ids=[0]))
+    b, _ = api.run_records(counts, pt, None, api._opts(gpu_ids=[0], comp_warp_per_gene=True))
+    _records_close(a, b, 1e-9, "warp per gene")
+
+
+def _symmetric_case(n_genes, seed):
+    """121 cells on a symmetric 4-dp grid with mirrored counts: the candidate knots come out symmetric (positions
+    1, 6, ..., 121 of min_span; < 25 of them, so no seq()), and in the first forward iteration the pair candidate at knot t and at
+    1 - t span mirror images of each other -> their scores tie after round(., 6) (marge2.R:537-549: which.max = FIRST maximum)."""
+    rng = np.random.default_rng(seed)
+    x = 0.02 + 0.008 * np.arange(121)
+    half = np.empty((n_genes, 61), dtype=np.int64)
+    for g in range(n_genes):
+        mu = np.exp(1.0 + rng.normal(0, 0.5) + rng.normal(0, 3.0) * np.maximum(x[:61] - rng.uniform(0.1, 0.45), 0.0))
+        half[g] = rng.negative_binomial(5.0, 5.0 / (5.0 + mu))
+    counts = np.concatenate([half, half[:, :60][:, ::-1]], axis=1).astype(np.int32)
+    assert np.array_equal(counts, counts[:, ::-1])
+    return counts, x
+
+
+def test_exact_score_ties_first_maximum_rule():
+    """Engineered exact ties (north_star: "ties broken identically"): symmetric data make the two best pair candidates tie after
+    round(score, 6); marge2.R's which.max() takes the first.  CUDA == oracle on every gene, and the tie is real."""
+    import sclane_b200 as sb
+    from sclane_b200 import api
+    counts, x = _symmetric_case(40, 7)
+    genes = [f"s{i}" for i in range(counts.shape[0])]
+    res = sb.testDynamic(counts, x, genes=genes, n_gpus=1, preds="none")
+    knots = np.array(res.lineage_info[0]["knots"])
+    assert len(knots) < 25 and np.allclose(knots + knots[::-1], 1.0, atol=1e-12), knots
+    _compare_with_oracle(res, oracle_test_dynamic(counts, x, genes, None, keep_preds=False))
+    # the sweep's own scores: intercept-only basis, sigma / mu of the null fit
+    beta, sigma, mu = api.stat_out_score_glm_null(counts, x, knots, [0], [0])
+    sc = api.score_fun_glm_sweep(counts, mu, sigma, x, knots, [0], [0])
+    n_tied = 0
+    for g in range(counts.shape[0]):
+        both = np.round(sc[g, 1], 6)
+        k = int(np.nanargmax(both))
+        mirror = len(knots) - 1 - k
+        if mirror != k and both[mirror] == both[k]:
+            n_tied += 1
+            rec = res.records[g]
+            if rec.fwd_n_terms >= 3 and rec.fwd_kind[2] == 2:            # iteration 1 took the pair: at the FIRST of the tied knots
+                assert rec.fwd_knot_idx[1] == min(k, mirror), (g, k, mirror, rec.fwd_knot_idx[1])
+    assert n_tied >= 10, n_tied
+
+
+def test_heavy_pseudotime_ties_and_few_knots():
+    """3,000 cells on only 40 distinct pseudotime values (D << 25 knots' worth after max_span), and a 200-cell lineage with
+    fewer than 25 candidate knots: CUDA == oracle."""
+    import sclane_b200 as sb
+    from tools import synth
+    rng = np.random.default_rng(11)
+    counts, pt, _ = synth.make_counts(24, 3000, seed=9)
+    pt40 = np.round(np.floor(pt.reshape(-1) * 40) / 40 + 0.0125, 4)
+    genes = [f"g{i}" for i in range(24)]
+    res = sb.testDynamic(counts, pt40, genes=genes, n_gpus=1, preds="none")
+    assert len(np.unique(pt40)) == 40 and len(res.lineage_info[0]["knots"]) <= 25
+    _compare_with_oracle(res, oracle_test_dynamic(counts, pt40, genes, None, keep_preds=False))
+    c2, p2, _ = synth.make_counts(24, 200, seed=10)
+    res2 = sb.testDynamic(c2, p2, genes=genes, n_gpus=1, preds="none")
+    assert len(res2.lineage_info[0]["knots"]) < 25
+    _compare_with_oracle(res2, oracle_test_dynamic(c2, p2.reshape(-1), genes, None, keep_preds=False))
+    del rng
+
+
+def test_pseudotime_outside_unit_interval_takes_per_cell_route():
+    """Pseudotime on [0, 50]: 4-dp rounding leaves D ~ N abscissae (> 0.8 N), so the library routes every fit to the per-cell
+    kernels on its own; with and without offsets, CUDA == oracle."""
+    import sclane_b200 as sb
+    from tools import synth
+    counts, pt, _ = synth.make_counts(24, 3000, seed=13)
+    pt50 = pt.reshape(-1) * 50.0
+    genes = [f"g{i}" for i in range(24)]
+    res = sb.testDynamic(counts, pt50, genes=genes, n_gpus=1, preds="none")
+    assert res.profile["ms"]["comp_forward"] == 0 and res.profile["ms"]["fwd_fit"] > 0
+    _compare_with_oracle(res, oracle_test_dynamic(counts, pt50, genes, None, keep_preds=False))
+    sf = sb.createCellOffset(counts)
+    res = sb.testDynamic(counts, pt50, genes=genes, size_factor_offset=sf, n_gpus=1, preds="none")
+    assert res.profile["ms"]["off_null"] == 0
+    _compare_with_oracle(res, oracle_test_dynamic(counts, pt50, genes, sf, keep_preds=False))
+
+
+@pytest.mark.parametrize("kw", [{"minspan": 30}, {"n_knot_max": 10}, {"n_knot_max": 32}, {"M": 7, "n_knot_max": 12}])
+def test_marge2_wrapper_options_vs_oracle(kw):
+    """marge2() (marge2.R:56-72) with minspan given, n.knot.max in {10, 12, 32} and M = 7: coefficient names and values == oracle."""
+    import sclane_b200 as sb
+    from tools import synth
+    counts, pt, _ = synth.make_counts(10, 2500, seed=31)
+    x = pt.reshape(-1)
+    n_ok = 0
+    for g in range(counts.shape[0]):
+        o = omarge.marge2(x, counts[g].astype(np.float64), None, **kw)
+        try:
+            r = sb.marge2(x, counts[g], **kw)
+        except sb.SclaneError:
+            assert not o.ok
+            continue
+        assert o.ok
+        assert r["coef_names"] == o.coef_names, (g, kw)
+        for a, b in zip(r["final_mod"]["coefficients"].values(), o.fit.coef):
+            assert rel(a, b) < TOL
+        assert rel(r["final_mod"]["logLik"], o.fit.loglik) < TOL
+        lim = kw.get("n_knot_max", 25)
+        assert len(r["knots"]) <= lim
+        n_ok += 1
+    assert n_ok >= 6
+
+
+def test_product_mirror_vs_reference_golden(golden_inputs, golden_models):
+    """The host mirror of the reference's R functions (sclane_b200/api.py) against the reference's own bundled output:
+    Gene_Dynamics (summarizeModel), MARGE_Slope_Data / testSlope, marge2() and modelLRT()."""
+    import sclane_b200 as sb
+    res = sb.testDynamic(golden_inputs["counts"], golden_inputs["pt"], genes=golden_inputs["genes"],
+                         size_factor_offset=golden_inputs["size_factor"], n_gpus=1, preds="none")
+    checked = 0
+    for g, gold in golden_models.items():
+        if g in GOLDEN_EXCEPTIONS:
+            continue
+        r = res[g]["Lineage_A"]
+        gd, gg = r["Gene_Dynamics"], gold["Gene_Dynamics"]
+        assert set(gd) == set(gg), (g, sorted(gd), sorted(gg))
+        for k in gg:
+            a, b = gd[k][0], gg[k][0]
+            if isinstance(b, str) or b is None or isinstance(a, str):
+                assert a == b, (g, k, a, b)
+            else:
+                assert a is not None and (abs(a - b) <= 1e-6 * (abs(b) + 1e-9)), (g, k, a, b)
+        sd, sg = r["MARGE_Slope_Data"], gold["MARGE_Slope_Data"]
+        assert sd["Notes"] == sg["Notes"] and sd["Direction"] == sg["Direction"]
+        for k in ("Breakpoint", "Rounded_Breakpoint", "Beta", "Test_Stat", "P_Val"):
+            for a, b in zip(sd[k], sg[k]):
+                assert (a is None and b is None) or rel(a, b, 1e-300) < 1e-5, (g, k, a, b)
+        checked += 1
+    assert checked == 89
+    # testSlope(): BH over all breakpoints, flags per gene
+    ts = sb.testSlope(res)
+    assert {"Gene", "Breakpoint", "P_Val_Adj", "Gene_Dynamic_Lineage_Slope", "Gene_Dynamic_Lineage", "Gene_Dynamic_Overall"} <= set(ts.columns)
+    pv = ts["P_Val"].to_numpy(dtype=float)
+    ok = ~np.isnan(pv)
+    from oracle.rmath import p_adjust_bh
+    assert np.allclose(ts["P_Val_Adj"].to_numpy(dtype=float)[ok], p_adjust_bh(pv[ok]), rtol=1e-12)
+    assert (ts.groupby("Gene")["Gene_Dynamic_Overall"].nunique() == 1).all()
+    # marge2() + modelLRT() on single genes == the batch result and the golden LRT
+    x, sf = golden_inputs["pt"].reshape(-1), golden_inputs["size_factor"]
+    for g in [gg for gg in golden_inputs["genes"] if gg not in GOLDEN_EXCEPTIONS][:12]:
+        i = golden_inputs["genes"].index(g)
+        gold = golden_models[g]
+        m1 = sb.marge2(x, golden_inputs["counts"][i], sf)
+        assert m1["coef_names"] == gold["MARGE_Summary"]["term"]
+        lrt = sb.modelLRT(m1, {"logLik": gold["LogLik_Null"], "df": 2})
+        assert rel(lrt["LRT_Stat"], gold["Test_Stat"], 1e-6) < TOL and lrt["DF"] == gold["Degrees_Freedom"]
+        assert rel(lrt["P_Val"], gold["P_Val"], 1e-300) < 1e-5
+    assert sb.modelLRT(None, {"logLik": 0.0, "df": 2})["Notes"] == "No test performed due to model failure."
+
+
+def test_in_library_multi_gpu_sharding_is_bit_identical():
+    """opts.n_gpus > 1: one host thread + stream per GPU inside the library; records equal those of one GPU byte for byte."""
+    import sclane_b200 as sb
+    from sclane_b200 import _abi, api
+    from tools import synth
+    n = sb.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    counts, pt, _ = synth.make_counts(301, 20000, seed=5)
+    a, _ = api.run_records(counts, pt, None, api._opts(gpu_ids=[0]))
+    b, _ = api.run_records(counts, pt, None, api._opts(gpu_ids=list(range(n))))
+    off, sz = _abi.SclaneRecord.gene_time.offset, 8
+    cyc, csz = _abi.SclaneRecord.stage_cycles.offset, 24
+    for ra, rb in zip(a, b):
+        ba, bb = bytearray(bytes(ra)), bytearray(bytes(rb))
+        for o_, s_ in ((off, sz), (cyc, csz)):
+            ba[o_:o_ + s_] = bb[o_:o_ + s_] = bytes(s_)
+        assert ba == bb
