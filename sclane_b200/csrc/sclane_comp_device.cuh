@@ -274,6 +274,7 @@ template <> struct CompTraits<PASS_SWEEP>      { static constexpr int NA = 5, NS
 template <> struct CompTraits<PASS_EMIT>       { static constexpr int NA = 0, NS = 0; };
 
 struct CompDevExec {
+  static constexpr bool kTabs = true;      // term tables attached to Work (sclane_core.cuh term_coef)
   Work* W;
   const Lineage* L;
   const CompGeneDev* cg;            // shared-memory copy

@@ -151,9 +151,11 @@ SC_HD void work_attach_tabs(Work& W, TermTabs* tt) {
   W.tal = tt ? tt->tal : nullptr;
   W.tga = tt ? tt->tga : nullptr;
 }
-// alpha/gamma of term j of model m in bucket b: from the tables when they exist, else on the fly
+// alpha/gamma of term j of model m in bucket b: from the tables (executors with E::kTabs: the CTA-per-gene kernels, where the
+// small algebra between two passes is serial time every warp of the CTA waits for) or on the fly (warp-per-gene kernels)
+template <bool TABS>
 SC_HD void term_coef(const Lineage& L, const Model& m, const Work& W, int j, int b, double& al, double& ga) {
-  if (W.tal) { al = W.tal[j][b]; ga = W.tga[j][b]; }
+  if (TABS) { al = W.tal[j][b]; ga = W.tga[j][b]; }
   else term_ab(L, m.kind[j], m.knot[j], b, al, ga);
 }
 
@@ -173,17 +175,18 @@ struct SetModelFn {
 template <class E>
 SC_HD void coop_set_model(E& ex, const Lineage& L, const Model& m, Work& W) {
   ex.sync();
-  if (W.tal == nullptr) return;                   // no tables: term_coef() computes on the fly (uniform branch)
+  if (!E::kTabs) return;                          // no tables: term_coef() computes on the fly
   SetModelFn fn{&L, &m, &W};
   ex.par_for(m.n * (L.T + 1), fn);
   ex.sync();
 }
 // eta parameters per bucket from beta (beta must live in shared memory).
+template <bool TABS>
 struct SetEtaFn {
   const Lineage* L; const Model* m; Work* W; const double* beta;
   SC_HD void operator()(int b) const {
     double a = 0.0, c = 0.0;
-    for (int j = 0; j < m->n; ++j) { double al, ga; term_coef(*L, *m, *W, j, b, al, ga); a += beta[j] * al; c += beta[j] * ga; }
+    for (int j = 0; j < m->n; ++j) { double al, ga; term_coef<TABS>(*L, *m, *W, j, b, al, ga); a += beta[j] * al; c += beta[j] * ga; }
     W->a[b] = a;
     W->c[b] = c;
   }
@@ -191,7 +194,7 @@ struct SetEtaFn {
 template <class E>
 SC_HD void coop_set_eta(E& ex, const Lineage& L, const Model& m, Work& W, const double* beta) {
   ex.sync();
-  SetEtaFn fn{&L, &m, &W, beta};
+  SetEtaFn<E::kTabs> fn{&L, &m, &W, beta};
   ex.par_for(L.T + 1, fn);
   ex.sync();
 }
@@ -232,6 +235,7 @@ SC_HD void coop_set_tables(E& ex, Work& W) {
 
 // Symmetric system from a pass: H[j][l] = <d_j, d_l> with accumulators I0..I0+2, grad[j] = <d_j, .> with J0, J0+1,
 // and (K0 >= 0) the extra column H[j][p] = <d_j, .> with K0, K0+1.  Results in W.H (NSYS stride) / W.grad.
+template <bool TABS>
 struct SystemFn {
   const Lineage* L; const Model* m; Work* W; int I0, J0, K0;
   SC_HD void operator()(int t) const {
@@ -244,8 +248,8 @@ struct SystemFn {
       double s = 0.0;
       for (int b = 0; b < nb; ++b) {
         double aj, gj, al, gl;
-        term_coef(*L, *m, *W, j, b, aj, gj);
-        term_coef(*L, *m, *W, l, b, al, gl);
+        term_coef<TABS>(*L, *m, *W, j, b, aj, gj);
+        term_coef<TABS>(*L, *m, *W, l, b, al, gl);
         s += aj * al * W->acc[b][I0] + (aj * gl + al * gj) * W->acc[b][I0 + 1] + gj * gl * W->acc[b][I0 + 2];
       }
       W->H[j * NSYS + l] = s;
@@ -253,12 +257,12 @@ struct SystemFn {
     } else if (t < ntri + p) {
       const int j = t - ntri;
       double s = 0.0;
-      for (int b = 0; b < nb; ++b) { double al, ga; term_coef(*L, *m, *W, j, b, al, ga); s += al * W->acc[b][J0] + ga * W->acc[b][J0 + 1]; }
+      for (int b = 0; b < nb; ++b) { double al, ga; term_coef<TABS>(*L, *m, *W, j, b, al, ga); s += al * W->acc[b][J0] + ga * W->acc[b][J0 + 1]; }
       W->grad[j] = s;
     } else {
       const int j = t - ntri - p;
       double s = 0.0;
-      for (int b = 0; b < nb; ++b) { double al, ga; term_coef(*L, *m, *W, j, b, al, ga); s += al * W->acc[b][K0] + ga * W->acc[b][K0 + 1]; }
+      for (int b = 0; b < nb; ++b) { double al, ga; term_coef<TABS>(*L, *m, *W, j, b, al, ga); s += al * W->acc[b][K0] + ga * W->acc[b][K0 + 1]; }
       W->H[j * NSYS + p] = s;
       W->H[p * NSYS + j] = s;
     }
@@ -266,7 +270,7 @@ struct SystemFn {
 };
 template <class E>
 SC_HD void coop_system(E& ex, const Lineage& L, const Model& m, Work& W, int I0, int J0, int K0) {
-  SystemFn fn{&L, &m, &W, I0, J0, K0};
+  SystemFn<E::kTabs> fn{&L, &m, &W, I0, J0, K0};
   const int p = m.n;
   ex.par_for(p * (p + 1) / 2 + (J0 >= 0 ? p : 0) + (K0 >= 0 ? p : 0), fn);
   ex.sync();
@@ -683,6 +687,7 @@ SC_HDN bool sweep_invert(const Model& m, Work& W) {
 
 // score of candidate knot k; both = pair (tp1, tp2) else tp1 only.  Any thread may call it once the
 // model tables (coop_set_model) and W.cov (sweep_invert) are in place.  NaN = NA.
+template <bool TABS>
 SC_HDN double sweep_score(const Lineage& L, const Model& m, const Work& W, int k, bool both) {
   if (cand_collinear(L, m, k, both)) return nan("");
   const int p = m.n, nb = L.T + 1;
@@ -700,7 +705,7 @@ SC_HDN double sweep_score(const Lineage& L, const Model& m, const Work& W, int k
       const double s0 = W.acc[b][0], s1 = W.acc[b][1], s2 = W.acc[b][2];
       const double w0 = al * s0 + ga * s1;      // <cand, 1>_w  restricted to the bucket
       const double w1 = al * s1 + ga * s2;      // <cand, u>_w
-      for (int j = 0; j < p; ++j) { double tj, gj; term_coef(L, m, W, j, b, tj, gj); C[q][j] += tj * w0 + gj * w1; }
+      for (int j = 0; j < p; ++j) { double tj, gj; term_coef<TABS>(L, m, W, j, b, tj, gj); C[q][j] += tj * w0 + gj * w1; }
       d += al * w0 + ga * w1;
       bv += al * W.acc[b][3] + ga * W.acc[b][4];
     }
@@ -1283,14 +1288,15 @@ SC_HDN void glm_nb(E& ex, const Lineage& L, const Model& m, const GeneStats& gst
 // The four per-gene stages as the kernels run them (K1 forward null fit, K2 score sweep,
 // K4 backward pass, K5 final + null glm.nb).  `st` and `W` are CTA-shared on device.
 // ---------------------------------------------------------------------------------------------
+template <bool TABS>
 struct ScoreFn {
   const Lineage* L;
   const Model* m;
   Work* W;
   SC_HD void operator()(int i) const {
     const int T = L->T;
-    if (i < T) { const double v = sweep_score(*L, *m, *W, i, false); W->sw_one[i] = v; W->sw_one_r[i] = r_round(v, 1e6); }
-    else if (i < 2 * T) { const double v = sweep_score(*L, *m, *W, i - T, true); W->sw_both[i - T] = v; W->sw_both_r[i - T] = r_round(v, 1e6); }
+    if (i < T) { const double v = sweep_score<TABS>(*L, *m, *W, i, false); W->sw_one[i] = v; W->sw_one_r[i] = r_round(v, 1e6); }
+    else if (i < 2 * T) { const double v = sweep_score<TABS>(*L, *m, *W, i - T, true); W->sw_both[i - T] = v; W->sw_both_r[i - T] = r_round(v, 1e6); }
   }
 };
 
@@ -1334,7 +1340,7 @@ SC_HDN void gene_sweep_select(E& ex, const Lineage& L, const GeneStats& gstat, G
     ex.sync();
     return;
   }
-  ScoreFn fn{&L, &st.fwd, &W};
+  ScoreFn<E::kTabs> fn{&L, &st.fwd, &W};
   ex.par_for(2 * L.T, fn);
   ex.sync();
   if (ex.leader()) forward_select(L, st, W);

@@ -47,6 +47,7 @@ template <> struct PassTraits<PASS_EMIT>       { static constexpr int NA = 0, NS
 //              (sclane_comp.cuh): no per-pass tables, no table look-ups and no large-count branch in the cell loop.
 template <bool HYB>
 struct DevExecT {
+  static constexpr bool kTabs = true;      // term tables attached to Work (sclane_core.cuh term_coef)
   Work* W;
   const Lineage* L;
   const int* __restrict__ y;        // sorted counts of this gene, row padded to Npad
@@ -620,6 +621,7 @@ k_sweep_moments(const Lineage* __restrict__ lineage, const int* __restrict__ ys,
 // marge2.R:368-587, the stat_out check and the forward bookkeeping.
 // ---------------------------------------------------------------------------------------------
 struct WarpExec {
+  static constexpr bool kTabs = false;      // term tables attached to Work (sclane_core.cuh term_coef)
   __device__ __forceinline__ PassTabs* tabs() const { return nullptr; }     // the select kernel runs no pass
   __device__ __forceinline__ bool leader() const { return (threadIdx.x & 31) == 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }

@@ -50,6 +50,7 @@ struct GeeShared {
 };
 
 struct GeeDevExec {
+  static constexpr bool kTabs = true;      // term tables attached to Work (sclane_core.cuh term_coef)
   GeeShared* S;
   const int* __restrict__ y;
   const unsigned char* __restrict__ bid;

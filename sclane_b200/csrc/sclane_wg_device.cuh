@@ -49,6 +49,7 @@ struct WgGeneShared {
 };
 
 struct WgExec {
+  static constexpr bool kTabs = false;      // term tables attached to Work (sclane_core.cuh term_coef)
   Work* W;
   const Lineage* L;
   const CompGeneDev* cg;            // global memory (read-only here)

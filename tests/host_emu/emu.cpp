@@ -13,6 +13,7 @@
 using namespace sclane;
 
 struct HostExec {
+  static constexpr bool kTabs = true;      // term tables attached to Work (sclane_core.cuh term_coef)
   Work* W;
   const Lineage* L;
   const int32_t* y;        // sorted counts of this gene [N]
@@ -45,6 +46,7 @@ struct HostExec {
 
 // ---- X-compressed executor (sclane_comp.cuh), serial: defines the semantics of the compressed passes ----
 struct CompHostExec {
+  static constexpr bool kTabs = false;      // term tables attached to Work (sclane_core.cuh term_coef)
   Work* W;
   const Lineage* L;
   const LineagePlan* P;
@@ -202,8 +204,9 @@ extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t 
       Work W;
       std::memset(&W, 0, sizeof(W));
       TermTabs tt;
-      // force_per_cell: term tables (as k_stage has them); otherwise none -> term_coef() on the fly (as the warp-per-gene kernels)
-      work_attach_tabs(W, opts->force_per_cell == 1 ? &tt : nullptr);
+      // HostExec reads the term tables (as k_stage / k_comp_stage do), CompHostExec computes term_ab() on the fly (as the
+      // warp-per-gene kernels do): both forms of term_coef() run on the CPU
+      work_attach_tabs(W, &tt);
       HostExec ex{&W, &L, y.data(), P.u.data(), P.off.empty() ? nullptr : P.off.data(), mu.data(), P.bucket.data(), PassTabs()};
       // opts->force_per_cell == 1: per-cell executor everywhere; otherwise the X-compressed executor runs every fit without
       // an offset (the routing the CUDA path uses)
@@ -241,6 +244,7 @@ extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t 
 
 // ---- GEE mode: serial executor over the subject-ordered cells (defines the semantics of the GEE passes) ----
 struct GeeHostExec {
+  static constexpr bool kTabs = true;      // term tables attached to Work (sclane_core.cuh term_coef)
   Work* W;
   GeeWork* G;
   const Lineage* L;

@@ -212,11 +212,11 @@ def test_eigen_dropins():
 
 
 def _rec_bytes(rec) -> bytes:
-    """Record bytes with the gene_time field (wall-clock surrogate) masked out."""
+    """Record bytes with the timing fields (gene_time: wall-clock surrogate; stage_cycles: clock64 profile) masked out."""
     from sclane_b200 import _abi
-    off = _abi.SclaneRecord.gene_time.offset
     b = bytearray(bytes(rec))
-    b[off:off + 8] = b"\0" * 8
+    for fld, n in ((_abi.SclaneRecord.gene_time, 8), (_abi.SclaneRecord.stage_cycles, 24)):
+        b[fld.offset:fld.offset + n] = b"\0" * n
     return bytes(b)
 
 

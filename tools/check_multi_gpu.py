@@ -14,6 +14,8 @@ off = sb._abi.SclaneRecord.gene_time.offset
 def masked(r):
     v = bytearray(bytes(r))
     v[off:off + 8] = bytes(8)          # gene_time is a wall-clock surrogate
+    c = sb._abi.SclaneRecord.stage_cycles.offset
+    v[c:c + 24] = bytes(24)            # clock64 profile
     return bytes(v)
 
 
