@@ -76,7 +76,8 @@ typedef struct sclane_opts {
   int32_t mode;               /* 0 = GLM (is.gee = FALSE, is.glmm = FALSE).  1 = GEE (is.gee = TRUE, gee.test = "wald");
                                  GEE needs subject ids: use sclane_test_dynamic_gee().  2 (GLMM) -> SCLANE_ERR_UNSUPPORTED */
   int32_t M;                  /* n.potential.basis.fns / marge2 M, default 5, 3 <= M <= SCLANE_PMAX */
-  int32_t approx_knot;        /* approx.knot, default 1 (0 -> SCLANE_ERR_UNSUPPORTED for now) */
+  int32_t approx_knot;        /* approx.knot, default 1.  0 = every abscissa kept by min_span() / max_span() is a candidate knot
+                                 (marge2.R:167-173): prefix-moment sweep over the abscissae, GLM mode only */
   int32_t n_knot_max;         /* n.knot.max, default 25, <= SCLANE_TMAX */
   int32_t minspan;            /* marge2 minspan; -1 = NULL (automatic, min_span.R:24-26) */
   double  tols_score;         /* marge2 tols_score, default 1e-5 */
@@ -115,7 +116,8 @@ typedef struct sclane_record {
   int32_t null_notes;                   /* SCLANE_NOTE_* of the null model */
   int32_t n_terms;                      /* columns of the final model incl. intercept; 0 if marge2 failed */
   int32_t term_kind[SCLANE_PMAX];       /* SCLANE_TERM_* ; term 0 is the intercept */
-  int32_t term_knot_idx[SCLANE_PMAX];   /* index into the lineage's candidate knots; -1 for the intercept */
+  int32_t term_knot_idx[SCLANE_PMAX];   /* index into the lineage's candidate knots (approx_knot = 0: into the gene's own table of
+                                           selected knots); -1 for the intercept */
   double  term_knot[SCLANE_PMAX];       /* the knot itself (what tp1/tp2 were built with, marge2.R:589-590) */
   double  term_label[SCLANE_PMAX];      /* signif(knot, 4): the number printed in the coefficient name and parsed back
                                            by extractBreakpoints() (marge2.R:593-594, extractBreakpoints.R:27-28) */
@@ -160,9 +162,9 @@ typedef struct sclane_record {
 /* Per-lineage description returned to the caller (knots, cell membership). */
 typedef struct sclane_lineage_info {
   int64_t n_cells;                      /* cells with a non-NA pseudotime in this lineage (testDynamic.R:183) */
-  int32_t n_knots;
+  int32_t n_knots;                      /* number of candidate knots (approx_knot = 0: may exceed SCLANE_TMAX) */
   int32_t minspan;
-  double  knots[SCLANE_TMAX];           /* X_red of marge2.R:152-166, ascending */
+  double  knots[SCLANE_TMAX];           /* X_red of marge2.R:152-166, ascending (approx_knot = 0: the first SCLANE_TMAX of them) */
   double  pt_min, pt_max;               /* of the unrounded pseudotime (summarizeModel.R:71-72) */
 } sclane_lineage_info;
 

@@ -585,7 +585,7 @@ def testDynamic(expr_mat=None, pt=None, genes=None, size_factor_offset=None, is_
             ptl, sfl = lin_cache[l]
             per_l[f"Lineage_{LETTERS[l]}"] = _record_to_list(recs[g * n_lin + l], genes[g], l, infos[l], ptl, ptl, sfl, preds, dev0, is_gee, gee_test if is_gee else "wald")
         res[genes[g]] = per_l
-    res.lineage_info = [{"n_cells": int(i.n_cells), "knots": [i.knots[k] for k in range(i.n_knots)], "minspan": int(i.minspan),
+    res.lineage_info = [{"n_cells": int(i.n_cells), "n_knots": int(i.n_knots), "knots": [i.knots[k] for k in range(min(i.n_knots, _abi.SCLANE_TMAX))], "minspan": int(i.minspan),
                          "pt_min": i.pt_min, "pt_max": i.pt_max} for i in infos]
     res.profile = get_profile()
     res.records = recs
@@ -633,7 +633,7 @@ def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False,
             raise SclaneError(0, _notes(rec.marge_notes, False))
         return {"final_mod": None, "basis_mtx": None, "WIC_mtx": None, "GCV": None, "model_type": "GLMM",
                 "coef_names": _term_names(rec, "A"), "marge_coef_names": _raw_term_names(rec, "Lineage_A"), "record": rec,
-                "knots": [infos[0].knots[k] for k in range(infos[0].n_knots)]}
+                "knots": [infos[0].knots[k] for k in range(min(infos[0].n_knots, _abi.SCLANE_TMAX))]}
     if is_gee:
         if id_vec is None:
             raise ValueError("id.vec in marge2() must be non-null if is.gee = TRUE.")
@@ -657,7 +657,7 @@ def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False,
                               ("var" if sandwich_var else "naiv.var"): np.array([rec.cov[j] for j in range(p * p)]).reshape(p, p)},
                 "basis_mtx": None, "WIC_mtx": None, "GCV": None, "model_type": "GEE",
                 "coef_names": names, "marge_coef_names": names, "record": rec,
-                "knots": [infos[0].knots[k] for k in range(infos[0].n_knots)]}
+                "knots": [infos[0].knots[k] for k in range(min(infos[0].n_knots, _abi.SCLANE_TMAX))]}
     return {"final_mod": {"coefficients": dict(zip(names, [rec.coef[j] for j in range(p)])),
                           "std.error": [rec.se[j] for j in range(p)], "theta": rec.theta, "SE.theta": rec.se_theta,
                           "twologlik": 2.0 * rec.loglik, "logLik": rec.loglik, "df": p + 1, "deviance": rec.deviance,
@@ -666,7 +666,7 @@ def marge2(X_pred=None, Y=None, Y_offset=None, M: int = 5, is_gee: bool = False,
                           "vcov": np.array([rec.cov[j] for j in range(p * p)]).reshape(p, p)},
             "basis_mtx": None, "WIC_mtx": None, "GCV": None, "model_type": "GLM",
             "coef_names": names, "marge_coef_names": names, "record": rec,
-            "knots": [infos[0].knots[k] for k in range(infos[0].n_knots)]}
+            "knots": [infos[0].knots[k] for k in range(min(infos[0].n_knots, _abi.SCLANE_TMAX))]}
 
 
 def glmmKnots(X_pred=None, Y=None, id_vec=None, M_glm: int = 3, approx_knot: bool = True, device: int = 0) -> dict:

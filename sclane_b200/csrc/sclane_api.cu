@@ -15,6 +15,7 @@
 
 #include "sclane_comp_device.cuh"
 #include "sclane_wg_device.cuh"
+#include "sclane_exact_device.cuh"
 #include "sclane_device.cuh"
 #include "sclane_gee_device.cuh"
 #include "sclane_gee_host.hpp"
@@ -187,6 +188,15 @@ struct DevicePlan {
     pbstart = (int*)pool.get("pbstart", sizeof(P.pbstart));
     CK(cudaMemcpyAsync(pbstart, P.pbstart, sizeof(P.pbstart), cudaMemcpyHostToDevice, s));
   }
+  // exact-knot mode
+  double* px = nullptr;
+  int* cand = nullptr;
+  void upload_exact(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
+    px = (double*)pool.get("ex_px", P.px.size() * sizeof(double));
+    cand = (int*)pool.get("ex_cand", P.cand.size() * sizeof(int));
+    CK(cudaMemcpyAsync(px, P.px.data(), P.px.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(cand, P.cand.data(), P.cand.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  }
   // offset quadrature tables
   OffsetNodes* on = nullptr;
   int* oord = nullptr;
@@ -280,7 +290,8 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   const size_t pool_held = pool.held();
   auto batch_size = [&](int Npad, int Dpad, bool use_comp) -> int64_t {
     const size_t per_gene = (h_counts ? (size_t)n_cells * 8 : 0) + (size_t)Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
-                            (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0);
+                            (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0) +
+                            (o.approx_knot ? 0 : (size_t)Dpad * 16);
     size_t budget = (size_t)((double)(free_b + pool_held) * 0.6);
     const size_t cap = (size_t)SCLANE_BATCH_CAP_GB << 30;
     if (budget > cap) budget = cap;
@@ -368,7 +379,9 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   const LineagePlan& P = *Pp;
   const Lineage& L = P.L;
   // X-compressed path (sclane_comp.cuh): worth it when the 4-decimal rounding leaves clearly fewer abscissae than cells
-  const bool use_comp = !o.force_per_cell && P.D > 0 && (double)P.D <= 0.8 * (double)L.N;
+  // approx.knot = FALSE always runs on the abscissae (its sweep is a scan over them; sclane_exact_device.cuh)
+  const bool exact = P.exact;
+  const bool use_comp = exact || (!o.force_per_cell && P.D > 0 && (double)P.D <= 0.8 * (double)L.N);
   const int Dpad = (P.D + 31) / 32 * 32;
   {
     const int64_t B_real = batch_size(L.Npad, Dpad, use_comp);
@@ -382,6 +395,8 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   DevicePlan D;
   D.upload(P, pool, s);
   if (use_comp) D.upload_points(P, pool, s);
+  if (exact) D.upload_exact(P, pool, s);
+  if (exact && use_offset && !(P.ON.on && !o.offset_per_cell)) throw CudaFail{"approx.knot = FALSE with a size-factor offset needs the offset quadrature (offsets spanning more than e^32, or offset_per_cell set)"};
   // fits with an offset: intercept-only models through the offset quadrature (needs the histogram of k_aggregate)
   const bool use_offq = use_comp && use_offset && P.ON.on && !o.offset_per_cell && !o.basis_only;
   if (use_offq) D.upload_offset_nodes(P, pool, s);
@@ -404,11 +419,19 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   double* d_off_q = use_offq ? (double*)pool.get("off_q", (size_t)B * (size_t)(kOffKMax * kOffJ) * 8) : nullptr;
   OffGeneDev* d_offg = use_offq ? (OffGeneDev*)pool.get("off_gene", (size_t)B * sizeof(OffGeneDev)) : nullptr;
   int* d_counters = (int*)pool.get("wg_counters", 8 * sizeof(int));
+  double* d_a0p = exact ? (double*)pool.get("ex_a0p", (size_t)B * (size_t)Dpad * 8) : nullptr;
+  double* d_b0p = exact ? (double*)pool.get("ex_b0p", (size_t)B * (size_t)Dpad * 8) : nullptr;
   // persistent warp-per-gene kernels: one CTA slot per resident CTA of the device
   static int sm_count[SCLANE_MAX_GPUS] = {0};
   if (sm_count[device % SCLANE_MAX_GPUS] == 0) { int v = 0; CK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); sm_count[device % SCLANE_MAX_GPUS] = v; }
   const int wg_slots = sm_count[device % SCLANE_MAX_GPUS] * SCLANE_WG_MINB;
-  const bool use_wg = use_comp && o.comp_warp_per_gene;
+  const bool use_wg = use_comp && o.comp_warp_per_gene && !exact;
+  const int ex_slots = sm_count[device % SCLANE_MAX_GPUS] * 2;
+  double* d_ex_scratch = exact ? (double*)pool.get("ex_scratch", (size_t)ex_slots * (size_t)(2 + kExMom) * (size_t)Dpad * 8) : nullptr;
+  if (exact) {
+    static std::once_flag ex_once[SCLANE_MAX_GPUS];
+    std::call_once(ex_once[device % SCLANE_MAX_GPUS], [] { CK(cudaFuncSetAttribute(k_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExactShared))); });
+  }
   const int n_iter = forward_iterations(o.M);
   EventTimer tm(s);
   for (int64_t b0 = g0, kb = 0; b0 < g1; b0 += B, ++kb) {
@@ -443,7 +466,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = D.off; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
     A.scores = nullptr; A.mom = d_mom; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
-    A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr;
+    A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr; A.exact = 0; A.pstart = nullptr;
     CompArgs CA;
     CA.order = nullptr;
     WgArgs WA;
@@ -452,14 +475,21 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     if (use_comp) {
       CA.lineage = D.lin; CA.pstart = D.pstart; CA.pn = D.pn; CA.pu = D.pu; CA.pb = D.pb; CA.pbstart = D.pbstart; CA.D = P.D; CA.Dpad = Dpad; CA.ys = d_ys;
       CA.s1 = d_s1; CA.q = d_q; CA.tail = d_tail; CA.big = d_big; CA.big_tmp = d_big_tmp; CA.cg = d_cg; CA.stats = d_stats; CA.out = d_out; CA.n_genes = nb; CA.M = o.M;
-      CA.n_iter = n_iter; CA.tols_score = o.tols_score; CA.compute_stats = 1;
+      CA.n_iter = n_iter; CA.tols_score = o.tols_score; CA.compute_stats = 1; CA.a0p = d_a0p; CA.b0p = d_b0p;
       tm.mark(SCLANE_STAGE_AGGREGATE);
       k_aggregate<<<nb, kThreads, 0, s>>>(CA);
       CK(cudaGetLastError());
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_AGGREGATE]++;
       tm.mark(SCLANE_STAGE_COMP_FWD);
-      if (use_wg) {
+      if (exact) {
+        // forward + backward pass (+ the final fits when there is no offset) of every gene, per-gene buckets
+        CK(cudaMemsetAsync(d_counters, 0, 8 * sizeof(int), s));
+        ExactArgs EA;
+        EA.C = CA; EA.px = D.px; EA.cand = D.cand; EA.n_cand = (int)P.cand.size(); EA.scratch = d_ex_scratch; EA.counter = d_counters + 4;
+        EA.do_final = (!use_offset && !o.basis_only) ? 1 : 0;
+        k_exact<<<nb < ex_slots ? nb : ex_slots, kCompThreads, sizeof(ExactShared), s>>>(EA);
+      } else if (use_wg) {
         CK(cudaMemsetAsync(d_counters, 0, 8 * sizeof(int), s));
         WA.C = CA; WA.counter = d_counters + 0;
         k_wg_stage<WG_FORWARD><<<wg_grid(nb), kWgThreads, 0, s>>>(WA);
@@ -470,7 +500,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     }
     // per-cell kernels: every gene when the compressed path is off, otherwise only the genes k_aggregate routed away
     // (counts >= kHistCap); genes that already finished a stage return at once
-    for (int it = 0; it < n_iter; ++it) {
+    for (int it = 0; it < n_iter && !exact; ++it) {
       tm.mark(SCLANE_STAGE_FWD_FIT);
       launch_stage<STAGE_FWD_FIT>(A, s);
       prof.launches[SCLANE_STAGE_FWD_FIT]++;
@@ -485,7 +515,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.launches[SCLANE_STAGE_SELECT] += 2;
     A.order = d_order;
     CA.order = d_order;
-    if (use_comp) {
+    if (use_comp && !exact) {
       tm.mark(SCLANE_STAGE_COMP_BWD);
       if (use_wg) {
         WA.C = CA; WA.counter = d_counters + 1;
@@ -495,9 +525,11 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_COMP_BWD]++;
     }
-    tm.mark(SCLANE_STAGE_BACKWARD);
-    launch_stage<STAGE_BACKWARD>(A, s);
-    prof.launches[SCLANE_STAGE_BACKWARD]++;
+    if (!exact) {
+      tm.mark(SCLANE_STAGE_BACKWARD);
+      launch_stage<STAGE_BACKWARD>(A, s);
+      prof.launches[SCLANE_STAGE_BACKWARD]++;
+    }
     if (!o.basis_only) {
     if (use_offq) {
       // offsets: node weights of every gene, then the intercept-only fits on the nodes (warp per gene); the per-cell kernel
@@ -527,7 +559,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.launches[SCLANE_STAGE_SELECT] += 2;
     A.order = d_order;
     CA.order = d_order;
-    if (use_comp && !use_offset) {
+    if (use_comp && !use_offset && !exact) {
       tm.mark(SCLANE_STAGE_COMP_FINAL);
       if (use_wg) {
         WA.C = CA; WA.counter = d_counters + 2;
@@ -541,7 +573,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     if (use_offq) {
       // alternatives with hinges: hybrid per-cell passes (mu-free terms from the histogram); genes without a histogram
       // (route 0) are left to the plain per-cell launch below, which skips everything already done
-      A.cg = d_cg; A.tail = d_tail; A.big = d_big;
+      A.cg = d_cg; A.tail = d_tail; A.big = d_big; A.exact = exact ? 1 : 0; A.pstart = D.pstart;
       launch_stage<STAGE_FINAL, true>(A, s);
       prof.launches[SCLANE_STAGE_FINAL]++;
     }
@@ -557,13 +589,23 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     if (h_counts && kb + 1 < n_batches) issue_h2d(kb + 1);
     CK(cudaStreamSynchronize(s));
     tm.collect(prof);
-    for (int i = 0; i < nb; ++i) {
-      GeneOut go;
-      go.st = h_out[i].st; go.alt = h_out[i].alt; go.null = h_out[i].null;
-      sclane_record& r = out[((b0 - out_g0) + i) * n_lineages + lin_idx];
-      finalize_record(go, L, r, o.basis_only != 0);
-      // sweeps actually run for this gene: one per forward iteration it entered
-      const int sw = go.st.fwd_iters;
+    // records: z / p-values, LRT, pchisq per gene (~1-2 us each) -- spread over host threads, chunk sums in chunk order
+    {
+      long long sw_chunk[kPlanChunks] = {0};
+      const bool basis_only = o.basis_only != 0;
+      parallel_chunks((size_t)nb, [&](int c, size_t i0, size_t i1) {
+        long long sw = 0;
+        for (size_t i = i0; i < i1; ++i) {
+          GeneOut go;
+          go.st = h_out[i].st; go.alt = h_out[i].alt; go.null = h_out[i].null;
+          sclane_record& r = out[((b0 - out_g0) + (int64_t)i) * n_lineages + lin_idx];
+          finalize_record(go, L, r, basis_only);
+          sw += go.st.fwd_iters;                       // sweeps actually run for this gene: one per forward iteration it entered
+        }
+        sw_chunk[c] = sw;
+      }, 1024);
+      long long sw = 0;
+      for (int c = 0; c < kPlanChunks; ++c) sw += sw_chunk[c];
       prof.sweep_gene_iters += sw;
       prof.sweep_bytes += 12.0 * (double)L.N * (double)sw;
     }
@@ -701,7 +743,7 @@ int check_opts(const sclane_opts* o, char* errbuf, size_t errlen) {
   if (o->mode != 0 && o->mode != 1) { set_err(errbuf, errlen, "mode %d is not built; 0 = GLM, 1 = GEE", o->mode); return SCLANE_ERR_UNSUPPORTED; }
   if (o->M < 3 || o->M > SCLANE_PMAX) { set_err(errbuf, errlen, "M must be in [3, %d]", SCLANE_PMAX); return SCLANE_ERR_ARG; }
   if (o->h2d_mode < 0 || o->h2d_mode > 2) { set_err(errbuf, errlen, "h2d_mode must be 0, 1 or 2"); return SCLANE_ERR_ARG; }
-  if (!o->approx_knot) { set_err(errbuf, errlen, "approx_knot = 0 is not supported yet"); return SCLANE_ERR_UNSUPPORTED; }
+  if (!o->approx_knot && o->mode != 0) { set_err(errbuf, errlen, "approx_knot = 0 is built for GLM mode only"); return SCLANE_ERR_UNSUPPORTED; }
   if (o->n_knot_max < 1 || o->n_knot_max > SCLANE_TMAX) { set_err(errbuf, errlen, "n_knot_max must be in [1, %d]", SCLANE_TMAX); return SCLANE_ERR_ARG; }
   return SCLANE_OK;
 }
@@ -825,7 +867,9 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
   }
   // every lineage's plan is built on a background thread, all started now: lineage 0's overlaps the first H2D, the others
   // are ready long before their turn
-  std::vector<LineagePlan> plans((size_t)n_lineages);
+  // plan objects are pooled across calls (calls are serialised by the library lock): their vectors keep their capacity
+  static std::vector<LineagePlan> plans;
+  if (plans.size() < (size_t)n_lineages) plans.resize((size_t)n_lineages);
   std::vector<std::shared_future<bool>> plans_ready((size_t)n_lineages);
   for (int l = 0; l < n_lineages; ++l) {
     LineagePlan* Pl = &plans[(size_t)l];
@@ -885,6 +929,10 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
       std::memset(&li, 0, sizeof(li));
       li.n_cells = P.L.N; li.n_knots = P.L.T; li.minspan = P.minspan;
       for (int k = 0; k < P.L.T; ++k) li.knots[k] = P.L.knots[k];
+      if (P.exact) {          // approx.knot = FALSE: n_knots = number of candidate abscissae, knots[] = the first SCLANE_TMAX of them
+        li.n_knots = (int32_t)P.cand.size();
+        for (size_t k = 0; k < P.cand.size() && k < (size_t)SCLANE_TMAX; ++k) li.knots[k] = P.px[(size_t)P.cand[k]];
+      }
       li.pt_min = P.pt_min; li.pt_max = P.pt_max;
     }
     for (int di = 0; di < nd; ++di) {
@@ -1281,7 +1329,7 @@ int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_
     CK(cudaMemcpyAsync(d_out, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = nullptr; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
-    A.scores = nullptr; A.mom = nullptr; A.n_genes = nb; A.M = 5; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr;
+    A.scores = nullptr; A.mom = nullptr; A.n_genes = nb; A.M = 5; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr; A.exact = 0; A.pstart = nullptr;
     launch_stage<STAGE_FWD_FIT>(A, s);
     CK(cudaMemcpyAsync(h.data(), d_out, (size_t)nb * sizeof(GeneOutDev), cudaMemcpyDeviceToHost, s));
     std::vector<double> hmu;
@@ -1338,7 +1386,7 @@ int32_t sclane_score_glm(const int32_t* counts, const double* mu, int64_t n_cell
     CK(cudaMemcpyAsync(d_out, h.data(), (size_t)nb * sizeof(GeneOutDev), cudaMemcpyHostToDevice, s));
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = nullptr; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
-    A.scores = d_scores; A.mom = d_mom; A.n_genes = nb; A.M = 99; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr;
+    A.scores = d_scores; A.mom = d_mom; A.n_genes = nb; A.M = 99; A.tols_score = 1e-5; A.use_offset = 0; A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr; A.exact = 0; A.pstart = nullptr;
     launch_sweep(A, true, s, nullptr, nullptr);
     std::vector<double> hs((size_t)nb * 2 * L.T);
     CK(cudaMemcpyAsync(hs.data(), d_scores, hs.size() * 8, cudaMemcpyDeviceToHost, s));

@@ -40,6 +40,8 @@ struct CompArgs {
   int compute_stats;
   double tols_score;
   const int* order;             // optional CTA -> gene map of the final stage (k_order_final), or nullptr
+  double* a0p;                  // optional [B][Dpad]: glm.fit start sums per point (sum w0, sum w0 z0) for the exact-knot kernels
+  double* b0p;
 };
 
 #ifndef SCLANE_COMP_WARPS
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
       }
       const double sd = (double)s, qd = (double)qq, u = A.pu[d];
       s1[d] = sd; q[d] = qd;
+      if (A.a0p) { A.a0p[(size_t)g * (size_t)A.Dpad + d] = a0; A.b0p[(size_t)g * (size_t)A.Dpad + d] = b0; }
       b = A.pb[d];
       v[0] = sd; v[1] = sd * u; v[2] = sd * u * u; v[3] = qd;
       v[4] = a0; v[5] = a0 * u; v[6] = a0 * u * u; v[7] = b0; v[8] = b0 * u;
@@ -289,6 +292,7 @@ struct CompDevExec {
   const int* __restrict__ big;
   double (*scw)[NSC];
   const FastTabs* ft;               // exp / log1p tables in shared memory (sclane_fastmath.cuh)
+  const double* __restrict__ px;    // exact-knot mode: abscissa per point, u = px[d] - ref[bucket] (the buckets are per gene); else nullptr
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -363,9 +367,16 @@ struct CompDevExec {
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
       const int p1 = pbstart[b + 1];
+      if (px) {
+        const double refb = L->ref[b];
 #pragma unroll kCompUnroll
-      for (int d = pbstart[b] + lane; d < p1; d += 32)
-        point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], a, c, sigma, theta, want_ll, ft, acc, sc);
+        for (int d = pbstart[b] + lane; d < p1; d += 32)
+          point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, px[d] - refb, a, c, sigma, theta, want_ll, ft, acc, sc);
+      } else {
+#pragma unroll kCompUnroll
+        for (int d = pbstart[b] + lane; d < p1; d += 32)
+          point_contrib<MODE>(pn[d], s1[d], MODE == PASS_IRLS ? q[d] : 0.0, pu[d], a, c, sigma, theta, want_ll, ft, acc, sc);
+      }
 #pragma unroll
       for (int k = 0; k < NA; ++k) {
         const double t = warp_sum(acc[k]);
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(C
   __syncthreads();
   const long long t_start = clock64();
   CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, pbs, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
-                 A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, scw, &ftab};
+                 A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, scw, &ftab, nullptr};
   if (STAGE == CSTAGE_FORWARD) {
     for (int it = 0; it < A.n_iter; ++it) {
       gene_forward_fit(ex, Ls, gs, st, W);

@@ -751,63 +751,87 @@ SC_HD int which_max_round6(const double* vr, int n, bool last) {
   return idx;
 }
 
-// The selection tree of marge2.R:368-587 (q = 1).  one/both: additive score vectors; in_set: 0 for the
-// first iteration (interaction scores are the constant -1e5, :244), 1 afterwards (the "interaction with
-// the intercept" scores duplicate the additive ones, :247-307).  Returns false for the breakFlag exit;
-// else trunc_type (1|2) and knot index (may be -1 = R subscript error).
-SC_HDN bool select_candidate(const double* one, const double* both, const double* one_r, const double* both_r, int T, int in_set,
-                             int& trunc_type, int& kidx) {
-  double one_int_c[TMAX], both_int_c[TMAX];
-  for (int i = 0; i < T; ++i) { one_int_c[i] = -1e5; both_int_c[i] = -1e5; }     // rounds to itself
-  const double* one_int = in_set ? one : one_int_c;
-  const double* both_int = in_set ? both : both_int_c;
-  const double* one_int_r = in_set ? one_r : one_int_c;
-  const double* both_int_r = in_set ? both_r : both_int_c;
-  const bool bi_na = all_na(both_int, T), oi_na = all_na(one_int, T);
-  const bool ba_na = all_na(both, T), oa_na = all_na(one, T);
-  const double mx_bi = rmax_na(both_int, T), mx_oi = rmax_na(one_int, T);
-  const double mx_ba = rmax_na(both, T), mx_oa = rmax_na(one, T);
-#define SEL(tt, vec, last) do { trunc_type = (tt); kidx = which_max_round6((vec##_r), T, (last)); return true; } while (0)
+// The selection tree of marge2.R:368-587 (q = 1) on per-vector SUMMARIES: all the tree looks at is, per score vector, whether
+// it is all NA and its maximum (NA dropped); the winner's index is then the first or the last maximum of round(score, 6).
+// Vectors: additive one / both, and the "interaction" ones -- the constant -1e5 in the first iteration (:244), duplicates of the
+// additive ones afterwards (the "interaction with the intercept", :247-307).  Returns false for the breakFlag exit; else
+// trunc_type (1 | 2), the vector the index is taken from (SEL_*) and whether the LAST maximum is meant.
+struct VecSummary {
+  bool na;             // every entry NA
+  double mx;           // max over the non-NA entries
+  int first, last;     // first / last index of the maximum of round(score, 6); -1 when all NA
+};
+enum SelVec : int { SEL_ONE = 0, SEL_BOTH = 1, SEL_ONE_INT = 2, SEL_BOTH_INT = 3 };
+SC_HDN bool select_tree(const VecSummary& bi, const VecSummary& oi, const VecSummary& ba, const VecSummary& oa, int& trunc_type, int& vec,
+                        int& last) {
+  const bool bi_na = bi.na, oi_na = oi.na, ba_na = ba.na, oa_na = oa.na;
+  const double mx_bi = bi.mx, mx_oi = oi.mx, mx_ba = ba.mx, mx_oa = oa.mx;
+#define SEL(tt, v, l) do { trunc_type = (tt); vec = (v); last = (l) ? 1 : 0; return true; } while (0)
   if (bi_na && oi_na) {                                            // :368
-    if (!ba_na && !oa_na) { if (mx_ba > mx_oa) SEL(2, both, true); SEL(1, one, true); }
-    if (ba_na && !oa_na) SEL(1, one, false);
-    if (!ba_na && oa_na) SEL(2, one, false);                       // sic (:386): all-NA vector -> error
+    if (!ba_na && !oa_na) { if (mx_ba > mx_oa) SEL(2, SEL_BOTH, true); SEL(1, SEL_ONE, true); }
+    if (ba_na && !oa_na) SEL(1, SEL_ONE, false);
+    if (!ba_na && oa_na) SEL(2, SEL_ONE, false);                   // sic (:386): all-NA vector -> error
     return false;
   }
   if (bi_na && !oi_na) {                                           // :392
     if (ba_na) {
-      if (oa_na) SEL(1, one_int, true);
-      if (mx_oi > mx_oa) SEL(1, one_int, true);
-      SEL(1, one, false);
+      if (oa_na) SEL(1, SEL_ONE_INT, true);
+      if (mx_oi > mx_oa) SEL(1, SEL_ONE_INT, true);
+      SEL(1, SEL_ONE, false);
     }
-    if (mx_oi > mx_ba) { if (mx_oi > mx_oa) SEL(1, one_int, true); SEL(1, one, true); }
-    if (mx_ba <= mx_oa) SEL(1, one, false);
-    SEL(2, both, false);
+    if (mx_oi > mx_ba) { if (mx_oi > mx_oa) SEL(1, SEL_ONE_INT, true); SEL(1, SEL_ONE, true); }
+    if (mx_ba <= mx_oa) SEL(1, SEL_ONE, false);
+    SEL(2, SEL_BOTH, false);
   }
   if (!bi_na && oi_na) {                                           // :443
-    if (ba_na) { if (mx_bi > mx_oa) SEL(2, both_int, true); SEL(1, one, false); }
-    if (mx_bi > mx_ba) SEL(2, both_int, true);
-    if (mx_ba <= mx_oa) SEL(1, one, false);
-    SEL(2, both, false);
+    if (ba_na) { if (mx_bi > mx_oa) SEL(2, SEL_BOTH_INT, true); SEL(1, SEL_ONE, false); }
+    if (mx_bi > mx_ba) SEL(2, SEL_BOTH_INT, true);
+    if (mx_ba <= mx_oa) SEL(1, SEL_ONE, false);
+    SEL(2, SEL_BOTH, false);
   }
   if (mx_bi > mx_oi) {                                             // :494
     if (!ba_na) {
-      if (mx_ba >= mx_bi) { if (mx_ba > mx_oa) SEL(2, both, false); SEL(1, one, false); }
-      if (mx_bi > mx_oa) SEL(2, both_int, true);
-      SEL(1, one, false);
+      if (mx_ba >= mx_bi) { if (mx_ba > mx_oa) SEL(2, SEL_BOTH, false); SEL(1, SEL_ONE, false); }
+      if (mx_bi > mx_oa) SEL(2, SEL_BOTH_INT, true);
+      SEL(1, SEL_ONE, false);
     }
-    if (mx_oa >= mx_bi) SEL(1, one, false);
-    SEL(2, both_int, true);
+    if (mx_oa >= mx_bi) SEL(1, SEL_ONE, false);
+    SEL(2, SEL_BOTH_INT, true);
   }
   if (!ba_na) {                                                    // :538
-    if (mx_ba >= mx_oi) { if (mx_ba <= mx_oa) SEL(1, one, false); SEL(2, both, false); }
-    if (mx_oi > mx_oa) SEL(1, one_int, true);
-    SEL(1, one, false);
+    if (mx_ba >= mx_oi) { if (mx_ba <= mx_oa) SEL(1, SEL_ONE, false); SEL(2, SEL_BOTH, false); }
+    if (mx_oi > mx_oa) SEL(1, SEL_ONE_INT, true);
+    SEL(1, SEL_ONE, false);
   }
-  if (oa_na) SEL(1, one_int, true);
-  if (mx_oa >= mx_oi) SEL(1, one, false);
-  SEL(1, one_int, true);
+  if (oa_na) SEL(1, SEL_ONE_INT, true);
+  if (mx_oa >= mx_oi) SEL(1, SEL_ONE, false);
+  SEL(1, SEL_ONE_INT, true);
 #undef SEL
+}
+
+SC_HD VecSummary summarize_scores(const double* v, const double* vr, int n) {
+  VecSummary s;
+  s.na = all_na(v, n);
+  s.mx = rmax_na(v, n);
+  s.first = which_max_round6(vr, n, false);
+  s.last = which_max_round6(vr, n, true);
+  return s;
+}
+
+// The same on explicit score vectors (T <= TMAX candidate knots): one/both = additive scores, *_r = round(score, 6); in_set: 0 for
+// the first iteration, 1 afterwards.  kidx may come back as -1 (R subscript error).
+SC_HDN bool select_candidate(const double* one, const double* both, const double* one_r, const double* both_r, int T, int in_set,
+                             int& trunc_type, int& kidx) {
+  const VecSummary oa = summarize_scores(one, one_r, T), ba = summarize_scores(both, both_r, T);
+  VecSummary ci;                                                   // the constant -1e5 vector (rounds to itself)
+  ci.na = false; ci.mx = -1e5; ci.first = 0; ci.last = T - 1;
+  const VecSummary& oi = in_set ? oa : ci;
+  const VecSummary& bi = in_set ? ba : ci;
+  int vec = 0, last = 0;
+  if (!select_tree(bi, oi, ba, oa, trunc_type, vec, last)) return false;
+  const VecSummary& sv = vec == SEL_ONE ? oa : (vec == SEL_BOTH ? ba : (vec == SEL_ONE_INT ? oi : bi));
+  kidx = last ? sv.last : sv.first;
+  return true;
 }
 
 // stat_out() (stat_out.R:23-47) for a candidate basis from the unweighted moments.  The Gram B'B and B'y are
@@ -869,6 +893,10 @@ struct GeneState {
   double wic[PMAX];
   int n_wic;
   long long cycles[3];  // profiling: clock64 ticks spent in the forward / backward / final kernels
+  // approx.knot = FALSE: the gene's own knot table (the knots its forward pass selected, ascending); Model.knot indexes it
+  int ex_T;
+  int ex_pidx[PMAX];    // point index (abscissa) of each knot
+  double ex_knots[PMAX];
   int done;             // bit 0: backward pass done, bit 1: final fits done (set by the X-compressed kernels; the per-cell
                         // kernels skip genes that already went through a stage)
 };

@@ -65,6 +65,8 @@ struct DevExecT {
   const int* __restrict__ big;
   const double* wtab;               // [64] glm.fit start weights by count (shared memory)
   const double* wztab;
+  const double* uoff;               // exact-knot mode: u[] is relative to the lineage's smallest abscissa and the buckets are the gene's
+                                    // own, so the bucket-local coordinate is u[i] - uoff[bucket]; nullptr otherwise
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -182,6 +184,7 @@ struct DevExecT {
       while (cur_b < T && Lr.bstart[cur_b + 1] <= first) ++cur_b;
       int b_hi = Lr.bstart[cur_b + 1];
       double a = W->a[cur_b], c = W->c[cur_b];
+      double uo = uoff ? uoff[cur_b] : 0.0;
       // constant linear predictor inside the bucket (no slope term, no offset): hoist exp / log1p / reciprocals
       constexpr bool kCanFlat = (MODE == PASS_FIT || MODE == PASS_IRLS || MODE == PASS_THETA || MODE == PASS_EMIT);
       bool flat = !HYB && kCanFlat && !use_off && c == 0.0;
@@ -195,7 +198,7 @@ struct DevExecT {
         if (g + 1 < g1 && (g << 5) + 64 <= b_hi) {
           // two groups inside the running bucket (b_hi <= N: every lane valid): two independent cells per lane
           const int y0 = __ldg(y + i), y1 = __ldg(y + i + 32);
-          const double u0 = __ldg(u + i), u1 = __ldg(u + i + 32);
+          const double u0 = __ldg(u + i) - uo, u1 = __ldg(u + i + 32) - uo;
           const double o0 = use_off ? __ldg(off + i) : 0.0, o1 = use_off ? __ldg(off + i + 32) : 0.0;
           double m0, m1;
           cell<MODE>(y0, u0, o0, a, c, sigma, theta, want_ll, acc, sc, m0);
@@ -208,7 +211,7 @@ struct DevExecT {
         if ((g << 5) + 32 <= b_hi) {
           // the whole group lies inside the running bucket (b_hi <= N, so every lane is valid)
           const int yi = __ldg(y + i);
-          const double ui = __ldg(u + i);
+          const double ui = __ldg(u + i) - uo;
           double mo;
           if (flat) {
             if (!HYB) cell_contrib_flat<MODE>(yi, ui, fb, sigma, theta, *tb, want_ll, acc, sc, mo);
@@ -223,10 +226,11 @@ struct DevExecT {
         // the group straddles a bucket boundary and/or the end of the gene (<= T + 1 times per pass)
         const bool valid = i < N;
         const int yi = __ldg(y + i);                   // rows are padded: always in bounds
-        const double ui = __ldg(u + i);
+        double ui = __ldg(u + i);
         const double oi = use_off ? __ldg(off + i) : 0.0;
         int b = cur_b;                                 // this lane's bucket (cells are sorted: b >= cur_b)
         while (valid && b < T && i >= Lr.bstart[b + 1]) ++b;
+        if (uoff) ui -= uoff[b];
         double ct[NACC], mo = 0.0;
 #pragma unroll
         for (int k = 0; k < NACC; ++k) ct[k] = 0.0;
@@ -250,6 +254,7 @@ struct DevExecT {
         cur_b = b_last;
         b_hi = Lr.bstart[cur_b + 1];
         a = W->a[cur_b]; c = W->c[cur_b];
+        uo = uoff ? uoff[cur_b] : 0.0;
         flat = !HYB && kCanFlat && !use_off && c == 0.0;
         if (flat) fb = make_flat_bucket(a, sigma);
         g += 1;
@@ -317,6 +322,8 @@ struct StageArgs {
   const CompGeneDev* cg;       // [B]
   const int* tail;             // [B][kHistCap]
   const int* big;              // [B][kBigCap]
+  int exact;                   // approx.knot = FALSE: the buckets are the gene's own (GeneState.ex_*); needs pstart
+  const int* pstart;           // [D + 1] first sorted cell of every abscissa
   const int* order;            // optional CTA -> gene map of the final stage (k_order_final: expensive genes first), or nullptr
 };
 
@@ -334,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   __shared__ FastTabs ftab;
   __shared__ TermTabs ttab;
   __shared__ double wtab[HYB ? 64 : 1], wztab[HYB ? 64 : 1];
+  __shared__ double uoff_s[NBMAX + 1];
   if ((int)blockIdx.x >= A.n_genes) return;
   const int g = ((STAGE == STAGE_FINAL || STAGE == STAGE_BACKWARD) && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
   if (HYB && A.cg[g].hdr.route == 0) return;          // block-uniform: this gene has no histogram (plain per-cell kernel fits it)
@@ -354,7 +362,22 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
     fast_tabs_load(&ftab, threadIdx.x, kThreads);
   }
   __syncthreads();
-  if (threadIdx.x == 0) work_attach_tabs(W, &ttab);
+  if (threadIdx.x == 0) {
+    work_attach_tabs(W, &ttab);
+    if (A.exact) {
+      // the gene's own buckets from the knots its forward pass selected (sclane_exact_device.cuh); u[] is relative to x0
+      const double x0 = Ls.ref[0];
+      const int T = st.ex_T;
+      Ls.T = T;
+      for (int k = 0; k < T; ++k) Ls.knots[k] = st.ex_knots[k];
+      Ls.ref[0] = T > 0 ? Ls.knots[0] : x0;
+      for (int b = 1; b <= T; ++b) Ls.ref[b] = Ls.knots[b - 1];
+      Ls.bstart[0] = 0;
+      for (int b = 1; b <= T; ++b) Ls.bstart[b] = A.pstart[st.ex_pidx[b - 1]];
+      for (int b = T + 1; b <= NBMAX; ++b) Ls.bstart[b] = Ls.N;
+      for (int b = 0; b <= T; ++b) uoff_s[b] = Ls.ref[b] - x0;
+    }
+  }
   __syncthreads();
   if (STAGE == STAGE_BACKWARD && (st.done & 1)) return;      // block-uniform: already handled by k_comp_stage
   if (STAGE == STAGE_FINAL && (st.done & 2)) return;
@@ -362,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   const long long t_start = clock64();
   DevExecT<HYB> ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs, &ftab,
                    HYB ? A.cg + g : nullptr, &gs, HYB ? A.tail + (size_t)g * (size_t)kHistCap : nullptr, HYB ? A.big + (size_t)g * (size_t)kBigCap : nullptr,
-                   wtab, wztab};
+                   wtab, wztab, A.exact ? uoff_s : nullptr};
   if (STAGE == STAGE_FWD_FIT) {
     gene_forward_fit(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_BACKWARD) {

@@ -8,14 +8,38 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <future>
 #include <limits>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sclane_comp.cuh"
 
 namespace sclane {
+
+// ---- host parallelism for the per-lineage plan (K0) ---------------------------------------------------
+// fn(chunk, begin, end) over kPlanChunks FIXED chunks of [0, n): any per-chunk partial result is combined in chunk order
+// afterwards, so every plan is bit-identical whatever the number of host threads (<= kPlanChunks) that ran it.
+constexpr int kPlanChunks = 16;
+template <class F>
+inline void parallel_chunks(size_t n, F fn, size_t min_parallel = 32768) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)(hw == 0 ? 4 : (hw > (unsigned)kPlanChunks ? (unsigned)kPlanChunks : hw));
+  if (n < min_parallel) nt = 1;
+  auto run = [&](int t) {
+    for (int c = t; c < kPlanChunks; c += nt) fn(c, n * (size_t)c / kPlanChunks, n * (size_t)(c + 1) / kPlanChunks);
+  };
+  if (nt == 1) { run(0); return; }
+  std::vector<std::thread> th;
+  th.reserve((size_t)nt);
+  try {
+    for (int t = 1; t < nt; ++t) th.emplace_back(run, t);
+  } catch (...) { for (auto& x : th) x.join(); throw; }
+  run(0);
+  for (auto& x : th) x.join();
+}
 
 // ---- R scalar semantics ------------------------------------------------------------------------
 inline double r_round_digits(double x, int digits) { return r_round(x, std::pow(10.0, digits)); }
@@ -41,6 +65,29 @@ inline double quantile7(std::vector<double> xs, double p) {
     if (index > (double)lo && xhi != q) q = (1.0 - h) * q + h * xhi;
   }
   return q;
+}
+
+// two quantiles (p_lo < p_hi) from ONE working copy: the second selection only looks at the part right of the first
+inline void quantile7_pair(const std::vector<double>& x, double p_lo, double p_hi, double& q_lo, double& q_hi, std::vector<double>* ws = nullptr) {
+  std::vector<double> local;
+  std::vector<double>& xs = ws ? *ws : local;
+  xs.assign(x.begin(), x.end());
+  const size_t n = xs.size();
+  auto one = [&](double p, size_t from) -> double {
+    const double index = 1.0 + (double)(n > 0 ? n - 1 : 0) * p;
+    const size_t lo = (size_t)std::floor(index), hi = (size_t)std::ceil(index);
+    std::nth_element(xs.begin() + from, xs.begin() + (lo - 1), xs.end());
+    double q = xs[lo - 1];
+    const double h = index - (double)lo;
+    if (hi > lo) {
+      const double xhi = *std::min_element(xs.begin() + lo, xs.end());
+      if (index > (double)lo && xhi != q) q = (1.0 - h) * q + h * xhi;
+    }
+    return q;
+  };
+  q_lo = one(p_lo, 0);
+  const size_t lo_pos = (size_t)std::floor(1.0 + (double)(n > 0 ? n - 1 : 0) * p_lo) - 1;   // everything left of it is <= q_lo
+  q_hi = one(p_hi, lo_pos);
 }
 
 // min_span.R:15-36 on an ASCENDING copy of round(x, 4)
@@ -92,15 +139,19 @@ inline std::vector<double> max_span(const std::vector<double>& X, int q) {
 }
 
 // marge2.R:152-166 given xs = ASCENDING round(x, 4): returns the candidate knots (ascending)
-inline std::vector<double> candidate_knots_sorted(const std::vector<double>& x_pred, std::vector<double> xs, bool approx_knot,
-                                                  int n_knot_max, int minspan_in, int* minspan_out) {
+// xs is consumed (reduced to its unique values in place)
+inline std::vector<double> candidate_knots_sorted(const std::vector<double>& x_pred, std::vector<double>& xs, bool approx_knot,
+                                                  int n_knot_max, int minspan_in, int* minspan_out,
+                                                  std::future<std::pair<double, double>>* quantiles = nullptr) {
   std::vector<double> r1 = min_span_sorted(xs, 1, minspan_in, minspan_out);
   xs.erase(std::unique(xs.begin(), xs.end()), xs.end());
   std::vector<double> r2 = max_span_sorted_unique(xs, 1);
   std::vector<double> red;
   for (double v : r1) if (std::binary_search(r2.begin(), r2.end(), v)) red.push_back(v);
   if (approx_knot) {
-    const double q05 = quantile7(x_pred, 0.05), q95 = quantile7(x_pred, 0.95);
+    double q05, q95;
+    if (quantiles) { const std::pair<double, double> qq = quantiles->get(); q05 = qq.first; q95 = qq.second; }     // computed concurrently by the caller
+    else quantile7_pair(x_pred, 0.05, 0.95, q05, q95);
     std::vector<double> f;
     for (double v : red) if (v > q05 && v < q95) f.push_back(v);
     red.swap(f);
@@ -123,7 +174,7 @@ inline std::vector<double> candidate_knots(const std::vector<double>& x_pred, bo
   for (size_t i = 0; i < X.size(); ++i) X[i] = r_round(x_pred[i], 1e4);
   std::vector<double> xs(X);
   std::sort(xs.begin(), xs.end());
-  std::vector<double> red = candidate_knots_sorted(x_pred, std::move(xs), approx_knot, n_knot_max, minspan_in, minspan_out);
+  std::vector<double> red = candidate_knots_sorted(x_pred, xs, approx_knot, n_knot_max, minspan_in, minspan_out);
   if (X_out) X_out->swap(X);
   return red;
 }
@@ -131,26 +182,31 @@ inline std::vector<double> candidate_knots(const std::vector<double>& x_pred, bo
 // Stable order of the cells by X = round(x, 4).  X is a multiple of 1e-4, so llround(1e4 X) is an order-preserving integer
 // key and a counting sort does it in O(N) when the key range is small (pseudotime in [0, 1]: 10,001 keys); otherwise a
 // comparison sort of (X, index) pairs -- both give exactly the order of a stable sort by X.
-inline std::vector<int32_t> stable_order_by_x(const std::vector<double>& X) {
+inline void stable_order_by_x(const std::vector<double>& X, std::vector<int32_t>& order, std::vector<int32_t>& start, std::vector<int32_t>& key) {
   const size_t N = X.size();
-  std::vector<int32_t> order(N);
+  order.resize(N);
   double lo = X[0], hi = X[0];
   for (double v : X) { if (v < lo) lo = v; if (v > hi) hi = v; }
   const double span = (hi - lo) * 1e4;
   if (std::isfinite(span) && span <= 4.0 * (double)N + 1024.0 && std::fabs(lo) < 1e8 && std::fabs(hi) < 1e8) {
     const long long k0 = std::llround(lo * 1e4);
     const size_t R = (size_t)(std::llround(hi * 1e4) - k0) + 1;
-    std::vector<int32_t> start(R + 1, 0);
-    std::vector<int32_t> key(N);
-    for (size_t i = 0; i < N; ++i) { key[i] = (int32_t)(std::llround(X[i] * 1e4) - k0); start[(size_t)key[i] + 1]++; }
+    start.assign(R + 1, 0);
+    key.resize(N);
+    parallel_chunks(N, [&](int, size_t a, size_t b) { for (size_t i = a; i < b; ++i) key[i] = (int32_t)(std::llround(X[i] * 1e4) - k0); });
+    for (size_t i = 0; i < N; ++i) start[(size_t)key[i] + 1]++;
     for (size_t k = 0; k < R; ++k) start[k + 1] += start[k];
     for (size_t i = 0; i < N; ++i) order[(size_t)start[(size_t)key[i]]++] = (int32_t)i;
-    return order;
+    return;
   }
   std::vector<std::pair<double, int32_t>> keyed(N);
   for (size_t i = 0; i < N; ++i) keyed[i] = {X[i], (int32_t)i};
   std::sort(keyed.begin(), keyed.end());
   for (size_t i = 0; i < N; ++i) order[i] = keyed[i].second;
+}
+inline std::vector<int32_t> stable_order_by_x(const std::vector<double>& X) {
+  std::vector<int32_t> order, start, key;
+  stable_order_by_x(X, order, start, key);
   return order;
 }
 
@@ -177,6 +233,15 @@ struct LineagePlan {
   std::vector<double> oxi;        // [Npad] position of o_i inside its bin, in [-1, 1] (sorted-cell order)
   std::vector<uint8_t> obin;      // [Npad] bin of o_i
   std::vector<int32_t> oord;      // [N] sorted-cell positions ordered by (bin, position)
+  // approx.knot = FALSE (marge2.R:167-173): every candidate knot is a data abscissa; the lineage carries ONE bucket (T = 0)
+  // and every gene builds its own buckets from the knots it selects (sclane_exact_device.cuh)
+  // scratch of build_lineage_plan(), kept with the plan so that a reused plan object (the library keeps a pool across calls) does
+  // not re-allocate: at 200,000 cells the ~15 fresh 1.6 MB vectors cost more in page faults than the arithmetic
+  std::vector<int32_t> ws_cells, ws_order, ws_start, ws_key;
+  std::vector<double> ws_x, ws_X, ws_xs, ws_q;
+  bool exact = false;
+  std::vector<double> px;         // [D] abscissa (rounded pseudotime) of point d
+  std::vector<int32_t> cand;      // [n_cand] point index of the candidate knots, ascending
 };
 
 // distinct abscissae of the sorted cells (a point never straddles a bucket: buckets are defined by the abscissa)
@@ -256,55 +321,96 @@ inline void build_offset_nodes(LineagePlan& P) {
 // pt_col: n_cells doubles with NaN = not in lineage.  size_factor may be null.
 inline bool build_lineage_plan(const double* pt_col, int64_t n_cells, const double* size_factor,
                                const sclane_opts& o, LineagePlan& P) {
-  std::vector<int32_t> cells;
-  std::vector<double> x;
+  std::vector<int32_t>& cells = P.ws_cells;
+  std::vector<double>& x = P.ws_x;
+  cells.clear(); x.clear();
+  cells.reserve((size_t)n_cells); x.reserve((size_t)n_cells);
+  P.error.clear();
   for (int64_t i = 0; i < n_cells; ++i)
     if (!std::isnan(pt_col[i])) { cells.push_back((int32_t)i); x.push_back(pt_col[i]); }
   const size_t N = x.size();
   if (N < 30) { P.error = "lineage has fewer than 30 cells"; return false; }
-  std::vector<double> X(N);
+  // the 5 % / 95 % quantiles of the UNROUNDED pseudotime (marge2.R:158-159) only need x: selected on another thread while
+  // this one rounds and sorts
+  std::future<std::pair<double, double>> qfut;
+  if (o.approx_knot != 0)
+    qfut = std::async(N >= 32768 ? std::launch::async : std::launch::deferred,
+                      [&x, &P]() { double a, b; quantile7_pair(x, 0.05, 0.95, a, b, &P.ws_q); return std::make_pair(a, b); });
+  std::vector<double>& X = P.ws_X;
+  X.resize(N);
   for (size_t i = 0; i < N; ++i) X[i] = r_round(x[i], 1e4);
-  std::vector<int32_t> order = stable_order_by_x(X);
-  std::vector<double> xs_sorted(N);
-  for (size_t i = 0; i < N; ++i) xs_sorted[i] = X[(size_t)order[i]];
-  std::vector<double> knots = candidate_knots_sorted(x, std::move(xs_sorted), o.approx_knot != 0, o.n_knot_max, o.minspan, &P.minspan);
+  std::vector<int32_t>& order = P.ws_order;
+  stable_order_by_x(X, order, P.ws_start, P.ws_key);
+  P.Xs.resize(N);
+  for (size_t i = 0; i < N; ++i) P.Xs[i] = X[(size_t)order[i]];
+  P.ws_xs.assign(P.Xs.begin(), P.Xs.end());
+  std::vector<double> knots = candidate_knots_sorted(x, P.ws_xs, o.approx_knot != 0, o.n_knot_max, o.minspan, &P.minspan,
+                                                     qfut.valid() ? &qfut : nullptr);
   if (knots.empty()) { P.error = "no candidate knots (pseudotime has too few distinct values)"; return false; }
-  if ((int)knots.size() > TMAX) { P.error = "more than SCLANE_TMAX candidate knots (approx.knot = FALSE is not supported yet)"; return false; }
   std::sort(knots.begin(), knots.end());
+  P.exact = o.approx_knot == 0;
+  std::vector<double> cand_values;
+  if (P.exact) { cand_values.swap(knots); knots.clear(); }        // the lineage itself has no knot: one bucket
+  if ((int)knots.size() > TMAX) { P.error = "more than SCLANE_TMAX candidate knots"; return false; }
   Lineage& L = P.L;
   std::memset(&L, 0, sizeof(L));
   L.N = (int)N;
   L.Npad = (int)((N + 127) / 128 * 128);
   L.T = (int)knots.size();
   for (int k = 0; k < L.T; ++k) L.knots[k] = knots[(size_t)k];
-  L.ref[0] = L.knots[0];
+  L.ref[0] = L.T > 0 ? L.knots[0] : P.Xs[0];                      // exact mode: reference = smallest abscissa
   for (int b = 1; b <= L.T; ++b) L.ref[b] = L.knots[b - 1];
-  // stable sort by rounded pseudotime
+  // the cells are sorted by X, so bucket b = #{k: t_k <= x} is the contiguous range starting at the first cell with X >= t_{b-1}
+  L.bstart[0] = 0;
+  for (int b = 1; b <= L.T; ++b) L.bstart[b] = (int)(std::lower_bound(P.Xs.begin(), P.Xs.end(), knots[(size_t)b - 1]) - P.Xs.begin());
+  for (int b = L.T + 1; b <= NBMAX; ++b) L.bstart[b] = (int)N;
   P.perm.resize(N);
-  P.Xs.resize(N);
   P.bucket.resize(N);
   P.u.assign((size_t)L.Npad, 0.0);
   if (size_factor) P.off.assign((size_t)L.Npad, 0.0); else P.off.clear();
-  for (int b = 0; b <= L.T + 1; ++b) L.bstart[b] = 0;
-  std::vector<int> cnt((size_t)L.T + 1, 0);
-  for (size_t i = 0; i < N; ++i) {
-    const int32_t src = order[i];
-    const double xv = X[(size_t)src];
-    P.perm[i] = cells[(size_t)src];
-    P.Xs[i] = xv;
-    const int b = (int)(std::upper_bound(knots.begin(), knots.end(), xv) - knots.begin());   // #{k: t_k <= x}
-    P.bucket[i] = b;
-    cnt[(size_t)b]++;
-    const double u = xv - L.ref[b];
-    P.u[i] = u;
-    L.U0[b] += 1.0; L.U1[b] += u; L.U2[b] += u * u;
-    if (size_factor) P.off[i] = std::log(1.0 / size_factor[cells[(size_t)src]]);
+  parallel_chunks(N, [&](int, size_t a, size_t b2) {
+    int b = (int)(std::upper_bound(L.bstart, L.bstart + L.T + 1, (int)a) - L.bstart) - 1;
+    for (size_t i = a; i < b2; ++i) {
+      while (b < L.T && (int)i >= L.bstart[b + 1]) ++b;
+      const int32_t src = order[i];
+      P.perm[i] = cells[(size_t)src];
+      P.bucket[i] = b;
+      P.u[i] = P.Xs[i] - L.ref[b];
+      if (size_factor) P.off[i] = std::log(1.0 / size_factor[cells[(size_t)src]]);
+    }
+  });
+  // unweighted bucket moments: one bucket per task, summed in cell order (bit-identical to a serial pass)
+  {
+    const int nb = L.T + 1;
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)(hw == 0 ? 4 : (hw > 8 ? 8 : hw));
+    if (N < 32768) nt = 1;
+    auto run = [&](int t) {
+      for (int b = t; b < nb; b += nt) {
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+        for (int i = L.bstart[b]; i < L.bstart[b + 1]; ++i) { const double u = P.u[(size_t)i]; u0 += 1.0; u1 += u; u2 += u * u; }
+        L.U0[b] = u0; L.U1[b] = u1; L.U2[b] = u2;
+      }
+    };
+    if (nt == 1) run(0);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 1; t < nt; ++t) th.emplace_back(run, t);
+      run(0);
+      for (auto& x2 : th) x2.join();
+    }
   }
-  int acc = 0;
-  for (int b = 0; b <= L.T; ++b) { L.bstart[b] = acc; acc += cnt[(size_t)b]; }
-  L.bstart[L.T + 1] = acc;
-  for (int b = L.T + 2; b <= NBMAX; ++b) L.bstart[b] = acc;
   build_points(P);
+  if (P.exact) {
+    P.px.resize((size_t)P.D);
+    for (int d = 0; d < P.D; ++d) P.px[(size_t)d] = P.Xs[(size_t)P.pstart[(size_t)d]];
+    P.cand.clear();
+    for (double v : cand_values) {
+      const auto it = std::lower_bound(P.px.begin(), P.px.end(), v);
+      if (it != P.px.end() && *it == v) P.cand.push_back((int32_t)(it - P.px.begin()));      // candidates are data values
+    }
+    if (P.cand.empty()) { P.error = "no candidate knots (pseudotime has too few distinct values)"; return false; }
+  }
   build_offset_nodes(P);
   P.pt_min = *std::min_element(x.begin(), x.end());
   P.pt_max = *std::max_element(x.begin(), x.end());
@@ -385,7 +491,7 @@ inline void finalize_record(const GeneOut& g, const Lineage& L, sclane_record& r
       r.term_kind[j] = st.fin.kind[j];
       r.term_knot_idx[j] = st.fin.kind[j] == SCLANE_TERM_INTERCEPT ? -1 : st.fin.knot[j];
       if (st.fin.kind[j] != SCLANE_TERM_INTERCEPT) {
-        r.term_knot[j] = L.knots[st.fin.knot[j]];
+        r.term_knot[j] = st.ex_T > 0 ? st.ex_knots[st.fin.knot[j]] : L.knots[st.fin.knot[j]];      // exact-knot mode: the gene's own knot table
         r.term_label[j] = r_signif(r.term_knot[j], 4);
       }
       if (basis_only) continue;

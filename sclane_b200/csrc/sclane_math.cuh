@@ -25,6 +25,13 @@ SC_HD double r_round(double x, double p10) {
   double x10 = p10 * v;
   if (x10 >= 4503599627370496.0) return x;  // 2^52: already an integer multiple
   double i10 = floor(x10);
+  {
+    // fast path: the scaled value is clearly on one side of the half-way point (the product p10 * v carries a relative error
+    // of 2^-53, far below the 1e-3 margin), so the nearer of the two decimal neighbours is known without comparing distances
+    const double fr = x10 - i10;
+    if (fr < 0.499 && x10 < 4.0e12) return s * (i10 / p10);
+    if (fr > 0.501 && x10 < 4.0e12) return s * ((i10 + 1.0) / p10);
+  }
   double xd = i10 / p10, xu = ceil(x10) / p10;
   double du = xu - v, dd = v - xd;
   bool even = fmod(i10, 2.0) == 0.0;

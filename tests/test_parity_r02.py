@@ -32,6 +32,23 @@ def oracle_parallel(counts, pt, genes, sf=None):
     return {g: out[g] for g in genes}
 
 
+def _oracle_chunk_opts(a):
+    from threadpoolctl import threadpool_limits
+    counts, pt, genes, sf, kw = a
+    with threadpool_limits(limits=1):
+        return oracle_test_dynamic(counts, pt, genes, sf, keep_preds=False, **kw)
+
+
+def oracle_parallel_opts(counts, pt, genes, sf=None, **kw):
+    cores = min(os.cpu_count() or 1, 16, len(genes))
+    chunks = [(counts[i::cores], pt, genes[i::cores], sf, kw) for i in range(cores)]
+    out = {}
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        for part in ex.map(_oracle_chunk_opts, chunks):
+            out.update(part)
+    return {g: out[g] for g in genes}
+
+
 def test_c2_shape_208_genes_vs_oracle():
     """BASELINE configs[1] shape (10,000 cells, M = 5, no offset), 208 genes of the bench generator: default (X-compressed) route
     against the dense oracle -- term sets, LRT, coefficients, SEs, log-likelihoods, deviances, theta."""
@@ -278,3 +295,30 @@ def test_in_library_multi_gpu_sharding_is_bit_identical():
         for o_, s_ in ((off, sz), (cyc, csz)):
             ba[o_:o_ + s_] = bb[o_:o_ + s_] = bytes(s_)
         assert ba == bb
+
+
+@pytest.mark.parametrize("n_cells,n_genes", [(3000, 56), (10000, 56)])
+def test_approx_knot_false_vs_oracle(n_cells, n_genes):
+    """approx.knot = FALSE (marge2.R:167-173): every abscissa kept by min_span() / max_span() is a candidate knot (hundreds to
+    thousands instead of 25).  The prefix-moment sweep (sclane_exact_device.cuh) against the dense oracle, which rebuilds the two
+    hinge columns per candidate like the reference does: term sets, knots, LRT, coefficients."""
+    import sclane_b200 as sb
+    from tools import synth
+    counts, pt, _ = synth.make_counts(n_genes, n_cells, seed=41)
+    genes = [f"g{i}" for i in range(n_genes)]
+    res = sb.testDynamic(counts, pt, genes=genes, approx_knot=False, n_gpus=1, preds="none")
+    assert res.lineage_info[0]["n_knots"] > 100
+    ref = oracle_parallel_opts(counts, pt.reshape(-1), genes, None, approx_knot=False)
+    worst = _compare_with_oracle(res, ref)
+    print(f"approx.knot = FALSE, {n_cells} cells, {res.lineage_info[0]['n_knots']} candidate knots: worst relative differences", worst)
+
+
+def test_approx_knot_false_with_offsets_vs_oracle():
+    """approx.knot = FALSE with createCellOffset() offsets: per-gene buckets in the hybrid per-cell final fits + offset quadrature."""
+    import sclane_b200 as sb
+    from tools import synth
+    counts, pt, _ = synth.make_counts(32, 4000, seed=43)
+    sf = sb.createCellOffset(counts)
+    genes = [f"g{i}" for i in range(32)]
+    res = sb.testDynamic(counts, pt, genes=genes, size_factor_offset=sf, approx_knot=False, n_gpus=1, preds="none")
+    _compare_with_oracle(res, oracle_parallel_opts(counts, pt.reshape(-1), genes, sf, approx_knot=False))
