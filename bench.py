@@ -308,6 +308,7 @@ def main():
     ap.add_argument("--per-cell", action="store_true", help="force the per-cell kernels for the whole run (profiling)")
     ap.add_argument("--warp-per-gene", action="store_true", help="X-compressed fits on the warp-per-gene kernels (A/B against the CTA-per-gene ones)")
     ap.add_argument("--offset-per-cell", action="store_true", help="intercept-only fits with an offset per cell (A/B against the offset quadrature)")
+    ap.add_argument("--approx-knot", type=int, default=1, help="0 = approx.knot = FALSE: every abscissa kept by min_span / max_span is a candidate knot")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.genes:
@@ -352,7 +353,8 @@ def main():
 
     def mk_opts(**kw):
         kw.setdefault("force_per_cell", args.per_cell)
-        o = sb.api._opts(gpu_ids=[local], comp_warp_per_gene=args.warp_per_gene, offset_per_cell=args.offset_per_cell, **kw)
+        o = sb.api._opts(gpu_ids=[local], comp_warp_per_gene=args.warp_per_gene, offset_per_cell=args.offset_per_cell,
+                         approx_knot=bool(args.approx_knot), **kw)
         if gee:
             o.mode = 1
             o.gee_cor = _abi.COR_CODES["ar1"]
@@ -447,7 +449,7 @@ def main():
 
     # ---- per-cell leg: the streaming score-sweep kernel, live -------------------------------------------
     sweep = None
-    if args.sweep_genes > 0 and not gee and rank == 0:
+    if args.sweep_genes > 0 and not gee and rank == 0 and args.approx_knot:
         Gs = min(G, args.sweep_genes)
         o_pc = mk_opts(force_per_cell=True)
         for _ in range(2):
@@ -506,7 +508,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["name"], "genes_total": G_total, "genes_per_gpu": G, "cells": N, "lineages": cfg["lineages"], "M": 5,
-                       "offsets": cfg["offsets"], "mode": cfg["kind"], "cells_per_lineage": int(n_lin_cells),
+                       "offsets": cfg["offsets"], "mode": cfg["kind"], "cells_per_lineage": int(n_lin_cells), "approx_knot": bool(args.approx_knot),
                        "sharding": f"contiguous gene blocks x{world}, no collective",
                        "timing": "value = wall clock around the library call with the counts resident in HBM (host plan, launches, D2H of the records, record "
                                  "finalisation included); max over ranks" + ("; the GEE entry takes host counts: value == the e2e path from pinned memory" if gee else ""),

@@ -16,6 +16,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from . import flavours
 from .eigen_helpers import eigen_map_mat_mult, eigen_map_matrix_invert
 from .knots import candidate_knots, tp1, tp2
 from .nbfit import NbMle, glm_nb, nb_mle, wald_nb
@@ -55,7 +56,11 @@ class NullStats:
 
 
 def stat_out_score_glm_null(Y: np.ndarray, B_null: np.ndarray, beta0=None) -> NullStats:
-    fit = nb_mle(B_null, Y, beta0)
+    if flavours.STATE["fitter"] == "emulate_gamlss":      # the reference's own fitter, emulated (oracle/flavours.py)
+        b, sg, mu_g, G, _ = flavours.gamlss_rs_nbi(B_null, Y)
+        fit = NbMle(beta=b, sigma=sg, mu=mu_g, loglik=-0.5 * G, poisson=False)
+    else:
+        fit = nb_mle(B_null, Y, beta0)
     sigma = fit.sigma
     mu = fit.mu
     V = mu * (1.0 + mu * sigma)
@@ -263,9 +268,21 @@ def forward_pass(Y, X, knots, M=5, tols_score=1e-5, trace: MargeTrace | None = N
         in_set = 1 if len(terms) > 1 else 0      # marge2.R:180 (q = 1: only "Intercept" differs from var_name)
         both_add = np.full(T, np.nan)
         one_add = np.full(T, np.nan)
+        colpiv = flavours.STATE["rank_rule"] == "colpiv_qr"      # the reference's numerical rank check, emulated
+
+        unchecked = flavours.STATE["rank_rule"] == "pair_unchecked"
+
+        def rank_def(XA, kinds, t):
+            if colpiv:
+                return flavours.rank_deficient_colpiv(B, XA)
+            if unchecked:                                        # only exactly duplicated columns are NA
+                return any((t2.kind, t2.knot_idx) == (kind, t) for t2 in terms for kind in kinds)
+            return _collinear(terms, kinds, t)
+
         for t in range(T):
-            both_add[t] = score_fun_glm(ns, np.stack([hinge1[t], hinge2[t]], 1), _collinear(terms, (TP1, TP2), t))
-            one_add[t] = score_fun_glm(ns, hinge1[t][:, None], _collinear(terms, (TP1,), t))
+            XA2 = np.stack([hinge1[t], hinge2[t]], 1)
+            both_add[t] = score_fun_glm(ns, XA2, rank_def(XA2, (TP1, TP2), t))
+            one_add[t] = score_fun_glm(ns, hinge1[t][:, None], rank_def(hinge1[t][:, None], (TP1,), t))
         if in_set == 0:
             both_int = np.full(T, -1e5)          # marge2.R:244
             one_int = np.full(T, -1e5)
@@ -285,7 +302,7 @@ def forward_pass(Y, X, knots, M=5, tols_score=1e-5, trace: MargeTrace | None = N
         # q = 1: an "interaction with the intercept" builds the same columns as the additive case
         new_terms = [Term(TP1, kidx), Term(TP2, kidx)] if trunc_type == 2 else [Term(TP1, kidx)]
         XA = build_design(new_terms, X, knots)
-        score2 = score_fun_glm(ns, XA, _collinear(terms, tuple(t.kind for t in new_terms), kidx))
+        score2 = score_fun_glm(ns, XA, rank_def(XA, tuple(t.kind for t in new_terms), kidx))
         B_temp = np.concatenate([B, XA], axis=1)
         so = stat_out(Y, B_temp, TSS, GCV_null, pen)
         if trace is not None:
@@ -315,6 +332,9 @@ def forward_pass(Y, X, knots, M=5, tols_score=1e-5, trace: MargeTrace | None = N
 
 def backward_sel_wic(Y, B):
     """backward_sel_WIC.R:44-52 (GLM branch)."""
+    if flavours.STATE["fitter"] == "emulate_gamlss":
+        wald, _ = flavours.gamlss_wald(B, Y)
+        return wald, None
     wald, fit = wald_nb(B, Y)
     return wald, fit
 

@@ -86,6 +86,7 @@ struct ExactShared {
   ScoreSummary sum1[kCompThreads], sum2[kCompThreads];
   int mk_pidx[PMAX];            // point index of the knot of every model term (-1: intercept)
   double Ainv[PMAX * PMAX];     // (B'WB)^-1 of the current model
+  double Ag[PMAX];              // (B'WB)^-1 B'r: the null fit's leftover score, projected out of the candidates' b
   int sel_trunc, sel_idx;       // selection broadcast
   double sel_score;
 };
@@ -95,8 +96,8 @@ struct ExactShared {
 __device__ void exact_rebuild(ExactShared& S, const ExactArgs& A, const Lineage* Lglob, const double* s1, const double* q, const double* a0p,
                               const double* b0p) {
   const CompArgs& C = A.C;
+  __syncthreads();                                     // the knot table may just have been updated by thread 0
   const int T = S.st.ex_T;
-  __syncthreads();
   if (threadIdx.x == 0) {
     Lineage& L = S.Lg;
     L.N = Lglob->N; L.Npad = Lglob->Npad; L.T = T;
@@ -171,7 +172,9 @@ __device__ __forceinline__ double exact_score(const ExactShared& S, const double
     }
     Cq[0][j] = c1; Cq[1][j] = c2;
   }
-  const double Dq[2] = {R[2], Lm[2]}, bq[2] = {R[4], Lm[4]};
+  const double Dq[2] = {R[2], Lm[2]};
+  double bq[2] = {R[4], Lm[4]};
+  for (int j = 0; j < np; ++j) { bq[0] -= Cq[0][j] * S.Ag[j]; bq[1] -= Cq[1][j] * S.Ag[j]; }
   double Sm[2][2] = {{0, 0}, {0, 0}};
   for (int a = 0; a < c; ++a)
     for (int b = 0; b <= a; ++b) {
@@ -207,10 +210,18 @@ __device__ void exact_sweep(ExactShared& S, CompDevExec& ex, const ExactArgs& A,
   coop_set_model(ex, S.Lg, st.fwd, W);
   coop_set_eta(ex, S.Lg, st.fwd, W, st.beta);
   ex.template pass<PASS_SWEEP>();
-  coop_system(ex, S.Lg, st.fwd, W, 0, -1, -1);
+  coop_system(ex, S.Lg, st.fwd, W, 0, 3, -1);            // B'WB and B'r
   if (threadIdx.x == 0) {
     W.flag = sweep_invert(st.fwd, W) ? 1 : 0;
     for (int j = 0; j < st.fwd.n; ++j) for (int l = 0; l < st.fwd.n; ++l) S.Ainv[j * PMAX + l] = W.cov[j * NSYS + l];
+    // B'r is zero at the exact MLE; what the Newton iteration left of it is projected out of every candidate's b below.  Among
+    // ~10^4 candidates some are collinear with the basis to 1e-8 (a knot a few cells away from an end of the lineage): their
+    // complement S is tiny and even a 1e-7 leak of B'r into b would dominate the score.
+    for (int j = 0; j < st.fwd.n; ++j) {
+      double v = 0.0;
+      for (int l = 0; l < st.fwd.n; ++l) v += W.cov[j * NSYS + l] * W.grad[l];
+      S.Ag[j] = v;                                       // A (B'r)
+    }
   }
   __syncthreads();
   if (!W.flag) {
