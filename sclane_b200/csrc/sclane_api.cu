@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <future>
@@ -21,6 +22,9 @@
 #include "sclane_gee_host.hpp"
 #include "sclane_host.hpp"
 
+namespace sclane {
+bool narrow_range_u16(const int32_t* src, size_t n, uint16_t* dst);      // sclane_narrow.cpp (AVX2 when the CPU has it)
+}
 using namespace sclane;
 
 #ifndef SCLANE_BATCH_CAP_GB
@@ -238,6 +242,38 @@ void launch_stage(const StageArgs& A, cudaStream_t s) {
   g_launches.fetch_add(1);
 }
 
+// Hybrid final stage on thread-block clusters: CL CTAs (on CL SMs of one GPC) per gene, partial moments exchanged through
+// distributed shared memory (sclane_device.cuh).  The cost of glm.nb varies 30x between genes and a single CTA cannot use more
+// than its SM's FP64 pipe, so the genes that hit the alternation limit used to run alone for tens of ms at the end of a launch.
+template <int CL>
+void launch_final_cluster(const StageArgs& A, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)A.n_genes * CL, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, k_stage<STAGE_FINAL, true, CL>, A));
+  g_launches.fetch_add(1);
+}
+
+// Cluster size of the hybrid final stage.  Measured on C4 (10,000 genes x 2 lineages of 30,000 cells, 1 x B200): final stage
+// 249 ms with CL = 1, 241 ms (2), 294 ms (4), 406 ms (8).  With 16,000 gene-lineages per run the launch is throughput bound
+// (sum of CTA time / 444 resident CTAs = 230 ms of the 264 ms): a cluster shortens the slowest gene 8x but every CTA of it now
+// idles at the cluster barrier and during the (replicated) serial algebra while holding one of the SM's three CTA slots.  So
+// the default is CL = 1; the cluster kernels stay built for small shards (SCLANE_FINAL_CLUSTER = 2 | 4 | 8), where the launch
+// is as long as its slowest gene.  The choice may only depend on the environment / lineage, never on the batch: the
+// summation order -- hence the last bits of a record -- differs between cluster sizes.
+int final_cluster_size(int n_cells_lineage) {
+  static const int forced = [] { const char* e = std::getenv("SCLANE_FINAL_CLUSTER"); return e ? std::atoi(e) : 0; }();
+  if ((forced == 2 || forced == 4 || forced == 8) && n_cells_lineage >= 4096) return forced;
+  return 1;
+}
+
 // K2 = k_sweep_moments (streaming, HBM bound) + k_sweep_select (warp per gene).  `first` also gathers the y moments.
 void launch_sweep(const StageArgs& A, bool first, cudaStream_t s, EventTimer* tm, sclane_profile* prof);
 
@@ -251,16 +287,187 @@ bool narrow_to_u16(const int32_t* src, size_t n, uint16_t* dst) {
   if (n < ((size_t)1 << 22)) nt = 1;
   std::vector<int> bad(nt, 0);
   auto work = [&](size_t t) {
-    const size_t a = n * t / nt, b = n * (t + 1) / nt;
-    unsigned acc = 0;
-    for (size_t i = a; i < b; ++i) { const uint32_t v = (uint32_t)src[i]; acc |= (v > 65534u) ? 1u : 0u; dst[i] = (uint16_t)v; }
-    bad[t] = (int)acc;
+    const size_t a = (n * t / nt) & ~(size_t)15, b = t + 1 == nt ? n : ((n * (t + 1) / nt) & ~(size_t)15);
+    bad[t] = narrow_range_u16(src + a, b - a, dst + a) ? 0 : 1;
   };
   if (nt == 1) work(0);
   else { ThreadGroup tg; for (size_t t = 0; t < nt; ++t) tg.run(work, t); tg.join(); }
   for (int b : bad) if (b) return false;
   return true;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Host -> device transfer of the caller's counts: its own host thread + copy stream, running ahead of the kernels.
+//
+// The PCIe link (55 GB/s measured) bounds the end-to-end time of a large matrix: 16 GB of int32 take 291 ms, the kernels 126 ms.
+// Counts almost always fit 16 bits, so the bytes can be halved on the host on their way out -- but narrowing costs host memory
+// bandwidth too (16 threads: ~60 GB/s of int32 consumed on the benchmark box).  The feeder therefore SPLITS every batch: the
+// genes [0, nA) are narrowed into a pinned staging buffer and sent as uint16, the genes [nA, nb) are copied straight from the
+// caller's buffer as int32 (no CPU involved).  Per batch it first queues the direct part -- the DMA engine is busy at once --
+// and narrows the staged part in chunks while that copy is on the wire; nA follows the measured rates (r_n = narrowing,
+// r_w = wire): both legs end together when f = nA / nb = 2 r_n / (2 r_w + r_n).  Pageable caller memory (an R matrix) cannot be
+// DMA-ed directly, so it is always staged (f = 1).  Three things overlap: narrow(k), wire(k - 1 .. k), kernels(k - 1).
+// Layout of a batch in its device buffer: the direct rows sit where they would sit in an all-int32 batch; the uint16 rows are
+// packed from offset 0 (inside the space the int32 rows of the same genes would take), so a batch whose staged part does not
+// fit 16 bits is simply re-sent as int32.
+// ---------------------------------------------------------------------------------------------
+class H2DFeeder {
+ public:
+  struct Layout { int64_t nA = 0; int a16 = 0; };      // genes [0, nA): uint16 rows (a16 = 1) or int32 rows; genes [nA, nb): int32 rows
+  enum Mode { DIRECT = 0, STAGED = 1, MIXED = 2 };
+
+  H2DFeeder(int device, cudaStream_t cs, const int32_t* h_counts, int64_t n_cells, int64_t g0, int64_t g1, int64_t B, Mode mode,
+            int* d_raw0, int* d_raw1, uint16_t* h_stage0, uint16_t* h_stage1)
+      : device_(device), cs_(cs), h_(h_counts), n_cells_(n_cells), g0_(g0), g1_(g1), B_(B), mode_(mode) {
+    d_raw_[0] = d_raw0; d_raw_[1] = d_raw1; h_stage_[0] = h_stage0; h_stage_[1] = h_stage1;
+    n_batches_ = (g1 - g0 + B - 1) / B;
+    layouts_.resize((size_t)n_batches_);
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&ev_h2d_[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_free_[i], cudaEventDisableTiming));
+      CK(cudaEventCreate(&ev_t0_[i]));
+      CK(cudaEventCreate(&ev_t1_[i]));
+    }
+    th_ = std::thread([this] { run(); });
+  }
+  ~H2DFeeder() {
+    { std::lock_guard<std::mutex> lk(mu_); abort_ = true; }
+    cv_.notify_all();
+    if (th_.joinable()) th_.join();
+    cudaStreamSynchronize(cs_);                       // nothing of this transfer may be in flight when the buffers are reused
+    for (int i = 0; i < 2; ++i) {
+      if (ev_h2d_[i]) cudaEventDestroy(ev_h2d_[i]);
+      if (ev_free_[i]) cudaEventDestroy(ev_free_[i]);
+      if (ev_t0_[i]) cudaEventDestroy(ev_t0_[i]);
+      if (ev_t1_[i]) cudaEventDestroy(ev_t1_[i]);
+    }
+  }
+  H2DFeeder(const H2DFeeder&) = delete;
+  H2DFeeder& operator=(const H2DFeeder&) = delete;
+
+  // compute thread: blocks until every copy of batch k and its completion event are queued on the copy stream
+  Layout wait(int64_t k) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return enqueued_ > k || failed_; });
+    if (enqueued_ <= k) throw CudaFail{error_};
+    return layouts_[(size_t)k];
+  }
+  cudaEvent_t ready(int64_t k) const { return ev_h2d_[k & 1]; }
+  const int* raw(int64_t k) const { return d_raw_[k & 1]; }
+  // compute thread: the gather of batch k is queued on `s`; its device buffer may be overwritten once that has run
+  void consumed(int64_t k, cudaStream_t s) {
+    CK(cudaEventRecord(ev_free_[k & 1], s));
+    { std::lock_guard<std::mutex> lk(mu_); gathered_ = k + 1; }
+    cv_.notify_all();
+  }
+  double h2d_bytes() const { return bytes_; }          // valid after the last wait() returned
+  long long copies() const { return copies_; }
+
+ private:
+  void run() {
+    try {
+      CK(cudaSetDevice(device_));
+      double r_n = 60e9, r_w = 52e9;                   // bytes of int32 per second: narrowing (all host threads), wire
+      bool had_direct[2] = {false, false};
+      size_t direct_bytes[2] = {0, 0};
+      for (int64_t k = 0; k < n_batches_; ++k) {
+        const int buf = (int)(k & 1);
+        const int64_t kb0 = g0_ + k * B_, kb1 = std::min<int64_t>(kb0 + B_, g1_);
+        const int64_t nbk = kb1 - kb0;
+        const int32_t* src = h_ + (size_t)kb0 * (size_t)n_cells_;
+        if (k >= 2) {
+          {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return gathered_ >= k - 1 || abort_; });
+            if (abort_) return;
+          }
+          CK(cudaStreamWaitEvent(cs_, ev_free_[buf], 0));              // the gather of batch k - 2 has consumed this device buffer
+          CK(cudaEventSynchronize(ev_h2d_[buf]));                      // ... and its copies have left the staging buffer
+          if (had_direct[buf]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev_t0_[buf], ev_t1_[buf]) == cudaSuccess && ms > 0.05f) r_w = (double)direct_bytes[buf] / (ms * 1e-3);
+            else cudaGetLastError();
+          }
+        } else {
+          std::lock_guard<std::mutex> lk(mu_);
+          if (abort_) return;
+        }
+        double f = mode_ == DIRECT ? 0.0 : (mode_ == STAGED ? 1.0 : 2.0 * r_n / (2.0 * r_w + r_n));
+        if (f > 0.93) f = 1.0;
+        if (f < 0.07) f = 0.0;
+        int64_t nA = (int64_t)std::llround(f * (double)nbk);
+        if (nA > nbk) nA = nbk;
+        Layout lay;
+        lay.nA = nA; lay.a16 = nA > 0 ? 1 : 0;
+        char* dbase = reinterpret_cast<char*>(d_raw_[buf]);
+        had_direct[buf] = false;
+        if (nA < nbk) {                                                // direct part first: keeps the link busy while the CPU narrows
+          const size_t off = (size_t)nA * (size_t)n_cells_ * 4, bytes = (size_t)(nbk - nA) * (size_t)n_cells_ * 4;
+          CK(cudaEventRecord(ev_t0_[buf], cs_));
+          CK(cudaMemcpyAsync(dbase + off, src + (size_t)nA * (size_t)n_cells_, bytes, cudaMemcpyHostToDevice, cs_));
+          CK(cudaEventRecord(ev_t1_[buf], cs_));
+          had_direct[buf] = true; direct_bytes[buf] = bytes;
+          bytes_ += (double)bytes; copies_++;
+        }
+        if (nA > 0) {
+          const size_t n_el = (size_t)nA * (size_t)n_cells_;
+          const size_t chunk = (size_t)1 << 25;                        // 128 MB of int32 per chunk: ~2 ms of narrowing
+          bool fits = true;
+          double t_n = 0.0;
+          for (size_t c0 = 0; c0 < n_el && fits; c0 += chunk) {
+            const size_t c1 = std::min(n_el, c0 + chunk);
+            const auto t0 = std::chrono::steady_clock::now();
+            fits = narrow_to_u16(src + c0, c1 - c0, h_stage_[buf] + c0);
+            t_n += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (fits) {
+              CK(cudaMemcpyAsync(dbase + c0 * 2, h_stage_[buf] + c0, (c1 - c0) * 2, cudaMemcpyHostToDevice, cs_));
+              bytes_ += (double)(c1 - c0) * 2.0; copies_++;
+            }
+            { std::lock_guard<std::mutex> lk(mu_); if (abort_) return; }
+          }
+          if (!fits) {                                                 // a count > 65534 (or < 0): this part travels as int32 after all
+            lay.a16 = 0;
+            CK(cudaMemcpyAsync(dbase, src, n_el * 4, cudaMemcpyHostToDevice, cs_));
+            bytes_ += (double)n_el * 4.0; copies_++;
+          } else if (t_n > 1e-4) {
+            r_n = (double)n_el * 4.0 / t_n;
+          }
+        }
+        CK(cudaEventRecord(ev_h2d_[buf], cs_));
+        {
+          std::lock_guard<std::mutex> lk(mu_);
+          layouts_[(size_t)k] = lay;
+          enqueued_ = k + 1;
+        }
+        cv_.notify_all();
+      }
+    } catch (const CudaFail& e) {
+      { std::lock_guard<std::mutex> lk(mu_); failed_ = true; error_ = e.msg; }
+      cv_.notify_all();
+    } catch (const std::exception& e) {
+      { std::lock_guard<std::mutex> lk(mu_); failed_ = true; error_ = std::string("transfer thread: ") + e.what(); }
+      cv_.notify_all();
+    }
+  }
+
+  int device_;
+  cudaStream_t cs_;
+  const int32_t* h_;
+  int64_t n_cells_, g0_, g1_, B_, n_batches_ = 0;
+  Mode mode_;
+  int* d_raw_[2];
+  uint16_t* h_stage_[2];
+  cudaEvent_t ev_h2d_[2] = {nullptr, nullptr}, ev_free_[2] = {nullptr, nullptr}, ev_t0_[2] = {nullptr, nullptr}, ev_t1_[2] = {nullptr, nullptr};
+  std::thread th_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int64_t enqueued_ = 0, gathered_ = 0;
+  bool abort_ = false, failed_ = false;
+  std::string error_;
+  std::vector<Layout> layouts_;
+  double bytes_ = 0.0;
+  long long copies_ = 0;
+};
 
 // The lineage plan (host: knots, sort, buckets, points) is built on a background thread while the first batch of counts is
 // already on its way to the device; get() joins it.
@@ -315,67 +522,38 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   const int Npad_guess = (int)((n_cells + 127) / 128 * 128);
   int64_t B = batch_size(Npad_guess, 10016, o.force_per_cell == 0);
   int64_t n_batches = (G + B - 1) / B;
-  // staged transfer (see sclane_opts.h2d_mode): automatic = when the copy is big enough to matter and pipelined
-  // automatic = pageable caller memory (an R integer matrix): cudaMemcpyAsync from it is staged by the driver at ~12 GB/s,
-  // the library's own threads + pinned buffers reach the PCIe rate; a pinned caller buffer (bench.py) is copied directly --
-  // narrowing 16 GB on this box's 16 host cores is no faster than sending it
-  bool pageable = false;
-  if (h_counts && o.h2d_mode == 0) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, h_counts) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
-    else cudaGetLastError();
-  }
-  bool staged = false;
-  uint16_t* h_stage[2] = {nullptr, nullptr};
-  int fmt16[2] = {0, 0};
-  int* d_raw2[2] = {nullptr, nullptr};
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  // transfer of the caller's counts (H2DFeeder above; sclane_opts.h2d_mode: 0 automatic, 1 direct int32, 2 staged uint16).
+  // Automatic: small inputs are copied directly; large pageable ones (an R integer matrix: cudaMemcpyAsync from it is staged by
+  // the driver at ~12 GB/s and blocks) go through the library's own pinned staging; large pinned ones are split between the two.
+  std::unique_ptr<H2DFeeder> feeder;
   cudaStream_t cs = nullptr;
-  auto setup_transfer = [&]() {                     // (re)sizes the transfer buffers for the current B
-    staged = h_counts && (o.h2d_mode == 2 || (o.h2d_mode == 0 && pageable && n_batches >= 2 && (double)G * (double)n_cells * 4.0 >= 256e6));
-    d_raw2[0] = (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4);
-    d_raw2[1] = n_batches > 1 ? (int*)pool.get("raw_b", (size_t)B * (size_t)n_cells * 4) : d_raw2[0];
-    if (staged) {
-      h_stage[0] = (uint16_t*)pool.get("stage_a", (size_t)B * (size_t)n_cells * 2, true);
-      h_stage[1] = n_batches > 1 ? (uint16_t*)pool.get("stage_b", (size_t)B * (size_t)n_cells * 2, true) : h_stage[0];
+  auto start_feeder = [&]() {                       // (re)sizes the transfer buffers for the current B and starts the transfer
+    feeder.reset();
+    H2DFeeder::Mode mode = H2DFeeder::DIRECT;
+    if (o.h2d_mode == 2) mode = H2DFeeder::STAGED;
+    else if (o.h2d_mode == 0 && (double)G * (double)n_cells * 4.0 >= 256e6) {
+      bool pageable = false;
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, h_counts) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+      else cudaGetLastError();
+      mode = pageable ? H2DFeeder::STAGED : H2DFeeder::MIXED;
     }
+    int* r0 = (int*)pool.get("raw", (size_t)B * (size_t)n_cells * 4);
+    int* r1 = n_batches > 1 ? (int*)pool.get("raw_b", (size_t)B * (size_t)n_cells * 4) : r0;
+    uint16_t *h0 = nullptr, *h1 = nullptr;
+    if (mode != H2DFeeder::DIRECT) {
+      h0 = (uint16_t*)pool.get("stage_a", (size_t)B * (size_t)n_cells * 2, true);
+      h1 = n_batches > 1 ? (uint16_t*)pool.get("stage_b", (size_t)B * (size_t)n_cells * 2, true) : h0;
+    }
+    feeder.reset(new H2DFeeder(device, cs, h_counts, n_cells, g0, g1, B, mode, r0, r1, h0, h1));
   };
   if (h_counts) {
     if (!pool.copy_stream) CK(cudaStreamCreateWithFlags(&pool.copy_stream, cudaStreamNonBlocking));
     cs = pool.copy_stream;
-    setup_transfer();
-    for (int i = 0; i < 2; ++i) {
-      CK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
-    }
+    start_feeder();                                 // the first batch travels while the plan is being built
   }
-  struct EventGuard {
-    cudaEvent_t* a; cudaEvent_t* b;
-    ~EventGuard() { for (int i = 0; i < 2; ++i) { if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); } }
-  } ev_guard{ev_h2d, ev_free};
-  auto issue_h2d = [&](int64_t k) {
-    const int buf = (int)(k & 1);
-    const int64_t kb0 = g0 + k * B, kb1 = std::min<int64_t>(kb0 + B, g1);
-    const size_t n_el = (size_t)(kb1 - kb0) * (size_t)n_cells;
-    const int32_t* src = h_counts + (size_t)kb0 * (size_t)n_cells;
-    fmt16[buf] = 0;
-    if (staged) {
-      if (k >= 2) CK(cudaEventSynchronize(ev_h2d[buf]));                // the H2D of batch k - 2 has left this staging buffer
-      fmt16[buf] = narrow_to_u16(src, n_el, h_stage[buf]) ? 1 : 0;
-    }
-    if (k >= 2) CK(cudaStreamWaitEvent(cs, ev_free[buf], 0));          // the gather of batch k - 2 has consumed this buffer
-    if (fmt16[buf]) CK(cudaMemcpyAsync(d_raw2[buf], h_stage[buf], n_el * 2, cudaMemcpyHostToDevice, cs));
-    else CK(cudaMemcpyAsync(d_raw2[buf], src, n_el * 4, cudaMemcpyHostToDevice, cs));
-    CK(cudaEventRecord(ev_h2d[buf], cs));
-    prof.h2d_bytes += (double)n_el * (fmt16[buf] ? 2.0 : 4.0);
-    prof.launches[SCLANE_STAGE_COPY]++;
-  };
-  const double h2d_before = prof.h2d_bytes;
-  const long long copies_before = prof.launches[SCLANE_STAGE_COPY];
-  if (h_counts) issue_h2d(0);                      // the first batch travels while the plan is being built
   const LineagePlan* Pp = nullptr;
-  try { Pp = &PS.get(); }
-  catch (...) { if (h_counts) cudaStreamSynchronize(cs); throw; }      // nothing may be in flight when the caller sees the error
+  Pp = &PS.get();                                   // (on failure the feeder's destructor drains the copy stream)
   const LineagePlan& P = *Pp;
   const Lineage& L = P.L;
   // X-compressed path (sclane_comp.cuh): worth it when the 4-decimal rounding leaves clearly fewer abscissae than cells
@@ -386,10 +564,10 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   {
     const int64_t B_real = batch_size(L.Npad, Dpad, use_comp);
     if (B_real != B) {                              // the guess was off (other route / more abscissae): restart the transfer
-      if (h_counts) CK(cudaStreamSynchronize(cs));
+      feeder.reset();
       B = B_real;
       n_batches = (G + B - 1) / B;
-      if (h_counts) { setup_transfer(); prof.h2d_bytes = h2d_before; prof.launches[SCLANE_STAGE_COPY] = copies_before; issue_h2d(0); }
+      if (h_counts) start_feeder();
     }
   }
   DevicePlan D;
@@ -439,30 +617,38 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     const int nb = (int)(b1 - b0);
     tm.mark(SCLANE_STAGE_COPY);             // on the compute stream this interval is the EXPOSED wait for the batch's H2D
     const int* raw = nullptr;
-    const bool raw16 = h_counts && fmt16[kb & 1];
+    H2DFeeder::Layout lay;                          // device-resident counts: one int32 part
+    lay.nA = 0; lay.a16 = 0;
     if (h_counts) {
-      CK(cudaStreamWaitEvent(s, ev_h2d[kb & 1], 0));
-      raw = d_raw2[kb & 1];
+      lay = feeder->wait(kb);
+      CK(cudaStreamWaitEvent(s, feeder->ready(kb), 0));
+      raw = feeder->raw(kb);
     } else {
       raw = d_counts + (size_t)b0 * (size_t)n_cells;
     }
     tm.mark(SCLANE_STAGE_GATHER);
-    if (use_comp) {
-      // compressed route: plain permutation copy, K CTAs per gene; k_aggregate derives the per-gene constants
-      int K = (int)((L.N + 8191) / 8192);
-      if (K < 1) K = 1;
-      if (K > 32) K = 32;
-      while (K > 1 && (((L.Npad / K + 127) / 128) * 128) * (K - 1) >= L.Npad) --K;      // no empty trailing part
-      if (raw16) k_gather_copy<unsigned short><<<(unsigned)((size_t)nb * K), kThreads, 0, s>>>((const unsigned short*)raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, nb, K);
-      else k_gather_copy<int><<<(unsigned)((size_t)nb * K), kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, nb, K);
-    } else {
-      if (raw16) k_gather_stats<unsigned short><<<nb, kThreads, 0, s>>>((const unsigned short*)raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
-      else k_gather_stats<int><<<nb, kThreads, 0, s>>>(raw, (long long)n_cells, D.perm, L.N, L.Npad, d_ys, d_stats, d_out, nb);
-    }
-    CK(cudaGetLastError());
-    if (h_counts) CK(cudaEventRecord(ev_free[kb & 1], s));
-    g_launches.fetch_add(1);
-    prof.launches[SCLANE_STAGE_GATHER]++;
+    // genes [gene0, gene0 + cnt) of the batch, whose rows start at `base` as uint16 or int32
+    auto gather_part = [&](const void* base, bool u16, int gene0, int cnt) {
+      int* ys_p = d_ys + (size_t)gene0 * (size_t)L.Npad;
+      if (use_comp) {
+        // compressed route: plain permutation copy, K CTAs per gene; k_aggregate derives the per-gene constants
+        int K = (int)((L.N + 8191) / 8192);
+        if (K < 1) K = 1;
+        if (K > 32) K = 32;
+        while (K > 1 && (((L.Npad / K + 127) / 128) * 128) * (K - 1) >= L.Npad) --K;      // no empty trailing part
+        if (u16) k_gather_copy<unsigned short><<<(unsigned)((size_t)cnt * K), kThreads, 0, s>>>((const unsigned short*)base, (long long)n_cells, D.perm, L.N, L.Npad, ys_p, cnt, K);
+        else k_gather_copy<int><<<(unsigned)((size_t)cnt * K), kThreads, 0, s>>>((const int*)base, (long long)n_cells, D.perm, L.N, L.Npad, ys_p, cnt, K);
+      } else {
+        if (u16) k_gather_stats<unsigned short><<<cnt, kThreads, 0, s>>>((const unsigned short*)base, (long long)n_cells, D.perm, L.N, L.Npad, ys_p, d_stats + gene0, d_out + gene0, cnt);
+        else k_gather_stats<int><<<cnt, kThreads, 0, s>>>((const int*)base, (long long)n_cells, D.perm, L.N, L.Npad, ys_p, d_stats + gene0, d_out + gene0, cnt);
+      }
+      CK(cudaGetLastError());
+      g_launches.fetch_add(1);
+      prof.launches[SCLANE_STAGE_GATHER]++;
+    };
+    if (lay.nA > 0) gather_part(raw, lay.a16 != 0, 0, (int)lay.nA);
+    if (lay.nA < nb) gather_part(reinterpret_cast<const char*>(raw) + (size_t)lay.nA * (size_t)n_cells * 4, false, (int)lay.nA, nb - (int)lay.nA);
+    if (h_counts) feeder->consumed(kb, s);
     StageArgs A;
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = D.off; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
     A.scores = nullptr; A.mom = d_mom; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
@@ -574,7 +760,12 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       // alternatives with hinges: hybrid per-cell passes (mu-free terms from the histogram); genes without a histogram
       // (route 0) are left to the plain per-cell launch below, which skips everything already done
       A.cg = d_cg; A.tail = d_tail; A.big = d_big; A.exact = exact ? 1 : 0; A.pstart = D.pstart;
-      launch_stage<STAGE_FINAL, true>(A, s);
+      switch (final_cluster_size(P.L.N)) {
+        case 8: launch_final_cluster<8>(A, s); break;
+        case 4: launch_final_cluster<4>(A, s); break;
+        case 2: launch_final_cluster<2>(A, s); break;
+        default: launch_stage<STAGE_FINAL, true>(A, s);
+      }
       prof.launches[SCLANE_STAGE_FINAL]++;
     }
     launch_stage<STAGE_FINAL>(A, s);
@@ -585,8 +776,6 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.d2h_bytes += (double)nb * sizeof(GeneOutDev);
     prof.launches[SCLANE_STAGE_COPY]++;
     tm.mark(-1);
-    // everything of batch kb is queued: prepare and send batch kb + 1 while the GPU works (host narrowing + copy stream)
-    if (h_counts && kb + 1 < n_batches) issue_h2d(kb + 1);
     CK(cudaStreamSynchronize(s));
     tm.collect(prof);
     // records: z / p-values, LRT, pchisq per gene (~1-2 us each) -- spread over host threads, chunk sums in chunk order
@@ -611,6 +800,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     }
     prof.sweep_bytes += 8.0 * (double)L.N * (double)n_iter;
   }
+  if (feeder) { prof.h2d_bytes += feeder->h2d_bytes(); prof.launches[SCLANE_STAGE_COPY] += feeder->copies(); }
 }
 
 // GEE mode: genes [g0, g1) of one lineage on one device.  Same batching as run_shard; one k_gee launch per batch.

@@ -45,7 +45,31 @@ template <> struct PassTraits<PASS_EMIT>       { static constexpr int NA = 0, NS
 //              mu_i = exp(a_b + c_b u_i + o_i) differs from cell to cell -- but every mu-free term (psi / trigamma / lgamma
 //              differences, (y + theta) log1p(sigma y)) from the gene's count histogram, exactly as the X-compressed passes do
 //              (sclane_comp.cuh): no per-pass tables, no table look-ups and no large-count branch in the cell loop.
-template <bool HYB>
+// Cluster barrier (all threads of all CTAs of the cluster): release / acquire, so that shared-memory writes made before it
+// are visible to remote reads (DSMEM) made after it.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// generic address of `p` (a shared-memory address of this CTA) in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ const double* cluster_map(const double* p, unsigned rank) {
+  unsigned long long out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(rank));
+  return reinterpret_cast<const double*>(out);
+}
+
+constexpr int kPartN = NBMAX * NACC + NSC;     // one CTA's partial sums of a pass (cluster mode)
+
+// CL > 1: a thread-block CLUSTER of CL CTAs fits one gene.  Every CTA keeps its own copy of the gene's state and runs the
+// identical control flow (the serial algebra is redundant, deterministic and therefore identical); a pass splits the cells
+// over the CL x 8 warps of the cluster and the CTAs exchange their partial moments through distributed shared memory:
+// each CTA writes part[buf], ONE cluster barrier, each CTA sums the CL partials in rank order (-> bit-identical in every
+// CTA and for every launch).  part[] is double buffered, which makes a second barrier per pass unnecessary.
+template <bool HYB, int CL = 1>
 struct DevExecT {
   static constexpr bool kTabs = true;      // term tables attached to Work (sclane_core.cuh term_coef)
   Work* W;
@@ -67,6 +91,9 @@ struct DevExecT {
   const double* wztab;
   const double* uoff;               // exact-knot mode: u[] is relative to the lineage's smallest abscissa and the buckets are the gene's
                                     // own, so the bucket-local coordinate is u[i] - uoff[bucket]; nullptr otherwise
+  double* part;                     // cluster mode: [2][kPartN] this CTA's partial sums (shared memory), else nullptr
+  int crank;                        // cluster mode: rank of this CTA in its cluster
+  int pbuf;                         // cluster mode: which half of part[] the running pass writes
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -105,6 +132,48 @@ struct DevExecT {
   template <int NA, int NS>
   __device__ __forceinline__ void combine(int T) {
     __syncthreads();
+    if (CL > 1) {
+      double* mine = part + pbuf * kPartN;
+      if (NA > 0) {
+        for (int i = threadIdx.x; i < (T + 1) * NACC; i += kThreads) {
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) s += (&slot[w][0][0])[i];
+          mine[i] = s;
+        }
+      }
+      if (NS > 0 && threadIdx.x < NS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += scw[w][threadIdx.x];
+        mine[NBMAX * NACC + threadIdx.x] = s;
+      }
+      cluster_sync_all();
+      if (NA > 0) {
+        double* out = &W->acc[0][0];
+        for (int i = threadIdx.x; i < (T + 1) * NACC; i += kThreads) {
+          double v[CL];
+#pragma unroll
+          for (int r = 0; r < CL; ++r) v[r] = cluster_map(mine, r)[i];
+          double s = 0.0;
+#pragma unroll
+          for (int r = 0; r < CL; ++r) s += v[r];
+          out[i] = s;
+        }
+      }
+      if (NS > 0 && threadIdx.x < NS) {
+        double v[CL];
+#pragma unroll
+        for (int r = 0; r < CL; ++r) v[r] = cluster_map(mine, r)[NBMAX * NACC + threadIdx.x];
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) s += v[r];
+        W->sc[threadIdx.x] = s;
+      }
+      pbuf ^= 1;
+      __syncthreads();
+      return;
+    }
     if (NA > 0) {
       double* out = &W->acc[0][0];
       for (int i = threadIdx.x; i < (T + 1) * NACC; i += kThreads) {
@@ -176,8 +245,9 @@ struct DevExecT {
 #endif
     // contiguous run of 32-cell groups per warp
     const int ngroups = (N + 31) >> 5;
-    const int g0 = (int)(((long long)ngroups * warp) / kWarps);
-    const int g1 = (int)(((long long)ngroups * (warp + 1)) / kWarps);
+    const int gw = CL > 1 ? crank * kWarps + warp : warp;      // this warp among the CL x 8 warps that share the gene
+    const int g0 = (int)(((long long)ngroups * gw) / (kWarps * CL));
+    const int g1 = (int)(((long long)ngroups * (gw + 1)) / (kWarps * CL));
     if (g0 < g1) {
       int cur_b = 0;                       // bucket the register accumulators belong to (warp uniform)
       const int first = g0 << 5;
@@ -271,9 +341,10 @@ struct DevExecT {
       // the mu-free terms of the pass from the gene's tail counts and its list of large counts (sclane_comp.cuh)
       const int ymax = cg->hdr.ymax;
       const int hmax = ymax < kHistCap ? ymax : kHistCap - 1;
-      for (int k = threadIdx.x; k < hmax; k += kThreads) hist_contrib<MODE>(k, (double)tail[k], (double)tail[k + 1], sigma, theta, want_ll, sc);
+      const int gt = CL > 1 ? crank * kThreads + (int)threadIdx.x : (int)threadIdx.x;
+      for (int k = gt; k < hmax; k += kThreads * CL) hist_contrib<MODE>(k, (double)tail[k], (double)tail[k + 1], sigma, theta, want_ll, sc);
       const int n_big = cg->hdr.n_big;
-      for (int e = threadIdx.x; e < n_big; e += kThreads) big_contrib<MODE>(big[e], sigma, theta, want_ll, sc);
+      for (int e = gt; e < n_big; e += kThreads * CL) big_contrib<MODE>(big[e], sigma, theta, want_ll, sc);
     }
     if (NS > 0) flush_uniform<NS>(sc, 0, &scw[warp][0], 0);
     combine<NA, NS>(T);
@@ -329,7 +400,7 @@ struct StageArgs {
 
 enum Stage : int { STAGE_FWD_FIT = 0, STAGE_BACKWARD = 2, STAGE_FINAL = 3 };
 
-template <int STAGE, bool HYB = false>
+template <int STAGE, bool HYB = false, int CL = 1>
 __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs A) {
   __shared__ Work W;
   __shared__ Lineage Ls;
@@ -342,8 +413,13 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   __shared__ TermTabs ttab;
   __shared__ double wtab[HYB ? 64 : 1], wztab[HYB ? 64 : 1];
   __shared__ double uoff_s[NBMAX + 1];
-  if ((int)blockIdx.x >= A.n_genes) return;
-  const int g = ((STAGE == STAGE_FINAL || STAGE == STAGE_BACKWARD) && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
+  __shared__ double part_s[CL > 1 ? 2 * kPartN : 1];
+  __shared__ NbResult dump_s[CL > 1 ? 2 : 1];        // cluster mode: CTAs other than rank 0 keep their (identical) results here
+  static_assert(CL == 1 || (HYB && STAGE == STAGE_FINAL), "clusters are used by the hybrid final stage only");
+  const int slot_g = (int)blockIdx.x / CL;            // every exit below is uniform over the cluster (gene-level conditions)
+  const int crank = CL > 1 ? (int)cluster_cta_rank() : 0;
+  if (slot_g >= A.n_genes) return;
+  const int g = ((STAGE == STAGE_FINAL || STAGE == STAGE_BACKWARD) && A.order) ? A.order[slot_g] : slot_g;
   if (HYB && A.cg[g].hdr.route == 0) return;          // block-uniform: this gene has no histogram (plain per-cell kernel fits it)
   {
     if (HYB && threadIdx.x < 64) start_cell(threadIdx.x, wtab[threadIdx.x], wztab[threadIdx.x]);
@@ -383,27 +459,30 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   if (STAGE == STAGE_FINAL && (st.done & 2)) return;
   const size_t row = (size_t)g * (size_t)Ls.Npad;
   const long long t_start = clock64();
-  DevExecT<HYB> ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs, &ftab,
-                   HYB ? A.cg + g : nullptr, &gs, HYB ? A.tail + (size_t)g * (size_t)kHistCap : nullptr, HYB ? A.big + (size_t)g * (size_t)kBigCap : nullptr,
-                   wtab, wztab, A.exact ? uoff_s : nullptr};
+  DevExecT<HYB, CL> ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs, &ftab,
+                       HYB ? A.cg + g : nullptr, &gs, HYB ? A.tail + (size_t)g * (size_t)kHistCap : nullptr, HYB ? A.big + (size_t)g * (size_t)kBigCap : nullptr,
+                       wtab, wztab, A.exact ? uoff_s : nullptr, CL > 1 ? part_s : nullptr, crank, 0};
   if (STAGE == STAGE_FWD_FIT) {
     gene_forward_fit(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_BACKWARD) {
     gene_backward(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_FINAL) {
     // genes whose intercept-only fits already ran on the offset quadrature (done bit 2) only need the alternative with hinges
-    gene_final(ex, Ls, gs, st, W, A.use_offset != 0, &A.out[g].alt, &A.out[g].null, (st.done & 4) ? 2 : 3);
+    NbResult* alt_out = crank == 0 ? &A.out[g].alt : &dump_s[0];
+    NbResult* null_out = crank == 0 ? &A.out[g].null : &dump_s[CL > 1 ? 1 : 0];
+    gene_final(ex, Ls, gs, st, W, A.use_offset != 0, alt_out, null_out, (st.done & 4) ? 2 : 3);
     __syncthreads();
     if (threadIdx.x == 0) st.done |= 2;
   }
   __syncthreads();
   if (threadIdx.x == 0) { st.passes += W.passes; st.cycles[STAGE == STAGE_FWD_FIT ? 0 : (STAGE == STAGE_BACKWARD ? 1 : 2)] += clock64() - t_start; }
   __syncthreads();
-  {
+  if (crank == 0) {
     int* d2 = reinterpret_cast<int*>(&A.out[g].st);
     const int* s2 = reinterpret_cast<const int*>(&st);
     for (int i = threadIdx.x; i < (int)(sizeof(GeneState) / sizeof(int)); i += kThreads) d2[i] = s2[i];
   }
+  if (CL > 1) cluster_sync_all();                      // no CTA leaves while another may still read its partial sums
 }
 
 // ---------------------------------------------------------------------------------------------

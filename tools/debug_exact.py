@@ -8,10 +8,14 @@ from sclane_b200 import api
 from tools import synth
 from test_parity_r02 import oracle_parallel_opts
 n_cells = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
-counts, pt, _ = synth.make_counts(56, n_cells, seed=41)
-genes = [f"g{i}" for i in range(56)]
-res = sb.testDynamic(counts, pt, genes=genes, approx_knot=False, n_gpus=1, preds="none")
-ref = oracle_parallel_opts(counts, pt.reshape(-1), genes, None, approx_knot=False)
+n_genes = int(sys.argv[2]) if len(sys.argv) > 2 else 56
+seed = int(sys.argv[3]) if len(sys.argv) > 3 else 41
+use_off = len(sys.argv) > 4 and sys.argv[4] == "off"
+counts, pt, _ = synth.make_counts(n_genes, n_cells, seed=seed)
+genes = [f"g{i}" for i in range(n_genes)]
+sf = sb.createCellOffset(counts) if use_off else None
+res = sb.testDynamic(counts, pt, genes=genes, size_factor_offset=sf, approx_knot=False, n_gpus=1, preds="none")
+ref = oracle_parallel_opts(counts, pt.reshape(-1), genes, sf, approx_knot=False)
 bad = 0
 for i, g in enumerate(genes):
     r, o = res[g]["Lineage_A"], ref[g]["Lineage_A"]

@@ -33,3 +33,11 @@ print("sum(cycles)/444 units: %.2f ms | slowest %.2f ms | median(hinge genes) %.
 print("alt fits: alternations median %d p90 %d max %d; irls iters median %d p90 %d max %d" % (np.median(alt[h]), np.quantile(alt[h], 0.9), alt[h].max(), np.median(irls[h]), np.quantile(irls[h], 0.9), irls[h].max()))
 o2 = np.argsort(-cyc)
 for i in o2[:8]: print("  gene-lineage", i, "ms %.2f" % (cyc[i] / clk * 1e3), "alternations", alt[i], "irls", irls[i], "theta %.4g" % recs[i].theta, "n_terms", nt[i], "fwd sigma", [round(x, 4) for x in recs[i].fwd_sigma[:2]])
+ms = cyc / clk * 1e3
+for thr in (2, 5, 10, 20, 40):
+    sel = ms > thr
+    print("  genes slower than %2d ms: %5d  (share of all CTA time %.3f)" % (thr, sel.sum(), ms[sel].sum() / ms.sum()))
+for lo, hi in ((1, 2), (3, 5), (6, 10), (11, 24), (25, 25)):
+    sel = h & (alt >= lo) & (alt <= hi)
+    if sel.any():
+        print("  alternations %2d-%2d: %5d genes, median %.2f ms, max %.2f ms, share of CTA time %.3f" % (lo, hi, sel.sum(), np.median(ms[sel]), ms[sel].max(), ms[sel].sum() / ms.sum()))
