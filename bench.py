@@ -308,6 +308,7 @@ def main():
     ap.add_argument("--per-cell", action="store_true", help="force the per-cell kernels for the whole run (profiling)")
     ap.add_argument("--warp-per-gene", action="store_true", help="X-compressed fits on the warp-per-gene kernels (A/B against the CTA-per-gene ones)")
     ap.add_argument("--offset-per-cell", action="store_true", help="intercept-only fits with an offset per cell (A/B against the offset quadrature)")
+    ap.add_argument("--genes-per-batch", type=int, default=0, help="sclane_opts.genes_per_batch of the end-to-end legs (0 = the library's choice)")
     ap.add_argument("--approx-knot", type=int, default=1, help="0 = approx.knot = FALSE: every abscissa kept by min_span / max_span is a candidate knot")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
@@ -391,7 +392,7 @@ def main():
         e2e_note = f"pinned host allocation of the full shard failed ({str(exc)[:60]}); e2e on the first {Ge} genes, pageable"
     torch.cuda.synchronize()
     h_np = h_counts.numpy()
-    opts_host = mk_opts(h2d_mode=args.h2d_mode)
+    opts_host = mk_opts(h2d_mode=args.h2d_mode, genes_per_batch=args.genes_per_batch)
 
     def step_device():
         return sb.run_records(G, pt_in, sf, opts, device_ptr=d_counts.data_ptr(), device=local)

@@ -170,6 +170,17 @@ struct EventTimer {
   ~EventTimer() { for (auto e : ev) cudaEventDestroy(e); }
 };
 
+// Wait for everything queued on `s` WITHOUT spinning: cudaStreamSynchronize busy-waits on a core by default, and during a
+// host-fed run every core is needed by the narrowing threads of the transfer.
+void stream_wait_blocking(cudaStream_t s) {
+  cudaEvent_t e;
+  CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+  cudaError_t r = cudaEventRecord(e, s);
+  if (r == cudaSuccess) r = cudaEventSynchronize(e);
+  cudaEventDestroy(e);
+  CK(r);
+}
+
 struct DevicePlan {
   int* perm = nullptr;
   double* u = nullptr;
@@ -242,6 +253,12 @@ void launch_stage(const StageArgs& A, cudaStream_t s) {
   g_launches.fetch_add(1);
 }
 
+// theta.ml on Chebyshev nodes in k_comp_stage<FINAL> (sclane_comp.cuh); SCLANE_THETA_NODES=0 walks the points instead (A/B).
+bool theta_nodes_enabled() {
+  static const bool on = [] { const char* e = std::getenv("SCLANE_THETA_NODES"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // Hybrid final stage on thread-block clusters: CL CTAs (on CL SMs of one GPC) per gene, partial moments exchanged through
 // distributed shared memory (sclane_device.cuh).  The cost of glm.nb varies 30x between genes and a single CTA cannot use more
 // than its SM's FP64 pipe, so the genes that hit the alternation limit used to run alone for tens of ms at the end of a launch.
@@ -281,20 +298,61 @@ int forward_iterations(int M) { return (M - 1 + 1) / 2; }   // m = 1, 3, 5, ... 
 
 // Host side of the staged transfer: int32 -> uint16 with a pool of threads.  Returns false (and the caller sends the batch
 // as int32) when a value does not fit.
-bool narrow_to_u16(const int32_t* src, size_t n, uint16_t* dst) {
-  unsigned hw = std::thread::hardware_concurrency();
-  size_t nt = hw == 0 ? 4 : std::min<unsigned>(hw, 16);
-  if (n < ((size_t)1 << 22)) nt = 1;
-  std::vector<int> bad(nt, 0);
-  auto work = [&](size_t t) {
-    const size_t a = (n * t / nt) & ~(size_t)15, b = t + 1 == nt ? n : ((n * (t + 1) / nt) & ~(size_t)15);
-    bad[t] = narrow_range_u16(src + a, b - a, dst + a) ? 0 : 1;
-  };
-  if (nt == 1) work(0);
-  else { ThreadGroup tg; for (size_t t = 0; t < nt; ++t) tg.run(work, t); tg.join(); }
-  for (int b : bad) if (b) return false;
-  return true;
-}
+// Worker threads that live as long as a transfer: a chunk of 128 MB is narrowed in ~1.5 ms, which is what spawning and joining
+// 16 threads per chunk would cost too.  run() hands every worker a slice of the chunk and returns when all are done; false when
+// a value does not fit (the caller then sends the rows as int32).
+class NarrowPool {
+ public:
+  explicit NarrowPool(int n_threads) : nt_(n_threads < 1 ? 1 : n_threads), bad_((size_t)nt_, 0) {
+    for (int t = 0; t < nt_; ++t) th_.emplace_back([this, t] { loop(t); });
+  }
+  ~NarrowPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++gen_; }
+    cv_.notify_all();
+    for (auto& t : th_) if (t.joinable()) t.join();
+  }
+  bool run(const int32_t* src, size_t n, uint16_t* dst) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      src_ = src; dst_ = dst; n_ = n; pending_ = nt_; ++gen_;
+    }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    for (int b : bad_) if (b) return false;
+    return true;
+  }
+
+ private:
+  void loop(int t) {
+    long long seen = 0;
+    for (;;) {
+      const int32_t* src; uint16_t* dst; size_t n;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        if (stop_) return;
+        seen = gen_; src = src_; dst = dst_; n = n_;
+      }
+      const size_t a = (n * (size_t)t / (size_t)nt_) & ~(size_t)15, b = t + 1 == nt_ ? n : ((n * (size_t)(t + 1) / (size_t)nt_) & ~(size_t)15);
+      bad_[(size_t)t] = narrow_range_u16(src + a, b - a, dst + a) ? 0 : 1;
+      bool last;
+      { std::lock_guard<std::mutex> lk(mu_); last = --pending_ == 0; }
+      if (last) done_.notify_one();
+    }
+  }
+  int nt_;
+  std::vector<int> bad_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const int32_t* src_ = nullptr;
+  uint16_t* dst_ = nullptr;
+  size_t n_ = 0;
+  int pending_ = 0;
+  long long gen_ = 0;
+  bool stop_ = false;
+};
 
 // ---------------------------------------------------------------------------------------------
 // Host -> device transfer of the caller's counts: its own host thread + copy stream, running ahead of the kernels.
@@ -323,7 +381,7 @@ class H2DFeeder {
     n_batches_ = (g1 - g0 + B - 1) / B;
     layouts_.resize((size_t)n_batches_);
     for (int i = 0; i < 2; ++i) {
-      CK(cudaEventCreateWithFlags(&ev_h2d_[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_h2d_[i], cudaEventDisableTiming | cudaEventBlockingSync));
       CK(cudaEventCreateWithFlags(&ev_free_[i], cudaEventDisableTiming));
       CK(cudaEventCreate(&ev_t0_[i]));
       CK(cudaEventCreate(&ev_t1_[i]));
@@ -367,7 +425,12 @@ class H2DFeeder {
   void run() {
     try {
       CK(cudaSetDevice(device_));
-      double r_n = 60e9, r_w = 52e9;                   // bytes of int32 per second: narrowing (all host threads), wire
+      double r_n = 75e9, r_w = 52e9;                   // bytes of int32 per second: narrowing (all host threads), wire
+      std::unique_ptr<NarrowPool> pool;
+      if (mode_ != DIRECT) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        pool.reset(new NarrowPool(hw == 0 ? 4 : (int)std::min<unsigned>(hw, 16)));
+      }
       bool had_direct[2] = {false, false};
       size_t direct_bytes[2] = {0, 0};
       for (int64_t k = 0; k < n_batches_; ++k) {
@@ -417,7 +480,7 @@ class H2DFeeder {
           for (size_t c0 = 0; c0 < n_el && fits; c0 += chunk) {
             const size_t c1 = std::min(n_el, c0 + chunk);
             const auto t0 = std::chrono::steady_clock::now();
-            fits = narrow_to_u16(src + c0, c1 - c0, h_stage_[buf] + c0);
+            fits = pool->run(src + c0, c1 - c0, h_stage_[buf] + c0);
             t_n += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             if (fits) {
               CK(cudaMemcpyAsync(dbase + c0 * 2, h_stage_[buf] + c0, (c1 - c0) * 2, cudaMemcpyHostToDevice, cs_));
@@ -655,6 +718,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr; A.exact = 0; A.pstart = nullptr;
     CompArgs CA;
     CA.order = nullptr;
+    CA.theta_nodes = 0;
     WgArgs WA;
     WA.on = D.on; WA.off_s = d_off_s; WA.off_q = d_off_q; WA.offg = d_offg; WA.counter = d_counters;
     auto wg_grid = [&](int n) { const int want = (n + kWgWarps - 1) / kWgWarps; return want < wg_slots ? want : wg_slots; };
@@ -750,7 +814,12 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       if (use_wg) {
         WA.C = CA; WA.counter = d_counters + 2;
         k_wg_stage<WG_FINAL><<<wg_grid(nb), kWgThreads, 0, s>>>(WA);
-      } else k_comp_stage<CSTAGE_FINAL><<<nb, kCompThreads, 0, s>>>(CA);
+      } else {
+        static std::once_flag tn_once[SCLANE_MAX_GPUS];
+        std::call_once(tn_once[device % SCLANE_MAX_GPUS], [] { CK(cudaFuncSetAttribute(k_comp_stage<CSTAGE_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ThetaNodes))); });
+        CA.theta_nodes = theta_nodes_enabled() ? 1 : 0;
+        k_comp_stage<CSTAGE_FINAL><<<nb, kCompThreads, CA.theta_nodes ? sizeof(ThetaNodes) : 0, s>>>(CA);
+      }
       CK(cudaGetLastError());
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_COMP_FINAL]++;
@@ -776,7 +845,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.d2h_bytes += (double)nb * sizeof(GeneOutDev);
     prof.launches[SCLANE_STAGE_COPY]++;
     tm.mark(-1);
-    CK(cudaStreamSynchronize(s));
+    if (h_counts) stream_wait_blocking(s); else CK(cudaStreamSynchronize(s));
     tm.collect(prof);
     // records: z / p-values, LRT, pchisq per gene (~1-2 us each) -- spread over host threads, chunk sums in chunk order
     {

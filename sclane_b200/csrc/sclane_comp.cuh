@@ -282,6 +282,79 @@ SC_HD void offnode_contrib(double n, double s, double q, double o, double a, dou
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// theta.ml on Chebyshev nodes (compressed route).
+//
+// MASS::theta.ml (glm.nb: once per alternation, restarted from the moment estimate every time) runs up to 25 Newton steps on
+// theta AT FIXED mu -- ~70 % of the passes of the final stage.  With mu fixed, both sums of a step are
+//     sum_d [ n_d A(eta_d; theta) + s_d B(eta_d; theta) ],   eta_d = a_b + c_b u_d  inside bucket b,
+// with A, B analytic in eta (singularities at Im eta = +-pi).  Per theta.ml call the points of every sloped bucket are
+// therefore condensed ONCE: the bucket's eta range is cut into bins of width <= kThBinWidth and inside a bin the integrand
+// is replaced by its degree-15 interpolant at the kOffJ = 16 Chebyshev nodes, which turns the point sums into node weights
+//     n_kj = sum_{d in bin k} n_d l_j(xi_d),   s_kj = sum s_d l_j(xi_d)
+// (Chebyshev moments of the points + a 16 x 16 cosine transform, as for the offset quadrature above).  A Newton step then
+// costs ~16 evaluations per bin (a few hundred per gene) instead of one per abscissa (up to 10,001).  Flat buckets are one
+// entry (their totals); buckets with too few points to gain keep their points.  Error: half-width 0.375 in eta, ellipse
+// through Im eta = pi/2: rho = 8.5, 4 rho^-16 / (rho - 1) ~ 7e-16 relative.  The layout is fixed by (a, c, the point
+// table) alone and every sum runs in a fixed order, so records stay bit-reproducible.
+// ---------------------------------------------------------------------------------------------
+constexpr int kThCap = 1024;             // node-list entries (shared memory: 3 doubles each)
+constexpr double kThBinWidth = 0.75;
+
+struct ThetaNodes {
+  int on;                                // 0: the list does not fit / would not pay -> theta passes walk the points
+  int n;                                 // entries
+  int first[NBMAX + 1];                  // first entry of bucket b
+  int bins[NBMAX + 1];                   // 0 = flat or empty bucket (one entry), -1 = the bucket's points as they are, K >= 1 = K bins
+  double ulo[NBMAX + 1], h[NBMAX + 1];   // binned buckets: smallest coordinate and bin width (in u)
+  double en[kThCap], es[kThCap], eeta[kThCap];
+};
+
+// Leader only.  ufirst / ulast: coordinate of the first / last point of bucket b (points are sorted inside a bucket).
+template <class UF>
+SC_HD void theta_nodes_layout(ThetaNodes& tn, int T, const double* c, const int* pbstart, UF u_of) {
+  int n = 0, saved = 0;
+  for (int b = 0; b <= T; ++b) {
+    const int p0 = pbstart[b], p1 = pbstart[b + 1], P = p1 - p0;
+    tn.first[b] = n;
+    if (c[b] == 0.0 || P <= 0) { tn.bins[b] = 0; n += 1; continue; }
+    const double u0 = u_of(b, p0), u1 = u_of(b, p1 - 1);
+    const double span = fabs(c[b]) * (u1 - u0);
+    int K = (int)ceil(span / kThBinWidth);
+    if (K < 1) K = 1;
+    if (!(span == span) || K > kThCap || 3 * K * kOffJ > 2 * P) { tn.bins[b] = -1; n += P; }       // not worth it: keep the points
+    else { tn.bins[b] = K; tn.ulo[b] = u0; tn.h[b] = (u1 - u0) / (double)K; n += K * kOffJ; saved += P - K * kOffJ; }
+    if (n > kThCap) { tn.on = 0; tn.n = 0; return; }
+  }
+  tn.n = n;
+  tn.on = (n <= kThCap && saved > 0) ? 1 : 0;
+}
+
+// One bin, serially (host twin of the warp-parallel build in sclane_comp_device.cuh): points [lo, hi) -> the bin's 16 entries.
+template <class UF>
+SC_HD void theta_nodes_bin_serial(ThetaNodes& tn, int b, int k, int lo, int hi, const double* pn, const double* s1, double a, double c,
+                                  const double (*ctab)[kOffJ], UF u_of) {
+  const double u0 = tn.ulo[b] + (double)k * tn.h[b], h = tn.h[b];
+  double cn[kOffJ], cs[kOffJ];
+  for (int m = 0; m < kOffJ; ++m) cn[m] = cs[m] = 0.0;
+  for (int d = lo; d < hi; ++d) {
+    double xi = h > 0.0 ? 2.0 * (u_of(b, d) - u0) / h - 1.0 : 0.0;
+    xi = xi < -1.0 ? -1.0 : (xi > 1.0 ? 1.0 : xi);
+    double t0 = 1.0, t1 = xi;
+    cn[0] += pn[d]; cs[0] += s1[d];
+    cn[1] += pn[d] * xi; cs[1] += s1[d] * xi;
+    for (int m = 2; m < kOffJ; ++m) { const double t2 = 2.0 * xi * t1 - t0; cn[m] += pn[d] * t2; cs[m] += s1[d] * t2; t0 = t1; t1 = t2; }
+  }
+  for (int j = 0; j < kOffJ; ++j) {
+    double sn = 0.0, ss = 0.0;
+    for (int m = kOffJ - 1; m >= 1; --m) { sn += ctab[m][j] * cn[m]; ss += ctab[m][j] * cs[m]; }
+    const int e = tn.first[b] + k * kOffJ + j;
+    tn.en[e] = (cn[0] + 2.0 * sn) / (double)kOffJ;
+    tn.es[e] = (cs[0] + 2.0 * ss) / (double)kOffJ;
+    tn.eeta[e] = a + c * (u0 + 0.5 * (ctab[1][j] + 1.0) * h);
+  }
+}
+
 // negative.binomial(theta = 1)$initialize start of glm.fit: per cell mu = y + (y == 0)/6, eta = log(mu), sigma = 1.
 // w = mu / (1 + mu), w z = w eta + (y - mu)/(1 + mu).
 SC_HD void start_cell(int yi, double& w, double& wz) {

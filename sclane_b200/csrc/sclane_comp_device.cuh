@@ -40,6 +40,7 @@ struct CompArgs {
   int compute_stats;
   double tols_score;
   const int* order;             // optional CTA -> gene map of the final stage (k_order_final), or nullptr
+  int theta_nodes;              // k_comp_stage<FINAL>: theta.ml on Chebyshev nodes (needs sizeof(ThetaNodes) bytes of dynamic shared memory)
   double* a0p;                  // optional [B][Dpad]: glm.fit start sums per point (sum w0, sum w0 z0) for the exact-knot kernels
   double* b0p;
 };
@@ -293,6 +294,76 @@ struct CompDevExec {
   double (*scw)[NSC];
   const FastTabs* ft;               // exp / log1p tables in shared memory (sclane_fastmath.cuh)
   const double* __restrict__ px;    // exact-knot mode: abscissa per point, u = px[d] - ref[bucket] (the buckets are per gene); else nullptr
+  ThetaNodes* tn;                   // theta.ml node list (shared memory; sclane_comp.cuh) or nullptr: theta passes walk the points
+  const double (*ctab)[kOffJ];      // T_m(xi_j) table (shared memory) when tn is set
+
+  __device__ __forceinline__ double u_of(int b, int d) const { return px ? px[d] - L->ref[b] : pu[d]; }
+
+  // theta.ml is about to iterate at the mean defined by W.a / W.c: condense the points into the node list (sclane_comp.cuh).
+  // Units (flat bucket / raw bucket / one bin) are dealt round-robin to the warps; a bin is built by one warp: lanes 0-15
+  // accumulate the Chebyshev moments of n, lanes 16-31 those of s (both halves walk all points of the bin, stride 16).
+  __device__ __noinline__ void theta_prepare() {
+    if (!tn) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int T = L->T;
+    __syncthreads();
+    if (threadIdx.x == 0) theta_nodes_layout(*tn, T, W->c, pbstart, [&](int b, int d) { return u_of(b, d); });
+    __syncthreads();
+    if (!tn->on) return;
+    int unit = 0;
+#pragma unroll 1
+    for (int b = 0; b <= T; ++b) {
+      const int kb = tn->bins[b], p0 = pbstart[b], p1 = pbstart[b + 1], e0 = tn->first[b];
+      const double a = W->a[b], c = W->c[b];
+      if (kb == 0) {
+        if ((unit++ & (kCompWarps - 1)) == warp && lane == 0) { tn->en[e0] = L->U0[b]; tn->es[e0] = cg->hdr.SB[b]; tn->eeta[e0] = a; }
+        continue;
+      }
+      if (kb < 0) {
+        if ((unit++ & (kCompWarps - 1)) == warp)
+          for (int d = p0 + lane; d < p1; d += 32) { const int e = e0 + (d - p0); tn->en[e] = pn[d]; tn->es[e] = s1[d]; tn->eeta[e] = a + c * u_of(b, d); }
+        continue;
+      }
+      const double h = tn->h[b], ulo = tn->ulo[b];
+#pragma unroll 1
+      for (int k = 0; k < kb; ++k) {
+        if ((unit++ & (kCompWarps - 1)) != warp) continue;
+        const double u0 = ulo + (double)k * h, u1 = ulo + (double)(k + 1) * h;
+        // point range of the bin: [first point with u >= u0, first point with u >= u1); the outer bins take the bucket's ends
+        int lo = p0, hi = p1;
+        if (k > 0) { int x = p0, y = p1; while (x < y) { const int m = (x + y) >> 1; if (u_of(b, m) < u0) x = m + 1; else y = m; } lo = x; }
+        if (k + 1 < kb) { int x = p0, y = p1; while (x < y) { const int m = (x + y) >> 1; if (u_of(b, m) < u1) x = m + 1; else y = m; } hi = x; }
+        const int half = lane >> 4, j = lane & 15;
+        const double* __restrict__ val = half ? s1 : pn;
+        const double sc2 = h > 0.0 ? 2.0 / h : 0.0;
+        double cm[kOffJ];
+#pragma unroll
+        for (int m = 0; m < kOffJ; ++m) cm[m] = 0.0;
+        for (int d = lo + j; d < hi; d += 16) {
+          const double v = val[d];
+          double xi = sc2 * (u_of(b, d) - u0) - 1.0;
+          xi = fmin(1.0, fmax(-1.0, xi));
+          double t0 = 1.0, t1 = xi;
+          cm[0] += v; cm[1] += v * xi;
+#pragma unroll
+          for (int m = 2; m < kOffJ; ++m) { const double t2 = 2.0 * xi * t1 - t0; cm[m] += v * t2; t0 = t1; t1 = t2; }
+        }
+#pragma unroll
+        for (int m = 0; m < kOffJ; ++m) {
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) cm[m] += __shfl_xor_sync(0xffffffffu, cm[m], o);
+        }
+        double sacc = 0.0;
+#pragma unroll
+        for (int m = kOffJ - 1; m >= 1; --m) sacc += ctab[m][j] * cm[m];
+        const double wgt = (cm[0] + 2.0 * sacc) * (1.0 / (double)kOffJ);
+        const int e = e0 + k * kOffJ + j;
+        if (half) tn->es[e] = wgt;
+        else { tn->en[e] = wgt; tn->eeta[e] = a + c * (u0 + 0.5 * (ctab[1][j] + 1.0) * h); }
+      }
+    }
+    __syncthreads();
+  }
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -343,8 +414,15 @@ struct CompDevExec {
 #pragma unroll
     for (int k = 0; k < NSC; ++k) sc[k] = 0.0;
     int n_sloped = 0;                               // running index among the non-flat buckets (warp-uniform)
+    const bool on_nodes = MODE == PASS_THETA && tn != nullptr && tn->on;     // block-uniform
+    if (on_nodes) {
+      const int ne = tn->n;
+      double dummy[1];
+      for (int e = threadIdx.x; e < ne; e += kCompThreads)
+        point_contrib<MODE>(tn->en[e], tn->es[e], 0.0, 0.0, tn->eeta[e], 0.0, sigma, theta, want_ll, ft, dummy, sc);
+    }
 #pragma unroll 1
-    for (int b = 0; b <= T; ++b) {
+    for (int b = 0; b <= (on_nodes ? -1 : T); ++b) {
       const double c = W->c[b];
       if (c == 0.0) {
         if ((b & (kCompWarps - 1)) != warp) continue;
@@ -424,9 +502,19 @@ __global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(C
   __shared__ double scw[kCompWarps][NSC];
   __shared__ FastTabs ftab;
   __shared__ TermTabs ttab;
+  __shared__ double ctab[STAGE == CSTAGE_FINAL ? kOffJ : 1][kOffJ];
+  extern __shared__ double comp_dyn_smem[];                // CSTAGE_FINAL: the theta.ml node list (sizeof(ThetaNodes) bytes)
   if ((int)blockIdx.x >= A.n_genes) return;
   const int g = ((STAGE == CSTAGE_FINAL || STAGE == CSTAGE_BACKWARD) && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
   if (A.cg[g].hdr.route == 0) return;                     // block-uniform: this gene takes the per-cell kernels
+  ThetaNodes* tn = (STAGE == CSTAGE_FINAL && A.theta_nodes) ? reinterpret_cast<ThetaNodes*>(comp_dyn_smem) : nullptr;
+  if (STAGE == CSTAGE_FINAL) {
+    for (int i = threadIdx.x; i < kOffJ * kOffJ; i += kCompThreads) {
+      const int m = i / kOffJ, j = i - m * kOffJ;
+      ctab[m][j] = cospi((double)(m * (2 * j + 1)) / (double)(2 * kOffJ));
+    }
+    if (tn && threadIdx.x == 0) { tn->on = 0; tn->n = 0; }
+  }
   {
     const int* src = reinterpret_cast<const int*>(A.lineage);
     int* dst = reinterpret_cast<int*>(&Ls);
@@ -450,7 +538,7 @@ __global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(C
   __syncthreads();
   const long long t_start = clock64();
   CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, pbs, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
-                 A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, scw, &ftab, nullptr};
+                 A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, scw, &ftab, nullptr, tn, ctab};
   if (STAGE == CSTAGE_FORWARD) {
     for (int it = 0; it < A.n_iter; ++it) {
       gene_forward_fit(ex, Ls, gs, st, W);

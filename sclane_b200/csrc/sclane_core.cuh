@@ -1156,12 +1156,20 @@ SC_HDN int glm_fit2(E& ex, const Lineage& L, const Model& m, const GeneStats& gs
   return it > kMaxitGlm ? kMaxitGlm : it;
 }
 
+// Executors that can condense the cells / points for the Newton steps of theta.ml (mu is fixed while theta.ml iterates)
+// implement theta_prepare(); for the others this is a no-op.
+template <class E>
+SC_HD auto theta_prepare_if(E& ex, int) -> decltype(ex.theta_prepare(), void()) { ex.theta_prepare(); }
+template <class E>
+SC_HD void theta_prepare_if(E&, long) {}
+
 // MASS::theta.ml(y, mu, n, limit = 25, eps = .Machine$double.eps^0.25).  mu is defined by the eta
 // parameters currently in W.a / W.c (+ offset).  Result: W.tm_theta, W.tm_info (-> SE), W.tm_notes.
 template <class E>
 SC_HDN void theta_ml(E& ex, const Lineage& L, Work& W, double t0sum) {
   const double eps = 1.220703125e-4;     // 2^-13 = .Machine$double.eps^0.25
   ex.sync();
+  theta_prepare_if(ex, 0);
   if (ex.leader()) {
     W.tm_theta = (double)L.N / t0sum;
     W.tm_info = nan("");

@@ -104,6 +104,33 @@ struct CompHostExec {
   void sync() const {}
   template <class F>
   void par_for(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
+  // theta.ml on Chebyshev nodes: serial twin of CompDevExec::theta_prepare (sclane_comp.cuh)
+  bool use_theta_nodes = true;
+  ThetaNodes tn;
+  long long theta_node_calls = 0, theta_node_entries = 0, theta_point_calls = 0;
+  void theta_prepare() {
+    tn.on = 0;
+    if (!use_theta_nodes || offnull) return;
+    static double ctab[kOffJ][kOffJ];
+    static bool have = false;
+    if (!have) { for (int m = 0; m < kOffJ; ++m) for (int j = 0; j < kOffJ; ++j) ctab[m][j] = std::cos(M_PI * (double)(m * (2 * j + 1)) / (double)(2 * kOffJ)); have = true; }
+    auto u_of = [&](int, int d) { return P->pu[(size_t)d]; };
+    theta_nodes_layout(tn, L->T, W->c, P->pbstart, u_of);
+    if (!tn.on) return;
+    for (int b = 0; b <= L->T; ++b) {
+      const int kb = tn.bins[b], p0 = P->pbstart[b], p1 = P->pbstart[b + 1], e0 = tn.first[b];
+      if (kb == 0) { tn.en[e0] = L->U0[b]; tn.es[e0] = H.SB[b]; tn.eeta[e0] = W->a[b]; continue; }
+      if (kb < 0) { for (int d = p0; d < p1; ++d) { const int e = e0 + (d - p0); tn.en[e] = P->pn[(size_t)d]; tn.es[e] = s1[(size_t)d]; tn.eeta[e] = W->a[b] + W->c[b] * P->pu[(size_t)d]; } continue; }
+      int lo = p0;
+      for (int k = 0; k < kb; ++k) {
+        const double u1 = tn.ulo[b] + (double)(k + 1) * tn.h[b];
+        int hi = p1;
+        if (k + 1 < kb) { hi = lo; while (hi < p1 && P->pu[(size_t)hi] < u1) ++hi; }
+        theta_nodes_bin_serial(tn, b, k, lo, hi, P->pn.data(), s1.data(), W->a[b], W->c[b], ctab, u_of);
+        lo = hi;
+      }
+    }
+  }
   void aggregate(const int32_t* y) {                       // y: sorted counts
     const int D = P->D;
     s1.assign((size_t)D, 0.0); q.assign((size_t)D, 0.0); a0.assign((size_t)D, 0.0); b0.assign((size_t)D, 0.0);
@@ -152,6 +179,15 @@ struct CompHostExec {
       return;
     }
     const bool want_ll = W->want_ll != 0;
+    if (MODE == PASS_THETA && tn.on) {
+      double dummy[NACC];
+      for (int e = 0; e < tn.n; ++e) point_contrib<MODE>(tn.en[e], tn.es[e], 0.0, 0.0, tn.eeta[e], 0.0, W->sigma, W->theta, want_ll, nullptr, dummy, W->sc);
+      for (int k = 0; k < hmax_; ++k) hist_contrib<MODE>(k, tail[(size_t)k], tail[(size_t)k + 1], W->sigma, W->theta, want_ll, W->sc);
+      for (int32_t v : big) big_contrib<MODE>(v, W->sigma, W->theta, want_ll, W->sc);
+      theta_node_calls++; theta_node_entries += tn.n;
+      return;
+    }
+    if (MODE == PASS_THETA) { bool sloped = false; for (int b = 0; b <= L->T; ++b) sloped = sloped || W->c[b] != 0.0; if (sloped) theta_point_calls++; }
     for (int b = 0; b <= L->T; ++b) {
       if (W->c[b] == 0.0) {
         flat_bucket_contrib<MODE>(L->U0[b], L->U1[b], L->U2[b], H.SB[b], H.SBu[b], H.SBuu[b], H.QB[b], W->a[b], W->sigma, W->theta, want_ll, nullptr, W->acc[b], W->sc);
@@ -212,6 +248,7 @@ extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t 
       // an offset (the routing the CUDA path uses)
       const bool comp = opts->force_per_cell != 1;
       CompHostExec cx{&W, &L, &P};
+      { const char* e = std::getenv("SCLANE_EMU_THETA_NODES"); cx.use_theta_nodes = !(e && e[0] == '0'); }
       if (comp) cx.aggregate(y.data());
       const bool use_comp = comp && cx.H.route;
       for (int it = 0; it < 4 && !go.st.fwd_done && !go.st.error; ++it) {
@@ -235,6 +272,9 @@ extern "C" int emu_test_dynamic(const int32_t* counts, int64_t n_cells, int64_t 
       if (std::getenv("SCLANE_EMU_STAGES"))
         std::fprintf(stderr, "gene %ld passes fwd %d bwd %d final %d (alt: alt=%d irls=%d; null: alt=%d irls=%d)\n", (long)g, p_fwd, p_bwd - p_fwd,
                      W.passes - p_bwd, go.alt.alternations, go.alt.irls_iters, go.null.alternations, go.null.irls_iters);
+      if (std::getenv("SCLANE_EMU_STAGES"))
+        std::fprintf(stderr, "   theta passes on nodes %lld (mean entries %.1f of %d points), on points %lld\n", cx.theta_node_calls,
+                     cx.theta_node_calls ? (double)cx.theta_node_entries / (double)cx.theta_node_calls : 0.0, P.D, cx.theta_point_calls);
       go.st.passes = W.passes;
       finalize_record(go, L, out[g * n_lineages + l]);
     }
@@ -425,6 +465,17 @@ extern "C" double emu_digamma(double x) { return digamma_pos(x); }
 extern "C" double emu_trigamma(double x) { return trigamma_pos(x); }
 extern "C" void emu_psi_tri(int y, double th, double* out) { psi_tri_diff(y, th, out[0], out[1]); }
 extern "C" double emu_nb_lambda(int y, double sigma) { return nb_lambda(y, sigma, 1.0 / sigma); }
+// table-driven exp / log / log1p of the fit kernels (sclane_fastmath.cuh), vectorised over n arguments
+extern "C" void emu_fastmath(int which, const double* x, double* out, long n) {
+  static FastTabs ft;
+  static bool have = false;
+  if (!have) { fast_tabs_host(&ft); have = true; }
+  for (long i = 0; i < n; ++i) {
+    if (which == 0) out[i] = fast_exp(x[i], ft);
+    else if (which == 1) out[i] = fast_log_ge1(x[i], ft);
+    else { const double t = 1.0 + x[i]; out[i] = fast_log1p_pos(x[i], t, 1.0 / t, ft); }
+  }
+}
 extern "C" void emu_default_opts(sclane_opts* o) {
   std::memset(o, 0, sizeof(*o));
   o->abi_version = SCLANE_ABI_VERSION; o->mode = 0; o->M = 5; o->approx_knot = 1; o->n_knot_max = 25; o->minspan = -1; o->tols_score = 1e-5; o->gee_cor = SCLANE_COR_AR1;

@@ -2,6 +2,7 @@
 host-side K0 (knots / sort / buckets) agrees with the oracle, and the shared host/device algorithm core (run through
 the serial test executor in tests/host_emu) reproduces the oracle on the bundled data and on synthetic data."""
 import ctypes as C
+import os
 import re
 
 import numpy as np
@@ -127,3 +128,72 @@ def test_core_algorithm_vs_oracle_synthetic(emu):
     assert recs[3].status == 0 and (recs[3].marge_notes & 32)
     _compare([recs[i] for i in range(16) if i != 3], {g: oracle[g] for i, g in enumerate(genes) if i != 3},
              [g for i, g in enumerate(genes) if i != 3])
+
+
+def test_theta_ml_on_chebyshev_nodes_vs_points(emu, capfd):
+    """theta.ml at fixed mu on the condensed node list (sclane_comp.cuh: ThetaNodes) against the same Newton steps walked over
+    every abscissa: identical schedules (alternations, IRLS iterations) and statistics equal far below the 1e-6 parity bar."""
+    from tools import synth
+    counts, pt, _ = synth.make_counts(24, 20000, seed=11)
+    os.environ["SCLANE_EMU_STAGES"] = "1"
+    try:
+        os.environ["SCLANE_EMU_THETA_NODES"] = "1"
+        a, _ = emu.run(counts, pt)
+        err = capfd.readouterr().err
+        os.environ["SCLANE_EMU_THETA_NODES"] = "0"
+        b, _ = emu.run(counts, pt)
+    finally:
+        os.environ.pop("SCLANE_EMU_THETA_NODES", None)
+        os.environ.pop("SCLANE_EMU_STAGES", None)
+    capfd.readouterr()
+    on_nodes = sum(int(m) for m in re.findall(r"theta passes on nodes (\d+)", err))
+    on_points = sum(int(m) for m in re.findall(r"on points (\d+)", err))
+    entries = [float(m) for m in re.findall(r"mean entries ([0-9.]+)", err) if float(m) > 0]
+    assert on_nodes > 5 * max(on_points, 1) and np.mean(entries) < 1024, (on_nodes, on_points)
+    worst = 0.0
+    n_fit = 0
+    for ra, rb in zip(a, b):
+        assert ra.status == rb.status and ra.n_terms == rb.n_terms
+        assert ra.alternations == rb.alternations and ra.irls_iters == rb.irls_iters and ra.fit_passes == rb.fit_passes
+        if ra.status != 3:
+            continue
+        n_fit += 1
+        runaway = ra.theta > 1e3                 # theta.ml's likelihood is flat there: theta itself is ill-conditioned
+        for x, y in ((ra.loglik, rb.loglik), (ra.deviance, rb.deviance), (ra.test_stat, rb.test_stat)) + tuple(zip(ra.coef[:ra.n_terms], rb.coef[:rb.n_terms])):
+            worst = max(worst, rel(x, y, 1e-3))
+        if not runaway:
+            worst = max(worst, rel(ra.theta, rb.theta))
+    assert n_fit >= 12 and worst < 1e-9, (n_fit, worst)
+
+
+def test_fastmath_tables_vs_libm():
+    """sclane_fastmath.cuh (the exp / log / log1p every pass of the fit kernels evaluates) against numpy on 10^6 arguments each:
+    a few ulp at most inside the documented range, the documented values outside."""
+    import __graft_entry__ as ge
+    lib = C.CDLL(ge.EMU)
+    lib.emu_fastmath.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_long]
+
+    def call(which, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        lib.emu_fastmath(which, x.ctypes.data, out.ctypes.data, x.size)
+        return out
+
+    rng = np.random.default_rng(5)
+    with np.errstate(over="ignore", under="ignore"):
+        x = np.concatenate([rng.uniform(-700.0, 700.0, 500000), rng.normal(0.0, 3.0, 500000), [0.0, -0.0, 1e-300, -1e-300, 700.0, -700.0]])
+        got, ref = call(0, x), np.exp(x)
+        ulp = np.abs(got - ref) / np.spacing(ref)
+        assert ulp.max() <= 2.0, ulp.max()
+        # the contract outside +-700 (a mean above 1e304 is a diverged fit either way): +inf / 0, NaN propagates
+        sp = call(0, np.array([np.inf, -np.inf, 700.5, -700.5, np.nan]))
+        assert sp[0] == np.inf and sp[1] == 0.0 and sp[2] == np.inf and sp[3] == 0.0 and np.isnan(sp[4])
+        t = np.concatenate([1.0 + rng.exponential(1.0, 400000), np.exp(rng.uniform(0.0, 690.0, 400000)), 1.0 + rng.uniform(0.0, 1e-6, 200000), [1.0]])
+        got, ref = call(1, t), np.log(t)
+        err = np.abs(got - ref) / np.maximum(np.spacing(ref), np.spacing(1.0) * 0.5 * np.abs(t - 1.0))
+        assert err.max() <= 4.0, err.max()
+        v = np.concatenate([np.exp(rng.uniform(-40.0, 40.0, 900000)), rng.uniform(0.0, 1e-8, 100000), [0.0]])
+        got, ref = call(2, v), np.log1p(v)
+        # log1p(x) computed from t = 1 + x as the kernels have it: the rounding of t is part of the contract for tiny x
+        tol = np.maximum(4.0 * np.spacing(ref), 1.5 * np.spacing(1.0) * np.minimum(1.0, ref + 1e-300) / np.maximum(v, 1e-300) * ref)
+        assert np.all(np.abs(got - ref) <= tol), float(np.max(np.abs(got - ref) / np.maximum(ref, 1e-300)))
