@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SCLANE_ABI_VERSION 3
+#define SCLANE_ABI_VERSION 4
 #define SCLANE_PMAX 7          /* max columns of a model (intercept + hinges): M <= 7 (marge2.R:756) */
 #define SCLANE_TMAX 32         /* max candidate knots per lineage (n.knot.max, marge2.R:66; default 25) */
 #define SCLANE_MAX_GPUS 16
@@ -104,6 +104,9 @@ typedef struct sclane_opts {
   int32_t basis_only;         /* 1 = stop after the backward pass and return the selected basis only (marge2(is.glmm = TRUE),
                                  marge2.R:871-879): records carry n_terms / term_* and SCLANE_MARGE_OK, every fitted quantity is NaN.
                                  Set by sclane_marge_basis(). */
+  int32_t host_plan;          /* testing / profiling only: 1 = build the per-lineage plan (K0: sort, candidate knots, bucket and
+                                 abscissa tables) on the host.  Default 0: on the device whenever it can be (approx_knot = 1, no
+                                 size factors, GLM mode, pseudotime range that fits a 24-bit radix key) -- bit-identical tables */
 } sclane_opts;
 
 /* One record per (gene, lineage): everything testDynamic() returns for that pair except the
@@ -183,7 +186,7 @@ void sclane_reset_launch_count(void);
 
 /* Device-side timing of the last sclane_test_dynamic*() call on this process (CUDA events on the
  * library's own stream, summed over batches / lineages / GPUs): what bench.py's roofline uses. */
-#define SCLANE_NSTAGES 14
+#define SCLANE_NSTAGES 15
 #define SCLANE_STAGE_GATHER 0      /* sort permutation + per-gene constants                                  */
 #define SCLANE_STAGE_FWD_FIT 1     /* K1 forward null fits (stat_out_score_glm_null)                         */
 #define SCLANE_STAGE_SWEEP 2       /* K2a score sweep, streaming kernel k_sweep_moments (HBM bound)          */
@@ -198,6 +201,7 @@ void sclane_reset_launch_count(void);
 #define SCLANE_STAGE_COMP_FINAL 11 /* X-compressed final + null glm.nb (no offset)                            */
 #define SCLANE_STAGE_OFF_AGG 12    /* offset quadrature: per-gene node weights (k_off_aggregate)               */
 #define SCLANE_STAGE_OFF_NULL 13   /* offset quadrature: intercept-only glm.nb with the size-factor offset     */
+#define SCLANE_STAGE_PLAN 14       /* K0 on the device: sort by round(x, 4), candidate knots, bucket / abscissa tables */
 typedef struct sclane_profile {
   double  ms[SCLANE_NSTAGES];          /* device milliseconds per stage                                   */
   int64_t launches[SCLANE_NSTAGES];    /* kernel launches (memcpys for SCLANE_STAGE_COPY) per stage        */
@@ -292,6 +296,18 @@ int32_t sclane_test_dynamic_gee(const int32_t* counts, int64_t n_cells, int64_t 
  * or a negative error code. */
 int32_t sclane_candidate_knots(const double* x, int64_t n, const sclane_opts* opts,
                                double* knots_out, int32_t* minspan_out);
+
+/* K0 in full: the per-lineage plan every gene of the lineage shares (marge2.R:150-166 + the sort, bucket and abscissa tables
+ * of DESIGN.md section 2), built on the HOST (on_device = 0; no GPU needed) or by the device kernels of the batch path
+ * (on_device = 1; SCLANE_ERR_UNSUPPORTED when the input is one the batch path would hand to the host: size factors,
+ * approx_knot = 0, a pseudotime range beyond the radix key).  pt: n_cells doubles, NaN = not in the lineage.  Outputs (any may
+ * be NULL): perm [N] sorted position -> cell; u [N] bucket-local coordinate; knots [T]; bstart [T + 2]; U [3 (T + 1)] =
+ * U0 | U1 | U2; pstart [D + 1]; pn, pu [D]; pb [D]; pbstart [T + 2]; dims = {N, T, D, minspan}.  Arrays must hold n_cells + 1
+ * entries (perm, u, pstart, pn, pu, pb) resp. SCLANE_TMAX + 2 / 3 (SCLANE_TMAX + 1).  The two builds are bit-identical
+ * (tests/test_parity_r02.py). */
+int32_t sclane_lineage_plan(const double* pt, int64_t n_cells, const sclane_opts* opts, int32_t on_device, int32_t device,
+                            int32_t* perm, double* u, double* knots, int32_t* bstart, double* U, int32_t* pstart, double* pn,
+                            double* pu, uint8_t* pb, int32_t* pbstart, int32_t* dims, char* errbuf, size_t errlen);
 
 /* ---------------------------------------------------------------------------------------
  * Single-step entry points used by the unit tests (and by an R-side marge2() wrapper).

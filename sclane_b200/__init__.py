@@ -9,13 +9,13 @@ lib()  # fail loudly at import time when the CUDA library has not been built
 
 from .api import (  # noqa: E402
     ScLANE, candidate_knots, createCellOffset, device_count, eigenMapMatMult, eigenMapMatrixInvert,
-    eigenMapPseudoInverse, get_profile, getFittedValues, glmmKnots, getResultsDE, launch_count, link_preds, marge2, modelLRT,
+    eigenMapPseudoInverse, get_profile, getFittedValues, glmmKnots, getResultsDE, launch_count, lineage_plan, link_preds, marge2, modelLRT,
     release, reset_launch_count, run_records, score_fun_glm_sweep, smoothedCountsMatrix, stat_out_score_glm_null, testDynamic,
     testSlope,
 )
 
 __all__ = [
     "LIB_PATH", "SclaneError", "ScLANE", "candidate_knots", "createCellOffset", "device_count", "eigenMapMatMult",
-    "eigenMapMatrixInvert", "eigenMapPseudoInverse", "get_profile", "getFittedValues", "glmmKnots", "getResultsDE", "launch_count", "link_preds", "marge2",
+    "eigenMapMatrixInvert", "eigenMapPseudoInverse", "get_profile", "getFittedValues", "glmmKnots", "getResultsDE", "launch_count", "lineage_plan", "link_preds", "marge2",
     "modelLRT", "release", "reset_launch_count", "run_records", "score_fun_glm_sweep", "smoothedCountsMatrix", "stat_out_score_glm_null", "testDynamic", "testSlope",
 ]

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-SCLANE_ABI_VERSION = 3
+SCLANE_ABI_VERSION = 4
 SCLANE_PMAX = 7
 SCLANE_TMAX = 32
 SCLANE_MAX_GPUS = 16
@@ -49,6 +49,7 @@ class SclaneOpts(C.Structure):
         ("comp_warp_per_gene", C.c_int32),
         ("offset_per_cell", C.c_int32),
         ("basis_only", C.c_int32),
+        ("host_plan", C.c_int32),
     ]
 
 
@@ -122,7 +123,7 @@ class SclaneLineageInfo(C.Structure):
 EXPORTED_SYMBOLS = [
     "sclane_abi_version", "sclane_device_count", "sclane_default_opts", "sclane_record_size",
     "sclane_launch_count", "sclane_reset_launch_count", "sclane_get_profile", "sclane_release",
-    "sclane_test_dynamic", "sclane_test_dynamic_device", "sclane_test_dynamic_gee", "sclane_test_dynamic_csc", "sclane_marge_basis", "sclane_candidate_knots",
+    "sclane_test_dynamic", "sclane_test_dynamic_device", "sclane_test_dynamic_gee", "sclane_test_dynamic_csc", "sclane_marge_basis", "sclane_candidate_knots", "sclane_lineage_plan",
     "sclane_null_stats_glm", "sclane_score_glm", "sclane_link_preds", "sclane_smoothed_counts",
     "sclane_matmul", "sclane_llt_inverse", "sclane_pinv",
 ]

@@ -54,6 +54,8 @@ def lib() -> C.CDLL:
     L.sclane_test_dynamic_device.restype = i32
     L.sclane_candidate_knots.argtypes = [p, i64, C.POINTER(_abi.SclaneOpts), p, p]
     L.sclane_candidate_knots.restype = i32
+    L.sclane_lineage_plan.argtypes = [p, i64, C.POINTER(_abi.SclaneOpts), i32, i32, p, p, p, p, p, p, p, p, p, p, p, *err]
+    L.sclane_lineage_plan.restype = i32
     L.sclane_null_stats_glm.argtypes = [p, i64, i64, p, p, i32, p, p, i32, i32, p, p, p, *err]
     L.sclane_null_stats_glm.restype = i32
     L.sclane_score_glm.argtypes = [p, p, i64, i64, p, p, i32, p, p, i32, p, i32, p, *err]

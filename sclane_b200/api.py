@@ -154,13 +154,13 @@ def release() -> None:
 
 
 class _Profile(C.Structure):
-    _fields_ = [("ms", C.c_double * 14), ("launches", C.c_int64 * 14), ("sweep_bytes", C.c_double),
+    _fields_ = [("ms", C.c_double * 15), ("launches", C.c_int64 * 15), ("sweep_bytes", C.c_double),
                 ("sweep_gene_iters", C.c_int64), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double),
                 ("wall_ms", C.c_double)]
 
 
 STAGE_NAMES = ["gather", "fwd_fit", "sweep", "backward", "final", "copy", "select", "gee", "aggregate", "comp_forward",
-               "comp_backward", "comp_final", "off_aggregate", "off_null"]
+               "comp_backward", "comp_final", "off_aggregate", "off_null", "plan"]
 
 
 def get_profile() -> dict:
@@ -174,7 +174,7 @@ def get_profile() -> dict:
 
 def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None, tols_score=1e-5,
           n_gpus=0, gpu_ids=None, genes_per_batch=0, verbose=False, force_per_cell=False, h2d_mode=0,
-          comp_warp_per_gene=False, offset_per_cell=False) -> _abi.SclaneOpts:
+          comp_warp_per_gene=False, offset_per_cell=False, host_plan=False) -> _abi.SclaneOpts:
     o = _abi.default_opts()
     o.M = int(n_potential_basis_fns)
     o.approx_knot = 1 if approx_knot else 0
@@ -195,7 +195,37 @@ def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None
     o.h2d_mode = int(h2d_mode)
     o.comp_warp_per_gene = 1 if comp_warp_per_gene else 0
     o.offset_per_cell = 1 if offset_per_cell else 0
+    o.host_plan = 1 if host_plan else 0
     return o
+
+
+def lineage_plan(pt, opts: _abi.SclaneOpts | None = None, on_device: bool = False, device: int = 0) -> dict:
+    """sclane_lineage_plan: K0 (sort by round(x, 4), candidate knots of marge2.R:150-166, bucket and abscissa tables) for one
+    pseudotime column (NaN = not in the lineage), built on the host or by the device kernels of the batch path."""
+    x = np.ascontiguousarray(pt, dtype=np.float64).reshape(-1)
+    n = x.shape[0]
+    if opts is None:
+        opts = _opts()
+    T2 = _abi.SCLANE_TMAX + 2
+    perm = np.zeros(n + 1, dtype=np.int32); u = np.zeros(n + 1); knots = np.zeros(T2); bstart = np.zeros(T2, dtype=np.int32)
+    U = np.zeros(3 * (T2 - 1)); pstart = np.zeros(n + 1, dtype=np.int32); pn = np.zeros(n + 1); pu = np.zeros(n + 1)
+    pb = np.zeros(n + 1, dtype=np.uint8); pbstart = np.zeros(T2, dtype=np.int32); dims = np.zeros(4, dtype=np.int32)
+    err = C.create_string_buffer(_ERRLEN)
+    rc = lib().sclane_lineage_plan(x.ctypes.data, n, C.byref(opts), 1 if on_device else 0, int(device), perm.ctypes.data, u.ctypes.data,
+                                   knots.ctypes.data, bstart.ctypes.data, U.ctypes.data, pstart.ctypes.data, pn.ctypes.data, pu.ctypes.data,
+                                   pb.ctypes.data, pbstart.ctypes.data, dims.ctypes.data, err, _ERRLEN)
+    if rc != 0:
+        raise SclaneError(rc, err.value.decode(errors="replace"))
+    N, T, D, minspan = (int(v) for v in dims)
+    return {"N": N, "T": T, "D": D, "minspan": minspan, "perm": perm[:N], "u": u[:N], "knots": knots[:T], "bstart": bstart[:T + 2],
+            "U": U[:3 * (T + 1)].reshape(3, T + 1), "pstart": pstart[:D + 1], "pn": pn[:D], "pu": pu[:D], "pb": pb[:D], "pbstart": pbstart[:T + 2]}
+
+
+def _alloc_records(n: int):
+    """Record array for the library to fill: uninitialised memory (the library writes every byte of every record; a zeroed
+    ctypes array of 20,000 records costs ~8 ms of page faults and memset on the calling thread before the call even starts)."""
+    buf = np.empty(max(1, n) * C.sizeof(_abi.SclaneRecord), dtype=np.uint8)
+    return (_abi.SclaneRecord * n).from_buffer(buf)
 
 
 def _is_sparse(m) -> bool:
@@ -233,7 +263,7 @@ def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = Non
         indptr = np.ascontiguousarray(csc.indptr, dtype=np.int32)
         indices = np.ascontiguousarray(csc.indices, dtype=np.int32)
         data = np.ascontiguousarray(csc.data, dtype=np.float64)
-        recs = (_abi.SclaneRecord * (n_genes * n_lin))()
+        recs = _alloc_records(n_genes * n_lin)
         infos = (_abi.SclaneLineageInfo * n_lin)()
         rc = L.sclane_test_dynamic_csc(indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, n_cells, n_genes, pt_cm.ctypes.data,
                                        n_lin, None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
@@ -242,7 +272,7 @@ def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = Non
         if counts.ndim != 2 or counts.shape[1] != n_cells:
             raise ValueError("expr.mat must be genes x cells with one column per row of pt")
         n_genes = counts.shape[0]
-        recs = (_abi.SclaneRecord * (n_genes * n_lin))()
+        recs = _alloc_records(n_genes * n_lin)
         infos = (_abi.SclaneLineageInfo * n_lin)()
         if subject_id is not None:
             sid = np.ascontiguousarray(subject_id, dtype=np.int32)
@@ -257,7 +287,7 @@ def run_records(counts, pt, size_factor=None, opts: _abi.SclaneOpts | None = Non
                                        None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)
     else:
         n_genes = int(counts)  # when a device pointer is given, `counts` is the number of genes
-        recs = (_abi.SclaneRecord * (n_genes * n_lin))()
+        recs = _alloc_records(n_genes * n_lin)
         infos = (_abi.SclaneLineageInfo * n_lin)()
         rc = L.sclane_test_dynamic_device(C.c_void_p(device_ptr), device, n_cells, n_genes, pt_cm.ctypes.data, n_lin,
                                           None if sf is None else sf.ctypes.data, C.byref(opts), recs, infos, err, _ERRLEN)

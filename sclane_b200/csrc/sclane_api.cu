@@ -19,6 +19,7 @@
 #include "sclane_exact_device.cuh"
 #include "sclane_device.cuh"
 #include "sclane_gee_device.cuh"
+#include "sclane_k0_device.cuh"
 #include "sclane_gee_host.hpp"
 #include "sclane_host.hpp"
 
@@ -44,6 +45,18 @@ void set_err(char* errbuf, size_t errlen, const char* fmt, ...) {
   vsnprintf(errbuf, errlen, fmt, ap);
   va_end(ap);
 }
+
+// SCLANE_TRACE=1: host-side timestamps (ms since the start of the call) of the phases of a batch call, on stderr
+struct Trace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  Trace() : on([] { const char* e = std::getenv("SCLANE_TRACE"); return e && e[0] == '1'; }()), t0(std::chrono::steady_clock::now()) {}
+  void start() { t0 = std::chrono::steady_clock::now(); }
+  void at(const char* what) const {
+    if (on) fprintf(stderr, "[sclane trace] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+  }
+};
+Trace g_trace;
 
 struct CudaFail {
   std::string msg;
@@ -181,6 +194,64 @@ void stream_wait_blocking(cudaStream_t s) {
   CK(r);
 }
 
+
+// ---- K0 on the device (sclane_k0_device.cuh) ---------------------------------------------------------------------------
+// What the host decides up front from one scan of the pseudotime column (all of it depends on N and the range only).
+struct K0Host {
+  bool eligible = false;
+  int N = 0;
+  double xmin = 0.0, xmax = 0.0;
+  long long key0 = 0;
+  int passes = 0;                 // 8-bit radix passes that cover the key range
+  int minspan = 0, maxspan = 0;
+  K0Quant Q;
+};
+
+K0Host k0_prescan(const double* pt_col, int64_t n_cells, const sclane_opts& o, bool has_size_factor) {
+  K0Host H;
+  std::memset(&H.Q, 0, sizeof(H.Q));
+  if (o.host_plan || !o.approx_knot || has_size_factor || o.mode != 0 || n_cells > (int64_t)(1 << 30)) return H;
+  {
+    static const bool env_host = [] { const char* e = std::getenv("SCLANE_HOST_PLAN"); return e && e[0] == '1'; }();
+    if (env_host) return H;
+  }
+  int64_t N = 0;
+  double lo = std::numeric_limits<double>::infinity(), hi = -lo;
+  for (int64_t i = 0; i < n_cells; ++i) {
+    const double v = pt_col[i];
+    if (v == v) { ++N; if (v < lo) lo = v; if (v > hi) hi = v; }
+  }
+  if (N < 30) return H;                                   // the host plan reports the error
+  const double Xlo = r_round(lo, 1e4), Xhi = r_round(hi, 1e4);
+  if (!(std::isfinite(Xlo) && std::isfinite(Xhi) && std::fabs(Xlo) < 1e8 && std::fabs(Xhi) < 1e8)) return H;
+  const long long k0 = std::llround(Xlo * 1e4);
+  const long long R = std::llround(Xhi * 1e4) - k0 + 1;
+  if (R < 1 || R > (1ll << 24)) return H;
+  int bits = 0;
+  while ((1ll << bits) < R) ++bits;
+  H.passes = bits <= 8 ? 1 : (bits <= 16 ? 2 : 3);
+  int minspan = o.minspan;                                // min_span.R:24-26 with q = 1
+  if (minspan < 0) minspan = (int)std::nearbyint(-std::log2(-(1.0 / (1.0 * (double)N)) * std::log(1.0 - 0.05)) / 2.5);
+  if (minspan < 0 || minspan > (1 << 28)) return H;
+  H.minspan = minspan;
+  H.maxspan = (int)std::nearbyint(3.0 - std::log2(0.05 / 1.0));      // max_span.R:20 with q = 1
+  const double ps[2] = {0.05, 0.95};
+  for (int w = 0; w < 2; ++w) {                           // quantile7() of sclane_host.hpp
+    const double index = 1.0 + (double)(N - 1) * ps[w];
+    const double flo = std::floor(index), fhi = std::ceil(index);
+    H.Q.lo[w] = (int)flo;
+    H.Q.has_hi[w] = fhi > flo ? 1 : 0;
+    H.Q.above[w] = index > flo ? 1 : 0;
+    H.Q.h[w] = index - flo;
+    H.Q.one_minus_h[w] = 1.0 - H.Q.h[w];
+  }
+  H.N = (int)N; H.xmin = lo; H.xmax = hi; H.key0 = k0;
+  H.eligible = true;
+  return H;
+}
+
+struct DevicePlan;
+
 struct DevicePlan {
   int* perm = nullptr;
   double* u = nullptr;
@@ -245,6 +316,92 @@ struct DevicePlan {
     }
   }
 };
+
+// Runs K0 on `s`; on return (stream synchronised) D points at the device tables and hdr carries what the host needs
+// (Lineage, D, pbstart, minspan, pseudotime range).  Throws PlanFail when the lineage has no candidate knot.
+void device_k0(DevicePool& pool, cudaStream_t s, const double* pt_col, int64_t n_cells, const K0Host& H, const sclane_opts& o,
+               LineagePlan& hdr, DevicePlan& D, sclane_profile* prof) {
+  const int N = H.N, Npad = (N + 127) / 128 * 128;
+  const int nb_cells = (int)((n_cells + kK0Threads - 1) / kK0Threads), nb = (N + kK0Threads - 1) / kK0Threads, nb_pad = (Npad + kK0Threads - 1) / kK0Threads;
+  K0Args A;
+  std::memset(&A, 0, sizeof(A));
+  double* d_pt = (double*)pool.get("k0_pt", (size_t)n_cells * 8);
+  A.pt = d_pt; A.n_cells = (int)n_cells; A.N = N; A.Npad = Npad; A.key0 = H.key0; A.step = H.minspan + 1; A.maxspan = H.maxspan;
+  A.n_knot_max = o.n_knot_max; A.Q = H.Q;
+  A.blk = (int*)pool.get("k0_blk", ((size_t)nb_cells + 2) * 4);
+  A.cells = (int*)pool.get("k0_cells", (size_t)N * 4);
+  A.xc = (double*)pool.get("k0_xc", (size_t)N * 8);
+  A.Xc = (double*)pool.get("k0_Xc", (size_t)N * 8);
+  A.key[0] = (unsigned*)pool.get("k0_key0", (size_t)N * 4);
+  A.key[1] = (unsigned*)pool.get("k0_key1", (size_t)N * 4);
+  A.idx[0] = (int*)pool.get("k0_idx0", (size_t)N * 4);
+  A.idx[1] = (int*)pool.get("k0_idx1", (size_t)N * 4);
+  A.hist = (int*)pool.get("k0_hist", ((size_t)256 * (size_t)nb + 1) * 4);
+  A.Xs = (double*)pool.get("k0_Xs", (size_t)N * 8);
+  A.xs = (double*)pool.get("k0_xs", (size_t)N * 8);
+  A.qstat = (double*)pool.get("k0_qstat", 4 * 8);
+  A.scal = (int*)pool.get("k0_scal", 4 * 4);
+  A.perm = D.perm = (int*)pool.get("perm", (size_t)N * 4);
+  A.u = D.u = (double*)pool.get("u", (size_t)Npad * 8);
+  A.lin = D.lin = (Lineage*)pool.get("lineage", sizeof(Lineage));
+  A.pstart = D.pstart = (int*)pool.get("pstart", ((size_t)N + 1) * 4);
+  A.pn = D.pn = (double*)pool.get("pn", (size_t)N * 8);
+  A.pu = D.pu = (double*)pool.get("pu", (size_t)N * 8);
+  A.pb = D.pb = (unsigned char*)pool.get("pb", (size_t)N);
+  A.pbstart = D.pbstart = (int*)pool.get("pbstart", sizeof(int) * (NBMAX + 1));
+  D.off = nullptr;
+  A.res = (K0Result*)pool.get("k0_res", sizeof(K0Result));
+  K0Result* h_res = (K0Result*)pool.get("k0_res_h", sizeof(K0Result), true);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CK(cudaEventCreate(&e0));
+  struct EvGuard { cudaEvent_t& a; cudaEvent_t& b; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg{e0, e1};
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, s));
+  CK(cudaMemcpyAsync(d_pt, pt_col, (size_t)n_cells * 8, cudaMemcpyHostToDevice, s));
+  int launches = 0;
+  k0_valid_count<<<nb_cells, kK0Threads, 0, s>>>(A);
+  k0_scan<<<1, kK0Threads, 0, s>>>(A.blk, nb_cells);
+  k0_compact<<<nb_cells, kK0Threads, 0, s>>>(A);
+  launches += 3;
+  int cur = 0;
+  for (int p = 0; p < H.passes; ++p) {
+    k0_radix_hist<<<nb, kK0Threads, 0, s>>>(A.key[cur], N, 8 * p, nb, A.hist);
+    k0_scan<<<1, kK0Threads, 0, s>>>(A.hist, 256 * nb);
+    k0_radix_scatter<<<nb, kK0Threads, 0, s>>>(A.key[cur], A.idx[cur], A.key[cur ^ 1], A.idx[cur ^ 1], N, 8 * p, nb, A.hist);
+    cur ^= 1;
+    launches += 3;
+  }
+  A.key_s = A.key[cur]; A.idx_s = A.idx[cur];
+  k0_sorted<<<nb, kK0Threads, 0, s>>>(A);
+  k0_scan<<<1, kK0Threads, 0, s>>>(A.blk, nb);
+  k0_points<<<nb, kK0Threads, 0, s>>>(A, nb);
+  k0_quantile_stats<<<4, kK0Threads, 0, s>>>(A);
+  k0_knots<<<1, kK0Threads, 0, s>>>(A);
+  k0_bucket_moments<<<NBMAX, 256, 0, s>>>(A);
+  k0_fill<<<nb_pad, kK0Threads, 0, s>>>(A);
+  launches += 7;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h_res, A.res, sizeof(K0Result), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(e1, s));
+  CK(cudaStreamSynchronize(s));
+  g_launches.fetch_add(launches);
+  if (prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) prof->ms[SCLANE_STAGE_PLAN] += ms;
+    prof->launches[SCLANE_STAGE_PLAN] += launches;
+    prof->h2d_bytes += (double)n_cells * 8.0;
+    prof->d2h_bytes += (double)sizeof(K0Result);
+  }
+  hdr.L = h_res->L;
+  hdr.D = h_res->D;
+  for (int b = 0; b <= NBMAX; ++b) hdr.pbstart[b] = h_res->pbstart[b];
+  hdr.minspan = H.minspan;
+  hdr.pt_min = H.xmin; hdr.pt_max = H.xmax;
+  hdr.exact = false;
+  hdr.ON.on = 0;
+  hdr.error.clear();
+  if (hdr.L.T < 1) { hdr.error = "no candidate knots (pseudotime has too few distinct values)"; throw PlanFail{hdr.error}; }
+}
 
 template <int STAGE, bool HYB = false>
 void launch_stage(const StageArgs& A, cudaStream_t s) {
@@ -541,6 +698,12 @@ struct PlanSource {
     if (ready.valid() && !ready.get()) throw PlanFail{plan->error};
     return *plan;
   }
+  // K0 on the device (sclane_k0_device.cuh): every shard builds the tables on its own GPU; `header` receives the host-side
+  // summary (Lineage, D, ...) of the shard with publish set
+  const K0Host* k0 = nullptr;
+  const double* pt_col = nullptr;
+  LineagePlan* header = nullptr;
+  bool publish = false;
 };
 
 // Run genes [g0, g1) of one lineage on one device.  Exactly one of h_counts / d_counts is non-null;
@@ -548,7 +711,7 @@ struct PlanSource {
 void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int64_t n_cells, int64_t g0, int64_t g1,
                PlanSource& PS, const sclane_opts& o, bool use_offset, sclane_record* out, int64_t out_g0, int n_lineages,
                int lin_idx, sclane_profile& prof) {
-  if (g1 <= g0) { PS.get(); return; }
+  if (g1 <= g0) { if (!PS.k0) PS.get(); return; }
   CK(cudaSetDevice(device));
   DevicePool& pool = pool_for(device);
   if (!pool.stream) CK(cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking));
@@ -616,9 +779,21 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     start_feeder();                                 // the first batch travels while the plan is being built
   }
   const LineagePlan* Pp = nullptr;
-  Pp = &PS.get();                                   // (on failure the feeder's destructor drains the copy stream)
+  LineagePlan k0_hdr;                               // device-built plan: only the header lives on the host
+  DevicePlan D;
+  if (PS.k0) {
+    try { device_k0(pool, s, PS.pt_col, n_cells, *PS.k0, o, k0_hdr, D, &prof); }
+    catch (const PlanFail&) { if (PS.publish) { PS.header->L = k0_hdr.L; PS.header->error = k0_hdr.error; } throw; }
+    if (PS.publish) {
+      LineagePlan& Hd = *PS.header;
+      Hd.L = k0_hdr.L; Hd.D = k0_hdr.D; Hd.minspan = k0_hdr.minspan; Hd.pt_min = k0_hdr.pt_min; Hd.pt_max = k0_hdr.pt_max;
+      Hd.exact = false; Hd.error.clear();
+    }
+    Pp = &k0_hdr;
+  } else Pp = &PS.get();                            // (on failure the feeder's destructor drains the copy stream)
   const LineagePlan& P = *Pp;
   const Lineage& L = P.L;
+  g_trace.at("plan ready");
   // X-compressed path (sclane_comp.cuh): worth it when the 4-decimal rounding leaves clearly fewer abscissae than cells
   // approx.knot = FALSE always runs on the abscissae (its sweep is a scan over them; sclane_exact_device.cuh)
   const bool exact = P.exact;
@@ -633,9 +808,10 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       if (h_counts) start_feeder();
     }
   }
-  DevicePlan D;
-  D.upload(P, pool, s);
-  if (use_comp) D.upload_points(P, pool, s);
+  if (!PS.k0) {
+    D.upload(P, pool, s);
+    if (use_comp) D.upload_points(P, pool, s);
+  }
   if (exact) D.upload_exact(P, pool, s);
   if (exact && use_offset && !(P.ON.on && !o.offset_per_cell)) throw CudaFail{"approx.knot = FALSE with a size-factor offset needs the offset quadrature (offsets spanning more than e^32, or offset_per_cell set)"};
   // fits with an offset: intercept-only models through the offset quadrature (needs the histogram of k_aggregate)
@@ -845,7 +1021,9 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.d2h_bytes += (double)nb * sizeof(GeneOutDev);
     prof.launches[SCLANE_STAGE_COPY]++;
     tm.mark(-1);
+    g_trace.at("batch queued");
     if (h_counts) stream_wait_blocking(s); else CK(cudaStreamSynchronize(s));
+    g_trace.at("batch done on the device");
     tm.collect(prof);
     // records: z / p-values, LRT, pchisq per gene (~1-2 us each) -- spread over host threads, chunk sums in chunk order
     {
@@ -866,6 +1044,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       for (int c = 0; c < kPlanChunks; ++c) sw += sw_chunk[c];
       prof.sweep_gene_iters += sw;
       prof.sweep_bytes += 12.0 * (double)L.N * (double)sw;
+      g_trace.at("records finalised");
     }
     prof.sweep_bytes += 8.0 * (double)L.N * (double)n_iter;
   }
@@ -1099,6 +1278,7 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
   else { for (int i = 0; i < ndev; ++i) devs.push_back(i); }
   for (int d : devs) if (d < 0 || d >= ndev) { set_err(errbuf, errlen, "device id %d out of range (0..%d)", d, ndev - 1); return SCLANE_ERR_ARG; }
   const auto t_start = std::chrono::steady_clock::now();
+  g_trace.start();
   {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     std::memset(&g_prof, 0, sizeof(g_prof));
@@ -1130,8 +1310,12 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
   static std::vector<LineagePlan> plans;
   if (plans.size() < (size_t)n_lineages) plans.resize((size_t)n_lineages);
   std::vector<std::shared_future<bool>> plans_ready((size_t)n_lineages);
+  // ... unless the plan can be built on the device (K0 kernels, sclane_k0_device.cuh): then the host only scans the column once
+  std::vector<K0Host> k0s((size_t)n_lineages);
   for (int l = 0; l < n_lineages; ++l) {
     LineagePlan* Pl = &plans[(size_t)l];
+    if (!gee) k0s[(size_t)l] = k0_prescan(pt + (int64_t)l * n_cells, n_cells, *opts, size_factor != nullptr);
+    if (k0s[(size_t)l].eligible) { std::promise<bool> pr; pr.set_value(true); plans_ready[(size_t)l] = pr.get_future().share(); Pl->error.clear(); continue; }
     plans_ready[(size_t)l] = std::async(std::launch::async, [Pl, pt, l, n_cells, size_factor, opts]() {
       return build_lineage_plan(pt + (int64_t)l * n_cells, n_cells, size_factor, *opts, *Pl);
     }).share();
@@ -1161,6 +1345,7 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
           const int32_t* dc = csc ? shard_base[(size_t)di] - (ptrdiff_t)g0 * (ptrdiff_t)n_cells : d_counts;
           PlanSource PS;
           PS.plan = &P; PS.ready = plan_ready;
+          if (k0s[(size_t)l].eligible) { PS.k0 = &k0s[(size_t)l]; PS.pt_col = pt + (int64_t)l * n_cells; PS.header = &P; PS.publish = g0 == 0 && g1 > 0; }
           run_shard(devs[(size_t)di], h_counts, dc, n_cells, g0, g1, PS, *opts, size_factor != nullptr, out, 0, n_lineages, l, profs[(size_t)di]);
         }
       } catch (const PlanFail&) {
@@ -1182,7 +1367,7 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
       for (int di = 0; di < nd; ++di) tg.run(work, di);
       tg.join();
     }
-    if (!plan_ready.get()) { set_err(errbuf, errlen, "lineage %d: %s", l, P.error.c_str()); return SCLANE_ERR_ARG; }
+    if (!plan_ready.get() || (k0s[(size_t)l].eligible && !P.error.empty())) { set_err(errbuf, errlen, "lineage %d: %s", l, P.error.c_str()); return SCLANE_ERR_ARG; }
     if (lineages) {
       sclane_lineage_info& li = lineages[l];
       std::memset(&li, 0, sizeof(li));
@@ -1203,6 +1388,7 @@ int test_dynamic_impl(const int32_t* h_counts, const int32_t* d_counts, int devi
     }
   }
   const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+  g_trace.at("return");
   {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.wall_ms = wall;
@@ -1553,6 +1739,58 @@ int32_t sclane_candidate_knots(const double* x, int64_t n, const sclane_opts* op
   return (int32_t)k.size();
 }
 
+int32_t sclane_lineage_plan(const double* pt, int64_t n_cells, const sclane_opts* opts, int32_t on_device, int32_t device,
+                            int32_t* perm, double* u, double* knots, int32_t* bstart, double* U, int32_t* pstart, double* pn,
+                            double* pu, uint8_t* pb, int32_t* pbstart, int32_t* dims, char* errbuf, size_t errlen) {
+  if (int rc = check_opts(opts, errbuf, errlen)) return rc;
+  if (!pt || n_cells < 1 || n_cells > (int64_t)2000000000) { set_err(errbuf, errlen, "bad arguments"); return SCLANE_ERR_ARG; }
+  auto put_lineage = [&](const Lineage& L, int D, int minspan) {
+    const int T = L.T;
+    if (knots) for (int k = 0; k < T; ++k) knots[k] = L.knots[k];
+    if (bstart) for (int b = 0; b <= T + 1; ++b) bstart[b] = L.bstart[b];
+    if (U) for (int b = 0; b <= T; ++b) { U[b] = L.U0[b]; U[(T + 1) + b] = L.U1[b]; U[2 * (T + 1) + b] = L.U2[b]; }
+    if (dims) { dims[0] = L.N; dims[1] = T; dims[2] = D; dims[3] = minspan; }
+  };
+  if (!on_device) {
+    LineagePlan P;
+    if (!build_lineage_plan(pt, n_cells, nullptr, *opts, P)) { set_err(errbuf, errlen, "%s", P.error.c_str()); return SCLANE_ERR_ARG; }
+    const int N = P.L.N, D = P.D, T = P.L.T;
+    put_lineage(P.L, D, P.minspan);
+    if (perm) std::memcpy(perm, P.perm.data(), (size_t)N * 4);
+    if (u) std::memcpy(u, P.u.data(), (size_t)N * 8);
+    if (pstart) std::memcpy(pstart, P.pstart.data(), ((size_t)D + 1) * 4);
+    if (pn) std::memcpy(pn, P.pn.data(), (size_t)D * 8);
+    if (pu) std::memcpy(pu, P.pu.data(), (size_t)D * 8);
+    if (pb) std::memcpy(pb, P.pb.data(), (size_t)D);
+    if (pbstart) for (int b = 0; b <= T + 1; ++b) pbstart[b] = P.pbstart[b];
+    return SCLANE_OK;
+  }
+  const int ndev = usable_devices();
+  if (ndev <= 0) { set_err(errbuf, errlen, "no usable CUDA device (this library has no CPU fallback)"); return SCLANE_ERR_CUDA; }
+  if (device < 0 || device >= ndev) { set_err(errbuf, errlen, "device id %d out of range (0..%d)", device, ndev - 1); return SCLANE_ERR_ARG; }
+  const K0Host H = k0_prescan(pt, n_cells, *opts, false);
+  if (!H.eligible) { set_err(errbuf, errlen, "this input keeps the host plan (approx_knot = 0, host_plan set, fewer than 30 cells, or a pseudotime range beyond the radix key)"); return SCLANE_ERR_UNSUPPORTED; }
+  CK(cudaSetDevice(device));
+  DevicePool& pool = pool_for(device);
+  if (!pool.stream) CK(cudaStreamCreateWithFlags(&pool.stream, cudaStreamNonBlocking));
+  cudaStream_t s = pool.stream;
+  LineagePlan hdr;
+  DevicePlan D;
+  try { device_k0(pool, s, pt, n_cells, H, *opts, hdr, D, nullptr); }
+  catch (const PlanFail& f) { set_err(errbuf, errlen, "%s", f.msg.c_str()); return SCLANE_ERR_ARG; }
+  const int N = hdr.L.N, Dn = hdr.D, T = hdr.L.T;
+  put_lineage(hdr.L, Dn, hdr.minspan);
+  if (perm) CK(cudaMemcpyAsync(perm, D.perm, (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+  if (u) CK(cudaMemcpyAsync(u, D.u, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
+  if (pstart) CK(cudaMemcpyAsync(pstart, D.pstart, ((size_t)Dn + 1) * 4, cudaMemcpyDeviceToHost, s));
+  if (pn) CK(cudaMemcpyAsync(pn, D.pn, (size_t)Dn * 8, cudaMemcpyDeviceToHost, s));
+  if (pu) CK(cudaMemcpyAsync(pu, D.pu, (size_t)Dn * 8, cudaMemcpyDeviceToHost, s));
+  if (pb) CK(cudaMemcpyAsync(pb, D.pb, (size_t)Dn, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (pbstart) for (int b = 0; b <= T + 1; ++b) pbstart[b] = hdr.pbstart[b];
+  return SCLANE_OK;
+}
+
 int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* x, const double* knots,
                               int32_t n_knots, const int32_t* term_kind, const int32_t* term_knot_idx, int32_t n_terms,
                               int32_t device, double* beta_out, double* sigma_out, double* mu_out, char* errbuf, size_t errlen) {
@@ -1835,6 +2073,13 @@ int32_t sclane_candidate_knots(const double* x, int64_t n, const sclane_opts* op
   try { return impl::sclane_candidate_knots(x, n, opts, knots_out, minspan_out); }
   catch (const std::bad_alloc&) { return -SCLANE_ERR_NOMEM; }
   catch (...) { return -SCLANE_ERR_INTERNAL; }
+}
+int32_t sclane_lineage_plan(const double* pt, int64_t n_cells, const sclane_opts* opts, int32_t on_device, int32_t device,
+                            int32_t* perm, double* u, double* knots, int32_t* bstart, double* U, int32_t* pstart, double* pn,
+                            double* pu, uint8_t* pb, int32_t* pbstart, int32_t* dims, char* errbuf, size_t errlen) {
+  return guarded(errbuf, errlen, [&]() -> int32_t {
+    return impl::sclane_lineage_plan(pt, n_cells, opts, on_device, device, perm, u, knots, bstart, U, pstart, pn, pu, pb, pbstart, dims, errbuf, errlen);
+  });
 }
 int32_t sclane_null_stats_glm(const int32_t* counts, int64_t n_cells, int64_t n_genes, const double* x, const double* knots,
                               int32_t n_knots, const int32_t* term_kind, const int32_t* term_knot_idx, int32_t n_terms,

@@ -362,3 +362,68 @@ def test_approx_knot_false_with_offsets_vs_oracle():
         o = ref[g]["Lineage_A"]
         if o["LogLik_Null"] == o["LogLik_Null"]:
             assert rel(res.records[i].null_loglik, o["LogLik_Null"]) < TOL and rel(res.records[i].null_deviance, o["Dev_Null"]) < TOL, g
+
+
+def _plan_cases():
+    rng = np.random.default_rng(20)
+    cases = []
+    cases.append(("uniform 200k", rng.uniform(0, 1, 200000), {}))
+    cases.append(("uniform 10k", rng.uniform(0, 1, 10000), {}))
+    x = rng.uniform(0, 1, 30000)
+    x[rng.uniform(size=x.size) < 0.4] = np.nan
+    cases.append(("40 % of the cells outside the lineage", x, {}))
+    cases.append(("two-decimal pseudotime (101 abscissae)", np.round(rng.uniform(0, 1, 20000), 2), {}))
+    cases.append(("41 abscissae, fewer candidates than n.knot.max", rng.integers(0, 41, 5000) / 40.0, {}))
+    cases.append(("minspan given", rng.beta(2, 5, 15000), {"minspan": 5}))
+    cases.append(("n.knot.max 10", rng.beta(0.5, 0.5, 15000), {"n_knot_max": 10}))
+    cases.append(("n.knot.max 32", rng.uniform(0, 1, 4000), {"n_knot_max": 32}))
+    cases.append(("pseudotime in [0, 37.5]: three radix passes", rng.uniform(0, 37.5, 120000), {}))
+    cases.append(("negative pseudotime", rng.normal(0, 0.3, 25000), {}))
+    cases.append(("35 cells", rng.uniform(0, 1, 35), {}))
+    return cases
+
+
+@pytest.mark.parametrize("case", _plan_cases(), ids=lambda c: c[0])
+def test_device_plan_bit_identical(case):
+    """K0 on the device (sclane_k0_device.cuh) against the host plan (sclane_host.hpp, itself == the oracle's knots in
+    tests/test_host_logic.py): every table -- sort permutation, knots, bucket table, coordinates, unweighted moments, abscissa
+    tables -- bit for bit (marge2.R:150-166, min_span.R:24-34, max_span.R:20-25)."""
+    from sclane_b200 import api
+    _, x, kw = case
+    o = api._opts(**kw)
+    host = api.lineage_plan(x, o, on_device=False)
+    dev = api.lineage_plan(x, o, on_device=True)
+    for k in ("N", "T", "D", "minspan"):
+        assert host[k] == dev[k], k
+    assert host["T"] >= 1
+    for k in ("perm", "u", "knots", "bstart", "U", "pstart", "pn", "pu", "pb", "pbstart"):
+        a, b = np.ascontiguousarray(host[k]), np.ascontiguousarray(dev[k])
+        assert a.shape == b.shape and a.tobytes() == b.tobytes(), k
+
+
+def test_device_plan_records_equal_host_plan_records():
+    """The batch path with K0 on the device (default) and with opts.host_plan = 1: records byte for byte; inputs the device
+    plan does not take (size factors, approx.knot = FALSE) keep the host plan."""
+    import sclane_b200 as sb
+    from sclane_b200 import api
+    from test_gpu_parity import _rec_bytes
+    from tools import synth
+    counts, pt, _ = synth.make_counts(160, 20000, seed=9)
+    pt2 = np.stack([pt.reshape(-1), np.where(np.arange(20000) % 3 == 0, np.nan, pt.reshape(-1) ** 2)], axis=1)
+    a, ia = api.run_records(counts, pt2, None, api._opts(gpu_ids=[0]))
+    assert sb.get_profile()["launches"]["plan"] > 0 and sb.get_profile()["ms"]["plan"] > 0
+    b, ib = api.run_records(counts, pt2, None, api._opts(gpu_ids=[0], host_plan=True))
+    assert sb.get_profile()["launches"]["plan"] == 0
+    for ra, rb in zip(a, b):
+        assert _rec_bytes(ra) == _rec_bytes(rb)
+    for la, lb in zip(ia, ib):
+        assert bytes(la) == bytes(lb)
+    sf = np.exp(np.random.default_rng(1).normal(0, 0.3, 20000))
+    api.run_records(counts[:16], pt2, sf, api._opts(gpu_ids=[0]))
+    assert sb.get_profile()["launches"]["plan"] == 0
+    with pytest.raises(sb.SclaneError):
+        api.lineage_plan(pt2[:, 0], api._opts(approx_knot=False), on_device=True)
+    with pytest.raises(sb.SclaneError):                         # a lineage without candidate knots is an argument error on both builds
+        api.run_records(counts[:4, :200], np.repeat([0.25, 0.5], 100), None, api._opts(gpu_ids=[0]))
+    with pytest.raises(sb.SclaneError):
+        api.run_records(counts[:4, :200], np.repeat([0.25, 0.5], 100), None, api._opts(gpu_ids=[0], host_plan=True))
