@@ -309,6 +309,7 @@ def main():
     ap.add_argument("--warp-per-gene", action="store_true", help="X-compressed fits on the warp-per-gene kernels (A/B against the CTA-per-gene ones)")
     ap.add_argument("--offset-per-cell", action="store_true", help="intercept-only fits with an offset per cell (A/B against the offset quadrature)")
     ap.add_argument("--genes-per-batch", type=int, default=0, help="sclane_opts.genes_per_batch of the end-to-end legs (0 = the library's choice)")
+    ap.add_argument("--batch-streams", type=int, default=0, help="sclane_opts.batch_streams of the timed legs: 0 = the library's default (2 gene batches in flight), 1 = sequential batches")
     ap.add_argument("--approx-knot", type=int, default=1, help="0 = approx.knot = FALSE: every abscissa kept by min_span / max_span is a candidate knot")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
@@ -318,6 +319,11 @@ def main():
         run_reference(args, cfg)
         return
 
+    # one rank per GPU shares the host with the other ranks: each takes its share of the cores for the library's host threads
+    # (plan / record finalisation / narrowing of the counts for the transfer) -- read by the library when it is loaded
+    _local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    if _local_world > 1:
+        os.environ.setdefault("SCLANE_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // _local_world)))
     import torch
     import torch.distributed as dist
     import sclane_b200 as sb
@@ -361,7 +367,8 @@ def main():
             o.gee_cor = _abi.COR_CODES["ar1"]
         return o
 
-    opts = mk_opts()
+    opts = mk_opts(batch_streams=args.batch_streams)
+    opts_seq = mk_opts(batch_streams=1)        # sequential batches: per-kernel CUDA-event times that do not overlap (stage breakdown, roofline legs)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
@@ -392,7 +399,7 @@ def main():
         e2e_note = f"pinned host allocation of the full shard failed ({str(exc)[:60]}); e2e on the first {Ge} genes, pageable"
     torch.cuda.synchronize()
     h_np = h_counts.numpy()
-    opts_host = mk_opts(h2d_mode=args.h2d_mode, genes_per_batch=args.genes_per_batch)
+    opts_host = mk_opts(h2d_mode=args.h2d_mode, genes_per_batch=args.genes_per_batch, batch_streams=args.batch_streams)
 
     def step_device():
         return sb.run_records(G, pt_in, sf, opts, device_ptr=d_counts.data_ptr(), device=local)
@@ -422,7 +429,25 @@ def main():
     barrier()
     launches = sb.launch_count()
     ms_step = float(np.mean(wall_steps))
-    event_ms = sum(prof_acc["ms"].values()) / args.steps
+    # stage breakdown: the same step with strictly sequential batches, so that the CUDA-event intervals of the stages add up
+    # (with two batches in flight the intervals of the two streams overlap)
+    seq_wall = []
+    prof_acc = None
+    for it_seq in range(3):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if gee:
+            sb.run_records(h_np, pt_in, sf, opts_seq, subject_id=subject)
+        else:
+            sb.run_records(G, pt_in, sf, opts_seq, device_ptr=d_counts.data_ptr(), device=local)
+        torch.cuda.synchronize()
+        if it_seq == 0:
+            continue                                    # the batch geometry differs from the timed legs: buffers are re-sized once
+        seq_wall.append(1000.0 * (time.perf_counter() - t0))
+        prof_acc = acc_profile(prof_acc, sb.get_profile())
+    n_prof_steps = 2
+    event_ms = sum(prof_acc["ms"].values()) / n_prof_steps
 
     # ---- end-to-end measurement (e2e): host buffers, copies inside the timed region ----------------
     def time_host(buf, steps):
@@ -452,7 +477,7 @@ def main():
     sweep = None
     if args.sweep_genes > 0 and not gee and rank == 0 and args.approx_knot:
         Gs = min(G, args.sweep_genes)
-        o_pc = mk_opts(force_per_cell=True)
+        o_pc = mk_opts(force_per_cell=True, batch_streams=1)
         for _ in range(2):
             sb.run_records(Gs, pt_in, None, o_pc, device_ptr=d_counts.data_ptr(), device=local)
         acc = None
@@ -476,7 +501,7 @@ def main():
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
-        stage_ms = {k: v / args.steps for k, v in prof_acc["ms"].items()}
+        stage_ms = {k: v / n_prof_steps for k, v in prof_acc["ms"].items()}
         fit_stages = ["fwd_fit", "backward", "final", "comp_forward", "comp_backward", "comp_final", "select", "gee", "off_null"]
         dom = max(fit_stages, key=lambda k: stage_ms.get(k, 0.0))
         off = type(last_recs[0]).fit_passes.offset
@@ -512,7 +537,9 @@ def main():
                        "offsets": cfg["offsets"], "mode": cfg["kind"], "cells_per_lineage": int(n_lin_cells), "approx_knot": bool(args.approx_knot),
                        "sharding": f"contiguous gene blocks x{world}, no collective",
                        "timing": "value = wall clock around the library call with the counts resident in HBM (host plan, launches, D2H of the records, record "
-                                 "finalisation included); max over ranks" + ("; the GEE entry takes host counts: value == the e2e path from pinned memory" if gee else ""),
+                                 "finalisation included); max over ranks" + ("; the GEE entry takes host counts: value == the e2e path from pinned memory" if gee else "")
+                                 + "; stage_ms_per_step / device_event_ms_per_step come from two extra steps with sequential batches (batch_streams = 1), whose wall clock is sequential_wall_ms_per_step",
+                       "batch_streams": args.batch_streams if args.batch_streams else 2,
                        "l2": "flushed between timed steps (256 MiB write); per-step working set >> 126 MB L2"},
             "e2e": {"value": e2e_val, "unit": "genes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": e2e_prof["h2d_bytes"] / args.steps,
                     "d2h_bytes_per_step": e2e_prof["d2h_bytes"] / args.steps, "host_buffer": "pinned", "h2d_mode": args.h2d_mode,
@@ -521,6 +548,7 @@ def main():
                               "host_buffer": "pageable (what an R integer matrix is); staged uint16 transfer"} if pageable_ms else None),
             "gpu_launches": int(launches),
             "device_event_ms_per_step": event_ms,
+            "sequential_wall_ms_per_step": float(np.mean(seq_wall)),
             "stage_ms_per_step": stage_ms,
             "roofline": roofline,
             "fits": fits,

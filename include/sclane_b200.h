@@ -107,6 +107,10 @@ typedef struct sclane_opts {
   int32_t host_plan;          /* testing / profiling only: 1 = build the per-lineage plan (K0: sort, candidate knots, bucket and
                                  abscissa tables) on the host.  Default 0: on the device whenever it can be (approx_knot = 1, no
                                  size factors, GLM mode, pseudotime range that fits a 24-bit radix key) -- bit-identical tables */
+  int32_t batch_streams;      /* gene batches of a shard in flight at once, each on its own stream (0 = default 2, max 4): the
+                                 launch tails of one batch's kernels and the host work between batches hide behind the other
+                                 batch.  1 = strictly sequential batches (clean per-kernel CUDA-event times for profiling);
+                                 records do not depend on it */
 } sclane_opts;
 
 /* One record per (gene, lineage): everything testDynamic() returns for that pair except the

@@ -50,6 +50,7 @@ class SclaneOpts(C.Structure):
         ("offset_per_cell", C.c_int32),
         ("basis_only", C.c_int32),
         ("host_plan", C.c_int32),
+        ("batch_streams", C.c_int32),
     ]
 
 

@@ -174,7 +174,7 @@ def get_profile() -> dict:
 
 def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None, tols_score=1e-5,
           n_gpus=0, gpu_ids=None, genes_per_batch=0, verbose=False, force_per_cell=False, h2d_mode=0,
-          comp_warp_per_gene=False, offset_per_cell=False, host_plan=False) -> _abi.SclaneOpts:
+          comp_warp_per_gene=False, offset_per_cell=False, host_plan=False, batch_streams=0) -> _abi.SclaneOpts:
     o = _abi.default_opts()
     o.M = int(n_potential_basis_fns)
     o.approx_knot = 1 if approx_knot else 0
@@ -196,6 +196,7 @@ def _opts(n_potential_basis_fns=5, approx_knot=True, n_knot_max=25, minspan=None
     o.comp_warp_per_gene = 1 if comp_warp_per_gene else 0
     o.offset_per_cell = 1 if offset_per_cell else 0
     o.host_plan = 1 if host_plan else 0
+    o.batch_streams = int(batch_streams)
     return o
 
 

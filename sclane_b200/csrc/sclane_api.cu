@@ -133,6 +133,7 @@ struct DevicePool {
   std::map<std::string, Slot> slots;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;      // H2D of the next batch overlaps the kernels of the current one
+  std::vector<cudaStream_t> extra_streams; // compute streams of the batch slots beyond the first (run_shard)
   void* get(const std::string& name, size_t bytes, bool pinned_host = false) {
     Slot& sl = slots[name];
     if (sl.bytes >= bytes && sl.p) return sl.p;
@@ -150,6 +151,8 @@ struct DevicePool {
     slots.clear();
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = nullptr; }
+    for (auto& e : extra_streams) if (e) cudaStreamDestroy(e);
+    extra_streams.clear();
   }
 };
 std::mutex g_pool_mu;
@@ -585,8 +588,18 @@ class H2DFeeder {
       double r_n = 75e9, r_w = 52e9;                   // bytes of int32 per second: narrowing (all host threads), wire
       std::unique_ptr<NarrowPool> pool;
       if (mode_ != DIRECT) {
-        const unsigned hw = std::thread::hardware_concurrency();
+        const unsigned hw = host_threads();
         pool.reset(new NarrowPool(hw == 0 ? 4 : (int)std::min<unsigned>(hw, 16)));
+        if (mode_ == MIXED && n_batches_ > 0) {
+          // calibrate the narrowing rate on a first slice (<= 32 MB) before the split of batch 0 is chosen: the default describes a
+          // host that is otherwise idle, and eight ranks sharing one host see a small fraction of it
+          const int64_t nb0 = std::min<int64_t>(B_, g1_ - g0_);
+          const size_t n_el = std::min<size_t>((size_t)nb0 * (size_t)n_cells_, (size_t)1 << 23);
+          const auto t0 = std::chrono::steady_clock::now();
+          pool->run(h_ + (size_t)g0_ * (size_t)n_cells_, n_el, h_stage_[0]);
+          const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+          if (dt > 1e-5) r_n = std::min(r_n, (double)n_el * 4.0 / dt);
+        }
       }
       bool had_direct[2] = {false, false};
       size_t direct_bytes[2] = {0, 0};
@@ -721,10 +734,13 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t pool_held = pool.held();
+  // batch slots in flight (see Slot below): sclane_opts.batch_streams, default 2
+  const int n_slots = o.batch_streams > 0 ? std::min(o.batch_streams, 4) : 2;
   auto batch_size = [&](int Npad, int Dpad, bool use_comp) -> int64_t {
-    const size_t per_gene = (h_counts ? (size_t)n_cells * 8 : 0) + (size_t)Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
-                            (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0) +
-                            (o.approx_knot ? 0 : (size_t)Dpad * 16);
+    const size_t per_gene_slot = (size_t)Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
+                                 (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0) +
+                                 (o.approx_knot ? 0 : (size_t)Dpad * 16);
+    const size_t per_gene = (h_counts ? (size_t)n_cells * 8 : 0) + (size_t)n_slots * per_gene_slot;
     size_t budget = (size_t)((double)(free_b + pool_held) * 0.6);
     const size_t cap = (size_t)SCLANE_BATCH_CAP_GB << 30;
     if (budget > cap) budget = cap;
@@ -738,6 +754,17 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       const bool heavy_final = use_offset || !use_comp;
       const int64_t want = std::max<int64_t>(2048, heavy_final ? (G + 1) / 2 : (G + 7) / 8);
       if (want < Bv) Bv = want;
+    } else if (n_slots > 1 && !(use_offset || !use_comp)) {
+      // device-resident counts: two batches per slot (but not below a couple of waves of CTAs each), so that every launch tail
+      // and every host-side pause between batches has another batch's kernels to hide behind.  Not for the per-cell final fits
+      // (offsets): there a launch is as long as its slowest genes (25 glm.nb alternations), which must all start at once
+      // (measured, tools/ab_slots.sh: a 2,500-gene shard gains nothing from being split -- 16.4 ms in one batch, 16.8 in two
+      // or three -- while 20,000 genes go from 117.7 ms to 110.0)
+      static const int64_t min_batch = [] { const char* e = std::getenv("SCLANE_MIN_BATCH"); const long v = e ? std::atol(e) : 0; return (int64_t)(v > 0 ? v : 2048); }();
+      if (G >= 2 * min_batch) {
+        const int64_t want = std::max<int64_t>(min_batch, (G + 2 * n_slots - 1) / (2 * n_slots));
+        if (want < Bv) Bv = want;
+      }
     }
     if (Bv > G) Bv = G;
     if (Bv < 1) throw CudaFail{"not enough free device memory for a single gene"};
@@ -818,42 +845,113 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   const bool use_offq = use_comp && use_offset && P.ON.on && !o.offset_per_cell && !o.basis_only;
   if (use_offq) D.upload_offset_nodes(P, pool, s);
   CK(cudaStreamSynchronize(s));                     // plan tables are in place before the kernels start
-  int* d_ys = (int*)pool.get("ys", (size_t)B * (size_t)L.Npad * 4);
-  double* d_mu = (double*)pool.get("mu", (size_t)B * (size_t)L.Npad * 8);
-  double* d_mom = (double*)pool.get("mom", (size_t)B * (size_t)NBMAX * NACC * 8);
-  GeneStats* d_stats = (GeneStats*)pool.get("stats", (size_t)B * sizeof(GeneStats));
-  GeneOutDev* d_out = (GeneOutDev*)pool.get("out", (size_t)B * sizeof(GeneOutDev));
-  GeneOutDev* h_out = (GeneOutDev*)pool.get("h_out", (size_t)B * sizeof(GeneOutDev), true);
-  double* d_s1 = use_comp ? (double*)pool.get("comp_s1", (size_t)B * (size_t)Dpad * 8) : nullptr;
-  double* d_q = use_comp ? (double*)pool.get("comp_q", (size_t)B * (size_t)Dpad * 8) : nullptr;
-  int* d_tail = use_comp ? (int*)pool.get("comp_tail", (size_t)B * (size_t)kHistCap * 4) : nullptr;
-  int* d_big = use_comp ? (int*)pool.get("comp_big", (size_t)B * (size_t)kBigCap * 4) : nullptr;
-  int* d_big_tmp = use_comp ? (int*)pool.get("comp_big_tmp", (size_t)B * (size_t)kBigCap * 4) : nullptr;
-  double* d_okeys = (double*)pool.get("order_keys", (size_t)B * 8);
-  int* d_order = (int*)pool.get("order", (size_t)B * 4);
-  CompGeneDev* d_cg = use_comp ? (CompGeneDev*)pool.get("comp_hdr", (size_t)B * sizeof(CompGeneDev)) : nullptr;
-  double* d_off_s = use_offq ? (double*)pool.get("off_s", (size_t)B * (size_t)(kOffKMax * kOffJ) * 8) : nullptr;
-  double* d_off_q = use_offq ? (double*)pool.get("off_q", (size_t)B * (size_t)(kOffKMax * kOffJ) * 8) : nullptr;
-  OffGeneDev* d_offg = use_offq ? (OffGeneDev*)pool.get("off_gene", (size_t)B * sizeof(OffGeneDev)) : nullptr;
-  int* d_counters = (int*)pool.get("wg_counters", 8 * sizeof(int));
-  double* d_a0p = exact ? (double*)pool.get("ex_a0p", (size_t)B * (size_t)Dpad * 8) : nullptr;
-  double* d_b0p = exact ? (double*)pool.get("ex_b0p", (size_t)B * (size_t)Dpad * 8) : nullptr;
-  // persistent warp-per-gene kernels: one CTA slot per resident CTA of the device
+  // Work buffers of one batch slot.  The batches of a shard run on n_slots streams, batch k on slot k % n_slots: the kernels of
+  // a batch are a chain of ~10 dependent launches, each ending in a tail of half-empty SMs (one CTA per gene, gene cost varies
+  // 10x), and between two batches the device used to wait for the host (D2H of the records, their finalisation, the next
+  // batch's launches).  With two chains in flight the block scheduler fills the tail of one with the CTAs of the other.
+  struct Slot {
+    cudaStream_t s = nullptr;
+    int* d_ys = nullptr; double* d_mu = nullptr; double* d_mom = nullptr; GeneStats* d_stats = nullptr; GeneOutDev* d_out = nullptr; GeneOutDev* h_out = nullptr;
+    double* d_s1 = nullptr; double* d_q = nullptr; int* d_tail = nullptr; int* d_big = nullptr; int* d_big_tmp = nullptr; double* d_okeys = nullptr; int* d_order = nullptr;
+    CompGeneDev* d_cg = nullptr; double* d_off_s = nullptr; double* d_off_q = nullptr; OffGeneDev* d_offg = nullptr; int* d_counters = nullptr;
+    double* d_a0p = nullptr; double* d_b0p = nullptr; double* d_ex_scratch = nullptr;
+    std::unique_ptr<EventTimer> tm;
+    int64_t b0 = 0; int nb = 0; bool busy = false;
+  };
   static int sm_count[SCLANE_MAX_GPUS] = {0};
   if (sm_count[device % SCLANE_MAX_GPUS] == 0) { int v = 0; CK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); sm_count[device % SCLANE_MAX_GPUS] = v; }
+  const int ex_slots = sm_count[device % SCLANE_MAX_GPUS] * 2;
+  std::vector<Slot> slots((size_t)n_slots);
+  for (int si = 0; si < n_slots; ++si) {
+    Slot& Z = slots[(size_t)si];
+    if (si == 0) Z.s = s;
+    else {
+      if (pool.extra_streams.size() < (size_t)si) pool.extra_streams.resize((size_t)si, nullptr);
+      if (!pool.extra_streams[(size_t)si - 1]) CK(cudaStreamCreateWithFlags(&pool.extra_streams[(size_t)si - 1], cudaStreamNonBlocking));
+      Z.s = pool.extra_streams[(size_t)si - 1];
+    }
+    const std::string sfx = si == 0 ? std::string() : "#" + std::to_string(si);
+    Z.d_ys = (int*)pool.get("ys" + sfx, (size_t)B * (size_t)L.Npad * 4);
+    Z.d_mu = (double*)pool.get("mu" + sfx, (size_t)B * (size_t)L.Npad * 8);
+    Z.d_mom = (double*)pool.get("mom" + sfx, (size_t)B * (size_t)NBMAX * NACC * 8);
+    Z.d_stats = (GeneStats*)pool.get("stats" + sfx, (size_t)B * sizeof(GeneStats));
+    Z.d_out = (GeneOutDev*)pool.get("out" + sfx, (size_t)B * sizeof(GeneOutDev));
+    Z.h_out = (GeneOutDev*)pool.get("h_out" + sfx, (size_t)B * sizeof(GeneOutDev), true);
+    if (use_comp) {
+      Z.d_s1 = (double*)pool.get("comp_s1" + sfx, (size_t)B * (size_t)Dpad * 8);
+      Z.d_q = (double*)pool.get("comp_q" + sfx, (size_t)B * (size_t)Dpad * 8);
+      Z.d_tail = (int*)pool.get("comp_tail" + sfx, (size_t)B * (size_t)kHistCap * 4);
+      Z.d_big = (int*)pool.get("comp_big" + sfx, (size_t)B * (size_t)kBigCap * 4);
+      Z.d_big_tmp = (int*)pool.get("comp_big_tmp" + sfx, (size_t)B * (size_t)kBigCap * 4);
+      Z.d_cg = (CompGeneDev*)pool.get("comp_hdr" + sfx, (size_t)B * sizeof(CompGeneDev));
+    }
+    Z.d_okeys = (double*)pool.get("order_keys" + sfx, (size_t)B * 8);
+    Z.d_order = (int*)pool.get("order" + sfx, (size_t)B * 4);
+    if (use_offq) {
+      Z.d_off_s = (double*)pool.get("off_s" + sfx, (size_t)B * (size_t)(kOffKMax * kOffJ) * 8);
+      Z.d_off_q = (double*)pool.get("off_q" + sfx, (size_t)B * (size_t)(kOffKMax * kOffJ) * 8);
+      Z.d_offg = (OffGeneDev*)pool.get("off_gene" + sfx, (size_t)B * sizeof(OffGeneDev));
+    }
+    Z.d_counters = (int*)pool.get("wg_counters" + sfx, 8 * sizeof(int));
+    if (exact) {
+      Z.d_a0p = (double*)pool.get("ex_a0p" + sfx, (size_t)B * (size_t)Dpad * 8);
+      Z.d_b0p = (double*)pool.get("ex_b0p" + sfx, (size_t)B * (size_t)Dpad * 8);
+      Z.d_ex_scratch = (double*)pool.get("ex_scratch" + sfx, (size_t)ex_slots * (size_t)(2 + kExMom) * (size_t)Dpad * 8);
+    }
+    Z.tm.reset(new EventTimer(Z.s));
+  }
+  // persistent warp-per-gene kernels: one CTA slot per resident CTA of the device
   const int wg_slots = sm_count[device % SCLANE_MAX_GPUS] * SCLANE_WG_MINB;
   const bool use_wg = use_comp && o.comp_warp_per_gene && !exact;
-  const int ex_slots = sm_count[device % SCLANE_MAX_GPUS] * 2;
-  double* d_ex_scratch = exact ? (double*)pool.get("ex_scratch", (size_t)ex_slots * (size_t)(2 + kExMom) * (size_t)Dpad * 8) : nullptr;
   if (exact) {
     static std::once_flag ex_once[SCLANE_MAX_GPUS];
     std::call_once(ex_once[device % SCLANE_MAX_GPUS], [] { CK(cudaFuncSetAttribute(k_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExactShared))); });
   }
   const int n_iter = forward_iterations(o.M);
-  EventTimer tm(s);
+  // a finished batch: records finalised on the host (z / p-values, LRT, pchisq per gene, ~1-2 us each -- spread over host
+  // threads, chunk sums in chunk order) while the other slot's kernels keep the device busy
+  auto finish = [&](Slot& Z) {
+    if (!Z.busy) return;
+    if (h_counts) stream_wait_blocking(Z.s); else CK(cudaStreamSynchronize(Z.s));
+    g_trace.at("batch done on the device");
+    Z.tm->collect(prof);
+    const int nb = Z.nb;
+    const int64_t b0 = Z.b0;
+    GeneOutDev* h_out = Z.h_out;
+    long long sw_chunk[kPlanChunks] = {0};
+    const bool basis_only = o.basis_only != 0;
+    parallel_chunks((size_t)nb, [&](int c, size_t i0, size_t i1) {
+      long long sw = 0;
+      for (size_t i = i0; i < i1; ++i) {
+        GeneOut go;
+        go.st = h_out[i].st; go.alt = h_out[i].alt; go.null = h_out[i].null;
+        sclane_record& r = out[((b0 - out_g0) + (int64_t)i) * n_lineages + lin_idx];
+        finalize_record(go, L, r, basis_only);
+        sw += go.st.fwd_iters;                       // sweeps actually run for this gene: one per forward iteration it entered
+      }
+      sw_chunk[c] = sw;
+    }, 1024);
+    long long sw = 0;
+    for (int c = 0; c < kPlanChunks; ++c) sw += sw_chunk[c];
+    prof.sweep_gene_iters += sw;
+    prof.sweep_bytes += 12.0 * (double)L.N * (double)sw;
+    prof.sweep_bytes += 8.0 * (double)L.N * (double)n_iter;
+    g_trace.at("records finalised");
+    Z.busy = false;
+  };
   for (int64_t b0 = g0, kb = 0; b0 < g1; b0 += B, ++kb) {
     const int64_t b1 = std::min<int64_t>(b0 + B, g1);
     const int nb = (int)(b1 - b0);
+    Slot& Z = slots[(size_t)(kb % n_slots)];
+    finish(Z);                                        // the batch that used this slot before (no-op for the first n_slots batches)
+    Z.b0 = b0; Z.nb = nb; Z.busy = true;
+    cudaStream_t s = Z.s;
+    EventTimer& tm = *Z.tm;
+    int* const d_ys = Z.d_ys; double* const d_mu = Z.d_mu; double* const d_mom = Z.d_mom; GeneStats* const d_stats = Z.d_stats;
+    GeneOutDev* const d_out = Z.d_out; GeneOutDev* const h_out = Z.h_out; double* const d_s1 = Z.d_s1; double* const d_q = Z.d_q;
+    int* const d_tail = Z.d_tail; int* const d_big = Z.d_big; int* const d_big_tmp = Z.d_big_tmp; double* const d_okeys = Z.d_okeys; int* const d_order = Z.d_order;
+    CompGeneDev* const d_cg = Z.d_cg; double* const d_off_s = Z.d_off_s; double* const d_off_q = Z.d_off_q; OffGeneDev* const d_offg = Z.d_offg;
+    int* const d_counters = Z.d_counters; double* const d_a0p = Z.d_a0p; double* const d_b0p = Z.d_b0p; double* const d_ex_scratch = Z.d_ex_scratch;
     tm.mark(SCLANE_STAGE_COPY);             // on the compute stream this interval is the EXPOSED wait for the batch's H2D
     const int* raw = nullptr;
     H2DFeeder::Layout lay;                          // device-resident counts: one int32 part
@@ -1022,31 +1120,13 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     prof.launches[SCLANE_STAGE_COPY]++;
     tm.mark(-1);
     g_trace.at("batch queued");
-    if (h_counts) stream_wait_blocking(s); else CK(cudaStreamSynchronize(s));
-    g_trace.at("batch done on the device");
-    tm.collect(prof);
-    // records: z / p-values, LRT, pchisq per gene (~1-2 us each) -- spread over host threads, chunk sums in chunk order
-    {
-      long long sw_chunk[kPlanChunks] = {0};
-      const bool basis_only = o.basis_only != 0;
-      parallel_chunks((size_t)nb, [&](int c, size_t i0, size_t i1) {
-        long long sw = 0;
-        for (size_t i = i0; i < i1; ++i) {
-          GeneOut go;
-          go.st = h_out[i].st; go.alt = h_out[i].alt; go.null = h_out[i].null;
-          sclane_record& r = out[((b0 - out_g0) + (int64_t)i) * n_lineages + lin_idx];
-          finalize_record(go, L, r, basis_only);
-          sw += go.st.fwd_iters;                       // sweeps actually run for this gene: one per forward iteration it entered
-        }
-        sw_chunk[c] = sw;
-      }, 1024);
-      long long sw = 0;
-      for (int c = 0; c < kPlanChunks; ++c) sw += sw_chunk[c];
-      prof.sweep_gene_iters += sw;
-      prof.sweep_bytes += 12.0 * (double)L.N * (double)sw;
-      g_trace.at("records finalised");
-    }
-    prof.sweep_bytes += 8.0 * (double)L.N * (double)n_iter;
+  }
+  // drain: oldest batch first
+  {
+    std::vector<Slot*> left;
+    for (auto& Z : slots) if (Z.busy) left.push_back(&Z);
+    std::sort(left.begin(), left.end(), [](const Slot* a, const Slot* b) { return a->b0 < b->b0; });
+    for (Slot* Z : left) finish(*Z);
   }
   if (feeder) { prof.h2d_bytes += feeder->h2d_bytes(); prof.launches[SCLANE_STAGE_COPY] += feeder->copies(); }
 }
@@ -1181,6 +1261,7 @@ int check_opts(const sclane_opts* o, char* errbuf, size_t errlen) {
   if (o->mode != 0 && o->mode != 1) { set_err(errbuf, errlen, "mode %d is not built; 0 = GLM, 1 = GEE", o->mode); return SCLANE_ERR_UNSUPPORTED; }
   if (o->M < 3 || o->M > SCLANE_PMAX) { set_err(errbuf, errlen, "M must be in [3, %d]", SCLANE_PMAX); return SCLANE_ERR_ARG; }
   if (o->h2d_mode < 0 || o->h2d_mode > 2) { set_err(errbuf, errlen, "h2d_mode must be 0, 1 or 2"); return SCLANE_ERR_ARG; }
+  if (o->batch_streams < 0 || o->batch_streams > 4) { set_err(errbuf, errlen, "batch_streams must be in [0, 4]"); return SCLANE_ERR_ARG; }
   if (!o->approx_knot && o->mode != 0) { set_err(errbuf, errlen, "approx_knot = 0 is built for GLM mode only"); return SCLANE_ERR_UNSUPPORTED; }
   if (o->n_knot_max < 1 || o->n_knot_max > SCLANE_TMAX) { set_err(errbuf, errlen, "n_knot_max must be in [1, %d]", SCLANE_TMAX); return SCLANE_ERR_ARG; }
   return SCLANE_OK;
@@ -1247,6 +1328,7 @@ void drain_device(int device) {
   DevicePool& pool = pool_for(device);
   if (pool.copy_stream) cudaStreamSynchronize(pool.copy_stream);
   if (pool.stream) cudaStreamSynchronize(pool.stream);
+  for (auto e : pool.extra_streams) if (e) cudaStreamSynchronize(e);
   cudaGetLastError();
 }
 

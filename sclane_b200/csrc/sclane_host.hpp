@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <limits>
@@ -23,9 +24,21 @@ namespace sclane {
 // fn(chunk, begin, end) over kPlanChunks FIXED chunks of [0, n): any per-chunk partial result is combined in chunk order
 // afterwards, so every plan is bit-identical whatever the number of host threads (<= kPlanChunks) that ran it.
 constexpr int kPlanChunks = 16;
+// Host threads the library may use (plan, record finalisation, narrowing of the counts for the transfer): the machine's, unless
+// SCLANE_HOST_THREADS says otherwise -- several processes sharing one host (one rank per GPU) should each take their share.
+inline unsigned host_threads() {
+  static const unsigned n = [] {
+    const char* e = std::getenv("SCLANE_HOST_THREADS");
+    const long v = e ? std::atol(e) : 0;
+    if (v > 0) return (unsigned)v;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw == 0 ? 4u : hw;
+  }();
+  return n;
+}
 template <class F>
 inline void parallel_chunks(size_t n, F fn, size_t min_parallel = 32768) {
-  unsigned hw = std::thread::hardware_concurrency();
+  unsigned hw = host_threads();
   int nt = (int)(hw == 0 ? 4 : (hw > (unsigned)kPlanChunks ? (unsigned)kPlanChunks : hw));
   if (n < min_parallel) nt = 1;
   auto run = [&](int t) {
@@ -382,7 +395,7 @@ inline bool build_lineage_plan(const double* pt_col, int64_t n_cells, const doub
   // unweighted bucket moments: one bucket per task, summed in cell order (bit-identical to a serial pass)
   {
     const int nb = L.T + 1;
-    unsigned hw = std::thread::hardware_concurrency();
+    unsigned hw = host_threads();
     int nt = (int)(hw == 0 ? 4 : (hw > 8 ? 8 : hw));
     if (N < 32768) nt = 1;
     auto run = [&](int t) {

@@ -427,3 +427,23 @@ def test_device_plan_records_equal_host_plan_records():
         api.run_records(counts[:4, :200], np.repeat([0.25, 0.5], 100), None, api._opts(gpu_ids=[0]))
     with pytest.raises(sb.SclaneError):
         api.run_records(counts[:4, :200], np.repeat([0.25, 0.5], 100), None, api._opts(gpu_ids=[0], host_plan=True))
+
+
+def test_batch_streams_do_not_change_records():
+    """Gene batches in flight on 1, 2 and 3 streams (sclane_opts.batch_streams), device-resident and host-fed, with and without
+    offsets: records byte for byte (which stream fits which gene affects nothing)."""
+    import torch
+    import sclane_b200 as sb
+    from sclane_b200 import api
+    from test_gpu_parity import _rec_bytes
+    from tools import synth
+    counts, pt, _ = synth.make_counts(700, 12000, seed=21)
+    sf = np.exp(np.random.default_rng(2).normal(0, 0.4, 12000))
+    d_counts = torch.from_numpy(counts).cuda()
+    for size_factor in (None, sf):
+        ref, _ = api.run_records(counts, pt, size_factor, api._opts(gpu_ids=[0], batch_streams=1))
+        for kw in ({"batch_streams": 2, "genes_per_batch": 100}, {"batch_streams": 3, "genes_per_batch": 64}, {"batch_streams": 0}):
+            got, _ = api.run_records(counts, pt, size_factor, api._opts(gpu_ids=[0], **kw))
+            assert all(_rec_bytes(a) == _rec_bytes(b) for a, b in zip(ref, got)), kw
+            got, _ = api.run_records(counts.shape[0], pt, size_factor, api._opts(gpu_ids=[0], **kw), device_ptr=d_counts.data_ptr(), device=0)
+            assert all(_rec_bytes(a) == _rec_bytes(b) for a, b in zip(ref, got)), kw
