@@ -291,6 +291,7 @@ struct DevicePlan {
   int* oord = nullptr;
   double* oxi_ord = nullptr;
   double* off_ord = nullptr;
+  int* ogrp = nullptr;
   std::vector<double> h_oxi_ord, h_off_ord;        // staging (must outlive the async copies: DevicePlan lives until the shard is done)
   void upload_offset_nodes(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
     const size_t N = (size_t)P.L.N;
@@ -304,6 +305,8 @@ struct DevicePlan {
     CK(cudaMemcpyAsync(oord, P.oord.data(), N * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(oxi_ord, h_oxi_ord.data(), N * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(off_ord, h_off_ord.data(), N * sizeof(double), cudaMemcpyHostToDevice, s));
+    ogrp = (int*)pool.get("off_ogrp", P.ogrp.size() * sizeof(int));
+    CK(cudaMemcpyAsync(ogrp, P.ogrp.data(), P.ogrp.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   }
   void upload(const LineagePlan& P, DevicePool& pool, cudaStream_t s) {
     perm = (int*)pool.get("perm", P.perm.size() * sizeof(int));
@@ -415,8 +418,8 @@ void launch_stage(const StageArgs& A, cudaStream_t s) {
 
 // theta.ml on Chebyshev nodes in k_comp_stage<FINAL> (sclane_comp.cuh); SCLANE_THETA_NODES=0 walks the points instead (A/B).
 bool theta_nodes_enabled() {
-  static const bool on = [] { const char* e = std::getenv("SCLANE_THETA_NODES"); return !(e && e[0] == '0'); }();
-  return on;
+  const char* e = std::getenv("SCLANE_THETA_NODES");      // read per call: the tests switch it inside one process
+  return !(e && e[0] == '0');
 }
 
 // Hybrid final stage on thread-block clusters: CL CTAs (on CL SMs of one GPC) per gene, partial moments exchanged through
@@ -739,7 +742,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   auto batch_size = [&](int Npad, int Dpad, bool use_comp) -> int64_t {
     const size_t per_gene_slot = (size_t)Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
                                  (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0) +
-                                 (o.approx_knot ? 0 : (size_t)Dpad * 16);
+                                 (o.approx_knot ? 0 : (size_t)Dpad * 16) + (use_offset ? 3 * (size_t)kHtCap * 8 + (size_t)(kOffKMax * kOffJ) * 16 : 0);
     const size_t per_gene = (h_counts ? (size_t)n_cells * 8 : 0) + (size_t)n_slots * per_gene_slot;
     size_t budget = (size_t)((double)(free_b + pool_held) * 0.6);
     const size_t cap = (size_t)SCLANE_BATCH_CAP_GB << 30;
@@ -849,12 +852,15 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   // a batch are a chain of ~10 dependent launches, each ending in a tail of half-empty SMs (one CTA per gene, gene cost varies
   // 10x), and between two batches the device used to wait for the host (D2H of the records, their finalisation, the next
   // batch's launches).  With two chains in flight the block scheduler fills the tail of one with the CTAs of the other.
+  // hybrid final stage (offsets): theta.ml on Chebyshev nodes of the (offset bin, bucket) groups (sclane_device.cuh)
+  const bool hyb_theta_nodes = use_offq && !exact && theta_nodes_enabled() && P.ON.K * (L.T + 1) <= kHtUnits;
   struct Slot {
     cudaStream_t s = nullptr;
     int* d_ys = nullptr; double* d_mu = nullptr; double* d_mom = nullptr; GeneStats* d_stats = nullptr; GeneOutDev* d_out = nullptr; GeneOutDev* h_out = nullptr;
     double* d_s1 = nullptr; double* d_q = nullptr; int* d_tail = nullptr; int* d_big = nullptr; int* d_big_tmp = nullptr; double* d_okeys = nullptr; int* d_order = nullptr;
     CompGeneDev* d_cg = nullptr; double* d_off_s = nullptr; double* d_off_q = nullptr; OffGeneDev* d_offg = nullptr; int* d_counters = nullptr;
     double* d_a0p = nullptr; double* d_b0p = nullptr; double* d_ex_scratch = nullptr;
+    double* d_ht = nullptr;            // hybrid final stage: theta.ml node lists, [B][3][kHtCap]
     std::unique_ptr<EventTimer> tm;
     int64_t b0 = 0; int nb = 0; bool busy = false;
   };
@@ -891,6 +897,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       Z.d_off_s = (double*)pool.get("off_s" + sfx, (size_t)B * (size_t)(kOffKMax * kOffJ) * 8);
       Z.d_off_q = (double*)pool.get("off_q" + sfx, (size_t)B * (size_t)(kOffKMax * kOffJ) * 8);
       Z.d_offg = (OffGeneDev*)pool.get("off_gene" + sfx, (size_t)B * sizeof(OffGeneDev));
+      if (hyb_theta_nodes) Z.d_ht = (double*)pool.get("hyb_theta" + sfx, (size_t)B * 3 * (size_t)kHtCap * 8);
     }
     Z.d_counters = (int*)pool.get("wg_counters" + sfx, 8 * sizeof(int));
     if (exact) {
@@ -990,6 +997,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     A.lineage = D.lin; A.ys = d_ys; A.u = D.u; A.off = D.off; A.mu = d_mu; A.stats = d_stats; A.out = d_out;
     A.scores = nullptr; A.mom = d_mom; A.n_genes = nb; A.M = o.M; A.tols_score = o.tols_score; A.use_offset = use_offset ? 1 : 0;
     A.order = nullptr; A.cg = nullptr; A.tail = nullptr; A.big = nullptr; A.exact = 0; A.pstart = nullptr;
+    A.on = nullptr; A.oord = nullptr; A.off_ord = nullptr; A.ogrp = nullptr; A.ht_scratch = nullptr;
     CompArgs CA;
     CA.order = nullptr;
     CA.theta_nodes = 0;
@@ -1103,6 +1111,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       // alternatives with hinges: hybrid per-cell passes (mu-free terms from the histogram); genes without a histogram
       // (route 0) are left to the plain per-cell launch below, which skips everything already done
       A.cg = d_cg; A.tail = d_tail; A.big = d_big; A.exact = exact ? 1 : 0; A.pstart = D.pstart;
+      if (hyb_theta_nodes) { A.on = D.on; A.oord = D.oord; A.off_ord = D.off_ord; A.ogrp = D.ogrp; A.ht_scratch = Z.d_ht; }
       switch (final_cluster_size(P.L.N)) {
         case 8: launch_final_cluster<8>(A, s); break;
         case 4: launch_final_cluster<4>(A, s); break;

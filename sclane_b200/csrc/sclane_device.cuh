@@ -8,6 +8,7 @@
 // warp-shuffle reduction into its private shared-memory slot.  Slots are combined across warps in a
 // fixed order, so every sum is bit-reproducible run to run and across GPU counts.
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "sclane_comp.cuh"
@@ -64,6 +65,30 @@ __device__ __forceinline__ const double* cluster_map(const double* p, unsigned r
 
 constexpr int kPartN = NBMAX * NACC + NSC;     // one CTA's partial sums of a pass (cluster mode)
 
+// theta.ml of a fit WITH a size-factor offset on Chebyshev nodes (hybrid final stage; same idea as ThetaNodes in sclane_comp.cuh).
+// mu is fixed while theta.ml iterates and both of its sums are  sum_i [A(z_i; theta) + y_i B(z_i; theta)]  with
+// z_i = a_b + c_b u_i + o_i.  The offset quadrature's bin-ordered cell list (oord: by offset bin, then pseudotime) makes the
+// cells of (offset bin k, knot bucket b) a contiguous, pseudotime-sorted range; inside it z spans at most |c_b| du + w (w <= 1/2
+// the bin width), so the range -- cut further along u when the slope is steep -- is one interval of width <= kThBinWidth in z and
+// its cells collapse into 16 node weights (Chebyshev moments of 1 and of y, one warp per interval, fixed summation order).
+// A Newton step then costs  (#bins x #buckets) x 16  node evaluations instead of N cell evaluations.
+constexpr int kHtUnits = 512;          // (offset bin, bucket) groups the unit table holds
+constexpr int kHtCap = 4096;           // entries of the node list (global scratch, 3 doubles each)
+struct HybTheta {                      // shared memory
+  int on, n;
+  int first[kHtUnits + 1];
+  short sub[kHtUnits];                 // 0 = empty group, -1 = its cells as they are, S >= 1 = S intervals along u
+  int wt[kWarps + 1];
+  double ctab[kOffJ][kOffJ];           // T_m(xi_j)
+};
+struct HybThetaArgs {
+  const OffsetNodes* on;
+  const int* oord;                     // [N] sorted-cell positions by (offset bin, position)
+  const double* off_ord;               // [N] offsets in that order
+  const int* ogrp;                     // [K (T + 2)] group boundaries inside oord
+  double* en; double* es; double* eeta;      // [kHtCap] each: this gene's node list
+};
+
 // CL > 1: a thread-block CLUSTER of CL CTAs fits one gene.  Every CTA keeps its own copy of the gene's state and runs the
 // identical control flow (the serial algebra is redundant, deterministic and therefore identical); a pass splits the cells
 // over the CL x 8 warps of the cluster and the CTAs exchange their partial moments through distributed shared memory:
@@ -94,6 +119,149 @@ struct DevExecT {
   double* part;                     // cluster mode: [2][kPartN] this CTA's partial sums (shared memory), else nullptr
   int crank;                        // cluster mode: rank of this CTA in its cluster
   int pbuf;                         // cluster mode: which half of part[] the running pass writes
+  HybTheta* ht = nullptr;           // hybrid mode, CL == 1: theta.ml node list bookkeeping (shared memory) or nullptr
+  HybThetaArgs hta = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+  // theta.ml is about to iterate at the mean defined by W.a / W.c (+ offset): condense the cells into the node list
+  __device__ __noinline__ void theta_prepare() {
+    if (!HYB || CL > 1 || ht == nullptr) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Lineage& Lr = *L;
+    const int T = Lr.T;
+    const OffsetNodes& O = *hta.on;
+    const int K = O.K, nU = K * (T + 1);
+    const double ow = O.w;
+    __syncthreads();
+    if (!(W->use_offset && off != nullptr) || nU > kHtUnits || !(ow <= kOffBinWidth + 1e-9)) {
+      if (threadIdx.x == 0) ht->on = 0;
+      __syncthreads();
+      return;
+    }
+    // entries per group: two consecutive groups per thread (kHtUnits = 2 x kThreads), exclusive scan in group order
+    const double room = kThBinWidth - ow;               // what the slope may use of the interval's width
+    int cnt[2] = {0, 0};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int unit = 2 * (int)threadIdx.x + j;
+      if (unit >= nU) continue;
+      const int k = unit / (T + 1), b = unit - k * (T + 1);
+      const int r0 = hta.ogrp[k * (T + 2) + b], r1 = hta.ogrp[k * (T + 2) + b + 1], P = r1 - r0;
+      int S = 0;
+      if (P > 0) {
+        const double c = W->c[b];
+        const double du = c != 0.0 ? u[hta.oord[r1 - 1]] - u[hta.oord[r0]] : 0.0;
+        const double span = fabs(c) * du;
+        S = (int)ceil(span / room);
+        if (S < 1) S = 1;
+        if (!(span == span) || S > 256 || 3 * S * kOffJ > 2 * P) { S = -1; cnt[j] = P; }
+        else cnt[j] = S * kOffJ;
+      }
+      ht->sub[unit] = (short)S;
+    }
+    {
+      const int v = cnt[0] + cnt[1];
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) ht->wt[warp] = inc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int runw = 0;
+        for (int w = 0; w < kWarps; ++w) { const int t = ht->wt[w]; ht->wt[w] = runw; runw += t; }
+        ht->wt[kWarps] = runw;
+        ht->n = runw;
+        ht->on = (runw <= kHtCap && 2 * runw <= Lr.N) ? 1 : 0;       // the list must fit and must at least halve the work
+      }
+      __syncthreads();
+      const int base = ht->wt[warp] + inc - v;
+      if (2 * (int)threadIdx.x < nU) ht->first[2 * threadIdx.x] = base;
+      if (2 * (int)threadIdx.x + 1 < nU) ht->first[2 * threadIdx.x + 1] = base + cnt[0];
+    }
+    __syncthreads();
+    if (!ht->on) return;
+    // build: one group per warp at a time
+#pragma unroll 1
+    for (int unit = warp; unit < nU; unit += kWarps) {
+      const int S = ht->sub[unit];
+      if (S == 0) continue;
+      const int k = unit / (T + 1), b = unit - k * (T + 1);
+      const int r0 = hta.ogrp[k * (T + 2) + b], r1 = hta.ogrp[k * (T + 2) + b + 1];
+      const double a = W->a[b], c = W->c[b];
+      const int e0 = ht->first[unit];
+      if (S < 0) {
+        for (int r = r0 + lane; r < r1; r += 32) {
+          const int i = hta.oord[r];
+          const int e = e0 + (r - r0);
+          hta.en[e] = 1.0; hta.es[e] = (double)y[i]; hta.eeta[e] = a + c * u[i] + hta.off_ord[r];
+        }
+        continue;
+      }
+      const double olo = O.omin + (double)k * ow, ohi = olo + ow;
+      const double ulo = u[hta.oord[r0]], uhi = u[hta.oord[r1 - 1]];
+      const double hu = (uhi - ulo) / (double)S;
+      const int half = lane >> 4, j = lane & 15;
+#pragma unroll 1
+      for (int sidx = 0; sidx < S; ++sidx) {
+        const double u0 = ulo + (double)sidx * hu, u1 = sidx + 1 == S ? uhi : ulo + (double)(sidx + 1) * hu;
+        int lo = r0, hi = r1;
+        if (sidx > 0) { int x = r0, yv = r1; while (x < yv) { const int m = (x + yv) >> 1; if (u[hta.oord[m]] < u0) x = m + 1; else yv = m; } lo = x; }
+        if (sidx + 1 < S) { int x = r0, yv = r1; while (x < yv) { const int m = (x + yv) >> 1; if (u[hta.oord[m]] < u1) x = m + 1; else yv = m; } hi = x; }
+        const double zA = a + c * u0, zB = a + c * u1;
+        const double zmin = fmin(zA, zB) + olo, zmax = fmax(zA, zB) + ohi;
+        const double zw = zmax - zmin;
+        const double sc2 = zw > 0.0 ? 2.0 / zw : 0.0;
+        double cm[kOffJ];
+#pragma unroll
+        for (int m = 0; m < kOffJ; ++m) cm[m] = 0.0;
+        for (int r = lo + j; r < hi; r += 16) {
+          const int i = hta.oord[r];
+          const double z = a + c * u[i] + hta.off_ord[r];
+          const double v = half ? (double)y[i] : 1.0;
+          double xi = sc2 * (z - zmin) - 1.0;
+          xi = fmin(1.0, fmax(-1.0, xi));
+          double t0 = 1.0, t1 = xi;
+          cm[0] += v; cm[1] += v * xi;
+#pragma unroll
+          for (int m = 2; m < kOffJ; ++m) { const double t2 = 2.0 * xi * t1 - t0; cm[m] += v * t2; t0 = t1; t1 = t2; }
+        }
+#pragma unroll
+        for (int m = 0; m < kOffJ; ++m) {
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) cm[m] += __shfl_xor_sync(0xffffffffu, cm[m], o);
+        }
+        double sacc = 0.0;
+#pragma unroll
+        for (int m = kOffJ - 1; m >= 1; --m) sacc += ht->ctab[m][j] * cm[m];
+        const double wgt = (cm[0] + 2.0 * sacc) * (1.0 / (double)kOffJ);
+        const int e = e0 + sidx * kOffJ + j;
+        if (half) hta.es[e] = wgt;
+        else { hta.en[e] = wgt; hta.eeta[e] = zmin + 0.5 * (ht->ctab[1][j] + 1.0) * zw; }
+      }
+    }
+    __syncthreads();
+  }
+
+  // a Newton step of theta.ml on the node list built by theta_prepare()
+  __device__ __noinline__ void pass_theta_nodes() {
+    constexpr int NS = PassTraits<PASS_THETA>::NS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double sigma = W->sigma, theta = W->theta;
+    if (lane < NSC) scw[warp][lane] = 0.0;
+    __syncwarp();
+    double sc[NSC], dummy[1];
+#pragma unroll
+    for (int k = 0; k < NSC; ++k) sc[k] = 0.0;
+    const int n = ht->n;
+    for (int e = threadIdx.x; e < n; e += kThreads)
+      point_contrib<PASS_THETA>(hta.en[e], hta.es[e], 0.0, 0.0, hta.eeta[e], 0.0, sigma, theta, false, ft, dummy, sc);
+    const int ymax = cg->hdr.ymax;
+    const int hmax = ymax < kHistCap ? ymax : kHistCap - 1;
+    for (int k = threadIdx.x; k < hmax; k += kThreads) hist_contrib<PASS_THETA>(k, (double)tail[k], (double)tail[k + 1], sigma, theta, false, sc);
+    const int n_big = cg->hdr.n_big;
+    for (int e = threadIdx.x; e < n_big; e += kThreads) big_contrib<PASS_THETA>(big[e], sigma, theta, false, sc);
+    flush_uniform<NS>(sc, 0, &scw[warp][0], 0);
+    combine<0, NS>(L->T);
+  }
 
   __device__ __forceinline__ bool leader() const { return threadIdx.x == 0; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -362,6 +530,9 @@ struct DevExecT {
   template <int MODE>
   __device__ __forceinline__ void pass() {
     static_assert(MODE != PASS_SWEEP, "the sweep streams through k_sweep_moments, not through a CTA pass");
+    if (HYB && CL == 1 && MODE == PASS_THETA) {
+      if (ht != nullptr && ht->on) { pass_theta_nodes(); return; }      // block-uniform
+    }
     pass_scalar<MODE>();
   }
 };
@@ -396,6 +567,12 @@ struct StageArgs {
   int exact;                   // approx.knot = FALSE: the buckets are the gene's own (GeneState.ex_*); needs pstart
   const int* pstart;           // [D + 1] first sorted cell of every abscissa
   const int* order;            // optional CTA -> gene map of the final stage (k_order_final: expensive genes first), or nullptr
+  // hybrid final stage: theta.ml on Chebyshev nodes (HybTheta above); all null = theta.ml walks the cells
+  const OffsetNodes* on = nullptr;
+  const int* oord = nullptr;
+  const double* off_ord = nullptr;
+  const int* ogrp = nullptr;
+  double* ht_scratch = nullptr;  // [B][3][kHtCap]
 };
 
 enum Stage : int { STAGE_FWD_FIT = 0, STAGE_BACKWARD = 2, STAGE_FINAL = 3 };
@@ -415,6 +592,10 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   __shared__ double uoff_s[NBMAX + 1];
   __shared__ double part_s[CL > 1 ? 2 * kPartN : 1];
   __shared__ NbResult dump_s[CL > 1 ? 2 : 1];        // cluster mode: CTAs other than rank 0 keep their (identical) results here
+  constexpr bool kHt = HYB && CL == 1 && STAGE == STAGE_FINAL;
+  using HtStore = typename std::conditional<kHt, HybTheta, int>::type;      // only the hybrid final stage pays for it
+  __shared__ HtStore ht_store;
+  HybTheta* const htp = kHt ? reinterpret_cast<HybTheta*>(&ht_store) : nullptr;
   static_assert(CL == 1 || (HYB && STAGE == STAGE_FINAL), "clusters are used by the hybrid final stage only");
   const int slot_g = (int)blockIdx.x / CL;            // every exit below is uniform over the cluster (gene-level conditions)
   const int crank = CL > 1 ? (int)cluster_cta_rank() : 0;
@@ -436,6 +617,13 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
     int* w = reinterpret_cast<int*>(&W);
     for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kThreads) w[i] = 0;
     fast_tabs_load(&ftab, threadIdx.x, kThreads);
+    if (kHt && A.ht_scratch) {
+      for (int i = threadIdx.x; i < kOffJ * kOffJ; i += kThreads) {
+        const int m = i / kOffJ, j = i - m * kOffJ;
+        htp->ctab[m][j] = cospi((double)(m * (2 * j + 1)) / (double)(2 * kOffJ));
+      }
+      if (threadIdx.x == 0) { htp->on = 0; htp->n = 0; }
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -462,6 +650,11 @@ __global__ void __launch_bounds__(kThreads, SCLANE_STAGE_MINB) k_stage(StageArgs
   DevExecT<HYB, CL> ex{&W, &Ls, A.ys + row, A.u, A.off, A.mu ? A.mu + row : nullptr, slot, scw, &tabs, &ftab,
                        HYB ? A.cg + g : nullptr, &gs, HYB ? A.tail + (size_t)g * (size_t)kHistCap : nullptr, HYB ? A.big + (size_t)g * (size_t)kBigCap : nullptr,
                        wtab, wztab, A.exact ? uoff_s : nullptr, CL > 1 ? part_s : nullptr, crank, 0};
+  if (kHt && A.ht_scratch && !A.exact) {
+    double* sc0 = A.ht_scratch + (size_t)g * 3 * (size_t)kHtCap;
+    ex.ht = htp;
+    ex.hta = HybThetaArgs{A.on, A.oord, A.off_ord, A.ogrp, sc0, sc0 + kHtCap, sc0 + 2 * kHtCap};
+  }
   if (STAGE == STAGE_FWD_FIT) {
     gene_forward_fit(ex, Ls, gs, st, W);
   } else if (STAGE == STAGE_BACKWARD) {

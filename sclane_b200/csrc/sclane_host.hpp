@@ -246,6 +246,8 @@ struct LineagePlan {
   std::vector<double> oxi;        // [Npad] position of o_i inside its bin, in [-1, 1] (sorted-cell order)
   std::vector<uint8_t> obin;      // [Npad] bin of o_i
   std::vector<int32_t> oord;      // [N] sorted-cell positions ordered by (bin, position)
+  std::vector<int32_t> ogrp;      // [K * (T + 2)] first entry of oord inside bin k whose position is >= bstart[b], b = 0 .. T + 1: the
+                                  // cells of (offset bin k, bucket b) are oord[ogrp[k (T + 2) + b] .. ogrp[k (T + 2) + b + 1])
   // approx.knot = FALSE (marge2.R:167-173): every candidate knot is a data abscissa; the lineage carries ONE bucket (T = 0)
   // and every gene builds its own buckets from the knots it selects (sclane_exact_device.cuh)
   // scratch of build_lineage_plan(), kept with the plan so that a reused plan object (the library keeps a pool across calls) does
@@ -329,6 +331,15 @@ inline void build_offset_nodes(LineagePlan& P) {
     for (int i = 0; i < N; ++i) P.oord[(size_t)pos[P.obin[(size_t)i]]++] = i;
   }
   for (int k = 0; k < K; ++k) off_moments_to_nodes(O, &cm[(size_t)k * kOffJ], &O.node_n[k * kOffJ]);
+  // (bin, bucket) groups: inside a bin the positions ascend, so a bucket is a contiguous range
+  const int T = P.L.T;
+  P.ogrp.assign((size_t)K * (size_t)(T + 2), 0);
+  for (int k = 0; k < K; ++k) {
+    const int32_t* lo_p = P.oord.data() + O.kstart[k];
+    const int32_t* hi_p = P.oord.data() + O.kstart[k + 1];
+    for (int b = 0; b <= T + 1; ++b)
+      P.ogrp[(size_t)k * (size_t)(T + 2) + (size_t)b] = (int32_t)(std::lower_bound(lo_p, hi_p, (int32_t)P.L.bstart[b]) - P.oord.data());
+  }
 }
 
 // pt_col: n_cells doubles with NaN = not in lineage.  size_factor may be null.

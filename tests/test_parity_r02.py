@@ -447,3 +447,39 @@ def test_batch_streams_do_not_change_records():
             assert all(_rec_bytes(a) == _rec_bytes(b) for a, b in zip(ref, got)), kw
             got, _ = api.run_records(counts.shape[0], pt, size_factor, api._opts(gpu_ids=[0], **kw), device_ptr=d_counts.data_ptr(), device=0)
             assert all(_rec_bytes(a) == _rec_bytes(b) for a, b in zip(ref, got)), kw
+
+
+def test_hybrid_theta_nodes_vs_cell_walk():
+    """Fits with a size-factor offset (hybrid final stage): theta.ml at fixed mu on the Chebyshev nodes of the (offset bin,
+    bucket) groups against the same Newton steps walked over every cell -- identical schedules (alternations, IRLS iterations,
+    passes) and statistics far below the 1e-6 parity bar; two lineages with NaN membership, wide and narrow offset ranges."""
+    from sclane_b200 import api
+    from tools import synth
+    counts, pt, _ = synth.make_counts(240, 30000, seed=17)
+    x = pt.reshape(-1)
+    rng = np.random.default_rng(4)
+    pt2 = np.stack([np.where(rng.uniform(size=x.size) < 0.7, x, np.nan), np.where(rng.uniform(size=x.size) < 0.5, 1.0 - x, np.nan)], axis=1)
+    for spread in (0.25, 1.2):
+        sf = np.exp(rng.normal(0, spread, x.size))
+        try:
+            os.environ["SCLANE_THETA_NODES"] = "1"
+            a, _ = api.run_records(counts, pt2, sf, api._opts(gpu_ids=[0]))
+            os.environ["SCLANE_THETA_NODES"] = "0"
+            b, _ = api.run_records(counts, pt2, sf, api._opts(gpu_ids=[0]))
+        finally:
+            os.environ.pop("SCLANE_THETA_NODES", None)
+        worst, n_fit, n_hinge = 0.0, 0, 0
+        for ra, rb in zip(a, b):
+            assert ra.status == rb.status and ra.n_terms == rb.n_terms
+            if ra.status != 3:
+                continue
+            runaway = ra.theta > 1e3 or rb.theta > 1e3           # theta.ml's likelihood is flat there
+            if not runaway:
+                assert ra.alternations == rb.alternations and ra.irls_iters == rb.irls_iters and ra.fit_passes == rb.fit_passes
+            n_fit += 1
+            n_hinge += ra.n_terms > 1
+            for u_, v_ in ((ra.loglik, rb.loglik), (ra.deviance, rb.deviance), (ra.test_stat, rb.test_stat)) + tuple(zip(ra.coef[:ra.n_terms], rb.coef[:rb.n_terms])):
+                worst = max(worst, rel(u_, v_, 1e-3))
+            if not runaway:
+                worst = max(worst, rel(ra.theta, rb.theta))
+        assert n_fit > 300 and n_hinge > 150 and worst < 1e-9, (n_fit, n_hinge, worst)
