@@ -146,7 +146,34 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
 
+    def _run_nvml(self) -> bool:
+        """In-process NVML polling (no fork, no second NVML client): an nvidia-smi child every 200 ms costs the timed steps
+        milliseconds of driver-lock and GIL stalls, which is a visible share of a 10 ms step."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for bit, name in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
+        return True
+
     def run(self):
+        if self._run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -429,6 +456,7 @@ def main():
     barrier()
     launches = sb.launch_count()
     ms_step = float(np.mean(wall_steps))
+    wall_steps_value = list(wall_steps)
     # stage breakdown: the same step with strictly sequential batches, so that the CUDA-event intervals of the stages add up
     # (with two batches in flight the intervals of the two streams overlap)
     seq_wall = []
@@ -549,6 +577,7 @@ def main():
             "gpu_launches": int(launches),
             "device_event_ms_per_step": event_ms,
             "sequential_wall_ms_per_step": float(np.mean(seq_wall)),
+            "wall_ms_of_each_step": [round(v, 3) for v in wall_steps_value],
             "stage_ms_per_step": stage_ms,
             "roofline": roofline,
             "fits": fits,

@@ -417,6 +417,11 @@ void launch_stage(const StageArgs& A, cudaStream_t s) {
 }
 
 // theta.ml on Chebyshev nodes in k_comp_stage<FINAL> (sclane_comp.cuh); SCLANE_THETA_NODES=0 walks the points instead (A/B).
+// bucket nodes of the X-compressed route (sclane_comp.cuh); SCLANE_BUCKET_NODES=0 walks the points instead (A/B, tests)
+bool bucket_nodes_enabled() {
+  const char* e = std::getenv("SCLANE_BUCKET_NODES");
+  return !(e && e[0] == '0');
+}
 bool theta_nodes_enabled() {
   const char* e = std::getenv("SCLANE_THETA_NODES");      // read per call: the tests switch it inside one process
   return !(e && e[0] == '0');
@@ -742,7 +747,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   auto batch_size = [&](int Npad, int Dpad, bool use_comp) -> int64_t {
     const size_t per_gene_slot = (size_t)Npad * 12 + sizeof(GeneOutDev) + sizeof(GeneStats) +
                                  (size_t)NBMAX * NACC * 8 + (use_comp ? (size_t)Dpad * 16 + (size_t)kHistCap * 4 + (size_t)kBigCap * 8 + sizeof(CompGeneDev) : 0) +
-                                 (o.approx_knot ? 0 : (size_t)Dpad * 16) + (use_offset ? 3 * (size_t)kHtCap * 8 + (size_t)(kOffKMax * kOffJ) * 16 : 0);
+                                 (o.approx_knot ? 0 : (size_t)Dpad * 16) + (size_t)(NBMAX * kOffJ) * 16 + (use_offset ? 3 * (size_t)kHtCap * 8 + (size_t)(kOffKMax * kOffJ) * 16 : 0);
     const size_t per_gene = (h_counts ? (size_t)n_cells * 8 : 0) + (size_t)n_slots * per_gene_slot;
     size_t budget = (size_t)((double)(free_b + pool_held) * 0.6);
     const size_t cap = (size_t)SCLANE_BATCH_CAP_GB << 30;
@@ -852,6 +857,16 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   // a batch are a chain of ~10 dependent launches, each ending in a tail of half-empty SMs (one CTA per gene, gene cost varies
   // 10x), and between two batches the device used to wait for the host (D2H of the records, their finalisation, the next
   // batch's launches).  With two chains in flight the block scheduler fills the tail of one with the CTAs of the other.
+  // bucket nodes of the X-compressed route: the gene independent part, once per lineage
+  BucketNodes* d_bn = nullptr;
+  if (use_comp && !exact && bucket_nodes_enabled()) {
+    d_bn = (BucketNodes*)pool.get("bucket_nodes", sizeof(BucketNodes));
+    k_bucket_nodes<<<1, kThreads, 0, s>>>(D.lin, D.pn, D.pu, D.pbstart, d_bn);
+    CK(cudaGetLastError());
+    g_launches.fetch_add(1);
+    prof.launches[SCLANE_STAGE_PLAN]++;
+    CK(cudaStreamSynchronize(s));                   // the other batch slots' streams read it
+  }
   // hybrid final stage (offsets): theta.ml on Chebyshev nodes of the (offset bin, bucket) groups (sclane_device.cuh)
   const bool hyb_theta_nodes = use_offq && !exact && theta_nodes_enabled() && P.ON.K * (L.T + 1) <= kHtUnits;
   struct Slot {
@@ -861,6 +876,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
     CompGeneDev* d_cg = nullptr; double* d_off_s = nullptr; double* d_off_q = nullptr; OffGeneDev* d_offg = nullptr; int* d_counters = nullptr;
     double* d_a0p = nullptr; double* d_b0p = nullptr; double* d_ex_scratch = nullptr;
     double* d_ht = nullptr;            // hybrid final stage: theta.ml node lists, [B][3][kHtCap]
+    double* d_bn_s = nullptr; double* d_bn_q = nullptr;      // bucket nodes: per-gene node weights [B][NBMAX][16]
     std::unique_ptr<EventTimer> tm;
     int64_t b0 = 0; int nb = 0; bool busy = false;
   };
@@ -890,6 +906,10 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       Z.d_big = (int*)pool.get("comp_big" + sfx, (size_t)B * (size_t)kBigCap * 4);
       Z.d_big_tmp = (int*)pool.get("comp_big_tmp" + sfx, (size_t)B * (size_t)kBigCap * 4);
       Z.d_cg = (CompGeneDev*)pool.get("comp_hdr" + sfx, (size_t)B * sizeof(CompGeneDev));
+      if (d_bn) {
+        Z.d_bn_s = (double*)pool.get("bn_s" + sfx, (size_t)B * (size_t)(NBMAX * kOffJ) * 8);
+        Z.d_bn_q = (double*)pool.get("bn_q" + sfx, (size_t)B * (size_t)(NBMAX * kOffJ) * 8);
+      }
     }
     Z.d_okeys = (double*)pool.get("order_keys" + sfx, (size_t)B * 8);
     Z.d_order = (int*)pool.get("order" + sfx, (size_t)B * 4);
@@ -1008,11 +1028,19 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
       CA.lineage = D.lin; CA.pstart = D.pstart; CA.pn = D.pn; CA.pu = D.pu; CA.pb = D.pb; CA.pbstart = D.pbstart; CA.D = P.D; CA.Dpad = Dpad; CA.ys = d_ys;
       CA.s1 = d_s1; CA.q = d_q; CA.tail = d_tail; CA.big = d_big; CA.big_tmp = d_big_tmp; CA.cg = d_cg; CA.stats = d_stats; CA.out = d_out; CA.n_genes = nb; CA.M = o.M;
       CA.n_iter = n_iter; CA.tols_score = o.tols_score; CA.compute_stats = 1; CA.a0p = d_a0p; CA.b0p = d_b0p;
+      CA.bn = d_bn; CA.bn_s = Z.d_bn_s; CA.bn_q = Z.d_bn_q;
       tm.mark(SCLANE_STAGE_AGGREGATE);
       k_aggregate<<<nb, kThreads, 0, s>>>(CA);
       CK(cudaGetLastError());
       g_launches.fetch_add(1);
       prof.launches[SCLANE_STAGE_AGGREGATE]++;
+      if (d_bn) {
+        const long long units = (long long)nb * (L.T + 1);
+        k_gene_bucket_nodes<<<(unsigned)((units + kWarps - 1) / kWarps), kThreads, 0, s>>>(CA);
+        CK(cudaGetLastError());
+        g_launches.fetch_add(1);
+        prof.launches[SCLANE_STAGE_AGGREGATE]++;
+      }
       tm.mark(SCLANE_STAGE_COMP_FWD);
       if (exact) {
         // forward + backward pass (+ the final fits when there is no offset) of every gene, per-gene buckets

@@ -301,8 +301,24 @@ SC_HD void offnode_contrib(double n, double s, double q, double o, double a, dou
 constexpr int kThCap = 1024;             // node-list entries (shared memory: 3 doubles each)
 constexpr double kThBinWidth = 0.75;
 
+// Bucket nodes: the points of a knot bucket condensed ONCE per gene into 16 Chebyshev nodes along u (fit independent).
+// Every sum of every pass is  sum_d [n_d A(u_d) + s_d B(u_d) + q_d C(u_d)]  with A, B, C analytic functions of z = a_b + c_b u
+// (times a power of u); point_contrib() is linear in (n, s, q), so evaluating it at the 16 nodes of the bucket with the node
+// weights (N_j, S_j, Q_j) = sum_d (n_d, s_d, q_d) l_j(xi_d) gives the sums of the degree-15 interpolant -- as for the offset
+// quadrature above and with the same bound: while |c_b| x (width of the bucket in u) <= kThBinWidth the error is below fp64
+// rounding; a bucket whose slope is steeper in some pass walks its points in that pass.  A pass over a 385-point bucket
+// (200,000 cells) becomes 16 evaluations.
+struct BucketNodes {                     // per lineage (gene independent part)
+  int elig[NBMAX];                       // 1 = the bucket has a node set (enough points to pay)
+  double ulo[NBMAX], uw[NBMAX];          // smallest coordinate / width in u of the bucket's points
+  double un[NBMAX][16];                  // node coordinates
+  double nn[NBMAX][16];                  // node weights of the cells
+};
+constexpr int kBnMinPoints = 48;
+
 struct ThetaNodes {
   int on;                                // 0: the list does not fit / would not pay -> theta passes walk the points
+  int skip;                              // 1: every sloped bucket runs on its bucket nodes in this theta.ml call, no list needed
   int n;                                 // entries
   int first[NBMAX + 1];                  // first entry of bucket b
   int bins[NBMAX + 1];                   // 0 = flat or empty bucket (one entry), -1 = the bucket's points as they are, K >= 1 = K bins

@@ -43,7 +43,61 @@ struct CompArgs {
   int theta_nodes;              // k_comp_stage<FINAL>: theta.ml on Chebyshev nodes (needs sizeof(ThetaNodes) bytes of dynamic shared memory)
   double* a0p;                  // optional [B][Dpad]: glm.fit start sums per point (sum w0, sum w0 z0) for the exact-knot kernels
   double* b0p;
+  const BucketNodes* bn = nullptr;   // bucket nodes (sclane_comp.cuh) or nullptr: every sloped bucket walks its points
+  double* bn_s = nullptr;            // [B][NBMAX][16] node weights of sum y
+  double* bn_q = nullptr;            // [B][NBMAX][16] node weights of sum y^2
 };
+
+// Chebyshev moments of val[] over the points [p0, p1) of one bucket -> the 16 node weights; lanes j and j + 16 both hold node
+// j's weight of `val_lo` (lanes 0-15) / `val_hi` (lanes 16-31).  All 32 lanes must call.
+__device__ __forceinline__ double bucket_node_weight(const double* __restrict__ val_lo, const double* __restrict__ val_hi, const double* __restrict__ pu,
+                                                     int p0, int p1, double ulo, double uw) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15;
+  const double* __restrict__ val = half ? val_hi : val_lo;
+  const double sc2 = uw > 0.0 ? 2.0 / uw : 0.0;
+  double cm[kOffJ];
+#pragma unroll
+  for (int m = 0; m < kOffJ; ++m) cm[m] = 0.0;
+  if (val != nullptr) {
+    for (int d = p0 + j; d < p1; d += 16) {
+      const double v = val[d];
+      double xi = sc2 * (pu[d] - ulo) - 1.0;
+      xi = fmin(1.0, fmax(-1.0, xi));
+      double t0 = 1.0, t1 = xi;
+      cm[0] += v; cm[1] += v * xi;
+#pragma unroll
+      for (int m = 2; m < kOffJ; ++m) { const double t2 = 2.0 * xi * t1 - t0; cm[m] += v * t2; t0 = t1; t1 = t2; }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < kOffJ; ++m) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) cm[m] += __shfl_xor_sync(0xffffffffu, cm[m], o);
+  }
+  double sacc = 0.0;
+#pragma unroll
+  for (int m = kOffJ - 1; m >= 1; --m) sacc += cospi((double)(m * (2 * j + 1)) / (double)(2 * kOffJ)) * cm[m];
+  return (cm[0] + 2.0 * sacc) * (1.0 / (double)kOffJ);
+}
+
+// gene independent part of the bucket nodes, once per lineage: one warp per bucket
+__global__ void __launch_bounds__(kThreads) k_bucket_nodes(const Lineage* __restrict__ lineage, const double* __restrict__ pn, const double* __restrict__ pu,
+                                                           const int* __restrict__ pbstart, BucketNodes* __restrict__ bn) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = lineage->T;
+  for (int b = warp; b < NBMAX; b += kWarps) {
+    const int p0 = b <= T ? pbstart[b] : 0, p1 = b <= T ? pbstart[b + 1] : 0;
+    const int P = p1 - p0;
+    const double ulo = P > 0 ? pu[p0] : 0.0, uw = P > 0 ? pu[p1 - 1] - ulo : 0.0;     // points are sorted by u inside a bucket
+    const bool ok = P >= kBnMinPoints && uw > 0.0;
+    const double w = ok ? bucket_node_weight(pn, nullptr, pu, p0, p1, ulo, uw) : 0.0;
+    if (lane == 0) { bn->elig[b] = ok ? 1 : 0; bn->ulo[b] = ulo; bn->uw[b] = uw; }
+    if (lane < kOffJ) {
+      bn->nn[b][lane] = w;
+      bn->un[b][lane] = ulo + 0.5 * (cospi((double)(2 * lane + 1) / (double)(2 * kOffJ)) + 1.0) * uw;
+    }
+  }
+}
 
 #ifndef SCLANE_COMP_WARPS
 #define SCLANE_COMP_WARPS 8
@@ -253,6 +307,22 @@ __global__ void __launch_bounds__(kThreads) k_aggregate(CompArgs A) {
   }
 }
 
+// Bucket nodes of every gene (its own kernel: inside k_aggregate the 16 moment registers cost that kernel two resident CTAs per
+// SM): one warp per (gene, bucket) builds the Chebyshev moments of s_d and q_d over the bucket's points -> 2 x 16 node weights.
+__global__ void __launch_bounds__(kThreads) k_gene_bucket_nodes(CompArgs A) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = A.lineage->T;
+  const long long unit = (long long)blockIdx.x * kWarps + warp;
+  const int g = (int)(unit / (T + 1)), b = (int)(unit - (long long)g * (T + 1));
+  if (g >= A.n_genes) return;
+  if (!A.bn->elig[b] || A.cg[g].hdr.route == 0) return;              // warp-uniform
+  const double* __restrict__ s1 = A.s1 + (size_t)g * (size_t)A.Dpad;
+  const double* __restrict__ q = A.q + (size_t)g * (size_t)A.Dpad;
+  const double w = bucket_node_weight(s1, q, A.pu, A.pbstart[b], A.pbstart[b + 1], A.bn->ulo[b], A.bn->uw[b]);
+  double* dst = (lane < kOffJ ? A.bn_s : A.bn_q) + (size_t)g * (size_t)(NBMAX * kOffJ) + b * kOffJ + (lane & 15);
+  *dst = w;
+}
+
 // Pure permutation copy (the compressed route's replacement of k_gather_stats): K CTAs per gene, so that the rows being
 // gathered at any moment fit in L2 and the 4-byte random reads of a row are served from there instead of costing a
 // 32-byte DRAM sector each.
@@ -296,6 +366,12 @@ struct CompDevExec {
   const double* __restrict__ px;    // exact-knot mode: abscissa per point, u = px[d] - ref[bucket] (the buckets are per gene); else nullptr
   ThetaNodes* tn;                   // theta.ml node list (shared memory; sclane_comp.cuh) or nullptr: theta passes walk the points
   const double (*ctab)[kOffJ];      // T_m(xi_j) table (shared memory) when tn is set
+  const BucketNodes* bn = nullptr;  // bucket nodes (global memory) or nullptr
+  const double* __restrict__ bs = nullptr;      // this gene's node weights of sum y   [NBMAX][16]
+  const double* __restrict__ bq = nullptr;      // ... of sum y^2
+  __device__ __forceinline__ bool on_bucket_nodes(int b, double c) const {
+    return bn != nullptr && px == nullptr && bn->elig[b] && fabs(c) * bn->uw[b] <= kThBinWidth;
+  }
 
   __device__ __forceinline__ double u_of(int b, int d) const { return px ? px[d] - L->ref[b] : pu[d]; }
 
@@ -307,6 +383,17 @@ struct CompDevExec {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = L->T;
     __syncthreads();
+    if (bn != nullptr && px == nullptr) {
+      // every sloped bucket on its bucket nodes: the Newton steps need no list of their own
+      if (threadIdx.x == 0) {
+        int ok = 1;
+        for (int b = 0; b <= T; ++b) { const double c = W->c[b]; if (c != 0.0 && !on_bucket_nodes(b, c)) ok = 0; }
+        tn->skip = ok;
+        if (ok) { tn->on = 0; tn->n = 0; }
+      }
+      __syncthreads();
+      if (tn->skip) return;
+    }
     if (threadIdx.x == 0) theta_nodes_layout(*tn, T, W->c, pbstart, [&](int b, int d) { return u_of(b, d); });
     __syncthreads();
     if (!tn->on) return;
@@ -445,7 +532,11 @@ struct CompDevExec {
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
       const int p1 = pbstart[b + 1];
-      if (px) {
+      if (on_bucket_nodes(b, c)) {
+        if (lane < kOffJ)
+          point_contrib<MODE>(__ldg(&bn->nn[b][lane]), bs[b * kOffJ + lane], MODE == PASS_IRLS ? bq[b * kOffJ + lane] : 0.0, __ldg(&bn->un[b][lane]), a, c,
+                              sigma, theta, want_ll, ft, acc, sc);
+      } else if (px) {
         const double refb = L->ref[b];
 #pragma unroll kCompUnroll
         for (int d = pbstart[b] + lane; d < p1; d += 32)
@@ -539,6 +630,7 @@ __global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(C
   const long long t_start = clock64();
   CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, pbs, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
                  A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, scw, &ftab, nullptr, tn, ctab};
+  if (A.bn != nullptr) { ex.bn = A.bn; ex.bs = A.bn_s + (size_t)g * (size_t)(NBMAX * kOffJ); ex.bq = A.bn_q + (size_t)g * (size_t)(NBMAX * kOffJ); }
   if (STAGE == CSTAGE_FORWARD) {
     for (int it = 0; it < A.n_iter; ++it) {
       gene_forward_fit(ex, Ls, gs, st, W);

@@ -483,3 +483,35 @@ def test_hybrid_theta_nodes_vs_cell_walk():
             if not runaway:
                 worst = max(worst, rel(ra.theta, rb.theta))
         assert n_fit > 300 and n_hinge > 150 and worst < 1e-9, (n_fit, n_hinge, worst)
+
+
+@pytest.mark.parametrize("n_genes,n_cells", [(400, 10000), (96, 200000)])
+def test_bucket_nodes_vs_point_walk(n_genes, n_cells):
+    """X-compressed route: every pass over a sloped knot bucket on the bucket's 16 Chebyshev nodes (sclane_comp.cuh: BucketNodes)
+    against the same pass walked over the bucket's abscissae -- the same discrete choices (forward / backward term sets, glm.nb
+    schedules) and statistics far below the 1e-6 parity bar."""
+    from sclane_b200 import api
+    from tools import synth
+    counts, pt, _ = synth.make_counts(n_genes, n_cells, seed=33)
+    try:
+        os.environ["SCLANE_BUCKET_NODES"] = "1"
+        a, _ = api.run_records(counts, pt, None, api._opts(gpu_ids=[0]))
+        os.environ["SCLANE_BUCKET_NODES"] = "0"
+        b, _ = api.run_records(counts, pt, None, api._opts(gpu_ids=[0]))
+    finally:
+        os.environ.pop("SCLANE_BUCKET_NODES", None)
+    worst, n_fit, n_sched = 0.0, 0, 0
+    for ra, rb in zip(a, b):
+        assert ra.status == rb.status and ra.n_terms == rb.n_terms
+        assert list(ra.term_kind[:ra.n_terms]) == list(rb.term_kind[:rb.n_terms]) and list(ra.term_knot_idx[:ra.n_terms]) == list(rb.term_knot_idx[:rb.n_terms])
+        assert list(ra.fwd_kind[:ra.fwd_n_terms]) == list(rb.fwd_kind[:rb.fwd_n_terms]) and list(ra.fwd_knot_idx[:ra.fwd_n_terms]) == list(rb.fwd_knot_idx[:rb.fwd_n_terms])
+        if ra.status != 3:
+            continue
+        n_fit += 1
+        runaway = ra.theta > 1e3 or rb.theta > 1e3
+        n_sched += (ra.alternations == rb.alternations and ra.irls_iters == rb.irls_iters)
+        for u_, v_ in ((ra.loglik, rb.loglik), (ra.deviance, rb.deviance), (ra.test_stat, rb.test_stat), (ra.null_loglik, rb.null_loglik)) + tuple(zip(ra.coef[:ra.n_terms], rb.coef[:rb.n_terms])) + tuple(zip(ra.se[:ra.n_terms], rb.se[:rb.n_terms])):
+            worst = max(worst, rel(u_, v_, 1e-3))
+        if not runaway:
+            worst = max(worst, rel(ra.theta, rb.theta))
+    assert n_fit > 0.8 * n_genes and n_sched >= n_fit - 2 and worst < 1e-9, (n_fit, n_sched, worst)
