@@ -395,8 +395,7 @@ void device_k0(DevicePool& pool, cudaStream_t s, const double* pt_col, int64_t n
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) prof->ms[SCLANE_STAGE_PLAN] += ms;
     prof->launches[SCLANE_STAGE_PLAN] += launches;
-    prof->h2d_bytes += (double)n_cells * 8.0;
-    prof->d2h_bytes += (double)sizeof(K0Result);
+    // (h2d_bytes / d2h_bytes count the counts and the records, as with the host plan, whose tables were not counted either)
   }
   hdr.L = h_res->L;
   hdr.D = h_res->D;
