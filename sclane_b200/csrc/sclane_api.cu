@@ -881,7 +881,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   };
   static int sm_count[SCLANE_MAX_GPUS] = {0};
   if (sm_count[device % SCLANE_MAX_GPUS] == 0) { int v = 0; CK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); sm_count[device % SCLANE_MAX_GPUS] = v; }
-  const int ex_slots = sm_count[device % SCLANE_MAX_GPUS] * 2;
+  const int ex_slots = sm_count[device % SCLANE_MAX_GPUS] * kExactCtasPerSm;
   std::vector<Slot> slots((size_t)n_slots);
   for (int si = 0; si < n_slots; ++si) {
     Slot& Z = slots[(size_t)si];

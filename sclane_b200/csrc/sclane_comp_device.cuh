@@ -100,12 +100,21 @@ __global__ void __launch_bounds__(kThreads) k_bucket_nodes(const Lineage* __rest
 }
 
 #ifndef SCLANE_COMP_WARPS
-#define SCLANE_COMP_WARPS 8
+#define SCLANE_COMP_WARPS 4
 #endif
 #ifndef SCLANE_COMP_MINB
-#define SCLANE_COMP_MINB 3
+#define SCLANE_COMP_MINB 8              // forward / backward stage: resident CTAs per SM the launch bounds ask for
 #endif
-// CTA shape of k_comp_stage.  Measured on B200 (C5 / C2 ms per step): 8 warps x 3 CTAs/SM 144.4 / 12.7, 4 x 6 150.0 / 13.6,
+#ifndef SCLANE_COMP_MINB_FINAL
+#define SCLANE_COMP_MINB_FINAL 4        // final stage (glm.nb: more live state; 128 registers per thread instead of 64)
+#endif
+// CTA shape of k_comp_stage.  With the bucket nodes (sclane_comp.cuh) a pass is 16 evaluations per sloped bucket and the kernels are
+// bound by the serial algebra between the passes and its barriers (ncu: 10-15 barrier stalls per issued instruction at 8 warps), so
+// many small CTAs per SM win.  Measured on B200, C5 ms of forward / backward / final stage (C2 step ms): 8 warps x 3 CTAs/SM
+// 13.0 / 12.7 / 19.9 (8.3); 4 x 6 11.5 / 8.7 / 19.8 (7.5); 4 x 4 11.7 / 10.4 / 16.4 (7.5); 2 x 12 11.2 / 9.0 / 21.9 (9.4);
+// 4 x 8 for forward + backward with 4 x 4 for the final stage 11.1 / 8.1 / 16.4 (6.8) <- default; 4 x 6 + 4 x 3 11.6 / 8.8 / 19.1;
+// 2 x 12 + 2 x 8 11.1 / 9.0 / 20.2 (14.1).
+// BEFORE the bucket nodes the passes were throughput bound and the opposite held (C5 / C2 ms per step): 8 warps x 3 CTAs/SM 144.4 / 12.7, 4 x 6 150.0 / 13.6,
 // 8 x 4 (64 registers) 143.3 / 13.2, 4 x 4 154.8 / 14.1, 8 x 2 167.8 / 13.7, 2 x 12 178.6 / 17.6 -- the passes are throughput bound, not leader-latency bound.
 // Also measured and rejected (same units; baseline 144.7 / 12.7): an exactly balanced split of the sloped points over the
 // warps with per-warp partial sums 153.9 / 13.9; two points per lane per iteration 161.4 / 14.9 (80 registers) and
@@ -583,7 +592,7 @@ struct CompDevExec {
 enum CompStage : int { CSTAGE_FORWARD = 0, CSTAGE_BACKWARD = 1, CSTAGE_FINAL = 2 };
 
 template <int STAGE>
-__global__ void __launch_bounds__(kCompThreads, SCLANE_COMP_MINB) k_comp_stage(CompArgs A) {
+__global__ void __launch_bounds__(kCompThreads, STAGE == CSTAGE_FINAL ? SCLANE_COMP_MINB_FINAL : SCLANE_COMP_MINB) k_comp_stage(CompArgs A) {
   __shared__ Work W;
   __shared__ Lineage Ls;
   __shared__ GeneState st;

@@ -404,7 +404,8 @@ __device__ void exact_sweep(ExactShared& S, CompDevExec& ex, const ExactArgs& A,
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kCompThreads, 2) k_exact(ExactArgs A) {
+constexpr int kExactCtasPerSm = 16 / kCompWarps;       // 16 warps per SM whatever the CTA shape of the compressed kernels
+__global__ void __launch_bounds__(kCompThreads, kExactCtasPerSm) k_exact(ExactArgs A) {
   extern __shared__ __align__(16) unsigned char ex_smem[];
   ExactShared& S = *reinterpret_cast<ExactShared*>(ex_smem);
   __shared__ int g_s;

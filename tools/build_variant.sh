@@ -3,4 +3,4 @@
 cd "$(dirname "$0")/.."
 name=$1; shift
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --shared -Xcompiler -fPIC -Xcompiler -pthread \
-  -I include "$@" sclane_b200/csrc/sclane_api.cu -o sclane_b200/lib/variant_$name.so && echo built variant_$name
+  -I include "$@" sclane_b200/csrc/sclane_api.cu sclane_b200/csrc/sclane_narrow.cpp -o sclane_b200/lib/variant_$name.so && echo built variant_$name

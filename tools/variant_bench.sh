@@ -1,15 +1,13 @@
 #!/bin/bash
-# times bench.py (C5 and C2) for every prebuilt library variant in sclane_b200/lib/variant_*.so
 cd "$(dirname "$0")/.."
 cp sclane_b200/lib/libsclane_b200.so /tmp/lib_backup.so
 for f in sclane_b200/lib/variant_*.so; do
   cp "$f" sclane_b200/lib/libsclane_b200.so
   for c in c5 c2; do
-    echo "== $f $c"
-    timeout 300 python bench.py --config $c --steps 3 --warmup 2 --cpu-sample 0 2>&1 | tail -1 | python -c "
+    python bench.py --config $c --steps 3 --warmup 2 --cpu-sample 0 --sweep-genes 0 --no-pageable 2>/dev/null | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
-print('value', round(d['value']), 'ms', round(d['ms_per_step'], 2), 'e2e', round(d['e2e']['value']), 'stages', {k: round(v, 2) for k, v in d['stage_ms_per_step'].items() if v > 0.3})
+print('$f $c', 'value', round(d['value']), 'ms', round(d['ms_per_step'], 2), 'seq', round(d['sequential_wall_ms_per_step'],2), 'stages', {k: round(v, 2) for k, v in d['stage_ms_per_step'].items() if v > 0.3})
 "
   done
 done
