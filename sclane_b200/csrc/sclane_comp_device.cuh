@@ -517,20 +517,44 @@ struct CompDevExec {
       for (int e = threadIdx.x; e < ne; e += kCompThreads)
         point_contrib<MODE>(tn->en[e], tn->es[e], 0.0, 0.0, tn->eeta[e], 0.0, sigma, theta, want_ll, ft, dummy, sc);
     }
+    // Since the bucket nodes a pass is short and its latency is what counts (the kernels wait at the barrier behind it), so the
+    // work of a pass is spread as widely as the warp allows:
+    //   flat buckets     one closed-form evaluation each, flat bucket f on lane f / kCompWarps of warp f % kCompWarps (all at once);
+    //   node buckets     16 evaluations each, two buckets per warp step (one per half warp, half-warp shuffle trees);
+    //   the rest         (slope too steep for the nodes in this pass, few points, exact-knot mode) walks its points, warp per bucket.
+    // Every sum still runs in a fixed order -> bit-reproducible.
+    const int half = lane >> 4, hl = lane & 15;
+    int n_flat = 0, n_node = 0, my_flat = -1, pend_b = -1;
+    auto node_pair = [&](int b0, int b1) {           // warp-uniform call; b1 may be -1
+      const int mb = half ? b1 : b0;
+      double acc[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+      if (mb >= 0)
+        point_contrib<MODE>(__ldg(&bn->nn[mb][hl]), bs[mb * kOffJ + hl], MODE == PASS_IRLS ? bq[mb * kOffJ + hl] : 0.0, __ldg(&bn->un[mb][hl]), W->a[mb], W->c[mb],
+                            sigma, theta, want_ll, ft, acc, sc);
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        double t = acc[k];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (hl == 0 && mb >= 0) W->acc[mb][k] = t;
+      }
+    };
 #pragma unroll 1
     for (int b = 0; b <= (on_nodes ? -1 : T); ++b) {
       const double c = W->c[b];
       if (c == 0.0) {
-        if ((b & (kCompWarps - 1)) != warp) continue;
-        double fa[NACC];
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) fa[k] = 0.0;
-        if (lane == 0) {
-          flat_bucket_contrib<MODE>(L->U0[b], L->U1[b], L->U2[b], cg->hdr.SB[b], cg->hdr.SBu[b], cg->hdr.SBuu[b], cg->hdr.QB[b], W->a[b], sigma,
-                                    theta, want_ll, ft, fa, sc);
-#pragma unroll
-          for (int k = 0; k < NA; ++k) W->acc[b][k] = fa[k];
-        }
+        const int f = n_flat++;
+        if ((f & (kCompWarps - 1)) == warp && (f / kCompWarps) == lane) my_flat = b;
+        continue;
+      }
+      if (on_bucket_nodes(b, c)) {
+        const int h = n_node++;
+        if (((h >> 1) & (kCompWarps - 1)) != warp) continue;
+        if ((h & 1) == 0) { pend_b = b; continue; }
+        node_pair(pend_b, b);
+        pend_b = -1;
         continue;
       }
       const int owner = n_sloped & (kCompWarps - 1);
@@ -541,11 +565,7 @@ struct CompDevExec {
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
       const int p1 = pbstart[b + 1];
-      if (on_bucket_nodes(b, c)) {
-        if (lane < kOffJ)
-          point_contrib<MODE>(__ldg(&bn->nn[b][lane]), bs[b * kOffJ + lane], MODE == PASS_IRLS ? bq[b * kOffJ + lane] : 0.0, __ldg(&bn->un[b][lane]), a, c,
-                              sigma, theta, want_ll, ft, acc, sc);
-      } else if (px) {
+      if (px) {
         const double refb = L->ref[b];
 #pragma unroll kCompUnroll
         for (int d = pbstart[b] + lane; d < p1; d += 32)
@@ -560,6 +580,16 @@ struct CompDevExec {
         const double t = warp_sum(acc[k]);
         if (lane == 0) W->acc[b][k] = t;
       }
+    }
+    if (pend_b >= 0) node_pair(pend_b, -1);          // warp-uniform: pend_b is
+    if (my_flat >= 0) {
+      double fa[NACC];
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) fa[k] = 0.0;
+      flat_bucket_contrib<MODE>(L->U0[my_flat], L->U1[my_flat], L->U2[my_flat], cg->hdr.SB[my_flat], cg->hdr.SBu[my_flat], cg->hdr.SBuu[my_flat],
+                                cg->hdr.QB[my_flat], W->a[my_flat], sigma, theta, want_ll, ft, fa, sc);
+#pragma unroll
+      for (int k = 0; k < NA; ++k) W->acc[my_flat][k] = fa[k];
     }
     // the mu-free histogram terms
     if (NS > 0 && MODE != PASS_SWEEP) {
