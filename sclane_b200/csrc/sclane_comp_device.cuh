@@ -339,6 +339,10 @@ __global__ void __launch_bounds__(kThreads) k_gene_bucket_nodes(CompArgs A) {
 // Pure permutation copy (the compressed route's replacement of k_gather_stats): K CTAs per gene, so that the rows being
 // gathered at any moment fit in L2 and the 4-byte random reads of a row are served from there instead of costing a
 // 32-byte DRAM sector each.
+// ncu (profiles/r02_ncu_final_c5.txt): DRAM traffic == the algorithmic 8 B/cell, 1.9 TB/s; the warps wait on the load / store unit
+// (lg_throttle 77, long scoreboard 41 per issued instruction): a warp's gather touches 32 different sectors, and 4e9 such
+// accesses per 20,000 x 200,000 step at ~1 sector per clock and SM are ~14 ms.  Measured and rejected: the same permutation as
+// a scatter (coalesced reads of the caller's row, 4-byte stores to the sorted positions): 29.6 ms against 16.6.
 // RAW = int (the caller's counts) or unsigned short (counts narrowed on the host for the PCIe transfer).
 template <class RAW>
 __global__ void __launch_bounds__(kThreads) k_gather_copy(const RAW* __restrict__ raw, long long ld, const int* __restrict__ perm, int N,
