@@ -57,11 +57,11 @@ CONFIGS = {
 # cell per swept gene + 8 B per cell), and where the FP64 / issue utilisation of the fit kernels is recorded.
 SWEEP_TRAFFIC_RATIO = {"c5": 1.0005, "c2": 1.044}            # profiles/r01_ncu_sweep_c5_full.txt, r01_ncu_sweep_v1.txt
 FIT_NCU = {
-    "comp_forward": {"kernel": "k_comp_stage<FORWARD> (X-compressed: NB null fits + score sweep + selection)", "source": "profiles/r02_ncu_fit_kernels.txt"},
-    "comp_backward": {"kernel": "k_comp_stage<BACKWARD> (X-compressed WIC pass)", "source": "profiles/r02_ncu_fit_kernels.txt"},
-    "comp_final": {"kernel": "k_comp_stage<FINAL> (X-compressed final + null glm.nb)", "source": "profiles/r02_ncu_fit_kernels.txt"},
-    "final": {"kernel": "k_stage<FINAL> (per-cell glm.nb of the alternatives that carry an offset)", "source": "profiles/r02_ncu_fit_kernels.txt"},
-    "off_null": {"kernel": "k_wg_stage<OFFNULL> (offset quadrature, warp per gene)", "source": "profiles/r02_ncu_fit_kernels.txt"},
+    "comp_forward": {"kernel": "k_comp_stage<FORWARD> (X-compressed: NB null fits + score sweep + selection)", "source": "profiles/r02_ncu_final_c5.txt"},
+    "comp_backward": {"kernel": "k_comp_stage<BACKWARD> (X-compressed WIC pass)", "source": "profiles/r02_ncu_final_c5.txt"},
+    "comp_final": {"kernel": "k_comp_stage<FINAL> (X-compressed final + null glm.nb)", "source": "profiles/r02_ncu_final_c5.txt"},
+    "final": {"kernel": "k_stage<FINAL, HYB> (hybrid per-cell glm.nb of the alternatives that carry an offset; theta.ml on nodes)", "source": "profiles/r02_ncu_final_c4.txt"},
+    "off_null": {"kernel": "k_wg_stage<OFFNULL> (offset quadrature, warp per gene)", "source": "profiles/r02_ncu_final_c4.txt"},
     "gee": {"kernel": "k_gee", "source": "profiles/r01_ncu_gee_c3.txt"},
 }
 
@@ -551,7 +551,7 @@ def main():
             roofline = {"kernel": FIT_NCU.get(dom, {}).get("kernel", dom), "bound": "fp64", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None,
                         "traffic": None, "note": "no HBM-bound kernel was timed on this path (GEE mode, or the per-cell leg was skipped): see `fits`"}
         sweep_equiv = prof_acc["sweep_bytes"] / 1e9 / (prof_acc["ms"]["comp_forward"] / 1000.0) if prof_acc["ms"].get("comp_forward", 0) > 0 else None
-        fits = {"dominant_stage": dom, "dominant_kernel": FIT_NCU.get(dom, {}).get("kernel", dom), "bound": "fp64 pipe / issue latency",
+        fits = {"dominant_stage": dom, "dominant_kernel": FIT_NCU.get(dom, {}).get("kernel", dom), "bound": "serial algebra + barriers between short passes (bucket nodes); fp64 pipe for the per-cell / GEE kernels",
                 "dominant_share_of_step": stage_ms[dom] / max(event_ms, 1e-9), "passes_per_gene_lineage": passes,
                 "ncu": FIT_NCU.get(dom, {}).get("source"),
                 "forward_stage_equivalent_GBps": sweep_equiv,
