@@ -81,6 +81,7 @@ struct HybTheta {                      // shared memory
   int wt[kWarps + 1];
   double ctab[kOffJ][kOffJ];           // T_m(xi_j)
 };
+static_assert(kHtUnits == 2 * kThreads, "theta_prepare() lays out two groups per thread");
 struct HybThetaArgs {
   const OffsetNodes* on;
   const int* oord;                     // [N] sorted-cell positions by (offset bin, position)
