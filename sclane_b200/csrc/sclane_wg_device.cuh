@@ -67,6 +67,10 @@ struct WgExec {
   const double* __restrict__ ons;
   const double* __restrict__ onq;
   const OffGeneDev* offg;
+  // bucket nodes (sclane_comp.cuh) or nullptr
+  const BucketNodes* bn = nullptr;
+  const double* __restrict__ bs = nullptr;
+  const double* __restrict__ bq = nullptr;
 
   __device__ __forceinline__ bool leader() const { return (threadIdx.x & 31) == 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
@@ -143,11 +147,35 @@ struct WgExec {
           for (int k = 0; k < NA; ++k) W->acc[b][k] = fa[k];
         }
       }
-      // sloped buckets: lane-strided over the bucket's points
+      // sloped buckets: on their 16 bucket nodes, two buckets per step (one per half warp), or lane-strided over the bucket's points
+      const int half = lane >> 4, hl = lane & 15;
+      auto node_pair = [&](int b0, int b1) {
+        const int mb = half ? b1 : b0;
+        double acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+        if (mb >= 0)
+          point_contrib<MODE>(__ldg(&bn->nn[mb][hl]), bs[mb * kOffJ + hl], MODE == PASS_IRLS ? bq[mb * kOffJ + hl] : 0.0, __ldg(&bn->un[mb][hl]), W->a[mb], W->c[mb],
+                              sigma, theta, want_ll, ft, acc, sc);
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+          double t = acc[k];
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (hl == 0 && mb >= 0) W->acc[mb][k] = t;
+        }
+      };
+      int pend = -1;
 #pragma unroll 1
       for (int b = 0; b <= T; ++b) {
         const double c = W->c[b];
         if (c == 0.0) continue;                      // warp-uniform
+        if (bn != nullptr && bn->elig[b] && fabs(c) * bn->uw[b] <= kThBinWidth) {
+          if (pend < 0) { pend = b; continue; }
+          node_pair(pend, b);
+          pend = -1;
+          continue;
+        }
         const double a = W->a[b];
         double acc[NACC];
 #pragma unroll
@@ -162,6 +190,7 @@ struct WgExec {
           if (lane == 0) W->acc[b][k] = t;
         }
       }
+      if (pend >= 0) node_pair(pend, -1);
     }
     if (NS > 0 && MODE != PASS_SWEEP) hist_terms<MODE>(sc, sigma, theta, want_ll);
     if (NS > 0) {
@@ -224,6 +253,7 @@ __global__ void __launch_bounds__(kWgThreads, SCLANE_WG_MINB) k_wg_stage(WgArgs 
               A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, &ftab,
               offmode ? WA.on : nullptr, offmode ? WA.off_s + (size_t)g * (size_t)(kOffKMax * kOffJ) : nullptr,
               offmode ? WA.off_q + (size_t)g * (size_t)(kOffKMax * kOffJ) : nullptr, offmode ? WA.offg + g : nullptr};
+    if (!offmode && A.bn != nullptr) { ex.bn = A.bn; ex.bs = A.bn_s + (size_t)g * (size_t)(NBMAX * kOffJ); ex.bq = A.bn_q + (size_t)g * (size_t)(NBMAX * kOffJ); }
     if (STAGE == WG_FORWARD) {
       for (int it = 0; it < A.n_iter; ++it) {
         gene_forward_fit(ex, Ls, gs, st, W);
