@@ -64,6 +64,40 @@ def test_candidate_knots_host_vs_oracle(n, seed, golden_inputs):
     assert ms == int(np.rint(-np.log2(-(1.0 / n) * np.log(0.95)) / 2.5))
 
 
+@pytest.mark.parametrize("case", ["uniform", "nan-membership", "ties"])
+def test_lineage_plan_host_tables(case):
+    """sclane_lineage_plan (host build; the device build is compared with it bit for bit in tests/test_parity_r02.py): knots == the
+    oracle's, the permutation is the stable order by round(x, 4), buckets / coordinates / abscissa tables are consistent."""
+    from sclane_b200 import api
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 1, 6000)
+    if case == "nan-membership":
+        x[rng.uniform(size=x.size) < 0.3] = np.nan
+    if case == "ties":
+        x = np.round(x, 2)
+    P = api.lineage_plan(x)
+    cells = np.flatnonzero(~np.isnan(x))
+    _, ko = oknots.candidate_knots(x[cells])
+    assert P["N"] == cells.size and np.array_equal(P["knots"], np.sort(ko))
+    X = np.array([oknots.r_round(v, 4) for v in x[cells]])
+    order = cells[np.argsort(X, kind="stable")]
+    assert np.array_equal(P["perm"], order)
+    Xs = np.array([oknots.r_round(v, 4) for v in x[P["perm"]]])
+    T = P["T"]
+    bstart = P["bstart"]
+    assert bstart[0] == 0 and bstart[T + 1] == P["N"] and np.array_equal(bstart[1:T + 1], np.searchsorted(Xs, P["knots"], side="left"))
+    ref = np.concatenate([[P["knots"][0]], P["knots"]])
+    bucket = np.searchsorted(bstart[1:T + 1], np.arange(P["N"]), side="right")
+    assert np.array_equal(P["u"], Xs - ref[bucket])
+    for b in range(T + 1):
+        ub = P["u"][bstart[b]:bstart[b + 1]]
+        assert P["U"][0, b] == ub.size and abs(P["U"][1, b] - ub.sum()) <= 1e-12 * max(1.0, abs(ub).sum()) and abs(P["U"][2, b] - (ub * ub).sum()) <= 1e-12
+    starts = np.flatnonzero(np.concatenate([[True], Xs[1:] != Xs[:-1]]))
+    assert P["D"] == starts.size and np.array_equal(P["pstart"], np.concatenate([starts, [P["N"]]]))
+    assert np.array_equal(P["pn"], np.diff(P["pstart"])) and np.array_equal(P["pu"], P["u"][starts]) and np.array_equal(P["pb"], bucket[starts])
+    assert np.array_equal(P["pbstart"], np.searchsorted(starts, bstart, side="left"))
+
+
 def test_scalar_helpers_vs_scipy(emu):
     from scipy.special import digamma, gammaln, polygamma
     from scipy.stats import chi2
