@@ -882,8 +882,9 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   static int sm_count[SCLANE_MAX_GPUS] = {0};
   if (sm_count[device % SCLANE_MAX_GPUS] == 0) { int v = 0; CK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); sm_count[device % SCLANE_MAX_GPUS] = v; }
   const int ex_slots = sm_count[device % SCLANE_MAX_GPUS] * kExactCtasPerSm;
-  std::vector<Slot> slots((size_t)n_slots);
-  for (int si = 0; si < n_slots; ++si) {
+  const int n_slots_used = (int)std::min<int64_t>((int64_t)n_slots, n_batches);      // a single batch needs a single set of buffers
+  std::vector<Slot> slots((size_t)n_slots_used);
+  for (int si = 0; si < n_slots_used; ++si) {
     Slot& Z = slots[(size_t)si];
     if (si == 0) Z.s = s;
     else {
@@ -968,7 +969,7 @@ void run_shard(int device, const int32_t* h_counts, const int32_t* d_counts, int
   for (int64_t b0 = g0, kb = 0; b0 < g1; b0 += B, ++kb) {
     const int64_t b1 = std::min<int64_t>(b0 + B, g1);
     const int nb = (int)(b1 - b0);
-    Slot& Z = slots[(size_t)(kb % n_slots)];
+    Slot& Z = slots[(size_t)(kb % n_slots_used)];
     finish(Z);                                        // the batch that used this slot before (no-op for the first n_slots batches)
     Z.b0 = b0; Z.nb = nb; Z.busy = true;
     cudaStream_t s = Z.s;
