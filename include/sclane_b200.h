@@ -207,7 +207,9 @@ void sclane_reset_launch_count(void);
 #define SCLANE_STAGE_OFF_NULL 13   /* offset quadrature: intercept-only glm.nb with the size-factor offset     */
 #define SCLANE_STAGE_PLAN 14       /* K0 on the device: sort by round(x, 4), candidate knots, bucket / abscissa tables */
 typedef struct sclane_profile {
-  double  ms[SCLANE_NSTAGES];          /* device milliseconds per stage                                   */
+  double  ms[SCLANE_NSTAGES];          /* device milliseconds per stage: CUDA-event intervals on the stream of each gene batch.  With
+                                          batch_streams > 1 (the default is 2) batches run concurrently and their intervals overlap:
+                                          the sum can exceed wall_ms; set batch_streams = 1 for a breakdown that adds up            */
   int64_t launches[SCLANE_NSTAGES];    /* kernel launches (memcpys for SCLANE_STAGE_COPY) per stage        */
   double  sweep_bytes;                 /* algorithmic bytes the sweep launches moved: sum of 12*N_l per
                                           (gene, forward iteration actually swept) + 8*N_l per launch       */
