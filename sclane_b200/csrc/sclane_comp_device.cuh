@@ -386,8 +386,12 @@ struct CompDevExec {
   const BucketNodes* bn = nullptr;  // bucket nodes (global memory) or nullptr
   const double* __restrict__ bs = nullptr;      // this gene's node weights of sum y   [NBMAX][16]
   const double* __restrict__ bq = nullptr;      // ... of sum y^2
+  const double* bnuw = nullptr;     // [NBMAX] shared-memory copy of bn->uw (-1 = bucket without nodes): the test below runs per bucket,
+                                    // per pass and per warp, and as two global loads it was 32 % of the final stage's stall samples
   __device__ __forceinline__ bool on_bucket_nodes(int b, double c) const {
-    return bn != nullptr && px == nullptr && bn->elig[b] && fabs(c) * bn->uw[b] <= kThBinWidth;
+    if (bnuw == nullptr || px != nullptr) return false;
+    const double w = bnuw[b];
+    return w > 0.0 && fabs(c) * w <= kThBinWidth;
   }
 
   __device__ __forceinline__ double u_of(int b, int d) const { return px ? px[d] - L->ref[b] : pu[d]; }
@@ -641,6 +645,7 @@ __global__ void __launch_bounds__(kCompThreads, STAGE == CSTAGE_FINAL ? SCLANE_C
   __shared__ FastTabs ftab;
   __shared__ TermTabs ttab;
   __shared__ double ctab[STAGE == CSTAGE_FINAL ? kOffJ : 1][kOffJ];
+  __shared__ double bnuw_s[NBMAX];
   extern __shared__ double comp_dyn_smem[];                // CSTAGE_FINAL: the theta.ml node list (sizeof(ThetaNodes) bytes)
   if ((int)blockIdx.x >= A.n_genes) return;
   const int g = ((STAGE == CSTAGE_FINAL || STAGE == CSTAGE_BACKWARD) && A.order) ? A.order[blockIdx.x] : (int)blockIdx.x;
@@ -669,6 +674,7 @@ __global__ void __launch_bounds__(kCompThreads, STAGE == CSTAGE_FINAL ? SCLANE_C
     int* w = reinterpret_cast<int*>(&W);
     for (int i = threadIdx.x; i < (int)(sizeof(Work) / sizeof(int)); i += kCompThreads) w[i] = 0;
     for (int i = threadIdx.x; i <= NBMAX; i += kCompThreads) pbs[i] = A.pbstart[i];
+    for (int i = threadIdx.x; i < NBMAX; i += kCompThreads) bnuw_s[i] = (A.bn != nullptr && A.bn->elig[i]) ? A.bn->uw[i] : -1.0;
     fast_tabs_load(&ftab, threadIdx.x, kCompThreads);
   }
   __syncthreads();
@@ -677,7 +683,7 @@ __global__ void __launch_bounds__(kCompThreads, STAGE == CSTAGE_FINAL ? SCLANE_C
   const long long t_start = clock64();
   CompDevExec ex{&W, &Ls, &cg, &gs, A.D, A.pn, A.pu, pbs, A.s1 + (size_t)g * (size_t)A.Dpad, A.q + (size_t)g * (size_t)A.Dpad,
                  A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, scw, &ftab, nullptr, tn, ctab};
-  if (A.bn != nullptr) { ex.bn = A.bn; ex.bs = A.bn_s + (size_t)g * (size_t)(NBMAX * kOffJ); ex.bq = A.bn_q + (size_t)g * (size_t)(NBMAX * kOffJ); }
+  if (A.bn != nullptr) { ex.bn = A.bn; ex.bnuw = bnuw_s; ex.bs = A.bn_s + (size_t)g * (size_t)(NBMAX * kOffJ); ex.bq = A.bn_q + (size_t)g * (size_t)(NBMAX * kOffJ); }
   if (STAGE == CSTAGE_FORWARD) {
     for (int it = 0; it < A.n_iter; ++it) {
       gene_forward_fit(ex, Ls, gs, st, W);

@@ -71,6 +71,7 @@ struct WgExec {
   const BucketNodes* bn = nullptr;
   const double* __restrict__ bs = nullptr;
   const double* __restrict__ bq = nullptr;
+  const double* bnuw = nullptr;     // [NBMAX] shared-memory copy of bn->uw (-1 = bucket without nodes)
 
   __device__ __forceinline__ bool leader() const { return (threadIdx.x & 31) == 0; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
@@ -170,7 +171,7 @@ struct WgExec {
       for (int b = 0; b <= T; ++b) {
         const double c = W->c[b];
         if (c == 0.0) continue;                      // warp-uniform
-        if (bn != nullptr && bn->elig[b] && fabs(c) * bn->uw[b] <= kThBinWidth) {
+        if (bnuw != nullptr && bnuw[b] > 0.0 && fabs(c) * bnuw[b] <= kThBinWidth) {
           if (pend < 0) { pend = b; continue; }
           node_pair(pend, b);
           pend = -1;
@@ -215,8 +216,10 @@ __global__ void __launch_bounds__(kWgThreads, SCLANE_WG_MINB) k_wg_stage(WgArgs 
   __shared__ FastTabs ftab;
   __shared__ int pbs[NBMAX + 1];
   __shared__ WgGeneShared wg[kWgWarps];
+  __shared__ double bnuw_s[NBMAX];
   const CompArgs& A = WA.C;
   {
+    for (int i = threadIdx.x; i < NBMAX; i += kWgThreads) bnuw_s[i] = (A.bn != nullptr && A.bn->elig[i]) ? A.bn->uw[i] : -1.0;
     const int* src = reinterpret_cast<const int*>(A.lineage);
     int* dst = reinterpret_cast<int*>(&Ls);
     for (int i = threadIdx.x; i < (int)(sizeof(Lineage) / sizeof(int)); i += kWgThreads) dst[i] = src[i];
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kWgThreads, SCLANE_WG_MINB) k_wg_stage(WgArgs 
               A.tail + (size_t)g * (size_t)kHistCap, A.big + (size_t)g * (size_t)kBigCap, &ftab,
               offmode ? WA.on : nullptr, offmode ? WA.off_s + (size_t)g * (size_t)(kOffKMax * kOffJ) : nullptr,
               offmode ? WA.off_q + (size_t)g * (size_t)(kOffKMax * kOffJ) : nullptr, offmode ? WA.offg + g : nullptr};
-    if (!offmode && A.bn != nullptr) { ex.bn = A.bn; ex.bs = A.bn_s + (size_t)g * (size_t)(NBMAX * kOffJ); ex.bq = A.bn_q + (size_t)g * (size_t)(NBMAX * kOffJ); }
+    if (!offmode && A.bn != nullptr) { ex.bn = A.bn; ex.bnuw = bnuw_s; ex.bs = A.bn_s + (size_t)g * (size_t)(NBMAX * kOffJ); ex.bq = A.bn_q + (size_t)g * (size_t)(NBMAX * kOffJ); }
     if (STAGE == WG_FORWARD) {
       for (int it = 0; it < A.n_iter; ++it) {
         gene_forward_fit(ex, Ls, gs, st, W);
