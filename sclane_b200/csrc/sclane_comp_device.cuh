@@ -521,7 +521,6 @@ struct CompDevExec {
     double sc[NSC];
 #pragma unroll
     for (int k = 0; k < NSC; ++k) sc[k] = 0.0;
-    int n_sloped = 0;                               // running index among the non-flat buckets (warp-uniform)
     const bool on_nodes = MODE == PASS_THETA && tn != nullptr && tn->on;     // block-uniform
     if (on_nodes) {
       const int ne = tn->n;
@@ -536,7 +535,6 @@ struct CompDevExec {
     //   the rest         (slope too steep for the nodes in this pass, few points, exact-knot mode) walks its points, warp per bucket.
     // Every sum still runs in a fixed order -> bit-reproducible.
     const int half = lane >> 4, hl = lane & 15;
-    int n_flat = 0, n_node = 0, my_flat = -1, pend_b = -1;
     auto node_pair = [&](int b0, int b1) {           // warp-uniform call; b1 may be -1
       const int mb = half ? b1 : b0;
       double acc[NACC];
@@ -553,26 +551,34 @@ struct CompDevExec {
         if (hl == 0 && mb >= 0) W->acc[mb][k] = t;
       }
     };
+    // The buckets are classified in parallel (lane l looks at buckets l and l + 32; a scalar loop over the <= 33 buckets in every
+    // warp was half of the final stage's stall samples) and handed out by rank among their class: flat bucket number f to lane
+    // f / kCompWarps of warp f % kCompWarps, node buckets 2p and 2p + 1 to warp p % kCompWarps, walked bucket number s to warp
+    // s % kCompWarps.
+    unsigned long long flat_m = 0ull, node_m = 0ull, walk_m = 0ull;
+    if (!on_nodes) {
+      int cls0 = 0, cls1 = 0;                        // 1 flat, 2 on its nodes, 3 walks its points
+      if (lane <= T) { const double c = W->c[lane]; cls0 = c == 0.0 ? 1 : (on_bucket_nodes(lane, c) ? 2 : 3); }
+      if (lane + 32 <= T) { const double c = W->c[lane + 32]; cls1 = c == 0.0 ? 1 : (on_bucket_nodes(lane + 32, c) ? 2 : 3); }
+      flat_m = (unsigned long long)__ballot_sync(0xffffffffu, cls0 == 1) | ((unsigned long long)__ballot_sync(0xffffffffu, cls1 == 1) << 32);
+      node_m = (unsigned long long)__ballot_sync(0xffffffffu, cls0 == 2) | ((unsigned long long)__ballot_sync(0xffffffffu, cls1 == 2) << 32);
+      walk_m = (unsigned long long)__ballot_sync(0xffffffffu, cls0 == 3) | ((unsigned long long)__ballot_sync(0xffffffffu, cls1 == 3) << 32);
+    }
+    auto nth = [](unsigned long long m, int n) -> int {    // position of the n-th (0-based) set bit of m, -1 when there is none
+      const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+      const int nlo = __popc(lo);
+      if (n < nlo) return (int)__fns(lo, 0, n + 1);
+      n -= nlo;
+      if (n < __popc(hi)) return 32 + (int)__fns(hi, 0, n + 1);
+      return -1;
+    };
+    const int n_node = __popcll(node_m), n_walk = __popcll(walk_m);
 #pragma unroll 1
-    for (int b = 0; b <= (on_nodes ? -1 : T); ++b) {
-      const double c = W->c[b];
-      if (c == 0.0) {
-        const int f = n_flat++;
-        if ((f & (kCompWarps - 1)) == warp && (f / kCompWarps) == lane) my_flat = b;
-        continue;
-      }
-      if (on_bucket_nodes(b, c)) {
-        const int h = n_node++;
-        if (((h >> 1) & (kCompWarps - 1)) != warp) continue;
-        if ((h & 1) == 0) { pend_b = b; continue; }
-        node_pair(pend_b, b);
-        pend_b = -1;
-        continue;
-      }
-      const int owner = n_sloped & (kCompWarps - 1);
-      ++n_sloped;
-      if (owner != warp) continue;
-      const double a = W->a[b];
+    for (int pr = warp; 2 * pr < n_node; pr += kCompWarps) node_pair(nth(node_m, 2 * pr), nth(node_m, 2 * pr + 1));
+#pragma unroll 1
+    for (int sidx = warp; sidx < n_walk; sidx += kCompWarps) {
+      const int b = nth(walk_m, sidx);
+      const double a = W->a[b], c = W->c[b];
       double acc[NACC];
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
@@ -593,7 +599,7 @@ struct CompDevExec {
         if (lane == 0) W->acc[b][k] = t;
       }
     }
-    if (pend_b >= 0) node_pair(pend_b, -1);          // warp-uniform: pend_b is
+    const int my_flat = nth(flat_m, lane * kCompWarps + warp);
     if (my_flat >= 0) {
       double fa[NACC];
 #pragma unroll
