@@ -539,13 +539,13 @@ SC_HDN void nb_mle_step(const Model& m, Work& W, double smin, double smax) {
   double Lm[NSYS * NSYS];
   bool ok = false;
   if (s_moves) {
-    _Pragma("unroll 1") for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+    copy_lower<NSYS>(p + 1, W.H, Lm);
     ok = chol_factor<NSYS>(p + 1, Lm);
     if (ok) chol_solve<NSYS>(p + 1, Lm, W.grad, W.step);
   }
   if (!ok) {
     // beta block alone (always used when s is fixed); safeguarded 1-D Newton on s otherwise
-    _Pragma("unroll 1") for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+    copy_lower<NSYS>(p, W.H, Lm);
     const bool okb = chol_factor<NSYS>(p, Lm);
     if (okb) chol_solve<NSYS>(p, Lm, W.grad, W.step);
     else { _Pragma("unroll 1") for (int j = 0; j < p; ++j) W.step[j] = 0.0; W.flag = 1; }   // singular information: stop here
@@ -644,7 +644,7 @@ SC_HDN void wald_from_fit(const Model& m, Work& W, bool poisson, double* out) {
   const int p = m.n;
   const int n = poisson ? p : p + 1;      // W.H / W.grad still hold the system of the last pass
   double Lm[NSYS * NSYS];
-  for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+  copy_lower<NSYS>(n, W.H, Lm);
   if (!chol_factor<NSYS>(n, Lm)) {
     for (int j = 1; j < p; ++j) out[j - 1] = nan("");
     return;
@@ -679,7 +679,7 @@ SC_HDN bool sweep_invert(const Model& m, Work& W) {
   const int p = m.n;
   if (p == 1) { W.cov[0] = 1.0 / W.H[0]; return true; }      // stat_out_score_glm_null.R:33-34
   double Lm[NSYS * NSYS];
-  for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+  copy_lower<NSYS>(p, W.H, Lm);
   if (!chol_factor<NSYS>(p, Lm)) return false;
   chol_inverse<NSYS>(p, Lm, W.cov);
   return true;
@@ -858,7 +858,7 @@ struct StatOutFn {
 SC_HDN double stat_out_gcvq1(const Lineage& L, const Model& m, const Work& W, const GeneStats& gs) {
   const int p = m.n;
   double Lm[NSYS * NSYS], coef[NSYS];
-  for (int i = 0; i < NSYS * NSYS; ++i) Lm[i] = W.H[i];
+  copy_lower<NSYS>(p, W.H, Lm);
   if (!chol_factor<NSYS>(p, Lm)) return nan("");
   chol_solve<NSYS>(p, Lm, W.grad, coef);
   double fit2 = 0.0;

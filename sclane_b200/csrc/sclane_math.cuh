@@ -126,6 +126,16 @@ SC_HD double nb_lambda(int y, double sigma, double th) {
   return nb_lambda_big(y, sigma, th);
 }
 
+// lower triangle of the leading n x n block (all that chol_factor / chol_solve / chol_inverse read): n (n + 1) / 2 moves instead of NS^2
+template <int NS>
+SC_HD void copy_lower(int n, const double* src, double* dst) {
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+#pragma unroll 1
+    for (int j = 0; j <= i; ++j) dst[i * NS + j] = src[i * NS + j];
+  }
+}
+
 // ---- tiny dense symmetric algebra, n <= NS, row-major a[NS*NS].
 // Cholesky A = L L^T in place (lower); returns false on a non-positive pivot.
 template <int NS>
